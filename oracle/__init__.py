@@ -1,0 +1,266 @@
+"""ctypes front-end of the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  The product (``diffrax_b200``)
+never does - it fails loudly when its CUDA library is missing instead of falling
+back to anything here.
+
+Parity status: "parity unpinned" against a live Diffrax (jax is not importable in
+the authoring container, and the reference ships no golden vectors for this path);
+pinned to the reference's own offline anchors in ``tests/test_oracle_*.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+F64, F32 = 0, 1
+SOLVERS = {"tsit5": 0, "dopri5": 1, "dopri8": 2, "heun": 3, "bosh3": 4, "midpoint": 5,
+           "ralston": 6, "euler": 7, "shark": 8}
+FIELDS = {"decay": 0, "lotka_volterra": 1, "lorenz": 2, "cr3bp": 3, "mlp": 4, "ou": 5,
+          "forced_osc": 6, "vdp": 7, "callback": 100}
+LEVY = {None: 0, "none": 0, "bi": 1, "brownian_increment": 1, "stla": 2, "space_time": 2}
+CTRL_CONSTANT, CTRL_PID = 0, 1
+
+CALLBACK = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("field_id", C.c_int32), ("dim", C.c_int32), ("dtype", C.c_int32), ("solver_id", C.c_int32),
+        ("field_params", C.c_void_p), ("n_field_params", C.c_int32),
+        ("callback", CALLBACK),
+        ("n_traj", C.c_int64),
+        ("y0", C.c_void_p),
+        ("t0", C.c_double), ("t1", C.c_double),
+        ("t0_per_traj", C.c_void_p), ("t1_per_traj", C.c_void_p),
+        ("dt0", C.c_double),
+        ("controller", C.c_int32),
+        ("rtol", C.c_double), ("atol", C.c_double), ("pcoeff", C.c_double), ("icoeff", C.c_double),
+        ("dcoeff", C.c_double), ("safety", C.c_double), ("factormin", C.c_double), ("factormax", C.c_double),
+        ("dtmin", C.c_double), ("dtmax", C.c_double),
+        ("force_dtmin", C.c_int32),
+        ("error_order", C.c_double),
+        ("hairer_initial_step", C.c_int32),
+        ("save_t0", C.c_int32), ("save_t1", C.c_int32), ("save_steps", C.c_int32), ("save_dense", C.c_int32),
+        ("save_ts", C.c_void_p), ("n_save_ts", C.c_int32), ("max_steps", C.c_int32),
+        ("out_size", C.c_int32),
+        ("ts_out", C.c_void_p), ("ys_out", C.c_void_p), ("stats", C.c_void_p), ("result", C.c_void_p),
+        ("dense_ts", C.c_void_p), ("dense_y0", C.c_void_p), ("dense_y1", C.c_void_p), ("dense_k", C.c_void_p),
+        ("dense_count", C.c_void_p), ("y_final", C.c_void_p), ("t_final", C.c_void_p),
+        ("levy_area", C.c_int32), ("bm_keys", C.c_void_p),
+        ("bm_t0", C.c_double), ("bm_t1", C.c_double), ("bm_tol", C.c_double),
+        ("threefry_partitionable", C.c_int32),
+        ("trace_traj", C.c_int64), ("trace", C.c_void_p),
+        ("num_threads", C.c_int32),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (gcc only)."""
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_core.inc", "oracle.h", "oracle_tableaux.h")]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-s", "-B", "liboracle.so"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_solve.argtypes = [C.POINTER(Desc)]
+        L.orc_solve.restype = C.c_int
+        L.orc_out_size.argtypes = [C.POINTER(Desc)]
+        L.orc_out_size.restype = C.c_int
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_num_stages.argtypes = [C.c_int]
+        L.orc_num_stages.restype = C.c_int
+        L.orc_hw_threads.restype = C.c_int
+        L.orc_threefry2x32.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)] * 2
+        L.orc_split.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+        L.orc_normal_f64.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_normal_f64.restype = C.c_double
+        L.orc_normal_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_normal_f32.restype = C.c_float
+        L.orc_erfinv_f64.argtypes = [C.c_double]
+        L.orc_erfinv_f64.restype = C.c_double
+        L.orc_erfinv_f32.argtypes = [C.c_float]
+        L.orc_erfinv_f32.restype = C.c_float
+        L.orc_vbt_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_double,
+                                       C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_vbt_evaluate.restype = C.c_int
+        L.orc_dense_evaluate.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
+                                         C.c_void_p]
+        L.orc_dense_evaluate.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def hw_threads() -> int:
+    return lib().orc_hw_threads()
+
+
+def threefry2x32(k0, k1, x0, x1):
+    a, b = C.c_uint32(), C.c_uint32()
+    lib().orc_threefry2x32(k0, k1, x0, x1, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def split(key, num, partitionable=True):
+    out = np.zeros((num, 2), np.uint32)
+    lib().orc_split(int(key[0]), int(key[1]), num, int(partitionable), out.ctypes.data)
+    return out
+
+
+def prng_key(seed: int):
+    """jax.random.key(seed) / PRNGKey(seed): words (hi32, lo32)."""
+    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], np.uint32)
+
+
+def normal(key, dtype=np.float64, partitionable=True):
+    if np.dtype(dtype) == np.float64:
+        return lib().orc_normal_f64(int(key[0]), int(key[1]), int(partitionable))
+    return np.float32(lib().orc_normal_f32(int(key[0]), int(key[1]), int(partitionable)))
+
+
+def erfinv(x, dtype=np.float64):
+    if np.dtype(dtype) == np.float64:
+        return lib().orc_erfinv_f64(float(x))
+    return np.float32(lib().orc_erfinv_f32(float(x)))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.float64,
+          controller="pid", rtol=1e-3, atol=1e-6, pcoeff=0.0, icoeff=1.0, dcoeff=0.0, safety=0.9,
+          factormin=0.2, factormax=10.0, dtmin=None, dtmax=None, force_dtmin=True, error_order=None,
+          hairer_initial_step=False, save_t0=False, save_t1=True, save_ts=None, save_steps=0,
+          save_dense=False, max_steps=4096, levy_area=None, keys=None, bm_t0=0.0, bm_t1=1.0,
+          bm_tol=1e-3, partitionable=True, callback=None, trace_traj=None, num_threads=0,
+          t0_per_traj=None, t1_per_traj=None):
+    """Run the oracle on a batch.  Mirrors one vmapped diffeqsolve call of the reference."""
+    L = lib()
+    dt = np.dtype(dtype)
+    y0 = np.ascontiguousarray(y0, dt)
+    if y0.ndim == 1:
+        y0 = y0[:, None]
+    n, d = y0.shape
+    D = Desc()
+    D.field_id = FIELDS[field] if isinstance(field, str) else int(field)
+    D.dim, D.dtype, D.solver_id = d, (F64 if dt == np.float64 else F32), SOLVERS[solver]
+    p = np.ascontiguousarray(params, np.float64).ravel()
+    D.field_params, D.n_field_params = _ptr(p), p.size
+    cb = None
+    if callback is not None:
+        def _cb(t, yp, op, dim):
+            yv = np.array([yp[i] for i in range(dim)])
+            o = callback(t, yv)
+            for i in range(dim):
+                op[i] = float(o[i])
+        cb = CALLBACK(_cb)
+        D.callback = cb
+        D.field_id = FIELDS["callback"]
+        num_threads = 1
+    D.n_traj, D.y0 = n, _ptr(y0)
+    D.t0, D.t1 = float(t0), float(t1)
+    t0a = None if t0_per_traj is None else np.ascontiguousarray(t0_per_traj, dt)
+    t1a = None if t1_per_traj is None else np.ascontiguousarray(t1_per_traj, dt)
+    D.t0_per_traj, D.t1_per_traj = _ptr(t0a), _ptr(t1a)
+    D.dt0 = math.nan if dt0 is None else float(dt0)
+    D.controller = CTRL_PID if controller == "pid" else CTRL_CONSTANT
+    D.rtol, D.atol, D.pcoeff, D.icoeff, D.dcoeff = rtol, atol, pcoeff, icoeff, dcoeff
+    D.safety, D.factormin, D.factormax = safety, factormin, factormax
+    D.dtmin = math.nan if dtmin is None else dtmin
+    D.dtmax = math.nan if dtmax is None else dtmax
+    D.force_dtmin = int(force_dtmin)
+    D.error_order = math.nan if error_order is None else float(error_order)
+    D.hairer_initial_step = int(hairer_initial_step)
+    D.save_t0, D.save_t1, D.save_steps, D.save_dense = int(save_t0), int(save_t1), int(save_steps), int(save_dense)
+    tsa = None if save_ts is None else np.ascontiguousarray(save_ts, dt)
+    D.save_ts, D.n_save_ts, D.max_steps = _ptr(tsa), (0 if tsa is None else tsa.size), int(max_steps)
+    T = L.orc_out_size(C.byref(D))
+    D.out_size = T
+    ts_out = np.empty((n, T), dt)
+    ys_out = np.empty((n, T, d), dt)
+    stats = np.zeros((n, 3), np.int32)
+    result = np.zeros(n, np.int32)
+    y_final = np.empty((n, d), dt)
+    t_final = np.empty(n, dt)
+    D.ts_out, D.ys_out, D.stats, D.result = _ptr(ts_out), _ptr(ys_out), _ptr(stats), _ptr(result)
+    D.y_final, D.t_final = _ptr(y_final), _ptr(t_final)
+    s = L.orc_num_stages(D.solver_id)
+    dense = None
+    if save_dense:
+        dts = np.empty((n, max_steps + 1), dt)
+        dy0 = np.empty((n, max_steps, d), dt)
+        dy1 = np.empty((n, max_steps, d), dt)
+        dk = np.empty((n, max_steps, s, d), dt) if solver not in ("euler", "shark") else None
+        dcount = np.zeros(n, np.int32)
+        D.dense_ts, D.dense_y0, D.dense_y1, D.dense_k, D.dense_count = _ptr(dts), _ptr(dy0), _ptr(dy1), _ptr(dk), _ptr(dcount)
+        dense = dict(ts=dts, y0=dy0, y1=dy1, k=dk, count=dcount)
+    D.levy_area = LEVY[levy_area]
+    ka = None
+    if keys is not None:
+        ka = np.ascontiguousarray(keys, np.uint32).reshape(n, 2)
+    D.bm_keys = _ptr(ka)
+    D.bm_t0, D.bm_t1, D.bm_tol = float(bm_t0), float(bm_t1), float(bm_tol)
+    D.threefry_partitionable = int(partitionable)
+    trace = None
+    if trace_traj is not None:
+        trace = np.full((max_steps, 3), np.nan)
+        D.trace_traj, D.trace = int(trace_traj), _ptr(trace)
+    D.num_threads = int(num_threads)
+    rc = L.orc_solve(C.byref(D))
+    if rc != 0:
+        raise ValueError(L.orc_last_error().decode())
+    out = dict(ts=ts_out, ys=ys_out, stats=stats, result=result, y_final=y_final, t_final=t_final)
+    if dense is not None:
+        out["dense"] = dense
+    if trace is not None:
+        out["trace"] = trace[: stats[trace_traj, 0]]
+    return out
+
+
+def vbt_evaluate(keys, ta, tb, *, bm_t0=0.0, bm_t1=1.0, tol=1e-3, levy_area="bi", dtype=np.float64,
+                 partitionable=True):
+    dt = np.dtype(dtype)
+    keys = np.ascontiguousarray(keys, np.uint32).reshape(-1, 2)
+    n = keys.shape[0]
+    ta_a = np.ascontiguousarray(np.broadcast_to(np.asarray(ta, dt), (n,)))
+    tb_a = np.ascontiguousarray(np.broadcast_to(np.asarray(tb, dt), (n,)))
+    W = np.empty(n, dt)
+    H = np.empty(n, dt)
+    lib().orc_vbt_evaluate(F64 if dt == np.float64 else F32, LEVY[levy_area], int(partitionable), n,
+                           keys.ctypes.data, bm_t0, bm_t1, tol, ta_a.ctypes.data, tb_a.ctypes.data, 1,
+                           W.ctypes.data, H.ctypes.data)
+    return W, H
+
+
+def dense_evaluate(solver, dense, tq, direction=1.0):
+    dts = dense["ts"]
+    dt = dts.dtype
+    n, msp1 = dts.shape
+    d = dense["y0"].shape[-1]
+    tq = np.ascontiguousarray(tq, dt).reshape(n, -1)
+    nq = tq.shape[1]
+    out = np.empty((n, nq, d), dt)
+    lib().orc_dense_evaluate(F64 if dt == np.float64 else F32, SOLVERS[solver], n, d, msp1 - 1, _ptr(dts),
+                             _ptr(dense["y0"]), _ptr(dense["y1"]), _ptr(dense["k"]), _ptr(dense["count"]),
+                             float(direction), _ptr(tq), nq, _ptr(out))
+    return out

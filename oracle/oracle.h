@@ -1,0 +1,125 @@
+/* oracle.h - CPU restatement of Diffrax's ensemble hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may call into this library; the product (diffrax_b200/) never does.
+ *
+ * PARITY STATUS: "parity unpinned" at the north-star tolerances against a live
+ * Diffrax: jax / equinox / optimistix are not importable in the authoring container
+ *  and the reference ships no golden vectors for this path (§8c).
+ * The oracle is pinned instead against every offline anchor the reference's tests
+ * use: the Random123 threefry2x32 known-answer vectors, analytic solutions
+ * (test_integrate.py:48-141, test_saveat_solution.py:29-195), scipy DOP853 on the
+ * DETEST problems (test_detest.py:390-469), Butcher order conditions
+ * (runge_kutta.py:126-130) and the statistical Brownian tests (test_brownian.py).
+ *
+ * Every function cites the reference file:line (under /root/reference/diffrax) it restates.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_DIM 8
+#define ORC_MAX_STAGES 14
+
+/* dtype */
+enum { ORC_F64 = 0, ORC_F32 = 1 };
+/* solver ids (same numbering as tools/gen_tableaux.py) */
+enum { ORC_TSIT5 = 0, ORC_DOPRI5 = 1, ORC_DOPRI8 = 2, ORC_HEUN = 3, ORC_BOSH3 = 4,
+       ORC_MIDPOINT = 5, ORC_RALSTON = 6, ORC_EULER = 7, ORC_SHARK = 8 };
+/* controller */
+enum { ORC_CTRL_CONSTANT = 0, ORC_CTRL_PID = 1 };
+/* vector fields */
+enum { ORC_FIELD_DECAY = 0, ORC_FIELD_LOTKA_VOLTERRA = 1, ORC_FIELD_LORENZ = 2,
+       ORC_FIELD_CR3BP = 3, ORC_FIELD_MLP = 4, ORC_FIELD_OU = 5, ORC_FIELD_FORCED_OSC = 6,
+       ORC_FIELD_VDP = 7, ORC_FIELD_CALLBACK = 100 };
+/* Brownian levy_area kind */
+enum { ORC_LEVY_NONE = 0, ORC_LEVY_BROWNIAN_INCREMENT = 1, ORC_LEVY_SPACE_TIME = 2 };
+/* RESULTS (_solution.py:13-31; only successful == 0 is pinned by the reference tests) */
+enum { ORC_OK = 0, ORC_MAX_STEPS_REACHED = 1, ORC_DT_MIN_REACHED = 2 };
+
+/* generic user vector field (ctypes callback): out[d] = f(t, y[d]) in double */
+typedef void (*orc_callback_vf)(double t, const double *y, double *out, int dim);
+
+typedef struct orc_desc {
+  /* problem */
+  int32_t field_id, dim, dtype, solver_id;
+  const double *field_params; /* host doubles, meaning depends on field */
+  int32_t n_field_params;
+  orc_callback_vf callback;   /* ORC_FIELD_CALLBACK only (fp64 only) */
+  /* batch + time */
+  int64_t n_traj;
+  const void *y0;            /* [N, d] REAL */
+  double t0, t1;             /* used when the per-trajectory arrays are NULL */
+  const void *t0_per_traj;   /* [N] REAL or NULL */
+  const void *t1_per_traj;   /* [N] REAL or NULL */
+  double dt0;                /* NaN => None */
+  /* controller (pid.py:299-311) */
+  int32_t controller;
+  double rtol, atol, pcoeff, icoeff, dcoeff, safety, factormin, factormax;
+  double dtmin, dtmax;       /* NaN => None */
+  int32_t force_dtmin;
+  double error_order;        /* NaN => solver.error_order(terms) */
+  int32_t hairer_initial_step; /* 0 => dt0=None means 0.01; 1 => pid.py:51-81 */
+  /* SaveAt (_saveat.py:22-26,72-76) */
+  int32_t save_t0, save_t1, save_steps, save_dense;
+  const void *save_ts;       /* [T] REAL or NULL */
+  int32_t n_save_ts;
+  int32_t max_steps;
+  /* outputs (caller-allocated, host) */
+  int32_t out_size;          /* T_out, see orc_out_size */
+  void *ts_out;              /* [N, T_out] */
+  void *ys_out;              /* [N, T_out, d] */
+  int32_t *stats;            /* [N, 3]: num_steps, accepted, rejected */
+  int32_t *result;           /* [N] */
+  void *dense_ts;            /* [N, max_steps+1] */
+  void *dense_y0, *dense_y1; /* [N, max_steps, d] */
+  void *dense_k;             /* [N, max_steps, s, d] (absent for 2-point interpolants) */
+  int32_t *dense_count;      /* [N] number of accepted steps stored */
+  void *y_final;             /* [N, d] optional */
+  void *t_final;             /* [N] optional */
+  /* Brownian motion (tree.py:245-301) */
+  int32_t levy_area;
+  const uint32_t *bm_keys;   /* [N, 2] user keys (before split_by_tree) */
+  double bm_t0, bm_t1, bm_tol;
+  int32_t threefry_partitionable;
+  /* test hook: per-step trace of (tprev, tnext, keep) for trajectory `trace_traj` */
+  int64_t trace_traj;
+  double *trace;             /* [max_steps, 3] or NULL */
+  int32_t num_threads;       /* worker threads, 0 => all online cores */
+} orc_desc;
+
+int orc_out_size(const orc_desc *d);           /* _integrate.py:1273-1293 */
+int orc_solve(const orc_desc *d);              /* 0 ok; <0 argument error */
+const char *orc_last_error(void);
+int orc_num_stages(int solver_id);
+int orc_hw_threads(void);
+
+/* PRNG (jax/_src/prng.py) */
+void orc_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t *o0, uint32_t *o1);
+void orc_split(uint32_t k0, uint32_t k1, int num, int partitionable, uint32_t *out /* [num,2] */);
+double orc_normal_f64(uint32_t k0, uint32_t k1, int partitionable);
+float orc_normal_f32(uint32_t k0, uint32_t k1, int partitionable);
+double orc_erfinv_f64(double x);
+float orc_erfinv_f32(float x);
+
+/* VirtualBrownianTree.evaluate(t0, t1, use_levy=True) for n independent scalar trees
+ * (tree.py:326-354).  keys: [n,2] user keys; outputs W[n], H[n] (H may be NULL). */
+int orc_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, const uint32_t *keys,
+                     double bm_t0, double bm_t1, double bm_tol, const void *ta, const void *tb,
+                     int per_traj_times, void *W, void *H);
+
+/* DenseInterpolation.evaluate (_global_interpolation.py:335-355) for one batch of queries:
+ * each trajectory i evaluates at tq[i*nq + q]. out: [N, nq, d] */
+int orc_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps,
+                       const void *dense_ts, const void *dense_y0, const void *dense_y1,
+                       const void *dense_k, const int32_t *dense_count, double direction,
+                       const void *tq, int nq, void *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
