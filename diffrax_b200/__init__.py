@@ -1,0 +1,18 @@
+"""diffrax_b200 - B200-native ensemble integrator behind Diffrax's diffeqsolve interface.
+
+Scope: ``diffeqsolve`` over a batch of independent trajectories with explicit
+Runge-Kutta solvers, PIDController / ConstantStepSize, SaveAt (t0/t1/ts/steps/dense) and
+VirtualBrownianTree-driven Heun / ShARK / Euler SDE solves.  All numerics run in hand-written
+sm_100a CUDA kernels (csrc/) behind the C ABI of include/diffrax_b200.h.
+"""
+from . import fields, random
+from ._api import (RESULTS, Bosh3, BrownianIncrement, ConstantStepSize, ControlTerm, DenseInterpolation,
+                   Dopri5, Dopri8, Euler, Heun, Midpoint, MultiTerm, ODETerm, PIDController, Ralston, SaveAt,
+                   ShARK, Solution, SpaceTimeLevyArea, Tsit5, VirtualBrownianTree, diffeqsolve, is_successful)
+
+__all__ = [
+    "RESULTS", "Bosh3", "BrownianIncrement", "ConstantStepSize", "ControlTerm", "DenseInterpolation", "Dopri5",
+    "Dopri8", "Euler", "Heun", "Midpoint", "MultiTerm", "ODETerm", "PIDController", "Ralston", "SaveAt", "ShARK",
+    "Solution", "SpaceTimeLevyArea", "Tsit5", "VirtualBrownianTree", "diffeqsolve", "is_successful", "fields",
+    "random",
+]

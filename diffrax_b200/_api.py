@@ -1,0 +1,589 @@
+"""Host-side mirror of the reference's public interface for the ensemble hot path.
+
+Same names, argument meaning and error behaviour as diffrax (file:line citations are into
+/root/reference/diffrax):
+
+    diffeqsolve            _integrate.py:888-1543
+    ODETerm / ControlTerm / MultiTerm      _term.py:174-226, 271-555, 666-731
+    SaveAt                 _saveat.py:65-105
+    PIDController          _step_size_controller/pid.py:299-567
+    ConstantStepSize       _step_size_controller/constant.py:20-104
+    Tsit5 / Dopri5 / Dopri8 / Heun / Bosh3 / Midpoint / Ralston / Euler / ShARK   _solver/*.py
+    VirtualBrownianTree    _brownian/tree.py:177-301
+    Solution / RESULTS     _solution.py:13-31, 82-201
+    DenseInterpolation     _global_interpolation.py:315-397
+
+The one structural difference: the reference is called under ``jax.vmap`` over ``y0`` (and
+keys); here the batch is explicit - ``y0`` has shape ``[N, d]`` and every output carries the
+leading ``N`` axis that ``jax.vmap`` would have produced (test/test_vmap.py:27-125).
+``ODETerm(vector_field)`` takes a *registered device functor* (``diffrax_b200.fields``)
+instead of a traced Python callable.
+
+PyTorch is only the device-memory / stream plumbing; all arithmetic happens in
+libdiffrax_b200.so (hand-written sm_100a kernels) behind the C ABI in include/diffrax_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from typing import Any, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from .fields import Field, FieldPart
+
+try:  # torch is plumbing: device memory + streams
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+# --------------------------------------------------------------------------------------
+# RESULTS / Solution
+# --------------------------------------------------------------------------------------
+class RESULTS:
+    """_solution.py:13-31.  ``successful`` is 0 (test/test_saveat_solution.py:21)."""
+    successful = 0
+    max_steps_reached = 1
+    dt_min_reached = 2
+    _messages = {
+        0: "",
+        1: "The maximum number of solver steps was reached. Try increasing `max_steps`.",
+        2: "The minimum step size was reached in the differential equation solver.",
+    }
+
+
+def is_successful(result):
+    return result == RESULTS.successful
+
+
+@dataclasses.dataclass
+class Solution:
+    """_solution.py:82-201 (fields the forward ensemble path fills)."""
+    t0: Any
+    t1: Any
+    ts: Any
+    ys: Any
+    interpolation: Optional["DenseInterpolation"]
+    stats: dict
+    result: Any
+    y_final: Any = None
+    t_final: Any = None
+
+    def evaluate(self, t0, t1=None, left=True):
+        if self.interpolation is None:
+            raise ValueError("Dense solution has not been saved; pass SaveAt(dense=True).")  # _solution.py:146-150
+        return self.interpolation.evaluate(t0, t1, left)
+
+
+# --------------------------------------------------------------------------------------
+# terms
+# --------------------------------------------------------------------------------------
+class ODETerm:
+    """_term.py:174-226: ``ODETerm(vector_field)``; vector_field is a registered functor."""
+
+    def __init__(self, vector_field: Union[Field, FieldPart]):
+        if isinstance(vector_field, Field):
+            vector_field = vector_field.drift
+        if not isinstance(vector_field, FieldPart) or vector_field.part != "drift":
+            raise TypeError("ODETerm(vector_field): vector_field must be a registered device functor "
+                            "from diffrax_b200.fields (or its `.drift`)")
+        self.vector_field = vector_field
+
+
+class ControlTerm:
+    """_term.py:271-555: ``ControlTerm(vector_field, control)`` with a VirtualBrownianTree control."""
+
+    def __init__(self, vector_field: FieldPart, control: "VirtualBrownianTree"):
+        if not isinstance(vector_field, FieldPart) or vector_field.part != "diffusion":
+            raise TypeError("ControlTerm(vector_field, control): vector_field must be `<sde functor>.diffusion`")
+        if not isinstance(control, VirtualBrownianTree):
+            raise TypeError("ControlTerm control must be a diffrax_b200.VirtualBrownianTree")
+        self.vector_field = vector_field
+        self.control = control
+
+
+class MultiTerm:
+    """_term.py:666-731."""
+
+    def __init__(self, *terms):
+        self.terms = tuple(terms)
+
+
+# --------------------------------------------------------------------------------------
+# solvers (tableaux live in csrc/tableaux.cuh)
+# --------------------------------------------------------------------------------------
+class _Solver:
+    name = ""
+    _order = 0
+    _strong_order = None
+
+    def order(self, terms=None):
+        return self._order
+
+    def strong_order(self, terms=None):
+        return self._strong_order
+
+    @property
+    def solver_id(self):
+        return _lib.SOLVER_IDS[self.name]
+
+    def __repr__(self):
+        return f"{type(self).__name__}()"
+
+
+class Tsit5(_Solver):
+    name, _order = "tsit5", 5       # tsit5.py:188
+
+
+class Dopri5(_Solver):
+    name, _order = "dopri5", 5      # dopri5.py:98
+
+
+class Dopri8(_Solver):
+    name, _order = "dopri8", 8      # dopri8.py:347
+
+
+class Heun(_Solver):
+    name, _order, _strong_order = "heun", 2, 0.5   # heun.py:41-45
+
+
+class Bosh3(_Solver):
+    name, _order = "bosh3", 3
+
+
+class Midpoint(_Solver):
+    name, _order = "midpoint", 2
+
+
+class Ralston(_Solver):
+    name, _order = "ralston", 2
+
+
+class Euler(_Solver):
+    name, _order, _strong_order = "euler", 1, 0.5  # euler.py:31-35
+
+
+class ShARK(_Solver):
+    name, _order, _strong_order = "shark", 2, 1.5  # shark.py:57-64
+
+
+# --------------------------------------------------------------------------------------
+# step size controllers
+# --------------------------------------------------------------------------------------
+class ConstantStepSize:
+    """constant.py:20-104."""
+
+
+@dataclasses.dataclass
+class PIDController:
+    """pid.py:299-311 (norm is optimistix.rms_norm, the reference default)."""
+    rtol: float
+    atol: float
+    pcoeff: float = 0
+    icoeff: float = 1
+    dcoeff: float = 0
+    dtmin: Optional[float] = None
+    dtmax: Optional[float] = None
+    force_dtmin: bool = True
+    factormin: float = 0.2
+    factormax: float = 10.0
+    safety: float = 0.9
+    error_order: Optional[float] = None
+
+
+# --------------------------------------------------------------------------------------
+# SaveAt
+# --------------------------------------------------------------------------------------
+class SaveAt:
+    """_saveat.py:65-105 (single SubSaveAt, fn == save_y)."""
+
+    def __init__(self, *, t0: bool = False, t1: bool = False, ts=None, steps: Union[bool, int] = False,
+                 dense: bool = False):
+        self.t0 = bool(t0)
+        self.t1 = bool(t1)
+        self.ts = None if ts is None else ts
+        self.steps = int(steps)  # `steps=True` == every step (_saveat.py:26-27)
+        self.dense = bool(dense)
+        if not (self.t0 or self.t1 or self.ts is not None or self.steps or self.dense):
+            raise ValueError("Empty saveat -- nothing will be saved.")  # _saveat.py:40-48
+
+
+# --------------------------------------------------------------------------------------
+# Brownian motion
+# --------------------------------------------------------------------------------------
+class BrownianIncrement:
+    levy_id = _lib.LEVY_BI
+
+
+class SpaceTimeLevyArea:
+    levy_id = _lib.LEVY_STLA
+
+
+class VirtualBrownianTree:
+    """tree.py:245-301.  ``key`` is an ``[N, 2]`` uint32 array: one tree per trajectory, the
+    pattern ``jax.vmap(lambda k: VirtualBrownianTree(t0, t1, tol, (), k))(jr.split(root, N))`` of
+    test/helpers.py:140-169.  Only ``shape == ()`` (scalar noise) is implemented."""
+
+    def __init__(self, t0, t1, tol, shape, key, levy_area=BrownianIncrement, *, partitionable: bool = True):
+        if not (t0 < t1):
+            raise ValueError("t0 must be strictly less than t1")  # tree.py:281
+        if tuple(shape) != ():
+            raise NotImplementedError("only shape=() Brownian motion is implemented")
+        self.t0, self.t1, self.tol = float(t0), float(t1), float(tol)
+        self.shape = ()
+        self.levy_area = levy_area
+        self.key = key
+        self.partitionable = bool(partitionable)
+
+    def evaluate(self, t0, t1, left=True, use_levy=False):
+        """tree.py:326-354, vmapped over the keys.  Returns W (and H when use_levy)."""
+        keys = _as_keys(self.key)
+        xp = _Backend.of(keys)
+        n = keys.shape[0]
+        dtype = np.float64 if not hasattr(t0, "dtype") else None
+        ta = xp.as_real(t0, n, dtype)
+        tb = xp.as_real(t1, n, ta.dtype if dtype is None else dtype)
+        W = xp.empty((n,), ta.dtype)
+        H = xp.empty((n,), ta.dtype)
+        L = _lib.lib()
+        if xp.device_ptrs:
+            _lib.check(L.dfx_vbt_evaluate(xp.dtype_id(ta.dtype), self.levy_area.levy_id, int(self.partitionable), n,
+                                          xp.ptr(keys), self.t0, self.t1, self.tol, xp.ptr(ta), xp.ptr(tb), 1,
+                                          xp.ptr(W), xp.ptr(H), xp.stream()))
+        else:
+            raise RuntimeError("VirtualBrownianTree.evaluate needs keys on a CUDA device")
+        return (W, H) if use_levy else W
+
+
+def _as_keys(key):
+    if torch is not None and isinstance(key, torch.Tensor):
+        k = key
+        if k.dtype in (torch.int64,):
+            k = k.to(torch.int32)
+        if k.dtype == torch.uint32:
+            k = k.view(torch.int32)
+        return k.reshape(-1, 2).contiguous()
+    return np.ascontiguousarray(key, np.uint32).reshape(-1, 2)
+
+
+# --------------------------------------------------------------------------------------
+# array backends: numpy (host path) and torch (host or device path)
+# --------------------------------------------------------------------------------------
+class _Backend:
+    device_ptrs = False
+
+    @staticmethod
+    def of(x):
+        if torch is not None and isinstance(x, torch.Tensor):
+            return _TorchBackend(x.device)
+        return _NumpyBackend()
+
+
+class _NumpyBackend(_Backend):
+    device_ptrs = False
+
+    def asarray(self, x, dtype):
+        return np.ascontiguousarray(x, dtype)
+
+    def empty(self, shape, dtype):
+        return np.empty(shape, dtype)
+
+    def ptr(self, a):
+        return None if a is None else a.ctypes.data
+
+    def dtype_id(self, dt):
+        return _lib.F64 if np.dtype(dt) == np.float64 else _lib.F32
+
+    def real_dtype(self, a):
+        return a.dtype
+
+    def int32(self):
+        return np.int32
+
+    def as_real(self, x, n, dtype):
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype), (n,)))
+
+    def stream(self):
+        return None
+
+
+class _TorchBackend(_Backend):
+    def __init__(self, device):
+        self.device = device
+        self.device_ptrs = device.type == "cuda"
+
+    def asarray(self, x, dtype):
+        return torch.as_tensor(x, dtype=dtype, device=self.device).contiguous()
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def ptr(self, a):
+        return None if a is None else a.data_ptr()
+
+    def dtype_id(self, dt):
+        return _lib.F64 if dt == torch.float64 else _lib.F32
+
+    def int32(self):
+        return torch.int32
+
+    def as_real(self, x, n, dtype):
+        if dtype is None:
+            dtype = x.dtype
+        elif dtype is np.float64:
+            dtype = torch.float64
+        t = torch.as_tensor(x, dtype=dtype, device=self.device)
+        return t.expand(n).contiguous()
+
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device_ptrs else None
+
+
+# --------------------------------------------------------------------------------------
+# DenseInterpolation
+# --------------------------------------------------------------------------------------
+class DenseInterpolation:
+    """_global_interpolation.py:315-397, batched over trajectories."""
+
+    def __init__(self, solver, ts, ts_size, infos, direction, t0_if_trivial, y0_if_trivial, backend):
+        self.solver = solver
+        self.ts = ts                    # [N, max_steps+1] normalised time
+        self.ts_size = ts_size          # [N] = accepted steps + 1
+        self.infos = infos              # dict(y0, y1, k)
+        self.direction = direction      # [N] or scalar +-1
+        self.t0_if_trivial = t0_if_trivial
+        self.y0_if_trivial = y0_if_trivial
+        self._xp = backend
+
+    def evaluate(self, t0, t1=None, left=True):
+        if t1 is not None:
+            return self.evaluate(t1, left=left) - self.evaluate(t0, left=left)
+        xp = self._xp
+        if not xp.device_ptrs:
+            raise RuntimeError("DenseInterpolation.evaluate needs the dense buffers on a CUDA device")
+        n, msp1 = self.ts.shape
+        d = self.infos["y0"].shape[-1]
+        tq = torch.as_tensor(t0, dtype=self.ts.dtype, device=self.ts.device)
+        squeeze = tq.ndim == 0 or (tq.ndim == 1 and tq.shape[0] == n and False)
+        if tq.ndim == 0:
+            tq = tq.expand(n, 1)
+        elif tq.ndim == 1:
+            tq = tq.unsqueeze(0).expand(n, tq.shape[0])
+        tq = tq.contiguous()
+        nq = tq.shape[1]
+        out = xp.empty((n, nq, d), self.ts.dtype)
+        count = (self.ts_size - 1).to(torch.int32).contiguous()
+        direction = float(self.direction)
+        _lib.check(_lib.lib().dfx_dense_evaluate(
+            xp.dtype_id(self.ts.dtype), self.solver.solver_id, n, d, msp1 - 1, xp.ptr(self.ts),
+            xp.ptr(self.infos["y0"]), xp.ptr(self.infos["y1"]), xp.ptr(self.infos.get("k")), xp.ptr(count),
+            direction, xp.ptr(tq), nq, xp.ptr(out), xp.stream()))
+        # trivial (t0 == t1) case: evaluate(t0) == y0  (_global_interpolation.py:343-355)
+        trivial = (self.ts_size == 1)
+        if bool(trivial.any()):
+            tt = tq * direction
+            m = trivial[:, None] & (tt == self.t0_if_trivial[:, None])
+            out = torch.where(m[:, :, None], self.y0_if_trivial[:, None, :].expand_as(out), out)
+        return out[:, 0, :] if squeeze else out
+
+
+# --------------------------------------------------------------------------------------
+# diffeqsolve
+# --------------------------------------------------------------------------------------
+def _parse_terms(terms):
+    """Returns (field, VirtualBrownianTree or None)."""
+    if isinstance(terms, ODETerm):
+        return terms.vector_field.field, None
+    if isinstance(terms, MultiTerm):
+        if len(terms.terms) != 2 or not isinstance(terms.terms[0], ODETerm) or not isinstance(terms.terms[1], ControlTerm):
+            raise ValueError("MultiTerm must be MultiTerm(ODETerm(drift), ControlTerm(diffusion, VirtualBrownianTree))")
+        drift, diff = terms.terms
+        if drift.vector_field.field is not diff.vector_field.field:
+            raise ValueError("drift and diffusion must come from the same registered SDE functor")
+        return drift.vector_field.field, diff.control
+    raise TypeError("terms must be ODETerm(...) or MultiTerm(ODETerm(...), ControlTerm(...))")
+
+
+def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
+                stepsize_controller=None, max_steps: Optional[int] = 4096, throw: bool = True,
+                device: int = 0) -> Solution:
+    """Batched forward solve == ``jax.vmap(lambda y0: diffrax.diffeqsolve(...))(y0)``
+    (_integrate.py:888-1543).
+
+    ``y0``: ``[N, d]`` (or ``[N]`` for scalar states).  torch CUDA tensors run in place on the
+    current stream (device path); numpy arrays / CPU tensors go through
+    ``dfx_ensemble_solve_host`` which stages them to GPU ``device`` and back.
+    ``t0`` / ``t1`` may be scalars or ``[N]`` arrays.
+    """
+    if args is not None:
+        raise ValueError("args must be None: functor parameters are bound when the functor is created")
+    saveat = SaveAt(t1=True) if saveat is None else saveat
+    ctrl = ConstantStepSize() if stepsize_controller is None else stepsize_controller
+    field, bm = _parse_terms(terms)
+    if max_steps is None:
+        raise ValueError("max_steps=None is not supported by the ensemble kernels")
+
+    xp = _Backend.of(y0)
+    is_torch = isinstance(xp, _TorchBackend)
+    y0a = y0 if is_torch else np.asarray(y0)
+    if y0a.dtype not in ((torch.float64, torch.float32) if is_torch else (np.dtype("float64"), np.dtype("float32"))):
+        y0a = xp.asarray(y0a, torch.float64 if is_torch else np.float64)
+    scalar_state = y0a.ndim == 1
+    if scalar_state:
+        y0a = y0a[:, None]
+    if y0a.ndim != 2:
+        raise ValueError("y0 must have shape [N, d]")
+    y0a = xp.asarray(y0a, y0a.dtype)
+    n, d = int(y0a.shape[0]), int(y0a.shape[1])
+    rdt = y0a.dtype
+    if field.dim not in (0, d):
+        raise ValueError(f"{type(field).__name__} has state dimension {field.dim}, got y0 with d={d}")
+
+    L = _lib.lib()
+    D = _lib.new_desc()
+    D.field_id, D.dim, D.dtype, D.solver_id = field.field_id, d, xp.dtype_id(rdt), solver.solver_id
+    params = np.ascontiguousarray(field.params(), np.float64)
+    D.field_params, D.n_field_params = params.ctypes.data, params.size
+    weights = field.weights(xp, rdt)
+    if weights is not None:
+        D.field_weights, D.n_field_weights = xp.ptr(weights), int(weights.numel() if is_torch else weights.size)
+    D.n_traj, D.y0 = n, xp.ptr(y0a)
+
+    keep_alive = [params, weights, y0a]
+
+    def _time_arg(x):
+        per = hasattr(x, "shape") and len(getattr(x, "shape")) == 1
+        if per:
+            a = xp.asarray(x, rdt)
+            keep_alive.append(a)
+            return float("nan"), a
+        return float(x), None
+
+    t0s, t0arr = _time_arg(t0)
+    t1s, t1arr = _time_arg(t1)
+    if (t0arr is None) != (t1arr is None):  # promote the scalar one
+        if t0arr is None:
+            t0arr = xp.as_real(t0s, n, rdt if is_torch else rdt)
+            keep_alive.append(t0arr)
+        else:
+            t1arr = xp.as_real(t1s, n, rdt if is_torch else rdt)
+            keep_alive.append(t1arr)
+    D.t0, D.t1 = (0.0 if t0arr is not None else t0s), (0.0 if t1arr is not None else t1s)
+    D.t0_per_traj, D.t1_per_traj = xp.ptr(t0arr), xp.ptr(t1arr)
+    D.dt0 = math.nan if dt0 is None else float(dt0)
+    if dt0 is not None and t0arr is None and (t1s - t0s) * float(dt0) < 0:
+        raise ValueError("Must have (t1 - t0) * dt0 >= 0")  # _integrate.py:1036-1045
+
+    if isinstance(ctrl, PIDController):
+        D.controller = _lib.CTRL_PID
+        D.rtol, D.atol = float(ctrl.rtol), float(ctrl.atol)
+        D.pcoeff, D.icoeff, D.dcoeff = float(ctrl.pcoeff), float(ctrl.icoeff), float(ctrl.dcoeff)
+        D.safety, D.factormin, D.factormax = float(ctrl.safety), float(ctrl.factormin), float(ctrl.factormax)
+        D.dtmin = math.nan if ctrl.dtmin is None else float(ctrl.dtmin)
+        D.dtmax = math.nan if ctrl.dtmax is None else float(ctrl.dtmax)
+        D.force_dtmin = int(ctrl.force_dtmin)
+        D.error_order = math.nan if ctrl.error_order is None else float(ctrl.error_order)
+        if isinstance(solver, Euler):
+            if bm is not None:
+                raise ValueError("An SDE should not be solved with adaptive step sizes with Euler's method, "
+                                 "as it may not converge to the correct solution.")  # _integrate.py:1143-1149
+            raise RuntimeError("Cannot use adaptive step sizes with a solver that does not provide error estimates.")
+    elif isinstance(ctrl, ConstantStepSize):
+        D.controller = _lib.CTRL_CONSTANT
+        D.dtmin = D.dtmax = D.error_order = math.nan
+        if dt0 is None:
+            raise ValueError("Constant step size solvers cannot select step size automatically; "
+                             "please pass a value for `dt0`.")  # constant.py:41-45
+    else:
+        raise TypeError("stepsize_controller must be ConstantStepSize() or PIDController(...)")
+
+    D.save_t0, D.save_t1, D.save_steps, D.save_dense = int(saveat.t0), int(saveat.t1), saveat.steps, int(saveat.dense)
+    ts_in = None
+    if saveat.ts is not None:
+        ts_in = xp.asarray(saveat.ts, rdt).reshape(-1)
+        keep_alive.append(ts_in)
+        ts_np = ts_in.detach().cpu().numpy() if is_torch else ts_in
+        if ts_np.size > 1:
+            dif = np.diff(ts_np)
+            if not (np.all(dif >= 0) or np.all(dif <= 0)):
+                raise RuntimeError("saveat.ts must be increasing or decreasing.")  # _integrate.py:1223-1227
+        if t0arr is None and ts_np.size:
+            lo, hi = min(t0s, t1s), max(t0s, t1s)
+            if ts_np.min() < lo or ts_np.max() > hi:
+                raise RuntimeError("saveat.ts must lie between t0 and t1.")  # _integrate.py:1228-1232
+        D.save_ts, D.n_save_ts = xp.ptr(ts_in), int(ts_in.shape[0])
+    D.max_steps = int(max_steps)
+
+    if bm is not None:
+        keys = _as_keys(bm.key)
+        if is_torch != (torch is not None and isinstance(keys, torch.Tensor)):
+            keys = (torch.as_tensor(np.asarray(keys).view(np.int32), device=y0a.device) if is_torch
+                    else keys.detach().cpu().numpy().view(np.uint32))
+        elif is_torch and keys.device != y0a.device:
+            keys = keys.to(y0a.device)
+        if int(keys.shape[0]) != n:
+            raise ValueError(f"VirtualBrownianTree has {int(keys.shape[0])} keys for {n} trajectories")
+        keep_alive.append(keys)
+        D.levy_area, D.bm_keys = bm.levy_area.levy_id, xp.ptr(keys)
+        D.bm_t0, D.bm_t1, D.bm_tol = bm.t0, bm.t1, bm.tol
+        D.threefry_partitionable = int(bm.partitionable)
+        if not field.is_sde:
+            raise ValueError(f"{type(field).__name__} is not an SDE functor")
+    elif isinstance(solver, ShARK):
+        raise ValueError("ShARK requires MultiTerm(ODETerm(drift), ControlTerm(diffusion, VirtualBrownianTree))")
+
+    T = L.dfx_out_size(C.byref(D))
+    i32 = xp.int32()
+    ts_out = xp.empty((n, T), rdt)
+    ys_out = xp.empty((n, T, d), rdt)
+    stats = xp.empty((n, 3), i32)
+    result = xp.empty((n,), i32)
+    y_final = xp.empty((n, d), rdt)
+    t_final = xp.empty((n,), rdt)
+    D.ts_out, D.ys_out, D.stats, D.result = xp.ptr(ts_out), xp.ptr(ys_out), xp.ptr(stats), xp.ptr(result)
+    D.y_final, D.t_final = xp.ptr(y_final), xp.ptr(t_final)
+    dense = None
+    if saveat.dense:
+        s = L.dfx_num_stages(solver.solver_id)
+        dense = dict(ts=xp.empty((n, max_steps + 1), rdt), y0=xp.empty((n, max_steps, d), rdt),
+                     y1=xp.empty((n, max_steps, d), rdt), count=xp.empty((n,), i32))
+        if solver.name not in ("euler", "shark"):
+            dense["k"] = xp.empty((n, max_steps, s, d), rdt)
+        D.dense_ts, D.dense_y0, D.dense_y1 = xp.ptr(dense["ts"]), xp.ptr(dense["y0"]), xp.ptr(dense["y1"])
+        D.dense_k, D.dense_count = xp.ptr(dense.get("k")), xp.ptr(dense["count"])
+
+    if xp.device_ptrs:
+        with torch.cuda.device(y0a.device):
+            _lib.check(L.dfx_ensemble_solve(C.byref(D), xp.stream()))
+    else:
+        _lib.check(L.dfx_ensemble_solve_host(C.byref(D), int(device)))
+    del keep_alive
+
+    stats_d = {"num_steps": stats[:, 0], "num_accepted_steps": stats[:, 1], "num_rejected_steps": stats[:, 2],
+               "max_steps": max_steps}
+    interpolation = None
+    if dense is not None and is_torch and xp.device_ptrs:
+        if t0arr is not None:
+            dirn = 1.0  # per-trajectory direction: only forward dense evaluation is wired up
+        else:
+            dirn = 1.0 if t0s < t1s else -1.0
+        t0_norm = (t0arr if t0arr is not None else xp.as_real(t0s, n, rdt)) * dirn
+        interpolation = DenseInterpolation(solver, dense["ts"], dense["count"].to(torch.int64) + 1,
+                                           {k: v for k, v in dense.items() if k in ("y0", "y1", "k")},
+                                           dirn, t0_norm, y0a, xp)
+    elif dense is not None:
+        interpolation = dense  # raw buffers on the host path
+    if scalar_state:
+        ys_out = ys_out[..., 0]
+        y_final = y_final[..., 0]
+    sol = Solution(t0=t0, t1=t1, ts=ts_out, ys=ys_out, interpolation=interpolation, stats=stats_d, result=result,
+                   y_final=y_final, t_final=t_final)
+    if throw:
+        bad = (result != RESULTS.successful)
+        if bool(bad.any()):
+            code = int(result[bad][0])
+            raise RuntimeError(RESULTS._messages.get(code, f"solver failed with code {code}"))  # _integrate.py:1541-1542
+    return sol

@@ -1,0 +1,84 @@
+"""Build libdiffrax_b200.so in-tree with nvcc for sm_100a (no torch extension machinery).
+
+    python -m diffrax_b200.build [--force] [-j N]
+
+Each translation unit under csrc/ is compiled to an object in csrc/_obj/ (in parallel) and
+linked into diffrax_b200/lib/libdiffrax_b200.so.  The .so travels to the GPU box with the
+gpurun snapshot; it is git-ignored.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import glob
+import os
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libdiffrax_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+         "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")]
+
+
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "diffrax_b200.h")]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(src):
+    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    log = obj + ".log"
+    t0 = time.time()
+    r = subprocess.run([NVCC, *ARCH, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+    with open(log, "w") as f:
+        f.write(r.stdout + r.stderr)
+    return src, obj, r.returncode, time.time() - t0, r.stderr
+
+
+def build(force=False, jobs=None, verbose=True):
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    hdrs = _headers()
+    todo = [s for s in srcs if force or _stale(os.path.join(OBJ, os.path.basename(s)[:-3] + ".o"), [s] + hdrs)]
+    jobs = jobs or min(len(todo) or 1, os.cpu_count() or 4)
+    if todo:
+        with cf.ThreadPoolExecutor(jobs) as ex:
+            for src, obj, rc, dt, err in ex.map(_compile, todo):
+                if verbose:
+                    print(f"[build] {os.path.basename(src)} rc={rc} {dt:.1f}s", flush=True)
+                if rc != 0:
+                    sys.stderr.write(err[-6000:])
+                    raise RuntimeError(f"nvcc failed on {src}")
+    objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    if force or todo or _stale(LIB, objs):
+        r = subprocess.run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stderr)
+            raise RuntimeError("link failed")
+        if verbose:
+            print(f"[build] linked {LIB}", flush=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("-j", type=int, default=None)
+    a = ap.parse_args()
+    build(a.force, a.j)

@@ -1,0 +1,523 @@
+// api.cu - C ABI of libdiffrax_b200 (include/diffrax_b200.h): registry, argument checking,
+// host-buffer wrapper, and the small standalone kernels (PRNG known-answer entry points,
+// VirtualBrownianTree.evaluate, DenseInterpolation.evaluate, pipe-peak microbenchmarks).
+#include <cstdarg>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "launch.cuh"
+
+namespace dfx {
+
+static thread_local char tl_error[512] = "";
+static thread_local long long tl_launches = 0;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { tl_launches += n; }
+
+using RegKey = std::tuple<int, int, int, int, int>;  // field, dim, solver, dtype, levy
+static std::map<RegKey, dfx_launcher_fn> &registry() {
+  static std::map<RegKey, dfx_launcher_fn> r;
+  return r;
+}
+static std::mutex &registry_mutex() {
+  static std::mutex m;
+  return m;
+}
+int register_builtin(int field_id, int dim, int solver_id, int dtype, int levy, dfx_launcher_fn fn) {
+  std::lock_guard<std::mutex> g(registry_mutex());
+  registry()[RegKey(field_id, dim, solver_id, dtype, levy)] = fn;
+  return 0;
+}
+static dfx_launcher_fn find_launcher(int field_id, int dim, int solver_id, int dtype, int levy) {
+  std::lock_guard<std::mutex> g(registry_mutex());
+  auto it = registry().find(RegKey(field_id, dim, solver_id, dtype, levy));
+  return it == registry().end() ? nullptr : it->second;
+}
+
+int device_sm_count(int *sms) {
+  static std::mutex m;
+  static std::map<int, int> cache;
+  int dev = 0;
+  DFX_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(m);
+  auto it = cache.find(dev);
+  if (it == cache.end()) {
+    int n = 0;
+    DFX_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    it = cache.emplace(dev, n).first;
+  }
+  *sms = it->second;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone kernels
+// ------------------------------------------------------------------------------------------
+__global__ void threefry_kernel(long long n, const uint32_t *keys, const uint32_t *ctrs, uint32_t *out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a, b;
+  threefry2x32(keys[2 * i], keys[2 * i + 1], ctrs[2 * i], ctrs[2 * i + 1], a, b);
+  out[2 * i] = a;
+  out[2 * i + 1] = b;
+}
+
+__global__ void split_kernel(long long n, const uint32_t *keys, int num, int partitionable, uint32_t *out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k0 = keys[2 * i], k1 = keys[2 * i + 1];
+  uint32_t *o = out + i * 2 * num;
+  for (int c = 0; c < num; ++c) {
+    uint32_t a, b;
+    if (partitionable) {
+      threefry2x32(k0, k1, 0u, (uint32_t)c, a, b);
+      o[2 * c] = a;
+      o[2 * c + 1] = b;
+    } else {
+      threefry2x32(k0, k1, (uint32_t)c, (uint32_t)(num + c), a, b);
+      o[c] = a;
+      o[num + c] = b;
+    }
+  }
+}
+
+template <class R>
+__global__ void normal_kernel(long long n, const uint32_t *keys, int partitionable, R *out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = random_normal<R>(Key{keys[2 * i], keys[2 * i + 1]}, partitionable != 0);
+}
+
+template <class R, bool STLA>
+__global__ void vbt_kernel(long long n, const uint32_t *keys, VbtParams vp, const R *ta, const R *tb, int per_traj,
+                           R *W, R *H) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  BrownianTree<R, STLA> bm;
+  bm.init(keys + 2 * i, vp);
+  R w, h;
+  bm.increment(ta[per_traj ? i : 0], tb[per_traj ? i : 0], vp, w, h);
+  W[i] = w;
+  if (H) H[i] = h;
+}
+
+// DenseInterpolation.evaluate (_global_interpolation.py:335-355), one thread per (trajectory, query).
+template <class R, class Solver, int D>
+__global__ void dense_eval_kernel(long long n_traj, int max_steps, const R *dts, const R *dy0, const R *dy1,
+                                  const R *dk, const int *dcount, R direction, const R *tq, int nq, R *out) {
+  constexpr int S = Solver::S;
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (gid >= n_traj * nq) return;
+  const long long i = gid / nq;
+  const R *ts = dts + i * (long long)(max_steps + 1);
+  const int ts_size = dcount[i] + 1;
+  R t = tq[gid] * direction;
+  // _nan_if_out_of_bounds (370-381)
+  if (ts_size <= 1 || t < ts[0] || t > ts[ts_size - 1]) t = Num<R>::nan();
+  // _interpret_t (36-45): searchsorted(ts, t, side="left") over the inf-padded array, then clip(index-1, 0, ts_size-2)
+  int lo = 0, hi = max_steps + 1;
+  if (t != t) lo = max_steps + 1;
+  else while (lo < hi) { const int mid = (lo + hi) >> 1; if (ts[mid] < t) lo = mid + 1; else hi = mid; }
+  int index = lo - 1;
+  if (index > ts_size - 2) index = ts_size - 2;
+  if (index < 0) index = 0;
+  R y0[D], y1[D], k[S][D], o[D];
+  const long long row = i * (long long)max_steps + index;
+#pragma unroll
+  for (int c = 0; c < D; ++c) { y0[c] = dy0[row * D + c]; y1[c] = dy1[row * D + c]; }
+#pragma unroll
+  for (int j = 0; j < S; ++j)
+#pragma unroll
+    for (int c = 0; c < D; ++c) k[j][c] = (Solver::kInterp != kInterpLinear && dk) ? dk[(row * S + j) * D + c] : R(0);
+  interp_eval<Solver::kInterp, R, S, D>(ts[index], ts[index + 1], y0, y1, k, t, o);
+#pragma unroll
+  for (int c = 0; c < D; ++c) out[gid * D + c] = o[c];
+}
+
+// Pipe-peak microbenchmarks: 8 independent FMA chains per thread, enough warps to fill every SM.
+template <class R>
+__global__ void fma_peak_kernel(R *out, int iters, R a, R b) {
+  R x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (R)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = x[i] * a + b;
+  }
+  R s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == (R)123456789) out[0] = s;
+}
+__global__ void int_peak_kernel(uint32_t *out, int iters) {
+  uint32_t x[8], y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = threadIdx.x + i; y[i] = blockIdx.x * 7 + i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] += y[i]; y[i] = rotl(y[i], 13); y[i] ^= x[i]; }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i] ^ y[i];
+  if (s == 0x12345678u) out[0] = s;
+}
+
+template <class R, class Solver>
+static int dense_eval_dispatch_dim(int dim, long long n, int ms, const void *dts, const void *dy0, const void *dy1,
+                                   const void *dk, const int *dc, double direction, const void *tq, int nq, void *out,
+                                   cudaStream_t st) {
+  const long long total = n * nq;
+  const unsigned blocks = (unsigned)((total + 127) / 128);
+#define DFX_DE(DD)                                                                                              \
+  case DD:                                                                                                      \
+    dense_eval_kernel<R, Solver, DD><<<blocks, 128, 0, st>>>(n, ms, (const R *)dts, (const R *)dy0, (const R *)dy1, \
+                                                             (const R *)dk, dc, (R)direction, (const R *)tq, nq, (R *)out); \
+    break;
+  switch (dim) {
+    DFX_DE(1) DFX_DE(2) DFX_DE(3) DFX_DE(4)
+    default:
+      set_error("dense_evaluate: unsupported dim %d", dim);
+      return DFX_ERR_UNSUPPORTED;
+  }
+#undef DFX_DE
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <class R>
+static int dense_eval_dispatch(int solver_id, int dim, long long n, int ms, const void *dts, const void *dy0,
+                               const void *dy1, const void *dk, const int *dc, double direction, const void *tq, int nq,
+                               void *out, cudaStream_t st) {
+  switch (solver_id) {
+#define DFX_DS(ID, T) case ID: return dense_eval_dispatch_dim<R, T>(dim, n, ms, dts, dy0, dy1, dk, dc, direction, tq, nq, out, st);
+    DFX_DS(DFX_TSIT5, Tsit5) DFX_DS(DFX_DOPRI5, Dopri5) DFX_DS(DFX_DOPRI8, Dopri8) DFX_DS(DFX_HEUN, Heun)
+    DFX_DS(DFX_BOSH3, Bosh3) DFX_DS(DFX_MIDPOINT, Midpoint) DFX_DS(DFX_RALSTON, Ralston)
+    DFX_DS(DFX_EULER, EulerSolver) DFX_DS(DFX_SHARK, SharkSolver)
+#undef DFX_DS
+  }
+  set_error("dense_evaluate: unknown solver %d", solver_id);
+  return DFX_ERR_BAD_ARGUMENT;
+}
+
+}  // namespace dfx
+
+using namespace dfx;
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int dfx_abi_version(void) { return DFX_ABI_VERSION; }
+const char *dfx_last_error(void) { return tl_error; }
+int64_t dfx_launch_count(void) { return tl_launches; }
+void dfx_reset_launch_count(void) { tl_launches = 0; }
+
+int dfx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int dfx_num_stages(int solver_id) {
+  switch (solver_id) {
+    case DFX_TSIT5: return Tsit5::S; case DFX_DOPRI5: return Dopri5::S; case DFX_DOPRI8: return Dopri8::S;
+    case DFX_HEUN: return Heun::S; case DFX_BOSH3: return Bosh3::S; case DFX_MIDPOINT: return Midpoint::S;
+    case DFX_RALSTON: return Ralston::S; case DFX_EULER: return 1; case DFX_SHARK: return 2;
+  }
+  return -1;
+}
+int dfx_solver_order(int solver_id) {
+  switch (solver_id) {
+    case DFX_TSIT5: return Tsit5::kOrder; case DFX_DOPRI5: return Dopri5::kOrder; case DFX_DOPRI8: return Dopri8::kOrder;
+    case DFX_HEUN: return Heun::kOrder; case DFX_BOSH3: return Bosh3::kOrder; case DFX_MIDPOINT: return Midpoint::kOrder;
+    case DFX_RALSTON: return Ralston::kOrder; case DFX_EULER: return 1; case DFX_SHARK: return 2;
+  }
+  return -1;
+}
+int dfx_field_dim(int field_id) {
+  switch (field_id) {
+    case DFX_FIELD_DECAY: return 0;
+    case DFX_FIELD_LOTKA_VOLTERRA: return 2; case DFX_FIELD_LORENZ: return 3; case DFX_FIELD_CR3BP: return 4;
+    case DFX_FIELD_OU: return 1; case DFX_FIELD_FORCED_OSC: return 2; case DFX_FIELD_VDP: return 2;
+    case DFX_FIELD_MLP: return 0;
+  }
+  return -1;
+}
+int dfx_has_kernel(int field_id, int dim, int solver_id, int dtype, int levy_area) {
+  return find_launcher(field_id, dim, solver_id, dtype, levy_area) != nullptr;
+}
+int dfx_register_launcher(int field_id, int dim, int solver_id, int dtype, int levy_area, dfx_launcher_fn fn) {
+  if (!fn) { set_error("null launcher"); return DFX_ERR_BAD_ARGUMENT; }
+  return register_builtin(field_id, dim, solver_id, dtype, levy_area, fn);
+}
+
+// _integrate.py:1273-1293
+int dfx_out_size(const dfx_solve_desc *d) {
+  int out = 0;
+  if (d->save_t0) out += 1;
+  if (d->save_ts) out += d->n_save_ts;
+  if (d->save_steps != 0) out += d->max_steps / d->save_steps;
+  if (d->save_t1 && (d->save_steps == 0 || (d->max_steps % d->save_steps) != 0)) out += 1;
+  return out;
+}
+
+static int check_desc(const dfx_solve_desc *d) {
+  if (!d) { set_error("null descriptor"); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->struct_size != sizeof(dfx_solve_desc) || d->abi_version != DFX_ABI_VERSION) {
+    set_error("descriptor ABI mismatch: size %u (want %zu), version %u (want %d)", d->struct_size,
+              sizeof(dfx_solve_desc), d->abi_version, DFX_ABI_VERSION);
+    return DFX_ERR_BAD_ARGUMENT;
+  }
+  if (d->n_traj < 0 || d->dim < 1 || d->dim > kMaxDim) { set_error("bad n_traj / dim"); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->dtype != DFX_F64 && d->dtype != DFX_F32) { set_error("bad dtype %d", d->dtype); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->n_traj > 0 && !d->y0) { set_error("y0 is null"); return DFX_ERR_BAD_ARGUMENT; }
+  if (!d->stats || !d->result) { set_error("stats / result buffers are required"); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->max_steps < 0) { set_error("max_steps must be >= 0 (max_steps=None is not supported)"); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->save_steps < 0) { set_error("save_steps must be >= 0"); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->controller == DFX_CTRL_CONSTANT && is_nan(d->dt0)) {
+    // constant.py:41-45
+    set_error("Constant step size solvers cannot select step size automatically; please pass a value for `dt0`.");
+    return DFX_ERR_BAD_ARGUMENT;
+  }
+  if (d->controller == DFX_CTRL_PID && d->solver_id == DFX_EULER) {
+    // pid.py:461-469 (Euler provides no error estimate)
+    set_error("Cannot use adaptive step sizes with a solver that does not provide error estimates.");
+    return DFX_ERR_BAD_ARGUMENT;
+  }
+  if (!d->t0_per_traj && !d->t1_per_traj && !is_nan(d->dt0) && (d->t1 - d->t0) * d->dt0 < 0) {
+    set_error("Must have (t1 - t0) * dt0 >= 0");  // _integrate.py:1036-1045
+    return DFX_ERR_BAD_ARGUMENT;
+  }
+  const int T = dfx_out_size(d);
+  if (T > 0 && (!d->ts_out || !d->ys_out)) { set_error("ts_out / ys_out are required (T_out = %d)", T); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->save_dense && (!d->dense_ts || !d->dense_y0 || !d->dense_y1 || !d->dense_count)) {
+    set_error("dense buffers are required for SaveAt(dense=True)");
+    return DFX_ERR_BAD_ARGUMENT;
+  }
+  if (d->levy_area != DFX_LEVY_NONE) {
+    if (!d->bm_keys) { set_error("SDE solve needs bm_keys"); return DFX_ERR_BAD_ARGUMENT; }
+    if (!(d->bm_t0 < d->bm_t1)) { set_error("t0 must be strictly less than t1"); return DFX_ERR_BAD_ARGUMENT; }  // tree.py:281
+    if (d->solver_id == DFX_SHARK && d->levy_area != DFX_LEVY_SPACE_TIME) {
+      set_error("The Brownian increment does not have the minimal Levy Area SpaceTimeLevyArea.");  // srk.py:391-395
+      return DFX_ERR_BAD_ARGUMENT;
+    }
+  } else if (d->solver_id == DFX_SHARK) {
+    set_error("ShARK needs MultiTerm(ODETerm, ControlTerm(VirtualBrownianTree))");
+    return DFX_ERR_BAD_ARGUMENT;
+  }
+  return 0;
+}
+
+int dfx_ensemble_solve(const dfx_solve_desc *d, void *cuda_stream) {
+  if (int rc = check_desc(d)) return rc;
+  dfx_launcher_fn fn = find_launcher(d->field_id, d->dim, d->solver_id, d->dtype, d->levy_area);
+  if (!fn) {
+    set_error("no kernel registered for field %d dim %d solver %d dtype %d levy %d", d->field_id, d->dim,
+              d->solver_id, d->dtype, d->levy_area);
+    return DFX_ERR_UNSUPPORTED;
+  }
+  return fn(d, cuda_stream);
+}
+
+// Host-buffer variant: pinned staging is the caller's business (pass pinned pointers for full
+// PCIe speed); this does plain cudaMemcpyAsync on one stream and synchronises it.
+int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
+  if (int rc = check_desc(h)) return rc;
+  if (dfx_device_count() <= device) { set_error("CUDA device %d not available", device); return DFX_ERR_NO_DEVICE; }
+  DFX_CUDA_OK(cudaSetDevice(device));
+  cudaStream_t st;
+  DFX_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const size_t es = h->dtype == DFX_F64 ? 8 : 4;
+  const size_t N = (size_t)h->n_traj, D = (size_t)h->dim;
+  const int T = dfx_out_size(h);
+  const int S = dfx_num_stages(h->solver_id);
+  const size_t ms = (size_t)h->max_steps;
+  dfx_solve_desc d = *h;
+  std::vector<void *> allocs;
+  std::vector<std::tuple<void *, void *, size_t>> d2h;  // host dst, device src, bytes
+  int rc = 0;
+  auto dev_in = [&](const void *src, size_t bytes) -> void * {
+    if (!src || bytes == 0 || rc) return nullptr;
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) { set_error("cudaMallocAsync(%zu) failed", bytes); rc = DFX_ERR_CUDA; return nullptr; }
+    allocs.push_back(p);
+    if (cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D copy failed"); rc = DFX_ERR_CUDA; }
+    return p;
+  };
+  auto dev_out = [&](void *dst, size_t bytes) -> void * {
+    if (!dst || bytes == 0 || rc) return nullptr;
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) { set_error("cudaMallocAsync(%zu) failed", bytes); rc = DFX_ERR_CUDA; return nullptr; }
+    allocs.push_back(p);
+    d2h.emplace_back(dst, p, bytes);
+    return p;
+  };
+  d.y0 = dev_in(h->y0, N * D * es);
+  d.t0_per_traj = dev_in(h->t0_per_traj, N * es);
+  d.t1_per_traj = dev_in(h->t1_per_traj, N * es);
+  d.save_ts = dev_in(h->save_ts, (size_t)h->n_save_ts * es);
+  d.bm_keys = (const uint32_t *)dev_in(h->bm_keys, N * 8);
+  d.field_weights = dev_in(h->field_weights, (size_t)h->n_field_weights * es);
+  d.ts_out = dev_out(h->ts_out, N * T * es);
+  d.ys_out = dev_out(h->ys_out, N * T * D * es);
+  d.stats = (int32_t *)dev_out(h->stats, N * 3 * 4);
+  d.result = (int32_t *)dev_out(h->result, N * 4);
+  d.save_count = (int32_t *)dev_out(h->save_count, N * 4);
+  if (h->save_dense) {
+    d.dense_ts = dev_out(h->dense_ts, N * (ms + 1) * es);
+    d.dense_y0 = dev_out(h->dense_y0, N * ms * D * es);
+    d.dense_y1 = dev_out(h->dense_y1, N * ms * D * es);
+    d.dense_k = dev_out(h->dense_k, N * ms * S * D * es);
+    d.dense_count = (int32_t *)dev_out(h->dense_count, N * 4);
+  }
+  d.y_final = dev_out(h->y_final, N * D * es);
+  d.t_final = dev_out(h->t_final, N * es);
+  if (!rc) rc = dfx_ensemble_solve(&d, (void *)st);
+  if (!rc)
+    for (auto &c : d2h)
+      if (cudaMemcpyAsync(std::get<0>(c), std::get<1>(c), std::get<2>(c), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        set_error("D2H copy failed");
+        rc = DFX_ERR_CUDA;
+        break;
+      }
+  for (void *p : allocs) cudaFreeAsync(p, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (!rc && e != cudaSuccess) { set_error("stream sync failed: %s", cudaGetErrorString(e)); rc = DFX_ERR_CUDA; }
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+int dfx_threefry2x32(int64_t n, const uint32_t *keys, const uint32_t *ctrs, uint32_t *out, void *stream) {
+  if (n <= 0) return 0;
+  threefry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, keys, ctrs, out);
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int dfx_random_split(int64_t n, const uint32_t *keys, int num, int partitionable, uint32_t *out, void *stream) {
+  if (n <= 0) return 0;
+  split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, keys, num, partitionable, out);
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int dfx_random_normal(int dtype, int64_t n, const uint32_t *keys, int partitionable, void *out, void *stream) {
+  if (n <= 0) return 0;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == DFX_F64) normal_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, keys, partitionable, (double *)out);
+  else normal_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, keys, partitionable, (float *)out);
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dfx_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, const uint32_t *keys, double bm_t0,
+                     double bm_t1, double bm_tol, const void *ta, const void *tb, int per_traj_times, void *W, void *H,
+                     void *stream) {
+  if (n <= 0) return 0;
+  if (!(bm_t0 < bm_t1)) { set_error("t0 must be strictly less than t1"); return DFX_ERR_BAD_ARGUMENT; }
+  VbtParams vp;
+  vp.t0 = bm_t0; vp.t1 = bm_t1; vp.levy = levy_area; vp.partitionable = partitionable;
+  const double tol_n = bm_tol / (bm_t1 - bm_t0);
+  int depth = 0;
+  while (std::ldexp(1.0, -depth) > tol_n && depth < 1000) ++depth;
+  vp.depth = depth;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool stla = levy_area == DFX_LEVY_SPACE_TIME;
+  if (dtype == DFX_F64) {
+    if (stla) vbt_kernel<double, true><<<blocks, 128, 0, st>>>(n, keys, vp, (const double *)ta, (const double *)tb, per_traj_times, (double *)W, (double *)H);
+    else vbt_kernel<double, false><<<blocks, 128, 0, st>>>(n, keys, vp, (const double *)ta, (const double *)tb, per_traj_times, (double *)W, (double *)H);
+  } else {
+    if (stla) vbt_kernel<float, true><<<blocks, 128, 0, st>>>(n, keys, vp, (const float *)ta, (const float *)tb, per_traj_times, (float *)W, (float *)H);
+    else vbt_kernel<float, false><<<blocks, 128, 0, st>>>(n, keys, vp, (const float *)ta, (const float *)tb, per_traj_times, (float *)W, (float *)H);
+  }
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dfx_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
+                       const void *dense_y0, const void *dense_y1, const void *dense_k, const int32_t *dense_count,
+                       double direction, const void *tq, int nq, void *out, void *stream) {
+  if (n_traj <= 0 || nq <= 0) return 0;
+  if (dtype == DFX_F64)
+    return dense_eval_dispatch<double>(solver_id, dim, n_traj, max_steps, dense_ts, dense_y0, dense_y1, dense_k,
+                                       dense_count, direction, tq, nq, out, (cudaStream_t)stream);
+  return dense_eval_dispatch<float>(solver_id, dim, n_traj, max_steps, dense_ts, dense_y0, dense_y1, dense_k,
+                                    dense_count, direction, tq, nq, out, (cudaStream_t)stream);
+}
+
+double dfx_measure_fma_peak(int dtype, int device) {
+  if (dfx_device_count() <= device) { set_error("CUDA device %d not available", device); return DFX_ERR_NO_DEVICE; }
+  cudaSetDevice(device);
+  int sms = 0;
+  if (device_sm_count(&sms)) return DFX_ERR_CUDA;
+  const int threads = 256, blocks = sms * 8, iters = dtype == DFX_F64 ? 4096 : 16384;
+  void *out = nullptr;
+  if (cudaMalloc(&out, 64) != cudaSuccess) return DFX_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    if (dtype == DFX_F64) fma_peak_kernel<double><<<blocks, threads>>>((double *)out, iters, 1.0000001, 1e-9);
+    else fma_peak_kernel<float><<<blocks, threads>>>((float *)out, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  count_launch(6);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess) return DFX_ERR_CUDA;
+  const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+  return flops / (best * 1e-3) / 1e12;
+}
+
+double dfx_measure_int_peak(int device) {
+  if (dfx_device_count() <= device) { set_error("CUDA device %d not available", device); return DFX_ERR_NO_DEVICE; }
+  cudaSetDevice(device);
+  int sms = 0;
+  if (device_sm_count(&sms)) return DFX_ERR_CUDA;
+  const int threads = 256, blocks = sms * 8, iters = 8192;
+  void *out = nullptr;
+  if (cudaMalloc(&out, 64) != cudaSuccess) return DFX_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    int_peak_kernel<<<blocks, threads>>>((uint32_t *)out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  count_launch(6);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess) return DFX_ERR_CUDA;
+  const double ops = 3.0 * 8.0 * (double)iters * (double)threads * (double)blocks;  // add, rotate, xor
+  return ops / (best * 1e-3) / 1e12;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// common.cuh - scalar helpers shared by the sm_100a ensemble kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/diffrax_b200.h"
+
+namespace dfx {
+
+constexpr int kMaxDim = 8;
+constexpr int kWarp = 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <class R> struct Num;
+template <> struct Num<double> {
+  using uint_t = unsigned long long;
+  using int_t = long long;
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+  static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+  static __device__ __forceinline__ double eps() { return 2.220446049250313e-16; }
+  static __device__ __forceinline__ long long bits(double x) { return __double_as_longlong(x); }
+  static __device__ __forceinline__ double from_bits(long long b) { return __longlong_as_double(b); }
+};
+template <> struct Num<float> {
+  using uint_t = unsigned int;
+  using int_t = int;
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+  static __device__ __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
+  static __device__ __forceinline__ float eps() { return 1.1920929e-07f; }
+  static __device__ __forceinline__ int bits(float x) { return __float_as_int(x); }
+  static __device__ __forceinline__ float from_bits(int b) { return __int_as_float(b); }
+};
+
+__device__ __forceinline__ double r_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double r_pow(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ float r_pow(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ double r_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float r_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double r_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float r_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double r_sin(double x) { return sin(x); }
+__device__ __forceinline__ float r_sin(float x) { return sinf(x); }
+__device__ __forceinline__ double r_exp(double x) { return exp(x); }
+__device__ __forceinline__ float r_exp(float x) { return expf(x); }
+__device__ __forceinline__ double r_log1p(double x) { return log1p(x); }
+__device__ __forceinline__ float r_log1p(float x) { return log1pf(x); }
+__device__ __forceinline__ double r_tanh(double x) { return tanh(x); }
+__device__ __forceinline__ float r_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ bool r_isnan(double x) { return x != x; }
+__device__ __forceinline__ bool r_isnan(float x) { return x != x; }
+__device__ __forceinline__ bool r_isinf(double x) { return fabs(x) == Num<double>::inf(); }
+__device__ __forceinline__ bool r_isinf(float x) { return fabsf(x) == Num<float>::inf(); }
+
+// jnp.maximum / jnp.minimum propagate NaN; CUDA fmax/fmin do not.
+template <class R> __device__ __forceinline__ R jnp_max(R a, R b) { return (a != a || b != b) ? Num<R>::nan() : r_max(a, b); }
+template <class R> __device__ __forceinline__ R jnp_min(R a, R b) { return (a != a || b != b) ? Num<R>::nan() : r_min(a, b); }
+
+// eqxi.prevbefore applied n times == nextafter(x, -inf) n times (_integrate.py:320-322),
+// done in one integer step on the ordered bit pattern.
+template <class R> __device__ __host__ inline R prev_n(R x, int n);
+template <> __device__ __host__ inline double prev_n<double>(double x, int n) {
+  if (x != x) return x;
+  long long b;
+#ifdef __CUDA_ARCH__
+  b = __double_as_longlong(x);
+#else
+  memcpy(&b, &x, 8);
+#endif
+  long long key = b >= 0 ? b : -(b & 0x7fffffffffffffffLL);
+  if (b == 0x7ff0000000000000LL) { /* +inf -> largest finite, then n-1 more */ }
+  key -= n;
+  long long ob = key >= 0 ? key : (long long)(0x8000000000000000ULL | (unsigned long long)(-key));
+  double out;
+#ifdef __CUDA_ARCH__
+  out = __longlong_as_double(ob);
+#else
+  memcpy(&out, &ob, 8);
+#endif
+  return out;
+}
+template <> __device__ __host__ inline float prev_n<float>(float x, int n) {
+  if (x != x) return x;
+  int b;
+#ifdef __CUDA_ARCH__
+  b = __float_as_int(x);
+#else
+  memcpy(&b, &x, 4);
+#endif
+  int key = b >= 0 ? b : -(b & 0x7fffffff);
+  key -= n;
+  int ob = key >= 0 ? key : (int)(0x80000000u | (unsigned)(-key));
+  float out;
+#ifdef __CUDA_ARCH__
+  out = __int_as_float(ob);
+#else
+  memcpy(&out, &ob, 4);
+#endif
+  return out;
+}
+
+// _misc.py:71-82
+template <class R> __device__ __forceinline__ R linear_rescale(R t0, R t, R t1) {
+  const bool cond = (t0 == t1);
+  const R num = cond ? R(0) : t - t0;
+  const R den = cond ? R(1) : t1 - t0;
+  return num / den;
+}
+
+// streaming (evict-first) stores for write-once outputs
+__device__ __forceinline__ void st_cs(double *p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_cs(float *p, float v) { __stcs(p, v); }
+
+}  // namespace dfx

@@ -1,0 +1,466 @@
+// ensemble_kernel.cuh - the persistent adaptive ensemble integrator kernel (K1/K2/K4 of SURVEY.md §2.1).
+//
+// One kernel replaces, per trajectory, the whole body of the reference's vmapped diffeqsolve:
+//   _integrate.py:302-885   loop / body_fun_aux: step -> adapt -> clip to t1 -> keep/restore -> counters -> save
+//   runge_kutta.py:446-1203 explicit single-tableau ERK step with FSAL / SSAL
+//   euler.py:46-59, srk.py:335-671 (+ shark.py:10-30) additive-noise SRK step
+//   pid.py:316-392, 394-567 PID controller; constant.py:30-104 ConstantStepSize
+//   _local_interpolation.py / tsit5.py / dopri5.py / dopri8.py interpolants for SaveAt(ts)
+//   _brownian/tree.py       VirtualBrownianTree increments (vbt.cuh)
+//
+// Mapping to the hardware
+//   * one trajectory per thread; y, the s stage values k[s][d], the FSAL derivative and the
+//     controller state stay in registers for the whole solve (stage loops fully unrolled, Butcher
+//     coefficients read from __constant__ memory as immediate c[bank][offset] operands);
+//   * HBM is touched only to read y0 once and to write saved outputs;
+//   * the adaptive loops diverge per trajectory, so the grid is persistent (a multiple of the SM
+//     count) and a lane that finishes its trajectory immediately claims the next one from a
+//     global work queue (warp-aggregated atomicAdd: one atomic per refilling warp).  The still
+//     active lanes therefore stay compacted in full warps until the queue drains; results do not
+//     depend on the lane <-> trajectory assignment because trajectories are independent.
+//   * accept / reject is a select, not a branch: every lane executes the same instruction stream.
+#pragma once
+#include "common.cuh"
+#include "fields.cuh"
+#include "interp.cuh"
+#include "tableaux.cuh"
+#include "vbt.cuh"
+
+namespace dfx {
+
+struct EulerSolver {
+  static constexpr int kId = DFX_EULER;
+  static constexpr int S = 1;
+  static constexpr int kOrder = 1;
+  static constexpr bool kFsal = false, kSsal = false;
+  static constexpr int kInterp = kInterpLinear;
+  static constexpr bool kIsTableau = false;
+};
+struct SharkSolver {
+  static constexpr int kId = DFX_SHARK;
+  static constexpr int S = 2;
+  static constexpr int kOrder = 2;
+  static constexpr bool kFsal = false, kSsal = false;
+  static constexpr int kInterp = kInterpLinear;
+  static constexpr bool kIsTableau = false;
+};
+template <class T, class = void> struct IsTableau { static constexpr bool value = true; };
+template <> struct IsTableau<EulerSolver> { static constexpr bool value = false; };
+template <> struct IsTableau<SharkSolver> { static constexpr bool value = false; };
+
+template <class R>
+struct SolveParams {
+  long long n_traj;
+  const R *y0;
+  const R *t0_arr, *t1_arr;
+  R t0, t1;
+  R dt0;
+  int has_dt0;
+  int controller;
+  R rtol, atol, safety, factormin, factormax, dtmin, dtmax;
+  int has_dtmin, has_dtmax, force_dtmin;
+  R coeff1, coeff2, coeff3;  // PID exponents (pid.py:512-514), computed in double on the host
+  int use_c1, use_c2, use_c3;
+  int save_t0, save_t1, save_steps, save_dense;
+  const R *save_ts;
+  int n_save_ts, max_steps, out_size;
+  R *ts_out, *ys_out;
+  int *stats, *result, *save_count;
+  R *dense_ts, *dense_y0, *dense_y1, *dense_k;
+  int *dense_count;
+  R *y_final, *t_final;
+  unsigned long long *work_counter;
+  const uint32_t *keys;
+  VbtParams vbt;
+};
+
+constexpr int kBlockThreads = 128;
+
+// Claim the next trajectory for every lane of the warp that needs one: one atomic per warp.
+__device__ __forceinline__ long long claim_work(bool need, unsigned long long *counter) {
+  const unsigned m = __ballot_sync(kFullMask, need);
+  if (m == 0) return -1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(kFullMask, base, leader);
+  return need ? (long long)(base + __popc(m & ((1u << lane) - 1u))) : -1;
+}
+
+// Template parameters
+//   R      working dtype (state == time dtype)
+//   Field  vector-field functor (fields.cuh)
+//   Solver generated tableau struct (tableaux.cuh), EulerSolver or SharkSolver
+//   LEVY   dfx_levy: 0 ODE, 1 BrownianIncrement, 2 SpaceTimeLevyArea
+//   RICH   false: SaveAt(t1=True) only (the C2/C4/C5 fast path); true: every SaveAt mode
+template <class R, class Field, class Solver, int LEVY, bool RICH>
+__global__ void __launch_bounds__(kBlockThreads)
+ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) {
+  constexpr int D = Field::kDim;
+  constexpr int S = Solver::S;
+  constexpr bool SDE = LEVY != DFX_LEVY_NONE;
+  constexpr bool TAB = IsTableau<Solver>::value;
+  constexpr bool FSAL = Solver::kFsal && !SDE;
+  constexpr int INTERP = Solver::kInterp;
+  constexpr bool DENSE_K = INTERP != kInterpLinear;
+
+  // ---- per-lane trajectory state (registers) ----
+  bool active = false, exhausted = false;
+  long long idx = -1;
+  R y[D], f_fsal[D];
+  R tprev = R(0), tnext = R(0), t0 = R(0), t1 = R(0), direction = R(1), t1_clip_floor = R(0);
+  R pid_inv = R(1), pid_prev_inv = R(1);
+  bool at_dtmin = false;
+  int cs_steps_completed = 1, cs_num_steps = 0;
+  int num_steps = 0, num_accepted = 0, result = DFX_RESULT_SUCCESSFUL;
+  int save_index = 0, saveat_ts_index = 0, dense_index = 0;
+  BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME> bm;
+#pragma unroll
+  for (int c = 0; c < D; ++c) { y[c] = R(0); f_fsal[c] = R(0); }
+
+  const R sqrt_d = (R)sqrt((double)D);
+
+  for (;;) {
+    // ---------------- refill: finished lanes claim the next trajectory ----------------
+    // `exhausted` is warp-uniform (it is set from a warp vote), so the collective below is convergent.
+    if (!exhausted) {
+      const long long got = claim_work(!active, p.work_counter);
+      // the queue only grows: once any lane is handed an index past the end, it is drained for good
+      exhausted = __any_sync(kFullMask, !active && got >= p.n_traj);
+      if (!active) {
+        if (got >= 0 && got < p.n_traj) {
+          idx = got;
+          // _integrate.py:1076-1079, 1157-1165: time dtype and direction normalisation
+          R a = p.t0_arr ? p.t0_arr[idx] : p.t0;
+          R b = p.t1_arr ? p.t1_arr[idx] : p.t1;
+          direction = (a < b) ? R(1) : R(-1);
+          t0 = a * direction;
+          t1 = b * direction;
+#pragma unroll
+          for (int c = 0; c < D; ++c) y[c] = p.y0[idx * D + c];
+          // controller init: pid.py:316-392 (dt0=None -> 0.01) / constant.py:30-55
+          R dt0 = p.has_dt0 ? p.dt0 * direction : R(0.01);
+          if (p.controller == DFX_CTRL_PID) {
+            if (p.has_dtmax) dt0 = jnp_min(dt0, p.dtmax);
+            if (p.has_dtmin) dt0 = jnp_max(dt0, p.dtmin);
+          } else {
+            const R dt0_up = Num<R>::from_bits(Num<R>::bits(dt0) + (dt0 > R(0) ? 1 : (dt0 < R(0) ? -1 : 1)));  // nextafter(dt0, +inf)
+            cs_num_steps = (int)ceil((double)((t1 - t0) / dt0_up));
+            cs_steps_completed = 1;
+          }
+          tprev = t0;
+          tnext = jnp_min(t0 + dt0, t1);  // _integrate.py:1265
+          t1_clip_floor = prev_n<R>(t1, 100);  // _integrate.py:320-322
+          pid_inv = R(1); pid_prev_inv = R(1); at_dtmin = false;
+          num_steps = 0; num_accepted = 0; result = DFX_RESULT_SUCCESSFUL;
+          save_index = 0; saveat_ts_index = 0; dense_index = 0;
+          if constexpr (SDE) bm.init(p.keys + 2 * idx, p.vbt);
+          if constexpr (FSAL) {
+            // runge_kutta.py:684-695: the first step evaluates stage 0 at (t0, y0); a rejected first
+            // step re-evaluates the same point, so computing it once here is value-identical.
+            Field::template eval<R>(fp, t0 * direction, y, f_fsal);
+          }
+          if constexpr (RICH) {
+            if (p.save_dense) p.dense_ts[idx * (long long)(p.max_steps + 1)] = t0;  // 324-327; dense_ts stays in normalised time (DenseInterpolation applies `direction`)
+            if (p.save_t0) {  // _integrate.py:329-341
+              p.ts_out[idx * (long long)p.out_size] = t0 * direction;
+#pragma unroll
+              for (int c = 0; c < D; ++c) p.ys_out[(idx * (long long)p.out_size) * D + c] = y[c];
+              save_index = 1;
+            }
+          }
+          active = true;
+        }
+      }
+    }
+    if (__all_sync(kFullMask, !active)) break;
+
+    // ---------------- one attempted step (all active lanes, same instruction stream) ----------------
+    bool finished = false;
+    if (active) {
+      const bool run = (tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL);  // 355-363, 685-687
+      if (run) {
+        const R st0 = tprev, st1 = tnext;
+        const R dt = st1 - st0;
+        R k[S][D];
+        R y1[D], yerr[D], f_last[D];
+        R W = R(0), H = R(0);
+        if constexpr (SDE) bm.increment(st0, st1, p.vbt, W, H);  // one Brownian query per step (runge_kutta.py:644, srk.py:390)
+
+        if constexpr (TAB) {
+          // ---- explicit RK step, runge_kutta.py:643-1203 ----
+          const R control = direction * dt;  // WrapTerm.contr (_term.py:742-745)
+          R yi[D], fi[D];
+          if constexpr (FSAL) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) k[0][c] = control * f_fsal[c];  // prod(f0), 695 & 771
+          } else {
+            Field::template eval<R>(fp, st0 * direction, y, fi);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              R kk = control * fi[c];
+              if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * W;  // MultiTerm.vf_prod (_term.py:711-722)
+              k[0][c] = kk;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < D; ++c) yi[c] = y[c];
+#pragma unroll
+          for (int i = 1; i < S; ++i) {  // rk_stage, 847-1069
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              R incr = R(0);
+#pragma unroll
+              for (int j = 0; j < i; ++j)
+                if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];  // vector_tree_dot (base.py:37-41); structural zeros skipped
+              yi[c] = y[c] + incr;  // 871
+            }
+            const R ti = (Solver::hC(i) == 1.0) ? st1 : st0 + Solver::template c<R>(i) * dt;  // 1023
+            Field::template eval<R>(fp, ti * direction, yi, fi);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              R kk = control * fi[c];
+              if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, ti) * W;
+              k[i][c] = kk;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < D; ++c) f_last[c] = fi[c];
+          if constexpr (Solver::kSsal) {  // 1161
+#pragma unroll
+            for (int c = 0; c < D; ++c) y1[c] = yi[c];
+          } else {  // 1177-1185
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              R incr = R(0);
+#pragma unroll
+              for (int j = 0; j < S; ++j)
+                if (Solver::hBsol(j) != 0.0) incr += Solver::template b_sol<R>(j) * k[j][c];
+              y1[c] = y[c] + incr;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < D; ++c) {  // 1186-1193
+            R e = R(0);
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+              if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
+            yerr[c] = e;
+          }
+        } else if constexpr (Solver::kId == DFX_EULER) {
+          // ---- euler.py:46-59 ----
+          R f0[D];
+          Field::template eval<R>(fp, st0 * direction, y, f0);
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            R kk = (direction * dt) * f0[c];
+            if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * W;
+            k[0][c] = kk;
+            y1[c] = y[c] + kk;
+            yerr[c] = R(0);
+            f_last[c] = R(0);
+          }
+        } else {
+          // ---- ShARK: srk.py:335-671 additive-noise branch with shark.py:10-30 ----
+          if constexpr (SDE) {
+            const R h = dt;
+            const R g0 = Field::template diffusion<R>(fp, st0), g1 = Field::template diffusion<R>(fp, st1);
+            const R g_delta = R(0.5) * (g1 - g0);
+            const R w_kg = g0 * W, h_kg = g0 * H;  // 441-447
+            R z[D], fz[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) z[c] = y[c] + R(0) + (R(kSharkAW0) * w_kg + R(kSharkAH0) * h_kg);  // stage 0: 545
+            Field::template eval<R>(fp, st0, z, fz);  // 548: t0 + 0*h
+#pragma unroll
+            for (int c = 0; c < D; ++c) k[0][c] = h * fz[c];
+#pragma unroll
+            for (int c = 0; c < D; ++c) z[c] = y[c] + R(kSharkA10) * k[0][c] + (R(kSharkAW1) * w_kg + R(kSharkAH1) * h_kg);
+            Field::template eval<R>(fp, st0 + R(kSharkC1) * h, z, fz);
+#pragma unroll
+            for (int c = 0; c < D; ++c) k[1][c] = h * fz[c];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              R diffusion_result = R(kSharkBW) * w_kg + R(kSharkBH) * h_kg;   // 603-607
+              diffusion_result = diffusion_result + g_delta * (W - R(2.0) * H);  // 612-618
+              yerr[c] = R(kSharkE0) * k[0][c] + R(kSharkE1) * k[1][c];        // 638-639, 663
+              const R drift_result = R(kSharkB0) * k[0][c] + R(kSharkB1) * k[1][c];  // 667
+              y1[c] = y[c] + drift_result + diffusion_result;                  // 669
+              f_last[c] = R(0);
+            }
+          }
+        }
+
+        // ---- step-size controller ----
+        bool keep;
+        R next_t0, next_t1;
+        if (p.controller == DFX_CTRL_PID) {
+          // pid.py:394-567.  y_error NaN -> inf first (_integrate.py:386).
+          bool nan_any = false;
+#pragma unroll
+          for (int c = 0; c < D; ++c) nan_any |= r_isnan(y1[c]);
+          R ss = R(0), sc0 = R(0);
+#pragma unroll
+          for (int c = 0; c < D; ++c) {  // _scale, 483-490
+            const R e = r_isnan(yerr[c]) ? Num<R>::inf() : yerr[c];
+            const R yc = nan_any ? y[c] : y1[c];
+            const R yy = r_max(r_abs(y[c]), r_abs(yc));
+            const R sc = e / (p.atol + yy * p.rtol);
+            ss += sc * sc;
+            sc0 = sc;
+          }
+          const R scaled_error = (D == 1) ? r_abs(sc0) : r_sqrt(ss) / sqrt_d;  // optx.rms_norm
+          keep = scaled_error < R(1);                     // 493
+          if (p.has_dtmin) keep = keep || at_dtmin;       // 495-496
+          R inv = R(1) / scaled_error;                    // 498
+          R factor = p.safety;
+          if (p.use_c1) factor = factor * r_pow(inv, p.coeff1);          // 515
+          if (p.use_c2) factor = factor * r_pow(pid_inv, p.coeff2);      // 516
+          if (p.use_c3) factor = factor * r_pow(pid_prev_inv, p.coeff3); // 517
+          const R fmin = keep ? R(1) : p.factormin;       // 518
+          const R fmax = keep ? p.factormax : p.safety;   // 520
+          factor = jnp_min(jnp_max(factor, fmin), fmax);  // 521-525
+          R dtn = dt * factor;                            // 531
+          if (inv == R(0) || r_isinf(inv)) inv = R(1);    // 537-538
+          if (p.has_dtmax) dtn = jnp_min(dtn, p.dtmax);   // 545-546
+          if (p.has_dtmin) {                              // 547-555
+            if (!p.force_dtmin && dtn < p.dtmin && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_DT_MIN_REACHED;
+            if (at_dtmin && factor == R(1)) dtn = p.dtmin;
+            at_dtmin = dtn <= p.dtmin;
+            dtn = jnp_max(dtn, p.dtmin);
+          }
+          next_t0 = keep ? st1 : st0;                     // 557-558
+          next_t1 = next_t0 + dtn;
+          if (keep) { pid_prev_inv = pid_inv; pid_inv = inv; }  // 560-564
+        } else {
+          // constant.py:57-104
+          keep = true;
+          cs_steps_completed += 1;
+          R t1n = t0 + (t1 - t0) * ((R)cs_steps_completed / (R)cs_num_steps);
+          if (cs_steps_completed == cs_num_steps) t1n = t1;
+          next_t0 = st1;
+          next_t1 = t1n;
+        }
+
+        // ---- book-keeping, _integrate.py:412-437 ----
+        const R tprev_new = jnp_min(next_t0, t1);
+        R tnext_new = next_t1;
+        if (next_t1 > t1_clip_floor) tnext_new = keep ? t1 : tprev_new + R(0.5) * (t1 - tprev_new);  // 278-284
+        num_steps += 1;
+        num_accepted += keep ? 1 : 0;
+
+        if constexpr (RICH) {
+          // ---- SaveAt(ts): interpolant on the attempted interval, kept steps only (456-487) ----
+          if (p.save_ts != nullptr && keep) {
+            while (saveat_ts_index < p.n_save_ts) {
+              const R tq = p.save_ts[saveat_ts_index] * direction;
+              if (!(tq <= st1)) break;
+              R yq[D];
+              interp_eval<INTERP, R, S, D>(st0, st1, y, y1, k, tq, yq);
+              const long long o = idx * (long long)p.out_size + save_index;
+              p.ts_out[o] = tq * direction;  // final ts *= direction (1479-1482)
+#pragma unroll
+              for (int c = 0; c < D; ++c) p.ys_out[o * D + c] = yq[c];
+              saveat_ts_index += 1;
+              save_index += 1;
+            }
+          }
+          // ---- SaveAt(steps=n) (493-524) ----
+          if (p.save_steps != 0 && keep && (num_accepted % p.save_steps) == 0) {
+            const long long o = idx * (long long)p.out_size + save_index;
+            p.ts_out[o] = tprev_new * direction;
+#pragma unroll
+            for (int c = 0; c < D; ++c) p.ys_out[o * D + c] = y1[c];
+            save_index += 1;
+          }
+          // ---- SaveAt(dense=True) (529-540) ----
+          if (p.save_dense && keep) {
+            const long long row = idx * (long long)p.max_steps + dense_index;
+            st_cs(&p.dense_ts[idx * (long long)(p.max_steps + 1) + dense_index + 1], tprev_new);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              st_cs(&p.dense_y0[row * D + c], y[c]);
+              st_cs(&p.dense_y1[row * D + c], y1[c]);
+            }
+            if constexpr (DENSE_K) {
+              if (p.dense_k != nullptr) {
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+#pragma unroll
+                  for (int c = 0; c < D; ++c) st_cs(&p.dense_k[(row * S + j) * D + c], k[j][c]);
+              }
+            }
+            dense_index += 1;
+          }
+        }
+
+        // keep-or-restore (422-424)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          y[c] = keep ? y1[c] : y[c];
+          if constexpr (FSAL) f_fsal[c] = keep ? f_last[c] : f_fsal[c];
+        }
+        tprev = tprev_new;
+        tnext = tnext_new;
+      }
+      finished = !((tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL));
+    }
+
+    // ---------------- finalize finished lanes ----------------
+    if (active && finished) {
+      if constexpr (RICH) {
+        if (t0 == t1 && p.save_ts != nullptr) {  // _integrate.py:823-845
+          for (int i = 0; i < p.n_save_ts; ++i) {
+            const long long o = idx * (long long)p.out_size + save_index;
+            p.ts_out[o] = t0 * direction;
+#pragma unroll
+            for (int c = 0; c < D; ++c) p.ys_out[o * D + c] = y[c];
+            save_index += 1;
+          }
+        }
+      }
+      if (p.save_t1) {  // _integrate.py:847-877
+        bool via_steps = false;
+        if (p.save_steps == 1) via_steps = true;
+        else if (p.save_steps > 1) via_steps = (num_accepted % p.save_steps) == 0;
+        if (!via_steps) {
+          const long long o = idx * (long long)p.out_size + save_index;
+          p.ts_out[o] = tprev * direction;
+#pragma unroll
+          for (int c = 0; c < D; ++c) p.ys_out[o * D + c] = y[c];
+          save_index += 1;
+        }
+      }
+      if ((tprev < t1) && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_MAX_STEPS_REACHED;  // 883
+      p.stats[idx * 3 + 0] = num_steps;
+      p.stats[idx * 3 + 1] = num_accepted;
+      p.stats[idx * 3 + 2] = num_steps - num_accepted;
+      p.result[idx] = result;
+      if (p.save_count) p.save_count[idx] = save_index;
+      if (p.dense_count) p.dense_count[idx] = dense_index;
+      if (p.y_final) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) p.y_final[idx * D + c] = y[c];
+      }
+      if (p.t_final) p.t_final[idx] = tprev * direction;
+      active = false;
+    }
+  }
+}
+
+// Pads the unused tail of the saved outputs with +inf (the reference pre-fills whole buffers,
+// _integrate.py:1296-1300, 1320-1322; writing only the tails touches every byte once).
+// One warp per trajectory row -> coalesced stores.
+template <class R>
+__global__ void pad_tail_kernel(R *buf, const int *count, long long n_rows, long long row_len, int per_item, int count_offset) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < n_rows; r += nwarps) {
+    const long long start = ((long long)count[r] + count_offset) * per_item;
+    R *row = buf + r * row_len;
+    for (long long i = start + lane; i < row_len; i += 32) st_cs(&row[i], Num<R>::inf());
+  }
+}
+
+}  // namespace dfx

@@ -1,0 +1,6 @@
+// inst_lv.cu - kernel instantiations + registry entries (one TU per field so nvcc runs in parallel)
+#include "launch.cuh"
+namespace {
+using F0 = ::dfx::LotkaVolterraField;
+DFX_REGISTER_ODE_FIELD(F0)
+}  // namespace

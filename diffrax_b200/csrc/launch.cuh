@@ -1,0 +1,195 @@
+// launch.cuh - host-side launcher template for ensemble_kernel and the launcher registry.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "ensemble_kernel.cuh"
+
+namespace dfx {
+
+// thread-local error string + launch counter (api.cu)
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+int register_builtin(int field_id, int dim, int solver_id, int dtype, int levy, dfx_launcher_fn fn);
+
+#define DFX_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      dfx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DFX_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+inline bool is_nan(double x) { return x != x; }
+
+// Fill the dtype-typed SolveParams from the descriptor.  Everything that the reference computes in
+// Python floats (error order, PID exponents) is computed here in double and rounded once.
+template <class R, class Solver>
+int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
+  std::memset(&p, 0, sizeof(p));
+  p.n_traj = d->n_traj;
+  p.y0 = (const R *)d->y0;
+  p.t0_arr = (const R *)d->t0_per_traj;
+  p.t1_arr = (const R *)d->t1_per_traj;
+  p.t0 = (R)d->t0;
+  p.t1 = (R)d->t1;
+  p.has_dt0 = !is_nan(d->dt0);
+  p.dt0 = p.has_dt0 ? (R)d->dt0 : (R)0;
+  p.controller = d->controller;
+  p.rtol = (R)d->rtol; p.atol = (R)d->atol; p.safety = (R)d->safety;
+  p.factormin = (R)d->factormin; p.factormax = (R)d->factormax;
+  p.has_dtmin = !is_nan(d->dtmin); p.has_dtmax = !is_nan(d->dtmax);
+  p.dtmin = p.has_dtmin ? (R)d->dtmin : (R)0;
+  p.dtmax = p.has_dtmax ? (R)d->dtmax : (R)0;
+  p.force_dtmin = d->force_dtmin;
+  // base.py:97-120: ODE -> order ; SDE -> strong_order + 0.5 (Euler/Heun 0.5, ShARK 1.5)
+  double error_order;
+  if (!is_nan(d->error_order)) error_order = d->error_order;
+  else if (sde) error_order = (Solver::kId == DFX_SHARK ? 1.5 : 0.5) + 0.5;
+  else error_order = (double)Solver::kOrder;
+  const double c1 = (d->icoeff + d->pcoeff + d->dcoeff) / error_order;  // pid.py:512-514
+  const double c2 = -(d->pcoeff + 2 * d->dcoeff) / error_order;
+  const double c3 = d->dcoeff / error_order;
+  p.coeff1 = (R)c1; p.coeff2 = (R)c2; p.coeff3 = (R)c3;
+  p.use_c1 = c1 != 0; p.use_c2 = c2 != 0; p.use_c3 = c3 != 0;
+  p.save_t0 = d->save_t0; p.save_t1 = d->save_t1; p.save_steps = d->save_steps; p.save_dense = d->save_dense;
+  p.save_ts = (const R *)d->save_ts;
+  p.n_save_ts = d->save_ts ? d->n_save_ts : 0;
+  p.max_steps = d->max_steps;
+  p.out_size = dfx_out_size(d);
+  p.ts_out = (R *)d->ts_out; p.ys_out = (R *)d->ys_out;
+  p.stats = d->stats; p.result = d->result; p.save_count = d->save_count;
+  p.dense_ts = (R *)d->dense_ts; p.dense_y0 = (R *)d->dense_y0; p.dense_y1 = (R *)d->dense_y1; p.dense_k = (R *)d->dense_k;
+  p.dense_count = d->dense_count;
+  p.y_final = (R *)d->y_final; p.t_final = (R *)d->t_final;
+  p.keys = d->bm_keys;
+  if (sde) {
+    p.vbt.t0 = d->bm_t0; p.vbt.t1 = d->bm_t1;
+    const double tol_n = d->bm_tol / (d->bm_t1 - d->bm_t0);  // tree.py:286
+    int depth = 0;
+    while (std::ldexp(1.0, -depth) > tol_n && depth < 1000) ++depth;  // tree.py:412
+    p.vbt.depth = depth;
+    p.vbt.levy = d->levy_area;
+    p.vbt.partitionable = d->threefry_partitionable;
+  }
+  return 0;
+}
+
+struct DeviceInfo { int sms; };
+int device_sm_count(int *sms);  // cached per device (api.cu)
+
+template <class R, class Field, class Solver, int LEVY, bool RICH>
+int launch_variant(const SolveParams<R> &p, const typename Field::template P<R> &fp, cudaStream_t stream) {
+  auto kern = ensemble_kernel<R, Field, Solver, LEVY, RICH>;
+  int sms = 0;
+  if (int rc = device_sm_count(&sms)) return rc;
+  int per_sm = 0;
+  DFX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
+  if (per_sm < 1) per_sm = 1;
+  // persistent grid: a whole number of CTAs per SM, but never more threads than trajectories
+  long long blocks = (long long)sms * per_sm;
+  const long long need = (p.n_traj + kBlockThreads - 1) / kBlockThreads;
+  if (blocks > need) blocks = need < 1 ? 1 : need;
+  kern<<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p, fp);
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <class R>
+int launch_pad(R *buf, const int *count, long long n_rows, long long row_len, int per_item, int count_offset,
+               cudaStream_t stream) {
+  if (!buf || n_rows == 0 || row_len == 0) return 0;
+  int sms = 0;
+  if (int rc = device_sm_count(&sms)) return rc;
+  long long warps_needed = n_rows;
+  long long blocks = (warps_needed * 32 + 255) / 256;
+  const long long cap = (long long)sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  pad_tail_kernel<R><<<(unsigned)blocks, 256, 0, stream>>>(buf, count, n_rows, row_len, per_item, count_offset);
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// The launcher bound into the registry for one (R, Field, Solver, LEVY) combination.
+template <class R, class Field, class Solver, int LEVY>
+int launch_solve(const dfx_solve_desc *d, void *stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  constexpr bool SDE = LEVY != DFX_LEVY_NONE;
+  SolveParams<R> p;
+  fill_params<R, Solver>(d, p, SDE);
+  if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
+  const auto fp = Field::template make<R>(d->field_params, d->n_field_params);
+  if (p.n_traj == 0) return 0;
+  const bool rich = d->save_t0 || d->save_ts || d->save_steps || d->save_dense;
+
+  // scratch: work-queue counter (+ save_count when the caller did not ask for it)
+  unsigned long long *counter = nullptr;
+  int *save_count = p.save_count;
+  const bool need_pad = rich && (d->save_ts || d->save_steps);
+  size_t scratch_bytes = 16 + ((need_pad && !save_count) ? sizeof(int) * (size_t)p.n_traj : 0);
+  char *scratch = nullptr;
+  DFX_CUDA_OK(cudaMallocAsync((void **)&scratch, scratch_bytes, stream));
+  DFX_CUDA_OK(cudaMemsetAsync(scratch, 0, 16, stream));
+  counter = (unsigned long long *)scratch;
+  if (need_pad && !save_count) save_count = (int *)(scratch + 16);
+  p.work_counter = counter;
+  p.save_count = save_count;
+
+  int rc;
+  if (rich) rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);
+  else rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
+  if (rc == 0 && need_pad) {
+    rc = launch_pad<R>(p.ts_out, save_count, p.n_traj, p.out_size, 1, 0, stream);
+    if (rc == 0) rc = launch_pad<R>(p.ys_out, save_count, p.n_traj, (long long)p.out_size * Field::kDim, Field::kDim, 0, stream);
+  }
+  if (rc == 0 && d->save_dense) {
+    const long long ms = p.max_steps;
+    rc = launch_pad<R>(p.dense_ts, p.dense_count, p.n_traj, ms + 1, 1, 1, stream);
+    if (rc == 0) rc = launch_pad<R>(p.dense_y0, p.dense_count, p.n_traj, ms * Field::kDim, Field::kDim, 0, stream);
+    if (rc == 0) rc = launch_pad<R>(p.dense_y1, p.dense_count, p.n_traj, ms * Field::kDim, Field::kDim, 0, stream);
+    if (rc == 0 && Solver::kInterp != kInterpLinear)
+      rc = launch_pad<R>(p.dense_k, p.dense_count, p.n_traj, ms * Solver::S * Field::kDim, Solver::S * Field::kDim, 0, stream);
+  }
+  cudaFreeAsync(scratch, stream);
+  return rc;
+}
+
+template <class R> struct DtypeOf;
+template <> struct DtypeOf<double> { static constexpr int value = DFX_F64; };
+template <> struct DtypeOf<float> { static constexpr int value = DFX_F32; };
+
+template <class R, class Field, class Solver, int LEVY>
+struct Registrar {
+  Registrar() { register_builtin(Field::kId, Field::kDim, Solver::kId, DtypeOf<R>::value, LEVY, &launch_solve<R, Field, Solver, LEVY>); }
+};
+
+#define DFX_CAT2(a, b) a##b
+#define DFX_CAT(a, b) DFX_CAT2(a, b)
+#define DFX_REGISTER(R, Field, Solver, LEVY) \
+  static ::dfx::Registrar<R, Field, Solver, LEVY> DFX_CAT(dfx_registrar_, __COUNTER__);
+
+// all explicit RK tableaux for an ODE field, both dtypes
+#define DFX_REGISTER_ODE_FIELD(Field)                     \
+  DFX_REGISTER(double, Field, ::dfx::Tsit5, 0)            \
+  DFX_REGISTER(double, Field, ::dfx::Dopri5, 0)           \
+  DFX_REGISTER(double, Field, ::dfx::Dopri8, 0)           \
+  DFX_REGISTER(double, Field, ::dfx::Heun, 0)             \
+  DFX_REGISTER(double, Field, ::dfx::Bosh3, 0)            \
+  DFX_REGISTER(double, Field, ::dfx::Midpoint, 0)         \
+  DFX_REGISTER(double, Field, ::dfx::Ralston, 0)          \
+  DFX_REGISTER(double, Field, ::dfx::EulerSolver, 0)      \
+  DFX_REGISTER(float, Field, ::dfx::Tsit5, 0)             \
+  DFX_REGISTER(float, Field, ::dfx::Dopri5, 0)            \
+  DFX_REGISTER(float, Field, ::dfx::Dopri8, 0)            \
+  DFX_REGISTER(float, Field, ::dfx::Heun, 0)              \
+  DFX_REGISTER(float, Field, ::dfx::Bosh3, 0)             \
+  DFX_REGISTER(float, Field, ::dfx::Midpoint, 0)          \
+  DFX_REGISTER(float, Field, ::dfx::Ralston, 0)           \
+  DFX_REGISTER(float, Field, ::dfx::EulerSolver, 0)
+
+}  // namespace dfx

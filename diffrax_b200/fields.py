@@ -1,0 +1,118 @@
+"""Handles for the registered device functors (csrc/fields.cuh).
+
+A handle stands where the reference takes a Python callable ``vector_field(t, y, args)``
+(diffrax/_term.py:174-211): ``ODETerm(fields.Lorenz(10., 28., 8/3))``.  The numeric arguments
+are what ``args`` / closed-over Python floats are in the reference; they are rounded once to
+the working dtype on the host (JAX weak typing).  SDE functors expose ``.drift`` and
+``.diffusion`` for ``MultiTerm(ODETerm(f.drift), ControlTerm(f.diffusion, bm))``.
+"""
+from __future__ import annotations
+
+from . import _lib
+
+
+class FieldPart:
+    def __init__(self, field, part):
+        self.field, self.part = field, part
+
+
+class Field:
+    name = ""
+    dim = 0          # 0 == any (templated on y0's last dimension)
+    is_sde = False
+
+    @property
+    def field_id(self):
+        return _lib.FIELD_IDS[self.name]
+
+    @property
+    def drift(self):
+        return FieldPart(self, "drift")
+
+    @property
+    def diffusion(self):
+        if not self.is_sde:
+            raise AttributeError(f"{type(self).__name__} has no diffusion")
+        return FieldPart(self, "diffusion")
+
+    def params(self):
+        return []
+
+    def weights(self, xp, dtype):
+        return None
+
+
+class LinearDecay(Field):
+    """dy/dt = -lam * y  (test/test_integrate.py:60, test_saveat_solution.py:29-41); d in {1,2,3}."""
+    name = "decay"
+
+    def __init__(self, lam=1.0):
+        self.lam = float(lam)
+
+    def params(self):
+        return [self.lam]
+
+
+class LotkaVolterra(Field):
+    """benchmarks/lotka_volterra.py:13-20: [a x + b x y, c y + d x y]."""
+    name, dim = "lotka_volterra", 2
+
+    def __init__(self, a=1.5, b=-1.0, c=-3.0, d=1.0):
+        self.p = [float(a), float(b), float(c), float(d)]
+
+    def params(self):
+        return self.p
+
+
+class Lorenz(Field):
+    """Lorenz-63: [sigma (y-x), x (rho - z) - y, x y - beta z]."""
+    name, dim = "lorenz", 3
+
+    def __init__(self, sigma=10.0, rho=28.0, beta=8.0 / 3.0):
+        self.p = [float(sigma), float(rho), float(beta)]
+
+    def params(self):
+        return self.p
+
+
+class CR3BP(Field):
+    """Planar circular restricted three-body problem, rotating frame, state (x, y, vx, vy)."""
+    name, dim = "cr3bp", 4
+
+    def __init__(self, mu=0.012277471):
+        self.mu = float(mu)
+
+    def params(self):
+        return [self.mu]
+
+
+class ForcedOscillator(Field):
+    """y0' = y1, y1' = -w0^2 y0 + A sin(w t)."""
+    name, dim = "forced_osc", 2
+
+    def __init__(self, w0sq=1.0, amp=1.0, w=2.0):
+        self.p = [float(w0sq), float(amp), float(w)]
+
+    def params(self):
+        return self.p
+
+
+class VanDerPol(Field):
+    name, dim = "vdp", 2
+
+    def __init__(self, mu=1.0):
+        self.mu = float(mu)
+
+    def params(self):
+        return [self.mu]
+
+
+class OrnsteinUhlenbeck(Field):
+    """dy = theta (mu - y) dt + sigma dW (additive scalar noise)."""
+    name, dim, is_sde = "ou", 1, True
+
+    def __init__(self, theta=1.0, mu=0.0, sigma=0.5):
+        self.p = [float(theta), float(mu), float(sigma)]
+
+    def params(self):
+        return self.p

@@ -1,0 +1,185 @@
+/* diffrax_b200.h - C ABI of the B200-native ensemble integrator.
+ *
+ * The reference (patrick-kidger/diffrax, pure Python on JAX) has NO native boundary for
+ * this path: the only entry is the Python call
+ *     diffeqsolve(terms, solver, t0, t1, dt0, y0, args, *, saveat, stepsize_controller,
+ *                 max_steps, throw, ...) -> Solution            (diffrax/_integrate.py:890-911)
+ * invoked under jax.vmap (test/test_vmap.py:28-39).  BASELINE.json's north star prescribes
+ * the boundary: a jax.ffi custom call behind that same Python signature.  Each entry point
+ * below is what such an FFI handler binds; the file:line beside it is the reference code
+ * whose work it replaces.  INTEGRATION.md shows the jax.ffi / ctypes stubs.
+ *
+ * Conventions
+ *  - plain C types only; every buffer is caller-owned; device entry points take device
+ *    pointers and a cudaStream_t (as void*), enqueue on that stream and never synchronise
+ *    the device; `_host` entry points take host pointers and do the H2D / D2H themselves.
+ *  - reentrant: no mutable globals except the launcher registry (guarded) and the
+ *    thread-local error string.
+ *  - return 0 on success, a negative DFX_ERR_* on argument / launch errors.  Numerical
+ *    failures are per-trajectory `result` codes (diffrax/_solution.py:13-31).
+ *  - layouts are C-contiguous with the trajectory index first, i.e. exactly what
+ *    jax.vmap(diffeqsolve) returns: ts[N,T], ys[N,T,d], stats[N,3].
+ */
+#ifndef DIFFRAX_B200_H
+#define DIFFRAX_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFX_ABI_VERSION 1
+
+enum dfx_dtype { DFX_F64 = 0, DFX_F32 = 1 };
+
+/* Solvers: diffrax/_solver/{tsit5,dopri5,dopri8,heun,bosh3,midpoint,ralston,euler,shark}.py */
+enum dfx_solver { DFX_TSIT5 = 0, DFX_DOPRI5 = 1, DFX_DOPRI8 = 2, DFX_HEUN = 3, DFX_BOSH3 = 4,
+                  DFX_MIDPOINT = 5, DFX_RALSTON = 6, DFX_EULER = 7, DFX_SHARK = 8 };
+
+/* Step size controllers: _step_size_controller/constant.py:20-104, pid.py:299-567 */
+enum dfx_controller { DFX_CTRL_CONSTANT = 0, DFX_CTRL_PID = 1 };
+
+/* Built-in registered vector-field functors (diffrax_b200/csrc/fields.cuh).
+ * User functors register further ids >= DFX_FIELD_USER with dfx_register_launcher. */
+enum dfx_field { DFX_FIELD_DECAY = 0, DFX_FIELD_LOTKA_VOLTERRA = 1, DFX_FIELD_LORENZ = 2,
+                 DFX_FIELD_CR3BP = 3, DFX_FIELD_MLP = 4, DFX_FIELD_OU = 5,
+                 DFX_FIELD_FORCED_OSC = 6, DFX_FIELD_VDP = 7, DFX_FIELD_USER = 1000 };
+
+/* VirtualBrownianTree(levy_area=...) (_brownian/tree.py:238-254) */
+enum dfx_levy { DFX_LEVY_NONE = 0, DFX_LEVY_BROWNIAN_INCREMENT = 1, DFX_LEVY_SPACE_TIME = 2 };
+
+/* RESULTS (_solution.py:13-31).  successful == 0 is the only value the reference pins
+ * (test/test_saveat_solution.py:21). */
+enum dfx_result { DFX_RESULT_SUCCESSFUL = 0, DFX_RESULT_MAX_STEPS_REACHED = 1,
+                  DFX_RESULT_DT_MIN_REACHED = 2 };
+
+enum dfx_error { DFX_OK = 0, DFX_ERR_BAD_ARGUMENT = -1, DFX_ERR_UNSUPPORTED = -2,
+                 DFX_ERR_CUDA = -3, DFX_ERR_NO_DEVICE = -4 };
+
+/* One vmapped diffeqsolve call.  Field-by-field mirror of the reference arguments. */
+typedef struct dfx_solve_desc {
+  uint32_t struct_size;       /* sizeof(dfx_solve_desc), for ABI evolution */
+  uint32_t abi_version;       /* DFX_ABI_VERSION */
+
+  /* terms: ODETerm(field) or MultiTerm(ODETerm(drift), ControlTerm(diffusion, VBT))
+   * (_term.py:174-226, 271-555, 666-731) */
+  int32_t field_id;           /* registered functor */
+  int32_t dim;                /* state dimension d */
+  int32_t dtype;              /* dfx_dtype: state == time dtype (_integrate.py:1060-1099) */
+  int32_t solver_id;          /* dfx_solver */
+  const double *field_params; /* HOST pointer, n_field_params doubles (Python-float args) */
+  int32_t n_field_params;
+  const void *field_weights;  /* DEVICE (or host for *_host) pointer to large parameters (MLP weights), dtype-typed */
+  int64_t n_field_weights;
+
+  /* batch and integration region; per-trajectory t0/t1 arrays are optional
+   * ("vmappable everything, including the region of integration", README.md:10) */
+  int64_t n_traj;
+  const void *y0;             /* [N, d] */
+  double t0, t1;
+  const void *t0_per_traj;    /* [N] or NULL */
+  const void *t1_per_traj;    /* [N] or NULL */
+  double dt0;                 /* NaN == None (pid.py:328-340 -> 0.01 through diffeqsolve) */
+
+  /* stepsize_controller */
+  int32_t controller;         /* dfx_controller */
+  double rtol, atol, pcoeff, icoeff, dcoeff, safety, factormin, factormax; /* pid.py:299-310 */
+  double dtmin, dtmax;        /* NaN == None */
+  int32_t force_dtmin;
+  double error_order;         /* NaN == solver.error_order(terms) (base.py:97-120) */
+
+  /* saveat (_saveat.py:22-26, 72-76) and max_steps (_integrate.py:904) */
+  int32_t save_t0, save_t1, save_steps, save_dense;
+  const void *save_ts;        /* [T] in the time dtype, or NULL */
+  int32_t n_save_ts;
+  int32_t max_steps;
+
+  /* outputs; T_out = dfx_out_size(desc) (_integrate.py:1273-1293).  Unused slots are +inf
+   * (_integrate.py:1296-1300 followed by ts * direction at 1480-1482). */
+  void *ts_out;               /* [N, T_out] or NULL when T_out == 0 */
+  void *ys_out;               /* [N, T_out, d] */
+  int32_t *stats;             /* [N, 3] num_steps, num_accepted_steps, num_rejected_steps (1518-1524) */
+  int32_t *result;            /* [N] dfx_result */
+  int32_t *save_count;        /* [N] filled output slots, or NULL */
+  /* SaveAt(dense=True): DenseInterpolation(ts, infos) (_integrate.py:1315-1323, 529-540) */
+  void *dense_ts;             /* [N, max_steps+1] */
+  void *dense_y0;             /* [N, max_steps, d] */
+  void *dense_y1;             /* [N, max_steps, d] */
+  void *dense_k;              /* [N, max_steps, s, d]; NULL for two-point interpolants (Euler, ShARK) */
+  int32_t *dense_count;       /* [N] accepted steps stored (ts_size - 1) */
+  /* final state (Solution.ys[-1] for SaveAt(t1=True) duplicates this; kept for multi-GPU gathers) */
+  void *y_final;              /* [N, d] or NULL */
+  void *t_final;              /* [N] or NULL */
+
+  /* VirtualBrownianTree(t0, t1, tol, shape=(), key, levy_area) per trajectory (tree.py:245-301) */
+  int32_t levy_area;          /* dfx_levy; DFX_LEVY_NONE for ODEs */
+  const uint32_t *bm_keys;    /* [N, 2] the keys the user passed to VirtualBrownianTree */
+  double bm_t0, bm_t1, bm_tol;
+  int32_t threefry_partitionable; /* jax_threefry_partitionable (default True since JAX 0.5) */
+} dfx_solve_desc;
+
+/* ---- library ---- */
+int dfx_abi_version(void);
+const char *dfx_last_error(void);          /* thread-local message for the last negative return */
+int dfx_device_count(void);                /* 0 when no CUDA device / driver */
+
+/* ---- registry introspection ---- */
+int dfx_num_stages(int solver_id);         /* ButcherTableau.num_stages (runge_kutta.py:164) */
+int dfx_solver_order(int solver_id);       /* solver.order(terms) */
+int dfx_field_dim(int field_id);           /* fixed dim of a registered functor, 0 = any */
+int dfx_has_kernel(int field_id, int dim, int solver_id, int dtype, int levy_area);
+
+/* replaces _allocate_output (_integrate.py:1273-1293): number of output slots T_out */
+int dfx_out_size(const dfx_solve_desc *desc);
+
+/* replaces jax.vmap(diffeqsolve) forward pass (_integrate.py:888-1543 incl. loop 302-885,
+ * runge_kutta.py:446-1203, srk.py:335-671, pid.py:316-567, constant.py:30-104, interpolants,
+ * tree.py:326-773).  Device pointers; enqueues on `cuda_stream`. */
+int dfx_ensemble_solve(const dfx_solve_desc *desc, void *cuda_stream);
+
+/* same call with HOST buffers: copies inputs H2D, solves, copies outputs D2H, synchronises.
+ * `device` selects the CUDA device.  This is the end-to-end (`e2e`) path of bench.py. */
+int dfx_ensemble_solve_host(const dfx_solve_desc *desc, int device);
+
+/* replaces VirtualBrownianTree.evaluate(t0, t1, use_levy=True) vmapped over keys
+ * (tree.py:326-354).  ta/tb: [n] if per_traj_times else [1].  W, H: [n]; H may be NULL. */
+int dfx_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, const uint32_t *keys,
+                     double bm_t0, double bm_t1, double bm_tol, const void *ta, const void *tb,
+                     int per_traj_times, void *W, void *H, void *cuda_stream);
+
+/* jax.random primitives the tree relies on, exposed for known-answer tests
+ * (jax/_src/prng.py threefry2x32 / split / random_bits+normal). */
+int dfx_threefry2x32(int64_t n, const uint32_t *keys /*[n,2]*/, const uint32_t *ctrs /*[n,2]*/,
+                     uint32_t *out /*[n,2]*/, void *cuda_stream);
+int dfx_random_split(int64_t n, const uint32_t *keys /*[n,2]*/, int num, int partitionable,
+                     uint32_t *out /*[n,num,2]*/, void *cuda_stream);
+int dfx_random_normal(int dtype, int64_t n, const uint32_t *keys /*[n,2]*/, int partitionable,
+                      void *out /*[n]*/, void *cuda_stream);
+
+/* replaces DenseInterpolation.evaluate vmapped (_global_interpolation.py:335-355):
+ * trajectory i is evaluated at tq[i, 0..nq).  out: [N, nq, d]. */
+int dfx_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps,
+                       const void *dense_ts, const void *dense_y0, const void *dense_y1,
+                       const void *dense_k, const int32_t *dense_count, double direction,
+                       const void *tq, int nq, void *out, void *cuda_stream);
+
+/* measured FMA-pipe peaks for the roofline denominators (dependent-free FMA chains);
+ * returns TFLOP/s (2 flop per FMA) or a negative dfx_error. */
+double dfx_measure_fma_peak(int dtype, int device);
+/* INT32 ALU peak (threefry-like add/rot/xor chain), Tera-ops/s */
+double dfx_measure_int_peak(int device);
+
+/* number of kernels this library launched on behalf of the calling thread since the last
+ * reset (bench.py's `gpu_launches`). */
+int64_t dfx_launch_count(void);
+void dfx_reset_launch_count(void);
+
+/* ---- user functor registration (see diffrax_b200/csrc/register_field.cuh) ---- */
+typedef int (*dfx_launcher_fn)(const dfx_solve_desc *desc, void *cuda_stream);
+int dfx_register_launcher(int field_id, int dim, int solver_id, int dtype, int levy_area,
+                          dfx_launcher_fn fn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFRAX_B200_H */
