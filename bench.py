@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the ensemble integrator (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c3|c5_heun|c5_shark]
+
+metric   accepted RK steps / s across the ensemble (whole job, all ranks)
+step     ONE pass of the hot path over one batch of synthetic input: a complete
+         `diffeqsolve` of the whole ensemble resident in HBM
+workload C2 (BASELINE.json configs[1]): Lorenz sigma=10 rho=28 beta=8/3, Dopri5,
+         PIDController(rtol=atol=1e-8), dt0=None, t in [0,2], SaveAt(t1=True), fp64,
+         2^20 trajectories PER GPU (weak scaling: the path shards by trajectory, no data-path
+         collective; NCCL only gathers final states / reduces statistics after the kernel)
+e2e      same metric through the public `diffrax_b200.diffeqsolve` call with HOST (pinned)
+         buffers: H2D of y0 and D2H of ys/ts/stats/result inside the timed region
+roofline FP64 FMA pipe: achieved = attempted steps x 316 flop / device time of
+         the ensemble kernel (CUDA events on the launch stream); peak = DFMA-chain
+         microbenchmark measured live (MEASURED_PEAKS.json has no FP64 figure)
+--impl reference  times the CPU restatement (oracle/, "port": the reference is pure Python on
+         JAX and jax is not installable here) on all host cores, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_ATTEMPTED_STEP = {"c2": 316, "c1": 228, "c3": 1536}
+
+
+def workload(name: str, n: int, seed_offset: int = 0):
+    """Synthetic inputs of SURVEY.md §8d (deterministic NumPy default_rng)."""
+    if name == "c2":
+        rng = np.random.default_rng(1 + seed_offset)
+        y0 = np.stack([rng.uniform(-15, 15, n), rng.uniform(-20, 20, n), rng.uniform(5, 45, n)], 1)
+        return dict(field="lorenz", params=[10.0, 28.0, 8.0 / 3.0], solver="dopri5", y0=y0, t0=0.0, t1=2.0, dt0=None,
+                    rtol=1e-8, atol=1e-8, dtype=np.float64, save_ts=None, controller="pid",
+                    label="C2 Lorenz/Dopri5/PID(1e-8,1e-8)/fp64/t in [0,2]/SaveAt(t1)")
+    if name == "c1":
+        rng = np.random.default_rng(0 + seed_offset)
+        y0 = rng.uniform(0.5, 2.0, (n, 2))
+        return dict(field="lotka_volterra", params=[1.5, -1.0, -3.0, 1.0], solver="tsit5", y0=y0, t0=0.0, t1=10.0,
+                    dt0=None, rtol=1e-6, atol=1e-6, dtype=np.float64, save_ts=np.linspace(0, 10, 100), controller="pid",
+                    label="C1 Lotka-Volterra/Tsit5/PID(1e-6,1e-6)/fp64/SaveAt(ts=100)")
+    raise ValueError(name)
+
+
+def _ours_objects(w):
+    import diffrax_b200 as dfx
+    F = {"lorenz": dfx.fields.Lorenz, "lotka_volterra": dfx.fields.LotkaVolterra}[w["field"]]
+    S = {"dopri5": dfx.Dopri5, "tsit5": dfx.Tsit5, "dopri8": dfx.Dopri8}[w["solver"]]
+    term = dfx.ODETerm(F(*w["params"]))
+    ctrl = dfx.PIDController(rtol=w["rtol"], atol=w["atol"])
+    saveat = dfx.SaveAt(t1=True) if w["save_ts"] is None else dfx.SaveAt(ts=w["save_ts"])
+    return dfx, term, S(), ctrl, saveat
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(w, sample: int, threads: int = 0):
+    """accepted steps / s of the oracle (CPU restatement) on `sample` trajectories."""
+    import oracle
+    y0 = w["y0"][:sample]
+    t = time.perf_counter()
+    o = oracle.solve(w["field"], y0, w["t0"], w["t1"], w["dt0"], solver=w["solver"], params=w["params"],
+                     rtol=w["rtol"], atol=w["atol"], dtype=w["dtype"], save_t1=w["save_ts"] is None,
+                     save_ts=w["save_ts"], num_threads=threads)
+    dt = time.perf_counter() - t
+    return float(o["stats"][:, 1].sum()) / dt, dt, oracle.hw_threads() if threads == 0 else threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  Diffrax itself needs
+    jax/equinox (absent, no network), so this is the oracle port on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args.workload, args.ref_sample)
+    for _ in range(args.warmup):
+        cpu_port_rate(w, min(args.ref_sample, 8192))
+    rates, times = [], []
+    cores = 1
+    for _ in range(args.steps):
+        r, dt, cores = cpu_port_rate(w, args.ref_sample)
+        rates.append(r); times.append(dt)
+    total_t = sum(times)
+    value = float(np.sum(np.array(rates) * np.array(times)) / total_t)
+    sample = f"{args.ref_sample} of the workload's trajectories per step (same seed/config), all host cores"
+    line = {"impl": "reference", "metric": "accepted_rk_steps_per_s", "value": value, "unit": "steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["label"], "trajectories_per_step": args.ref_sample},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from diffrax_b200 import _dist, _lib
+
+    rank, local, world = _dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+
+    n_local = args.trajectories
+    w = workload(args.workload, n_local, seed_offset=1000 * rank)
+    dfx, term, solver, ctrl, saveat = _ours_objects(w)
+    y0_dev = torch.tensor(w["y0"], device=dev)
+    y0_host = torch.tensor(w["y0"]).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # prepared call: descriptor + output buffers built once; each step is ONE C-ABI call
+    plan = dfx.prepare(term, solver, w["t0"], w["t1"], w["dt0"], y0_dev, saveat=saveat, stepsize_controller=ctrl)
+
+    def step_device():
+        return plan(throw=False)
+
+    def step_host():
+        return dfx.diffeqsolve(term, solver, w["t0"], w["t1"], w["dt0"], y0_host, saveat=saveat,
+                               stepsize_controller=ctrl, throw=False, device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also pays cudaMallocAsync pool growth, module load) ----
+    for _ in range(max(args.warmup, 3)):
+        sol = step_device()
+    torch.cuda.synchronize()
+    acc_local = int(sol.stats["num_accepted_steps"].sum())
+    att_local = int(sol.stats["num_steps"].sum())
+    failed_local = int((sol.result != 0).sum())
+
+    # ---- timed: K steps, per-step CUDA events on the launch stream, L2 flushed between steps ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    L.dfx_reset_launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    for e0, e1 in ev:
+        flush.fill_(1)  # L2 flush, outside the event pair
+        e0.record()
+        sol = step_device()
+        e1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = int(L.dfx_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)  # device time of the K solves
+
+    # ---- e2e: same K steps through the host-buffer call (H2D + D2H inside the timed region) ----
+    for _ in range(2):
+        sh = step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sh = step_host()
+        _ = int(sh.result[0])  # read the step's result on the host
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = y0_host.numel() * y0_host.element_size()
+    d2h = sum(int(t.numel() * t.element_size()) for t in (sh.ts, sh.ys, sh.result, sh.y_final, sh.t_final)) \
+        + 3 * int(sh.stats["num_steps"].numel()) * 4
+
+    # ---- max over ranks, totals over ranks ----
+    t_max = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([acc_local, att_local, failed_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        # the only communication of the path: gather final states + reduce statistics (not timed)
+        _ = _dist.gather_final_states(sol.y_final, n_local * world)
+    dev_ms_max, e2e_ms_max, wall_ms_max = (float(x) for x in t_max)
+    acc, att, failed = (int(x) for x in tot)
+
+    if rank == 0:
+        ms_per_step = dev_ms_max / args.steps
+        value = acc / (ms_per_step * 1e-3)
+        flop = FLOP_PER_ATTEMPTED_STEP.get(args.workload)
+        peak = float(L.dfx_measure_fma_peak(_lib.F64, local))  # TFLOP/s, live DFMA-chain microbenchmark
+        achieved = (att / world) * flop / (ms_per_step * 1e-3) / 1e12  # per-GPU: the kernel of ONE rank
+        cpu_rate, cpu_dt, cores = cpu_port_rate(w, args.cpu_sample)
+        line = {
+            "metric": "accepted_rk_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["label"], "trajectories_per_gpu": n_local, "trajectories_total": n_local * world,
+                       "accepted_steps_per_solve": acc, "attempted_steps_per_solve": att, "failed_trajectories": failed,
+                       "l2": "flushed between timed steps (256 MiB write outside the per-step CUDA-event pairs)",
+                       "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
+            "e2e": {"value": acc / (e2e_ms_max * 1e-3 / args.steps), "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fma_fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                         "peak_source": "dfx_measure_fma_peak: 8 independent DFMA chains/thread, 8 CTAs x 256 thr/SM, "
+                                        "measured in this run (MEASURED_PEAKS.json holds no FP64 FMA figure)",
+                         "flop_per_attempted_step": flop, "kernel": "ensemble_kernel<double,Lorenz,Dopri5,0,false>"},
+            "cpu_baseline": {"value": cpu_rate, "unit": "steps/s", "cores": cores, "kind": "port",
+                             "sample": f"first {args.cpu_sample} trajectories of rank 0's batch, oracle (C port), "
+                                       f"{cpu_dt:.2f} s"},
+            "clocks": clocks, "wall_ms_per_step_incl_flush_and_host": wall_ms_max / args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--trajectories", type=int, default=1 << 20, help="trajectories per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="trajectories of the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=1 << 16, help="trajectories per step of --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

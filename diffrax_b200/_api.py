@@ -319,6 +319,8 @@ class _TorchBackend(_Backend):
         return torch.as_tensor(x, dtype=dtype, device=self.device).contiguous()
 
     def empty(self, shape, dtype):
+        if self.device.type == "cpu" and torch.cuda.is_available():
+            return torch.empty(shape, dtype=dtype, pin_memory=True)  # host path: D2H straight into pinned memory
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     def ptr(self, a):
@@ -351,12 +353,16 @@ class DenseInterpolation:
     def __init__(self, solver, ts, ts_size, infos, direction, t0_if_trivial, y0_if_trivial, backend):
         self.solver = solver
         self.ts = ts                    # [N, max_steps+1] normalised time
-        self.ts_size = ts_size          # [N] = accepted steps + 1
+        self._count = ts_size           # [N] int32 accepted steps (ts_size - 1), filled by the solve
         self.infos = infos              # dict(y0, y1, k)
         self.direction = direction      # [N] or scalar +-1
         self.t0_if_trivial = t0_if_trivial
         self.y0_if_trivial = y0_if_trivial
         self._xp = backend
+
+    @property
+    def ts_size(self):
+        return self._count.to(torch.int64) + 1
 
     def evaluate(self, t0, t1=None, left=True):
         if t1 is not None:
@@ -375,14 +381,14 @@ class DenseInterpolation:
         tq = tq.contiguous()
         nq = tq.shape[1]
         out = xp.empty((n, nq, d), self.ts.dtype)
-        count = (self.ts_size - 1).to(torch.int32).contiguous()
+        count = self._count
         direction = float(self.direction)
         _lib.check(_lib.lib().dfx_dense_evaluate(
             xp.dtype_id(self.ts.dtype), self.solver.solver_id, n, d, msp1 - 1, xp.ptr(self.ts),
             xp.ptr(self.infos["y0"]), xp.ptr(self.infos["y1"]), xp.ptr(self.infos.get("k")), xp.ptr(count),
             direction, xp.ptr(tq), nq, xp.ptr(out), xp.stream()))
         # trivial (t0 == t1) case: evaluate(t0) == y0  (_global_interpolation.py:343-355)
-        trivial = (self.ts_size == 1)
+        trivial = (self._count == 0)
         if bool(trivial.any()):
             tt = tq * direction
             m = trivial[:, None] & (tt == self.t0_if_trivial[:, None])
@@ -407,6 +413,35 @@ def _parse_terms(terms):
     raise TypeError("terms must be ODETerm(...) or MultiTerm(ODETerm(...), ControlTerm(...))")
 
 
+class EnsembleSolve:
+    """A prepared ensemble solve: descriptor + caller-owned buffers, reusable across launches.
+
+    ``prepare(...)`` does all argument checking and buffer allocation once; calling the object
+    enqueues exactly one `dfx_ensemble_solve` (device buffers, current stream) or runs one
+    `dfx_ensemble_solve_host` (host buffers).  Output tensors are overwritten by every call.
+    """
+
+    def __init__(self):
+        self.desc = None
+        self._keep = []
+
+    def __call__(self, throw: bool = True) -> Solution:
+        xp = self._xp
+        L = _lib.lib()
+        if xp.device_ptrs:
+            with torch.cuda.device(self._device):
+                _lib.check(L.dfx_ensemble_solve(C.byref(self.desc), xp.stream()))
+        else:
+            _lib.check(L.dfx_ensemble_solve_host(C.byref(self.desc), int(self._host_device)))
+        sol = self._solution
+        if throw:
+            bad = (sol.result != RESULTS.successful)
+            if bool(bad.any()):
+                code = int(sol.result[bad][0])
+                raise RuntimeError(RESULTS._messages.get(code, f"solver failed with code {code}"))  # _integrate.py:1541-1542
+        return sol
+
+
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
                 stepsize_controller=None, max_steps: Optional[int] = 4096, throw: bool = True,
                 device: int = 0) -> Solution:
@@ -418,6 +453,13 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = N
     ``dfx_ensemble_solve_host`` which stages them to GPU ``device`` and back.
     ``t0`` / ``t1`` may be scalars or ``[N]`` arrays.
     """
+    return prepare(terms, solver, t0, t1, dt0, y0, args, saveat=saveat, stepsize_controller=stepsize_controller,
+                   max_steps=max_steps, device=device)(throw=throw)
+
+
+def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
+            stepsize_controller=None, max_steps: Optional[int] = 4096, device: int = 0) -> EnsembleSolve:
+    """Validate the arguments of a `diffeqsolve` call and allocate its outputs once."""
     if args is not None:
         raise ValueError("args must be None: functor parameters are bound when the functor is created")
     saveat = SaveAt(t1=True) if saveat is None else saveat
@@ -555,13 +597,6 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = N
         D.dense_ts, D.dense_y0, D.dense_y1 = xp.ptr(dense["ts"]), xp.ptr(dense["y0"]), xp.ptr(dense["y1"])
         D.dense_k, D.dense_count = xp.ptr(dense.get("k")), xp.ptr(dense["count"])
 
-    if xp.device_ptrs:
-        with torch.cuda.device(y0a.device):
-            _lib.check(L.dfx_ensemble_solve(C.byref(D), xp.stream()))
-    else:
-        _lib.check(L.dfx_ensemble_solve_host(C.byref(D), int(device)))
-    del keep_alive
-
     stats_d = {"num_steps": stats[:, 0], "num_accepted_steps": stats[:, 1], "num_rejected_steps": stats[:, 2],
                "max_steps": max_steps}
     interpolation = None
@@ -571,7 +606,7 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = N
         else:
             dirn = 1.0 if t0s < t1s else -1.0
         t0_norm = (t0arr if t0arr is not None else xp.as_real(t0s, n, rdt)) * dirn
-        interpolation = DenseInterpolation(solver, dense["ts"], dense["count"].to(torch.int64) + 1,
+        interpolation = DenseInterpolation(solver, dense["ts"], dense["count"],
                                            {k: v for k, v in dense.items() if k in ("y0", "y1", "k")},
                                            dirn, t0_norm, y0a, xp)
     elif dense is not None:
@@ -579,11 +614,12 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = N
     if scalar_state:
         ys_out = ys_out[..., 0]
         y_final = y_final[..., 0]
-    sol = Solution(t0=t0, t1=t1, ts=ts_out, ys=ys_out, interpolation=interpolation, stats=stats_d, result=result,
-                   y_final=y_final, t_final=t_final)
-    if throw:
-        bad = (result != RESULTS.successful)
-        if bool(bad.any()):
-            code = int(result[bad][0])
-            raise RuntimeError(RESULTS._messages.get(code, f"solver failed with code {code}"))  # _integrate.py:1541-1542
-    return sol
+    call = EnsembleSolve()
+    call.desc = D
+    call._keep = keep_alive + [ts_out, ys_out, stats, result, y_final, t_final, dense]
+    call._xp = xp
+    call._device = y0a.device if is_torch else None
+    call._host_device = device
+    call._solution = Solution(t0=t0, t1=t1, ts=ts_out, ys=ys_out, interpolation=interpolation, stats=stats_d,
+                              result=result, y_final=y_final, t_final=t_final)
+    return call

@@ -52,6 +52,12 @@ int device_sm_count(int *sms) {
   if (it == cache.end()) {
     int n = 0;
     DFX_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    // keep stream-ordered scratch cached in the default pool instead of returning it at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     it = cache.emplace(dev, n).first;
   }
   *sms = it->second;

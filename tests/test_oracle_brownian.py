@@ -1,0 +1,112 @@
+"""Pins the oracle's VirtualBrownianTree with the reference's own (statistical) Brownian tests:
+test_brownian.py:117-180 (increments ~ N(0, t1-t0), H ~ N(0, (t1-t0)/12), W _|_ H), 460-490
+(conditional statistics of the bridge), 679-695 (reverse-time antisymmetry) and the SDE strong
+order checks of test_sde1.py:17-94 / test_integrate.py:193-322."""
+import numpy as np
+import pytest
+from scipy import stats
+
+import oracle
+
+N = 60000  # the reference uses 600 000 vmapped keys; 60 000 keeps the CPU suite fast
+
+
+@pytest.fixture(scope="module")
+def keys():
+    return oracle.split(oracle.prng_key(1234), N)
+
+
+@pytest.mark.parametrize("levy", ["bi", "stla"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("interval", [(0.0, 3.0), (0.3, 2.2), (1.0, 1.0 + 2 ** -9)])
+def test_increment_statistics(keys, levy, dtype, interval):
+    ta, tb = interval
+    W, H = oracle.vbt_evaluate(keys, ta, tb, bm_t0=0.0, bm_t1=3.0, tol=2.0 ** -7, levy_area=levy, dtype=dtype)
+    dt = tb - ta
+    assert stats.kstest(W.astype(np.float64) / np.sqrt(dt), "norm").pvalue > 0.01
+    if levy == "stla":
+        assert stats.kstest(H.astype(np.float64) / np.sqrt(dt / 12), "norm").pvalue > 0.01
+        assert abs(np.mean(W.astype(np.float64) * H.astype(np.float64))) < 0.02 * dt   # test_brownian.py:176
+
+
+@pytest.mark.parametrize("levy", ["bi", "stla"])
+def test_chen_additivity_and_independence(keys, levy):
+    kw = dict(bm_t0=0.0, bm_t1=1.0, tol=2.0 ** -8, levy_area=levy)
+    W1, H1 = oracle.vbt_evaluate(keys, 0.0, 0.4, **kw)
+    W2, H2 = oracle.vbt_evaluate(keys, 0.4, 1.0, **kw)
+    W3, H3 = oracle.vbt_evaluate(keys, 0.0, 1.0, **kw)
+    assert np.max(np.abs(W1 + W2 - W3)) < 1e-14
+    assert abs(np.corrcoef(W1, W2)[0, 1]) < 0.02
+    if levy == "stla":
+        # Chen's relation for space-time Levy area over [s,u] = [s,t] U [t,u]
+        s, t, u = 0.0, 0.4, 1.0
+        H_chen = ((t - s) * H1 + (u - t) * H2 + 0.5 * ((u - t) * W1 - (t - s) * W2)) / (u - s)
+        assert np.max(np.abs(H_chen - H3)) < 1e-13
+
+
+def test_reverse_time_antisymmetry(keys):
+    # test_brownian.py:679-695: W(t1, t0) == -W(t0, t1)
+    W, _ = oracle.vbt_evaluate(keys[:1000], 0.2, 0.9, tol=2.0 ** -8)
+    Wr, _ = oracle.vbt_evaluate(keys[:1000], 0.9, 0.2, tol=2.0 ** -8)
+    assert np.array_equal(W, -Wr)
+
+
+def test_conditional_bridge_statistics(keys):
+    # test_brownian.py:460-490: W_r | W_s, W_u  ~ N(W_s + (r-s)/(u-s) (W_u - W_s), (r-s)(u-r)/(u-s))
+    s, r, u = 0.25, 0.40625, 0.5
+    Ws, _ = oracle.vbt_evaluate(keys, 0.0, s, tol=2.0 ** -6)
+    Wr, _ = oracle.vbt_evaluate(keys, 0.0, r, tol=2.0 ** -6)
+    Wu, _ = oracle.vbt_evaluate(keys, 0.0, u, tol=2.0 ** -6)
+    resid = Wr - (Ws + (r - s) / (u - s) * (Wu - Ws))
+    var = (r - s) * (u - r) / (u - s)
+    assert stats.kstest(resid / np.sqrt(var), "norm").pvalue > 0.01
+    assert abs(np.corrcoef(resid, Wu - Ws)[0, 1]) < 0.02
+
+
+def test_descent_key_selection_quirk():
+    """Going RIGHT (r > t_mid) continues with key_st, LEFT with key_tu (tree.py:431-432): re-derive W(1/4) by hand."""
+    k = oracle.prng_key(77)
+    leaf = oracle.split(k, 1)[0]
+    state, kw = oracle.split(leaf, 2)
+    W1 = oracle.normal(kw)
+    # level 0: interval [0,1], midpoint 1/2; r = 0.25 goes LEFT -> key_tu
+    key_st, mid, key_tu = oracle.split(state, 3)
+    w_half = 0.5 * W1 + (np.sqrt(1.0) / 2) * oracle.normal(mid)
+    # level 1: interval [0,1/2], midpoint 1/4; r = 0.25 is not > 0.25 -> LEFT again
+    key_st2, mid2, key_tu2 = oracle.split(key_tu, 3)
+    w_quarter = 0.5 * w_half + (np.sqrt(0.5) / 2) * oracle.normal(mid2)
+    # tol = 1/4 -> two levels; final interval [0, 1/4], sr = 1/4, ru = 0 -> bridge term vanishes
+    W, _ = oracle.vbt_evaluate(k[None], 0.0, 0.25, tol=0.25)
+    assert abs(W[0] - w_quarter) < 1e-15
+
+
+@pytest.mark.parametrize("solver,levy,order", [("euler", "bi", 1.0), ("heun", "bi", 1.0), ("shark", "stla", 1.5)])
+def test_sde_strong_order_additive_noise(solver, levy, order):
+    """OU (additive noise): Euler/Heun strong order 1 for additive noise, ShARK 1.5 (shark.py:57-64).
+    Reference = same Brownian paths at a much finer step (test/helpers.py:136-295 recipe)."""
+    nk = 200
+    keys = oracle.split(oracle.prng_key(99), nk)
+    kw = dict(params=[1.0, 0.0, 0.5], controller="constant", levy_area=levy, keys=keys, bm_tol=2.0 ** -14)
+    fine = oracle.solve("ou", np.ones((nk, 1)), 0.0, 1.0, 2.0 ** -11, solver="shark", max_steps=1 << 14,
+                        **{**kw, "levy_area": "stla"})["ys"][:, 0, 0]
+    if levy == "bi":  # a BrownianIncrement tree is a different path than the STLA tree: build its own fine reference
+        fine = oracle.solve("ou", np.ones((nk, 1)), 0.0, 1.0, 2.0 ** -11, solver="heun", max_steps=1 << 14, **kw)["ys"][:, 0, 0]
+    errs, dts = [], []
+    for k in range(2, 7):
+        dt = 2.0 ** -k
+        y = oracle.solve("ou", np.ones((nk, 1)), 0.0, 1.0, dt, solver=solver, **kw)["ys"][:, 0, 0]
+        errs.append(np.sqrt(np.mean((y - fine) ** 2))); dts.append(dt)
+    slope = np.polyfit(np.log(dts), np.log(errs), 1)[0]
+    assert slope > order - 0.35, (solver, slope, errs)
+
+
+def test_ou_moments():
+    n = 40000
+    keys = oracle.split(oracle.prng_key(5), n)
+    for solver, levy in (("heun", "bi"), ("shark", "stla")):
+        r = oracle.solve("ou", np.ones((n, 1)), 0.0, 1.0, 2.0 ** -6, solver=solver, params=[1.0, 0.0, 0.5],
+                         controller="constant", levy_area=levy, keys=keys, bm_tol=2.0 ** -8)
+        y = r["ys"][:, 0, 0]
+        assert abs(y.mean() - np.exp(-1)) < 4 * np.sqrt(0.108 / n) + 2e-3
+        assert abs(y.var() - 0.125 * (1 - np.exp(-2))) < 3e-3
+        assert np.all(r["stats"][:, 0] == 64)

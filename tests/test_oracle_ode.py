@@ -1,0 +1,190 @@
+"""Pins the oracle's ODE path against the anchors the reference's own tests use:
+analytic solutions (test_integrate.py:48-141, test_saveat_solution.py:24-195), convergence order
+(test_integrate.py:144-190), scipy DOP853 on DETEST-style problems (test_detest.py:390-469),
+SaveAt semantics (test_saveat_solution.py:116-180, 323-428), reverse time (test_integrate.py:325-413)."""
+import math
+
+import numpy as np
+import pytest
+from scipy.integrate import solve_ivp
+
+import oracle
+
+ADAPTIVE = ["tsit5", "dopri5", "dopri8", "heun", "bosh3", "midpoint", "ralston"]
+
+
+@pytest.mark.parametrize("solver", ADAPTIVE)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_basic_decay(solver, dtype):
+    # test_integrate.py:48-141: dy=-y, y(1) = y0/e within 1e-2
+    y0 = np.array([[2.1], [0.3]])
+    r = oracle.solve("decay", y0, 0.0, 1.0, 0.01, solver=solver, params=[1.0], dtype=dtype, rtol=1e-4, atol=1e-6)
+    assert np.all(r["result"] == 0)
+    assert np.allclose(r["ys"][:, 0, 0], y0[:, 0] / math.e, rtol=1e-2, atol=1e-2)
+    assert r["ys"].dtype == np.dtype(dtype)
+
+
+def test_saveat_ts_matches_analytic():
+    # test_saveat_solution.py:24-41, 97-114: dy=-0.5y, Dopri5, PID(1e-8,1e-8), dt0=None, ts=[0.5,0.8]
+    r = oracle.solve("decay", np.array([[2.1]]), 0.0, 1.0, None, solver="dopri5", params=[0.5], rtol=1e-8, atol=1e-8,
+                     save_t1=False, save_ts=[0.5, 0.8])
+    assert np.array_equal(r["ts"][0], [0.5, 0.8])
+    assert np.allclose(r["ys"][0, :, 0], 2.1 * np.exp(-0.5 * np.array([0.5, 0.8])), rtol=1e-5, atol=1e-8)
+    assert r["stats"][0, 0] > 0
+
+
+def test_saveat_steps_counts_and_padding():
+    # test_saveat_solution.py:116-180
+    kw = dict(solver="dopri5", params=[0.5], rtol=1e-8, atol=1e-8)
+    r = oracle.solve("decay", np.array([[2.1]]), 0.0, 1.0, None, save_t1=False, save_steps=1, **kw)
+    assert r["ts"].shape == (1, 4096) and r["ys"].shape == (1, 4096, 1)
+    n = r["stats"][0, 1]
+    assert np.all(np.isfinite(r["ts"][0, :n])) and np.all(r["ts"][0, n:] == np.inf) and np.all(r["ys"][0, n:] == np.inf)
+    assert r["ts"][0, n - 1] == 1.0
+    assert np.allclose(r["ys"][0, :n, 0], 2.1 * np.exp(-0.5 * r["ts"][0, :n]), rtol=1e-5, atol=1e-8)
+    r2 = oracle.solve("decay", np.array([[2.1]]), 0.0, 1.0, None, save_t1=False, save_steps=2, **kw)
+    assert r2["ts"].shape[1] == 4096 // 2
+    n2 = np.isfinite(r2["ts"][0]).sum()
+    assert n2 == n // 2 and np.array_equal(r2["ts"][0, :n2], r["ts"][0, 1:n:2])
+    r3 = oracle.solve("decay", np.array([[2.1]]), 0.0, 1.0, None, save_t1=True, save_steps=2, **kw)
+    assert r3["ts"].shape[1] == 4096 // 2        # max_steps % 2 == 0 -> no extra slot (1288-1293)
+    r4 = oracle.solve("decay", np.array([[2.1]]), 0.0, 1.0, None, save_t1=True, save_steps=3, **kw)
+    assert r4["ts"].shape[1] == 4096 // 3 + 1
+    n4 = np.isfinite(r4["ts"][0]).sum()
+    assert r4["ts"][0, n4 - 1] == 1.0 and n4 == n // 3 + (1 if n % 3 else 0)
+    r5 = oracle.solve("decay", np.array([[2.1]]), 0.0, 1.0, None, save_t0=True, save_t1=True, save_ts=[0.25, 0.75], **kw)
+    assert np.array_equal(r5["ts"][0], [0.0, 0.25, 0.75, 1.0])
+    assert r5["ys"][0, 0, 0] == 2.1
+
+
+def test_t0_equals_t1():
+    # test_saveat_solution.py:323-428: every requested output returns y0; per-lane under "vmap"
+    y0 = np.array([[2.1], [0.7]])
+    r = oracle.solve("decay", y0, 0.0, 0.0, 0.1, solver="tsit5", params=[1.0], rtol=1e-6, atol=1e-6,
+                     save_t0=True, save_t1=True, save_ts=[0.0, 0.0], t0_per_traj=[0.0, 0.0], t1_per_traj=[0.0, 1.0])
+    assert np.array_equal(r["ys"][0, :, 0], [2.1] * 4) and np.array_equal(r["ts"][0], [0.0] * 4)
+    assert r["stats"][0, 0] == 0 and r["stats"][1, 0] > 0
+    assert abs(r["ys"][1, -1, 0] - 0.7 / math.e) < 1e-5
+
+
+def test_reverse_time_equals_negated_field():
+    # test_integrate.py:325-413: solving backwards == solving the negated field forwards (ts negated, same ys)
+    y0 = np.array([[1.3, -0.4]])
+    ts = np.linspace(0.0, 2.0, 9)
+    fwd = oracle.solve("forced_osc", y0, 0.0, 2.0, None, solver="tsit5", params=[1.0, 0.0, 0.0], rtol=1e-8, atol=1e-8,
+                       save_ts=ts, save_t1=False)
+    # reverse: from t=0 down to t=-2 of y' = f  <=>  forward of y' = -f ; for the undamped oscillator -f is f with y1 -> -y1
+    rev = oracle.solve("forced_osc", y0 * [1, -1], 0.0, -2.0, None, solver="tsit5", params=[1.0, 0.0, 0.0],
+                       rtol=1e-8, atol=1e-8, save_ts=-ts, save_t1=False)
+    assert np.array_equal(rev["ts"][0], -ts)
+    assert np.allclose(rev["ys"][0] * [1, -1], fwd["ys"][0], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(rev["stats"], fwd["stats"])
+
+
+@pytest.mark.parametrize("solver,order", [("heun", 2), ("midpoint", 2), ("ralston", 2), ("bosh3", 3), ("dopri5", 5),
+                                            ("tsit5", 5), ("dopri8", 8), ("euler", 1)])
+def test_convergence_order(solver, order):
+    # test_integrate.py:144-190 recipe: fixed steps dt = 2^-k, slope of log error within +-0.9 of order
+    y0 = np.array([[1.0, 0.5]])
+    exact = solve_ivp(lambda t, y: [y[1], -y[0] + 0.7 * np.sin(2 * t)], (0, 2), y0[0], method="DOP853",
+                      rtol=1e-13, atol=1e-13).y[:, -1]
+    ks = range(2, 7) if order < 8 else range(0, 4)
+    errs, dts = [], []
+    for k in ks:
+        dt = 2.0 ** -k
+        r = oracle.solve("forced_osc", y0, 0.0, 2.0, dt, solver=solver, params=[1.0, 0.7, 2.0], controller="constant")
+        errs.append(np.linalg.norm(r["ys"][0, 0] - exact)); dts.append(dt)
+        assert r["stats"][0, 0] == round(2.0 / dt)
+    slope = np.polyfit(np.log(dts), np.log(errs), 1)[0]
+    assert abs(slope - order) < 0.9, (solver, slope, errs)
+
+
+# DETEST-style nonstiff problems (test_detest.py:40-300) through the generic callback field
+def _a1(t, y): return [-y[0]]
+def _a3(t, y): return [y[0] * np.cos(t)]
+def _a4(t, y): return [y[0] / 4 * (1 - y[0] / 20)]
+def _b1(t, y): return [2 * (y[0] - y[0] * y[1]), -(y[1] - y[0] * y[1])]     # test_detest.py:66-75 (Lotka-Volterra variant)
+def _b4(t, y):
+    r = np.sqrt(y[0] ** 2 + y[1] ** 2)
+    return [-y[1] - y[0] * y[2] / r, y[0] - y[1] * y[2] / r, y[0] / r]
+def _d1(t, y):                                                                # two-body orbit, eccentricity 0.1
+    r3 = (y[0] ** 2 + y[1] ** 2) ** 1.5
+    return [y[2], y[3], -y[0] / r3, -y[1] / r3]
+def _e2(t, y): return [y[1], (1 - y[0] ** 2) * y[1] - y[0]]                   # van der Pol
+
+DETEST = {"A1": (_a1, [1.0]), "A3": (_a3, [1.0]), "A4": (_a4, [1.0]), "B1": (_b1, [1.0, 3.0]),
+          "B4": (_b4, [3.0, 0.0, 0.0]), "D1": (_d1, [0.9, 0.0, 0.0, math.sqrt(1.1 / 0.9)]), "E2": (_e2, [2.0, 0.0])}
+
+
+@pytest.mark.parametrize("prob", list(DETEST))
+@pytest.mark.parametrize("solver", ["tsit5", "dopri5", "dopri8"])
+def test_detest_vs_scipy_dop853(prob, solver):
+    # test_detest.py:440-469: PID(1e-8,1e-8), dt0=None, max_steps=16**4, t in [0,20], DOP853 at 1e-8 -> within 4e-5
+    f, y0 = DETEST[prob]
+    ref = solve_ivp(f, (0, 20), y0, method="DOP853", rtol=1e-8, atol=1e-8).y[:, -1]
+    r = oracle.solve("callback", np.array([y0]), 0.0, 20.0, None, solver=solver, rtol=1e-8, atol=1e-8,
+                     max_steps=16 ** 4, callback=f)
+    assert r["result"][0] == 0
+    assert np.allclose(r["ys"][0, 0], ref, rtol=4e-5, atol=4e-5), (r["ys"][0, 0], ref)
+
+
+def test_builtin_fields_match_callback_definitions():
+    """Each registered field equals its textbook definition evaluated through the callback path, bit for bit."""
+    lor = lambda t, y: [10.0 * (y[1] - y[0]), y[0] * (28.0 - y[2]) - y[1], y[0] * y[1] - (8.0 / 3.0) * y[2]]
+    lv = lambda t, y: [1.5 * y[0] + (-1.0 * y[0]) * y[1], -3.0 * y[1] + (1.0 * y[0]) * y[1]]
+    vdp = lambda t, y: [y[1], 1.5 * (1 - y[0] * y[0]) * y[1] - y[0]]
+    for name, params, f, y0, t1 in (("lorenz", [10.0, 28.0, 8.0 / 3.0], lor, [1.0, 2.0, 20.0], 1.0),
+                                    ("lotka_volterra", [1.5, -1.0, -3.0, 1.0], lv, [1.0, 1.0], 5.0),
+                                    ("vdp", [1.5], vdp, [2.0, 0.0], 3.0)):
+        a = oracle.solve(name, np.array([y0]), 0.0, t1, None, solver="dopri5", params=params, rtol=1e-7, atol=1e-7)
+        b = oracle.solve("callback", np.array([y0]), 0.0, t1, None, solver="dopri5", rtol=1e-7, atol=1e-7, callback=f)
+        assert np.array_equal(a["ys"], b["ys"]) and np.array_equal(a["stats"], b["stats"])
+
+
+def test_initial_step_is_constant_001():
+    """through diffeqsolve, dt0=None means a first trial step of 0.01."""
+    r = oracle.solve("lorenz", np.array([[1.0, 2.0, 20.0]]), 0.0, 2.0, None, solver="dopri5", params=[10, 28, 8 / 3],
+                     rtol=1e-8, atol=1e-8, trace_traj=0)
+    assert r["trace"][0, 0] == 0.0 and r["trace"][0, 1] == 0.01
+    h = oracle.solve("lorenz", np.array([[1.0, 2.0, 20.0]]), 0.0, 2.0, None, solver="dopri5", params=[10, 28, 8 / 3],
+                     rtol=1e-8, atol=1e-8, trace_traj=0, hairer_initial_step=True)
+    assert h["trace"][0, 1] != 0.01 and np.allclose(h["ys"], r["ys"], rtol=1e-6)
+
+
+def test_pid_rejection_and_clipping_trace():
+    """A too-large dt0 is rejected with factor in [0.2, 0.9]; the last step lands exactly on t1 (App. A5)."""
+    r = oracle.solve("vdp", np.array([[2.0, 0.0]]), 0.0, 3.0, 1.0, solver="tsit5", params=[5.0], rtol=1e-6, atol=1e-6,
+                     trace_traj=0)
+    tr = r["trace"]
+    assert tr[0, 2] == 0.0                              # first attempt rejected
+    w0, w1 = tr[0, 1] - tr[0, 0], tr[1, 1] - tr[1, 0]
+    assert tr[1, 0] == tr[0, 0] and 0.2 * w0 - 1e-15 <= w1 <= 0.9 * w0 + 1e-15
+    assert tr[-1, 1] == 3.0 and tr[-1, 2] == 1.0
+    kept = tr[tr[:, 2] == 1.0]
+    assert np.all(kept[1:, 0] == kept[:-1, 1])          # accepted steps tile [t0, t1]
+    assert r["stats"][0, 0] == len(tr) and r["stats"][0, 1] == len(kept)
+
+
+def test_max_steps_reached_and_dtmin():
+    r = oracle.solve("lorenz", np.array([[1.0, 2.0, 20.0]]), 0.0, 50.0, None, solver="dopri5", params=[10, 28, 8 / 3],
+                     rtol=1e-8, atol=1e-8, max_steps=64)
+    assert r["result"][0] == 1 and r["stats"][0, 0] == 64 and r["t_final"][0] < 50.0
+    r = oracle.solve("vdp", np.array([[2.0, 0.0]]), 0.0, 3.0, 0.5, solver="tsit5", params=[50.0], rtol=1e-10, atol=1e-10,
+                     dtmin=1e-2, force_dtmin=False, max_steps=10000)
+    assert r["result"][0] == 2
+    r = oracle.solve("vdp", np.array([[2.0, 0.0]]), 0.0, 3.0, 0.5, solver="tsit5", params=[50.0], rtol=1e-10, atol=1e-10,
+                     dtmin=1e-2, force_dtmin=True, max_steps=10000)
+    assert r["result"][0] == 0 and r["t_final"][0] == 3.0
+
+
+def test_dense_interpolation_reproduces_knots_and_solution():
+    # test_global_interpolation.py:312-390: first point reproduces y0 EXACTLY; values within 1e-6 of exp(-t)
+    for solver in ("tsit5", "dopri5", "dopri8", "heun", "bosh3"):
+        r = oracle.solve("decay", np.array([[1.0], [0.5]]), 0.0, 1.0, 1e-2 if solver in ("heun", "bosh3") else 0.05,
+                         solver=solver, params=[1.0], controller="constant", save_dense=True, max_steps=256)
+        tq = np.tile(np.linspace(0, 1, 101), (2, 1))
+        ev = oracle.dense_evaluate(solver, r["dense"], tq)
+        assert np.array_equal(ev[:, 0, 0], [1.0, 0.5])
+        assert np.allclose(ev[:, :, 0], np.array([[1.0], [0.5]]) * np.exp(-tq), atol=1e-5 if solver in ("heun",) else 1e-6)
+        out = oracle.dense_evaluate(solver, r["dense"], np.array([[1.5], [-0.1]]))
+        assert np.all(np.isnan(out))                      # _nan_if_out_of_bounds
