@@ -110,6 +110,37 @@ template <class R> __device__ __forceinline__ R linear_rescale(R t0, R t, R t1) 
   return num / den;
 }
 
+// ---- fast, division-free building blocks for the PID controller's hot path ----
+// 1/d for positive normal d: MUFU.RCP64H seed (rel. err <= 2^-23) + two Newton steps -> ~1 ulp.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ float fast_rcp(float d) { return __frcp_rn(d); }
+
+template <int M> __device__ __forceinline__ double ipow(double z) {
+  if constexpr (M == 1) return z;
+  else if constexpr (M % 2 == 0) { const double h = ipow<M / 2>(z); return h * h; }
+  else return ipow<M - 1>(z) * z;
+}
+// q^(-1/M) for q in [1e-36, 1e36]: fp32 SFU seed (MUFU.LG2 / MUFU.EX2, rel. err ~1e-6) refined by two
+// steps of the division-free Newton iteration z <- z + z (1 - q z^M) / M (error e -> (M+1)/2 e^2),
+// i.e. ~1 ulp in fp64 at a cost of 2 (log2(M)+4) FP64 instructions instead of pow()'s ~100.
+template <int M> __device__ __forceinline__ double inv_root(double q) {
+  const float s = exp2f(__log2f((float)q) * (-1.0f / (float)M));
+  double z = (double)s;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double r = fma(-q, ipow<M>(z), 1.0);
+    z = fma(z * r, 1.0 / (double)M, z);
+  }
+  return z;
+}
+
 // streaming (evict-first) stores for write-once outputs
 __device__ __forceinline__ void st_cs(double *p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(float *p, float v) { __stcs(p, v); }

@@ -61,6 +61,7 @@ struct SolveParams {
   int has_dtmin, has_dtmax, force_dtmin;
   R coeff1, coeff2, coeff3;  // PID exponents (pid.py:512-514), computed in double on the host
   int use_c1, use_c2, use_c3;
+  int fast_pid;  // pcoeff == dcoeff == 0, icoeff == 1 and error_order == solver order: pure I-controller fast path
   int save_t0, save_t1, save_steps, save_dense;
   const R *save_ts;
   int n_save_ts, max_steps, out_size;
@@ -104,6 +105,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   constexpr bool FSAL = Solver::kFsal && !SDE;
   constexpr int INTERP = Solver::kInterp;
   constexpr bool DENSE_K = INTERP != kInterpLinear;
+  constexpr bool FAST_PID = TAB && !SDE && sizeof(R) == 8;  // fp64 ODE solves: division-/pow-free I-controller path
 
   // ---- per-lane trajectory state (registers) ----
   bool active = false, exhausted = false;
@@ -299,29 +301,61 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           bool nan_any = false;
 #pragma unroll
           for (int c = 0; c < D; ++c) nan_any |= r_isnan(y1[c]);
-          R ss = R(0), sc0 = R(0);
+          R dtn, inv = R(1), factor;
+          bool slow = true;
+          if constexpr (FAST_PID) {
+            // ---- fast path: pure I-controller (pcoeff = dcoeff = 0, icoeff = 1) at the solver's own order ----
+            // scaled_error = sqrt(ss / D), so   keep <=> ss < D   and   factor = safety * (ss/D)^(-1/(2 order)).
+            // No sqrt, no IEEE division, no pow(): reciprocals and the 2*order-th root are Newton-refined SFU seeds.
+            // Anything unusual (non-finite / extreme error, or ss within 1e-9 of the accept boundary, where the
+            // reference's own rounding of sqrt and '/' decides) takes the faithful path below.
+            if (p.fast_pid) {
+              R ss = R(0);
 #pragma unroll
-          for (int c = 0; c < D; ++c) {  // _scale, 483-490
-            const R e = r_isnan(yerr[c]) ? Num<R>::inf() : yerr[c];
-            const R yc = nan_any ? y[c] : y1[c];
-            const R yy = r_max(r_abs(y[c]), r_abs(yc));
-            const R sc = e / (p.atol + yy * p.rtol);
-            ss += sc * sc;
-            sc0 = sc;
+              for (int c = 0; c < D; ++c) {  // _scale, 483-490
+                const R yc = nan_any ? y[c] : y1[c];
+                const R yy = r_max(r_abs(y[c]), r_abs(yc));
+                const R sc = yerr[c] * fast_rcp(p.atol + yy * p.rtol);
+                ss += sc * sc;
+              }
+              const R q = ss * R(1.0 / D);
+              if (q > R(1e-30) && q < R(1e30) && r_abs(q - R(1)) > R(1e-9)) {
+                slow = false;
+                keep = q < R(1);                                   // 493
+                if (p.has_dtmin) keep = keep || at_dtmin;          // 495-496
+                factor = p.safety * (R)inv_root<2 * Solver::kOrder>((double)q);  // 515, 522
+                const R fmin = keep ? R(1) : p.factormin;          // 518
+                const R fmax = keep ? p.factormax : p.safety;      // 520
+                factor = r_min(r_max(factor, fmin), fmax);         // 521-525
+                dtn = dt * factor;                                 // 531
+              }
+            }
           }
-          const R scaled_error = (D == 1) ? r_abs(sc0) : r_sqrt(ss) / sqrt_d;  // optx.rms_norm
-          keep = scaled_error < R(1);                     // 493
-          if (p.has_dtmin) keep = keep || at_dtmin;       // 495-496
-          R inv = R(1) / scaled_error;                    // 498
-          R factor = p.safety;
-          if (p.use_c1) factor = factor * r_pow(inv, p.coeff1);          // 515
-          if (p.use_c2) factor = factor * r_pow(pid_inv, p.coeff2);      // 516
-          if (p.use_c3) factor = factor * r_pow(pid_prev_inv, p.coeff3); // 517
-          const R fmin = keep ? R(1) : p.factormin;       // 518
-          const R fmax = keep ? p.factormax : p.safety;   // 520
-          factor = jnp_min(jnp_max(factor, fmin), fmax);  // 521-525
-          R dtn = dt * factor;                            // 531
-          if (inv == R(0) || r_isinf(inv)) inv = R(1);    // 537-538
+          if (slow) {
+            R ss = R(0), sc0 = R(0);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {  // _scale, 483-490
+              const R e = r_isnan(yerr[c]) ? Num<R>::inf() : yerr[c];
+              const R yc = nan_any ? y[c] : y1[c];
+              const R yy = r_max(r_abs(y[c]), r_abs(yc));
+              const R sc = e / (p.atol + yy * p.rtol);
+              ss += sc * sc;
+              sc0 = sc;
+            }
+            const R scaled_error = (D == 1) ? r_abs(sc0) : r_sqrt(ss) / sqrt_d;  // optx.rms_norm
+            keep = scaled_error < R(1);                     // 493
+            if (p.has_dtmin) keep = keep || at_dtmin;       // 495-496
+            inv = R(1) / scaled_error;                      // 498
+            factor = p.safety;
+            if (p.use_c1) factor = factor * r_pow(inv, p.coeff1);          // 515
+            if (p.use_c2) factor = factor * r_pow(pid_inv, p.coeff2);      // 516
+            if (p.use_c3) factor = factor * r_pow(pid_prev_inv, p.coeff3); // 517
+            const R fmin = keep ? R(1) : p.factormin;       // 518
+            const R fmax = keep ? p.factormax : p.safety;   // 520
+            factor = jnp_min(jnp_max(factor, fmin), fmax);  // 521-525
+            dtn = dt * factor;                              // 531
+            if (inv == R(0) || r_isinf(inv)) inv = R(1);    // 537-538
+          }
           if (p.has_dtmax) dtn = jnp_min(dtn, p.dtmax);   // 545-546
           if (p.has_dtmin) {                              // 547-555
             if (!p.force_dtmin && dtn < p.dtmin && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_DT_MIN_REACHED;

@@ -54,6 +54,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   const double c3 = d->dcoeff / error_order;
   p.coeff1 = (R)c1; p.coeff2 = (R)c2; p.coeff3 = (R)c3;
   p.use_c1 = c1 != 0; p.use_c2 = c2 != 0; p.use_c3 = c3 != 0;
+  p.fast_pid = !sde && d->pcoeff == 0 && d->dcoeff == 0 && d->icoeff == 1 && error_order == (double)Solver::kOrder;
   p.save_t0 = d->save_t0; p.save_t1 = d->save_t1; p.save_steps = d->save_steps; p.save_dense = d->save_dense;
   p.save_ts = (const R *)d->save_ts;
   p.n_save_ts = d->save_ts ? d->n_save_ts : 0;
