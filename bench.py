@@ -34,32 +34,63 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_ATTEMPTED_STEP = {"c2": 316, "c1": 228, "c3": 1536}
+DEFAULT_TRAJECTORIES = {"c1": 1024, "c2": 1 << 20, "c3": 1 << 18, "c5_heun": 1 << 20, "c5_shark": 1 << 20}
 
 
 def workload(name: str, n: int, seed_offset: int = 0):
     """Synthetic inputs of SURVEY.md §8d (deterministic NumPy default_rng)."""
+    base = dict(dt0=None, dtype=np.float64, save_ts=None, controller="pid", levy_area=None, save_dense=False,
+                max_steps=4096, rtol=0.0, atol=0.0, keys=None)
     if name == "c2":
         rng = np.random.default_rng(1 + seed_offset)
         y0 = np.stack([rng.uniform(-15, 15, n), rng.uniform(-20, 20, n), rng.uniform(5, 45, n)], 1)
-        return dict(field="lorenz", params=[10.0, 28.0, 8.0 / 3.0], solver="dopri5", y0=y0, t0=0.0, t1=2.0, dt0=None,
-                    rtol=1e-8, atol=1e-8, dtype=np.float64, save_ts=None, controller="pid",
-                    label="C2 Lorenz/Dopri5/PID(1e-8,1e-8)/fp64/t in [0,2]/SaveAt(t1)")
+        return dict(base, field="lorenz", params=[10.0, 28.0, 8.0 / 3.0], solver="dopri5", y0=y0, t0=0.0, t1=2.0,
+                    rtol=1e-8, atol=1e-8, label="C2 Lorenz/Dopri5/PID(1e-8,1e-8)/fp64/t in [0,2]/SaveAt(t1)")
     if name == "c1":
         rng = np.random.default_rng(0 + seed_offset)
         y0 = rng.uniform(0.5, 2.0, (n, 2))
-        return dict(field="lotka_volterra", params=[1.5, -1.0, -3.0, 1.0], solver="tsit5", y0=y0, t0=0.0, t1=10.0,
-                    dt0=None, rtol=1e-6, atol=1e-6, dtype=np.float64, save_ts=np.linspace(0, 10, 100), controller="pid",
+        return dict(base, field="lotka_volterra", params=[1.5, -1.0, -3.0, 1.0], solver="tsit5", y0=y0, t0=0.0, t1=10.0,
+                    rtol=1e-6, atol=1e-6, save_ts=np.linspace(0, 10, 100),
                     label="C1 Lotka-Volterra/Tsit5/PID(1e-6,1e-6)/fp64/SaveAt(ts=100)")
+    if name == "c3":
+        # Arenstorf initial condition perturbed by 1e-4 N(0,1) (1e-3 sends a third of the ensemble through lunar
+        # near-collisions needing > 8192 steps, see DESIGN.md); one period; dense output with max_steps = 768 (103 GB of dense buffers).
+        rng = np.random.default_rng(2 + seed_offset)
+        y0 = np.array([0.994, 0.0, 0.0, -2.00158510637908252]) + 1e-4 * rng.standard_normal((n, 4))
+        return dict(base, field="cr3bp", params=[0.012277471], solver="dopri8", y0=y0, t0=0.0, t1=17.0652165601579625,
+                    rtol=1e-12, atol=1e-12, save_dense=True, max_steps=768,
+                    label="C3 CR3BP(Arenstorf+1e-4 N(0,1))/Dopri8/PID(1e-12,1e-12)/fp64/one period/SaveAt(dense), max_steps=768")
+    if name in ("c5_heun", "c5_shark"):
+        import diffrax_b200 as dfx
+        keys = dfx.random.split(dfx.random.key(seed_offset), n)
+        sh = name == "c5_shark"
+        return dict(base, field="ou", params=[1.0, 0.0, 0.5], solver="shark" if sh else "heun", dtype=np.float32,
+                    y0=np.ones((n, 1), np.float32), t0=0.0, t1=1.0, dt0=2.0 ** -6, controller="constant",
+                    levy_area="stla" if sh else "bi", keys=keys, bm_tol=2.0 ** -8,
+                    label=f"C5 OU/{'ShARK+SpaceTimeLevyArea' if sh else 'Heun+BrownianIncrement'}/VirtualBrownianTree(tol=2^-8)"
+                          "/ConstantStepSize(2^-6)/fp32/SaveAt(t1)")
     raise ValueError(name)
 
 
-def _ours_objects(w):
+def _ours_objects(w, dev=None):
+    import torch
     import diffrax_b200 as dfx
-    F = {"lorenz": dfx.fields.Lorenz, "lotka_volterra": dfx.fields.LotkaVolterra}[w["field"]]
-    S = {"dopri5": dfx.Dopri5, "tsit5": dfx.Tsit5, "dopri8": dfx.Dopri8}[w["solver"]]
-    term = dfx.ODETerm(F(*w["params"]))
-    ctrl = dfx.PIDController(rtol=w["rtol"], atol=w["atol"])
-    saveat = dfx.SaveAt(t1=True) if w["save_ts"] is None else dfx.SaveAt(ts=w["save_ts"])
+    F = {"lorenz": dfx.fields.Lorenz, "lotka_volterra": dfx.fields.LotkaVolterra, "cr3bp": dfx.fields.CR3BP,
+         "ou": dfx.fields.OrnsteinUhlenbeck}[w["field"]]
+    S = {"dopri5": dfx.Dopri5, "tsit5": dfx.Tsit5, "dopri8": dfx.Dopri8, "heun": dfx.Heun, "shark": dfx.ShARK}[w["solver"]]
+    field = F(*w["params"])
+    if w["levy_area"]:
+        keys = w["keys"] if dev is None else torch.tensor(w["keys"].view(np.int32), device=dev)
+        lv = dfx.BrownianIncrement if w["levy_area"] == "bi" else dfx.SpaceTimeLevyArea
+        bm = dfx.VirtualBrownianTree(0.0, 1.0, w["bm_tol"], (), keys, lv)
+        term = dfx.MultiTerm(dfx.ODETerm(field.drift), dfx.ControlTerm(field.diffusion, bm))
+    else:
+        term = dfx.ODETerm(field)
+    ctrl = dfx.PIDController(rtol=w["rtol"], atol=w["atol"]) if w["controller"] == "pid" else dfx.ConstantStepSize()
+    if w["save_dense"]:
+        saveat = dfx.SaveAt(dense=True)
+    else:
+        saveat = dfx.SaveAt(t1=True) if w["save_ts"] is None else dfx.SaveAt(ts=w["save_ts"])
     return dfx, term, S(), ctrl, saveat
 
 
@@ -75,7 +106,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -110,8 +141,10 @@ def cpu_port_rate(w, sample: int, threads: int = 0):
     y0 = w["y0"][:sample]
     t = time.perf_counter()
     o = oracle.solve(w["field"], y0, w["t0"], w["t1"], w["dt0"], solver=w["solver"], params=w["params"],
-                     rtol=w["rtol"], atol=w["atol"], dtype=w["dtype"], save_t1=w["save_ts"] is None,
-                     save_ts=w["save_ts"], num_threads=threads)
+                     rtol=w["rtol"], atol=w["atol"], dtype=w["dtype"], save_t1=w["save_ts"] is None and not w["save_dense"],
+                     save_ts=w["save_ts"], num_threads=threads, controller=w["controller"], levy_area=w["levy_area"],
+                     keys=None if w["keys"] is None else w["keys"][:sample], bm_tol=w.get("bm_tol", 1e-3),
+                     save_dense=w["save_dense"], max_steps=w["max_steps"])
     dt = time.perf_counter() - t
     return float(o["stats"][:, 1].sum()) / dt, dt, oracle.hw_threads() if threads == 0 else threads
 
@@ -122,6 +155,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    args.ref_sample = min(args.ref_sample, DEFAULT_TRAJECTORIES[args.workload])
     w = workload(args.workload, args.ref_sample)
     for _ in range(args.warmup):
         cpu_port_rate(w, min(args.ref_sample, 8192))
@@ -135,7 +169,8 @@ def run_reference(args):
     sample = f"{args.ref_sample} of the workload's trajectories per step (same seed/config), all host cores"
     line = {"impl": "reference", "metric": "accepted_rk_steps_per_s", "value": value, "unit": "steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if w["dtype"] == np.float64 else "f32", "data": "synthetic",
             "config": {"workload": w["label"], "trajectories_per_step": args.ref_sample},
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -154,22 +189,32 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     L = _lib.lib()
 
-    n_local = args.trajectories
+    n_local = args.trajectories or DEFAULT_TRAJECTORIES[args.workload]
     w = workload(args.workload, n_local, seed_offset=1000 * rank)
-    dfx, term, solver, ctrl, saveat = _ours_objects(w)
+    dfx, term, solver, ctrl, saveat = _ours_objects(w, dev)
     y0_dev = torch.tensor(w["y0"], device=dev)
     y0_host = torch.tensor(w["y0"]).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # prepared call: descriptor + output buffers built once; each step is ONE C-ABI call
-    plan = dfx.prepare(term, solver, w["t0"], w["t1"], w["dt0"], y0_dev, saveat=saveat, stepsize_controller=ctrl)
+    plan = dfx.prepare(term, solver, w["t0"], w["t1"], w["dt0"], y0_dev, saveat=saveat, stepsize_controller=ctrl,
+                       max_steps=w["max_steps"])
+    def _tensors(x):
+        if isinstance(x, torch.Tensor):
+            yield x
+        elif isinstance(x, dict):
+            for v in x.values():
+                yield from _tensors(v)
+    out_bytes = sum(int(t.numel() * t.element_size()) for k in plan._keep for t in _tensors(k))
+    do_e2e = out_bytes < (2 << 30)      # C3's 69 GB of dense output is not staged through the host
+    _, term_h, _, _, _ = _ours_objects(w, None)
 
     def step_device():
         return plan(throw=False)
 
     def step_host():
-        return dfx.diffeqsolve(term, solver, w["t0"], w["t1"], w["dt0"], y0_host, saveat=saveat,
-                               stepsize_controller=ctrl, throw=False, device=local)
+        return dfx.diffeqsolve(term_h, solver, w["t0"], w["t1"], w["dt0"], y0_host, saveat=saveat,
+                               stepsize_controller=ctrl, throw=False, device=local, max_steps=w["max_steps"])
 
     def barrier():
         if world > 1:
@@ -204,21 +249,23 @@ def run_ours(args):
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)  # device time of the K solves
 
     # ---- e2e: same K steps through the host-buffer call (H2D + D2H inside the timed region) ----
-    for _ in range(2):
-        sh = step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sh = step_host()
-        _ = int(sh.result[0])  # read the step's result on the host
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d = y0_host.numel() * y0_host.element_size()
-    d2h = sum(int(t.numel() * t.element_size()) for t in (sh.ts, sh.ys, sh.result, sh.y_final, sh.t_final)) \
-        + 3 * int(sh.stats["num_steps"].numel()) * 4
+    e2e_s, h2d, d2h = float("nan"), 0, 0
+    if do_e2e:
+        for _ in range(2):
+            sh = step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sh = step_host()
+            _ = int(sh.result[0])  # read the step's result on the host
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        h2d = y0_host.numel() * y0_host.element_size() + (0 if w["keys"] is None else w["keys"].nbytes)
+        d2h = sum(int(t.numel() * t.element_size()) for t in (sh.ts, sh.ys, sh.result, sh.y_final, sh.t_final)) \
+            + 3 * int(sh.stats["num_steps"].numel()) * 4
 
     # ---- max over ranks, totals over ranks ----
-    t_max = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
+    t_max = torch.tensor([dev_ms, (e2e_s if do_e2e else 0.0) * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
     tot = torch.tensor([acc_local, att_local, failed_local], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
@@ -232,27 +279,47 @@ def run_ours(args):
         ms_per_step = dev_ms_max / args.steps
         value = acc / (ms_per_step * 1e-3)
         flop = FLOP_PER_ATTEMPTED_STEP.get(args.workload)
-        peak = float(L.dfx_measure_fma_peak(_lib.F64, local))  # TFLOP/s, live DFMA-chain microbenchmark
-        achieved = (att / world) * flop / (ms_per_step * 1e-3) / 1e12  # per-GPU: the kernel of ONE rank
-        cpu_rate, cpu_dt, cores = cpu_port_rate(w, args.cpu_sample)
+        if flop is not None:
+            peak = float(L.dfx_measure_fma_peak(_lib.F64, local))  # TFLOP/s, live DFMA-chain microbenchmark
+            achieved = (att / world) * flop / (ms_per_step * 1e-3) / 1e12  # per-GPU: the kernel of ONE rank
+            roof = {"bound": "fma_fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                    "peak_source": "dfx_measure_fma_peak: 8 independent DFMA chains/thread, 8 CTAs x 256 thr/SM, "
+                                   "measured in this run (MEASURED_PEAKS.json holds no FP64 FMA figure)",
+                    "flop_per_attempted_step": flop}
+            if args.workload == "c3":   # dense output: 8 (16 d + 1) = 520 B per accepted step + inf padding of the tails
+                by = float(out_bytes)
+                roof["hbm_write"] = {"bytes_per_launch": by, "achieved_GBps": by / (ms_per_step * 1e-3) / 1e9 / world,
+                                     "peak_GBps": 6546.6, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)"}
+        else:
+            # C5: threefry blocks on the INT32 ALU.  Per step with end-point reuse: one descent of L=8 levels:
+            # BI 3 blocks/level + root 3 + leaf 1 (+1 leaf split) ; STLA 7 blocks/level + root 5 + leaf 4.
+            blocks = {"c5_heun": 3 * 8 + 4, "c5_shark": 7 * 8 + 9}[args.workload]
+            ops = blocks * 77.0          # 20 x (add, rotate, xor) + 17 injection adds per block
+            peak = float(L.dfx_measure_int_peak(local))
+            achieved = (att / world) * ops / (ms_per_step * 1e-3) / 1e12
+            roof = {"bound": "int32_alu", "achieved": achieved, "peak": peak, "unit": "Tera-op/s",
+                    "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                    "peak_source": "dfx_measure_int_peak: add/rotate/xor chains, measured in this run",
+                    "threefry_blocks_per_step": blocks}
+        cpu_sample = min(args.cpu_sample, n_local)
+        cpu_rate, cpu_dt, cores = cpu_port_rate(w, cpu_sample)
         line = {
             "metric": "accepted_rk_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if w["dtype"] == np.float64 else "f32", "data": "synthetic",
             "config": {"workload": w["label"], "trajectories_per_gpu": n_local, "trajectories_total": n_local * world,
                        "accepted_steps_per_solve": acc, "attempted_steps_per_solve": att, "failed_trajectories": failed,
                        "l2": "flushed between timed steps (256 MiB write outside the per-step CUDA-event pairs)",
                        "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
-            "e2e": {"value": acc / (e2e_ms_max * 1e-3 / args.steps), "unit": "steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps},
+            "e2e": ({"value": acc / (e2e_ms_max * 1e-3 / args.steps), "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps} if do_e2e else
+                    {"value": None, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                     "note": "outputs exceed 2 GiB; not staged through the host"}),
             "gpu_launches": launches,
-            "roofline": {"bound": "fma_fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                         "peak_source": "dfx_measure_fma_peak: 8 independent DFMA chains/thread, 8 CTAs x 256 thr/SM, "
-                                        "measured in this run (MEASURED_PEAKS.json holds no FP64 FMA figure)",
-                         "flop_per_attempted_step": flop, "kernel": "ensemble_kernel<double,Lorenz,Dopri5,0,false>"},
+            "roofline": roof,
             "cpu_baseline": {"value": cpu_rate, "unit": "steps/s", "cores": cores, "kind": "port",
-                             "sample": f"first {args.cpu_sample} trajectories of rank 0's batch, oracle (C port), "
+                             "sample": f"first {cpu_sample} trajectories of rank 0's batch, oracle (C port), "
                                        f"{cpu_dt:.2f} s"},
             "clocks": clocks, "wall_ms_per_step_incl_flush_and_host": wall_ms_max / args.steps,
         }
@@ -265,11 +332,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--trajectories", type=int, default=1 << 20, help="trajectories per GPU")
+    ap.add_argument("--trajectories", type=int, default=0, help="trajectories per GPU (default: the workload's size)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="trajectories of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=1 << 16, help="trajectories per step of --impl reference")
     args = ap.parse_args()

@@ -24,7 +24,7 @@ LIB = os.path.join(LIBDIR, "libdiffrax_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-         "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")]
+         "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")] + os.environ.get("DFX_NVCC_EXTRA", "").split()
 
 
 def _headers():

@@ -130,8 +130,10 @@ template <int M> __device__ __forceinline__ double ipow(double z) {
 // q^(-1/M) for q in [1e-36, 1e36]: fp32 SFU seed (MUFU.LG2 / MUFU.EX2, rel. err ~1e-6) refined by two
 // steps of the division-free Newton iteration z <- z + z (1 - q z^M) / M (error e -> (M+1)/2 e^2),
 // i.e. ~1 ulp in fp64 at a cost of 2 (log2(M)+4) FP64 instructions instead of pow()'s ~100.
-template <int M> __device__ __forceinline__ double inv_root(double q) {
-  const float s = exp2f(__log2f((float)q) * (-1.0f / (float)M));
+template <int M> __device__ __forceinline__ double inv_root(double q, float qf) {
+  // qf == (float)q is in [1e-30, 1e30]: no denormal / overflow handling needed around the SFU ops
+  float s;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(__log2f(qf) * (-1.0f / (float)M)));
   double z = (double)s;
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
@@ -141,8 +143,68 @@ template <int M> __device__ __forceinline__ double inv_root(double q) {
   return z;
 }
 
+// max(|a|, |b|) and min / max of POSITIVE doubles on the integer ALU (the IEEE bit patterns of non-negative
+// doubles order like the values; NaN has the largest pattern and therefore propagates through max).
+// Keeps these off the FP64 pipe, where DSETP + select + NaN fix-up would cost an FP64 issue slot each.
+__device__ __forceinline__ double abs_max_bits(double a, double b) {
+  const long long x = __double_as_longlong(a) & 0x7fffffffffffffffLL, y = __double_as_longlong(b) & 0x7fffffffffffffffLL;
+  return __longlong_as_double(x > y ? x : y);
+}
+__device__ __forceinline__ double pos_max_bits(double a, double b) {
+  const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+  return __longlong_as_double(x > y ? x : y);
+}
+__device__ __forceinline__ double pos_min_bits(double a, double b) {
+  const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+  return __longlong_as_double(x < y ? x : y);
+}
+__device__ __forceinline__ float abs_max_bits(float a, float b) { return fmaxf(fabsf(a), fabsf(b)); }
+__device__ __forceinline__ float pos_max_bits(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float pos_min_bits(float a, float b) { return fminf(a, b); }
+
 // streaming (evict-first) stores for write-once outputs
 __device__ __forceinline__ void st_cs(double *p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(float *p, float v) { __stcs(p, v); }
+
+// Store a register-resident row of N values with the widest vector store its size allows: 256-bit
+// (STG.E.256, new on sm_100), 128-bit, else scalar.  `vec_ok` says the destination rows are 32-byte aligned
+// (checked on the host from the base pointer and the row stride); every store is a streaming (.cs) store.
+// A lane writing a contiguous row with 256-bit stores covers whole 32-byte sectors by itself, so the L2 sees
+// full-sector writes even though neighbouring lanes write to different trajectories' rows.
+template <int N>
+__device__ __forceinline__ void store_row(double *dst, const double (&v)[N], bool vec_ok) {
+  if (vec_ok && N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4)
+      asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "d"(v[i]), "d"(v[i + 1 < N ? i + 1 : i]),
+                   "d"(v[i + 2 < N ? i + 2 : i]), "d"(v[i + 3 < N ? i + 3 : i]) : "memory");
+  } else if (vec_ok && N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2)
+      asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(dst + i), "d"(v[i]), "d"(v[i + 1 < N ? i + 1 : i]) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) __stcs(dst + i, v[i]);
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_row(float *dst, const float (&v)[N], bool vec_ok) {
+  if (vec_ok && N % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 8)
+      asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + i), "f"(v[i]),
+                   "f"(v[i + 1 < N ? i + 1 : i]), "f"(v[i + 2 < N ? i + 2 : i]), "f"(v[i + 3 < N ? i + 3 : i]),
+                   "f"(v[i + 4 < N ? i + 4 : i]), "f"(v[i + 5 < N ? i + 5 : i]), "f"(v[i + 6 < N ? i + 6 : i]),
+                   "f"(v[i + 7 < N ? i + 7 : i]) : "memory");
+  } else if (vec_ok && N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4)
+      asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1 < N ? i + 1 : i]),
+                   "f"(v[i + 2 < N ? i + 2 : i]), "f"(v[i + 3 < N ? i + 3 : i]) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) __stcs(dst + i, v[i]);
+  }
+}
 
 }  // namespace dfx

@@ -69,13 +69,39 @@ struct SolveParams {
   int *stats, *result, *save_count;
   R *dense_ts, *dense_y0, *dense_y1, *dense_k;
   int *dense_count;
+  int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
   R *y_final, *t_final;
   unsigned long long *work_counter;
   const uint32_t *keys;
   VbtParams vbt;
 };
 
-constexpr int kBlockThreads = 128;
+#ifndef DFX_BLOCK_THREADS
+#define DFX_BLOCK_THREADS 128
+#endif
+constexpr int kBlockThreads = DFX_BLOCK_THREADS;
+
+// Occupancy target handed to ptxas.  The stage values k[S][D] must stay in registers; the rest of the state needs
+// ~64 more (+ the interpolation / save bookkeeping of the RICH variant, + the Brownian tree for SDEs).  Measured on
+// C2 (Lorenz/Dopri5/fp64): 3 CTAs/SM (140 regs) 4.53 ms, 6 CTAs/SM (79 regs, no spills) 3.71 ms, 8 CTAs/SM
+// (64 regs, spills) 3.87 ms - so the default asks for as many CTAs as comfortably fit (capped at 6) and
+// MinBlocksOverride pins the measured optimum for the benchmark configurations.
+template <class R, class Field, class Solver, int LEVY, bool RICH>
+struct MinBlocksOverride { static constexpr int value = 0; };
+template <> struct MinBlocksOverride<double, LorenzField, Dopri5, 0, false> { static constexpr int value = 6; };
+
+template <class R, class Field, class Solver, int LEVY, bool RICH>
+constexpr int min_blocks_per_sm() {
+#ifdef DFX_MIN_BLOCKS
+  return DFX_MIN_BLOCKS;
+#else
+  if (MinBlocksOverride<R, Field, Solver, LEVY, RICH>::value > 0) return MinBlocksOverride<R, Field, Solver, LEVY, RICH>::value;
+  const int words = (int)sizeof(R) / 4;
+  const int budget = Solver::S * Field::kDim * words + 64 + (RICH ? 32 : 0) + (LEVY != 0 ? 24 * words : 0);
+  const int blocks = 65536 / (kBlockThreads * budget);
+  return blocks < 1 ? 1 : (blocks > 6 ? 6 : blocks);
+#endif
+}
 
 // Claim the next trajectory for every lane of the warp that needs one: one atomic per warp.
 __device__ __forceinline__ long long claim_work(bool need, unsigned long long *counter) {
@@ -96,7 +122,7 @@ __device__ __forceinline__ long long claim_work(bool need, unsigned long long *c
 //   LEVY   dfx_levy: 0 ODE, 1 BrownianIncrement, 2 SpaceTimeLevyArea
 //   RICH   false: SaveAt(t1=True) only (the C2/C4/C5 fast path); true: every SaveAt mode
 template <class R, class Field, class Solver, int LEVY, bool RICH>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<R, Field, Solver, LEVY, RICH>())
 ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) {
   constexpr int D = Field::kDim;
   constexpr int S = Solver::S;
@@ -298,40 +324,42 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         R next_t0, next_t1;
         if (p.controller == DFX_CTRL_PID) {
           // pid.py:394-567.  y_error NaN -> inf first (_integrate.py:386).
-          bool nan_any = false;
-#pragma unroll
-          for (int c = 0; c < D; ++c) nan_any |= r_isnan(y1[c]);
           R dtn, inv = R(1), factor;
           bool slow = true;
           if constexpr (FAST_PID) {
             // ---- fast path: pure I-controller (pcoeff = dcoeff = 0, icoeff = 1) at the solver's own order ----
-            // scaled_error = sqrt(ss / D), so   keep <=> ss < D   and   factor = safety * (ss/D)^(-1/(2 order)).
-            // No sqrt, no IEEE division, no pow(): reciprocals and the 2*order-th root are Newton-refined SFU seeds.
-            // Anything unusual (non-finite / extreme error, or ss within 1e-9 of the accept boundary, where the
-            // reference's own rounding of sqrt and '/' decides) takes the faithful path below.
+            // scaled_error = sqrt(ss / D), so   keep <=> ss/D < 1   and   factor = safety * (ss/D)^(-1/(2 order)).
+            // No sqrt, no IEEE division, no pow(), no FP64 compares: reciprocals and the 2*order-th root are
+            // Newton-refined SFU seeds, max/min/clip run on the integer ALU, and the range / accept tests are made
+            // on (float)q.  NaN or inf anywhere (y1, y_error) makes q non-finite and fails the range test, and q
+            // within 1e-6 of the accept boundary (where the reference's own rounding of sqrt and '/' decides) is
+            // excluded too: all of those take the faithful path below, so accept/reject decisions are the reference's.
             if (p.fast_pid) {
               R ss = R(0);
 #pragma unroll
-              for (int c = 0; c < D; ++c) {  // _scale, 483-490
-                const R yc = nan_any ? y[c] : y1[c];
-                const R yy = r_max(r_abs(y[c]), r_abs(yc));
+              for (int c = 0; c < D; ++c) {  // _scale, 483-490 (a NaN y1 propagates through abs_max_bits)
+                const R yy = abs_max_bits(y[c], y1[c]);
                 const R sc = yerr[c] * fast_rcp(p.atol + yy * p.rtol);
                 ss += sc * sc;
               }
               const R q = ss * R(1.0 / D);
-              if (q > R(1e-30) && q < R(1e30) && r_abs(q - R(1)) > R(1e-9)) {
+              const float qf = (float)q;
+              if (qf > 1e-30f && qf < 1e30f && fabsf(qf - 1.0f) > 1e-6f) {
                 slow = false;
-                keep = q < R(1);                                   // 493
+                keep = qf < 1.0f;                                  // 493 (same decision as q < 1 outside the 1e-6 band)
                 if (p.has_dtmin) keep = keep || at_dtmin;          // 495-496
-                factor = p.safety * (R)inv_root<2 * Solver::kOrder>((double)q);  // 515, 522
+                factor = p.safety * (R)inv_root<2 * Solver::kOrder>((double)q, qf);  // 515, 522
                 const R fmin = keep ? R(1) : p.factormin;          // 518
                 const R fmax = keep ? p.factormax : p.safety;      // 520
-                factor = r_min(r_max(factor, fmin), fmax);         // 521-525
+                factor = pos_min_bits(pos_max_bits(factor, fmin), fmax);  // 521-525 (all operands positive)
                 dtn = dt * factor;                                 // 531
               }
             }
           }
           if (slow) {
+            bool nan_any = false;
+#pragma unroll
+            for (int c = 0; c < D; ++c) nan_any |= r_isnan(y1[c]);
             R ss = R(0), sc0 = R(0);
 #pragma unroll
             for (int c = 0; c < D; ++c) {  // _scale, 483-490
@@ -377,7 +405,9 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         }
 
         // ---- book-keeping, _integrate.py:412-437 ----
-        const R tprev_new = jnp_min(next_t0, t1);
+        // 412: tprev = min(tprev, t1) is the identity here: next_t0 is st0 or st1, and tnext never exceeds t1
+        // (it starts as min(t0 + dt0, t1) and every update below clips it to t1).
+        const R tprev_new = next_t0;
         R tnext_new = next_t1;
         if (next_t1 > t1_clip_floor) tnext_new = keep ? t1 : tprev_new + R(0.5) * (t1 - tprev_new);  // 278-284
         num_steps += 1;
@@ -411,17 +441,17 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           if (p.save_dense && keep) {
             const long long row = idx * (long long)p.max_steps + dense_index;
             st_cs(&p.dense_ts[idx * (long long)(p.max_steps + 1) + dense_index + 1], tprev_new);
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              st_cs(&p.dense_y0[row * D + c], y[c]);
-              st_cs(&p.dense_y1[row * D + c], y1[c]);
-            }
+            store_row<D>(&p.dense_y0[row * D], y, p.dense_vec_ok != 0);
+            store_row<D>(&p.dense_y1[row * D], y1, p.dense_vec_ok != 0);
             if constexpr (DENSE_K) {
               if (p.dense_k != nullptr) {
+                // k[S][D] is contiguous in the output row (S*D values): one lane streams whole sectors
+                R flat[S * D];
 #pragma unroll
                 for (int j = 0; j < S; ++j)
 #pragma unroll
-                  for (int c = 0; c < D; ++c) st_cs(&p.dense_k[(row * S + j) * D + c], k[j][c]);
+                  for (int c = 0; c < D; ++c) flat[j * D + c] = k[j][c];
+                store_row<S * D>(&p.dense_k[row * (S * D)], flat, p.dense_vec_ok != 0);
               }
             }
             dense_index += 1;

@@ -79,11 +79,11 @@ struct Cr3bpField {
     const R x = y[0], yy = y[1], vx = y[2], vy = y[3];
     const R dx1 = x + p.mu, dx2 = x - p.mup;
     const R r1s = dx1 * dx1 + yy * yy, r2s = dx2 * dx2 + yy * yy;
-    const R d1 = r1s * r_sqrt(r1s), d2 = r2s * r_sqrt(r2s);
+    const R w1 = p.mup / (r1s * r_sqrt(r1s)), w2 = p.mu / (r2s * r_sqrt(r2s));  // (1-mu)/r1^3, mu/r2^3
     f[0] = vx;
     f[1] = vy;
-    f[2] = x + R(2) * vy - p.mup * dx1 / d1 - p.mu * dx2 / d2;
-    f[3] = yy - R(2) * vx - p.mup * yy / d1 - p.mu * yy / d2;
+    f[2] = x + R(2) * vy - w1 * dx1 - w2 * dx2;
+    f[3] = yy - R(2) * vx - (w1 + w2) * yy;
   }
 };
 
