@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_ATTEMPTED_STEP = {"c2": 316, "c1": 228, "c3": 1536}
-DEFAULT_TRAJECTORIES = {"c1": 1024, "c2": 1 << 20, "c3": 1 << 18, "c5_heun": 1 << 20, "c5_shark": 1 << 20}
+DEFAULT_TRAJECTORIES = {"c1": 1024, "c2": 1 << 20, "c3": 1 << 18, "c4": 1 << 16, "c5_heun": 1 << 20, "c5_shark": 1 << 20}
 
 
 def workload(name: str, n: int, seed_offset: int = 0):
@@ -60,6 +60,14 @@ def workload(name: str, n: int, seed_offset: int = 0):
         return dict(base, field="cr3bp", params=[0.012277471], solver="dopri8", y0=y0, t0=0.0, t1=17.0652165601579625,
                     rtol=1e-12, atol=1e-12, save_dense=True, max_steps=768,
                     label="C3 CR3BP(Arenstorf+1e-4 N(0,1))/Dopri8/PID(1e-12,1e-12)/fp64/one period/SaveAt(dense), max_steps=768")
+    if name == "c4":
+        import diffrax_b200 as dfx
+        mlp = dfx.fields.MLP.init(3, d=4, width=128)          # weights ~ U(+-1/sqrt(fan_in)), seed 3
+        rng = np.random.default_rng(30 + seed_offset)
+        y0 = rng.standard_normal((n, 4)).astype(np.float32)
+        return dict(base, field="mlp", params=mlp.oracle_params(), mlp=mlp, solver="tsit5", dtype=np.float32, y0=y0,
+                    t0=0.0, t1=10.0, rtol=1e-3, atol=1e-6,
+                    label="C4 neural ODE MLP(4->128->128->4, softplus, tanh)/Tsit5/PID(1e-3,1e-6)/fp32/t in [0,10]/SaveAt(t1)")
     if name in ("c5_heun", "c5_shark"):
         import diffrax_b200 as dfx
         keys = dfx.random.split(dfx.random.key(seed_offset), n)
@@ -76,9 +84,9 @@ def _ours_objects(w, dev=None):
     import torch
     import diffrax_b200 as dfx
     F = {"lorenz": dfx.fields.Lorenz, "lotka_volterra": dfx.fields.LotkaVolterra, "cr3bp": dfx.fields.CR3BP,
-         "ou": dfx.fields.OrnsteinUhlenbeck}[w["field"]]
+         "ou": dfx.fields.OrnsteinUhlenbeck, "mlp": None}[w["field"]]
     S = {"dopri5": dfx.Dopri5, "tsit5": dfx.Tsit5, "dopri8": dfx.Dopri8, "heun": dfx.Heun, "shark": dfx.ShARK}[w["solver"]]
-    field = F(*w["params"])
+    field = w["mlp"] if w["field"] == "mlp" else F(*w["params"])
     if w["levy_area"]:
         keys = w["keys"] if dev is None else torch.tensor(w["keys"].view(np.int32), device=dev)
         lv = dfx.BrownianIncrement if w["levy_area"] == "bi" else dfx.SpaceTimeLevyArea
@@ -279,7 +287,7 @@ def run_ours(args):
         ms_per_step = dev_ms_max / args.steps
         value = acc / (ms_per_step * 1e-3)
         flop = FLOP_PER_ATTEMPTED_STEP.get(args.workload)
-        if flop is not None:
+        if flop is not None and args.workload != "c4":
             peak = float(L.dfx_measure_fma_peak(_lib.F64, local))  # TFLOP/s, live DFMA-chain microbenchmark
             achieved = (att / world) * flop / (ms_per_step * 1e-3) / 1e12  # per-GPU: the kernel of ONE rank
             roof = {"bound": "fma_fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -291,6 +299,28 @@ def run_ours(args):
                 by = float(out_bytes)
                 roof["hbm_write"] = {"bytes_per_launch": by, "achieved_GBps": by / (ms_per_step * 1e-3) / 1e9 / world,
                                      "peak_GBps": 6546.6, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)"}
+        elif args.workload == "c4":
+            # MLP field: 6 evaluations x 2 (128 d + 128^2 + 128 d) = 208 896 flop per attempted step;
+            # 196 608 of them are the 128x128 hidden layer that runs on tcgen05 (issued 3x for 3xTF32, and the kernel
+            # evaluates 7 stages per step: stage 0 is recomputed instead of carried, value-identical).
+            flop = 208896
+            a = torch.randn(8192, 8192, device=dev); b = torch.randn(8192, 8192, device=dev)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            best = 1e9
+            for _ in range(6):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            peak = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+            achieved = (att / world) * flop / (ms_per_step * 1e-3) / 1e12
+            issued = (att / world) * 7 * 3 * 2 * 128 * 128 / (ms_per_step * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                    "peak_source": "cuBLAS TF32 GEMM 8192^3 (torch.matmul, allow_tf32) measured in this run; "
+                                   "MEASURED_PEAKS.json has bf16 only",
+                    "flop_per_attempted_step": flop, "issued_tensor_tflops": issued,
+                    "note": "whole-solve average incl. the CUDA-core layers, softplus/tanh and the RK/PID algebra; "
+                            "tensor-pipe utilisation of the kernel: profiles/ ncu summary"}
         else:
             # C5: threefry blocks on the INT32 ALU.  Per step with end-point reuse: one descent of L=8 levels:
             # BI 3 blocks/level + root 3 + leaf 1 (+1 leaf split) ; STLA 7 blocks/level + root 5 + leaf 4.

@@ -89,6 +89,9 @@ constexpr int kBlockThreads = DFX_BLOCK_THREADS;
 template <class R, class Field, class Solver, int LEVY, bool RICH>
 struct MinBlocksOverride { static constexpr int value = 0; };
 template <> struct MinBlocksOverride<double, LorenzField, Dopri5, 0, false> { static constexpr int value = 6; };
+// the per-thread MLP evaluation keeps the 128 hidden activations in registers
+template <class R, int D, int W, class Solver, int LEVY, bool RICH>
+struct MinBlocksOverride<R, MlpField<D, W>, Solver, LEVY, RICH> { static constexpr int value = 2; };
 
 template <class R, class Field, class Solver, int LEVY, bool RICH>
 constexpr int min_blocks_per_sm() {

@@ -9,7 +9,7 @@
 // Interface (duck-typed, used by ensemble_kernel.cuh):
 //   static constexpr int kId, kDim;  static constexpr bool kSde;
 //   template <class R> struct P;                                   // POD parameters
-//   template <class R> static P<R> make(const double *p, int n);    // host
+//   template <class R> static P<R> make(const double *p, int n, const void *weights);  // host; weights = device pointer
 //   template <class R> static __device__ void eval(const P<R>&, R t, const R (&y)[kDim], R (&f)[kDim]);
 //   (kSde) template <class R> static __device__ R diffusion(const P<R>&, R t);  // additive scalar noise
 #pragma once
@@ -25,7 +25,7 @@ struct DecayField {
   static constexpr bool kSde = false;
   static constexpr int kNumParams = 1;
   template <class R> struct P { R lambda; };
-  template <class R> static P<R> make(const double *p, int) { return P<R>{(R)p[0]}; }
+  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0]}; }
   template <class R>
   static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[D], R (&f)[D]) {
 #pragma unroll
@@ -40,7 +40,7 @@ struct LotkaVolterraField {
   static constexpr bool kSde = false;
   static constexpr int kNumParams = 4;
   template <class R> struct P { R a, b, c, d; };
-  template <class R> static P<R> make(const double *p, int) { return P<R>{(R)p[0], (R)p[1], (R)p[2], (R)p[3]}; }
+  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0], (R)p[1], (R)p[2], (R)p[3]}; }
   template <class R>
   static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[2], R (&f)[2]) {
     const R x = y[0], yy = y[1];
@@ -56,7 +56,7 @@ struct LorenzField {
   static constexpr bool kSde = false;
   static constexpr int kNumParams = 3;
   template <class R> struct P { R sigma, rho, beta; };
-  template <class R> static P<R> make(const double *p, int) { return P<R>{(R)p[0], (R)p[1], (R)p[2]}; }
+  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0], (R)p[1], (R)p[2]}; }
   template <class R>
   static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[3], R (&f)[3]) {
     f[0] = p.sigma * (y[1] - y[0]);
@@ -73,7 +73,7 @@ struct Cr3bpField {
   static constexpr bool kSde = false;
   static constexpr int kNumParams = 1;
   template <class R> struct P { R mu, mup; };
-  template <class R> static P<R> make(const double *p, int) { return P<R>{(R)p[0], (R)1 - (R)p[0]}; }
+  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0], (R)1 - (R)p[0]}; }
   template <class R>
   static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[4], R (&f)[4]) {
     const R x = y[0], yy = y[1], vx = y[2], vy = y[3];
@@ -95,7 +95,7 @@ struct ForcedOscField {
   static constexpr bool kSde = false;
   static constexpr int kNumParams = 3;
   template <class R> struct P { R w0sq, amp, w; };
-  template <class R> static P<R> make(const double *p, int) { return P<R>{(R)p[0], (R)p[1], (R)p[2]}; }
+  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0], (R)p[1], (R)p[2]}; }
   template <class R>
   static __device__ __forceinline__ void eval(const P<R> &p, R t, const R (&y)[2], R (&f)[2]) {
     f[0] = y[1];
@@ -110,7 +110,7 @@ struct VdpField {
   static constexpr bool kSde = false;
   static constexpr int kNumParams = 1;
   template <class R> struct P { R mu; };
-  template <class R> static P<R> make(const double *p, int) { return P<R>{(R)p[0]}; }
+  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0]}; }
   template <class R>
   static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[2], R (&f)[2]) {
     f[0] = y[1];
@@ -126,12 +126,64 @@ struct OuField {
   static constexpr bool kSde = true;
   static constexpr int kNumParams = 3;
   template <class R> struct P { R theta, mu, sigma; };
-  template <class R> static P<R> make(const double *p, int) { return P<R>{(R)p[0], (R)p[1], (R)p[2]}; }
+  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0], (R)p[1], (R)p[2]}; }
   template <class R>
   static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[1], R (&f)[1]) {
     f[0] = p.theta * (p.mu - y[0]);
   }
   template <class R> static __device__ __forceinline__ R diffusion(const P<R> &p, R) { return p.sigma; }
+};
+
+// Neural-ODE vector field (BASELINE config 4): eqx.nn.MLP(d -> W -> W -> d) with softplus hidden activations and
+// a tanh output (docs/examples/neural_ode.ipynb cell 5; benchmarks/small_neural_ode.py:25-28), evaluated per thread
+// on the FP32 CUDA cores.  This is the exact-fp32 reference implementation of the field inside the generic ensemble
+// kernel; the tensor-core (tcgen05, 3xTF32) kernel lives in mlp_kernel.cuh.
+// Weights (device memory, fp32/fp64 as R, eqx Linear layout (out, in) row-major):
+//   W1[W][D], b1[W], W2[W][W], b2[W], W3[D][W], b3[D]
+// Every lane reads the same weight at the same time, so the loads are L1 broadcasts (one transaction per warp).
+template <int D, int W>
+struct MlpField {
+  static constexpr int kId = DFX_FIELD_MLP;
+  static constexpr int kDim = D;
+  static constexpr int kWidth = W;
+  static constexpr bool kSde = false;
+  static constexpr int kNumParams = 2;  // [width, depth] for checking
+  static constexpr long long kNumWeights = (long long)W * D + W + (long long)W * W + W + (long long)D * W + D;
+  template <class R> struct P { const R *w; };
+  template <class R> static P<R> make(const double *, int, const void *weights) { return P<R>{(const R *)weights}; }
+
+  template <class R> static __device__ __forceinline__ R softplus(R x) {
+    // jax.nn.softplus = logaddexp(x, 0) = max(x, 0) + log1p(exp(-|x|))
+    return r_max(x, R(0)) + r_log1p(r_exp(-r_abs(x)));
+  }
+
+  template <class R>
+  static __device__ __noinline__ void eval(const P<R> &p, R, const R (&y)[D], R (&f)[D]) {
+    const R *W1 = p.w, *b1 = W1 + W * D, *W2 = b1 + W, *b2 = W2 + W * W, *W3 = b2 + W, *b3 = W3 + D * W;
+    R h1[W];
+#pragma unroll
+    for (int o = 0; o < W; ++o) {
+      R acc = R(0);
+#pragma unroll
+      for (int k = 0; k < D; ++k) acc += __ldg(W1 + o * D + k) * y[k];
+      h1[o] = softplus(acc + __ldg(b1 + o));
+    }
+    R out[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[c] = R(0);
+#pragma unroll 1
+    for (int o = 0; o < W; ++o) {
+      const R *row = W2 + o * W;
+      R acc = R(0);
+#pragma unroll
+      for (int k = 0; k < W; ++k) acc += __ldg(row + k) * h1[k];
+      const R h2 = softplus(acc + __ldg(b2 + o));
+#pragma unroll
+      for (int c = 0; c < D; ++c) out[c] += __ldg(W3 + c * W + o) * h2;
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) f[c] = r_tanh(out[c] + __ldg(b3 + c));
+  }
 };
 
 }  // namespace dfx

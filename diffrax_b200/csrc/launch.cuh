@@ -125,7 +125,7 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   SolveParams<R> p;
   fill_params<R, Solver>(d, p, SDE);
   if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
-  const auto fp = Field::template make<R>(d->field_params, d->n_field_params);
+  const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
   const bool rich = d->save_t0 || d->save_ts || d->save_steps || d->save_dense;
 

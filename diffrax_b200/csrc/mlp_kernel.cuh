@@ -1,0 +1,394 @@
+// mlp_kernel.cuh - neural-ODE ensemble kernel with the MLP vector field on the 5th-gen tensor cores (K3 of SURVEY.md §2.1).
+//
+// Field: eqx.nn.MLP(4 -> 128 -> 128 -> 4), softplus hidden, tanh final (docs/examples/neural_ode.ipynb cell 5).
+// The 128 x 128 hidden layer is the only real contraction (16 384 of the 17 408 MACs per evaluation); it runs as
+//   D[128 traj x 128] = A[128 traj x 128] . W2^T        tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8
+// with fp32-faithful 3xTF32 splitting: x = hi + lo (both rounded to TF32 with cvt.rna), A.B ~= Ahi.Bhi + Ahi.Blo + Alo.Bhi
+// accumulated in fp32 in TMEM (residual ~2^-21 relative, the level of fp32 summation noise).
+//
+// Mapping
+//   * one CTA = 128 trajectories = the M tile; 256 threads: thread (warp w, lane l) owns row m = 32 (w % 4) + l (its TMEM
+//     lane) and the hidden-unit half w / 4 (columns [64 h, 64 h + 64)).  Both threads of a row carry the (tiny, d = 4) RK
+//     state redundantly and bit-identically, so only the MLP evaluation needs communication.
+//   * A (softplus(W1 y + b1), split hi/lo) is written by its owner threads straight into TMEM with tcgen05.st - a thread's
+//     row IS its TMEM lane - so A never touches shared memory; W2 (hi and lo, 2 x 64 KB) is resident in shared memory for
+//     the whole kernel in the canonical K-major no-swizzle UMMA layout; the accumulator D lives in TMEM and is read back
+//     with tcgen05.ld for the epilogue (bias, softplus, the 128 -> 4 output layer, tanh).
+//   * TMEM columns: D [0,128)  A_hi [128,256)  A_lo [256,384)  (512 allocated).
+//   * per-trajectory adaptive stepping: every lane has its own t / dt / accept-reject; a finished lane claims the next
+//     trajectory from the global queue; the stage loop is CTA-synchronous (one MMA batch per stage evaluation).
+//   * every stage, including stage 0, is evaluated each step (the FSAL value f(t1, y1) equals f at the next step's
+//     (t0, y0) bit for bit, so re-evaluating it is value-identical to diffrax's reuse; runge_kutta.py:684-695).
+#pragma once
+#include "ensemble_kernel.cuh"
+
+namespace dfx {
+
+constexpr int kMlpD = 4, kMlpW = 128;
+constexpr int kMlpThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+
+struct MlpSmem {
+  float Bhi[kMlpW * kMlpW];     // W2 hi, canonical K-major no-swizzle: (n,k) -> (n/8)*1024 + (k/4)*32 + (n%8)*4 + (k%4)
+  float Blo[kMlpW * kMlpW];
+  float W1[kMlpW * kMlpD];
+  float b1[kMlpW];
+  float b2[kMlpW];
+  float W3[kMlpD * kMlpW];
+  float b3[kMlpD];
+  float part[2][kMlpW][kMlpD];  // layer-3 partial sums of the two hidden-unit halves
+  long long idx[kMlpW];
+  unsigned long long mbar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor), K-major, SWIZZLE_NONE:
+// start address, LBO (K-adjacent core matrices) and SBO (8-row groups) in 16-byte units, version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version_
+  return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+// UMMA instruction descriptor (InstrDescriptor): D fp32, A/B TF32, both K-major, N=128, M=128.
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kIdescTf32), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}\n" :: "r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+
+// softplus = max(x,0) + log1p(exp(-|x|))   (jax.nn.softplus = logaddexp(x, 0))
+template <bool FAST> __device__ __forceinline__ float mlp_softplus(float x) {
+  if constexpr (FAST) {
+    // SFU path: e = 2^(-|x| log2 e) (MUFU.EX2), log1p(e) = ln2 * log2(1 + e) (MUFU.LG2); abs. error ~1e-7
+    const float e = exp2f(-fabsf(x) * 1.4426950408889634f);
+    return fmaxf(x, 0.0f) + 0.6931471805599453f * __log2f(1.0f + e);
+  } else {
+    return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
+  }
+}
+
+template <class Solver, bool FAST_ACT>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
+  using R = float;
+  constexpr int D = kMlpD, W = kMlpW, S = Solver::S;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  MlpSmem &sm = *reinterpret_cast<MlpSmem *>(smem_raw);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+  const int col0 = half * 64;  // this thread's hidden units [col0, col0 + 64)
+
+  // ---------------- one-time set-up: weights -> smem (W2 split into TF32 hi / lo), TMEM, mbarrier ----------------
+  const float *gW1 = w, *gb1 = gW1 + W * D, *gW2 = gb1 + W, *gb2 = gW2 + W * W, *gW3 = gb2 + W, *gb3 = gW3 + D * W;
+  for (int i = tid; i < W * W; i += kMlpThreads) {
+    const int n = i >> 7, k = i & 127;  // W2[n][k], (out, in) row-major == K-major B operand
+    const float v = __ldg(gW2 + i), hi = to_tf32(v), lo = to_tf32(v - hi);
+    const int off = (n >> 3) * 1024 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
+    sm.Bhi[off] = hi;
+    sm.Blo[off] = lo;
+  }
+  for (int i = tid; i < W * D; i += kMlpThreads) { sm.W1[i] = __ldg(gW1 + i); sm.W3[i] = __ldg(gW3 + i); }
+  for (int i = tid; i < W; i += kMlpThreads) { sm.b1[i] = __ldg(gb1 + i); sm.b2[i] = __ldg(gb2 + i); }
+  if (tid < D) sm.b3[tid] = __ldg(gb3 + tid);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's lane quadrant
+  const uint32_t mbar = smem_u32(&sm.mbar);
+  const uint64_t bdesc_hi = make_b_desc(smem_u32(sm.Bhi), 128, 4096), bdesc_lo = make_b_desc(smem_u32(sm.Blo), 128, 4096);
+  uint32_t phase = 0;
+
+  // ---------------- the MLP evaluation: all 256 threads, CTA-synchronous ----------------
+  auto eval = [&](const R (&yin)[D], R (&fout)[D]) {
+    // layer 1 (4 -> 128) + softplus on the CUDA cores; split to TF32 hi/lo; straight into TMEM as the A operand
+#pragma unroll
+    for (int c16 = 0; c16 < 4; ++c16) {
+      uint32_t vh[16], vl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int o = col0 + c16 * 16 + j;
+        const float4 w1 = *reinterpret_cast<const float4 *>(&sm.W1[o * D]);
+        float acc = w1.x * yin[0];
+        acc += w1.y * yin[1];
+        acc += w1.z * yin[2];
+        acc += w1.w * yin[3];
+        const float h = mlp_softplus<FAST_ACT>(acc + sm.b1[o]);
+        const float hi = to_tf32(h), lo = to_tf32(h - hi);
+        vh[j] = __float_as_uint(hi);
+        vl[j] = __float_as_uint(lo);
+      }
+      tmem_st16(t_lane + 128 + col0 + c16 * 16, vh);
+      tmem_st16(t_lane + 256 + col0 + c16 * 16, vl);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    // hidden layer on the tensor core: 3 x 16 MMAs of 128 x 128 x 8 issued by one thread
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a_col = (pass == 2) ? 256u : 128u;            // A_lo only in the third pass
+        const uint64_t bd = (pass == 1) ? bdesc_lo : bdesc_hi;       // B_lo only in the second pass
+#pragma unroll
+        for (int kk = 0; kk < W / 8; ++kk)
+          umma_tf32_ts(tmem, tmem + a_col + kk * 8, bd + (uint64_t)(kk * (256 >> 4)), (pass | kk) ? 1u : 0u);
+      }
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: D row -> + b2 -> softplus -> partial 128 -> 4 output layer over this thread's 64 hidden units
+    R acc3[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc3[c] = 0.0f;
+#pragma unroll
+    for (int c16 = 0; c16 < 4; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(t_lane + col0 + c16 * 16, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int o = col0 + c16 * 16 + j;
+        const float h2 = mlp_softplus<FAST_ACT>(__uint_as_float(v[j]) + sm.b2[o]);
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc3[c] += sm.W3[c * W + o] * h2;
+      }
+    }
+    *reinterpret_cast<float4 *>(&sm.part[half][row][0]) = make_float4(acc3[0], acc3[1], acc3[2], acc3[3]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    const float4 p0 = *reinterpret_cast<const float4 *>(&sm.part[0][row][0]);
+    const float4 p1 = *reinterpret_cast<const float4 *>(&sm.part[1][row][0]);
+    fout[0] = tanhf((p0.x + p1.x) + sm.b3[0]);
+    fout[1] = tanhf((p0.y + p1.y) + sm.b3[1]);
+    fout[2] = tanhf((p0.z + p1.z) + sm.b3[2]);
+    fout[3] = tanhf((p0.w + p1.w) + sm.b3[3]);
+  };
+
+  // ---------------- per-lane trajectory state (identical in both threads of a row) ----------------
+  bool active = false, exhausted = false;
+  long long idx = -1;
+  R y[D];
+  R tprev = 0.f, tnext = 0.f, t0 = 0.f, t1 = 0.f, direction = 1.f, t1_clip_floor = 0.f;
+  R pid_inv = 1.f, pid_prev_inv = 1.f;
+  bool at_dtmin = false;
+  int cs_steps_completed = 1, cs_num_steps = 0;
+  int num_steps = 0, num_accepted = 0, result = DFX_RESULT_SUCCESSFUL;
+#pragma unroll
+  for (int c = 0; c < D; ++c) y[c] = 0.f;
+  const R sqrt_d = 2.0f;  // sqrt(D), D == 4
+
+  for (;;) {
+    // ---- refill (claims are made by the half-0 thread of each row and shared through smem) ----
+    if (!exhausted) {
+      if (half == 0) {
+        const long long got = claim_work(!active, p.work_counter);
+        sm.idx[row] = got;
+      }
+      __syncthreads();
+      const long long got = sm.idx[row];
+      const bool fail = !active && got >= p.n_traj;
+      if (!active && got >= 0 && got < p.n_traj) {
+        idx = got;
+        const R a = p.t0_arr ? p.t0_arr[idx] : p.t0, b = p.t1_arr ? p.t1_arr[idx] : p.t1;
+        direction = (a < b) ? 1.f : -1.f;
+        t0 = a * direction;
+        t1 = b * direction;
+#pragma unroll
+        for (int c = 0; c < D; ++c) y[c] = p.y0[idx * D + c];
+        R dt0 = p.has_dt0 ? p.dt0 * direction : 0.01f;  // pid.py:48-49 through WrapTerm
+        if (p.controller == DFX_CTRL_PID) {
+          if (p.has_dtmax) dt0 = jnp_min(dt0, p.dtmax);
+          if (p.has_dtmin) dt0 = jnp_max(dt0, p.dtmin);
+        } else {
+          const R dt0_up = __int_as_float(__float_as_int(dt0) + (dt0 > 0.f ? 1 : (dt0 < 0.f ? -1 : 1)));
+          cs_num_steps = (int)ceil((double)((t1 - t0) / dt0_up));
+          cs_steps_completed = 1;
+        }
+        tprev = t0;
+        tnext = jnp_min(t0 + dt0, t1);
+        t1_clip_floor = prev_n<R>(t1, 100);
+        pid_inv = 1.f; pid_prev_inv = 1.f; at_dtmin = false;
+        num_steps = 0; num_accepted = 0; result = DFX_RESULT_SUCCESSFUL;
+        active = true;
+      }
+      exhausted = __syncthreads_or(fail) != 0;
+    }
+    if (__syncthreads_and(!active)) break;
+
+    // ---- one attempted step for every lane of the CTA ----
+    const bool run = active && (tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL);
+    const R st0 = tprev, st1 = tnext;
+    const R dt = st1 - st0;
+    const R control = direction * dt;
+    R k[S][D], y1[D], yerr[D], yi[D], fi[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) yi[c] = y[c];
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      if (i > 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          R incr = 0.f;
+#pragma unroll
+          for (int j = 0; j < i; ++j)
+            if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];
+          yi[c] = y[c] + incr;
+        }
+      }
+      eval(yi, fi);  // the field is autonomous: stage times do not enter
+#pragma unroll
+      for (int c = 0; c < D; ++c) k[i][c] = control * fi[c];
+    }
+    if constexpr (Solver::kSsal) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) y1[c] = yi[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        R incr = 0.f;
+#pragma unroll
+        for (int j = 0; j < S; ++j)
+          if (Solver::hBsol(j) != 0.0) incr += Solver::template b_sol<R>(j) * k[j][c];
+        y1[c] = y[c] + incr;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      R e = 0.f;
+#pragma unroll
+      for (int j = 0; j < S; ++j)
+        if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
+      yerr[c] = e;
+    }
+
+    if (run) {
+      bool keep;
+      R next_t0, next_t1;
+      if (p.controller == DFX_CTRL_PID) {  // pid.py:394-567 (faithful fp32 path)
+        bool nan_any = false;
+#pragma unroll
+        for (int c = 0; c < D; ++c) nan_any |= r_isnan(y1[c]);
+        R ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const R e = r_isnan(yerr[c]) ? Num<R>::inf() : yerr[c];
+          const R yc = nan_any ? y[c] : y1[c];
+          const R sc = e / (p.atol + fmaxf(fabsf(y[c]), fabsf(yc)) * p.rtol);
+          ss += sc * sc;
+        }
+        const R scaled_error = sqrtf(ss) / sqrt_d;
+        keep = scaled_error < 1.f;
+        if (p.has_dtmin) keep = keep || at_dtmin;
+        R inv = 1.f / scaled_error;
+        R factor = p.safety;
+        if (p.use_c1) factor = factor * powf(inv, p.coeff1);
+        if (p.use_c2) factor = factor * powf(pid_inv, p.coeff2);
+        if (p.use_c3) factor = factor * powf(pid_prev_inv, p.coeff3);
+        factor = jnp_min(jnp_max(factor, keep ? 1.f : p.factormin), keep ? p.factormax : p.safety);
+        R dtn = dt * factor;
+        if (inv == 0.f || r_isinf(inv)) inv = 1.f;
+        if (p.has_dtmax) dtn = jnp_min(dtn, p.dtmax);
+        if (p.has_dtmin) {
+          if (!p.force_dtmin && dtn < p.dtmin && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_DT_MIN_REACHED;
+          if (at_dtmin && factor == 1.f) dtn = p.dtmin;
+          at_dtmin = dtn <= p.dtmin;
+          dtn = jnp_max(dtn, p.dtmin);
+        }
+        next_t0 = keep ? st1 : st0;
+        next_t1 = next_t0 + dtn;
+        if (keep) { pid_prev_inv = pid_inv; pid_inv = inv; }
+      } else {  // constant.py:57-104
+        keep = true;
+        cs_steps_completed += 1;
+        R t1n = t0 + (t1 - t0) * ((R)cs_steps_completed / (R)cs_num_steps);
+        if (cs_steps_completed == cs_num_steps) t1n = t1;
+        next_t0 = st1;
+        next_t1 = t1n;
+      }
+      const R tprev_new = next_t0;
+      R tnext_new = next_t1;
+      if (next_t1 > t1_clip_floor) tnext_new = keep ? t1 : tprev_new + 0.5f * (t1 - tprev_new);
+      num_steps += 1;
+      num_accepted += keep ? 1 : 0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) y[c] = keep ? y1[c] : y[c];
+      tprev = tprev_new;
+      tnext = tnext_new;
+    }
+    const bool finished = active && !((tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL));
+    if (finished) {
+      if ((tprev < t1) && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_MAX_STEPS_REACHED;
+      if (half == 0) {
+        if (p.save_t1) {
+          p.ts_out[idx] = tprev * direction;
+          *reinterpret_cast<float4 *>(&p.ys_out[idx * D]) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+        p.stats[idx * 3 + 0] = num_steps;
+        p.stats[idx * 3 + 1] = num_accepted;
+        p.stats[idx * 3 + 2] = num_steps - num_accepted;
+        p.result[idx] = result;
+        if (p.y_final) *reinterpret_cast<float4 *>(&p.y_final[idx * D]) = make_float4(y[0], y[1], y[2], y[3]);
+        if (p.t_final) p.t_final[idx] = tprev * direction;
+      }
+      active = false;
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+}  // namespace dfx

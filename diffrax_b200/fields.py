@@ -116,3 +116,50 @@ class OrnsteinUhlenbeck(Field):
 
     def params(self):
         return self.p
+
+
+class MLP(Field):
+    """Neural-ODE vector field: ``eqx.nn.MLP(in=d, out=d, width, depth=2, activation=softplus, final_activation=tanh)``
+    (docs/examples/neural_ode.ipynb cell 5).  ``layers`` is ``[(W1, b1), (W2, b2), (W3, b3)]`` with eqx ``Linear``
+    weight shapes ``(out, in)``.  Built-in kernels exist for d=4, width=128, fp32."""
+    name, dim = "mlp", 4
+
+    def __init__(self, layers):
+        import numpy as np
+        self.layers = [(np.asarray(W), np.asarray(b)) for W, b in layers]
+        if len(self.layers) != 3:
+            raise ValueError("MLP functor supports depth=2 (three Linear layers)")
+        self.width = self.layers[0][0].shape[0]
+        self.dim = self.layers[0][0].shape[1]
+        self._cache = {}
+
+    @staticmethod
+    def init(key_seed: int, d: int = 4, width: int = 128, dtype="float32"):
+        """eqx.nn.Linear initialisation: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weights and biases (NumPy RNG)."""
+        import numpy as np
+        rng = np.random.default_rng(key_seed)
+        layers = []
+        for fan_in, fan_out in ((d, width), (width, width), (width, d)):
+            lim = 1.0 / np.sqrt(fan_in)
+            layers.append((rng.uniform(-lim, lim, (fan_out, fan_in)).astype(dtype), rng.uniform(-lim, lim, fan_out).astype(dtype)))
+        return MLP(layers)
+
+    def params(self):
+        return [float(self.width), 2.0]
+
+    def flat(self, dtype):
+        import numpy as np
+        return np.concatenate([np.concatenate([W.ravel(), b.ravel()]) for W, b in self.layers]).astype(dtype)
+
+    def oracle_params(self):
+        """[width, depth, W1, b1, W2, b2, W3, b3] as doubles (the oracle's field_params layout)."""
+        import numpy as np
+        return np.concatenate([[float(self.width), 2.0], self.flat(np.float64)])
+
+    def weights(self, xp, dtype):
+        import numpy as np
+        key = (type(xp).__name__, str(getattr(xp, "device", "")), str(dtype))
+        if key not in self._cache:
+            np_dt = np.float32 if "32" in str(dtype) else np.float64
+            self._cache[key] = xp.asarray(self.flat(np_dt), dtype)
+        return self._cache[key]

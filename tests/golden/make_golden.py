@@ -43,6 +43,10 @@ case("pid_coeffs_dtmax_heun", field="decay", params=[0.7], solver="heun", y0=rng
 case("f32_tsit5", field="lorenz", params=[10.0, 28.0, 8.0 / 3.0], solver="tsit5", dtype=np.float32,
      y0=np.stack([rng.uniform(-15, 15, n), rng.uniform(-20, 20, n), rng.uniform(5, 45, n)], 1).astype(np.float32),
      t0=0.0, t1=1.0, dt0=None, rtol=1e-6, atol=1e-6)
+import diffrax_b200 as _dfx  # noqa: E402  (host-side weight initialiser only; no CUDA needed)
+_mlp = _dfx.fields.MLP.init(3, d=4, width=128)
+case("c4_mlp_tsit5_f32", field="mlp", params=_mlp.oracle_params(), solver="tsit5", dtype=np.float32,
+     y0=rng.standard_normal((n, 4)).astype(np.float32), t0=0.0, t1=10.0, dt0=None, rtol=1e-3, atol=1e-6)
 keys = oracle.split(oracle.prng_key(2024), n)
 for dt_, tag in ((np.float64, "f64"), (np.float32, "f32")):
     case(f"c5_ou_heun_{tag}", field="ou", params=[1.0, 0.0, 0.5], solver="heun", dtype=dt_, y0=np.ones((n, 1), dt_), t0=0.0, t1=1.0,
