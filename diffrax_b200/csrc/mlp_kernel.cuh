@@ -37,6 +37,7 @@ struct MlpSmem {
   float W3[kMlpD * kMlpW];
   float b3[kMlpD];
   float part[2][kMlpW][kMlpD];  // layer-3 partial sums of the two hidden-unit halves
+  float k[14 * kMlpD][kMlpThreads];  // stage values k[i][c] of every thread (element-major: conflict-free), S <= 14
   long long idx[kMlpW];
   unsigned long long mbar;
   uint32_t tmem_base;
@@ -98,8 +99,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 template <bool FAST> __device__ __forceinline__ float mlp_softplus(float x) {
   if constexpr (FAST) {
     // SFU path: e = 2^(-|x| log2 e) (MUFU.EX2), log1p(e) = ln2 * log2(1 + e) (MUFU.LG2); abs. error ~1e-7
-    const float e = exp2f(-fabsf(x) * 1.4426950408889634f);
-    return fmaxf(x, 0.0f) + 0.6931471805599453f * __log2f(1.0f + e);
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(x) * 1.4426950408889634f));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+    return fmaxf(x, 0.0f) + 0.6931471805599453f * l;
   } else {
     return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
   }
@@ -150,7 +153,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
   // ---------------- the MLP evaluation: all 256 threads, CTA-synchronous ----------------
   auto eval = [&](const R (&yin)[D], R (&fout)[D]) {
     // layer 1 (4 -> 128) + softplus on the CUDA cores; split to TF32 hi/lo; straight into TMEM as the A operand
-#pragma unroll
+#pragma unroll 1
     for (int c16 = 0; c16 < 4; ++c16) {
       uint32_t vh[16], vl[16];
 #pragma unroll
@@ -192,7 +195,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
     R acc3[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) acc3[c] = 0.0f;
-#pragma unroll
+#pragma unroll 1
     for (int c16 = 0; c16 < 4; ++c16) {
       uint32_t v[16];
       tmem_ld16(t_lane + col0 + c16 * 16, v);
@@ -272,45 +275,48 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
     const R st0 = tprev, st1 = tnext;
     const R dt = st1 - st0;
     const R control = direction * dt;
-    R k[S][D], y1[D], yerr[D], yi[D], fi[D];
+    // The stage loop is rolled (one copy of the MLP evaluation in the instruction stream - the unrolled version
+    // thrashed the instruction cache with only 8 warps per SM); the stage values therefore live in shared memory.
+    R y1[D], yerr[D], yi[D], fi[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) yi[c] = y[c];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < S; ++i) {
       if (i > 0) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-          R incr = 0.f;
+        for (int c = 0; c < D; ++c) yi[c] = 0.f;
+        for (int j = 0; j < i; ++j) {
+          const R a = Solver::template a<R>(i, j);  // structural zeros contribute exact zeros
 #pragma unroll
-          for (int j = 0; j < i; ++j)
-            if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];
-          yi[c] = y[c] + incr;
+          for (int c = 0; c < D; ++c) yi[c] += a * sm.k[j * D + c][tid];
         }
+#pragma unroll
+        for (int c = 0; c < D; ++c) yi[c] = y[c] + yi[c];
       }
       eval(yi, fi);  // the field is autonomous: stage times do not enter
 #pragma unroll
-      for (int c = 0; c < D; ++c) k[i][c] = control * fi[c];
+      for (int c = 0; c < D; ++c) sm.k[i * D + c][tid] = control * fi[c];
     }
     if constexpr (Solver::kSsal) {
 #pragma unroll
       for (int c = 0; c < D; ++c) y1[c] = yi[c];
     } else {
 #pragma unroll
-      for (int c = 0; c < D; ++c) {
-        R incr = 0.f;
+      for (int c = 0; c < D; ++c) y1[c] = 0.f;
+      for (int j = 0; j < S; ++j) {
+        const R b = Solver::template b_sol<R>(j);
 #pragma unroll
-        for (int j = 0; j < S; ++j)
-          if (Solver::hBsol(j) != 0.0) incr += Solver::template b_sol<R>(j) * k[j][c];
-        y1[c] = y[c] + incr;
+        for (int c = 0; c < D; ++c) y1[c] += b * sm.k[j * D + c][tid];
       }
+#pragma unroll
+      for (int c = 0; c < D; ++c) y1[c] = y[c] + y1[c];
     }
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
-      R e = 0.f;
+    for (int c = 0; c < D; ++c) yerr[c] = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const R b = Solver::template b_err<R>(j);
 #pragma unroll
-      for (int j = 0; j < S; ++j)
-        if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
-      yerr[c] = e;
+      for (int c = 0; c < D; ++c) yerr[c] += b * sm.k[j * D + c][tid];
     }
 
     if (run) {
