@@ -269,7 +269,7 @@ def run_ours(args):
         barrier()
         e2e_s = time.perf_counter() - t0
         h2d = y0_host.numel() * y0_host.element_size() + (0 if w["keys"] is None else w["keys"].nbytes)
-        d2h = sum(int(t.numel() * t.element_size()) for t in (sh.ts, sh.ys, sh.result, sh.y_final, sh.t_final)) \
+        d2h = sum(int(t.numel() * t.element_size()) for t in (sh.ts, sh.ys, sh.result)) \
             + 3 * int(sh.stats["num_steps"].numel()) * 4
 
     # ---- max over ranks, totals over ranks ----

@@ -583,8 +583,11 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     ys_out = xp.empty((n, T, d), rdt)
     stats = xp.empty((n, 3), i32)
     result = xp.empty((n,), i32)
-    y_final = xp.empty((n, d), rdt)
-    t_final = xp.empty((n,), rdt)
+    # final state: with SaveAt(t1=True) it is ys[:, -1] already; a separate buffer only when t1 is not saved
+    y_final = t_final = None
+    if not saveat.t1:
+        y_final = xp.empty((n, d), rdt)
+        t_final = xp.empty((n,), rdt)
     D.ts_out, D.ys_out, D.stats, D.result = xp.ptr(ts_out), xp.ptr(ys_out), xp.ptr(stats), xp.ptr(result)
     D.y_final, D.t_final = xp.ptr(y_final), xp.ptr(t_final)
     dense = None
@@ -611,6 +614,8 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
                                            dirn, t0_norm, y0a, xp)
     elif dense is not None:
         interpolation = dense  # raw buffers on the host path
+    if y_final is None and T > 0:
+        y_final, t_final = ys_out[:, T - 1, :], ts_out[:, T - 1]   # views: the SaveAt(t1) slot is the last one
     if scalar_state:
         ys_out = ys_out[..., 0]
         y_final = y_final[..., 0]

@@ -336,23 +336,22 @@ int dfx_ensemble_solve(const dfx_solve_desc *d, void *cuda_stream) {
   return fn(d, cuda_stream);
 }
 
-// Host-buffer variant: pinned staging is the caller's business (pass pinned pointers for full
-// PCIe speed); this does plain cudaMemcpyAsync on one stream and synchronises it.
-int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
-  if (int rc = check_desc(h)) return rc;
-  if (dfx_device_count() <= device) { set_error("CUDA device %d not available", device); return DFX_ERR_NO_DEVICE; }
-  DFX_CUDA_OK(cudaSetDevice(device));
-  cudaStream_t st;
-  DFX_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+// Host-buffer variant.  The batch is cut into chunks that are pipelined over two streams (H2D of chunk i+1 and D2H of
+// chunk i-1 overlap the kernel of chunk i); trajectories are independent, so chunking does not change any result.
+// Pass pinned host pointers for full PCIe speed.  Dense output is not chunked (its buffers are large; one chunk).
+static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cudaStream_t st, std::vector<void *> &allocs) {
   const size_t es = h->dtype == DFX_F64 ? 8 : 4;
-  const size_t N = (size_t)h->n_traj, D = (size_t)h->dim;
+  const size_t N = (size_t)cnt, D = (size_t)h->dim;
   const int T = dfx_out_size(h);
   const int S = dfx_num_stages(h->solver_id);
   const size_t ms = (size_t)h->max_steps;
   dfx_solve_desc d = *h;
-  std::vector<void *> allocs;
+  d.n_traj = cnt;
   std::vector<std::tuple<void *, void *, size_t>> d2h;  // host dst, device src, bytes
   int rc = 0;
+  auto off = [&](const void *base, size_t per_traj_bytes) -> const char * {
+    return base ? (const char *)base + (size_t)lo * per_traj_bytes : nullptr;
+  };
   auto dev_in = [&](const void *src, size_t bytes) -> void * {
     if (!src || bytes == 0 || rc) return nullptr;
     void *p = nullptr;
@@ -361,34 +360,34 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
     if (cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D copy failed"); rc = DFX_ERR_CUDA; }
     return p;
   };
-  auto dev_out = [&](void *dst, size_t bytes) -> void * {
+  auto dev_out = [&](const void *dst, size_t bytes) -> void * {
     if (!dst || bytes == 0 || rc) return nullptr;
     void *p = nullptr;
     if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) { set_error("cudaMallocAsync(%zu) failed", bytes); rc = DFX_ERR_CUDA; return nullptr; }
     allocs.push_back(p);
-    d2h.emplace_back(dst, p, bytes);
+    d2h.emplace_back((void *)dst, p, bytes);
     return p;
   };
-  d.y0 = dev_in(h->y0, N * D * es);
-  d.t0_per_traj = dev_in(h->t0_per_traj, N * es);
-  d.t1_per_traj = dev_in(h->t1_per_traj, N * es);
+  d.y0 = dev_in(off(h->y0, D * es), N * D * es);
+  d.t0_per_traj = dev_in(off(h->t0_per_traj, es), N * es);
+  d.t1_per_traj = dev_in(off(h->t1_per_traj, es), N * es);
   d.save_ts = dev_in(h->save_ts, (size_t)h->n_save_ts * es);
-  d.bm_keys = (const uint32_t *)dev_in(h->bm_keys, N * 8);
+  d.bm_keys = (const uint32_t *)dev_in(off(h->bm_keys, 8), N * 8);
   d.field_weights = dev_in(h->field_weights, (size_t)h->n_field_weights * es);
-  d.ts_out = dev_out(h->ts_out, N * T * es);
-  d.ys_out = dev_out(h->ys_out, N * T * D * es);
-  d.stats = (int32_t *)dev_out(h->stats, N * 3 * 4);
-  d.result = (int32_t *)dev_out(h->result, N * 4);
-  d.save_count = (int32_t *)dev_out(h->save_count, N * 4);
+  d.ts_out = dev_out(off(h->ts_out, T * es), N * T * es);
+  d.ys_out = dev_out(off(h->ys_out, T * D * es), N * T * D * es);
+  d.stats = (int32_t *)dev_out(off(h->stats, 12), N * 3 * 4);
+  d.result = (int32_t *)dev_out(off(h->result, 4), N * 4);
+  d.save_count = (int32_t *)dev_out(off(h->save_count, 4), N * 4);
   if (h->save_dense) {
-    d.dense_ts = dev_out(h->dense_ts, N * (ms + 1) * es);
-    d.dense_y0 = dev_out(h->dense_y0, N * ms * D * es);
-    d.dense_y1 = dev_out(h->dense_y1, N * ms * D * es);
-    d.dense_k = dev_out(h->dense_k, N * ms * S * D * es);
-    d.dense_count = (int32_t *)dev_out(h->dense_count, N * 4);
+    d.dense_ts = dev_out(off(h->dense_ts, (ms + 1) * es), N * (ms + 1) * es);
+    d.dense_y0 = dev_out(off(h->dense_y0, ms * D * es), N * ms * D * es);
+    d.dense_y1 = dev_out(off(h->dense_y1, ms * D * es), N * ms * D * es);
+    d.dense_k = dev_out(off(h->dense_k, ms * S * D * es), N * ms * S * D * es);
+    d.dense_count = (int32_t *)dev_out(off(h->dense_count, 4), N * 4);
   }
-  d.y_final = dev_out(h->y_final, N * D * es);
-  d.t_final = dev_out(h->t_final, N * es);
+  d.y_final = dev_out(off(h->y_final, D * es), N * D * es);
+  d.t_final = dev_out(off(h->t_final, es), N * es);
   if (!rc) rc = dfx_ensemble_solve(&d, (void *)st);
   if (!rc)
     for (auto &c : d2h)
@@ -397,10 +396,32 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
         rc = DFX_ERR_CUDA;
         break;
       }
-  for (void *p : allocs) cudaFreeAsync(p, st);
-  cudaError_t e = cudaStreamSynchronize(st);
-  if (!rc && e != cudaSuccess) { set_error("stream sync failed: %s", cudaGetErrorString(e)); rc = DFX_ERR_CUDA; }
-  cudaStreamDestroy(st);
+  return rc;
+}
+
+int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
+  if (int rc = check_desc(h)) return rc;
+  if (dfx_device_count() <= device) { set_error("CUDA device %d not available", device); return DFX_ERR_NO_DEVICE; }
+  DFX_CUDA_OK(cudaSetDevice(device));
+  // chunks of >= 128K trajectories keep every SM busy; at most 8 chunks; dense output stays in one piece
+  int64_t nchunks = h->save_dense ? 1 : h->n_traj / (128 * 1024);
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > 8) nchunks = 8;
+  cudaStream_t st[2];
+  const int nstreams = nchunks > 1 ? 2 : 1;
+  for (int i = 0; i < nstreams; ++i) DFX_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+  std::vector<void *> allocs[2];
+  int rc = 0;
+  for (int64_t c = 0; c < nchunks && !rc; ++c) {
+    const int64_t lo = h->n_traj * c / nchunks, hi = h->n_traj * (c + 1) / nchunks;
+    rc = solve_host_chunk(h, lo, hi - lo, st[c % nstreams], allocs[c % nstreams]);
+  }
+  for (int i = 0; i < nstreams; ++i) {
+    for (void *p : allocs[i]) cudaFreeAsync(p, st[i]);
+    cudaError_t e = cudaStreamSynchronize(st[i]);
+    if (!rc && e != cudaSuccess) { set_error("stream sync failed: %s", cudaGetErrorString(e)); rc = DFX_ERR_CUDA; }
+    cudaStreamDestroy(st[i]);
+  }
   return rc;
 }
 

@@ -292,6 +292,49 @@ def test_per_trajectory_regions_and_t0_equals_t1(dev):
     assert np.allclose(to_np(sol.ys)[:, 1, 0], y0[:, 0] * np.exp(-1.3 * t1), rtol=1e-6)
 
 
+def test_mlp_tensor_core_kernel_matches_cuda_core_functor_and_oracle(dev, monkeypatch):
+    """BASELINE config 4: the tcgen05 (3xTF32) kernel vs the exact-fp32 CUDA-core functor vs the oracle, and the
+    fall-back to the generic kernel for SaveAt modes the tensor-core kernel does not implement."""
+    mlp = make_golden._mlp
+    rng = np.random.default_rng(5)
+    n = 3000  # not a multiple of 128: exercises partially filled tiles and the queue drain
+    y0 = rng.standard_normal((n, 4)).astype(np.float32)
+    term, ctrl = dfx.ODETerm(mlp), dfx.PIDController(rtol=1e-3, atol=1e-6)
+    y0d = torch.tensor(y0, device=dev)
+    tc = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d, stepsize_controller=ctrl)
+    monkeypatch.setenv("DFX_MLP_NO_TC", "1")
+    cc = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d, stepsize_controller=ctrl)
+    monkeypatch.delenv("DFX_MLP_NO_TC")
+    o = oracle.solve("mlp", y0, 0.0, 10.0, None, solver="tsit5", params=mlp.oracle_params(), dtype=np.float32, rtol=1e-3, atol=1e-6)
+    for sol in (tc, cc):
+        assert int((sol.result != 0).sum()) == 0
+        assert relerr_state(to_np(sol.ys), o["ys"]) < RTOL32                     # north star: 1e-4 in fp32
+        assert np.abs(to_np(sol.stats["num_accepted_steps"]) - o["stats"][:, 1]).max() <= 1
+        assert (to_np(sol.stats["num_steps"]) == o["stats"][:, 0]).mean() > 0.95
+    assert relerr_state(to_np(tc.ys), to_np(cc.ys)) < RTOL32
+    # constant steps: no controller noise, so the two GPU paths agree to fp32 rounding
+    a = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 2.0, 0.25, y0d)
+    monkeypatch.setenv("DFX_MLP_NO_TC", "1")
+    b = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 2.0, 0.25, y0d)
+    monkeypatch.delenv("DFX_MLP_NO_TC")
+    assert relerr_state(to_np(a.ys), to_np(b.ys)) < 2e-5   # SFU softplus (abs. err ~1e-7 per unit) + 3xTF32 vs exact fp32
+    # SaveAt(ts) is served by the generic kernel with the same functor
+    ts = np.linspace(0, 10, 6).astype(np.float32)
+    r = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d[:256], saveat=dfx.SaveAt(ts=ts), stepsize_controller=ctrl)
+    orr = oracle.solve("mlp", y0[:256], 0.0, 10.0, None, solver="tsit5", params=mlp.oracle_params(), dtype=np.float32,
+                       rtol=1e-3, atol=1e-6, save_ts=ts, save_t1=False)
+    assert relerr_state(to_np(r.ys), orr["ys"]) < RTOL32
+
+
+def test_tensor_core_sass_present():
+    """The MLP kernel really is tcgen05: UTC*MMA + TMEM load/store opcodes in the shipped cubin."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    out = subprocess.run(["cuobjdump", "-sass", os.path.join(root, "diffrax_b200", "csrc", "_obj", "inst_mlp.o")],
+                         capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out and "LDTM" in out and "STTM" in out
+
+
 def test_failure_codes_and_throw(dev):
     y0 = torch.tensor([[1.0, 2.0, 20.0]] * 8, device=dev, dtype=torch.float64)
     term = dfx.ODETerm(dfx.fields.Lorenz())
@@ -320,6 +363,10 @@ def test_full_size_properties_c2(dev):
     b = dfx.diffeqsolve(term, dfx.Dopri5(), 0.0, 2.0, None, y0d[perm].contiguous(), stepsize_controller=ctrl)
     assert torch.equal(a.ys[perm], b.ys) and torch.equal(a.stats["num_steps"][perm], b.stats["num_steps"])
     assert bool(torch.isfinite(a.ys).all()) and int((a.result != 0).sum()) == 0
+    # host-buffer entry point at full size: 8 chunks pipelined over two streams, same bits as the device path
+    h = dfx.diffeqsolve(term, dfx.Dopri5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl)
+    assert np.array_equal(h.ys, to_np(a.ys)) and np.array_equal(h.stats["num_steps"], to_np(a.stats["num_steps"]))
+    assert np.array_equal(h.ts, to_np(a.ts)) and np.array_equal(h.result, to_np(a.result))
     sl = slice(12345, 12345 + 4096)
     o = oracle.solve("lorenz", y0[sl], 0.0, 2.0, None, solver="dopri5", params=[10.0, 28.0, 8.0 / 3.0], rtol=1e-8, atol=1e-8)
     assert np.abs(to_np(a.stats["num_accepted_steps"])[sl] - o["stats"][:, 1]).max() <= 1
