@@ -143,6 +143,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
+    summary (profiles/r01_<workload>_*_ncu_full.txt), in bytes per launch; None when no capture is committed."""
+    import glob
+    import re
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r01_{workload}_*ncu_full.txt"))):
+        tot, units = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for m in re.finditer(r"dram__bytes_(read|write)\.sum \[(\w+)\] = ([0-9.]+)", open(f).read()):
+            tot += float(m.group(3)) * units.get(m.group(2), 1.0)
+        if tot > 0:
+            return tot
+    return None
+
+
 def cpu_port_rate(w, sample: int, threads: int = 0):
     """accepted steps / s of the oracle (CPU restatement) on `sample` trajectories."""
     import oracle
@@ -332,6 +346,7 @@ def run_ours(args):
                     "frac": achieved / peak if peak > 0 else None, "traffic": None,
                     "peak_source": "dfx_measure_int_peak: add/rotate/xor chains, measured in this run",
                     "threefry_blocks_per_step": blocks}
+        roof["traffic"] = ncu_traffic(args.workload.split("_")[0])
         cpu_sample = min(args.cpu_sample, n_local)
         cpu_rate, cpu_dt, cores = cpu_port_rate(w, cpu_sample)
         line = {

@@ -69,6 +69,7 @@ struct SolveParams {
   int *stats, *result, *save_count;
   R *dense_ts, *dense_y0, *dense_y1, *dense_k;
   int *dense_count;
+  int dense_coop;    // SaveAt(dense): stage records through shared memory and store them warp-cooperatively (launcher provides the smem)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
   R *y_final, *t_final;
   unsigned long long *work_counter;
@@ -152,6 +153,13 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
 
   const R sqrt_d = (R)sqrt((double)D);
 
+  // SaveAt(dense=True) staging: one record of kDenseRec values per lane, padded to an odd stride (conflict-free reads)
+  constexpr int kDenseK = DENSE_K ? S * D : 0;
+  constexpr int kDenseRec = kDenseK + 2 * D;
+  constexpr int kDenseStride = kDenseRec | 1;
+  extern __shared__ __align__(16) unsigned char dense_smem_raw[];
+  [[maybe_unused]] R *dense_smem = reinterpret_cast<R *>(dense_smem_raw);
+
   for (;;) {
     // ---------------- refill: finished lanes claim the next trajectory ----------------
     // `exhausted` is warp-uniform (it is set from a warp vote), so the collective below is convergent.
@@ -209,6 +217,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
 
     // ---------------- one attempted step (all active lanes, same instruction stream) ----------------
     bool finished = false;
+    [[maybe_unused]] long long dense_row = -1;  // >= 0: this lane staged a dense record in shared memory this iteration
     if (active) {
       const bool run = (tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL);  // 355-363, 685-687
       if (run) {
@@ -444,17 +453,28 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           if (p.save_dense && keep) {
             const long long row = idx * (long long)p.max_steps + dense_index;
             st_cs(&p.dense_ts[idx * (long long)(p.max_steps + 1) + dense_index + 1], tprev_new);
-            store_row<D>(&p.dense_y0[row * D], y, p.dense_vec_ok != 0);
-            store_row<D>(&p.dense_y1[row * D], y1, p.dense_vec_ok != 0);
-            if constexpr (DENSE_K) {
-              if (p.dense_k != nullptr) {
-                // k[S][D] is contiguous in the output row (S*D values): one lane streams whole sectors
-                R flat[S * D];
+            if (p.dense_coop) {
+              // stage this lane's record {k[S][D], y0[D], y1[D]} in shared memory; the warp flushes it below
+              R *rec = dense_smem + ((threadIdx.x >> 5) * 32 + (threadIdx.x & 31)) * kDenseStride;
 #pragma unroll
-                for (int j = 0; j < S; ++j)
+              for (int j = 0; j < S; ++j)
 #pragma unroll
-                  for (int c = 0; c < D; ++c) flat[j * D + c] = k[j][c];
-                store_row<S * D>(&p.dense_k[row * (S * D)], flat, p.dense_vec_ok != 0);
+                for (int c = 0; c < D; ++c) rec[DENSE_K ? j * D + c : 0] = k[j][c];
+#pragma unroll
+              for (int c = 0; c < D; ++c) { rec[kDenseK + c] = y[c]; rec[kDenseK + D + c] = y1[c]; }
+              dense_row = row;
+            } else {
+              store_row<D>(&p.dense_y0[row * D], y, p.dense_vec_ok != 0);
+              store_row<D>(&p.dense_y1[row * D], y1, p.dense_vec_ok != 0);
+              if constexpr (DENSE_K) {
+                if (p.dense_k != nullptr) {
+                  R flat[S * D];
+#pragma unroll
+                  for (int j = 0; j < S; ++j)
+#pragma unroll
+                    for (int c = 0; c < D; ++c) flat[j * D + c] = k[j][c];
+                  store_row<S * D>(&p.dense_k[row * (S * D)], flat, p.dense_vec_ok != 0);
+                }
               }
             }
             dense_index += 1;
@@ -471,6 +491,38 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         tnext = tnext_new;
       }
       finished = !((tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL));
+    }
+
+    // ---------------- SaveAt(dense): warp-cooperative flush of the staged records ----------------
+    // A lane's record is (S + 2) D contiguous values per output array row; written by its own lane it would be
+    // (S + 2) D / 4 separate 32-byte sector writes scattered over 32 trajectories' rows per instruction.  Here the whole
+    // warp writes one record at a time: consecutive lanes store consecutive elements, i.e. full contiguous lines.
+    if constexpr (RICH) {
+      if (p.save_dense && p.dense_coop) {
+        const unsigned staged = __ballot_sync(kFullMask, dense_row >= 0);
+        if (staged) {
+          __syncwarp();
+          const int lane = threadIdx.x & 31;
+          const R *wrec = dense_smem + (threadIdx.x >> 5) * 32 * kDenseStride;
+          for (unsigned m = staged; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const long long row = __shfl_sync(kFullMask, dense_row, src);
+#pragma unroll
+            for (int e0 = 0; e0 < kDenseRec; e0 += 32) {
+              const int e = e0 + lane;
+              if (e < kDenseRec) {
+                const R v = wrec[src * kDenseStride + e];
+                R *dst;
+                if (e < kDenseK) dst = p.dense_k + row * kDenseK + e;
+                else if (e < kDenseK + D) dst = p.dense_y0 + row * D + (e - kDenseK);
+                else dst = p.dense_y1 + row * D + (e - kDenseK - D);
+                st_cs(dst, v);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
     }
 
     // ---------------- finalize finished lanes ----------------

@@ -83,18 +83,32 @@ struct DeviceInfo { int sms; };
 int device_sm_count(int *sms);  // cached per device (api.cu)
 
 template <class R, class Field, class Solver, int LEVY, bool RICH>
-int launch_variant(const SolveParams<R> &p, const typename Field::template P<R> &fp, cudaStream_t stream) {
+int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, cudaStream_t stream) {
   auto kern = ensemble_kernel<R, Field, Solver, LEVY, RICH>;
   int sms = 0;
   if (int rc = device_sm_count(&sms)) return rc;
+  // SaveAt(dense=True): per-lane staging records for the warp-cooperative stores
+  size_t smem = 0;
+  p.dense_coop = 0;
+  if (RICH && p.save_dense && (Solver::kInterp == kInterpLinear || p.dense_k != nullptr)) {
+    const int kk = Solver::kInterp != kInterpLinear ? Solver::S * Field::kDim : 0;
+    const int stride = (kk + 2 * Field::kDim) | 1;
+    smem = (size_t)kBlockThreads * stride * sizeof(R);
+    if (smem <= 100 * 1024) {
+      p.dense_coop = 1;
+      if (smem > 48 * 1024) DFX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+      smem = 0;
+    }
+  }
   int per_sm = 0;
-  DFX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
+  DFX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
   if (per_sm < 1) per_sm = 1;
   // persistent grid: a whole number of CTAs per SM, but never more threads than trajectories
   long long blocks = (long long)sms * per_sm;
   const long long need = (p.n_traj + kBlockThreads - 1) / kBlockThreads;
   if (blocks > need) blocks = need < 1 ? 1 : need;
-  kern<<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p, fp);
+  kern<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(p, fp);
   count_launch();
   DFX_CUDA_OK(cudaGetLastError());
   return 0;
