@@ -382,8 +382,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--trajectories", type=int, default=0, help="trajectories per GPU (default: the workload's size)")
-    ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="trajectories of the cpu_baseline sample")
-    ap.add_argument("--ref-sample", type=int, default=1 << 16, help="trajectories per step of --impl reference")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="trajectories of the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=1 << 19, help="trajectories per step of --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
