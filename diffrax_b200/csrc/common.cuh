@@ -111,13 +111,15 @@ template <class R> __device__ __forceinline__ R linear_rescale(R t0, R t, R t1) 
 }
 
 // ---- fast, division-free building blocks for the PID controller's hot path ----
-// 1/d for positive normal d: MUFU.RCP64H seed (rel. err <= 2^-23) + two Newton steps -> ~1 ulp.
+// The step-size factor does not need to be correctly rounded: a relative error eps in dt changes the state by
+// ~order * eps * (local error) (1e-13 relative here moves a 1e-8-accurate step by ~1e-20), and the accept/reject
+// decision is protected separately (the kernel sends anything within 1e-6 of the boundary to the faithful path).
+// So one Newton step on each SFU seed (~1e-13) is ample; CUDA's pow() / IEEE division would cost ~10x more.
+// 1/d for positive normal d: MUFU.RCP64H seed (rel. err <= 2^-23) + one Newton step -> ~2^-46.
 __device__ __forceinline__ double fast_rcp(double d) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
+  const double e = fma(-d, r, 1.0);
   return fma(r, e, r);
 }
 __device__ __forceinline__ float fast_rcp(float d) { return __frcp_rn(d); }
@@ -127,20 +129,21 @@ template <int M> __device__ __forceinline__ double ipow(double z) {
   else if constexpr (M % 2 == 0) { const double h = ipow<M / 2>(z); return h * h; }
   else return ipow<M - 1>(z) * z;
 }
-// q^(-1/M) for q in [1e-36, 1e36]: fp32 SFU seed (MUFU.LG2 / MUFU.EX2, rel. err ~1e-6) refined by two
-// steps of the division-free Newton iteration z <- z + z (1 - q z^M) / M (error e -> (M+1)/2 e^2),
-// i.e. ~1 ulp in fp64 at a cost of 2 (log2(M)+4) FP64 instructions instead of pow()'s ~100.
+template <int M> __device__ __forceinline__ float ipowf(float z) {
+  if constexpr (M == 1) return z;
+  else if constexpr (M % 2 == 0) { const float h = ipowf<M / 2>(z); return h * h; }
+  else return ipowf<M - 1>(z) * z;
+}
+// q^(-1/M) for q in [1e-30, 1e30] (qf == (float)q): fp32 SFU seed (MUFU.LG2 / MUFU.EX2, ~1e-6) refined by one
+// division-free Newton step z <- z + z (1 - q z^M) / M in fp32 (FMA pipe, -> ~1e-7) and one in fp64
+// (error e -> (M+1)/2 e^2 ~ 1e-13): log2(M) + 4 FP64 instructions.
 template <int M> __device__ __forceinline__ double inv_root(double q, float qf) {
-  // qf == (float)q is in [1e-30, 1e30]: no denormal / overflow handling needed around the SFU ops
   float s;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(__log2f(qf) * (-1.0f / (float)M)));
+  s = fmaf(s * fmaf(-qf, ipowf<M>(s), 1.0f), 1.0f / (float)M, s);
   double z = (double)s;
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double r = fma(-q, ipow<M>(z), 1.0);
-    z = fma(z * r, 1.0 / (double)M, z);
-  }
-  return z;
+  const double r = fma(-q, ipow<M>(z), 1.0);
+  return fma(z * r, 1.0 / (double)M, z);
 }
 
 // max(|a|, |b|) and min / max of POSITIVE doubles on the integer ALU (the IEEE bit patterns of non-negative
