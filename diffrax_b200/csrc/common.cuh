@@ -139,7 +139,9 @@ template <int M> __device__ __forceinline__ float ipowf(float z) {
 // (error e -> (M+1)/2 e^2 ~ 1e-13): log2(M) + 4 FP64 instructions.
 template <int M> __device__ __forceinline__ double inv_root(double q, float qf) {
   float s;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(__log2f(qf) * (-1.0f / (float)M)));
+  float lg;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(qf));  // qf is a normal number: no denormal fix-up needed
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(lg * (-1.0f / (float)M)));
   s = fmaf(s * fmaf(-qf, ipowf<M>(s), 1.0f), 1.0f / (float)M, s);
   double z = (double)s;
   const double r = fma(-q, ipow<M>(z), 1.0);
@@ -150,8 +152,11 @@ template <int M> __device__ __forceinline__ double inv_root(double q, float qf) 
 // doubles order like the values; NaN has the largest pattern and therefore propagates through max).
 // Keeps these off the FP64 pipe, where DSETP + select + NaN fix-up would cost an FP64 issue slot each.
 __device__ __forceinline__ double abs_max_bits(double a, double b) {
-  const long long x = __double_as_longlong(a) & 0x7fffffffffffffffLL, y = __double_as_longlong(b) & 0x7fffffffffffffffLL;
-  return __longlong_as_double(x > y ? x : y);
+  // 32-bit halves on purpose: masking the 64-bit pattern is turned back into DADD |x| (an FP64-pipe op) by ptxas
+  const int ah = __double2hiint(a) & 0x7fffffff, bh = __double2hiint(b) & 0x7fffffff;
+  const unsigned al = (unsigned)__double2loint(a), bl = (unsigned)__double2loint(b);
+  const bool gt = (ah > bh) || (ah == bh && al > bl);
+  return __hiloint2double(gt ? ah : bh, (int)(gt ? al : bl));
 }
 __device__ __forceinline__ double pos_max_bits(double a, double b) {
   const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
