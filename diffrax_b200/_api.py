@@ -444,21 +444,24 @@ class EnsembleSolve:
 
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
                 stepsize_controller=None, max_steps: Optional[int] = 4096, throw: bool = True,
-                device: int = 0) -> Solution:
+                device: int = 0, hairer_initial_step: bool = False) -> Solution:
     """Batched forward solve == ``jax.vmap(lambda y0: diffrax.diffeqsolve(...))(y0)``
     (_integrate.py:888-1543).
 
     ``y0``: ``[N, d]`` (or ``[N]`` for scalar states).  torch CUDA tensors run in place on the
     current stream (device path); numpy arrays / CPU tensors go through
     ``dfx_ensemble_solve_host`` which stages them to GPU ``device`` and back.
-    ``t0`` / ``t1`` may be scalars or ``[N]`` arrays.
+    ``t0`` / ``t1`` may be scalars or ``[N]`` arrays.  ``hairer_initial_step=True`` (extension) selects the
+    starting-step algorithm coded at pid.py:51-81 for ``dt0=None``; the default reproduces what ``diffeqsolve`` does
+    today, a first trial step of 0.01.
     """
     return prepare(terms, solver, t0, t1, dt0, y0, args, saveat=saveat, stepsize_controller=stepsize_controller,
-                   max_steps=max_steps, device=device)(throw=throw)
+                   max_steps=max_steps, device=device, hairer_initial_step=hairer_initial_step)(throw=throw)
 
 
 def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
-            stepsize_controller=None, max_steps: Optional[int] = 4096, device: int = 0) -> EnsembleSolve:
+            stepsize_controller=None, max_steps: Optional[int] = 4096, device: int = 0,
+            hairer_initial_step: bool = False) -> EnsembleSolve:
     """Validate the arguments of a `diffeqsolve` call and allocate its outputs once."""
     if args is not None:
         raise ValueError("args must be None: functor parameters are bound when the functor is created")
@@ -528,6 +531,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         D.dtmax = math.nan if ctrl.dtmax is None else float(ctrl.dtmax)
         D.force_dtmin = int(ctrl.force_dtmin)
         D.error_order = math.nan if ctrl.error_order is None else float(ctrl.error_order)
+        D.hairer_initial_step = int(bool(hairer_initial_step))
         if isinstance(solver, Euler):
             if bm is not None:
                 raise ValueError("An SDE should not be solved with adaptive step sizes with Euler's method, "

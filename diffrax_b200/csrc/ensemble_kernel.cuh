@@ -61,6 +61,8 @@ struct SolveParams {
   int has_dtmin, has_dtmax, force_dtmin;
   R coeff1, coeff2, coeff3;  // PID exponents (pid.py:512-514), computed in double on the host
   int use_c1, use_c2, use_c3;
+  int hairer;    // dt0 == None: use the Hairer starting step of pid.py:51-81 instead of the constant 0.01
+  R inv_error_order;
   int fast_pid;  // pcoeff == dcoeff == 0, icoeff == 1 and error_order == solver order: pure I-controller fast path
   int save_t0, save_t1, save_steps, save_dense;
   const R *save_ts;
@@ -199,6 +201,41 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             // runge_kutta.py:684-695: the first step evaluates stage 0 at (t0, y0); a rejected first
             // step re-evaluates the same point, so computing it once here is value-identical.
             Field::template eval<R>(fp, t0 * direction, y, f_fsal);
+          }
+          if constexpr (TAB && !SDE && RICH) {  // (the launcher routes hairer solves to the RICH instantiation)
+            if (p.hairer && !p.has_dt0 && p.controller == DFX_CTRL_PID) {
+              // _select_initial_step, pid.py:51-81 (Hairer, Norsett, Wanner II.4) - behind a flag: through diffeqsolve
+              // the reference never reaches it.  func == terms.vf: WrapTerm passes t * direction.
+              R f0[D], f1[D], ya[D], sc[D];
+              if constexpr (FSAL) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) f0[c] = f_fsal[c];
+              } else {
+                Field::template eval<R>(fp, t0 * direction, y, f0);
+              }
+              R s0 = R(0), s1 = R(0), s2 = R(0);
+#pragma unroll
+              for (int c = 0; c < D; ++c) {
+                sc[c] = p.atol + r_abs(y[c]) * p.rtol;
+                const R a = y[c] / sc[c], b = f0[c] / sc[c];
+                s0 += a * a; s1 += b * b;
+              }
+              const R d0 = (D == 1) ? r_sqrt(s0) : r_sqrt(s0) / sqrt_d, d1 = (D == 1) ? r_sqrt(s1) : r_sqrt(s1) / sqrt_d;
+              const bool cond = (d0 < R(1e-5)) || (d1 < R(1e-5));
+              const R h0 = cond ? R(1e-6) : R(0.01) * (d0 / (cond ? R(1) : d1));
+#pragma unroll
+              for (int c = 0; c < D; ++c) ya[c] = y[c] + h0 * f0[c];
+              Field::template eval<R>(fp, (t0 + h0) * direction, ya, f1);
+#pragma unroll
+              for (int c = 0; c < D; ++c) { const R a = (f1[c] - f0[c]) / sc[c]; s2 += a * a; }
+              const R d2 = ((D == 1) ? r_sqrt(s2) : r_sqrt(s2) / sqrt_d) / h0;
+              const R max_d = jnp_max(d1, d2);
+              const R h1 = (max_d <= R(1e-15)) ? jnp_max(R(1e-6), h0 * R(1e-3)) : r_pow(R(0.01) / max_d, p.inv_error_order);
+              R dth = jnp_min(R(100) * h0, h1);
+              if (p.has_dtmax) dth = jnp_min(dth, p.dtmax);
+              if (p.has_dtmin) dth = jnp_max(dth, p.dtmin);
+              tnext = jnp_min(t0 + dth, t1);
+            }
           }
           if constexpr (RICH) {
             if (p.save_dense) p.dense_ts[idx * (long long)(p.max_steps + 1)] = t0;  // 324-327; dense_ts stays in normalised time (DenseInterpolation applies `direction`)

@@ -87,6 +87,9 @@ typedef struct dfx_solve_desc {
   double dtmin, dtmax;        /* NaN == None */
   int32_t force_dtmin;
   double error_order;         /* NaN == solver.error_order(terms) (base.py:97-120) */
+  int32_t hairer_initial_step; /* dt0 == None only.  0: first trial step 0.01, which is what diffeqsolve does today
+                                * (pid.py:48-49 is reached with WrapTerm-wrapped terms);
+                                * 1: the Hairer II.4 starting step coded at pid.py:51-81 (ODE solves only) */
 
   /* saveat (_saveat.py:22-26, 72-76) and max_steps (_integrate.py:904) */
   int32_t save_t0, save_t1, save_steps, save_dense;

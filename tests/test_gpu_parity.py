@@ -335,6 +335,26 @@ def test_tensor_core_sass_present():
     assert "UTCHMMA" in out and "LDTM" in out and "STTM" in out
 
 
+def test_hairer_initial_step_flag(dev):
+    """K2: the starting-step algorithm of pid.py:51-81 behind a flag; default is the constant 0.01 the reference uses."""
+    rng = np.random.default_rng(9)
+    y0 = np.stack([rng.uniform(-15, 15, 256), rng.uniform(-20, 20, 256), rng.uniform(5, 45, 256)], 1)
+    kw = dict(solver="dopri5", params=[10.0, 28.0, 8.0 / 3.0], rtol=1e-8, atol=1e-8)
+    term, ctrl = dfx.ODETerm(dfx.fields.Lorenz()), dfx.PIDController(1e-8, 1e-8)
+    for flag in (False, True):
+        o = oracle.solve("lorenz", y0, 0.0, 1.0, None, hairer_initial_step=flag, save_steps=1, save_t1=False, max_steps=512, **kw)
+        s = dfx.diffeqsolve(term, dfx.Dopri5(), 0.0, 1.0, None, torch.tensor(y0, device=dev), stepsize_controller=ctrl,
+                            saveat=dfx.SaveAt(steps=True), max_steps=512, hairer_initial_step=flag)
+        assert np.array_equal(stats_np(s), o["stats"])
+        # the first accepted step end is t0 + the starting step ((f1 - f0) / h0 amplifies rounding in the Hairer estimate)
+        assert relerr(to_np(s.ts)[:, 0], o["ts"][:, 0]) < 1e-8
+        if not flag:
+            assert np.all(to_np(s.ts)[:, 0] == 0.01)
+        else:
+            assert np.mean(to_np(s.ts)[:, 0] != 0.01) > 0.9
+        assert relerr(to_np(s.ys)[:, :50], o["ys"][:, :50]) < 1e-9
+
+
 def test_failure_codes_and_throw(dev):
     y0 = torch.tensor([[1.0, 2.0, 20.0]] * 8, device=dev, dtype=torch.float64)
     term = dfx.ODETerm(dfx.fields.Lorenz())
