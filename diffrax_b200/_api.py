@@ -194,6 +194,33 @@ class PIDController:
     error_order: Optional[float] = None
 
 
+class ClipStepSizeController:
+    """clip.py:120-428: wraps an adaptive controller so that the solver steps exactly to `step_ts` and steps
+    around `jump_ts` (to the float just before, resuming from the float just after; FSAL solvers re-evaluate
+    their carried derivative).  `store_rejected_steps` is not implemented."""
+
+    def __init__(self, controller, step_ts=None, jump_ts=None, store_rejected_steps=None):
+        if not isinstance(controller, PIDController):
+            raise ValueError("Can only apply `ClipStepSizeController` to adaptive step size controllers, "
+                             f"but got {controller}.")  # clip.py:203-207
+        if store_rejected_steps is not None:
+            raise NotImplementedError("store_rejected_steps is not implemented by the ensemble kernels")
+        self.controller = controller
+        self.step_ts = None if step_ts is None else np.sort(np.asarray(step_ts, np.float64).reshape(-1))  # clip.py:209
+        self.jump_ts = None if jump_ts is None else np.sort(np.asarray(jump_ts, np.float64).reshape(-1))
+
+    rtol = property(lambda self: self.controller.rtol)
+    atol = property(lambda self: self.controller.atol)
+
+
+def pid_controller(*args, step_ts=None, jump_ts=None, **kwargs):
+    """`PIDController(..., step_ts=s, jump_ts=j)` backwards-compatible spelling (pid.py:88-97)."""
+    ctrl = PIDController(*args, **kwargs)
+    if step_ts is not None or jump_ts is not None:
+        return ClipStepSizeController(ctrl, step_ts, jump_ts)
+    return ctrl
+
+
 # --------------------------------------------------------------------------------------
 # SaveAt
 # --------------------------------------------------------------------------------------
@@ -522,6 +549,14 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     if dt0 is not None and t0arr is None and (t1s - t0s) * float(dt0) < 0:
         raise ValueError("Must have (t1 - t0) * dt0 >= 0")  # _integrate.py:1036-1045
 
+    if isinstance(ctrl, ClipStepSizeController):
+        for name, arr in (("step_ts", ctrl.step_ts), ("jump_ts", ctrl.jump_ts)):
+            if arr is not None:
+                a = xp.asarray(arr, rdt)
+                keep_alive.append(a)
+                setattr(D, name, xp.ptr(a))
+                setattr(D, "n_" + name, int(a.shape[0]))
+        ctrl = ctrl.controller
     if isinstance(ctrl, PIDController):
         D.controller = _lib.CTRL_PID
         D.rtol, D.atol = float(ctrl.rtol), float(ctrl.atol)

@@ -296,6 +296,11 @@ static int check_desc(const dfx_solve_desc *d) {
     set_error("Constant step size solvers cannot select step size automatically; please pass a value for `dt0`.");
     return DFX_ERR_BAD_ARGUMENT;
   }
+  if ((d->step_ts || d->jump_ts) && d->controller != DFX_CTRL_PID) {
+    // clip.py:203-207
+    set_error("Can only apply `ClipStepSizeController` to adaptive step size controllers.");
+    return DFX_ERR_BAD_ARGUMENT;
+  }
   if (d->controller == DFX_CTRL_PID && d->solver_id == DFX_EULER) {
     // pid.py:461-469 (Euler provides no error estimate)
     set_error("Cannot use adaptive step sizes with a solver that does not provide error estimates.");
@@ -372,6 +377,8 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
   d.t0_per_traj = dev_in(off(h->t0_per_traj, es), N * es);
   d.t1_per_traj = dev_in(off(h->t1_per_traj, es), N * es);
   d.save_ts = dev_in(h->save_ts, (size_t)h->n_save_ts * es);
+  d.step_ts = dev_in(h->step_ts, (size_t)h->n_step_ts * es);
+  d.jump_ts = dev_in(h->jump_ts, (size_t)h->n_jump_ts * es);
   d.bm_keys = (const uint32_t *)dev_in(off(h->bm_keys, 8), N * 8);
   d.field_weights = dev_in(h->field_weights, (size_t)h->n_field_weights * es);
   d.ts_out = dev_out(off(h->ts_out, T * es), N * T * es);

@@ -61,6 +61,8 @@ struct SolveParams {
   int has_dtmin, has_dtmax, force_dtmin;
   R coeff1, coeff2, coeff3;  // PID exponents (pid.py:512-514), computed in double on the host
   int use_c1, use_c2, use_c3;
+  const R *step_ts, *jump_ts;  // ClipStepSizeController (clip.py): sorted, user time; RICH instantiation only
+  int n_step_ts, n_jump_ts;
   int hairer;    // dt0 == None: use the Hairer starting step of pid.py:51-81 instead of the constant 0.01
   R inv_error_order;
   int fast_pid;  // pcoeff == dcoeff == 0, icoeff == 1 and error_order == solver order: pure I-controller fast path
@@ -121,6 +123,37 @@ __device__ __forceinline__ long long claim_work(bool need, unsigned long long *c
   return need ? (long long)(base + __popc(m & ((1u << lane) - 1u))) : -1;
 }
 
+// ---- ClipStepSizeController helpers (clip.py:53-97).  After wrap(direction) the controller sees sort(ts * direction):
+// element i is direction > 0 ? ts[i] : -ts[n-1-i].
+template <class R> __device__ __forceinline__ R clip_at(const R *ts, int n, int i, R direction) {
+  return direction > R(0) ? ts[i] : -ts[n - 1 - i];
+}
+template <class R> __device__ __forceinline__ R clip_get_t(const R *ts, int n, int i, R direction) {  // _get_t
+  return (n == 0 || i >= n) ? Num<R>::inf() : clip_at(ts, n, i, direction);
+}
+template <class R> __device__ __forceinline__ R next_after_up(R x) {  // eqxi.nextafter(x) == nextafter(x, +inf), finite x
+  return -prev_n<R>(-x, 1);
+}
+template <class R> __device__ __forceinline__ bool clip_contains(const R *ts, int n, R x, R direction) {  // jnp.any(x == ts)
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (clip_at(ts, n, mid, direction) < x) lo = mid + 1; else hi = mid; }
+  return lo < n && clip_at(ts, n, lo, direction) == x;
+}
+template <class R> __device__ __forceinline__ R clip_bump(R next_t0, const R *ts, int n, R direction, bool &made_jump) {  // _bump_next_t0
+  const R nn = next_after_up(next_t0);
+  const bool mj1 = clip_contains(ts, n, nn, direction), mj2 = clip_contains(ts, n, next_t0, direction);
+  if (mj1) next_t0 = next_after_up(nn);
+  if (mj2) next_t0 = nn;
+  made_jump = mj1 || mj2;
+  return next_t0;
+}
+template <class R> __device__ __forceinline__ int clip_find_idx(R t, const R *ts, int n, int hint, R direction) {  // _find_idx_with_hint
+  int i = hint;
+  while (i < n && clip_at(ts, n, i, direction) <= t) ++i;
+  while (i > 0 && clip_at(ts, n, i - 1, direction) > t) --i;
+  return i;
+}
+
 // Template parameters
 //   R      working dtype (state == time dtype)
 //   Field  vector-field functor (fields.cuh)
@@ -149,6 +182,8 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   int cs_steps_completed = 1, cs_num_steps = 0;
   int num_steps = 0, num_accepted = 0, result = DFX_RESULT_SUCCESSFUL;
   int save_index = 0, saveat_ts_index = 0, dense_index = 0;
+  [[maybe_unused]] int step_index = 0, jump_index = 0;  // ClipStepSizeController state (RICH only)
+  [[maybe_unused]] bool made_jump = false;
   BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME> bm;
 #pragma unroll
   for (int c = 0; c < D; ++c) { y[c] = R(0); f_fsal[c] = R(0); }
@@ -191,7 +226,19 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             cs_steps_completed = 1;
           }
           tprev = t0;
-          tnext = jnp_min(t0 + dt0, t1);  // _integrate.py:1265
+          tnext = t0 + dt0;
+          if constexpr (RICH) {  // ClipStepSizeController.init, clip.py:246-302
+            made_jump = false;
+            if (p.step_ts != nullptr) {
+              step_index = clip_find_idx(t0, p.step_ts, p.n_step_ts, 0, direction);  // searchsorted(side="right")
+              tnext = jnp_min(clip_get_t(p.step_ts, p.n_step_ts, step_index, direction), tnext);
+            }
+            if (p.jump_ts != nullptr) {
+              jump_index = clip_find_idx(t0, p.jump_ts, p.n_jump_ts, 0, direction);
+              tnext = jnp_min(prev_n<R>(clip_get_t(p.jump_ts, p.n_jump_ts, jump_index, direction), 1), tnext);
+            }
+          }
+          tnext = jnp_min(tnext, t1);  // _integrate.py:1265
           t1_clip_floor = prev_n<R>(t1, 100);  // _integrate.py:320-322
           pid_inv = R(1); pid_prev_inv = R(1); at_dtmin = false;
           num_steps = 0; num_accepted = 0; result = DFX_RESULT_SUCCESSFUL;
@@ -270,6 +317,11 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           const R control = direction * dt;  // WrapTerm.contr (_term.py:742-745)
           R yi[D], fi[D];
           if constexpr (FSAL) {
+            if constexpr (RICH) {
+              // eval_first_stage = first_step | made_jump (runge_kutta.py:687): after stepping around a jump the carried
+              // derivative belongs to the other side of the discontinuity and is re-evaluated at (tprev, y)
+              if (made_jump) Field::template eval<R>(fp, st0 * direction, y, f_fsal);
+            }
 #pragma unroll
             for (int c = 0; c < D; ++c) k[0][c] = control * f_fsal[c];  // prod(f0), 695 & 771
           } else {
@@ -453,10 +505,27 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           next_t1 = t1n;
         }
 
+        if constexpr (RICH) {  // ClipStepSizeController.adapt_step_size, clip.py:350-377
+          bool ctrl_made_jump = false;
+          if (p.step_ts != nullptr) {
+            bool dummy;
+            const R nt0 = clip_bump(next_t0, p.step_ts, p.n_step_ts, direction, dummy);
+            step_index = clip_find_idx(nt0, p.step_ts, p.n_step_ts, step_index, direction);
+            next_t1 = jnp_min(clip_get_t(p.step_ts, p.n_step_ts, step_index, direction), next_t1);
+          }
+          if (p.jump_ts != nullptr) {
+            next_t0 = clip_bump(next_t0, p.jump_ts, p.n_jump_ts, direction, ctrl_made_jump);
+            next_t1 = jnp_max(next_after_up(next_t0), next_t1);
+            jump_index = clip_find_idx(next_t0, p.jump_ts, p.n_jump_ts, jump_index, direction);
+            next_t1 = jnp_min(prev_n<R>(clip_get_t(p.jump_ts, p.n_jump_ts, jump_index, direction), 1), next_t1);
+          }
+          if (keep) made_jump = ctrl_made_jump;  // _integrate.py:425
+        }
+
         // ---- book-keeping, _integrate.py:412-437 ----
-        // 412: tprev = min(tprev, t1) is the identity here: next_t0 is st0 or st1, and tnext never exceeds t1
-        // (it starts as min(t0 + dt0, t1) and every update below clips it to t1).
-        const R tprev_new = next_t0;
+        // 412: tprev = min(tprev, t1) is the identity without jump_ts: next_t0 is st0 or st1, and tnext never exceeds t1
+        // (it starts as min(t0 + dt0, t1) and every update below clips it to t1); a bumped next_t0 is clipped explicitly.
+        const R tprev_new = (RICH && p.jump_ts != nullptr) ? jnp_min(next_t0, t1) : next_t0;
         R tnext_new = next_t1;
         if (next_t1 > t1_clip_floor) tnext_new = keep ? t1 : tprev_new + R(0.5) * (t1 - tprev_new);  // 278-284
         num_steps += 1;

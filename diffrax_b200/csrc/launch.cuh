@@ -54,6 +54,8 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   const double c3 = d->dcoeff / error_order;
   p.coeff1 = (R)c1; p.coeff2 = (R)c2; p.coeff3 = (R)c3;
   p.use_c1 = c1 != 0; p.use_c2 = c2 != 0; p.use_c3 = c3 != 0;
+  p.step_ts = (const R *)d->step_ts; p.n_step_ts = d->step_ts ? d->n_step_ts : 0;
+  p.jump_ts = (const R *)d->jump_ts; p.n_jump_ts = d->jump_ts ? d->n_jump_ts : 0;
   p.hairer = d->hairer_initial_step && !sde;
   p.inv_error_order = (R)(1.0 / error_order);
   p.fast_pid = !sde && d->pcoeff == 0 && d->dcoeff == 0 && d->icoeff == 1 && error_order == (double)Solver::kOrder;
@@ -143,7 +145,8 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
-  const bool rich = d->save_t0 || d->save_ts || d->save_steps || d->save_dense || (d->hairer_initial_step && std::isnan(d->dt0));
+  const bool rich = d->save_t0 || d->save_ts || d->save_steps || d->save_dense || (d->hairer_initial_step && std::isnan(d->dt0)) ||
+                    d->step_ts || d->jump_ts;
 
   // scratch: work-queue counter (+ save_count when the caller did not ask for it)
   unsigned long long *counter = nullptr;

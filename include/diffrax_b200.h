@@ -91,6 +91,15 @@ typedef struct dfx_solve_desc {
                                 * (pid.py:48-49 is reached with WrapTerm-wrapped terms);
                                 * 1: the Hairer II.4 starting step coded at pid.py:51-81 (ODE solves only) */
 
+  /* ClipStepSizeController(controller, step_ts, jump_ts) (_step_size_controller/clip.py:120-428; also
+   * PIDController(step_ts=, jump_ts=), pid.py:88-97): times that must be stepped to exactly / stepped around.
+   * Sorted ascending, user time, time dtype; shared by all trajectories; NULL when unused.
+   * store_rejected_steps is not implemented. */
+  const void *step_ts;
+  int32_t n_step_ts;
+  const void *jump_ts;
+  int32_t n_jump_ts;
+
   /* saveat (_saveat.py:22-26, 72-76) and max_steps (_integrate.py:904) */
   int32_t save_t0, save_t1, save_steps, save_dense;
   const void *save_ts;        /* [T] in the time dtype, or NULL */

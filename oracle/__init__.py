@@ -49,6 +49,7 @@ class Desc(C.Structure):
         ("force_dtmin", C.c_int32),
         ("error_order", C.c_double),
         ("hairer_initial_step", C.c_int32),
+        ("step_ts", C.c_void_p), ("n_step_ts", C.c_int32), ("jump_ts", C.c_void_p), ("n_jump_ts", C.c_int32),
         ("save_t0", C.c_int32), ("save_t1", C.c_int32), ("save_steps", C.c_int32), ("save_dense", C.c_int32),
         ("save_ts", C.c_void_p), ("n_save_ts", C.c_int32), ("max_steps", C.c_int32),
         ("out_size", C.c_int32),
@@ -153,7 +154,7 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
           hairer_initial_step=False, save_t0=False, save_t1=True, save_ts=None, save_steps=0,
           save_dense=False, max_steps=4096, levy_area=None, keys=None, bm_t0=0.0, bm_t1=1.0,
           bm_tol=1e-3, partitionable=True, callback=None, trace_traj=None, num_threads=0,
-          t0_per_traj=None, t1_per_traj=None):
+          t0_per_traj=None, t1_per_traj=None, step_ts=None, jump_ts=None):
     """Run the oracle on a batch.  Mirrors one vmapped diffeqsolve call of the reference."""
     L = lib()
     dt = np.dtype(dtype)
@@ -191,6 +192,10 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
     D.force_dtmin = int(force_dtmin)
     D.error_order = math.nan if error_order is None else float(error_order)
     D.hairer_initial_step = int(hairer_initial_step)
+    sta = None if step_ts is None else np.sort(np.ascontiguousarray(step_ts, dt))
+    jta = None if jump_ts is None else np.sort(np.ascontiguousarray(jump_ts, dt))
+    D.step_ts, D.n_step_ts = _ptr(sta), (0 if sta is None else sta.size)
+    D.jump_ts, D.n_jump_ts = _ptr(jta), (0 if jta is None else jta.size)
     D.save_t0, D.save_t1, D.save_steps, D.save_dense = int(save_t0), int(save_t1), int(save_steps), int(save_dense)
     tsa = None if save_ts is None else np.ascontiguousarray(save_ts, dt)
     D.save_ts, D.n_save_ts, D.max_steps = _ptr(tsa), (0 if tsa is None else tsa.size), int(max_steps)

@@ -64,6 +64,9 @@ typedef struct orc_desc {
   int32_t force_dtmin;
   double error_order;        /* NaN => solver.error_order(terms) */
   int32_t hairer_initial_step; /* 0 => dt0=None means 0.01; 1 => pid.py:51-81 */
+  /* ClipStepSizeController(controller, step_ts, jump_ts) (clip.py:120-428); sorted ascending, user time */
+  const void *step_ts; int32_t n_step_ts;
+  const void *jump_ts; int32_t n_jump_ts;
   /* SaveAt (_saveat.py:22-26,72-76) */
   int32_t save_t0, save_t1, save_steps, save_dense;
   const void *save_ts;       /* [T] REAL or NULL */

@@ -335,6 +335,47 @@ def test_tensor_core_sass_present():
     assert "UTCHMMA" in out and "LDTM" in out and "STTM" in out
 
 
+@pytest.mark.parametrize("solver", ["tsit5", "dopri5", "heun", "bosh3"])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_clip_step_size_controller(dev, solver, reverse):
+    """ClipStepSizeController(step_ts, jump_ts) - steps land exactly on step_ts, step around
+    jump_ts (prevbefore / nextafter), FSAL derivative re-evaluated after a jump (clip.py:120-428)."""
+    rng = np.random.default_rng(17)
+    n = 128
+    y0 = rng.uniform(-2, 2, (n, 2))
+    t0, t1 = (3.0, 0.0) if reverse else (0.0, 3.0)
+    step_ts, jump_ts = [0.5, 1.0, 1.7, 2.5], [0.8, 2.2]
+    kw = dict(solver=solver, params=[1.0, 0.7, 2.0], rtol=1e-7 if solver in ("tsit5", "dopri5") else 1e-4, atol=1e-9)
+    o = oracle.solve("forced_osc", y0, t0, t1, 0.3 * (-1 if reverse else 1), step_ts=step_ts, jump_ts=jump_ts, save_steps=1,
+                     save_t1=False, max_steps=2048, **kw)
+    ctrl = dfx.ClipStepSizeController(dfx.PIDController(rtol=kw["rtol"], atol=kw["atol"]), step_ts=step_ts, jump_ts=jump_ts)
+    s = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.ForcedOscillator(1.0, 0.7, 2.0)), SOLVERS[solver](), t0, t1,
+                        0.3 * (-1 if reverse else 1), torch.tensor(y0, device=dev), saveat=dfx.SaveAt(steps=True),
+                        stepsize_controller=ctrl, max_steps=2048)
+    st = stats_np(s)
+    same = np.all(st == o["stats"], axis=1)
+    assert same.mean() >= 0.98 and np.abs(st[:, 1] - o["stats"][:, 1]).max() <= 1
+    ts, ots = to_np(s.ts), o["ts"]
+    for i in range(0, n, 16):
+        row = ts[i][np.isfinite(ts[i])]
+        for t in step_ts:                                  # stepped to exactly
+            assert t in row
+        for t in jump_ts:                                  # stepped around: the float before and the float after
+            lo, hi = np.nextafter(t, -np.inf), np.nextafter(t, np.inf)
+            assert ((lo in row) or (hi in row)) and (t not in row)
+    assert relerr(ts[same], ots[same]) < 1e-3            # step times carry the error-estimate rounding noise (DESIGN.md §4)
+    assert relerr(to_np(s.ys)[same], o["ys"][same]) < 1e-3
+    # fixed-time comparison through SaveAt(ts): tight
+    q = np.linspace(t0, t1, 9)
+    o2 = oracle.solve("forced_osc", y0, t0, t1, 0.3 * (-1 if reverse else 1), step_ts=step_ts, jump_ts=jump_ts, save_ts=q,
+                      save_t1=False, max_steps=2048, **kw)
+    s2 = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.ForcedOscillator(1.0, 0.7, 2.0)), SOLVERS[solver](), t0, t1,
+                         0.3 * (-1 if reverse else 1), torch.tensor(y0, device=dev), saveat=dfx.SaveAt(ts=q),
+                         stepsize_controller=ctrl, max_steps=2048)
+    same2 = np.all(stats_np(s2) == o2["stats"], axis=1)
+    assert relerr(to_np(s2.ys)[same2], o2["ys"][same2]) < RTOL64
+
+
 def test_hairer_initial_step_flag(dev):
     """K2: the starting-step algorithm of pid.py:51-81 behind a flag; default is the constant 0.01 the reference uses."""
     rng = np.random.default_rng(9)

@@ -188,3 +188,33 @@ def test_dense_interpolation_reproduces_knots_and_solution():
         assert np.allclose(ev[:, :, 0], np.array([[1.0], [0.5]]) * np.exp(-tq), atol=1e-5 if solver in ("heun",) else 1e-6)
         out = oracle.dense_evaluate(solver, r["dense"], np.array([[1.5], [-0.1]]))
         assert np.all(np.isnan(out))                      # _nan_if_out_of_bounds
+
+
+def test_clip_step_size_controller_semantics():
+    """test_adaptive_stepsize_controller.py:19-70 recipe: with step_ts the solver lands exactly on those times, with
+    jump_ts it steps to prevbefore(t) and resumes from nextafter(t); a discontinuous field is then integrated without
+    rejections piling up at the jump."""
+    y0 = np.array([[1.0]])
+    r = oracle.solve("decay", y0, 0.0, 2.0, None, solver="tsit5", params=[1.0], rtol=1e-6, atol=1e-9,
+                     step_ts=[0.5, 1.0, 1.5], save_steps=1, save_t1=False, max_steps=256)
+    ts = r["ts"][0][np.isfinite(r["ts"][0])]
+    assert all(t in ts for t in (0.5, 1.0, 1.5, 2.0))
+    assert abs(r["ys"][0][len(ts) - 1, 0] - math.exp(-2)) < 1e-6
+    r = oracle.solve("decay", y0, 0.0, 2.0, None, solver="dopri5", params=[1.0], rtol=1e-6, atol=1e-9, jump_ts=[0.7],
+                     save_steps=1, save_t1=False, max_steps=256, trace_traj=0)
+    tr = r["trace"]
+    i = int(np.argmin(np.abs(tr[:, 1] - 0.7)))
+    assert tr[i, 1] == np.nextafter(0.7, 0.0) and tr[i + 1, 0] == np.nextafter(0.7, 1.0)
+    # reverse time: step_ts are negated and re-sorted by wrap(direction) (clip.py:232-236)
+    r = oracle.solve("decay", y0, 2.0, 0.0, None, solver="tsit5", params=[1.0], rtol=1e-6, atol=1e-9,
+                     step_ts=[0.5, 1.0, 1.5], save_steps=1, save_t1=False, max_steps=256)
+    ts = r["ts"][0][np.isfinite(r["ts"][0])]
+    assert all(t in ts for t in (0.5, 1.0, 1.5, 0.0)) and np.all(np.diff(ts) < 0)
+    # a forcing jump: y' = -y + H(t - 1); with jump_ts the solve matches the analytic solution and rejects less
+    def f(t, y):
+        return [-y[0] + (1.0 if t > 1.0 else 0.0)]
+    exact = math.exp(-2) + (1 - math.exp(-1))
+    a = oracle.solve("callback", y0, 0.0, 2.0, None, solver="dopri5", rtol=1e-8, atol=1e-10, jump_ts=[1.0], callback=f)
+    b = oracle.solve("callback", y0, 0.0, 2.0, None, solver="dopri5", rtol=1e-8, atol=1e-10, callback=f)
+    assert abs(a["ys"][0, 0, 0] - exact) < 1e-8
+    assert a["stats"][0, 2] < b["stats"][0, 2]
