@@ -168,6 +168,16 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   constexpr bool SDE = LEVY != DFX_LEVY_NONE;
   constexpr bool TAB = IsTableau<Solver>::value;
   constexpr bool FSAL = Solver::kFsal && !SDE;
+#ifndef DFX_OPT_CHAIN_Y0
+#define DFX_OPT_CHAIN_Y0 1
+#endif
+#ifndef DFX_OPT_LAST_STAGE_F
+#define DFX_OPT_LAST_STAGE_F 1
+#endif
+  // Instruction-count reductions of the ODE step (see the stage loop).  The chained form is limited to pairs with <= 7
+  // stages: the 14-stage Dopri8 sums are kept in the reference's "sum, then add y0" order (rtol 1e-12 territory).
+  [[maybe_unused]] constexpr bool kChainY0 = DFX_OPT_CHAIN_Y0 && TAB && !SDE && Solver::S <= 7;
+  [[maybe_unused]] constexpr bool kLastStageF = DFX_OPT_LAST_STAGE_F && TAB && FSAL && Solver::kSsal;
   constexpr int INTERP = Solver::kInterp;
   constexpr bool DENSE_K = INTERP != kInterpLinear;
   constexpr bool FAST_PID = TAB && !SDE && sizeof(R) == 8;  // fp64 ODE solves: division-/pow-free I-controller path
@@ -339,16 +349,30 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           for (int i = 1; i < S; ++i) {  // rk_stage, 847-1069
 #pragma unroll
             for (int c = 0; c < D; ++c) {
-              R incr = R(0);
+              if constexpr (kChainY0) {
+                // y_i = y0 + sum_j a_ij k_j as ONE chain of FMAs seeded with y0: saves the separate add per stage and
+                // component (18 of ~200 FP64 instructions of a Lorenz/Dopri5 step) at the price of rounding each partial
+                // sum at ulp(y0) instead of once
+                R acc = y[c];
 #pragma unroll
-              for (int j = 0; j < i; ++j)
-                if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];  // vector_tree_dot (base.py:37-41); structural zeros skipped
-              yi[c] = y[c] + incr;  // 871
+                for (int j = 0; j < i; ++j)
+                  if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) acc += Solver::template a<R>(i, j) * k[j][c];
+                yi[c] = acc;
+              } else {
+                R incr = R(0);
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                  if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];  // vector_tree_dot (base.py:37-41); structural zeros skipped
+                yi[c] = y[c] + incr;  // 871
+              }
             }
             const R ti = (Solver::hC(i) == 1.0) ? st1 : st0 + Solver::template c<R>(i) * dt;  // 1023
             Field::template eval<R>(fp, ti * direction, yi, fi);
 #pragma unroll
             for (int c = 0; c < D; ++c) {
+              if constexpr (kLastStageF && !RICH) {
+                if (i == S - 1) continue;  // the last stage value is only read by the error estimate, through f_last below
+              }
               R kk = control * fi[c];
               if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, ti) * W;
               k[i][c] = kk;
@@ -372,9 +396,18 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
 #pragma unroll
           for (int c = 0; c < D; ++c) {  // 1186-1193
             R e = R(0);
+            if constexpr (kLastStageF) {
+              // FSAL+SSAL pairs: k_{s-1} = dt f(y1) enters only here, so take it as (b_err[s-1] dt) f(y1) and keep f(y1)
+              // (the next step's FSAL derivative) as the one live copy instead of k_{s-1} AND f(y1)
 #pragma unroll
-            for (int j = 0; j < S; ++j)
-              if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
+              for (int j = 0; j < S - 1; ++j)
+                if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
+              if (Solver::hBerr(S - 1) != 0.0) e += (Solver::template b_err<R>(S - 1) * control) * f_last[c];
+            } else {
+#pragma unroll
+              for (int j = 0; j < S; ++j)
+                if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
+            }
             yerr[c] = e;
           }
         } else if constexpr (Solver::kId == DFX_EULER) {
