@@ -285,7 +285,7 @@ static int check_desc(const dfx_solve_desc *d) {
               sizeof(dfx_solve_desc), d->abi_version, DFX_ABI_VERSION);
     return DFX_ERR_BAD_ARGUMENT;
   }
-  if (d->n_traj < 0 || d->dim < 1 || d->dim > kMaxDim) { set_error("bad n_traj / dim"); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->n_traj < 0 || d->n_traj > 0x7fffffffLL || d->dim < 1 || d->dim > kMaxDim) { set_error("bad n_traj (0 .. 2^31-1 per call) / dim"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->dtype != DFX_F64 && d->dtype != DFX_F32) { set_error("bad dtype %d", d->dtype); return DFX_ERR_BAD_ARGUMENT; }
   if (d->n_traj > 0 && !d->y0) { set_error("y0 is null"); return DFX_ERR_BAD_ARGUMENT; }
   if (!d->stats || !d->result) { set_error("stats / result buffers are required"); return DFX_ERR_BAD_ARGUMENT; }

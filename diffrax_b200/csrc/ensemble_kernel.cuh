@@ -73,6 +73,7 @@ struct SolveParams {
   int *stats, *result, *save_count;
   R *dense_ts, *dense_y0, *dense_y1, *dense_k;
   int *dense_count;
+  int refill_batch;  // finished lanes wait until this many can be finalised + refilled in one pass (>= 1)
   int dense_coop;    // SaveAt(dense): stage records through shared memory and store them warp-cooperatively (launcher provides the smem)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
   R *y_final, *t_final;
@@ -184,12 +185,12 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
 
   // ---- per-lane trajectory state (registers) ----
   bool active = false, exhausted = false;
-  long long idx = -1;
+  int idx_i = -1;  // trajectory index (n_traj < 2^31 is checked on the host); widened at each use
   R y[D], f_fsal[D];
   R tprev = R(0), tnext = R(0), t0 = R(0), t1 = R(0), direction = R(1), t1_clip_floor = R(0);
   R pid_inv = R(1), pid_prev_inv = R(1);
   bool at_dtmin = false;
-  int cs_steps_completed = 1, cs_num_steps = 0;
+  int cs_num_steps = 0;  // ConstantStepSize: steps_completed (constant.py:84) is num_steps + 1, every step being accepted
   int num_steps = 0, num_accepted = 0, result = DFX_RESULT_SUCCESSFUL;
   int save_index = 0, saveat_ts_index = 0, dense_index = 0;
   [[maybe_unused]] int step_index = 0, jump_index = 0;  // ClipStepSizeController state (RICH only)
@@ -208,15 +209,65 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   [[maybe_unused]] R *dense_smem = reinterpret_cast<R *>(dense_smem_raw);
 
   for (;;) {
-    // ---------------- refill: finished lanes claim the next trajectory ----------------
-    // `exhausted` is warp-uniform (it is set from a warp vote), so the collective below is convergent.
-    if (!exhausted) {
+    // Finalising a trajectory and claiming + initialising the next one is ~300 instructions that the whole warp
+    // issues for however few lanes need them; lanes finish at unrelated iterations, so doing it per lane costs about
+    // 32 * 300 / (steps per trajectory * instructions per step) of the run (10 % on C2).  Finished lanes therefore
+    // wait (idle) until `refill_batch` of them can share one pass, or nothing else is running.
+    // a lane is `done` when its loop condition (_integrate.py:355-363, 685-687) has turned false
+    const bool done = active && !((tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL));
+    const unsigned running = __ballot_sync(kFullMask, active && !done);
+    const unsigned waiting = __ballot_sync(kFullMask, done);
+    if (running == 0u || __popc(waiting) >= p.refill_batch) {
+      // ---------------- finalize finished lanes ----------------
+      if (done) {
+        const long long idx = idx_i;
+        if constexpr (RICH) {
+          if (t0 == t1 && p.save_ts != nullptr) {  // _integrate.py:823-845
+            for (int i = 0; i < p.n_save_ts; ++i) {
+              const long long o = idx * (long long)p.out_size + save_index;
+              p.ts_out[o] = t0 * direction;
+  #pragma unroll
+              for (int c = 0; c < D; ++c) p.ys_out[o * D + c] = y[c];
+              save_index += 1;
+            }
+          }
+        }
+        if (p.save_t1) {  // _integrate.py:847-877
+          bool via_steps = false;
+          if (p.save_steps == 1) via_steps = true;
+          else if (p.save_steps > 1) via_steps = (num_accepted % p.save_steps) == 0;
+          if (!via_steps) {
+            const long long o = idx * (long long)p.out_size + save_index;
+            p.ts_out[o] = tprev * direction;
+  #pragma unroll
+            for (int c = 0; c < D; ++c) p.ys_out[o * D + c] = y[c];
+            save_index += 1;
+          }
+        }
+        if ((tprev < t1) && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_MAX_STEPS_REACHED;  // 883
+        p.stats[idx * 3 + 0] = num_steps;
+        p.stats[idx * 3 + 1] = num_accepted;
+        p.stats[idx * 3 + 2] = num_steps - num_accepted;
+        p.result[idx] = result;
+        if (p.save_count) p.save_count[idx] = save_index;
+        if (p.dense_count) p.dense_count[idx] = dense_index;
+        if (p.y_final) {
+  #pragma unroll
+          for (int c = 0; c < D; ++c) p.y_final[idx * D + c] = y[c];
+        }
+        if (p.t_final) p.t_final[idx] = tprev * direction;
+        active = false;
+      }
+      // ---------------- refill: finished lanes claim the next trajectory ----------------
+      // `exhausted` is warp-uniform (it is set from a warp vote), so the collective below is convergent.
+      if (!exhausted) {
       const long long got = claim_work(!active, p.work_counter);
       // the queue only grows: once any lane is handed an index past the end, it is drained for good
       exhausted = __any_sync(kFullMask, !active && got >= p.n_traj);
       if (!active) {
         if (got >= 0 && got < p.n_traj) {
-          idx = got;
+          idx_i = (int)got;
+          const long long idx = got;
           // _integrate.py:1076-1079, 1157-1165: time dtype and direction normalisation
           R a = p.t0_arr ? p.t0_arr[idx] : p.t0;
           R b = p.t1_arr ? p.t1_arr[idx] : p.t1;
@@ -233,7 +284,6 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           } else {
             const R dt0_up = Num<R>::from_bits(Num<R>::bits(dt0) + (dt0 > R(0) ? 1 : (dt0 < R(0) ? -1 : 1)));  // nextafter(dt0, +inf)
             cs_num_steps = (int)ceil((double)((t1 - t0) / dt0_up));
-            cs_steps_completed = 1;
           }
           tprev = t0;
           tnext = t0 + dt0;
@@ -306,15 +356,16 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           active = true;
         }
       }
+      }
     }
     if (__all_sync(kFullMask, !active)) break;
 
     // ---------------- one attempted step (all active lanes, same instruction stream) ----------------
-    bool finished = false;
     [[maybe_unused]] long long dense_row = -1;  // >= 0: this lane staged a dense record in shared memory this iteration
     if (active) {
       const bool run = (tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL);  // 355-363, 685-687
       if (run) {
+        [[maybe_unused]] const long long idx = idx_i;
         const R st0 = tprev, st1 = tnext;
         const R dt = st1 - st0;
         R k[S][D];
@@ -518,12 +569,14 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             dtn = dt * factor;                              // 531
             if (inv == R(0) || r_isinf(inv)) inv = R(1);    // 537-538
           }
-          if (p.has_dtmax) dtn = jnp_min(dtn, p.dtmax);   // 545-546
-          if (p.has_dtmin) {                              // 547-555
-            if (!p.force_dtmin && dtn < p.dtmin && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_DT_MIN_REACHED;
-            if (at_dtmin && factor == R(1)) dtn = p.dtmin;
-            at_dtmin = dtn <= p.dtmin;
-            dtn = jnp_max(dtn, p.dtmin);
+          if (p.has_dtmax | p.has_dtmin) {  // one uniform branch around both limits: neither is set by default
+            if (p.has_dtmax) dtn = jnp_min(dtn, p.dtmax);   // 545-546
+            if (p.has_dtmin) {                              // 547-555
+              if (!p.force_dtmin && dtn < p.dtmin && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_DT_MIN_REACHED;
+              if (at_dtmin && factor == R(1)) dtn = p.dtmin;
+              at_dtmin = dtn <= p.dtmin;
+              dtn = jnp_max(dtn, p.dtmin);
+            }
           }
           next_t0 = keep ? st1 : st0;                     // 557-558
           next_t1 = next_t0 + dtn;
@@ -531,7 +584,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         } else {
           // constant.py:57-104
           keep = true;
-          cs_steps_completed += 1;
+          const int cs_steps_completed = num_steps + 2;
           R t1n = t0 + (t1 - t0) * ((R)cs_steps_completed / (R)cs_num_steps);
           if (cs_steps_completed == cs_num_steps) t1n = t1;
           next_t0 = st1;
@@ -629,7 +682,6 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         tprev = tprev_new;
         tnext = tnext_new;
       }
-      finished = !((tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL));
     }
 
     // ---------------- SaveAt(dense): warp-cooperative flush of the staged records ----------------
@@ -664,45 +716,6 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
       }
     }
 
-    // ---------------- finalize finished lanes ----------------
-    if (active && finished) {
-      if constexpr (RICH) {
-        if (t0 == t1 && p.save_ts != nullptr) {  // _integrate.py:823-845
-          for (int i = 0; i < p.n_save_ts; ++i) {
-            const long long o = idx * (long long)p.out_size + save_index;
-            p.ts_out[o] = t0 * direction;
-#pragma unroll
-            for (int c = 0; c < D; ++c) p.ys_out[o * D + c] = y[c];
-            save_index += 1;
-          }
-        }
-      }
-      if (p.save_t1) {  // _integrate.py:847-877
-        bool via_steps = false;
-        if (p.save_steps == 1) via_steps = true;
-        else if (p.save_steps > 1) via_steps = (num_accepted % p.save_steps) == 0;
-        if (!via_steps) {
-          const long long o = idx * (long long)p.out_size + save_index;
-          p.ts_out[o] = tprev * direction;
-#pragma unroll
-          for (int c = 0; c < D; ++c) p.ys_out[o * D + c] = y[c];
-          save_index += 1;
-        }
-      }
-      if ((tprev < t1) && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_MAX_STEPS_REACHED;  // 883
-      p.stats[idx * 3 + 0] = num_steps;
-      p.stats[idx * 3 + 1] = num_accepted;
-      p.stats[idx * 3 + 2] = num_steps - num_accepted;
-      p.result[idx] = result;
-      if (p.save_count) p.save_count[idx] = save_index;
-      if (p.dense_count) p.dense_count[idx] = dense_index;
-      if (p.y_final) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) p.y_final[idx * D + c] = y[c];
-      }
-      if (p.t_final) p.t_final[idx] = tprev * direction;
-      active = false;
-    }
   }
 }
 

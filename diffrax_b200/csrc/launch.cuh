@@ -1,5 +1,6 @@
 // launch.cuh - host-side launcher template for ensemble_kernel and the launcher registry.
 #pragma once
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -94,6 +95,12 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
   // SaveAt(dense=True): per-lane staging records for the warp-cooperative stores
   size_t smem = 0;
   p.dense_coop = 0;
+  {
+    // finalize/refill batching (ensemble_kernel.cuh): 2 is within a few percent of the optimum sqrt(2048 X / (n I)) for
+    // anything from short to long trajectories; DFX_REFILL_BATCH overrides it for experiments
+    static const int env_batch = [] { const char *e = getenv("DFX_REFILL_BATCH"); return e ? atoi(e) : 0; }();
+    p.refill_batch = env_batch >= 1 ? (env_batch > 32 ? 32 : env_batch) : 2;
+  }
   if (RICH && p.save_dense && (Solver::kInterp == kInterpLinear || p.dense_k != nullptr)) {
     const int kk = Solver::kInterp != kInterpLinear ? Solver::S * Field::kDim : 0;
     const int stride = (kk + 2 * Field::kDim) | 1;
