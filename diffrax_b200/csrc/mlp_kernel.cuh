@@ -7,13 +7,18 @@
 // accumulated in fp32 in TMEM (residual ~2^-21 relative, the level of fp32 summation noise).
 //
 // Mapping
-//   * one CTA = 128 trajectories = the M tile; 256 threads: thread (warp w, lane l) owns row m = 32 (w % 4) + l (its TMEM
-//     lane) and the hidden-unit half w / 4 (columns [64 h, 64 h + 64)).  Both threads of a row carry the (tiny, d = 4) RK
-//     state redundantly and bit-identically, so only the MLP evaluation needs communication.
+//   * one CTA = 128 trajectories = the M tile; 16 compute warps + 1 MMA warp.  Compute thread (warp w, lane l) owns row
+//     m = 32 (w % 4) + l (its TMEM lane) and the hidden-unit quarter w / 4 (columns [32 q, 32 q + 32)).  The four threads of
+//     a row carry the (tiny, d = 4) RK state redundantly and bit-identically, so only the MLP evaluation communicates.
 //   * A (softplus(W1 y + b1), split hi/lo) is written by its owner threads straight into TMEM with tcgen05.st - a thread's
 //     row IS its TMEM lane - so A never touches shared memory; W2 (hi and lo, 2 x 64 KB) is resident in shared memory for
 //     the whole kernel in the canonical K-major no-swizzle UMMA layout; the accumulator D lives in TMEM and is read back
 //     with tcgen05.ld for the epilogue (bias, softplus, the 128 -> 4 output layer, tanh).
+//   * The contraction is software-pipelined over K against the layer-1 phase: every thread produces its 32 hidden units
+//     in 4 chunks of 8 (= one K = 8 MMA step per quarter); after each chunk it signals a named barrier (bar.arrive, no
+//     wait) and the MMA warp (bar.sync on the same barrier) issues that chunk's 4 K-steps x 3 TF32 passes, so the tensor
+//     pipe works on chunk c while the CUDA cores compute chunk c + 1; one tcgen05.commit per evaluation releases the
+//     epilogue through an mbarrier.
 //   * TMEM columns: D [0,128)  A_hi [128,256)  A_lo [256,384)  (512 allocated).
 //   * per-trajectory adaptive stepping: every lane has its own t / dt / accept-reject; a finished lane claims the next
 //     trajectory from the global queue; the stage loop is CTA-synchronous (one MMA batch per stage evaluation).
@@ -25,7 +30,9 @@
 namespace dfx {
 
 constexpr int kMlpD = 4, kMlpW = 128;
-constexpr int kMlpThreads = 256;
+constexpr int kMlpComputeThreads = 512;               // 16 warps: 4 TMEM lane quadrants x 4 hidden-unit quarters
+constexpr int kMlpThreads = kMlpComputeThreads + 32;  // + the MMA-issuing warp
+constexpr int kMlpChunks = 4, kMlpChunk = 8;          // a thread's 32 hidden units in 4 chunks of 8 (one K = 8 step each)
 constexpr uint32_t kTmemCols = 512;
 
 struct MlpSmem {
@@ -34,10 +41,10 @@ struct MlpSmem {
   float W1[kMlpW * kMlpD];
   float b1[kMlpW];
   float b2[kMlpW];
-  float W3[kMlpD * kMlpW];
+  float W3[kMlpW * kMlpD];     // transposed: W3t[o][c]
   float b3[kMlpD];
-  float part[2][kMlpW][kMlpD];  // layer-3 partial sums of the two hidden-unit halves
-  float k[14 * kMlpD][kMlpThreads];  // stage values k[i][c] of every thread (element-major: conflict-free), S <= 14
+  float part[4][kMlpW][kMlpD];  // layer-3 partial sums of the four hidden-unit quarters
+  float k[14 * kMlpD][kMlpW];   // stage values k[i][c] per row (the 4 threads of a row write identical values), S <= 14
   long long idx[kMlpW];
   unsigned long long mbar;
   uint32_t tmem_base;
@@ -87,6 +94,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -96,15 +109,41 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 // softplus = max(x,0) + log1p(exp(-|x|))   (jax.nn.softplus = logaddexp(x, 0))
+// FAST: the kernel works in base 2.  With z' = z log2(e):  softplus(z) = ln2 * sp2(z'),  sp2(z') = max(z',0) + log2(1 + 2^-|z'|)
+// (MUFU.EX2 + MUFU.LG2, abs. error ~1e-7).  The log2(e) is folded into W1, b1, b2 and the ln2 into W3 when the weights are
+// staged in shared memory; between the two hidden layers the factors cancel (ln2 * log2(e) = 1), so W2 is used as is.
 template <bool FAST> __device__ __forceinline__ float mlp_softplus(float x) {
   if constexpr (FAST) {
-    // SFU path: e = 2^(-|x| log2 e) (MUFU.EX2), log1p(e) = ln2 * log2(1 + e) (MUFU.LG2); abs. error ~1e-7
     float e, l;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(x) * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(x)));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
-    return fmaxf(x, 0.0f) + 0.6931471805599453f * l;
+    return fmaxf(x, 0.0f) + l;
   } else {
     return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
+  }
+}
+template <bool FAST> __device__ __forceinline__ float mlp_tanh(float x) {
+  if constexpr (FAST) {
+    // tanh(x) = 1 - 2 / (1 + e^(2x)); abs. error ~1e-7 (saturates correctly: e -> inf gives 1, e -> 0 gives -1)
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return fmaf(-2.0f, r, 1.0f);
+  } else {
+    return tanhf(x);
+  }
+}
+// TF32 operand split x = hi + lo for 3xTF32.  FAST: hi = x with the 13 low mantissa bits cleared - exactly what the tensor
+// core reads of an fp32 word - and lo = x - hi (exact); lo is in turn truncated by the hardware, so the dropped part is
+// < 2^-20 |x|.  Otherwise both are rounded to nearest with cvt.rna.tf32 (dropped part < 2^-22 |x|).
+template <bool FAST> __device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
+  if constexpr (FAST) {
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+  } else {
+    const float h = to_tf32(x);
+    hi = __float_as_uint(h);
+    lo = __float_as_uint(to_tf32(x - h));
   }
 }
 
@@ -117,8 +156,9 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
   MlpSmem &sm = *reinterpret_cast<MlpSmem *>(smem_raw);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
-  const int col0 = half * 64;  // this thread's hidden units [col0, col0 + 64)
+  const bool mma_warp = warp == kMlpComputeThreads / 32;
+  const int quad = warp & 3, part = (warp >> 2) & 3, row = quad * 32 + lane;
+  const int col0 = part * 32;  // this thread's hidden units [col0, col0 + 32)
 
   // ---------------- one-time set-up: weights -> smem (W2 split into TF32 hi / lo), TMEM, mbarrier ----------------
   const float *gW1 = w, *gb1 = gW1 + W * D, *gW2 = gb1 + W, *gb2 = gW2 + W * W, *gW3 = gb2 + W, *gb3 = gW3 + D * W;
@@ -129,8 +169,14 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
     sm.Bhi[off] = hi;
     sm.Blo[off] = lo;
   }
-  for (int i = tid; i < W * D; i += kMlpThreads) { sm.W1[i] = __ldg(gW1 + i); sm.W3[i] = __ldg(gW3 + i); }
-  for (int i = tid; i < W; i += kMlpThreads) { sm.b1[i] = __ldg(gb1 + i); sm.b2[i] = __ldg(gb2 + i); }
+  constexpr float kIn = FAST_ACT ? 1.4426950408889634f : 1.0f;   // log2(e) into the pre-activations
+  constexpr float kOut = FAST_ACT ? 0.6931471805599453f : 1.0f;  // ln2 back out of the last hidden layer
+  for (int i = tid; i < W * D; i += kMlpThreads) {
+    sm.W1[i] = __ldg(gW1 + i) * kIn;
+    const int c = i >> 7, o = i & 127;  // W3[c][o] -> W3t[o][c]: one 16-byte load per hidden unit in the epilogue
+    sm.W3[o * D + c] = __ldg(gW3 + i) * kOut;
+  }
+  for (int i = tid; i < W; i += kMlpThreads) { sm.b1[i] = __ldg(gb1 + i) * kIn; sm.b2[i] = __ldg(gb2 + i) * kIn; }
   if (tid < D) sm.b3[tid] = __ldg(gb3 + tid);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
@@ -150,53 +196,70 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
   const uint64_t bdesc_hi = make_b_desc(smem_u32(sm.Bhi), 128, 4096), bdesc_lo = make_b_desc(smem_u32(sm.Blo), 128, 4096);
   uint32_t phase = 0;
 
-  // ---------------- the MLP evaluation: all 256 threads, CTA-synchronous ----------------
+  // ---------------- the MMA warp's side of one MLP evaluation ----------------
+  // chunk c of every quarter q is K-step kk = 4 q + c; 3xTF32: (A_hi, B_hi), (A_hi, B_lo), (A_lo, B_hi)
+  auto mma_eval = [&]() {
+#pragma unroll 1
+    for (int c = 0; c < kMlpChunks; ++c) {
+      named_bar_sync(1 + c, kMlpThreads);  // all 512 producers have stored (and fenced) chunk c of A
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a_col = (pass == 2) ? 256u : 128u;
+          const uint64_t bd = (pass == 1) ? bdesc_lo : bdesc_hi;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int kk = 4 * q + c;
+            umma_tf32_ts(tmem, tmem + a_col + kk * 8, bd + (uint64_t)(kk * (256 >> 4)), (c | pass | q) ? 1u : 0u);
+          }
+        }
+        if (c == kMlpChunks - 1) umma_commit(mbar);
+      }
+      __syncwarp();
+    }
+  };
+
+  // ---------------- the MLP evaluation, compute threads ----------------
   auto eval = [&](const R (&yin)[D], R (&fout)[D]) {
     // layer 1 (4 -> 128) + softplus on the CUDA cores; split to TF32 hi/lo; straight into TMEM as the A operand
 #pragma unroll 1
-    for (int c16 = 0; c16 < 4; ++c16) {
-      uint32_t vh[16], vl[16];
+    for (int c = 0; c < kMlpChunks; ++c) {
+      uint32_t vh[kMlpChunk], vl[kMlpChunk];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int o = col0 + c16 * 16 + j;
+      for (int j = 0; j < kMlpChunk; ++j) {
+        const int o = col0 + c * kMlpChunk + j;
         const float4 w1 = *reinterpret_cast<const float4 *>(&sm.W1[o * D]);
-        float acc = w1.x * yin[0];
-        acc += w1.y * yin[1];
-        acc += w1.z * yin[2];
-        acc += w1.w * yin[3];
-        const float h = mlp_softplus<FAST_ACT>(acc + sm.b1[o]);
-        const float hi = to_tf32(h), lo = to_tf32(h - hi);
-        vh[j] = __float_as_uint(hi);
-        vl[j] = __float_as_uint(lo);
+        float acc;
+        if constexpr (FAST_ACT) {
+          acc = fmaf(w1.x, yin[0], sm.b1[o]);
+          acc = fmaf(w1.y, yin[1], acc);
+          acc = fmaf(w1.z, yin[2], acc);
+          acc = fmaf(w1.w, yin[3], acc);
+        } else {
+          acc = w1.x * yin[0];
+          acc += w1.y * yin[1];
+          acc += w1.z * yin[2];
+          acc += w1.w * yin[3];
+          acc += sm.b1[o];
+        }
+        tf32_split<FAST_ACT>(mlp_softplus<FAST_ACT>(acc), vh[j], vl[j]);
       }
-      tmem_st16(t_lane + 128 + col0 + c16 * 16, vh);
-      tmem_st16(t_lane + 256 + col0 + c16 * 16, vl);
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    // hidden layer on the tensor core: 3 x 16 MMAs of 128 x 128 x 8 issued by one thread
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a_col = (pass == 2) ? 256u : 128u;            // A_lo only in the third pass
-        const uint64_t bd = (pass == 1) ? bdesc_lo : bdesc_hi;       // B_lo only in the second pass
-#pragma unroll
-        for (int kk = 0; kk < W / 8; ++kk)
-          umma_tf32_ts(tmem, tmem + a_col + kk * 8, bd + (uint64_t)(kk * (256 >> 4)), (pass | kk) ? 1u : 0u);
-      }
-      umma_commit(mbar);
+      tmem_st8(t_lane + 128 + col0 + c * kMlpChunk, vh);
+      tmem_st8(t_lane + 256 + col0 + c * kMlpChunk, vl);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      named_bar_arrive(1 + c, kMlpThreads);
     }
     mbar_wait(mbar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // epilogue: D row -> + b2 -> softplus -> partial 128 -> 4 output layer over this thread's 64 hidden units
+    // epilogue: D row -> + b2 -> softplus -> partial 128 -> 4 output layer over this thread's 32 hidden units
     R acc3[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) acc3[c] = 0.0f;
 #pragma unroll 1
-    for (int c16 = 0; c16 < 4; ++c16) {
+    for (int c16 = 0; c16 < 2; ++c16) {
       uint32_t v[16];
       tmem_ld16(t_lane + col0 + c16 * 16, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -204,22 +267,27 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
       for (int j = 0; j < 16; ++j) {
         const int o = col0 + c16 * 16 + j;
         const float h2 = mlp_softplus<FAST_ACT>(__uint_as_float(v[j]) + sm.b2[o]);
-#pragma unroll
-        for (int c = 0; c < D; ++c) acc3[c] += sm.W3[c * W + o] * h2;
+        const float4 w3 = *reinterpret_cast<const float4 *>(&sm.W3[o * D]);
+        acc3[0] += w3.x * h2;
+        acc3[1] += w3.y * h2;
+        acc3[2] += w3.z * h2;
+        acc3[3] += w3.w * h2;
       }
     }
-    *reinterpret_cast<float4 *>(&sm.part[half][row][0]) = make_float4(acc3[0], acc3[1], acc3[2], acc3[3]);
+    *reinterpret_cast<float4 *>(&sm.part[part][row][0]) = make_float4(acc3[0], acc3[1], acc3[2], acc3[3]);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    named_bar_sync(6, kMlpComputeThreads);
     const float4 p0 = *reinterpret_cast<const float4 *>(&sm.part[0][row][0]);
     const float4 p1 = *reinterpret_cast<const float4 *>(&sm.part[1][row][0]);
-    fout[0] = tanhf((p0.x + p1.x) + sm.b3[0]);
-    fout[1] = tanhf((p0.y + p1.y) + sm.b3[1]);
-    fout[2] = tanhf((p0.z + p1.z) + sm.b3[2]);
-    fout[3] = tanhf((p0.w + p1.w) + sm.b3[3]);
+    const float4 p2 = *reinterpret_cast<const float4 *>(&sm.part[2][row][0]);
+    const float4 p3 = *reinterpret_cast<const float4 *>(&sm.part[3][row][0]);
+    fout[0] = mlp_tanh<FAST_ACT>(((p0.x + p1.x) + (p2.x + p3.x)) + sm.b3[0]);
+    fout[1] = mlp_tanh<FAST_ACT>(((p0.y + p1.y) + (p2.y + p3.y)) + sm.b3[1]);
+    fout[2] = mlp_tanh<FAST_ACT>(((p0.z + p1.z) + (p2.z + p3.z)) + sm.b3[2]);
+    fout[3] = mlp_tanh<FAST_ACT>(((p0.w + p1.w) + (p2.w + p3.w)) + sm.b3[3]);
   };
 
-  // ---------------- per-lane trajectory state (identical in both threads of a row) ----------------
+  // ---------------- per-lane trajectory state (identical in the four threads of a row) ----------------
   bool active = false, exhausted = false;
   long long idx = -1;
   R y[D];
@@ -233,50 +301,60 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
   const R sqrt_d = 2.0f;  // sqrt(D), D == 4
 
   for (;;) {
-    // ---- refill (claims are made by the half-0 thread of each row and shared through smem) ----
+    // ---- refill (claims are made by the quarter-0 thread of each row and shared through smem) ----
     if (!exhausted) {
-      if (half == 0) {
+      if (!mma_warp && part == 0) {
         const long long got = claim_work(!active, p.work_counter);
         sm.idx[row] = got;
       }
       __syncthreads();
-      const long long got = sm.idx[row];
-      const bool fail = !active && got >= p.n_traj;
-      if (!active && got >= 0 && got < p.n_traj) {
-        idx = got;
-        const R a = p.t0_arr ? p.t0_arr[idx] : p.t0, b = p.t1_arr ? p.t1_arr[idx] : p.t1;
-        direction = (a < b) ? 1.f : -1.f;
-        t0 = a * direction;
-        t1 = b * direction;
+      bool fail = false;
+      if (!mma_warp) {
+        const long long got = sm.idx[row];
+        fail = !active && got >= p.n_traj;
+        if (!active && got >= 0 && got < p.n_traj) {
+          idx = got;
+          const R a = p.t0_arr ? p.t0_arr[idx] : p.t0, b = p.t1_arr ? p.t1_arr[idx] : p.t1;
+          direction = (a < b) ? 1.f : -1.f;
+          t0 = a * direction;
+          t1 = b * direction;
 #pragma unroll
-        for (int c = 0; c < D; ++c) y[c] = p.y0[idx * D + c];
-        R dt0 = p.has_dt0 ? p.dt0 * direction : 0.01f;  // pid.py:48-49 through WrapTerm
-        if (p.controller == DFX_CTRL_PID) {
-          if (p.has_dtmax) dt0 = jnp_min(dt0, p.dtmax);
-          if (p.has_dtmin) dt0 = jnp_max(dt0, p.dtmin);
-        } else {
-          const R dt0_up = __int_as_float(__float_as_int(dt0) + (dt0 > 0.f ? 1 : (dt0 < 0.f ? -1 : 1)));
-          cs_num_steps = (int)ceil((double)((t1 - t0) / dt0_up));
-          cs_steps_completed = 1;
+          for (int c = 0; c < D; ++c) y[c] = p.y0[idx * D + c];
+          R dt0 = p.has_dt0 ? p.dt0 * direction : 0.01f;  // pid.py:48-49 through WrapTerm
+          if (p.controller == DFX_CTRL_PID) {
+            if (p.has_dtmax) dt0 = jnp_min(dt0, p.dtmax);
+            if (p.has_dtmin) dt0 = jnp_max(dt0, p.dtmin);
+          } else {
+            const R dt0_up = __int_as_float(__float_as_int(dt0) + (dt0 > 0.f ? 1 : (dt0 < 0.f ? -1 : 1)));
+            cs_num_steps = (int)ceil((double)((t1 - t0) / dt0_up));
+            cs_steps_completed = 1;
+          }
+          tprev = t0;
+          tnext = jnp_min(t0 + dt0, t1);
+          t1_clip_floor = prev_n<R>(t1, 100);
+          pid_inv = 1.f; pid_prev_inv = 1.f; at_dtmin = false;
+          num_steps = 0; num_accepted = 0; result = DFX_RESULT_SUCCESSFUL;
+          active = true;
         }
-        tprev = t0;
-        tnext = jnp_min(t0 + dt0, t1);
-        t1_clip_floor = prev_n<R>(t1, 100);
-        pid_inv = 1.f; pid_prev_inv = 1.f; at_dtmin = false;
-        num_steps = 0; num_accepted = 0; result = DFX_RESULT_SUCCESSFUL;
-        active = true;
       }
       exhausted = __syncthreads_or(fail) != 0;
     }
-    if (__syncthreads_and(!active)) break;
+    if (__syncthreads_and(mma_warp || !active)) break;
+
+    if (mma_warp) {  // S evaluations per attempted step, CTA-uniform
+#pragma unroll 1
+      for (int i = 0; i < S; ++i) mma_eval();
+      continue;
+    }
 
     // ---- one attempted step for every lane of the CTA ----
     const bool run = active && (tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL);
     const R st0 = tprev, st1 = tnext;
     const R dt = st1 - st0;
     const R control = direction * dt;
-    // The stage loop is rolled (one copy of the MLP evaluation in the instruction stream - the unrolled version
-    // thrashed the instruction cache with only 8 warps per SM); the stage values therefore live in shared memory.
+    // The stage loop is rolled (one copy of the MLP evaluation in the instruction stream); the stage values therefore
+    // live in shared memory, one copy per row: the four threads of a row store bit-identical values to the same word and
+    // each reads back what it wrote itself, so no barrier is needed.
     R y1[D], yerr[D], yi[D], fi[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) yi[c] = y[c];
@@ -288,14 +366,14 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
         for (int j = 0; j < i; ++j) {
           const R a = Solver::template a<R>(i, j);  // structural zeros contribute exact zeros
 #pragma unroll
-          for (int c = 0; c < D; ++c) yi[c] += a * sm.k[j * D + c][tid];
+          for (int c = 0; c < D; ++c) yi[c] += a * sm.k[j * D + c][row];
         }
 #pragma unroll
         for (int c = 0; c < D; ++c) yi[c] = y[c] + yi[c];
       }
       eval(yi, fi);  // the field is autonomous: stage times do not enter
 #pragma unroll
-      for (int c = 0; c < D; ++c) sm.k[i * D + c][tid] = control * fi[c];
+      for (int c = 0; c < D; ++c) sm.k[i * D + c][row] = control * fi[c];
     }
     if constexpr (Solver::kSsal) {
 #pragma unroll
@@ -306,7 +384,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
       for (int j = 0; j < S; ++j) {
         const R b = Solver::template b_sol<R>(j);
 #pragma unroll
-        for (int c = 0; c < D; ++c) y1[c] += b * sm.k[j * D + c][tid];
+        for (int c = 0; c < D; ++c) y1[c] += b * sm.k[j * D + c][row];
       }
 #pragma unroll
       for (int c = 0; c < D; ++c) y1[c] = y[c] + y1[c];
@@ -316,7 +394,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
     for (int j = 0; j < S; ++j) {
       const R b = Solver::template b_err<R>(j);
 #pragma unroll
-      for (int c = 0; c < D; ++c) yerr[c] += b * sm.k[j * D + c][tid];
+      for (int c = 0; c < D; ++c) yerr[c] += b * sm.k[j * D + c][row];
     }
 
     if (run) {
@@ -376,7 +454,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
     const bool finished = active && !((tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL));
     if (finished) {
       if ((tprev < t1) && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_MAX_STEPS_REACHED;
-      if (half == 0) {
+      if (part == 0) {
         if (p.save_t1) {
           p.ts_out[idx] = tprev * direction;
           *reinterpret_cast<float4 *>(&p.ys_out[idx * D]) = make_float4(y[0], y[1], y[2], y[3]);
