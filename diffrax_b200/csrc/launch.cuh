@@ -125,22 +125,6 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
   return 0;
 }
 
-template <class R>
-int launch_pad(R *buf, const int *count, long long n_rows, long long row_len, int per_item, int count_offset,
-               cudaStream_t stream) {
-  if (!buf || n_rows == 0 || row_len == 0) return 0;
-  int sms = 0;
-  if (int rc = device_sm_count(&sms)) return rc;
-  long long warps_needed = n_rows;
-  long long blocks = (warps_needed * 32 + 255) / 256;
-  const long long cap = (long long)sms * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  pad_tail_kernel<R><<<(unsigned)blocks, 256, 0, stream>>>(buf, count, n_rows, row_len, per_item, count_offset);
-  count_launch();
-  DFX_CUDA_OK(cudaGetLastError());
-  return 0;
-}
 
 // The launcher bound into the registry for one (R, Field, Solver, LEVY) combination.
 template <class R, class Field, class Solver, int LEVY>
@@ -155,34 +139,18 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   const bool rich = d->save_t0 || d->save_ts || d->save_steps || d->save_dense || (d->hairer_initial_step && std::isnan(d->dt0)) ||
                     d->step_ts || d->jump_ts;
 
-  // scratch: work-queue counter (+ save_count when the caller did not ask for it)
+  // scratch: the work-queue counter.  (The +inf padding of unfilled output slots is written by the solve kernel itself
+  // when it finalises a trajectory, so there is no second pass over the buffers.)
   unsigned long long *counter = nullptr;
-  int *save_count = p.save_count;
-  const bool need_pad = rich && (d->save_ts || d->save_steps);
-  size_t scratch_bytes = 16 + ((need_pad && !save_count) ? sizeof(int) * (size_t)p.n_traj : 0);
   char *scratch = nullptr;
-  DFX_CUDA_OK(cudaMallocAsync((void **)&scratch, scratch_bytes, stream));
+  DFX_CUDA_OK(cudaMallocAsync((void **)&scratch, 16, stream));
   DFX_CUDA_OK(cudaMemsetAsync(scratch, 0, 16, stream));
   counter = (unsigned long long *)scratch;
-  if (need_pad && !save_count) save_count = (int *)(scratch + 16);
   p.work_counter = counter;
-  p.save_count = save_count;
 
   int rc;
   if (rich) rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);
   else rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
-  if (rc == 0 && need_pad) {
-    rc = launch_pad<R>(p.ts_out, save_count, p.n_traj, p.out_size, 1, 0, stream);
-    if (rc == 0) rc = launch_pad<R>(p.ys_out, save_count, p.n_traj, (long long)p.out_size * Field::kDim, Field::kDim, 0, stream);
-  }
-  if (rc == 0 && d->save_dense) {
-    const long long ms = p.max_steps;
-    rc = launch_pad<R>(p.dense_ts, p.dense_count, p.n_traj, ms + 1, 1, 1, stream);
-    if (rc == 0) rc = launch_pad<R>(p.dense_y0, p.dense_count, p.n_traj, ms * Field::kDim, Field::kDim, 0, stream);
-    if (rc == 0) rc = launch_pad<R>(p.dense_y1, p.dense_count, p.n_traj, ms * Field::kDim, Field::kDim, 0, stream);
-    if (rc == 0 && Solver::kInterp != kInterpLinear)
-      rc = launch_pad<R>(p.dense_k, p.dense_count, p.n_traj, ms * Solver::S * Field::kDim, Solver::S * Field::kDim, 0, stream);
-  }
   cudaFreeAsync(scratch, stream);
   return rc;
 }

@@ -222,10 +222,10 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
 
   // ---------------- the MLP evaluation, compute threads ----------------
   auto eval = [&](const R (&yin)[D], R (&fout)[D]) {
-    // layer 1 (4 -> 128) + softplus on the CUDA cores; split to TF32 hi/lo; straight into TMEM as the A operand
-#pragma unroll 1
-    for (int c = 0; c < kMlpChunks; ++c) {
-      uint32_t vh[kMlpChunk], vl[kMlpChunk];
+    // layer 1 (4 -> 128) + softplus on the CUDA cores; split to TF32 hi/lo; straight into TMEM as the A operand.
+    // Chunk c is stored, then chunk c + 1 is computed BEFORE waiting for those stores (tcgen05.wait::st) and signalling
+    // the MMA warp, so the TMEM store latency hides behind arithmetic.
+    auto layer1_chunk = [&](int c, uint32_t (&vh)[kMlpChunk], uint32_t (&vl)[kMlpChunk]) {
 #pragma unroll
       for (int j = 0; j < kMlpChunk; ++j) {
         const int o = col0 + c * kMlpChunk + j;
@@ -245,11 +245,24 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
         }
         tf32_split<FAST_ACT>(mlp_softplus<FAST_ACT>(acc), vh[j], vl[j]);
       }
-      tmem_st8(t_lane + 128 + col0 + c * kMlpChunk, vh);
-      tmem_st8(t_lane + 256 + col0 + c * kMlpChunk, vl);
+    };
+    {
+      uint32_t vh[kMlpChunk], vl[kMlpChunk];
+      layer1_chunk(0, vh, vl);
+      tmem_st8(t_lane + 128 + col0, vh);
+      tmem_st8(t_lane + 256 + col0, vl);
+#pragma unroll 1
+      for (int c = 1; c < kMlpChunks; ++c) {
+        layer1_chunk(c, vh, vl);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        named_bar_arrive(c, kMlpThreads);  // chunk c - 1 is in TMEM (barrier ids 1 .. 4 <-> chunks 0 .. 3)
+        tmem_st8(t_lane + 128 + col0 + c * kMlpChunk, vh);
+        tmem_st8(t_lane + 256 + col0 + c * kMlpChunk, vl);
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      named_bar_arrive(1 + c, kMlpThreads);
+      named_bar_arrive(kMlpChunks, kMlpThreads);
     }
     mbar_wait(mbar, phase);
     phase ^= 1u;
@@ -258,21 +271,25 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
     R acc3[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) acc3[c] = 0.0f;
-#pragma unroll 1
-    for (int c16 = 0; c16 < 2; ++c16) {
-      uint32_t v[16];
-      tmem_ld16(t_lane + col0 + c16 * 16, v);
+    {
+      uint32_t v0[16], v1[16];
+      tmem_ld16(t_lane + col0, v0);  // both halves of this thread's 32 accumulator columns in flight at once
+      tmem_ld16(t_lane + col0 + 16, v1);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      auto out16 = [&](int base, const uint32_t (&v)[16]) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int o = col0 + c16 * 16 + j;
-        const float h2 = mlp_softplus<FAST_ACT>(__uint_as_float(v[j]) + sm.b2[o]);
-        const float4 w3 = *reinterpret_cast<const float4 *>(&sm.W3[o * D]);
-        acc3[0] += w3.x * h2;
-        acc3[1] += w3.y * h2;
-        acc3[2] += w3.z * h2;
-        acc3[3] += w3.w * h2;
-      }
+        for (int j = 0; j < 16; ++j) {
+          const int o = base + j;
+          const float h2 = mlp_softplus<FAST_ACT>(__uint_as_float(v[j]) + sm.b2[o]);
+          const float4 w3 = *reinterpret_cast<const float4 *>(&sm.W3[o * D]);
+          acc3[0] += w3.x * h2;
+          acc3[1] += w3.y * h2;
+          acc3[2] += w3.z * h2;
+          acc3[3] += w3.w * h2;
+        }
+      };
+      out16(col0, v0);
+      out16(col0 + 16, v1);
     }
     *reinterpret_cast<float4 *>(&sm.part[part][row][0]) = make_float4(acc3[0], acc3[1], acc3[2], acc3[3]);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
