@@ -170,6 +170,32 @@ class ShARK(_Solver):
     name, _order, _strong_order = "shark", 2, 1.5  # shark.py:57-64
 
 
+class HalfSolver(_Solver):
+    """_solver/base.py:250-346: wraps `solver`; every step also makes two half steps, the pair of half steps is the
+    result and |y1 - y1_full| the error estimate, so any solver can be used with an adaptive controller (the documented
+    recipe for adaptive SDE stepping, docs/usage/getting-started.md:102-110).  Order / strong order / interpolant are the
+    wrapped solver's; the error order is order + 1 (ODE) or strong_order + 0.5 (SDE)."""
+
+    def __init__(self, solver):
+        if isinstance(solver, HalfSolver) or not isinstance(solver, _Solver):
+            raise NotImplementedError("HalfSolver wraps one of the built-in solvers (not another HalfSolver)")
+        self.solver = solver
+        self.name = solver.name  # dense_info / interpolant are the wrapped solver's
+
+    def order(self, terms=None):
+        return self.solver.order(terms)
+
+    def strong_order(self, terms=None):
+        return self.solver.strong_order(terms)
+
+    @property
+    def solver_id(self):
+        return _lib.HALF_SOLVER | self.solver.solver_id
+
+    def __repr__(self):
+        return f"HalfSolver({self.solver!r})"
+
+
 # --------------------------------------------------------------------------------------
 # step size controllers
 # --------------------------------------------------------------------------------------
@@ -567,11 +593,13 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         D.force_dtmin = int(ctrl.force_dtmin)
         D.error_order = math.nan if ctrl.error_order is None else float(ctrl.error_order)
         D.hairer_initial_step = int(bool(hairer_initial_step))
-        if isinstance(solver, Euler):
-            if bm is not None:
+        inner = solver.solver if isinstance(solver, HalfSolver) else solver
+        if isinstance(inner, Euler):
+            if bm is not None:  # "Specific check to not work even if using HalfSolver(Euler())", _integrate.py:1143-1149
                 raise ValueError("An SDE should not be solved with adaptive step sizes with Euler's method, "
-                                 "as it may not converge to the correct solution.")  # _integrate.py:1143-1149
-            raise RuntimeError("Cannot use adaptive step sizes with a solver that does not provide error estimates.")
+                                 "as it may not converge to the correct solution.")
+            if not isinstance(solver, HalfSolver):
+                raise RuntimeError("Cannot use adaptive step sizes with a solver that does not provide error estimates.")
     elif isinstance(ctrl, ConstantStepSize):
         D.controller = _lib.CTRL_CONSTANT
         D.dtmin = D.dtmax = D.error_order = math.nan
@@ -613,7 +641,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         D.threefry_partitionable = int(bm.partitionable)
         if not field.is_sde:
             raise ValueError(f"{type(field).__name__} is not an SDE functor")
-    elif isinstance(solver, ShARK):
+    elif isinstance(solver.solver if isinstance(solver, HalfSolver) else solver, ShARK):
         raise ValueError("ShARK requires MultiTerm(ODETerm(drift), ControlTerm(diffusion, VirtualBrownianTree))")
 
     T = L.dfx_out_size(C.byref(D))

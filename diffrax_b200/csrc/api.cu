@@ -204,7 +204,7 @@ template <class R>
 static int dense_eval_dispatch(int solver_id, int dim, long long n, int ms, const void *dts, const void *dy0,
                                const void *dy1, const void *dk, const int *dc, double direction, const void *tq, int nq,
                                void *out, cudaStream_t st) {
-  switch (solver_id) {
+  switch (solver_id & ~DFX_HALF_SOLVER) {  // HalfSolver(inner) records the inner solver's dense_info
 #define DFX_DS(ID, T) case ID: return dense_eval_dispatch_dim<R, T>(dim, n, ms, dts, dy0, dy1, dk, dc, direction, tq, nq, out, st);
     DFX_DS(DFX_TSIT5, Tsit5) DFX_DS(DFX_DOPRI5, Dopri5) DFX_DS(DFX_DOPRI8, Dopri8) DFX_DS(DFX_HEUN, Heun)
     DFX_DS(DFX_BOSH3, Bosh3) DFX_DS(DFX_MIDPOINT, Midpoint) DFX_DS(DFX_RALSTON, Ralston)
@@ -236,7 +236,7 @@ int dfx_device_count(void) {
 }
 
 int dfx_num_stages(int solver_id) {
-  switch (solver_id) {
+  switch (solver_id & ~DFX_HALF_SOLVER) {  // HalfSolver(inner): the inner solver's stages (its dense_info)
     case DFX_TSIT5: return Tsit5::S; case DFX_DOPRI5: return Dopri5::S; case DFX_DOPRI8: return Dopri8::S;
     case DFX_HEUN: return Heun::S; case DFX_BOSH3: return Bosh3::S; case DFX_MIDPOINT: return Midpoint::S;
     case DFX_RALSTON: return Ralston::S; case DFX_EULER: return 1; case DFX_SHARK: return 2;
@@ -244,7 +244,7 @@ int dfx_num_stages(int solver_id) {
   return -1;
 }
 int dfx_solver_order(int solver_id) {
-  switch (solver_id) {
+  switch (solver_id & ~DFX_HALF_SOLVER) {
     case DFX_TSIT5: return Tsit5::kOrder; case DFX_DOPRI5: return Dopri5::kOrder; case DFX_DOPRI8: return Dopri8::kOrder;
     case DFX_HEUN: return Heun::kOrder; case DFX_BOSH3: return Bosh3::kOrder; case DFX_MIDPOINT: return Midpoint::kOrder;
     case DFX_RALSTON: return Ralston::kOrder; case DFX_EULER: return 1; case DFX_SHARK: return 2;
@@ -301,6 +301,11 @@ static int check_desc(const dfx_solve_desc *d) {
     set_error("Can only apply `ClipStepSizeController` to adaptive step size controllers.");
     return DFX_ERR_BAD_ARGUMENT;
   }
+  if (d->controller == DFX_CTRL_PID && d->levy_area != DFX_LEVY_NONE && (d->solver_id & ~DFX_HALF_SOLVER) == DFX_EULER) {
+    // _integrate.py:1143-1149 ("Specific check to not work even if using HalfSolver(Euler())")
+    set_error("An SDE should not be solved with adaptive step sizes with Euler's method, as it may not converge to the correct solution.");
+    return DFX_ERR_BAD_ARGUMENT;
+  }
   if (d->controller == DFX_CTRL_PID && d->solver_id == DFX_EULER) {
     // pid.py:461-469 (Euler provides no error estimate)
     set_error("Cannot use adaptive step sizes with a solver that does not provide error estimates.");
@@ -319,11 +324,11 @@ static int check_desc(const dfx_solve_desc *d) {
   if (d->levy_area != DFX_LEVY_NONE) {
     if (!d->bm_keys) { set_error("SDE solve needs bm_keys"); return DFX_ERR_BAD_ARGUMENT; }
     if (!(d->bm_t0 < d->bm_t1)) { set_error("t0 must be strictly less than t1"); return DFX_ERR_BAD_ARGUMENT; }  // tree.py:281
-    if (d->solver_id == DFX_SHARK && d->levy_area != DFX_LEVY_SPACE_TIME) {
+    if ((d->solver_id & ~DFX_HALF_SOLVER) == DFX_SHARK && d->levy_area != DFX_LEVY_SPACE_TIME) {
       set_error("The Brownian increment does not have the minimal Levy Area SpaceTimeLevyArea.");  // srk.py:391-395
       return DFX_ERR_BAD_ARGUMENT;
     }
-  } else if (d->solver_id == DFX_SHARK) {
+  } else if ((d->solver_id & ~DFX_HALF_SOLVER) == DFX_SHARK) {
     set_error("ShARK needs MultiTerm(ODETerm, ControlTerm(VirtualBrownianTree))");
     return DFX_ERR_BAD_ARGUMENT;
   }

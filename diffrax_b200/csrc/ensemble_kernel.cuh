@@ -44,9 +44,23 @@ struct SharkSolver {
   static constexpr int kInterp = kInterpLinear;
   static constexpr bool kIsTableau = false;
 };
+// HalfSolver(inner), _solver/base.py:250-346: every step is two half steps of `inner` (the result) and one full step (the
+// dense_info and, through |y1 - y1_alt|, the error estimate).  Inherits the inner solver's tableau / interpolant.
+template <class Inner>
+struct HalfOf : Inner {
+  static constexpr int kId = DFX_HALF_SOLVER | Inner::kId;
+  static constexpr int kInnerId = Inner::kId;
+  static constexpr int kOrder = Inner::kOrder + 1;  // error order on an ODE (base.py:296-299)
+  static constexpr bool kHalf = true;
+};
+template <class T, class = void> struct IsHalf { static constexpr bool value = false; };
+template <class I> struct IsHalf<HalfOf<I>> { static constexpr bool value = true; };
+template <class T> struct InnerId { static constexpr int value = T::kId; };
+template <class I> struct InnerId<HalfOf<I>> { static constexpr int value = I::kId; };
 template <class T, class = void> struct IsTableau { static constexpr bool value = true; };
 template <> struct IsTableau<EulerSolver> { static constexpr bool value = false; };
 template <> struct IsTableau<SharkSolver> { static constexpr bool value = false; };
+template <class I> struct IsTableau<HalfOf<I>> { static constexpr bool value = IsTableau<I>::value; };
 
 template <class R>
 struct SolveParams {
@@ -399,141 +413,164 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         [[maybe_unused]] const long long idx = idx_i;
         const R st0 = tprev, st1 = tnext;
         const R dt = st1 - st0;
-        R k[S][D];
-        R y1[D], yerr[D], f_last[D];
-        R W = R(0), H = R(0);
-        if constexpr (SDE) bm.increment(st0, st1, p.vbt, W, H);  // one Brownian query per step (runge_kutta.py:644, srk.py:390)
+        // One step of the (unwrapped) solver on [st0, st1] from y: AbstractRungeKutta.step / Euler.step / the ShARK branch
+        // of AbstractSRK.step.  f_in = carried FSAL derivative, reeval = made_jump; k, y1, yerr, f_last are the outputs.
+        auto single_step = [&](const R st0, const R st1, const R (&y)[D], [[maybe_unused]] const R (&f_in)[D],
+                               [[maybe_unused]] const bool reeval, R (&y1)[D], R (&yerr)[D], R (&k)[S][D], R (&f_last)[D]) {
+          const R dt = st1 - st0;
+          R W = R(0), H = R(0);
+          if constexpr (SDE) bm.increment(st0, st1, p.vbt, W, H);  // one Brownian query per step (runge_kutta.py:644, srk.py:390)
 
-        if constexpr (TAB) {
-          // ---- explicit RK step, runge_kutta.py:643-1203 ----
-          const R control = direction * dt;  // WrapTerm.contr (_term.py:742-745)
-          R yi[D], fi[D];
-          if constexpr (FSAL) {
-            if constexpr (RICH) {
-              // eval_first_stage = first_step | made_jump (runge_kutta.py:687): after stepping around a jump the carried
-              // derivative belongs to the other side of the discontinuity and is re-evaluated at (tprev, y)
-              if (made_jump) Field::template eval<R>(fp, st0 * direction, y, f_fsal);
-            }
-#pragma unroll
-            for (int c = 0; c < D; ++c) k[0][c] = control * f_fsal[c];  // prod(f0), 695 & 771
-          } else {
-            Field::template eval<R>(fp, st0 * direction, y, fi);
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              R kk = control * fi[c];
-              if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * W;  // MultiTerm.vf_prod (_term.py:711-722)
-              k[0][c] = kk;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < D; ++c) yi[c] = y[c];
-#pragma unroll
-          for (int i = 1; i < S; ++i) {  // rk_stage, 847-1069
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              if constexpr (kChainY0) {
-                // y_i = y0 + sum_j a_ij k_j as ONE chain of FMAs seeded with y0: saves the separate add per stage and
-                // component (18 of ~200 FP64 instructions of a Lorenz/Dopri5 step) at the price of rounding each partial
-                // sum at ulp(y0) instead of once
-                R acc = y[c];
-#pragma unroll
-                for (int j = 0; j < i; ++j)
-                  if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) acc += Solver::template a<R>(i, j) * k[j][c];
-                yi[c] = acc;
-              } else {
-                R incr = R(0);
-#pragma unroll
-                for (int j = 0; j < i; ++j)
-                  if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];  // vector_tree_dot (base.py:37-41); structural zeros skipped
-                yi[c] = y[c] + incr;  // 871
+          if constexpr (TAB) {
+            // ---- explicit RK step, runge_kutta.py:643-1203 ----
+            const R control = direction * dt;  // WrapTerm.contr (_term.py:742-745)
+            R yi[D], fi[D];
+            if constexpr (FSAL) {
+              R f0[D];
+  #pragma unroll
+              for (int c = 0; c < D; ++c) f0[c] = f_in[c];
+              if constexpr (RICH) {
+                // eval_first_stage = first_step | made_jump (runge_kutta.py:687): after stepping around a jump the carried
+                // derivative belongs to the other side of the discontinuity and is re-evaluated at (st0, y)
+                if (reeval) Field::template eval<R>(fp, st0 * direction, y, f0);
               }
-            }
-            const R ti = (Solver::hC(i) == 1.0) ? st1 : st0 + Solver::template c<R>(i) * dt;  // 1023
-            Field::template eval<R>(fp, ti * direction, yi, fi);
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              if constexpr (kLastStageF && !RICH) {
-                if (i == S - 1) continue;  // the last stage value is only read by the error estimate, through f_last below
-              }
-              R kk = control * fi[c];
-              if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, ti) * W;
-              k[i][c] = kk;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < D; ++c) f_last[c] = fi[c];
-          if constexpr (Solver::kSsal) {  // 1161
-#pragma unroll
-            for (int c = 0; c < D; ++c) y1[c] = yi[c];
-          } else {  // 1177-1185
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              R incr = R(0);
-#pragma unroll
-              for (int j = 0; j < S; ++j)
-                if (Solver::hBsol(j) != 0.0) incr += Solver::template b_sol<R>(j) * k[j][c];
-              y1[c] = y[c] + incr;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < D; ++c) {  // 1186-1193
-            R e = R(0);
-            if constexpr (kLastStageF) {
-              // FSAL+SSAL pairs: k_{s-1} = dt f(y1) enters only here, so take it as (b_err[s-1] dt) f(y1) and keep f(y1)
-              // (the next step's FSAL derivative) as the one live copy instead of k_{s-1} AND f(y1)
-#pragma unroll
-              for (int j = 0; j < S - 1; ++j)
-                if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
-              if (Solver::hBerr(S - 1) != 0.0) e += (Solver::template b_err<R>(S - 1) * control) * f_last[c];
+  #pragma unroll
+              for (int c = 0; c < D; ++c) k[0][c] = control * f0[c];  // prod(f0), 695 & 771
             } else {
-#pragma unroll
-              for (int j = 0; j < S; ++j)
-                if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
+              Field::template eval<R>(fp, st0 * direction, y, fi);
+  #pragma unroll
+              for (int c = 0; c < D; ++c) {
+                R kk = control * fi[c];
+                if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * W;  // MultiTerm.vf_prod (_term.py:711-722)
+                k[0][c] = kk;
+              }
             }
-            yerr[c] = e;
-          }
-        } else if constexpr (Solver::kId == DFX_EULER) {
-          // ---- euler.py:46-59 ----
-          R f0[D];
-          Field::template eval<R>(fp, st0 * direction, y, f0);
-#pragma unroll
-          for (int c = 0; c < D; ++c) {
-            R kk = (direction * dt) * f0[c];
-            if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * W;
-            k[0][c] = kk;
-            y1[c] = y[c] + kk;
-            yerr[c] = R(0);
-            f_last[c] = R(0);
-          }
-        } else {
-          // ---- ShARK: srk.py:335-671 additive-noise branch with shark.py:10-30 ----
-          if constexpr (SDE) {
-            const R h = dt;
-            const R g0 = Field::template diffusion<R>(fp, st0), g1 = Field::template diffusion<R>(fp, st1);
-            const R g_delta = R(0.5) * (g1 - g0);
-            const R w_kg = g0 * W, h_kg = g0 * H;  // 441-447
-            R z[D], fz[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) z[c] = y[c] + R(0) + (R(kSharkAW0) * w_kg + R(kSharkAH0) * h_kg);  // stage 0: 545
-            Field::template eval<R>(fp, st0, z, fz);  // 548: t0 + 0*h
-#pragma unroll
-            for (int c = 0; c < D; ++c) k[0][c] = h * fz[c];
-#pragma unroll
-            for (int c = 0; c < D; ++c) z[c] = y[c] + R(kSharkA10) * k[0][c] + (R(kSharkAW1) * w_kg + R(kSharkAH1) * h_kg);
-            Field::template eval<R>(fp, st0 + R(kSharkC1) * h, z, fz);
-#pragma unroll
-            for (int c = 0; c < D; ++c) k[1][c] = h * fz[c];
-#pragma unroll
+  #pragma unroll
+            for (int c = 0; c < D; ++c) yi[c] = y[c];
+  #pragma unroll
+            for (int i = 1; i < S; ++i) {  // rk_stage, 847-1069
+  #pragma unroll
+              for (int c = 0; c < D; ++c) {
+                if constexpr (kChainY0) {
+                  // y_i = y0 + sum_j a_ij k_j as ONE chain of FMAs seeded with y0: saves the separate add per stage and
+                  // component (18 of ~200 FP64 instructions of a Lorenz/Dopri5 step) at the price of rounding each partial
+                  // sum at ulp(y0) instead of once
+                  R acc = y[c];
+  #pragma unroll
+                  for (int j = 0; j < i; ++j)
+                    if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) acc += Solver::template a<R>(i, j) * k[j][c];
+                  yi[c] = acc;
+                } else {
+                  R incr = R(0);
+  #pragma unroll
+                  for (int j = 0; j < i; ++j)
+                    if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];  // vector_tree_dot (base.py:37-41); structural zeros skipped
+                  yi[c] = y[c] + incr;  // 871
+                }
+              }
+              const R ti = (Solver::hC(i) == 1.0) ? st1 : st0 + Solver::template c<R>(i) * dt;  // 1023
+              Field::template eval<R>(fp, ti * direction, yi, fi);
+  #pragma unroll
+              for (int c = 0; c < D; ++c) {
+                if constexpr (kLastStageF && !RICH) {
+                  if (i == S - 1) continue;  // the last stage value is only read by the error estimate, through f_last below
+                }
+                R kk = control * fi[c];
+                if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, ti) * W;
+                k[i][c] = kk;
+              }
+            }
+  #pragma unroll
+            for (int c = 0; c < D; ++c) f_last[c] = fi[c];
+            if constexpr (Solver::kSsal) {  // 1161
+  #pragma unroll
+              for (int c = 0; c < D; ++c) y1[c] = yi[c];
+            } else {  // 1177-1185
+  #pragma unroll
+              for (int c = 0; c < D; ++c) {
+                R incr = R(0);
+  #pragma unroll
+                for (int j = 0; j < S; ++j)
+                  if (Solver::hBsol(j) != 0.0) incr += Solver::template b_sol<R>(j) * k[j][c];
+                y1[c] = y[c] + incr;
+              }
+            }
+  #pragma unroll
+            for (int c = 0; c < D; ++c) {  // 1186-1193
+              R e = R(0);
+              if constexpr (kLastStageF) {
+                // FSAL+SSAL pairs: k_{s-1} = dt f(y1) enters only here, so take it as (b_err[s-1] dt) f(y1) and keep f(y1)
+                // (the next step's FSAL derivative) as the one live copy instead of k_{s-1} AND f(y1)
+  #pragma unroll
+                for (int j = 0; j < S - 1; ++j)
+                  if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
+                if (Solver::hBerr(S - 1) != 0.0) e += (Solver::template b_err<R>(S - 1) * control) * f_last[c];
+              } else {
+  #pragma unroll
+                for (int j = 0; j < S; ++j)
+                  if (Solver::hBerr(j) != 0.0) e += Solver::template b_err<R>(j) * k[j][c];
+              }
+              yerr[c] = e;
+            }
+          } else if constexpr (InnerId<Solver>::value == DFX_EULER) {
+            // ---- euler.py:46-59 ----
+            R f0[D];
+            Field::template eval<R>(fp, st0 * direction, y, f0);
+  #pragma unroll
             for (int c = 0; c < D; ++c) {
-              R diffusion_result = R(kSharkBW) * w_kg + R(kSharkBH) * h_kg;   // 603-607
-              diffusion_result = diffusion_result + g_delta * (W - R(2.0) * H);  // 612-618
-              yerr[c] = R(kSharkE0) * k[0][c] + R(kSharkE1) * k[1][c];        // 638-639, 663
-              const R drift_result = R(kSharkB0) * k[0][c] + R(kSharkB1) * k[1][c];  // 667
-              y1[c] = y[c] + drift_result + diffusion_result;                  // 669
+              R kk = (direction * dt) * f0[c];
+              if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * W;
+              k[0][c] = kk;
+              y1[c] = y[c] + kk;
+              yerr[c] = R(0);
               f_last[c] = R(0);
             }
+          } else {
+            // ---- ShARK: srk.py:335-671 additive-noise branch with shark.py:10-30 ----
+            if constexpr (SDE) {
+              const R h = dt;
+              const R g0 = Field::template diffusion<R>(fp, st0), g1 = Field::template diffusion<R>(fp, st1);
+              const R g_delta = R(0.5) * (g1 - g0);
+              const R w_kg = g0 * W, h_kg = g0 * H;  // 441-447
+              R z[D], fz[D];
+  #pragma unroll
+              for (int c = 0; c < D; ++c) z[c] = y[c] + R(0) + (R(kSharkAW0) * w_kg + R(kSharkAH0) * h_kg);  // stage 0: 545
+              Field::template eval<R>(fp, st0, z, fz);  // 548: t0 + 0*h
+  #pragma unroll
+              for (int c = 0; c < D; ++c) k[0][c] = h * fz[c];
+  #pragma unroll
+              for (int c = 0; c < D; ++c) z[c] = y[c] + R(kSharkA10) * k[0][c] + (R(kSharkAW1) * w_kg + R(kSharkAH1) * h_kg);
+              Field::template eval<R>(fp, st0 + R(kSharkC1) * h, z, fz);
+  #pragma unroll
+              for (int c = 0; c < D; ++c) k[1][c] = h * fz[c];
+  #pragma unroll
+              for (int c = 0; c < D; ++c) {
+                R diffusion_result = R(kSharkBW) * w_kg + R(kSharkBH) * h_kg;   // 603-607
+                diffusion_result = diffusion_result + g_delta * (W - R(2.0) * H);  // 612-618
+                yerr[c] = R(kSharkE0) * k[0][c] + R(kSharkE1) * k[1][c];        // 638-639, 663
+                const R drift_result = R(kSharkB0) * k[0][c] + R(kSharkB1) * k[1][c];  // 667
+                y1[c] = y[c] + drift_result + diffusion_result;                  // 669
+                f_last[c] = R(0);
+              }
+            }
           }
+        };
+        R k[S][D];
+        R y1[D], yerr[D], f_last[D];
+        [[maybe_unused]] R y1_alt[D];
+        if constexpr (!IsHalf<Solver>::value) {
+          single_step(st0, st1, y, f_fsal, made_jump, y1, yerr, k, f_last);
+        } else {  // HalfSolver.step, base.py:312-341
+          R yhalf[D], f_half[D], f_alt[D], e_[D], k_half[S][D];
+          const R thalf = st0 + R(0.5) * (st1 - st0);
+          single_step(st0, thalf, y, f_fsal, made_jump, yhalf, e_, k_half, f_half);
+          single_step(thalf, st1, yhalf, f_half, false, y1, e_, k_half, f_last);
+          single_step(st0, st1, y, f_fsal, made_jump, y1_alt, e_, k, f_alt);  // dense_info comes from the full step
+#pragma unroll
+          for (int c = 0; c < D; ++c) yerr[c] = r_abs(y1[c] - y1_alt[c]);
         }
+        // the end point the local interpolant / dense output sees: dense_info["y1"] (y1_alt under HalfSolver)
+        [[maybe_unused]] auto &y1_dense = *(IsHalf<Solver>::value ? &y1_alt : &y1);
 
         // ---- step-size controller ----
         bool keep;
@@ -655,7 +692,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               const R tq = p.save_ts[saveat_ts_index] * direction;
               if (!(tq <= st1)) break;
               R yq[D];
-              interp_eval<INTERP, R, S, D>(st0, st1, y, y1, k, tq, yq);
+              interp_eval<INTERP, R, S, D>(st0, st1, y, y1_dense, k, tq, yq);
               const long long o = idx * (long long)p.out_size + save_index;
               p.ts_out[o] = tq * direction;  // final ts *= direction (1479-1482)
 #pragma unroll
@@ -684,11 +721,11 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
 #pragma unroll
                 for (int c = 0; c < D; ++c) rec[DENSE_K ? j * D + c : 0] = k[j][c];
 #pragma unroll
-              for (int c = 0; c < D; ++c) { rec[kDenseK + c] = y[c]; rec[kDenseK + D + c] = y1[c]; }
+              for (int c = 0; c < D; ++c) { rec[kDenseK + c] = y[c]; rec[kDenseK + D + c] = y1_dense[c]; }
               dense_row = row;
             } else {
               store_row<D>(&p.dense_y0[row * D], y, p.dense_vec_ok != 0);
-              store_row<D>(&p.dense_y1[row * D], y1, p.dense_vec_ok != 0);
+              store_row<D>(&p.dense_y1[row * D], y1_dense, p.dense_vec_ok != 0);
               if constexpr (DENSE_K) {
                 if (p.dense_k != nullptr) {
                   R flat[S * D];

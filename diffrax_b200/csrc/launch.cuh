@@ -48,7 +48,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   // base.py:97-120: ODE -> order ; SDE -> strong_order + 0.5 (Euler/Heun 0.5, ShARK 1.5)
   double error_order;
   if (!is_nan(d->error_order)) error_order = d->error_order;
-  else if (sde) error_order = (Solver::kId == DFX_SHARK ? 1.5 : 0.5) + 0.5;
+  else if (sde) error_order = (InnerId<Solver>::value == DFX_SHARK ? 1.5 : 0.5) + 0.5;  // HalfSolver: the same (base.py:291-295)
   else error_order = (double)Solver::kOrder;
   const double c1 = (d->icoeff + d->pcoeff + d->dcoeff) / error_order;  // pid.py:512-514
   const double c2 = -(d->pcoeff + 2 * d->dcoeff) / error_order;
@@ -186,6 +186,10 @@ struct Registrar {
   DFX_REGISTER(float, Field, ::dfx::Bosh3, 0)             \
   DFX_REGISTER(float, Field, ::dfx::Midpoint, 0)          \
   DFX_REGISTER(float, Field, ::dfx::Ralston, 0)           \
-  DFX_REGISTER(float, Field, ::dfx::EulerSolver, 0)
+  DFX_REGISTER(float, Field, ::dfx::EulerSolver, 0) \
+  DFX_REGISTER(double, Field, ::dfx::HalfOf<::dfx::EulerSolver>, 0) \
+  DFX_REGISTER(double, Field, ::dfx::HalfOf<::dfx::Heun>, 0)        \
+  DFX_REGISTER(float, Field, ::dfx::HalfOf<::dfx::EulerSolver>, 0)  \
+  DFX_REGISTER(float, Field, ::dfx::HalfOf<::dfx::Heun>, 0)
 
 }  // namespace dfx

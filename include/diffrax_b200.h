@@ -34,7 +34,9 @@ enum dfx_dtype { DFX_F64 = 0, DFX_F32 = 1 };
 
 /* Solvers: diffrax/_solver/{tsit5,dopri5,dopri8,heun,bosh3,midpoint,ralston,euler,shark}.py */
 enum dfx_solver { DFX_TSIT5 = 0, DFX_DOPRI5 = 1, DFX_DOPRI8 = 2, DFX_HEUN = 3, DFX_BOSH3 = 4,
-                  DFX_MIDPOINT = 5, DFX_RALSTON = 6, DFX_EULER = 7, DFX_SHARK = 8 };
+                  DFX_MIDPOINT = 5, DFX_RALSTON = 6, DFX_EULER = 7, DFX_SHARK = 8,
+                  /* flag: HalfSolver(inner) is DFX_HALF_SOLVER | inner (diffrax/_solver/base.py:250-346) */
+                  DFX_HALF_SOLVER = 0x100 };
 
 /* Step size controllers: _step_size_controller/constant.py:20-104, pid.py:299-567 */
 enum dfx_controller { DFX_CTRL_CONSTANT = 0, DFX_CTRL_PID = 1 };

@@ -148,6 +148,13 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
+HALF = 0x100  # ORC_HALF: HalfSolver(inner) is spelled "half:<inner>", e.g. "half:euler"
+
+
+def solver_id(name):
+    return (HALF | SOLVERS[name[5:]]) if name.startswith("half:") else SOLVERS[name]
+
+
 def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.float64,
           controller="pid", rtol=1e-3, atol=1e-6, pcoeff=0.0, icoeff=1.0, dcoeff=0.0, safety=0.9,
           factormin=0.2, factormax=10.0, dtmin=None, dtmax=None, force_dtmin=True, error_order=None,
@@ -164,7 +171,7 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
     n, d = y0.shape
     D = Desc()
     D.field_id = FIELDS[field] if isinstance(field, str) else int(field)
-    D.dim, D.dtype, D.solver_id = d, (F64 if dt == np.float64 else F32), SOLVERS[solver]
+    D.dim, D.dtype, D.solver_id = d, (F64 if dt == np.float64 else F32), solver_id(solver)
     p = np.ascontiguousarray(params, np.float64).ravel()
     D.field_params, D.n_field_params = _ptr(p), p.size
     cb = None
@@ -215,7 +222,7 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
         dts = np.empty((n, max_steps + 1), dt)
         dy0 = np.empty((n, max_steps, d), dt)
         dy1 = np.empty((n, max_steps, d), dt)
-        dk = np.empty((n, max_steps, s, d), dt) if solver not in ("euler", "shark") else None
+        dk = np.empty((n, max_steps, s, d), dt) if solver.split(":")[-1] not in ("euler", "shark") else None
         dcount = np.zeros(n, np.int32)
         D.dense_ts, D.dense_y0, D.dense_y1, D.dense_k, D.dense_count = _ptr(dts), _ptr(dy0), _ptr(dy1), _ptr(dk), _ptr(dcount)
         dense = dict(ts=dts, y0=dy0, y1=dy1, k=dk, count=dcount)
@@ -265,7 +272,7 @@ def dense_evaluate(solver, dense, tq, direction=1.0):
     tq = np.ascontiguousarray(tq, dt).reshape(n, -1)
     nq = tq.shape[1]
     out = np.empty((n, nq, d), dt)
-    lib().orc_dense_evaluate(F64 if dt == np.float64 else F32, SOLVERS[solver], n, d, msp1 - 1, _ptr(dts),
+    lib().orc_dense_evaluate(F64 if dt == np.float64 else F32, solver_id(solver), n, d, msp1 - 1, _ptr(dts),
                              _ptr(dense["y0"]), _ptr(dense["y1"]), _ptr(dense["k"]), _ptr(dense["count"]),
                              float(direction), _ptr(tq), nq, _ptr(out))
     return out

@@ -215,6 +215,7 @@ static void solve_range(void *ctx, int64_t lo, int64_t hi) {
 }
 
 int orc_num_stages(int solver_id) {
+  solver_id &= ~ORC_HALF; /* HalfSolver(inner): the inner solver's stages / interpolant */
   for (int i = 0; i < ORC_NUM_TABLEAUX; ++i)
     if (orc_tableaux[i].id == solver_id) return orc_tableaux[i].stages;
   if (solver_id == ORC_SHARK) return 2;
@@ -265,6 +266,7 @@ int orc_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, con
 int orc_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
                        const void *dense_y0, const void *dense_y1, const void *dense_k, const int32_t *dense_count,
                        double direction, const void *tq, int nq, void *out) {
+  solver_id &= ~ORC_HALF;
   const int s = orc_num_stages(solver_id);
   for (int64_t i = 0; i < n_traj; ++i) {
     for (int q = 0; q < nq; ++q) {

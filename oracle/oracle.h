@@ -29,7 +29,8 @@ extern "C" {
 enum { ORC_F64 = 0, ORC_F32 = 1 };
 /* solver ids (same numbering as tools/gen_tableaux.py) */
 enum { ORC_TSIT5 = 0, ORC_DOPRI5 = 1, ORC_DOPRI8 = 2, ORC_HEUN = 3, ORC_BOSH3 = 4,
-       ORC_MIDPOINT = 5, ORC_RALSTON = 6, ORC_EULER = 7, ORC_SHARK = 8 };
+       ORC_MIDPOINT = 5, ORC_RALSTON = 6, ORC_EULER = 7, ORC_SHARK = 8,
+       ORC_HALF = 0x100 /* flag: HalfSolver(inner), _solver/base.py:250-346 */ };
 /* controller */
 enum { ORC_CTRL_CONSTANT = 0, ORC_CTRL_PID = 1 };
 /* vector fields */

@@ -31,6 +31,11 @@ SOLVERS = {"tsit5": dfx.Tsit5, "dopri5": dfx.Dopri5, "dopri8": dfx.Dopri8, "heun
            "midpoint": dfx.Midpoint, "ralston": dfx.Ralston, "euler": dfx.Euler, "shark": dfx.ShARK}
 
 
+def make_solver(name):
+    """'half:<inner>' is the oracle's spelling of HalfSolver(inner)."""
+    return dfx.HalfSolver(SOLVERS[name[5:]]()) if name.startswith("half:") else SOLVERS[name]()
+
+
 def relerr(a, b):
     """Relative error per element, |a-b| / (|b| + 1e-3 max|b|); +-inf padding must coincide."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
@@ -57,7 +62,7 @@ def run_case(kw, dev, host=False):
     kw = dict(kw)
     fname, fparams = kw.pop("field"), kw.pop("params")
     field = make_golden._mlp if fname == "mlp" else FIELDS[fname](*fparams)
-    solver = SOLVERS[kw.pop("solver")]()
+    solver = make_solver(kw.pop("solver"))
     dtype = np.dtype(kw.pop("dtype", np.float64))
     y0 = np.asarray(kw.pop("y0"), dtype)
     t0, t1, dt0 = kw.pop("t0"), kw.pop("t1"), kw.pop("dt0")
@@ -374,6 +379,73 @@ def test_clip_step_size_controller(dev, solver, reverse):
                          stepsize_controller=ctrl, max_steps=2048)
     same2 = np.all(stats_np(s2) == o2["stats"], axis=1)
     assert relerr(to_np(s2.ys)[same2], o2["ys"][same2]) < RTOL64
+
+
+@pytest.mark.parametrize("inner", ["euler", "heun"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_half_solver_ode(dev, inner, dtype):
+    """HalfSolver(inner) (_solver/base.py:250-346) on an ODE: two half steps + one full step per step, error estimate
+    |y1 - y1_full|, error order = order + 1; SaveAt(ts) interpolates the FULL step's dense_info."""
+    f32 = dtype == np.float32
+    kw, n = _osc_case("half:" + inner, dtype, save_t0=True, save_t1=True, save_ts=np.linspace(0.0, 3.0, 13),
+                      rtol=1e-4 if inner == "euler" else 1e-6, atol=1e-6 if inner == "euler" else 1e-8, max_steps=20000)
+    o, sol = _oracle(kw), run_case(kw, dev)
+    st = stats_np(sol)
+    assert np.all(to_np(sol.result) == 0) and np.all(o["result"] == 0)
+    same = np.all(st == o["stats"], axis=1)
+    if not f32:
+        assert np.abs(st[:, 1] - o["stats"][:, 1]).max() <= 1
+        assert same.mean() >= 0.98, same.mean()
+    assert np.array_equal(to_np(sol.ts), o["ts"])
+    ys, oys = to_np(sol.ys), o["ys"]
+    if f32:
+        assert relerr_state(ys, oys) < 5e-4
+    else:
+        assert relerr(ys[same], oys[same]) < RTOL64
+        assert relerr(ys, oys) < 100 * kw["rtol"]
+
+
+@pytest.mark.parametrize("inner,lv", [("heun", "bi"), ("shark", "stla")])
+def test_half_solver_adaptive_sde(dev, inner, lv):
+    """The documented recipe for adaptive SDE stepping (docs/usage/getting-started.md:102-110): HalfSolver(solver) with
+    PIDController(pcoeff=0.1, icoeff=0.3); three Brownian queries per step ((t0,thalf), (thalf,t1), (t0,t1)) on the same tree.
+
+    The error estimate |y1 - y1_alt| is a difference of noise terms that often passes close to zero, so the step-size
+    feedback amplifies a 1-ulp difference (pow / division rounding) by ~10^3 per step (measured: 3e-15 -> 3e-12 -> ...):
+    after a handful of steps two correct implementations walk different step sequences.  Hence three checks:
+    (1) fixed steps (no feedback): whole solves agree to 1e-12; (2) adaptive, first 3 steps: 1e-6; (3) adaptive, whole
+    solve: everything succeeds and both land equally close to a fine fixed-step solution on the same Brownian paths."""
+    n = 256
+    keys = dfx.random.split(dfx.random.key(7), n)
+    base = dict(field="ou", params=[1.0, 0.0, 0.5], y0=np.ones((n, 1)), t0=0.0, t1=1.0, dt0=0.05, solver="half:" + inner,
+                levy_area=lv, keys=keys, bm_tol=2.0 ** -12, save_t1=True)
+    pid = dict(controller="pid", rtol=1e-3, atol=1e-4, pcoeff=0.1, icoeff=0.3, dtmin=2.0 ** -10)
+    kw = dict(base, controller="constant", max_steps=4096)
+    o, sol = _oracle(kw), run_case(kw, dev)
+    assert np.array_equal(stats_np(sol), o["stats"]) and relerr(to_np(sol.ys), o["ys"]) < 1e-12
+    kw = dict(base, max_steps=3, **pid)
+    o, sol = _oracle(kw), run_case(kw, dev)
+    assert np.array_equal(stats_np(sol), o["stats"])
+    assert relerr(to_np(sol.ts), o["ts"]) < 1e-6 and relerr(to_np(sol.ys), o["ys"]) < 1e-6   # (measured up to 1e-8 at step 3)
+    kw = dict(base, max_steps=4096, **pid)
+    o, sol = _oracle(kw), run_case(kw, dev)
+    assert np.all(to_np(sol.result) == 0) and np.all(o["result"] == 0)
+    fine = _oracle(dict(base, solver=inner, dt0=2.0 ** -11, controller="constant", max_steps=4096))["ys"]
+    e_gpu, e_orc = np.abs(to_np(sol.ys) - fine), np.abs(o["ys"] - fine)
+    assert e_gpu.max() < 0.05 and abs(e_gpu.mean() - e_orc.mean()) < 0.25 * e_orc.mean() + 1e-6, (e_gpu.mean(), e_orc.mean())
+    st, ost = stats_np(sol), o["stats"]
+    assert abs(st[:, 0].mean() - ost[:, 0].mean()) < 0.05 * ost[:, 0].mean()
+
+
+def test_half_solver_euler_sde_is_refused(dev):
+    """_integrate.py:1143-1149: 'Specific check to not work even if using HalfSolver(Euler())'."""
+    keys = dfx.random.split(dfx.random.key(0), 4)
+    ou = dfx.fields.OrnsteinUhlenbeck(1.0, 0.0, 0.5)
+    bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -8, (), torch.tensor(keys.view(np.int32), device=dev))
+    terms = dfx.MultiTerm(dfx.ODETerm(ou.drift), dfx.ControlTerm(ou.diffusion, bm))
+    with pytest.raises(ValueError, match="Euler"):
+        dfx.diffeqsolve(terms, dfx.HalfSolver(dfx.Euler()), 0.0, 1.0, 0.1, torch.ones(4, 1, device=dev, dtype=torch.float64),
+                        stepsize_controller=dfx.PIDController(rtol=1e-3, atol=1e-3))
 
 
 def test_hairer_initial_step_flag(dev):

@@ -218,3 +218,48 @@ def test_clip_step_size_controller_semantics():
     b = oracle.solve("callback", y0, 0.0, 2.0, None, solver="dopri5", rtol=1e-8, atol=1e-10, callback=f)
     assert abs(a["ys"][0, 0, 0] - exact) < 1e-8
     assert a["stats"][0, 2] < b["stats"][0, 2]
+
+
+def test_half_solver_semantics():
+    """HalfSolver.step (_solver/base.py:312-341) restated by hand for Euler on y' = -lam*y with the default I-controller:
+    y1 = two half steps, y1_alt = one full step, y_error = |y1 - y1_alt|, error order = order + 1 = 2 (base.py:296-299),
+    and SaveAt(ts) interpolates the FULL step's dense_info (linear between y0 and y1_alt for Euler)."""
+    lam, rtol, atol, t1 = 1.3, 1e-3, 1e-6, 2.0
+    r = oracle.solve("decay", np.array([[1.0]]), 0.0, t1, 0.1, solver="half:euler", params=[lam], controller="pid",
+                     rtol=rtol, atol=atol, save_t1=False, save_steps=1, max_steps=4096)
+    n_acc = int(r["stats"][0, 1])
+    t, tn, y, ts, ys, acc, rej = 0.0, 0.1, 1.0, [], [], 0, 0
+    floor = t1
+    for _ in range(100):
+        floor = np.nextafter(floor, -np.inf)
+    while t < t1:
+        h = tn - t
+        thalf = t + 0.5 * h
+        yh = y + (thalf - t) * (-lam * y)
+        y1 = yh + (tn - thalf) * (-lam * yh)
+        y1_alt = y + h * (-lam * y)
+        err = abs(y1 - y1_alt)
+        scaled = abs(err / (atol + max(abs(y), abs(y1)) * rtol))
+        keep = scaled < 1
+        factor = min(max(0.9 * (1.0 / scaled) ** (1.0 / 2.0), 1.0 if keep else 0.2), 10.0 if keep else 0.9)
+        nt0 = tn if keep else t
+        nt1 = nt0 + h * factor
+        if nt1 > floor:
+            nt1 = t1 if keep else nt0 + 0.5 * (t1 - nt0)
+        if keep:
+            y = y1; acc += 1; ts.append(nt0); ys.append(y)
+        else:
+            rej += 1
+        t, tn = nt0, nt1
+    assert (acc, rej) == (n_acc, int(r["stats"][0, 2]))
+    assert np.allclose(r["ts"][0, :n_acc], ts, rtol=1e-13, atol=0)
+    assert np.allclose(r["ys"][0, :n_acc, 0], ys, rtol=1e-12, atol=0)
+    # twice as accurate as the plain solver at the same (constant) step
+    plain = oracle.solve("decay", np.array([[1.0]]), 0.0, 1.0, 0.01, solver="euler", params=[1.0], controller="constant")
+    half = oracle.solve("decay", np.array([[1.0]]), 0.0, 1.0, 0.01, solver="half:euler", params=[1.0], controller="constant")
+    e_plain, e_half = abs(plain["ys"][0, -1, 0] - math.exp(-1)), abs(half["ys"][0, -1, 0] - math.exp(-1))
+    assert 1.8 < e_plain / e_half < 2.2
+    # FSAL inner solver: the carried derivative goes first half -> second half -> next step
+    r5 = oracle.solve("decay", np.array([[1.0]]), 0.0, 2.0, 0.1, solver="half:tsit5", params=[1.0], controller="pid",
+                      rtol=1e-9, atol=1e-12)
+    assert abs(r5["ys"][0, -1, 0] - math.exp(-2.0)) < 1e-10
