@@ -5,6 +5,7 @@
 
 #include "launch.cuh"
 #include "mlp_kernel.cuh"
+#include "mlp_kernel2.cuh"
 
 namespace {
 using namespace dfx;
@@ -32,14 +33,24 @@ int launch_mlp(const dfx_solve_desc *d, void *stream_v) {
     p.work_counter = counter;
     const char *slow_act = std::getenv("DFX_MLP_EXACT_ACT");
     const bool fast = !(slow_act && slow_act[0] == '1');
-    auto kern = fast ? mlp_tc_kernel<Solver, true> : mlp_tc_kernel<Solver, false>;
-    const int smem = (int)sizeof(MlpSmem);
-    DFX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int sms = 0;
     if (int rc = device_sm_count(&sms)) return rc;
-    long long blocks = (p.n_traj + 127) / 128;
-    if (blocks > sms) blocks = sms;  // persistent: one CTA (one 128-trajectory M tile) per SM
-    kern<<<(unsigned)blocks, kMlpThreads, smem, stream>>>(p, (const float *)d->field_weights);
+    const char *tiles_env = std::getenv("DFX_MLP_TILES");  // 2 (default): two tiles in flight per SM, mlp_kernel2.cuh; 1: mlp_kernel.cuh
+    if (tiles_env && tiles_env[0] == '1') {
+      auto kern = fast ? mlp_tc_kernel<Solver, true> : mlp_tc_kernel<Solver, false>;
+      const int smem = (int)sizeof(MlpSmem);
+      DFX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      long long blocks = (p.n_traj + 127) / 128;
+      if (blocks > sms) blocks = sms;  // persistent: one CTA (one 128-trajectory M tile) per SM
+      kern<<<(unsigned)blocks, kMlpThreads, smem, stream>>>(p, (const float *)d->field_weights);
+    } else {
+      auto kern = fast ? mlp_tc2_kernel<Solver, true> : mlp_tc2_kernel<Solver, false>;
+      const int smem = (int)sizeof(MlpSmem2);
+      DFX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      long long blocks = (p.n_traj + 255) / 256;
+      if (blocks > sms) blocks = sms;  // persistent: one CTA (two 128-trajectory M tiles) per SM
+      kern<<<(unsigned)blocks, kMlp2Threads, smem, stream>>>(p, (const float *)d->field_weights);
+    }
     count_launch();
     DFX_CUDA_OK(cudaGetLastError());
     cudaFreeAsync(counter, stream);

@@ -306,12 +306,15 @@ def test_mlp_tensor_core_kernel_matches_cuda_core_functor_and_oracle(dev, monkey
     y0 = rng.standard_normal((n, 4)).astype(np.float32)
     term, ctrl = dfx.ODETerm(mlp), dfx.PIDController(rtol=1e-3, atol=1e-6)
     y0d = torch.tensor(y0, device=dev)
-    tc = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d, stepsize_controller=ctrl)
+    tc = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d, stepsize_controller=ctrl)   # two tiles per SM (mlp_kernel2.cuh)
+    monkeypatch.setenv("DFX_MLP_TILES", "1")
+    tc1 = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d, stepsize_controller=ctrl)  # one tile per SM (mlp_kernel.cuh)
+    monkeypatch.delenv("DFX_MLP_TILES")
     monkeypatch.setenv("DFX_MLP_NO_TC", "1")
     cc = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d, stepsize_controller=ctrl)
     monkeypatch.delenv("DFX_MLP_NO_TC")
     o = oracle.solve("mlp", y0, 0.0, 10.0, None, solver="tsit5", params=mlp.oracle_params(), dtype=np.float32, rtol=1e-3, atol=1e-6)
-    for sol in (tc, cc):
+    for sol in (tc, tc1, cc):
         assert int((sol.result != 0).sum()) == 0
         assert relerr_state(to_np(sol.ys), o["ys"]) < RTOL32                     # north star: 1e-4 in fp32
         assert np.abs(to_np(sol.stats["num_accepted_steps"]) - o["stats"][:, 1]).max() <= 1
