@@ -83,10 +83,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}\n" :: "r"(mbar), "r"(parity) : "memory");
+      "DONE_%=:\n\t}\n" :: "r"(mbar), "r"(parity), "r"(20000u) : "memory");  // suspend-time hint (ns): sleep in hardware instead of spinning on issue slots
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
