@@ -8,12 +8,12 @@ sm_100a CUDA kernels (csrc/) behind the C ABI of include/diffrax_b200.h.
 from . import fields, random
 from ._api import (RESULTS, Bosh3, BrownianIncrement, ClipStepSizeController, ConstantStepSize, ControlTerm, DenseInterpolation,
                    Dopri5, Dopri8, Euler, HalfSolver, Heun, Midpoint, MultiTerm, ODETerm, PIDController, Ralston, SaveAt,
-                   ShARK, Solution, SpaceTimeLevyArea, Tsit5, VirtualBrownianTree, diffeqsolve, is_successful, prepare, EnsembleSolve)
+                   ShARK, Solution, SpaceTimeLevyArea, SubSaveAt, Tsit5, VirtualBrownianTree, diffeqsolve, is_successful, prepare, EnsembleSolve)
 
 __all__ = [
     "RESULTS", "Bosh3", "BrownianIncrement", "ClipStepSizeController", "ConstantStepSize", "ControlTerm", "DenseInterpolation", "Dopri5",
     "Dopri8", "Euler", "HalfSolver", "Heun", "Midpoint", "MultiTerm", "ODETerm", "PIDController", "Ralston", "SaveAt", "ShARK",
-    "Solution", "SpaceTimeLevyArea", "Tsit5", "VirtualBrownianTree", "diffeqsolve", "is_successful", "prepare",
+    "Solution", "SpaceTimeLevyArea", "SubSaveAt", "Tsit5", "VirtualBrownianTree", "diffeqsolve", "is_successful", "prepare",
     "EnsembleSolve", "fields",
     "random",
 ]

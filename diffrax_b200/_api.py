@@ -250,18 +250,72 @@ def pid_controller(*args, step_ts=None, jump_ts=None, **kwargs):
 # --------------------------------------------------------------------------------------
 # SaveAt
 # --------------------------------------------------------------------------------------
-class SaveAt:
-    """_saveat.py:65-105 (single SubSaveAt, fn == save_y)."""
+def save_y(t, y, args):
+    """_saveat.py:10-11, the default `fn`."""
+    return y
 
-    def __init__(self, *, t0: bool = False, t1: bool = False, ts=None, steps: Union[bool, int] = False,
-                 dense: bool = False):
+
+class SubSaveAt:
+    """_saveat.py:14-48: what to save, and how (`fn(t, y, args)`).
+
+    `fn` is the vectorised form of the reference's: it is called once, after the solve, with `t: [N, T]` and
+    `y: [N, T, d]` (every saved slot of every trajectory) and must return `[N, T, ...]`; unfilled slots are reset to `inf`
+    afterwards (the reference's padding, _integrate.py:1296-1300).  Saving does not feed back into the stepping, so
+    applying `fn` to the saved states is value-identical to applying it at save time."""
+
+    def __init__(self, *, t0: bool = False, t1: bool = False, ts=None, steps: Union[bool, int] = False, fn=save_y):
         self.t0 = bool(t0)
         self.t1 = bool(t1)
         self.ts = None if ts is None else ts
         self.steps = int(steps)  # `steps=True` == every step (_saveat.py:26-27)
-        self.dense = bool(dense)
-        if not (self.t0 or self.t1 or self.ts is not None or self.steps or self.dense):
+        self.fn = fn
+        if not (self.t0 or self.t1 or self.ts is not None or self.steps):
             raise ValueError("Empty saveat -- nothing will be saved.")  # _saveat.py:40-48
+
+
+class SaveAt:
+    """_saveat.py:65-105.  `subs` may be a SubSaveAt or a (nested) list / tuple / dict of them; `Solution.ts` / `.ys`
+    then have the same structure.  Each SubSaveAt is served by its own launch of the same solve (the step sequence does
+    not depend on what is saved, so the values are those of a single solve)."""
+
+    def __init__(self, *, t0: bool = False, t1: bool = False, ts=None, steps: Union[bool, int] = False, fn=save_y,
+                 subs=None, dense: bool = False):
+        self.dense = bool(dense)
+        if subs is None:
+            if t0 or t1 or ts is not None or steps:
+                subs = SubSaveAt(t0=t0, t1=t1, ts=ts, steps=steps, fn=fn)
+        elif t0 or t1 or ts is not None or steps:
+            raise ValueError("Cannot pass both `subs` and any of `t0`, `t1`, `ts`, `steps` to `SaveAt`.")  # _saveat.py:84-92
+        self.subs = subs
+        if subs is None and not self.dense:
+            raise ValueError("Empty saveat -- nothing will be saved.")  # _saveat.py:40-48
+
+    # the single-SubSaveAt view the descriptor is filled from
+    @property
+    def _single(self):
+        return self.subs if isinstance(self.subs, SubSaveAt) or self.subs is None else None
+
+    t0 = property(lambda self: bool(self._single and self._single.t0))
+    t1 = property(lambda self: bool(self._single and self._single.t1))
+    ts = property(lambda self: self._single.ts if self._single else None)
+    steps = property(lambda self: self._single.steps if self._single else 0)
+    fn = property(lambda self: self._single.fn if self._single else save_y)
+
+
+def _tree_map_subs(f, subs):
+    if isinstance(subs, SubSaveAt):
+        return f(subs)
+    if isinstance(subs, dict):
+        return {k: _tree_map_subs(f, v) for k, v in subs.items()}
+    if isinstance(subs, (list, tuple)):
+        return type(subs)(_tree_map_subs(f, v) for v in subs)
+    raise TypeError("SaveAt(subs=...) must be a SubSaveAt or a list / tuple / dict of them")
+
+
+def _tree_leaves_subs(subs):
+    out = []
+    _tree_map_subs(out.append, subs)
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -420,13 +474,29 @@ class DenseInterpolation:
     def evaluate(self, t0, t1=None, left=True):
         if t1 is not None:
             return self.evaluate(t1, left=left) - self.evaluate(t0, left=left)
+        out, tq, squeeze = self._query("dfx_dense_evaluate", t0)
+        # trivial (t0 == t1) case: evaluate(t0) == y0  (_global_interpolation.py:343-355)
+        trivial = (self._count == 0)
+        if bool(trivial.any()):
+            tt = tq * float(self.direction)
+            m = trivial[:, None] & (tt == self.t0_if_trivial[:, None])
+            out = torch.where(m[:, :, None], self.y0_if_trivial[:, None, :].expand_as(out), out)
+        return out[:, 0, :] if squeeze else out
+
+    def derivative(self, t, left=True):
+        """_global_interpolation.py:357-368: d/dt of the interpolant.  Outside [t0, t1] it is NaN, except for the linear
+        interpolant (Euler, ShARK), whose jvp tangent does not involve the NaN primal: the last interval's slope."""
+        out, _, squeeze = self._query("dfx_dense_derivative", t)
+        return out[:, 0, :] if squeeze else out
+
+    def _query(self, entry, t):
         xp = self._xp
         if not xp.device_ptrs:
-            raise RuntimeError("DenseInterpolation.evaluate needs the dense buffers on a CUDA device")
+            raise RuntimeError("DenseInterpolation needs the dense buffers on a CUDA device")
         n, msp1 = self.ts.shape
         d = self.infos["y0"].shape[-1]
-        tq = torch.as_tensor(t0, dtype=self.ts.dtype, device=self.ts.device)
-        squeeze = tq.ndim == 0 or (tq.ndim == 1 and tq.shape[0] == n and False)
+        tq = torch.as_tensor(t, dtype=self.ts.dtype, device=self.ts.device)
+        squeeze = tq.ndim == 0
         if tq.ndim == 0:
             tq = tq.expand(n, 1)
         elif tq.ndim == 1:
@@ -434,19 +504,11 @@ class DenseInterpolation:
         tq = tq.contiguous()
         nq = tq.shape[1]
         out = xp.empty((n, nq, d), self.ts.dtype)
-        count = self._count
-        direction = float(self.direction)
-        _lib.check(_lib.lib().dfx_dense_evaluate(
+        _lib.check(getattr(_lib.lib(), entry)(
             xp.dtype_id(self.ts.dtype), self.solver.solver_id, n, d, msp1 - 1, xp.ptr(self.ts),
-            xp.ptr(self.infos["y0"]), xp.ptr(self.infos["y1"]), xp.ptr(self.infos.get("k")), xp.ptr(count),
-            direction, xp.ptr(tq), nq, xp.ptr(out), xp.stream()))
-        # trivial (t0 == t1) case: evaluate(t0) == y0  (_global_interpolation.py:343-355)
-        trivial = (self._count == 0)
-        if bool(trivial.any()):
-            tt = tq * direction
-            m = trivial[:, None] & (tt == self.t0_if_trivial[:, None])
-            out = torch.where(m[:, :, None], self.y0_if_trivial[:, None, :].expand_as(out), out)
-        return out[:, 0, :] if squeeze else out
+            xp.ptr(self.infos["y0"]), xp.ptr(self.infos["y1"]), xp.ptr(self.infos.get("k")), xp.ptr(self._count),
+            float(self.direction), xp.ptr(tq), nq, xp.ptr(out), xp.stream()))
+        return out, tq, squeeze
 
 
 # --------------------------------------------------------------------------------------
@@ -492,7 +554,32 @@ class EnsembleSolve:
             if bool(bad.any()):
                 code = int(sol.result[bad][0])
                 raise RuntimeError(RESULTS._messages.get(code, f"solver failed with code {code}"))  # _integrate.py:1541-1542
+        fn = getattr(self, "_fn", save_y)
+        if fn is not save_y:  # SubSaveAt.fn, applied to every saved slot at once (see SubSaveAt)
+            ts, ys = sol.ts, sol.ys
+            out = fn(ts, ys, None)
+            valid = (ts == ts) & (abs(ts) != math.inf)
+            while valid.ndim < out.ndim:
+                valid = valid[..., None]
+            inf = math.inf
+            out = torch.where(valid, out, torch.full_like(out, inf)) if isinstance(out, torch.Tensor) else np.where(valid, out, inf)
+            sol = dataclasses.replace(sol, ys=out)
         return sol
+
+
+class _MultiSolve:
+    """SaveAt(subs=<tree of SubSaveAt>): one prepared solve per leaf; `ts` / `ys` come back in the structure of `subs`."""
+
+    def __init__(self, subs, solves):
+        self.subs, self.solves = subs, solves
+
+    def __call__(self, throw: bool = True) -> Solution:
+        sols = [sv(throw=throw) for sv in self.solves]
+        it = iter(sols)
+        ts = _tree_map_subs(lambda _: next(it).ts, self.subs)
+        it = iter(sols)
+        ys = _tree_map_subs(lambda _: next(it).ys, self.subs)
+        return dataclasses.replace(sols[0], ts=ts, ys=ys)
 
 
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
@@ -519,6 +606,14 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     if args is not None:
         raise ValueError("args must be None: functor parameters are bound when the functor is created")
     saveat = SaveAt(t1=True) if saveat is None else saveat
+    if saveat.subs is not None and not isinstance(saveat.subs, SubSaveAt):
+        leaves = _tree_leaves_subs(saveat.subs)
+        if not leaves:
+            raise ValueError("Empty saveat -- nothing will be saved.")
+        solves = [prepare(terms, solver, t0, t1, dt0, y0, args, saveat=SaveAt(subs=leaf, dense=saveat.dense and i == 0),
+                          stepsize_controller=stepsize_controller, max_steps=max_steps, device=device,
+                          hairer_initial_step=hairer_initial_step) for i, leaf in enumerate(leaves)]
+        return _MultiSolve(saveat.subs, solves)
     ctrl = ConstantStepSize() if stepsize_controller is None else stepsize_controller
     field, bm = _parse_terms(terms)
     if max_steps is None:
@@ -692,6 +787,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     call._xp = xp
     call._device = y0a.device if is_torch else None
     call._host_device = device
+    call._fn = saveat.fn
     call._solution = Solution(t0=t0, t1=t1, ts=ts_out, ys=ys_out, interpolation=interpolation, stats=stats_d,
                               result=result, y_final=y_final, t_final=t_final)
     return call

@@ -115,8 +115,8 @@ __global__ void vbt_kernel(long long n, const uint32_t *keys, VbtParams vp, cons
   if (H) H[i] = h;
 }
 
-// DenseInterpolation.evaluate (_global_interpolation.py:335-355), one thread per (trajectory, query).
-template <class R, class Solver, int D>
+// DenseInterpolation.evaluate / .derivative (_global_interpolation.py:335-368), one thread per (trajectory, query).
+template <class R, class Solver, int D, bool DERIV>
 __global__ void dense_eval_kernel(long long n_traj, int max_steps, const R *dts, const R *dy0, const R *dy1,
                                   const R *dk, const int *dcount, R direction, const R *tq, int nq, R *out) {
   constexpr int S = Solver::S;
@@ -143,9 +143,15 @@ __global__ void dense_eval_kernel(long long n_traj, int max_steps, const R *dts,
   for (int j = 0; j < S; ++j)
 #pragma unroll
     for (int c = 0; c < D; ++c) k[j][c] = (Solver::kInterp != kInterpLinear && dk) ? dk[(row * S + j) * D + c] : R(0);
-  interp_eval<Solver::kInterp, R, S, D>(ts[index], ts[index + 1], y0, y1, k, t, o);
+  if constexpr (DERIV) {
+    interp_deriv<Solver::kInterp, R, S, D>(ts[index], ts[index + 1], y0, y1, k, t, o);
 #pragma unroll
-  for (int c = 0; c < D; ++c) out[gid * D + c] = o[c];
+    for (int c = 0; c < D; ++c) out[gid * D + c] = direction * o[c];  // 366: direction * derivative
+  } else {
+    interp_eval<Solver::kInterp, R, S, D>(ts[index], ts[index + 1], y0, y1, k, t, o);
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[gid * D + c] = o[c];
+  }
 }
 
 // Pipe-peak microbenchmarks: 8 independent FMA chains per thread, enough warps to fill every SM.
@@ -178,15 +184,19 @@ __global__ void int_peak_kernel(uint32_t *out, int iters) {
 }
 
 template <class R, class Solver>
-static int dense_eval_dispatch_dim(int dim, long long n, int ms, const void *dts, const void *dy0, const void *dy1,
+static int dense_eval_dispatch_dim(bool deriv, int dim, long long n, int ms, const void *dts, const void *dy0, const void *dy1,
                                    const void *dk, const int *dc, double direction, const void *tq, int nq, void *out,
                                    cudaStream_t st) {
   const long long total = n * nq;
   const unsigned blocks = (unsigned)((total + 127) / 128);
 #define DFX_DE(DD)                                                                                              \
   case DD:                                                                                                      \
-    dense_eval_kernel<R, Solver, DD><<<blocks, 128, 0, st>>>(n, ms, (const R *)dts, (const R *)dy0, (const R *)dy1, \
-                                                             (const R *)dk, dc, (R)direction, (const R *)tq, nq, (R *)out); \
+    if (deriv)                                                                                                  \
+      dense_eval_kernel<R, Solver, DD, true><<<blocks, 128, 0, st>>>(n, ms, (const R *)dts, (const R *)dy0, (const R *)dy1, \
+                                                                     (const R *)dk, dc, (R)direction, (const R *)tq, nq, (R *)out); \
+    else                                                                                                        \
+      dense_eval_kernel<R, Solver, DD, false><<<blocks, 128, 0, st>>>(n, ms, (const R *)dts, (const R *)dy0, (const R *)dy1, \
+                                                                      (const R *)dk, dc, (R)direction, (const R *)tq, nq, (R *)out); \
     break;
   switch (dim) {
     DFX_DE(1) DFX_DE(2) DFX_DE(3) DFX_DE(4)
@@ -201,11 +211,11 @@ static int dense_eval_dispatch_dim(int dim, long long n, int ms, const void *dts
 }
 
 template <class R>
-static int dense_eval_dispatch(int solver_id, int dim, long long n, int ms, const void *dts, const void *dy0,
+static int dense_eval_dispatch(bool deriv, int solver_id, int dim, long long n, int ms, const void *dts, const void *dy0,
                                const void *dy1, const void *dk, const int *dc, double direction, const void *tq, int nq,
                                void *out, cudaStream_t st) {
   switch (solver_id & ~DFX_HALF_SOLVER) {  // HalfSolver(inner) records the inner solver's dense_info
-#define DFX_DS(ID, T) case ID: return dense_eval_dispatch_dim<R, T>(dim, n, ms, dts, dy0, dy1, dk, dc, direction, tq, nq, out, st);
+#define DFX_DS(ID, T) case ID: return dense_eval_dispatch_dim<R, T>(deriv, dim, n, ms, dts, dy0, dy1, dk, dc, direction, tq, nq, out, st);
     DFX_DS(DFX_TSIT5, Tsit5) DFX_DS(DFX_DOPRI5, Dopri5) DFX_DS(DFX_DOPRI8, Dopri8) DFX_DS(DFX_HEUN, Heun)
     DFX_DS(DFX_BOSH3, Bosh3) DFX_DS(DFX_MIDPOINT, Midpoint) DFX_DS(DFX_RALSTON, Ralston)
     DFX_DS(DFX_EULER, EulerSolver) DFX_DS(DFX_SHARK, SharkSolver)
@@ -487,15 +497,27 @@ int dfx_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, con
   return 0;
 }
 
+static int dense_eval_entry(bool deriv, int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
+                            const void *dense_y0, const void *dense_y1, const void *dense_k, const int32_t *dense_count,
+                            double direction, const void *tq, int nq, void *out, void *stream) {
+  if (n_traj <= 0 || nq <= 0) return 0;
+  if (dtype == DFX_F64)
+    return dense_eval_dispatch<double>(deriv, solver_id, dim, n_traj, max_steps, dense_ts, dense_y0, dense_y1, dense_k,
+                                       dense_count, direction, tq, nq, out, (cudaStream_t)stream);
+  return dense_eval_dispatch<float>(deriv, solver_id, dim, n_traj, max_steps, dense_ts, dense_y0, dense_y1, dense_k,
+                                    dense_count, direction, tq, nq, out, (cudaStream_t)stream);
+}
 int dfx_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
                        const void *dense_y0, const void *dense_y1, const void *dense_k, const int32_t *dense_count,
                        double direction, const void *tq, int nq, void *out, void *stream) {
-  if (n_traj <= 0 || nq <= 0) return 0;
-  if (dtype == DFX_F64)
-    return dense_eval_dispatch<double>(solver_id, dim, n_traj, max_steps, dense_ts, dense_y0, dense_y1, dense_k,
-                                       dense_count, direction, tq, nq, out, (cudaStream_t)stream);
-  return dense_eval_dispatch<float>(solver_id, dim, n_traj, max_steps, dense_ts, dense_y0, dense_y1, dense_k,
-                                    dense_count, direction, tq, nq, out, (cudaStream_t)stream);
+  return dense_eval_entry(false, dtype, solver_id, n_traj, dim, max_steps, dense_ts, dense_y0, dense_y1, dense_k, dense_count,
+                          direction, tq, nq, out, stream);
+}
+int dfx_dense_derivative(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
+                         const void *dense_y0, const void *dense_y1, const void *dense_k, const int32_t *dense_count,
+                         double direction, const void *tq, int nq, void *out, void *stream) {
+  return dense_eval_entry(true, dtype, solver_id, n_traj, dim, max_steps, dense_ts, dense_y0, dense_y1, dense_k, dense_count,
+                          direction, tq, nq, out, stream);
 }
 
 double dfx_measure_fma_peak(int dtype, int device) {

@@ -23,11 +23,24 @@ template <> struct TabConst<float> {
   static __device__ __forceinline__ float d8(int i, int m) { return kDopri8Eval_f32[i * 6 + m]; }
 };
 
-// Evaluate the interpolant of kind KIND on [t0, t1] at time t.  k is [S][D] (ignored for linear).
-template <int KIND, class R, int S, int D>
-__device__ __forceinline__ void interp_eval(R t0, R t1, const R (&y0)[D], const R (&y1)[D], const R (&k)[S][D],
-                                            R t, R (&out)[D]) {
-  const R th = linear_rescale(t0, t, t1);
+// Forward-mode dual number: the interpolants below are written once, generically in the type of theta; instantiated with
+// Dual<R> they return the derivative the reference obtains from jax.jvp of `evaluate` (AbstractPath.derivative, _path.py).
+template <class R> struct Dual { R v, d; };
+template <class R> __device__ __forceinline__ Dual<R> operator+(Dual<R> a, Dual<R> b) { return {a.v + b.v, a.d + b.d}; }
+template <class R> __device__ __forceinline__ Dual<R> operator+(Dual<R> a, R b) { return {a.v + b, a.d}; }
+template <class R> __device__ __forceinline__ Dual<R> operator+(R a, Dual<R> b) { return {a + b.v, b.d}; }
+template <class R> __device__ __forceinline__ Dual<R> operator-(Dual<R> a, Dual<R> b) { return {a.v - b.v, a.d - b.d}; }
+template <class R> __device__ __forceinline__ Dual<R> operator-(Dual<R> a, R b) { return {a.v - b, a.d}; }
+template <class R> __device__ __forceinline__ Dual<R> operator*(Dual<R> a, Dual<R> b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+template <class R> __device__ __forceinline__ Dual<R> operator*(Dual<R> a, R b) { return {a.v * b, a.d * b}; }
+template <class R> __device__ __forceinline__ Dual<R> operator*(R a, Dual<R> b) { return {a * b.v, a * b.d}; }
+template <class R> __device__ __forceinline__ R zero_like(R) { return R(0); }
+template <class R> __device__ __forceinline__ Dual<R> zero_like(Dual<R>) { return {R(0), R(0)}; }
+template <class R> __device__ __forceinline__ Dual<R> &operator+=(Dual<R> &a, Dual<R> b) { a = a + b; return a; }
+
+// The interpolant of kind KIND at theta = th (T = R: value; T = Dual<R>: value and d/dtheta).  k is [S][D] (ignored for linear).
+template <int KIND, class R, int S, int D, class T>
+__device__ __forceinline__ void interp_core(const T th, const R (&y0)[D], const R (&y1)[D], const R (&k)[S][D], T (&out)[D]) {
   if constexpr (KIND == kInterpLinear) {
 #pragma unroll
     for (int c = 0; c < D; ++c) out[c] = y0[c] + th * (y1[c] - y0[c]);
@@ -37,7 +50,7 @@ __device__ __forceinline__ void interp_eval(R t0, R t1, const R (&y0)[D], const 
       const R k0 = k[0][c], k1 = k[S - 1][c];
       const R a = k0 + k1 + R(2) * y0[c] - R(2) * y1[c];
       const R b = R(-2) * k0 - k1 - R(3) * y0[c] + R(3) * y1[c];
-      R p = R(0) * th + a;   // jnp.polyval: Horner from zero
+      T p = R(0) * th + a;   // jnp.polyval: Horner from zero
       p = p * th + b;
       p = p * th + k0;
       p = p * th + y0[c];
@@ -55,7 +68,7 @@ __device__ __forceinline__ void interp_eval(R t0, R t1, const R (&y0)[D], const 
       const R a = R(2) * (f1 - f0) - R(8) * (y1[c] + y0[c]) + R(16) * ymid;
       const R b = R(5) * f0 - R(3) * f1 + R(18) * y0[c] + R(14) * y1[c] - R(32) * ymid;
       const R cc = f1 - R(4) * f0 - R(11) * y0[c] - R(5) * y1[c] + R(16) * ymid;
-      R p = R(0) * th + a;
+      T p = R(0) * th + a;
       p = p * th + b;
       p = p * th + cc;
       p = p * th + f0;
@@ -63,8 +76,8 @@ __device__ __forceinline__ void interp_eval(R t0, R t1, const R (&y0)[D], const 
       out[c] = p;
     }
   } else if constexpr (KIND == kInterpTsit5) {
-    const R x = th, x2 = x * x;
-    R b[7];
+    const T x = th, x2 = x * x;
+    T b[7];
     b[0] = R(-1.0530884977290216) * x * (x - R(1.3299890189751412)) * (x2 - R(1.4364028541716351) * x + R(0.7139816917074209));
     b[1] = R(0.1017) * x2 * (x2 - R(2.1966568338249754) * x + R(1.2949852507374631));
     b[2] = R(2.490627285651252793) * x2 * (x2 - R(2.38535645472061657) * x + R(1.57803468208092486));
@@ -74,33 +87,52 @@ __device__ __forceinline__ void interp_eval(R t0, R t1, const R (&y0)[D], const 
     b[6] = R(2.5) * (x - R(1)) * (x - R(0.6)) * x2;
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-      R acc = R(0);
+      T acc = zero_like(th);
 #pragma unroll
       for (int j = 0; j < 7; ++j) acc += b[j] * k[j][c];
       out[c] = y0[c] + acc;
     }
   } else {  // kInterpDopri8
-    R w[14];
+    T w[14];
 #pragma unroll
     for (int j = 0; j < 14; ++j) {
       if (dopri8_eval_row_nonzero(j)) {
-        R p = R(0) * th + TabConst<R>::d8(j, 0);
+        T p = R(0) * th + TabConst<R>::d8(j, 0);
 #pragma unroll
         for (int m = 1; m < 6; ++m) p = p * th + TabConst<R>::d8(j, m);
         w[j] = p * th;
       } else {
-        w[j] = R(0);
+        w[j] = zero_like(th);
       }
     }
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-      R acc = R(0);
+      T acc = zero_like(th);
 #pragma unroll
       for (int j = 0; j < 14; ++j)
         if (dopri8_eval_row_nonzero(j)) acc += w[j] * k[j][c];
       out[c] = y0[c] + acc;
     }
   }
+}
+
+// Evaluate the interpolant of kind KIND on [t0, t1] at time t.
+template <int KIND, class R, int S, int D>
+__device__ __forceinline__ void interp_eval(R t0, R t1, const R (&y0)[D], const R (&y1)[D], const R (&k)[S][D],
+                                            R t, R (&out)[D]) {
+  interp_core<KIND, R, S, D, R>(linear_rescale(t0, t, t1), y0, y1, k, out);
+}
+
+// d/dt of the interpolant at time t: the tangent of `evaluate` w.r.t. t (AbstractPath.derivative via jax.jvp), including
+// linear_rescale's own tangent where(t0 == t1, 0, 1 / (t1 - t0)) (_misc.py:71-82).
+template <int KIND, class R, int S, int D>
+__device__ __forceinline__ void interp_deriv(R t0, R t1, const R (&y0)[D], const R (&y1)[D], const R (&k)[S][D],
+                                             R t, R (&out)[D]) {
+  const Dual<R> th{linear_rescale(t0, t, t1), (t0 == t1) ? R(0) : R(1) / (t1 - t0)};
+  Dual<R> o[D];
+  interp_core<KIND, R, S, D, Dual<R>>(th, y0, y1, k, o);
+#pragma unroll
+  for (int c = 0; c < D; ++c) out[c] = o[c].d;
 }
 
 }  // namespace dfx

@@ -176,6 +176,12 @@ int dfx_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int ma
                        const void *dense_ts, const void *dense_y0, const void *dense_y1,
                        const void *dense_k, const int32_t *dense_count, double direction,
                        const void *tq, int nq, void *out, void *cuda_stream);
+/* replaces DenseInterpolation.derivative vmapped (_global_interpolation.py:357-368; the local interpolants' derivative is
+ * the jax.jvp tangent of their evaluate, _path.py): same arguments, out[i, q, :] = d/dt of the interpolant at tq[i, q]. */
+int dfx_dense_derivative(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps,
+                         const void *dense_ts, const void *dense_y0, const void *dense_y1,
+                         const void *dense_k, const int32_t *dense_count, double direction,
+                         const void *tq, int nq, void *out, void *cuda_stream);
 
 /* measured FMA-pipe peaks for the roofline denominators (dependent-free FMA chains);
  * returns TFLOP/s (2 flop per FMA) or a negative dfx_error. */

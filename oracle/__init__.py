@@ -107,6 +107,8 @@ def lib():
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
                                          C.c_void_p]
         L.orc_dense_evaluate.restype = C.c_int
+        L.orc_dense_derivative.argtypes = L.orc_dense_evaluate.argtypes
+        L.orc_dense_derivative.restype = C.c_int
         _lib = L
     return _lib
 
@@ -264,7 +266,7 @@ def vbt_evaluate(keys, ta, tb, *, bm_t0=0.0, bm_t1=1.0, tol=1e-3, levy_area="bi"
     return W, H
 
 
-def dense_evaluate(solver, dense, tq, direction=1.0):
+def dense_evaluate(solver, dense, tq, direction=1.0, derivative=False):
     dts = dense["ts"]
     dt = dts.dtype
     n, msp1 = dts.shape
@@ -272,7 +274,8 @@ def dense_evaluate(solver, dense, tq, direction=1.0):
     tq = np.ascontiguousarray(tq, dt).reshape(n, -1)
     nq = tq.shape[1]
     out = np.empty((n, nq, d), dt)
-    lib().orc_dense_evaluate(F64 if dt == np.float64 else F32, solver_id(solver), n, d, msp1 - 1, _ptr(dts),
+    fn = lib().orc_dense_derivative if derivative else lib().orc_dense_evaluate
+    fn(F64 if dt == np.float64 else F32, solver_id(solver), n, d, msp1 - 1, _ptr(dts),
                              _ptr(dense["y0"]), _ptr(dense["y1"]), _ptr(dense["k"]), _ptr(dense["count"]),
                              float(direction), _ptr(tq), nq, _ptr(out))
     return out

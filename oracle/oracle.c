@@ -263,7 +263,7 @@ int orc_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, con
   return 0;
 }
 
-int orc_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
+static int dense_eval_entry(int deriv, int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
                        const void *dense_y0, const void *dense_y1, const void *dense_k, const int32_t *dense_count,
                        double direction, const void *tq, int nq, void *out) {
   solver_id &= ~ORC_HALF;
@@ -275,15 +275,25 @@ int orc_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int ma
                            (const double *)dense_y0 + (size_t)i * max_steps * dim,
                            (const double *)dense_y1 + (size_t)i * max_steps * dim,
                            dense_k ? (const double *)dense_k + (size_t)i * max_steps * s * dim : NULL, dense_count[i],
-                           direction, ((const double *)tq)[(size_t)i * nq + q], (double *)out + ((size_t)i * nq + q) * dim);
+                           direction, ((const double *)tq)[(size_t)i * nq + q], deriv, (double *)out + ((size_t)i * nq + q) * dim);
       } else {
         dense_eval_one_f32(solver_id, dim, max_steps, (const float *)dense_ts + (size_t)i * (max_steps + 1),
                            (const float *)dense_y0 + (size_t)i * max_steps * dim,
                            (const float *)dense_y1 + (size_t)i * max_steps * dim,
                            dense_k ? (const float *)dense_k + (size_t)i * max_steps * s * dim : NULL, dense_count[i],
-                           (float)direction, ((const float *)tq)[(size_t)i * nq + q], (float *)out + ((size_t)i * nq + q) * dim);
+                           (float)direction, ((const float *)tq)[(size_t)i * nq + q], deriv, (float *)out + ((size_t)i * nq + q) * dim);
       }
     }
   }
   return 0;
+}
+int orc_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
+                       const void *dense_y0, const void *dense_y1, const void *dense_k, const int32_t *dense_count,
+                       double direction, const void *tq, int nq, void *out) {
+  return dense_eval_entry(0, dtype, solver_id, n_traj, dim, max_steps, dense_ts, dense_y0, dense_y1, dense_k, dense_count, direction, tq, nq, out);
+}
+int orc_dense_derivative(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, const void *dense_ts,
+                         const void *dense_y0, const void *dense_y1, const void *dense_k, const int32_t *dense_count,
+                         double direction, const void *tq, int nq, void *out) {
+  return dense_eval_entry(1, dtype, solver_id, n_traj, dim, max_steps, dense_ts, dense_y0, dense_y1, dense_k, dense_count, direction, tq, nq, out);
 }

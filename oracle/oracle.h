@@ -122,6 +122,11 @@ int orc_dense_evaluate(int dtype, int solver_id, int64_t n_traj, int dim, int ma
                        const void *dense_ts, const void *dense_y0, const void *dense_y1,
                        const void *dense_k, const int32_t *dense_count, double direction,
                        const void *tq, int nq, void *out);
+/* DenseInterpolation.derivative, _global_interpolation.py:357-368 */
+int orc_dense_derivative(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps,
+                       const void *dense_ts, const void *dense_y0, const void *dense_y1,
+                       const void *dense_k, const int32_t *dense_count, double direction,
+                       const void *tq, int nq, void *out);
 
 #ifdef __cplusplus
 }

@@ -265,6 +265,17 @@ def test_every_solver_step_indexed_outputs(dev, solver):
     oev = oracle.dense_evaluate(solver, o["dense"], np.tile(q, (n, 1)))
     assert relerr(ev[same], oev[same]) < 1e-9
     assert np.array_equal(ev[:, 0], kw["y0"])                        # theta == 0 reproduces y0 exactly (test_global_interpolation.py:346)
+    # DenseInterpolation.derivative: dual numbers through the evaluate code (CUDA) vs the hand-written analytic derivative
+    # (oracle), both on the GPU's own dense buffers so that the comparison is independent of the step sequence
+    gd = dict(ts=to_np(di.ts), y0=to_np(di.infos["y0"]), y1=to_np(di.infos["y1"]), k=to_np(di.infos["k"]), count=to_np(di._count))
+    qd = np.linspace(-0.1, 3.1, 33)
+    dg = to_np(di.derivative(torch.tensor(qd, device=dev)))
+    do = oracle.dense_evaluate(solver, gd, np.tile(qd, (n, 1)), derivative=True)
+    assert np.all(np.isnan(dg[:, 0])) and np.all(np.isnan(dg[:, -1]))          # NaN outside [t0, t1]
+    assert relerr(dg, do) < 1e-7    # 1/(t1 - t0) amplifies rounding: the clipped last step to t1 can be ~1e-7 wide
+    fd = (to_np(di.evaluate(torch.tensor(qd[1:-1] + 1e-6, device=dev))) - to_np(di.evaluate(torch.tensor(qd[1:-1] - 1e-6, device=dev)))) / 2e-6
+    err = np.abs(fd - dg[:, 1:-1])                                              # and it IS the slope of evaluate
+    assert (err[np.isfinite(err)] < 1e-6).mean() > 0.98                         # (a difference may straddle a knot, where low-order interpolants kink)
     # self-consistency: the saved step values are the interpolant's right end points
     nacc = st[:, 1]
     tsg, ysg = to_np(sol.ts), to_np(sol.ys)
@@ -449,6 +460,33 @@ def test_half_solver_euler_sde_is_refused(dev):
     with pytest.raises(ValueError, match="Euler"):
         dfx.diffeqsolve(terms, dfx.HalfSolver(dfx.Euler()), 0.0, 1.0, 0.1, torch.ones(4, 1, device=dev, dtype=torch.float64),
                         stepsize_controller=dfx.PIDController(rtol=1e-3, atol=1e-3))
+
+
+def test_saveat_fn_and_subs(dev):
+    """SaveAt(fn=...) and SaveAt(subs=[SubSaveAt, ...]) (_saveat.py:14-105, test_saveat_solution.py:110-195): every
+    sub-saveat reports what a solve with that saveat alone reports; `fn` maps the saved states; padding stays inf."""
+    rng = np.random.default_rng(3)
+    y0 = torch.tensor(rng.uniform(0.5, 2.0, (300, 2)), device=dev)
+    term, ctrl = dfx.ODETerm(dfx.fields.LotkaVolterra()), dfx.PIDController(rtol=1e-6, atol=1e-8)
+    ts = np.linspace(0.0, 4.0, 9)
+    kw = dict(stepsize_controller=ctrl, max_steps=1024)
+    subs = {"end": dfx.SubSaveAt(t1=True), "grid": dfx.SubSaveAt(t0=True, ts=ts[1:], fn=lambda t, y, args: (y ** 2).sum(-1)),
+            "steps": [dfx.SubSaveAt(steps=True, fn=lambda t, y, args: y[..., :1])]}
+    sol = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 4.0, None, y0, saveat=dfx.SaveAt(subs=subs, dense=True), **kw)
+    ref_end = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 4.0, None, y0, saveat=dfx.SaveAt(t1=True), **kw)
+    ref_grid = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 4.0, None, y0, saveat=dfx.SaveAt(t0=True, ts=ts[1:]), **kw)
+    ref_steps = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 4.0, None, y0, saveat=dfx.SaveAt(steps=True), **kw)
+    assert set(sol.ys) == {"end", "grid", "steps"} and isinstance(sol.ys["steps"], list)
+    assert torch.equal(sol.ys["end"], ref_end.ys) and torch.equal(sol.ts["end"], ref_end.ts)
+    assert torch.equal(sol.ts["grid"], ref_grid.ts) and sol.ys["grid"].shape == (300, 9)
+    assert torch.equal(sol.ys["grid"], (ref_grid.ys ** 2).sum(-1))
+    got, want = sol.ys["steps"][0], ref_steps.ys[..., :1]
+    assert got.shape == (300, 1024, 1) and torch.equal(got, want)          # inf padding preserved through fn
+    assert bool(torch.isinf(got[:, -1]).all())
+    assert torch.equal(sol.stats["num_steps"], ref_end.stats["num_steps"])
+    assert sol.interpolation is not None and torch.allclose(sol.evaluate(4.0), ref_end.ys[:, 0], rtol=1e-12, atol=0)
+    with pytest.raises(ValueError):
+        dfx.SaveAt(t1=True, subs=dfx.SubSaveAt(t0=True))
 
 
 def test_hairer_initial_step_flag(dev):

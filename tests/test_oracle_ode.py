@@ -263,3 +263,32 @@ def test_half_solver_semantics():
     r5 = oracle.solve("decay", np.array([[1.0]]), 0.0, 2.0, 0.1, solver="half:tsit5", params=[1.0], controller="pid",
                       rtol=1e-9, atol=1e-12)
     assert abs(r5["ys"][0, -1, 0] - math.exp(-2.0)) < 1e-10
+
+
+def test_dense_derivative_is_slope_of_evaluate():
+    """DenseInterpolation.derivative (_global_interpolation.py:357-368): every local interpolant's analytic derivative
+    against central differences of evaluate; NaN out of bounds; direction factor on a reversed solve."""
+    rng = np.random.default_rng(0)
+    y0 = rng.uniform(-1, 1, (5, 2))
+    tq = np.tile(np.array([0.31, 0.77, 1.53]), (5, 1))
+    h = 1e-6
+    for solver in ("tsit5", "dopri5", "dopri8", "heun", "bosh3", "midpoint", "euler"):
+        kw = dict(solver=solver, params=[1.0, 0.7, 2.0], save_dense=True, max_steps=4096)
+        kw.update(dict(controller="constant") if solver == "euler" else dict(rtol=1e-5, atol=1e-7))
+        r = oracle.solve("forced_osc", y0, 0.0, 2.0, 0.0437, **kw)
+        assert np.all(r["result"] == 0)
+        d = oracle.dense_evaluate(solver, r["dense"], tq, derivative=True)
+        fd = (oracle.dense_evaluate(solver, r["dense"], tq + h) - oracle.dense_evaluate(solver, r["dense"], tq - h)) / (2 * h)
+        assert np.abs(d - fd).max() < 5e-8, solver
+        oob = oracle.dense_evaluate(solver, r["dense"], np.full((5, 1), 2.5), derivative=True)
+        if solver == "euler":
+            # linear interpolant: the jvp tangent (y1 - y0) / (t1 - t0) does not involve the (NaN) primal, so out of
+            # bounds the reference returns the slope of the interval NaN indexes to - the last one - not NaN
+            last = oracle.dense_evaluate(solver, r["dense"], np.full((5, 1), 1.999), derivative=True)
+            assert np.array_equal(oob, last)
+        else:
+            assert np.all(np.isnan(oob))
+    rr = oracle.solve("forced_osc", y0, 2.0, 0.0, -0.05, solver="tsit5", params=[1.0, 0.7, 2.0], save_dense=True, rtol=1e-8, atol=1e-10)
+    d = oracle.dense_evaluate("tsit5", rr["dense"], tq, direction=-1.0, derivative=True)
+    fd = (oracle.dense_evaluate("tsit5", rr["dense"], tq + h, direction=-1.0) - oracle.dense_evaluate("tsit5", rr["dense"], tq - h, direction=-1.0)) / (2 * h)
+    assert np.abs(d - fd).max() < 5e-8
