@@ -6,12 +6,12 @@ VirtualBrownianTree-driven Heun / ShARK / Euler SDE solves.  All numerics run in
 sm_100a CUDA kernels (csrc/) behind the C ABI of include/diffrax_b200.h.
 """
 from . import fields, random
-from ._api import (RESULTS, Bosh3, BrownianIncrement, ClipStepSizeController, ConstantStepSize, ControlTerm, DenseInterpolation,
+from ._api import (RESULTS, AffineEvent, Event, Newton, SteadyStateEvent, is_event, is_okay, steady_state_event, Bosh3, BrownianIncrement, ClipStepSizeController, ConstantStepSize, ControlTerm, DenseInterpolation,
                    Dopri5, Dopri8, Euler, HalfSolver, Heun, Midpoint, MultiTerm, ODETerm, PIDController, Ralston, SaveAt,
                    ShARK, Solution, SpaceTimeLevyArea, SubSaveAt, Tsit5, VirtualBrownianTree, diffeqsolve, is_successful, prepare, EnsembleSolve)
 
 __all__ = [
-    "RESULTS", "Bosh3", "BrownianIncrement", "ClipStepSizeController", "ConstantStepSize", "ControlTerm", "DenseInterpolation", "Dopri5",
+    "RESULTS", "AffineEvent", "Event", "Newton", "SteadyStateEvent", "is_event", "is_okay", "steady_state_event", "Bosh3", "BrownianIncrement", "ClipStepSizeController", "ConstantStepSize", "ControlTerm", "DenseInterpolation", "Dopri5",
     "Dopri8", "Euler", "HalfSolver", "Heun", "Midpoint", "MultiTerm", "ODETerm", "PIDController", "Ralston", "SaveAt", "ShARK",
     "Solution", "SpaceTimeLevyArea", "SubSaveAt", "Tsit5", "VirtualBrownianTree", "diffeqsolve", "is_successful", "prepare",
     "EnsembleSolve", "fields",

@@ -48,15 +48,27 @@ class RESULTS:
     successful = 0
     max_steps_reached = 1
     dt_min_reached = 2
+    event_occurred = 3
+    event_root_find_failed = 4   # stands in for the promoted optimistix failure codes (_integrate.py:757-761)
     _messages = {
         0: "",
         1: "The maximum number of solver steps was reached. Try increasing `max_steps`.",
         2: "The minimum step size was reached in the differential equation solver.",
+        3: "Terminating differential equation solve because an event occurred.",
+        4: "The root finder locating the event time did not converge.",
     }
 
 
 def is_successful(result):
     return result == RESULTS.successful
+
+
+def is_event(result):
+    return result == RESULTS.event_occurred   # _solution.py:61-62
+
+
+def is_okay(result):
+    return is_successful(result) | is_event(result)   # _solution.py:52-54
 
 
 @dataclasses.dataclass
@@ -250,6 +262,78 @@ def pid_controller(*args, step_ts=None, jump_ts=None, **kwargs):
 # --------------------------------------------------------------------------------------
 # SaveAt
 # --------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------
+# events
+# --------------------------------------------------------------------------------------
+class AffineEvent:
+    """Real-valued condition function  c(t, y) = w . y + wt * t + b  (a registered device functor standing in for the
+    reference's arbitrary `cond_fn(t, y, args, **kwargs)`): the solve terminates on the step where c changes sign.
+    `t` is the solver's own time (t * direction for a backwards solve), as in the reference's call (_integrate.py:553-567).
+    The bouncing ball of _event.py:74-110 is `AffineEvent([1.0, 0.0])`."""
+    kind = _lib.EVENT_AFFINE
+
+    def __init__(self, w, b: float = 0.0, wt: float = 0.0):
+        self.w = [float(x) for x in np.atleast_1d(np.asarray(w, np.float64))]
+        self.b, self.wt = float(b), float(wt)
+
+    def params(self, d, ctrl):
+        if len(self.w) != d:
+            raise ValueError(f"AffineEvent has {len(self.w)} weights for a state of dimension {d}")
+        return self.w + [self.b, self.wt]
+
+
+class SteadyStateEvent:
+    """_event.py:120-170 `steady_state_event(rtol, atol)`: boolean condition  rms(f(t, y)) < atol + rtol * rms(y);
+    tolerances default to the adaptive step size controller's."""
+    kind = _lib.EVENT_STEADY_STATE
+
+    def __init__(self, rtol=None, atol=None):
+        self.rtol, self.atol = rtol, atol
+
+    def params(self, d, ctrl):
+        msg = ("The `rtol`, `atol`, and `norm` for `steady_state_event` default to the values used with an adaptive step "
+               "size controller (such as `diffrax.PIDController`). Either use an adaptive step size controller, or specify "
+               "these tolerances manually.")
+        inner = ctrl.controller if isinstance(ctrl, ClipStepSizeController) else ctrl
+        out = []
+        for v, name in ((self.rtol, "rtol"), (self.atol, "atol")):
+            if v is None:
+                if not isinstance(inner, PIDController):
+                    raise ValueError(msg)
+                v = getattr(inner, name)
+            out.append(float(v))
+        return out
+
+
+def steady_state_event(rtol=None, atol=None, norm=None):
+    if norm is not None:
+        raise NotImplementedError("steady_state_event uses optx.rms_norm (the default); custom norms are not supported")
+    return SteadyStateEvent(rtol, atol)
+
+
+@dataclasses.dataclass
+class Newton:
+    """[EXT] optimistix.Newton(rtol, atol) as `Event.root_finder`: Newton iterations on the scalar event function along the
+    triggering step's interpolant, clipped to the step (`options=dict(lower=..., upper=...)`, _integrate.py:737-747)."""
+    rtol: float
+    atol: float
+
+
+class Event:
+    """_event.py:13-118: `Event(cond_fn, root_finder=None, direction=None)` with ONE registered condition function."""
+
+    def __init__(self, cond_fn, root_finder: Optional[Newton] = None, direction: Optional[bool] = None):
+        if not isinstance(cond_fn, (AffineEvent, SteadyStateEvent)):
+            raise TypeError("Event(cond_fn): cond_fn must be an AffineEvent or steady_state_event(...) "
+                            "(condition functions are registered device functors; PyTrees of them are not supported)")
+        if direction not in (None, False, True):
+            raise ValueError("`direction` must be a `None`, `bool`, or a PyTree of `None | bool`s "
+                             "with the same structure as `cond_fn`.")  # _event.py:43-47
+        if root_finder is not None and not isinstance(root_finder, Newton):
+            raise TypeError("Event(root_finder=...) must be None or diffrax_b200.Newton(rtol, atol)")
+        self.cond_fn, self.root_finder, self.direction = cond_fn, root_finder, direction
+
+
 def save_y(t, y, args):
     """_saveat.py:10-11, the default `fn`."""
     return y
@@ -550,7 +634,7 @@ class EnsembleSolve:
             _lib.check(L.dfx_ensemble_solve_host(C.byref(self.desc), int(self._host_device)))
         sol = self._solution
         if throw:
-            bad = (sol.result != RESULTS.successful)
+            bad = ~is_okay(sol.result)  # an event is not an error (_integrate.py:1541-1542 with is_okay)
             if bool(bad.any()):
                 code = int(sol.result[bad][0])
                 raise RuntimeError(RESULTS._messages.get(code, f"solver failed with code {code}"))  # _integrate.py:1541-1542
@@ -583,7 +667,7 @@ class _MultiSolve:
 
 
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
-                stepsize_controller=None, max_steps: Optional[int] = 4096, throw: bool = True,
+                stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096, throw: bool = True,
                 device: int = 0, hairer_initial_step: bool = False) -> Solution:
     """Batched forward solve == ``jax.vmap(lambda y0: diffrax.diffeqsolve(...))(y0)``
     (_integrate.py:888-1543).
@@ -595,12 +679,12 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = N
     starting-step algorithm coded at pid.py:51-81 for ``dt0=None``; the default reproduces what ``diffeqsolve`` does
     today, a first trial step of 0.01.
     """
-    return prepare(terms, solver, t0, t1, dt0, y0, args, saveat=saveat, stepsize_controller=stepsize_controller,
+    return prepare(terms, solver, t0, t1, dt0, y0, args, saveat=saveat, stepsize_controller=stepsize_controller, event=event,
                    max_steps=max_steps, device=device, hairer_initial_step=hairer_initial_step)(throw=throw)
 
 
 def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
-            stepsize_controller=None, max_steps: Optional[int] = 4096, device: int = 0,
+            stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096, device: int = 0,
             hairer_initial_step: bool = False) -> EnsembleSolve:
     """Validate the arguments of a `diffeqsolve` call and allocate its outputs once."""
     if args is not None:
@@ -611,7 +695,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         if not leaves:
             raise ValueError("Empty saveat -- nothing will be saved.")
         solves = [prepare(terms, solver, t0, t1, dt0, y0, args, saveat=SaveAt(subs=leaf, dense=saveat.dense and i == 0),
-                          stepsize_controller=stepsize_controller, max_steps=max_steps, device=device,
+                          stepsize_controller=stepsize_controller, event=event, max_steps=max_steps, device=device,
                           hairer_initial_step=hairer_initial_step) for i, leaf in enumerate(leaves)]
         return _MultiSolve(saveat.subs, solves)
     ctrl = ConstantStepSize() if stepsize_controller is None else stepsize_controller
@@ -739,6 +823,13 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     elif isinstance(solver.solver if isinstance(solver, HalfSolver) else solver, ShARK):
         raise ValueError("ShARK requires MultiTerm(ODETerm(drift), ControlTerm(diffusion, VirtualBrownianTree))")
 
+    if event is not None:
+        ev_params = np.ascontiguousarray(event.cond_fn.params(d, ctrl), np.float64)
+        keep_alive.append(ev_params)
+        D.event_kind, D.event_params, D.n_event_params = event.cond_fn.kind, ev_params.ctypes.data, ev_params.size
+        D.event_direction = 0 if event.direction is None else (1 if event.direction else 2)
+        if event.root_finder is not None:
+            D.event_root_find, D.event_rtol, D.event_atol = 1, float(event.root_finder.rtol), float(event.root_finder.atol)
     T = L.dfx_out_size(C.byref(D))
     i32 = xp.int32()
     ts_out = xp.empty((n, T), rdt)

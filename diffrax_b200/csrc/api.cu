@@ -325,6 +325,13 @@ static int check_desc(const dfx_solve_desc *d) {
     set_error("Must have (t1 - t0) * dt0 >= 0");  // _integrate.py:1036-1045
     return DFX_ERR_BAD_ARGUMENT;
   }
+  if (d->event_kind != DFX_EVENT_NONE) {
+    const int need = d->event_kind == DFX_EVENT_AFFINE ? d->dim + 2 : (d->event_kind == DFX_EVENT_STEADY_STATE ? 2 : -1);
+    if (need < 0 || !d->event_params || d->n_event_params != need || d->dim > 4 || d->event_direction < 0 || d->event_direction > 2) {
+      set_error("bad event: kind %d needs %d event_params (got %d), dim <= 4, direction in {0,1,2}", d->event_kind, need, d->n_event_params);
+      return DFX_ERR_BAD_ARGUMENT;
+    }
+  }
   const int T = dfx_out_size(d);
   if (T > 0 && (!d->ts_out || !d->ys_out)) { set_error("ts_out / ys_out are required (T_out = %d)", T); return DFX_ERR_BAD_ARGUMENT; }
   if (d->save_dense && (!d->dense_ts || !d->dense_y0 || !d->dense_y1 || !d->dense_count)) {

@@ -87,6 +87,10 @@ struct SolveParams {
   int *stats, *result, *save_count;
   R *dense_ts, *dense_y0, *dense_y1, *dense_k;
   int *dense_count;
+  // Event (RICH instantiation only): kind, direction (0 any / 1 up / 2 down), Newton root find on the local interpolant
+  int event_kind, event_dir, event_root;
+  R ev_w[4], ev_b, ev_wt, ev_rtol, ev_atol;  // affine: w, b, wt; steady state: ev_rtol / ev_atol; root finder: ev_rtol / ev_atol
+  R ev_ss_rtol, ev_ss_atol;
   int refill_batch;  // finished lanes wait until this many can be finalised + refilled in one pass (>= 1)
   int dense_coop;    // SaveAt(dense): stage records through shared memory and store them warp-cooperatively (launcher provides the smem)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
@@ -214,11 +218,31 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   int save_index = 0, saveat_ts_index = 0, dense_index = 0;
   [[maybe_unused]] int step_index = 0, jump_index = 0;  // ClipStepSizeController state (RICH only)
   [[maybe_unused]] bool made_jump = false;
+  [[maybe_unused]] R event_value = R(0);  // Event: cond_fn at the previous state (RICH only)
   BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME> bm;
 #pragma unroll
   for (int c = 0; c < D; ++c) { y[c] = R(0); f_fsal[c] = R(0); }
 
   const R sqrt_d = (R)sqrt((double)D);
+
+  // Event condition (see dfx_solve_desc): affine  w . y + wt t + b,  or steady state  rms(f) < atol + rtol rms(y)  (1 = True)
+  [[maybe_unused]] auto event_cond = [&](R t, const R (&yy)[D], R dir) -> R {
+    if (p.event_kind == DFX_EVENT_AFFINE) {
+      R v = R(0);
+#pragma unroll
+      for (int c = 0; c < D; ++c) v += p.ev_w[c < 4 ? c : 3] * yy[c];
+      return v + p.ev_wt * t + p.ev_b;
+    }
+    R f[D], nf = R(0), ny = R(0);
+    Field::template eval<R>(fp, t * dir, yy, f);
+    if constexpr (D == 1) { nf = r_abs(f[0]); ny = r_abs(yy[0]); }
+    else {
+#pragma unroll
+      for (int c = 0; c < D; ++c) { nf += f[c] * f[c]; ny += yy[c] * yy[c]; }
+      nf = r_sqrt(nf) / sqrt_d; ny = r_sqrt(ny) / sqrt_d;
+    }
+    return (nf < p.ev_ss_atol + p.ev_ss_rtol * ny) ? R(1) : R(0);
+  };
 
   // SaveAt(dense=True) staging: one record of kDenseRec values per lane, padded to an odd stride (conflict-free reads)
   constexpr int kDenseK = DENSE_K ? S * D : 0;
@@ -251,11 +275,14 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             }
           }
         }
-        if (p.save_t1) {  // _integrate.py:847-877
+        {  // _integrate.py:847-877
           bool via_steps = false;
           if (p.save_steps == 1) via_steps = true;
           else if (p.save_steps > 1) via_steps = (num_accepted % p.save_steps) == 0;
-          if (!via_steps) {
+          // 862-872: with an event root finder the final value is (re)written whenever steps would have saved it
+          const bool ev_rule = RICH && p.event_kind != DFX_EVENT_NONE && p.event_root;
+          const bool pred = ev_rule ? (p.save_t1 || via_steps) : (p.save_t1 && !via_steps);
+          if (pred && save_index < p.out_size) {
             const long long o = idx * (long long)p.out_size + save_index;
             p.ts_out[o] = tprev * direction;
   #pragma unroll
@@ -397,6 +424,9 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               for (int c = 0; c < D; ++c) p.ys_out[(idx * (long long)p.out_size) * D + c] = y[c];
               save_index = 1;
             }
+          }
+          if constexpr (RICH) {
+            if (p.event_kind != DFX_EVENT_NONE) event_value = event_cond(tprev, y, direction);  // _integrate.py:1432-1476
           }
           active = true;
         }
@@ -685,12 +715,73 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         num_steps += 1;
         num_accepted += keep ? 1 : 0;
 
+        // ---- Event: _integrate.py:548-633 (detection at the new state of every step) and 691-821 (root find) ----
+        // The reference saves the step, then finds the event time, then deletes every saved time after it ("unsave");
+        // here the event time is found first and the saves below simply stop at it - the same buffers come out.
+        [[maybe_unused]] bool ev_hit = false;
+        [[maybe_unused]] R t_event = tprev_new;
+        [[maybe_unused]] R y_event[D];
+        if constexpr (RICH) {
+          if (p.event_kind != DFX_EVENT_NONE) {
+            R ynew[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) ynew[c] = keep ? y1[c] : y[c];
+            const R nv = event_cond(tprev_new, ynew, direction);
+            const int so = (event_value > R(0)) - (event_value < R(0)), sn = (nv > R(0)) - (nv < R(0));
+            bool m;
+            if (p.event_kind == DFX_EVENT_STEADY_STATE) m = nv != R(0);
+            else if (p.event_dir == 0) m = so != sn;
+            else if (p.event_dir == 1) m = (so <= 0) && (sn > 0);
+            else m = (so > 0) && (sn <= 0);
+            event_value = nv;
+            if (m) {
+              ev_hit = true;
+              result = DFX_RESULT_EVENT_OCCURRED;
+              if (p.event_root) {
+                R tf = st1;
+                bool ok = true;
+                if (p.event_kind == DFX_EVENT_AFFINE) {
+                  // [EXT] optimistix.Newton(rtol, atol), options lower / upper = the step, y0 = its end, max_steps 256:
+                  // clipped Newton steps; Cauchy termination on the iterate and on the function value
+                  auto along = [&](R t, R &g, R &dg) {
+                    R yq[D], dq[D];
+                    interp_eval<INTERP, R, S, D>(st0, st1, y, y1_dense, k, t, yq);
+                    interp_deriv<INTERP, R, S, D>(st0, st1, y, y1_dense, k, t, dq);
+                    R v = R(0), dv = R(0);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) { v += p.ev_w[c < 4 ? c : 3] * yq[c]; dv += p.ev_w[c < 4 ? c : 3] * dq[c]; }
+                    g = v + p.ev_wt * t + p.ev_b;
+                    dg = dv + p.ev_wt;
+                  };
+                  R g, dg;
+                  along(tf, g, dg);
+                  ok = false;
+                  for (int it = 0; it < 256; ++it) {
+                    R tn = jnp_min(jnp_max(tf - g / dg, st0), st1);
+                    R gn, dgn;
+                    along(tn, gn, dgn);
+                    const bool conv = (r_abs(tn - tf) < p.ev_atol + p.ev_rtol * r_abs(tn)) && (r_abs(gn - g) < p.ev_atol + p.ev_rtol * r_abs(gn));
+                    tf = tn; g = gn; dg = dgn;
+                    if (conv) { ok = true; break; }
+                  }
+                }
+                t_event = tf;
+                interp_eval<INTERP, R, S, D>(st0, st1, y, y1_dense, k, tf, y_event);
+                if (!ok) result = DFX_RESULT_EVENT_ROOT_FIND_FAILED;
+              }
+            }
+          }
+        }
+        // with a root finder, saves of this step at times after the event time do not survive (777-806)
+        [[maybe_unused]] const bool ev_cut = RICH && ev_hit && p.event_root;
+
         if constexpr (RICH) {
           // ---- SaveAt(ts): interpolant on the attempted interval, kept steps only (456-487) ----
           if (p.save_ts != nullptr && keep) {
             while (saveat_ts_index < p.n_save_ts) {
               const R tq = p.save_ts[saveat_ts_index] * direction;
               if (!(tq <= st1)) break;
+              if (ev_cut && tq > t_event) break;
               R yq[D];
               interp_eval<INTERP, R, S, D>(st0, st1, y, y1_dense, k, tq, yq);
               const long long o = idx * (long long)p.out_size + save_index;
@@ -702,7 +793,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             }
           }
           // ---- SaveAt(steps=n) (493-524) ----
-          if (p.save_steps != 0 && keep && (num_accepted % p.save_steps) == 0) {
+          if (p.save_steps != 0 && keep && (num_accepted % p.save_steps) == 0 && !(ev_cut && tprev_new > t_event)) {
             const long long o = idx * (long long)p.out_size + save_index;
             p.ts_out[o] = tprev_new * direction;
 #pragma unroll
@@ -749,6 +840,13 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         }
         tprev = tprev_new;
         tnext = tnext_new;
+        if constexpr (RICH) {
+          if (ev_cut) {  // tfinal, yfinal = the event time and the interpolant there (745-756)
+            tprev = t_event;
+#pragma unroll
+            for (int c = 0; c < D; ++c) y[c] = y_event[c];
+          }
+        }
       }
     }
 

@@ -72,6 +72,16 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   p.dense_vec_ok = (((uintptr_t)d->dense_y0 | (uintptr_t)d->dense_y1 | (uintptr_t)d->dense_k) & 31u) == 0;
   p.y_final = (R *)d->y_final; p.t_final = (R *)d->t_final;
   p.keys = d->bm_keys;
+  p.event_kind = d->event_kind; p.event_dir = d->event_direction; p.event_root = d->event_root_find;
+  for (int c = 0; c < 4; ++c) p.ev_w[c] = R(0);
+  p.ev_b = p.ev_wt = p.ev_ss_rtol = p.ev_ss_atol = R(0);
+  p.ev_rtol = (R)d->event_rtol; p.ev_atol = (R)d->event_atol;
+  if (d->event_kind == DFX_EVENT_AFFINE) {
+    for (int c = 0; c < d->dim && c < 4; ++c) p.ev_w[c] = (R)d->event_params[c];
+    p.ev_b = (R)d->event_params[d->dim]; p.ev_wt = (R)d->event_params[d->dim + 1];
+  } else if (d->event_kind == DFX_EVENT_STEADY_STATE) {
+    p.ev_ss_rtol = (R)d->event_params[0]; p.ev_ss_atol = (R)d->event_params[1];
+  }
   if (sde) {
     p.vbt.t0 = d->bm_t0; p.vbt.t1 = d->bm_t1;
     const double tol_n = d->bm_tol / (d->bm_t1 - d->bm_t0);  // tree.py:286
@@ -137,7 +147,7 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
   const bool rich = d->save_t0 || d->save_ts || d->save_steps || d->save_dense || (d->hairer_initial_step && std::isnan(d->dt0)) ||
-                    d->step_ts || d->jump_ts;
+                    d->step_ts || d->jump_ts || d->event_kind != DFX_EVENT_NONE;
 
   // scratch: the work-queue counter.  (The +inf padding of unfilled output slots is written by the solve kernel itself
   // when it finalises a trajectory, so there is no second pass over the buffers.)

@@ -53,7 +53,9 @@ enum dfx_levy { DFX_LEVY_NONE = 0, DFX_LEVY_BROWNIAN_INCREMENT = 1, DFX_LEVY_SPA
 /* RESULTS (_solution.py:13-31).  successful == 0 is the only value the reference pins
  * (test/test_saveat_solution.py:21). */
 enum dfx_result { DFX_RESULT_SUCCESSFUL = 0, DFX_RESULT_MAX_STEPS_REACHED = 1,
-                  DFX_RESULT_DT_MIN_REACHED = 2 };
+                  DFX_RESULT_DT_MIN_REACHED = 2, DFX_RESULT_EVENT_OCCURRED = 3 /* not a failure: _solution.py:52-62 is_okay */,
+                  DFX_RESULT_EVENT_ROOT_FIND_FAILED = 4 };
+enum dfx_event { DFX_EVENT_NONE = 0, DFX_EVENT_AFFINE = 1, DFX_EVENT_STEADY_STATE = 2 };
 
 enum dfx_error { DFX_OK = 0, DFX_ERR_BAD_ARGUMENT = -1, DFX_ERR_UNSUPPORTED = -2,
                  DFX_ERR_CUDA = -3, DFX_ERR_NO_DEVICE = -4 };
@@ -130,6 +132,18 @@ typedef struct dfx_solve_desc {
   const uint32_t *bm_keys;    /* [N, 2] the keys the user passed to VirtualBrownianTree */
   double bm_t0, bm_t1, bm_tol;
   int32_t threefry_partitionable; /* jax_threefry_partitionable (default True since JAX 0.5) */
+
+  /* Event(cond_fn, root_finder, direction): _event.py:13-118, _integrate.py:542-633 (detection), 691-821 (root find, unsave).
+   * One registered condition function, evaluated in the solver's (direction-normalised) time like the reference's
+   * cond_fn(tprev, y, ...):
+   *   DFX_EVENT_AFFINE        c(t, y) = w . y + wt * t + b        event_params = [w[0..d), b, wt]  real-valued: sign change
+   *   DFX_EVENT_STEADY_STATE  rms(f(t, y)) < atol + rtol * rms(y)  event_params = [rtol, atol]      boolean (_event.py:120-170)
+   * event_direction: 0 = None (any crossing), 1 = True (upcrossing), 2 = False (downcrossing).
+   * event_root_find: 0 = root_finder None (the solve ends at the end of the triggering step); 1 = Newton(event_rtol,
+   *   event_atol) on the step's local interpolant, bracketed to the step, saved values after the event time removed. */
+  int32_t event_kind, event_direction, event_root_find;
+  const double *event_params; int32_t n_event_params; /* host */
+  double event_rtol, event_atol;
 } dfx_solve_desc;
 
 /* ---- library ---- */

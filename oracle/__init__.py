@@ -59,6 +59,9 @@ class Desc(C.Structure):
         ("levy_area", C.c_int32), ("bm_keys", C.c_void_p),
         ("bm_t0", C.c_double), ("bm_t1", C.c_double), ("bm_tol", C.c_double),
         ("threefry_partitionable", C.c_int32),
+        ("event_kind", C.c_int32), ("event_direction", C.c_int32), ("event_root_find", C.c_int32),
+        ("event_params", C.c_void_p), ("n_event_params", C.c_int32),
+        ("event_rtol", C.c_double), ("event_atol", C.c_double),
         ("trace_traj", C.c_int64), ("trace", C.c_void_p),
         ("num_threads", C.c_int32),
     ]
@@ -163,7 +166,8 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
           hairer_initial_step=False, save_t0=False, save_t1=True, save_ts=None, save_steps=0,
           save_dense=False, max_steps=4096, levy_area=None, keys=None, bm_t0=0.0, bm_t1=1.0,
           bm_tol=1e-3, partitionable=True, callback=None, trace_traj=None, num_threads=0,
-          t0_per_traj=None, t1_per_traj=None, step_ts=None, jump_ts=None):
+          t0_per_traj=None, t1_per_traj=None, step_ts=None, jump_ts=None,
+          event=None, event_params=(), event_direction=None, event_root=None):
     """Run the oracle on a batch.  Mirrors one vmapped diffeqsolve call of the reference."""
     L = lib()
     dt = np.dtype(dtype)
@@ -235,6 +239,15 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
     D.bm_keys = _ptr(ka)
     D.bm_t0, D.bm_t1, D.bm_tol = float(bm_t0), float(bm_t1), float(bm_tol)
     D.threefry_partitionable = int(partitionable)
+    if event is not None:
+        # event: "affine" (params w[0..d), b, wt) or "steady_state" (params rtol, atol); event_direction None / True / False;
+        # event_root: None or (rtol, atol) of the Newton root finder
+        D.event_kind = {"affine": 1, "steady_state": 2}[event]
+        ev_params = np.ascontiguousarray(event_params, np.float64)
+        D.event_params, D.n_event_params = _ptr(ev_params), ev_params.size
+        D.event_direction = 0 if event_direction is None else (1 if event_direction else 2)
+        if event_root is not None:
+            D.event_root_find, D.event_rtol, D.event_atol = 1, float(event_root[0]), float(event_root[1])
     trace = None
     if trace_traj is not None:
         trace = np.full((max_steps, 3), np.nan)

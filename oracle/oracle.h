@@ -31,6 +31,7 @@ enum { ORC_F64 = 0, ORC_F32 = 1 };
 enum { ORC_TSIT5 = 0, ORC_DOPRI5 = 1, ORC_DOPRI8 = 2, ORC_HEUN = 3, ORC_BOSH3 = 4,
        ORC_MIDPOINT = 5, ORC_RALSTON = 6, ORC_EULER = 7, ORC_SHARK = 8,
        ORC_HALF = 0x100 /* flag: HalfSolver(inner), _solver/base.py:250-346 */ };
+enum { ORC_EVENT_NONE = 0, ORC_EVENT_AFFINE = 1, ORC_EVENT_STEADY_STATE = 2 };
 /* controller */
 enum { ORC_CTRL_CONSTANT = 0, ORC_CTRL_PID = 1 };
 /* vector fields */
@@ -40,7 +41,7 @@ enum { ORC_FIELD_DECAY = 0, ORC_FIELD_LOTKA_VOLTERRA = 1, ORC_FIELD_LORENZ = 2,
 /* Brownian levy_area kind */
 enum { ORC_LEVY_NONE = 0, ORC_LEVY_BROWNIAN_INCREMENT = 1, ORC_LEVY_SPACE_TIME = 2 };
 /* RESULTS (_solution.py:13-31; only successful == 0 is pinned by the reference tests) */
-enum { ORC_OK = 0, ORC_MAX_STEPS_REACHED = 1, ORC_DT_MIN_REACHED = 2 };
+enum { ORC_OK = 0, ORC_MAX_STEPS_REACHED = 1, ORC_DT_MIN_REACHED = 2, ORC_EVENT_OCCURRED = 3, ORC_EVENT_ROOT_FIND_FAILED = 4 };
 
 /* generic user vector field (ctypes callback): out[d] = f(t, y[d]) in double */
 typedef void (*orc_callback_vf)(double t, const double *y, double *out, int dim);
@@ -90,6 +91,17 @@ typedef struct orc_desc {
   const uint32_t *bm_keys;   /* [N, 2] user keys (before split_by_tree) */
   double bm_t0, bm_t1, bm_tol;
   int32_t threefry_partitionable;
+  /* Event(cond_fn, root_finder, direction) (_event.py:13-118; _integrate.py:542-633, 691-821) with one registered condition:
+   *   ORC_EVENT_AFFINE        c(t, y) = w . y + wt * t + b      event_params = [w[0..d), b, wt]   (real-valued: sign change)
+   *   ORC_EVENT_STEADY_STATE  rms(f(t, y)) < atol + rtol * rms(y) event_params = [rtol, atol]      (boolean, _event.py:120-170)
+   * t is the solver's (direction-normalised) time, as in the reference's call cond_fn(tprev, y, ...).
+   * event_direction: 0 = None (any crossing), 1 = True (upcrossing), 2 = False (downcrossing).
+   * event_root_find: 0 = root_finder None; 1 = Newton(event_rtol, event_atol) on the local interpolant, bracketed to the
+   *   triggering step ([EXT] optimistix.Newton, restated from its published algorithm: clipped Newton steps from the step's
+   *   end, Cauchy termination on both the iterate and the function value, at most 256 iterations). */
+  int32_t event_kind, event_direction, event_root_find;
+  const double *event_params; int32_t n_event_params;
+  double event_rtol, event_atol;
   /* test hook: per-step trace of (tprev, tnext, keep) for trajectory `trace_traj` */
   int64_t trace_traj;
   double *trace;             /* [max_steps, 3] or NULL */

@@ -489,6 +489,60 @@ def test_saveat_fn_and_subs(dev):
         dfx.SaveAt(t1=True, subs=dfx.SubSaveAt(t0=True))
 
 
+@pytest.mark.parametrize("root", [None, (1e-10, 1e-12)])
+@pytest.mark.parametrize("direction", [None, True, False])
+@pytest.mark.parametrize("solver", ["tsit5", "dopri5", "heun"])
+def test_events_affine(dev, solver, direction, root):
+    """Event(cond_fn, root_finder, direction) (_event.py:13-118; _integrate.py:542-633, 691-821): a real-valued condition
+    (x crossing 0.3) on the forced oscillator; detection step, Newton-located event time, unsave + final save."""
+    kw, n = _osc_case(solver, np.float64, save_t0=True, save_t1=True, save_ts=np.linspace(0.0, 3.0, 25)[1:])
+    ev = dict(event="affine", event_params=[1.0, 0.0, -0.3, 0.0], event_direction=direction, event_root=root)
+    o = _oracle(dict(kw, **ev))
+    kw2 = dict(kw)
+    fname, fparams = kw2["field"], kw2["params"]
+    y0t = torch.tensor(np.asarray(kw2["y0"], np.float64), device=dev)
+    event = dfx.Event(dfx.AffineEvent([1.0, 0.0], b=-0.3), None if root is None else dfx.Newton(*root), direction)
+    sol = dfx.diffeqsolve(dfx.ODETerm(FIELDS[fname](*fparams)), make_solver(solver), kw2["t0"], kw2["t1"], kw2["dt0"], y0t,
+                          saveat=dfx.SaveAt(t0=True, t1=True, ts=kw2["save_ts"]), event=event,
+                          stepsize_controller=dfx.PIDController(rtol=kw2["rtol"], atol=kw2["atol"]), max_steps=kw2["max_steps"])
+    res, ores = to_np(sol.result), o["result"]
+    assert set(np.unique(ores)) <= {0, 3} and (ores == 3).sum() > 20 and (ores == 0).sum() > 0   # both outcomes are exercised
+    st = stats_np(sol)
+    same = np.all(st == o["stats"], axis=1) & (res == ores)
+    assert same.mean() >= 0.98, same.mean()
+    assert np.array_equal(np.isfinite(to_np(sol.ts))[same], np.isfinite(o["ts"])[same])     # same slots filled / unsaved
+    # without a root finder the reported event time is a raw accepted-step time, which carries the ~1e-16 / rtol noise of
+    # the embedded error estimate in any implementation (see test_every_solver_step_indexed_outputs)
+    assert relerr(to_np(sol.ts)[same], o["ts"][same]) < (1e-9 if root is not None else 1e-6)
+    assert relerr(to_np(sol.ys)[same], o["ys"][same]) < (1e-8 if root is not None else 1e-5)
+    if root is not None:   # at the located event time the condition function vanishes
+        hit = same & (res == 3)
+        last = np.isfinite(to_np(sol.ts)).sum(1) - 1
+        x_ev = to_np(sol.ys)[np.arange(n), last, 0]
+        assert np.abs(x_ev[hit] - 0.3).max() < 1e-8
+
+
+def test_events_steady_state_and_results(dev):
+    """steady_state_event (_event.py:120-170, boolean condition, tolerances inherited from the controller) and the result
+    codes: an event is `is_okay` but not `is_successful`, and does not raise under throw=True."""
+    rng = np.random.default_rng(2)
+    y0 = rng.uniform(0.5, 2.0, (64, 1))
+    ctrl = dfx.PIDController(rtol=1e-6, atol=1e-4)
+    sol = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.LinearDecay(1.0)), dfx.Tsit5(), 0.0, 100.0, 0.01, torch.tensor(y0, device=dev),
+                          stepsize_controller=ctrl, event=dfx.Event(dfx.steady_state_event()))
+    o = oracle.solve("decay", y0, 0.0, 100.0, 0.01, solver="tsit5", params=[1.0], rtol=1e-6, atol=1e-4,
+                     event="steady_state", event_params=[1e-6, 1e-4])
+    assert bool(dfx.is_event(sol.result).all()) and bool(dfx.is_okay(sol.result).all()) and not bool(dfx.is_successful(sol.result).any())
+    assert np.all(o["result"] == 3)
+    same = np.all(stats_np(sol) == o["stats"], axis=1)
+    assert same.mean() > 0.95
+    assert relerr(to_np(sol.ts)[same], o["ts"][same]) < 1e-9 and relerr(to_np(sol.ys)[same], o["ys"][same]) < 1e-8
+    assert float(sol.ts.max()) < 20.0                                    # stopped long before t1 = 100
+    with pytest.raises(ValueError, match="steady_state_event"):
+        dfx.diffeqsolve(dfx.ODETerm(dfx.fields.LinearDecay(1.0)), dfx.Tsit5(), 0.0, 1.0, 0.01, torch.tensor(y0, device=dev),
+                        event=dfx.Event(dfx.steady_state_event()))
+
+
 def test_hairer_initial_step_flag(dev):
     """K2: the starting-step algorithm of pid.py:51-81 behind a flag; default is the constant 0.01 the reference uses."""
     rng = np.random.default_rng(9)

@@ -292,3 +292,32 @@ def test_dense_derivative_is_slope_of_evaluate():
     d = oracle.dense_evaluate("tsit5", rr["dense"], tq, direction=-1.0, derivative=True)
     fd = (oracle.dense_evaluate("tsit5", rr["dense"], tq + h, direction=-1.0) - oracle.dense_evaluate("tsit5", rr["dense"], tq - h, direction=-1.0)) / (2 * h)
     assert np.abs(d - fd).max() < 5e-8
+
+
+def test_event_bouncing_ball_docstring():
+    """_event.py:74-110: x'' = -8, x(0) = 10, Tsit5, dt0 = 0.1 constant, Event(x, Newton(1e-5, 1e-5)):
+    'Event time: 1.58...', 'Velocity at event time: -12.64...' (exact: sqrt(2.5), -8 sqrt(2.5))."""
+    vf = lambda t, y: np.array([y[1], -8.0])
+    kw = dict(solver="tsit5", callback=vf, controller="constant", event="affine", event_params=[1.0, 0.0, 0.0, 0.0], max_steps=4096)
+    r = oracle.solve("callback", np.array([[10.0, 0.0]]), 0.0, 1e3, 0.1, event_root=(1e-5, 1e-5), **kw)
+    assert r["result"][0] == 3                                            # RESULTS.event_occurred
+    assert abs(r["ts"][0, 0] - math.sqrt(2.5)) < 1e-9 and abs(r["ys"][0, 0, 1] + 8 * math.sqrt(2.5)) < 1e-8
+    assert f"{r['ts'][0, 0]:.2f}" == "1.58" and f"{r['ys'][0, 0, 1]:.2f}" == "-12.65"
+    # without a root finder the solve stops at the end of the step on which the sign changed
+    r0 = oracle.solve("callback", np.array([[10.0, 0.0]]), 0.0, 1e3, 0.1, **kw)
+    assert r0["result"][0] == 3 and abs(r0["ts"][0, 0] - 1.6) < 1e-12 and r0["stats"][0, 0] == 16
+    # direction=True (upcrossing only) ignores the downward crossing: the ball falls until max_steps
+    r1 = oracle.solve("callback", np.array([[10.0, 0.0]]), 0.0, 3.0, 0.1, event_direction=True, **kw)
+    assert r1["result"][0] == 0 and abs(r1["ts"][0, 0] - 3.0) < 1e-12
+    # SaveAt(ts) + steps: nothing after the event time survives (unsave, _integrate.py:777-806); t1 re-saved (862-872)
+    ts = np.linspace(0.0, 3.0, 31)
+    r2 = oracle.solve("callback", np.array([[10.0, 0.0]]), 0.0, 3.0, 0.1, event_root=(1e-8, 1e-8), save_ts=ts, **kw)
+    n_before = int((ts <= math.sqrt(2.5)).sum())
+    assert np.all(np.isfinite(r2["ts"][0, :n_before])) and np.all(np.isinf(r2["ts"][0, n_before + 1:]))
+    assert abs(r2["ts"][0, n_before] - math.sqrt(2.5)) < 1e-9             # the t1 slot holds (tfinal, yfinal)
+    assert np.allclose(r2["ys"][0, :n_before, 0], 10 - 4 * ts[:n_before] ** 2, atol=1e-9)
+    # steady state (boolean): y' = -y reaches |f| < 1e-3 at t = ln(1000); detected at the end of that step
+    r3 = oracle.solve("decay", np.array([[1.0]]), 0.0, 100.0, 0.01, solver="tsit5", params=[1.0], rtol=1e-6, atol=1e-9,
+                      event="steady_state", event_params=[0.0, 1e-3])
+    assert r3["result"][0] == 3 and math.log(1000) <= r3["ts"][0, 0] < math.log(1000) + 1.0
+    assert abs(r3["ys"][0, 0, 0]) < 1e-3
