@@ -130,12 +130,12 @@ constexpr int min_blocks_per_sm() {
 #endif
 }
 
-// Claim the next trajectory for every lane of the warp that needs one: one atomic per warp.
 // +inf into row[start, len), one warp, coalesced streaming stores
 template <class R> __device__ __forceinline__ void pad_tail(R *row, long long start, long long len, int lane) {
   for (long long i = start + lane; i < len; i += 32) st_cs(&row[i], Num<R>::inf());
 }
 
+// Claim the next trajectory for every lane of the warp that needs one: one atomic per warp.
 __device__ __forceinline__ long long claim_work(bool need, unsigned long long *counter) {
   const unsigned m = __ballot_sync(kFullMask, need);
   if (m == 0) return -1;
@@ -184,7 +184,10 @@ template <class R> __device__ __forceinline__ int clip_find_idx(R t, const R *ts
 //   Solver generated tableau struct (tableaux.cuh), EulerSolver or SharkSolver
 //   LEVY   dfx_levy: 0 ODE, 1 BrownianIncrement, 2 SpaceTimeLevyArea
 //   RICH   false: SaveAt(t1=True) only (the C2/C4/C5 fast path); true: every SaveAt mode
-template <class R, class Field, class Solver, int LEVY, bool RICH>
+//   EXTRA  (RICH only) the rarely used machinery: ClipStepSizeController, the Hairer starting step, Events.  Kept out of
+//          the plain SaveAt kernels because it costs them registers and instruction-cache footprint (Dopri8 dense: 216 ->
+//          255 registers with spills when it was compiled in)
+template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<R, Field, Solver, LEVY, RICH>())
 ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) {
   constexpr int D = Field::kDim;
@@ -280,7 +283,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           if (p.save_steps == 1) via_steps = true;
           else if (p.save_steps > 1) via_steps = (num_accepted % p.save_steps) == 0;
           // 862-872: with an event root finder the final value is (re)written whenever steps would have saved it
-          const bool ev_rule = RICH && p.event_kind != DFX_EVENT_NONE && p.event_root;
+          const bool ev_rule = EXTRA && p.event_kind != DFX_EVENT_NONE && p.event_root;
           const bool pred = ev_rule ? (p.save_t1 || via_steps) : (p.save_t1 && !via_steps);
           if (pred && save_index < p.out_size) {
             const long long o = idx * (long long)p.out_size + save_index;
@@ -359,7 +362,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           }
           tprev = t0;
           tnext = t0 + dt0;
-          if constexpr (RICH) {  // ClipStepSizeController.init, clip.py:246-302
+          if constexpr (EXTRA) {  // ClipStepSizeController.init, clip.py:246-302
             made_jump = false;
             if (p.step_ts != nullptr) {
               step_index = clip_find_idx(t0, p.step_ts, p.n_step_ts, 0, direction);  // searchsorted(side="right")
@@ -381,7 +384,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             // step re-evaluates the same point, so computing it once here is value-identical.
             Field::template eval<R>(fp, t0 * direction, y, f_fsal);
           }
-          if constexpr (TAB && !SDE && RICH) {  // (the launcher routes hairer solves to the RICH instantiation)
+          if constexpr (TAB && !SDE && EXTRA) {  // (the launcher routes hairer solves to the EXTRA instantiation)
             if (p.hairer && !p.has_dt0 && p.controller == DFX_CTRL_PID) {
               // _select_initial_step, pid.py:51-81 (Hairer, Norsett, Wanner II.4) - behind a flag: through diffeqsolve
               // the reference never reaches it.  func == terms.vf: WrapTerm passes t * direction.
@@ -425,7 +428,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               save_index = 1;
             }
           }
-          if constexpr (RICH) {
+          if constexpr (EXTRA) {
             if (p.event_kind != DFX_EVENT_NONE) event_value = event_cond(tprev, y, direction);  // _integrate.py:1432-1476
           }
           active = true;
@@ -459,7 +462,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               R f0[D];
   #pragma unroll
               for (int c = 0; c < D; ++c) f0[c] = f_in[c];
-              if constexpr (RICH) {
+              if constexpr (EXTRA) {
                 // eval_first_stage = first_step | made_jump (runge_kutta.py:687): after stepping around a jump the carried
                 // derivative belongs to the other side of the discontinuity and is re-evaluated at (st0, y)
                 if (reeval) Field::template eval<R>(fp, st0 * direction, y, f0);
@@ -585,6 +588,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             }
           }
         };
+        static_assert(!(EXTRA && !RICH), "EXTRA implies RICH");
         R k[S][D];
         R y1[D], yerr[D], f_last[D];
         [[maybe_unused]] R y1_alt[D];
@@ -689,7 +693,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           next_t1 = t1n;
         }
 
-        if constexpr (RICH) {  // ClipStepSizeController.adapt_step_size, clip.py:350-377
+        if constexpr (EXTRA) {  // ClipStepSizeController.adapt_step_size, clip.py:350-377
           bool ctrl_made_jump = false;
           if (p.step_ts != nullptr) {
             bool dummy;
@@ -709,7 +713,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         // ---- book-keeping, _integrate.py:412-437 ----
         // 412: tprev = min(tprev, t1) is the identity without jump_ts: next_t0 is st0 or st1, and tnext never exceeds t1
         // (it starts as min(t0 + dt0, t1) and every update below clips it to t1); a bumped next_t0 is clipped explicitly.
-        const R tprev_new = (RICH && p.jump_ts != nullptr) ? jnp_min(next_t0, t1) : next_t0;
+        const R tprev_new = (EXTRA && p.jump_ts != nullptr) ? jnp_min(next_t0, t1) : next_t0;
         R tnext_new = next_t1;
         if (next_t1 > t1_clip_floor) tnext_new = keep ? t1 : tprev_new + R(0.5) * (t1 - tprev_new);  // 278-284
         num_steps += 1;
@@ -721,7 +725,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         [[maybe_unused]] bool ev_hit = false;
         [[maybe_unused]] R t_event = tprev_new;
         [[maybe_unused]] R y_event[D];
-        if constexpr (RICH) {
+        if constexpr (EXTRA) {
           if (p.event_kind != DFX_EVENT_NONE) {
             R ynew[D];
 #pragma unroll
@@ -773,7 +777,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           }
         }
         // with a root finder, saves of this step at times after the event time do not survive (777-806)
-        [[maybe_unused]] const bool ev_cut = RICH && ev_hit && p.event_root;
+        [[maybe_unused]] const bool ev_cut = EXTRA && ev_hit && p.event_root;
 
         if constexpr (RICH) {
           // ---- SaveAt(ts): interpolant on the attempted interval, kept steps only (456-487) ----
@@ -840,7 +844,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         }
         tprev = tprev_new;
         tnext = tnext_new;
-        if constexpr (RICH) {
+        if constexpr (EXTRA) {
           if (ev_cut) {  // tfinal, yfinal = the event time and the interpolant there (745-756)
             tprev = t_event;
 #pragma unroll

@@ -39,8 +39,9 @@ template <class R> __device__ __forceinline__ Dual<R> zero_like(Dual<R>) { retur
 template <class R> __device__ __forceinline__ Dual<R> &operator+=(Dual<R> &a, Dual<R> b) { a = a + b; return a; }
 
 // The interpolant of kind KIND at theta = th (T = R: value; T = Dual<R>: value and d/dtheta).  k is [S][D] (ignored for linear).
-template <int KIND, class R, int S, int D, class T>
-__device__ __forceinline__ void interp_core(const T th, const R (&y0)[D], const R (&y1)[D], const R (&k)[S][D], T (&out)[D]) {
+// K: anything spelling an element k[j][c] (a plain R[S][D] array, or the shared-memory view of ensemble_kernel.cuh)
+template <int KIND, class R, int S, int D, class T, class K>
+__device__ __forceinline__ void interp_core(const T th, const R (&y0)[D], const R (&y1)[D], const K &k, T (&out)[D]) {
   if constexpr (KIND == kInterpLinear) {
 #pragma unroll
     for (int c = 0; c < D; ++c) out[c] = y0[c] + th * (y1[c] - y0[c]);
@@ -117,16 +118,16 @@ __device__ __forceinline__ void interp_core(const T th, const R (&y0)[D], const 
 }
 
 // Evaluate the interpolant of kind KIND on [t0, t1] at time t.
-template <int KIND, class R, int S, int D>
-__device__ __forceinline__ void interp_eval(R t0, R t1, const R (&y0)[D], const R (&y1)[D], const R (&k)[S][D],
+template <int KIND, class R, int S, int D, class K>
+__device__ __forceinline__ void interp_eval(R t0, R t1, const R (&y0)[D], const R (&y1)[D], const K &k,
                                             R t, R (&out)[D]) {
   interp_core<KIND, R, S, D, R>(linear_rescale(t0, t, t1), y0, y1, k, out);
 }
 
 // d/dt of the interpolant at time t: the tangent of `evaluate` w.r.t. t (AbstractPath.derivative via jax.jvp), including
 // linear_rescale's own tangent where(t0 == t1, 0, 1 / (t1 - t0)) (_misc.py:71-82).
-template <int KIND, class R, int S, int D>
-__device__ __forceinline__ void interp_deriv(R t0, R t1, const R (&y0)[D], const R (&y1)[D], const R (&k)[S][D],
+template <int KIND, class R, int S, int D, class K>
+__device__ __forceinline__ void interp_deriv(R t0, R t1, const R (&y0)[D], const R (&y1)[D], const K &k,
                                              R t, R (&out)[D]) {
   const Dual<R> th{linear_rescale(t0, t, t1), (t0 == t1) ? R(0) : R(1) / (t1 - t0)};
   Dual<R> o[D];

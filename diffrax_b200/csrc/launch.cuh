@@ -97,9 +97,9 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
 struct DeviceInfo { int sms; };
 int device_sm_count(int *sms);  // cached per device (api.cu)
 
-template <class R, class Field, class Solver, int LEVY, bool RICH>
+template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false>
 int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, cudaStream_t stream) {
-  auto kern = ensemble_kernel<R, Field, Solver, LEVY, RICH>;
+  auto kern = ensemble_kernel<R, Field, Solver, LEVY, RICH, EXTRA>;
   int sms = 0;
   if (int rc = device_sm_count(&sms)) return rc;
   // SaveAt(dense=True): per-lane staging records for the warp-cooperative stores
@@ -146,8 +146,9 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
-  const bool rich = d->save_t0 || d->save_ts || d->save_steps || d->save_dense || (d->hairer_initial_step && std::isnan(d->dt0)) ||
-                    d->step_ts || d->jump_ts || d->event_kind != DFX_EVENT_NONE;
+  // EXTRA: ClipStepSizeController / Hairer starting step / Event; RICH: any SaveAt mode beyond t1 (EXTRA implies RICH)
+  const bool extra = (d->hairer_initial_step && std::isnan(d->dt0)) || d->step_ts || d->jump_ts || d->event_kind != DFX_EVENT_NONE;
+  const bool rich = extra || d->save_t0 || d->save_ts || d->save_steps || d->save_dense;
 
   // scratch: the work-queue counter.  (The +inf padding of unfilled output slots is written by the solve kernel itself
   // when it finalises a trajectory, so there is no second pass over the buffers.)
@@ -159,7 +160,8 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   p.work_counter = counter;
 
   int rc;
-  if (rich) rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);
+  if (extra) rc = launch_variant<R, Field, Solver, LEVY, true, true>(p, fp, stream);
+  else if (rich) rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);
   else rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
   cudaFreeAsync(scratch, stream);
   return rc;
