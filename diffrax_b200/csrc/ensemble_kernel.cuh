@@ -92,6 +92,7 @@ struct SolveParams {
   R ev_w[4], ev_b, ev_wt, ev_rtol, ev_atol;  // affine: w, b, wt; steady state: ev_rtol / ev_atol; root finder: ev_rtol / ev_atol
   R ev_ss_rtol, ev_ss_atol;
   int refill_batch;  // finished lanes wait until this many can be finalised + refilled in one pass (>= 1)
+  int dense_cs;      // dense records with st.global.cs (evict-first) instead of write-back stores
   int dense_coop;    // SaveAt(dense): stage records through shared memory and store them warp-cooperatively (launcher provides the smem)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
   R *y_final, *t_final;
@@ -807,7 +808,8 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           // ---- SaveAt(dense=True) (529-540) ----
           if (p.save_dense && keep) {
             const long long row = idx * (long long)p.max_steps + dense_index;
-            st_cs(&p.dense_ts[idx * (long long)(p.max_steps + 1) + dense_index + 1], tprev_new);
+            if (p.dense_cs) st_cs(&p.dense_ts[idx * (long long)(p.max_steps + 1) + dense_index + 1], tprev_new);
+            else p.dense_ts[idx * (long long)(p.max_steps + 1) + dense_index + 1] = tprev_new;
             if (p.dense_coop) {
               // stage this lane's record {k[S][D], y0[D], y1[D]} in shared memory; the warp flushes it below
               R *rec = dense_smem + ((threadIdx.x >> 5) * 32 + (threadIdx.x & 31)) * kDenseStride;
@@ -877,7 +879,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
                 if (e < kDenseK) dst = p.dense_k + row * kDenseK + e;
                 else if (e < kDenseK + D) dst = p.dense_y0 + row * D + (e - kDenseK);
                 else dst = p.dense_y1 + row * D + (e - kDenseK - D);
-                st_cs(dst, v);
+                if (p.dense_cs) st_cs(dst, v); else *dst = v;
               }
             }
           }

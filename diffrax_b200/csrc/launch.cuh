@@ -106,6 +106,14 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
   size_t smem = 0;
   p.dense_coop = 0;
   {
+    // dense records with write-back stores: consecutive steps of a trajectory are adjacent in every dense array (32 B of
+    // y0 / y1, 8 B of ts, 448 B of k per step for Dopri8, d = 4), and the ~38 k resident trajectories' open lines fit the
+    // L2 many times over, so L2 merges them into full lines before they go to HBM; evict-first (st.global.cs) stores send
+    // the partial sectors out one by one (C3: 27.1 ms vs 25.7 ms).  DFX_DENSE_CS=1 selects the streaming stores.
+    static const int env_cs = [] { const char *e = getenv("DFX_DENSE_CS"); return e ? atoi(e) : 0; }();
+    p.dense_cs = env_cs;
+  }
+  {
     // finalize/refill batching (ensemble_kernel.cuh): 2 is within a few percent of the optimum sqrt(2048 X / (n I)) for
     // anything from short to long trajectories; DFX_REFILL_BATCH overrides it for experiments
     static const int env_batch = [] { const char *e = getenv("DFX_REFILL_BATCH"); return e ? atoi(e) : 0; }();
