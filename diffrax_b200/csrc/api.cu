@@ -436,6 +436,10 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
   int64_t nchunks = h->save_dense ? 1 : h->n_traj / (128 * 1024);
   if (nchunks < 1) nchunks = 1;
   if (nchunks > 8) nchunks = 8;
+  if (const char *e = std::getenv("DFX_HOST_CHUNKS")) {  // experiments
+    const int64_t v = atoll(e);
+    if (v >= 1 && !h->save_dense) nchunks = v > h->n_traj ? (h->n_traj > 0 ? h->n_traj : 1) : v;
+  }
   cudaStream_t st[2];
   const int nstreams = nchunks > 1 ? 2 : 1;
   for (int i = 0; i < nstreams; ++i) DFX_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
