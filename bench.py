@@ -336,16 +336,34 @@ def run_ours(args):
                     "note": "whole-solve average incl. the CUDA-core layers, softplus/tanh and the RK/PID algebra; "
                             "tensor-pipe utilisation of the kernel: profiles/ ncu summary"}
         else:
-            # C5: threefry blocks on the INT32 ALU.  Per step with end-point reuse: one descent of L=8 levels:
-            # BI 3 blocks/level + root 3 + leaf 1 (+1 leaf split) ; STLA 7 blocks/level + root 5 + leaf 4.
-            blocks = {"c5_heun": 3 * 8 + 4, "c5_shark": 7 * 8 + 9}[args.workload]
+            # C5: threefry blocks on the INT32 ALU.  A query W(r) walks L = 8 tree levels (BI 3 blocks/level, STLA 7) and
+            # draws the leaf bridge (BI 1 block, STLA 4); the step's other end point is the previous step's query, and the
+            # descent cache (csrc/vbt.cuh) resumes each walk at the first level where it leaves the previous one - so the
+            # ALGORITHM executes, per step, only the levels below the common prefix.  Counted exactly for this time grid:
+            def walk(r, depth=8):
+                s_, bits = 0.0, []
+                for lv in range(depth):
+                    t_ = s_ + 2.0 ** -(lv + 1)
+                    right = r > t_
+                    bits.append(right)
+                    s_ = t_ if right else s_
+                return bits
+            nsteps_grid, lv_total, prev = 64, 0, walk(0.0)
+            for k_ in range(1, nsteps_grid + 1):
+                cur = walk(k_ / 64.0)
+                common = next((i for i in range(8) if cur[i] != prev[i]), 8)
+                lv_total += 8 - common
+                prev = cur
+            per_level, leaf = {"c5_heun": (3, 1), "c5_shark": (7, 4)}[args.workload]
+            blocks = per_level * lv_total / nsteps_grid + leaf
+            blocks_nocache = {"c5_heun": 3 * 8 + 4, "c5_shark": 7 * 8 + 9}[args.workload]
             ops = blocks * 77.0          # 20 x (add, rotate, xor) + 17 injection adds per block
             peak = float(L.dfx_measure_int_peak(local))
             achieved = (att / world) * ops / (ms_per_step * 1e-3) / 1e12
             roof = {"bound": "int32_alu", "achieved": achieved, "peak": peak, "unit": "Tera-op/s",
                     "frac": achieved / peak if peak > 0 else None, "traffic": None,
                     "peak_source": "dfx_measure_int_peak: add/rotate/xor chains, measured in this run",
-                    "threefry_blocks_per_step": blocks}
+                    "threefry_blocks_per_step": blocks, "threefry_blocks_per_step_without_descent_cache": blocks_nocache}
         roof["traffic"] = ncu_traffic(args.workload.split("_")[0])
         cpu_sample = min(args.cpu_sample, n_local)
         cpu_rate, cpu_dt, cores = cpu_port_rate(w, cpu_sample)

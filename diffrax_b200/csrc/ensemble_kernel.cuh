@@ -92,6 +92,7 @@ struct SolveParams {
   R ev_w[4], ev_b, ev_wt, ev_rtol, ev_atol;  // affine: w, b, wt; steady state: ev_rtol / ev_atol; root finder: ev_rtol / ev_atol
   R ev_ss_rtol, ev_ss_atol;
   int refill_batch;  // finished lanes wait until this many can be finalised + refilled in one pass (>= 1)
+  int dense_smem_offset;  // bytes of dynamic shared memory in front of the dense staging records (the VBT descent cache)
   int dense_cs;      // dense records with st.global.cs (evict-first) instead of write-back stores
   int dense_coop;    // SaveAt(dense): stage records through shared memory and store them warp-cooperatively (launcher provides the smem)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
@@ -252,8 +253,10 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   constexpr int kDenseK = DENSE_K ? S * D : 0;
   constexpr int kDenseRec = kDenseK + 2 * D;
   constexpr int kDenseStride = kDenseRec | 1;
+  // dynamic shared memory: [VBT descent cache (SDE kernels)] [dense staging records (RICH, SaveAt(dense))]
   extern __shared__ __align__(16) unsigned char dense_smem_raw[];
-  [[maybe_unused]] R *dense_smem = reinterpret_cast<R *>(dense_smem_raw);
+  [[maybe_unused]] R *dense_smem = reinterpret_cast<R *>(dense_smem_raw + p.dense_smem_offset);
+  if constexpr (SDE) bm.attach_cache(reinterpret_cast<R *>(dense_smem_raw), p.vbt);
 
   for (;;) {
     // Finalising a trajectory and claiming + initialising the next one is ~300 instructions that the whole warp

@@ -119,17 +119,32 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
     static const int env_batch = [] { const char *e = getenv("DFX_REFILL_BATCH"); return e ? atoi(e) : 0; }();
     p.refill_batch = env_batch >= 1 ? (env_batch > 32 ? 32 : env_batch) : 2;
   }
+  // SDE kernels: the VBT descent cache (vbt.cuh), as many tree levels as fit ~24 KB per CTA (all of them for C5)
+  p.dense_smem_offset = 0;
+  p.vbt.cache_levels = 0;
+  p.vbt.cache_stride = kBlockThreads;
+  if (LEVY != DFX_LEVY_NONE) {
+    static const int env_cache = [] { const char *e = getenv("DFX_VBT_CACHE"); return e ? atoi(e) : 1; }();
+    const size_t per_level = (size_t)(LEVY == DFX_LEVY_SPACE_TIME ? 7 : 5) * kBlockThreads * sizeof(R);
+    int levels = env_cache ? (int)((24 * 1024) / per_level) : 0;
+    if (levels > p.vbt.depth) levels = p.vbt.depth;
+    if (levels > 32) levels = 32;
+    if (levels >= 2) {
+      p.vbt.cache_levels = levels;
+      smem = ((levels * per_level + 15) / 16) * 16;
+      p.dense_smem_offset = (int)smem;
+    }
+  }
   if (RICH && p.save_dense && (Solver::kInterp == kInterpLinear || p.dense_k != nullptr)) {
     const int kk = Solver::kInterp != kInterpLinear ? Solver::S * Field::kDim : 0;
     const int stride = (kk + 2 * Field::kDim) | 1;
-    smem = (size_t)kBlockThreads * stride * sizeof(R);
-    if (smem <= 100 * 1024) {
+    const size_t rec = (size_t)kBlockThreads * stride * sizeof(R);
+    if (smem + rec <= 100 * 1024) {
       p.dense_coop = 1;
-      if (smem > 48 * 1024) DFX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else {
-      smem = 0;
+      smem += rec;
     }
   }
+  if (smem > 48 * 1024) DFX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   DFX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
   if (per_sm < 1) per_sm = 1;

@@ -20,7 +20,35 @@ struct VbtParams {
   int depth;       // number of descent levels: smallest L with 2^-L <= tol/(t1-t0)
   int levy;        // dfx_levy
   int partitionable;
+  // descent cache (see VbtCache): number of tree levels whose entry state is kept per thread, and the slot stride
+  // (= threads per CTA); 0 levels = no cache.  Filled by the launcher together with the dynamic shared memory size.
+  int cache_levels, cache_stride;
 };
+
+// Descent cache.  _evaluate_leaf is a pure function of (key, r); two queries share every level of the descent on which
+// they branch the same way, and consecutive solver steps query neighbouring times.  Per thread, shared memory keeps the
+// state at the ENTRY of each level of the last descent (key, s, w_s, w_su [, bhh_s, bhh_su]) and the branch taken; a new
+// query replays the cached branches (one load + one compare per level), resumes from the first level where it branches
+// differently, and overwrites the cache from there.  The values are those of a full descent, bit for bit.
+// Layout: slot (level, word) of a thread at base[(level * kWords + word) * stride], base already offset by the thread.
+template <class R, bool STLA> struct VbtCache {
+  static constexpr int kWords = STLA ? 7 : 5;
+  R *base = nullptr;
+  int levels = 0, stride = 0;
+  int n_entry = 0;      // entry states of levels 0 .. n_entry-1 are valid
+  uint32_t path = 0;    // bit j: the cached descent went right at level j (valid for j < n_entry - 1)
+  __device__ __forceinline__ R &slot(int level, int word) const { return base[(level * kWords + word) * stride]; }
+  static __device__ __forceinline__ R from_u32(uint32_t u);
+  static __device__ __forceinline__ uint32_t to_u32(R v);
+};
+template <> __device__ __forceinline__ float VbtCache<float, false>::from_u32(uint32_t u) { return __uint_as_float(u); }
+template <> __device__ __forceinline__ float VbtCache<float, true>::from_u32(uint32_t u) { return __uint_as_float(u); }
+template <> __device__ __forceinline__ double VbtCache<double, false>::from_u32(uint32_t u) { return __longlong_as_double((long long)u); }
+template <> __device__ __forceinline__ double VbtCache<double, true>::from_u32(uint32_t u) { return __longlong_as_double((long long)u); }
+template <> __device__ __forceinline__ uint32_t VbtCache<float, false>::to_u32(float v) { return __float_as_uint(v); }
+template <> __device__ __forceinline__ uint32_t VbtCache<float, true>::to_u32(float v) { return __float_as_uint(v); }
+template <> __device__ __forceinline__ uint32_t VbtCache<double, false>::to_u32(double v) { return (uint32_t)__double_as_longlong(v); }
+template <> __device__ __forceinline__ uint32_t VbtCache<double, true>::to_u32(double v) { return (uint32_t)__double_as_longlong(v); }
 
 // 2^-level as R, exact
 template <class R> __device__ __forceinline__ R pow2_neg(int level);
@@ -33,20 +61,50 @@ template <class R> __device__ __forceinline__ R relu(R x) { return (x != x) ? x 
 
 // tree.py:366-624 with `leaf_key` = split_by_tree(user_key, shape)[0] (tree.py:301)
 template <class R, bool STLA>
-__device__ __forceinline__ LevyVal<R> vbt_evaluate_leaf(Key leaf_key, R r, const VbtParams &vp) {
+__device__ __forceinline__ LevyVal<R> vbt_evaluate_leaf(Key leaf_key, R r, const VbtParams &vp, VbtCache<R, STLA> *cache = nullptr) {
   const bool part = vp.partitionable != 0;
   Key key;
   R w_s = R(0), w_su, bhh_s = R(0), bhh_su = R(0);
-  if constexpr (STLA) {  // state_key, init_key_w, init_key_hh = split(key, 3)
-    key = split_child<3>(leaf_key, 0, part);
-    w_su = random_normal<R>(split_child<3>(leaf_key, 1, part), part);
-    bhh_su = random_normal<R>(split_child<3>(leaf_key, 2, part), part) / R(3.4641016151377544);  // math.sqrt(12)
-  } else {               // state_key, init_key_w = split(key, 2)
-    key = split_child<2>(leaf_key, 0, part);
-    w_su = random_normal<R>(split_child<2>(leaf_key, 1, part), part);
-  }
   R s = R(0);
-  for (int level = 0; level < vp.depth; ++level) {
+  int level0 = 0;
+  const bool use_cache = cache != nullptr && cache->levels > 0;
+  if (use_cache && cache->n_entry > 0) {
+    // replay the cached branches while this query takes the same ones
+    int j = 0;
+    while (j < cache->n_entry - 1) {
+      const R sj = cache->slot(j, 2);
+      const bool right = r > sj + pow2_neg<R>(j + 1);
+      if (right != (((cache->path >> j) & 1u) != 0u)) break;
+      ++j;
+    }
+    level0 = j;
+    key.a = VbtCache<R, STLA>::to_u32(cache->slot(j, 0));
+    key.b = VbtCache<R, STLA>::to_u32(cache->slot(j, 1));
+    s = cache->slot(j, 2);
+    w_s = cache->slot(j, 3);
+    w_su = cache->slot(j, 4);
+    if constexpr (STLA) { bhh_s = cache->slot(j, 5); bhh_su = cache->slot(j, 6); }
+    cache->n_entry = j + 1;
+    cache->path &= (j >= 32) ? 0xFFFFFFFFu : ((1u << j) - 1u);
+  } else {
+    if constexpr (STLA) {  // state_key, init_key_w, init_key_hh = split(key, 3)
+      key = split_child<3>(leaf_key, 0, part);
+      w_su = random_normal<R>(split_child<3>(leaf_key, 1, part), part);
+      bhh_su = random_normal<R>(split_child<3>(leaf_key, 2, part), part) / R(3.4641016151377544);  // math.sqrt(12)
+    } else {               // state_key, init_key_w = split(key, 2)
+      key = split_child<2>(leaf_key, 0, part);
+      w_su = random_normal<R>(split_child<2>(leaf_key, 1, part), part);
+    }
+    if (use_cache) {
+      cache->slot(0, 0) = VbtCache<R, STLA>::from_u32(key.a);
+      cache->slot(0, 1) = VbtCache<R, STLA>::from_u32(key.b);
+      cache->slot(0, 2) = s; cache->slot(0, 3) = w_s; cache->slot(0, 4) = w_su;
+      if constexpr (STLA) { cache->slot(0, 5) = bhh_s; cache->slot(0, 6) = bhh_su; }
+      cache->n_entry = 1;
+      cache->path = 0;
+    }
+  }
+  for (int level = level0; level < vp.depth; ++level) {
     const R su = pow2_neg<R>(level);
     const R st = su / R(2);
     const R t = s + st;
@@ -83,6 +141,15 @@ __device__ __forceinline__ LevyVal<R> vbt_evaluate_leaf(Key leaf_key, R r, const
     if constexpr (STLA) {
       bhh_s = right ? bhh_t : bhh_s;
       bhh_su = right ? bhh_tu : bhh_st;
+    }
+    if (use_cache && level + 1 < cache->levels && level < 32) {  // entry state of level + 1, and the branch just taken
+      const int e = level + 1;
+      cache->slot(e, 0) = VbtCache<R, STLA>::from_u32(key.a);
+      cache->slot(e, 1) = VbtCache<R, STLA>::from_u32(key.b);
+      cache->slot(e, 2) = s; cache->slot(e, 3) = w_s; cache->slot(e, 4) = w_su;
+      if constexpr (STLA) { cache->slot(e, 5) = bhh_s; cache->slot(e, 6) = bhh_su; }
+      cache->n_entry = e + 1;
+      cache->path |= right ? (1u << level) : 0u;
     }
   }
   // tree.py:450-455
@@ -130,8 +197,18 @@ struct BrownianTree {
   R T0, T1, sqrt_len;
   R memo_t[2];
   LevyVal<R> memo_v[2];
+  VbtCache<R, STLA> cache;
+
+  // the descent cache lives in dynamic shared memory: `smem` = the CTA's cache area, this thread uses column threadIdx.x
+  __device__ __forceinline__ void attach_cache(R *smem, const VbtParams &vp) {
+    cache.base = smem + threadIdx.x;
+    cache.levels = vp.cache_levels;
+    cache.stride = vp.cache_stride;
+  }
 
   __device__ __forceinline__ void init(const uint32_t *user_key, const VbtParams &vp) {
+    cache.n_entry = 0;
+    cache.path = 0;
     Key k{user_key[0], user_key[1]};
     leaf = split_child<1>(k, 0, vp.partitionable != 0);  // split_by_tree(key, shape=()) == split(key, 1)[0]
     T0 = (R)vp.t0;
@@ -143,7 +220,7 @@ struct BrownianTree {
   __device__ __forceinline__ LevyVal<R> at(R t, const VbtParams &vp) {
     if (t == memo_t[1]) return memo_v[1];
     if (t == memo_t[0]) return memo_v[0];
-    return vbt_evaluate_leaf<R, STLA>(leaf, linear_rescale(T0, t, T1), vp);
+    return vbt_evaluate_leaf<R, STLA>(leaf, linear_rescale(T0, t, T1), vp, &cache);
   }
 
   // evaluate(ta, tb, use_levy=True): tree.py:326-354 + _levy_diff + _denormalise_bm_inc
