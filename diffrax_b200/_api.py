@@ -83,6 +83,9 @@ class Solution:
     result: Any
     y_final: Any = None
     t_final: Any = None
+    solver_state: Any = None       # [N, 1 + d]: (first_step, carried FSAL derivative); SaveAt(solver_state=True)
+    controller_state: Any = None   # [N, 3]: (prev_inv_scaled_error, prev_prev_inv_scaled_error, at_dtmin); pid.py:388-392
+    made_jump: Any = None          # [N]
 
     def evaluate(self, t0, t1=None, left=True):
         if self.interpolation is None:
@@ -363,15 +366,17 @@ class SaveAt:
     not depend on what is saved, so the values are those of a single solve)."""
 
     def __init__(self, *, t0: bool = False, t1: bool = False, ts=None, steps: Union[bool, int] = False, fn=save_y,
-                 subs=None, dense: bool = False):
+                 subs=None, dense: bool = False, solver_state: bool = False, controller_state: bool = False,
+                 made_jump: bool = False):
         self.dense = bool(dense)
+        self.solver_state, self.controller_state, self.made_jump = bool(solver_state), bool(controller_state), bool(made_jump)
         if subs is None:
             if t0 or t1 or ts is not None or steps:
                 subs = SubSaveAt(t0=t0, t1=t1, ts=ts, steps=steps, fn=fn)
         elif t0 or t1 or ts is not None or steps:
             raise ValueError("Cannot pass both `subs` and any of `t0`, `t1`, `ts`, `steps` to `SaveAt`.")  # _saveat.py:84-92
         self.subs = subs
-        if subs is None and not self.dense:
+        if subs is None and not (self.dense or self.solver_state or self.controller_state or self.made_jump):
             raise ValueError("Empty saveat -- nothing will be saved.")  # _saveat.py:40-48
 
     # the single-SubSaveAt view the descriptor is filled from
@@ -668,6 +673,7 @@ class _MultiSolve:
 
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
                 stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096, throw: bool = True,
+                solver_state=None, controller_state=None, made_jump=None,
                 device: int = 0, hairer_initial_step: bool = False) -> Solution:
     """Batched forward solve == ``jax.vmap(lambda y0: diffrax.diffeqsolve(...))(y0)``
     (_integrate.py:888-1543).
@@ -680,11 +686,13 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = N
     today, a first trial step of 0.01.
     """
     return prepare(terms, solver, t0, t1, dt0, y0, args, saveat=saveat, stepsize_controller=stepsize_controller, event=event,
-                   max_steps=max_steps, device=device, hairer_initial_step=hairer_initial_step)(throw=throw)
+                   max_steps=max_steps, solver_state=solver_state, controller_state=controller_state, made_jump=made_jump,
+                   device=device, hairer_initial_step=hairer_initial_step)(throw=throw)
 
 
 def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
-            stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096, device: int = 0,
+            stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096,
+            solver_state=None, controller_state=None, made_jump=None, device: int = 0,
             hairer_initial_step: bool = False) -> EnsembleSolve:
     """Validate the arguments of a `diffeqsolve` call and allocate its outputs once."""
     if args is not None:
@@ -696,6 +704,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
             raise ValueError("Empty saveat -- nothing will be saved.")
         solves = [prepare(terms, solver, t0, t1, dt0, y0, args, saveat=SaveAt(subs=leaf, dense=saveat.dense and i == 0),
                           stepsize_controller=stepsize_controller, event=event, max_steps=max_steps, device=device,
+                          solver_state=solver_state, controller_state=controller_state, made_jump=made_jump,
                           hairer_initial_step=hairer_initial_step) for i, leaf in enumerate(leaves)]
         return _MultiSolve(saveat.subs, solves)
     ctrl = ConstantStepSize() if stepsize_controller is None else stepsize_controller
@@ -830,6 +839,23 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         D.event_direction = 0 if event.direction is None else (1 if event.direction else 2)
         if event.root_finder is not None:
             D.event_root_find, D.event_rtol, D.event_atol = 1, float(event.root_finder.rtol), float(event.root_finder.atol)
+    # resuming (_integrate.py:1250-1271) / returning (1489-1500) the controller and solver states: one [N, 5 + d] record
+    state_out = None
+    if solver_state is not None or controller_state is not None or made_jump is not None:
+        st_in = xp.empty((n, 5 + d), rdt)
+        st_in[...] = 0
+        flags = 0
+        if controller_state is not None:
+            st_in[:, 0:3] = xp.asarray(controller_state, rdt); flags |= 1
+        if solver_state is not None:
+            st_in[:, 4:] = xp.asarray(solver_state, rdt); flags |= 2
+        if made_jump is not None:
+            st_in[:, 3] = xp.asarray(made_jump, rdt); flags |= 4
+        keep_alive.append(st_in)
+        D.state_in, D.state_in_flags = xp.ptr(st_in), flags
+    if saveat.solver_state or saveat.controller_state or saveat.made_jump:
+        state_out = xp.empty((n, 5 + d), rdt)
+        D.state_out = xp.ptr(state_out)
     T = L.dfx_out_size(C.byref(D))
     i32 = xp.int32()
     ts_out = xp.empty((n, T), rdt)
@@ -880,5 +906,9 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     call._host_device = device
     call._fn = saveat.fn
     call._solution = Solution(t0=t0, t1=t1, ts=ts_out, ys=ys_out, interpolation=interpolation, stats=stats_d,
-                              result=result, y_final=y_final, t_final=t_final)
+                              result=result, y_final=y_final, t_final=t_final,
+                              solver_state=state_out[:, 4:] if (state_out is not None and saveat.solver_state) else None,
+                              controller_state=state_out[:, 0:3] if (state_out is not None and saveat.controller_state) else None,
+                              made_jump=(state_out[:, 3] != 0) if (state_out is not None and saveat.made_jump) else None)
+    call._keep.append(state_out)
     return call

@@ -54,6 +54,7 @@ class SolveDesc(C.Structure):
         ("event_kind", C.c_int32), ("event_direction", C.c_int32), ("event_root_find", C.c_int32),
         ("event_params", C.c_void_p), ("n_event_params", C.c_int32),
         ("event_rtol", C.c_double), ("event_atol", C.c_double),
+        ("state_in", C.c_void_p), ("state_in_flags", C.c_int32), ("state_out", C.c_void_p),
     ]
 
 

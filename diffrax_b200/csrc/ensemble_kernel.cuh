@@ -91,6 +91,7 @@ struct SolveParams {
   int event_kind, event_dir, event_root;
   R ev_w[4], ev_b, ev_wt, ev_rtol, ev_atol;  // affine: w, b, wt; steady state: ev_rtol / ev_atol; root finder: ev_rtol / ev_atol
   R ev_ss_rtol, ev_ss_atol;
+  const R *state_in; R *state_out; int state_in_flags;  // resumed / returned controller + solver state, [N, 5 + d] (EXTRA only)
   int refill_batch;  // finished lanes wait until this many can be finalised + refilled in one pass (>= 1)
   int dense_smem_offset;  // bytes of dynamic shared memory in front of the dense staging records (the VBT descent cache)
   int dense_cs;      // dense records with st.global.cs (evict-first) instead of write-back stores
@@ -309,6 +310,18 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           for (int c = 0; c < D; ++c) p.y_final[idx * D + c] = y[c];
         }
         if (p.t_final) p.t_final[idx] = tprev * direction;
+        if constexpr (EXTRA) {
+          if (p.state_out != nullptr) {
+            R *so = p.state_out + idx * (5 + D);
+            so[0] = pid_inv; so[1] = pid_prev_inv; so[2] = at_dtmin ? R(1) : R(0); so[3] = made_jump ? R(1) : R(0);
+            // first_step stays True only while no step has been kept (runge_kutta.py:1199-1200 sets it False on a kept step)
+            bool first = FSAL && num_accepted == 0;
+            if (first && p.state_in != nullptr && (p.state_in_flags & 2)) first = p.state_in[idx * (5 + D) + 4] != R(0);
+            so[4] = first ? R(1) : R(0);
+#pragma unroll
+            for (int c = 0; c < D; ++c) so[5 + c] = FSAL ? f_fsal[c] : R(0);
+          }
+        }
         active = false;
       }
       if constexpr (RICH) {
@@ -387,6 +400,19 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             // runge_kutta.py:684-695: the first step evaluates stage 0 at (t0, y0); a rejected first
             // step re-evaluates the same point, so computing it once here is value-identical.
             Field::template eval<R>(fp, t0 * direction, y, f_fsal);
+          }
+          if constexpr (EXTRA) {  // resumed states (_integrate.py:1250-1271)
+            if (p.state_in != nullptr) {
+              const R *si = p.state_in + idx * (5 + D);
+              if (p.state_in_flags & 1) { pid_inv = si[0]; pid_prev_inv = si[1]; at_dtmin = si[2] != R(0); }
+              if (p.state_in_flags & 4) made_jump = si[3] != R(0);
+              if constexpr (FSAL) {
+                if ((p.state_in_flags & 2) && si[4] == R(0)) {  // (first_step == True means "evaluate", which was just done)
+#pragma unroll
+                  for (int c = 0; c < D; ++c) f_fsal[c] = si[5 + c];
+                }
+              }
+            }
           }
           if constexpr (TAB && !SDE && EXTRA) {  // (the launcher routes hairer solves to the EXTRA instantiation)
             if (p.hairer && !p.has_dt0 && p.controller == DFX_CTRL_PID) {

@@ -72,6 +72,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   p.dense_vec_ok = (((uintptr_t)d->dense_y0 | (uintptr_t)d->dense_y1 | (uintptr_t)d->dense_k) & 31u) == 0;
   p.y_final = (R *)d->y_final; p.t_final = (R *)d->t_final;
   p.keys = d->bm_keys;
+  p.state_in = (const R *)d->state_in; p.state_out = (R *)d->state_out; p.state_in_flags = d->state_in_flags;
   p.event_kind = d->event_kind; p.event_dir = d->event_direction; p.event_root = d->event_root_find;
   for (int c = 0; c < 4; ++c) p.ev_w[c] = R(0);
   p.ev_b = p.ev_wt = p.ev_ss_rtol = p.ev_ss_atol = R(0);
@@ -170,7 +171,8 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
   // EXTRA: ClipStepSizeController / Hairer starting step / Event; RICH: any SaveAt mode beyond t1 (EXTRA implies RICH)
-  const bool extra = (d->hairer_initial_step && std::isnan(d->dt0)) || d->step_ts || d->jump_ts || d->event_kind != DFX_EVENT_NONE;
+  const bool extra = (d->hairer_initial_step && std::isnan(d->dt0)) || d->step_ts || d->jump_ts || d->event_kind != DFX_EVENT_NONE ||
+                     d->state_in || d->state_out;
   const bool rich = extra || d->save_t0 || d->save_ts || d->save_steps || d->save_dense;
 
   // scratch: the work-queue counter.  (The +inf padding of unfilled output slots is written by the solve kernel itself

@@ -144,6 +144,14 @@ typedef struct dfx_solve_desc {
   int32_t event_kind, event_direction, event_root_find;
   const double *event_params; int32_t n_event_params; /* host */
   double event_rtol, event_atol;
+
+  /* Resuming a solve: diffeqsolve(..., solver_state=, controller_state=, made_jump=) and SaveAt(solver_state=True,
+   * controller_state=True, made_jump=True) (_integrate.py:1250-1271, 1489-1500).  One record per trajectory, [N, 5 + d]:
+   *   [0] prev_inv_scaled_error  [1] prev_prev_inv_scaled_error  [2] at_dtmin   (PIDController state, pid.py:388-392)
+   *   [3] made_jump   [4] first_step   [5 ..] the carried FSAL derivative       (solver state, runge_kutta.py:415-444)
+   * state_in_flags: bit 0 controller_state passed, bit 1 solver_state passed, bit 2 made_jump passed. */
+  const void *state_in; int32_t state_in_flags;
+  void *state_out;
 } dfx_solve_desc;
 
 /* ---- library ---- */

@@ -62,6 +62,7 @@ class Desc(C.Structure):
         ("event_kind", C.c_int32), ("event_direction", C.c_int32), ("event_root_find", C.c_int32),
         ("event_params", C.c_void_p), ("n_event_params", C.c_int32),
         ("event_rtol", C.c_double), ("event_atol", C.c_double),
+        ("state_in", C.c_void_p), ("state_in_flags", C.c_int32), ("state_out", C.c_void_p),
         ("trace_traj", C.c_int64), ("trace", C.c_void_p),
         ("num_threads", C.c_int32),
     ]
@@ -167,7 +168,8 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
           save_dense=False, max_steps=4096, levy_area=None, keys=None, bm_t0=0.0, bm_t1=1.0,
           bm_tol=1e-3, partitionable=True, callback=None, trace_traj=None, num_threads=0,
           t0_per_traj=None, t1_per_traj=None, step_ts=None, jump_ts=None,
-          event=None, event_params=(), event_direction=None, event_root=None):
+          event=None, event_params=(), event_direction=None, event_root=None,
+          state_in=None, state_in_flags=7, save_state=False):
     """Run the oracle on a batch.  Mirrors one vmapped diffeqsolve call of the reference."""
     L = lib()
     dt = np.dtype(dtype)
@@ -248,6 +250,13 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
         D.event_direction = 0 if event_direction is None else (1 if event_direction else 2)
         if event_root is not None:
             D.event_root_find, D.event_rtol, D.event_atol = 1, float(event_root[0]), float(event_root[1])
+    state_out = None
+    if state_in is not None:
+        state_in = np.ascontiguousarray(state_in, dt)
+        D.state_in, D.state_in_flags = _ptr(state_in), int(state_in_flags)
+    if save_state:
+        state_out = np.empty((n, 5 + d), dt)
+        D.state_out = _ptr(state_out)
     trace = None
     if trace_traj is not None:
         trace = np.full((max_steps, 3), np.nan)
@@ -259,6 +268,8 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
     out = dict(ts=ts_out, ys=ys_out, stats=stats, result=result, y_final=y_final, t_final=t_final)
     if dense is not None:
         out["dense"] = dense
+    if state_out is not None:
+        out["state"] = state_out
     if trace is not None:
         out["trace"] = trace[: stats[trace_traj, 0]]
     return out

@@ -543,6 +543,41 @@ def test_events_steady_state_and_results(dev):
                         event=dfx.Event(dfx.steady_state_event()))
 
 
+def test_resume_with_solver_and_controller_state(dev):
+    """diffeqsolve(..., solver_state=, controller_state=, made_jump=) + SaveAt(solver_state=True, controller_state=True,
+    made_jump=True) (_integrate.py:1250-1271, 1489-1500): a PI-controlled solve split at t = 1 and resumed with the saved
+    states; the PID history changes the first factors of the second leg, so resuming is observable."""
+    rng = np.random.default_rng(4)
+    n = 128
+    y0 = rng.uniform(-2, 2, (n, 2))
+    okw = dict(solver="tsit5", params=[1.0, 0.7, 2.0], rtol=1e-7, atol=1e-9, pcoeff=0.3, icoeff=0.4)
+    term, ctrl = dfx.ODETerm(dfx.fields.ForcedOscillator(1.0, 0.7, 2.0)), dfx.PIDController(rtol=1e-7, atol=1e-9, pcoeff=0.3, icoeff=0.4)
+    save = dfx.SaveAt(t1=True, solver_state=True, controller_state=True, made_jump=True)
+    a = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 1.0, 0.05, torch.tensor(y0, device=dev), saveat=save, stepsize_controller=ctrl)
+    oa = oracle.solve("forced_osc", y0, 0.0, 1.0, 0.05, save_state=True, **okw)
+    same = np.all(stats_np(a) == oa["stats"], axis=1)
+    assert same.mean() > 0.97
+    assert a.controller_state.shape == (n, 3) and a.solver_state.shape == (n, 3) and a.made_jump.shape == (n,)
+    # inverse scaled errors: 1 / (an error estimate); the clipped last step to t1 can be tiny, its estimate rounding noise
+    cs, ocs = to_np(a.controller_state)[same][:, :2], oa["state"][same, 0:2]
+    rel = np.abs(cs - ocs) / np.abs(ocs)
+    assert np.median(rel) < 1e-6 and rel.max() < 0.1, (np.median(rel), rel.max())
+    assert np.array_equal(to_np(a.controller_state)[:, 2], oa["state"][:, 2])
+    assert relerr(to_np(a.solver_state)[same], oa["state"][same, 4:]) < 1e-9
+    assert not bool(a.made_jump.any())
+    y1 = a.ys[:, -1]
+    b = dfx.diffeqsolve(term, dfx.Tsit5(), 1.0, 2.0, 0.05, y1, saveat=save, stepsize_controller=ctrl,
+                        solver_state=a.solver_state, controller_state=a.controller_state, made_jump=a.made_jump)
+    # the oracle resumed from the GPU's own states and end point: the second leg alone is compared
+    st_in = np.zeros((n, 7)); st_in[:, 0:3] = to_np(a.controller_state); st_in[:, 4:] = to_np(a.solver_state)
+    ob = oracle.solve("forced_osc", to_np(y1), 1.0, 2.0, 0.05, state_in=st_in, save_state=True, **okw)
+    same_b = np.all(stats_np(b) == ob["stats"], axis=1)
+    assert same_b.mean() > 0.97
+    assert relerr(to_np(b.ys)[same_b], ob["ys"][same_b]) < 1e-10
+    fresh = dfx.diffeqsolve(term, dfx.Tsit5(), 1.0, 2.0, 0.05, y1, saveat=save, stepsize_controller=ctrl)
+    assert not torch.equal(fresh.stats["num_steps"], b.stats["num_steps"]) or not torch.equal(fresh.ys, b.ys)   # the history matters
+
+
 def test_hairer_initial_step_flag(dev):
     """K2: the starting-step algorithm of pid.py:51-81 behind a flag; default is the constant 0.01 the reference uses."""
     rng = np.random.default_rng(9)
