@@ -643,6 +643,9 @@ class EnsembleSolve:
             if bool(bad.any()):
                 code = int(sol.result[bad][0])
                 raise RuntimeError(RESULTS._messages.get(code, f"solver failed with code {code}"))  # _integrate.py:1541-1542
+        mj = getattr(self, "_made_jump_src", None)
+        if mj is not None:
+            sol = dataclasses.replace(sol, made_jump=(mj != 0))
         fn = getattr(self, "_fn", save_y)
         if fn is not save_y:  # SubSaveAt.fn, applied to every saved slot at once (see SubSaveAt)
             ts, ys = sol.ts, sol.ys
@@ -909,6 +912,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
                               result=result, y_final=y_final, t_final=t_final,
                               solver_state=state_out[:, 4:] if (state_out is not None and saveat.solver_state) else None,
                               controller_state=state_out[:, 0:3] if (state_out is not None and saveat.controller_state) else None,
-                              made_jump=(state_out[:, 3] != 0) if (state_out is not None and saveat.made_jump) else None)
+                              made_jump=None)   # filled in after the solve (it is a comparison, not a view)
+    call._made_jump_src = state_out[:, 3] if (state_out is not None and saveat.made_jump) else None
     call._keep.append(state_out)
     return call

@@ -173,6 +173,23 @@ __device__ __forceinline__ float pos_min_bits(float a, float b) { return fminf(a
 // streaming (evict-first) stores for write-once outputs
 __device__ __forceinline__ void st_cs(double *p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(float *p, float v) { __stcs(p, v); }
+// 32 bytes (STG.E.256, new on sm_100) of one value / of four or eight given values; p must be 32-byte aligned
+__device__ __forceinline__ void st32B_fill_cs(double *p, double v) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %1, %1, %1};" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st32B_fill_cs(float *p, float v) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st32B(double *p, const double *v, bool cs) {  // v: 4 values (shared memory, 16-byte aligned)
+  const double2 a = *reinterpret_cast<const double2 *>(v), b = *reinterpret_cast<const double2 *>(v + 2);
+  if (cs) asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+  else asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+__device__ __forceinline__ void st32B(float *p, const float *v, bool cs) {    // v: 8 values
+  const float4 a = *reinterpret_cast<const float4 *>(v), b = *reinterpret_cast<const float4 *>(v + 4);
+  if (cs) asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+  else asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 
 // Store a register-resident row of N values with the widest vector store its size allows: 256-bit
 // (STG.E.256, new on sm_100), 128-bit, else scalar.  `vec_ok` says the destination rows are 32-byte aligned

@@ -94,6 +94,7 @@ struct SolveParams {
   const R *state_in; R *state_out; int state_in_flags;  // resumed / returned controller + solver state, [N, 5 + d] (EXTRA only)
   int refill_batch;  // finished lanes wait until this many can be finalised + refilled in one pass (>= 1)
   int dense_smem_offset;  // bytes of dynamic shared memory in front of the dense staging records (the VBT descent cache)
+  int pad_vec, flush_vec;  // 32-byte stores for the +inf padding / the dense record flush
   int dense_cs;      // dense records with st.global.cs (evict-first) instead of write-back stores
   int dense_coop;    // SaveAt(dense): stage records through shared memory and store them warp-cooperatively (launcher provides the smem)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
@@ -134,8 +135,24 @@ constexpr int min_blocks_per_sm() {
 }
 
 // +inf into row[start, len), one warp, coalesced streaming stores
-template <class R> __device__ __forceinline__ void pad_tail(R *row, long long start, long long len, int lane) {
-  for (long long i = start + lane; i < len; i += 32) st_cs(&row[i], Num<R>::inf());
+template <class R> __device__ __forceinline__ void pad_tail(R *row, long long start, long long len, int lane, bool vec = true) {
+  if (!vec) {
+    for (long long i = start + lane; i < len; i += 32) st_cs(&row[i], Num<R>::inf());
+    return;
+  }
+  constexpr int VW = 32 / (int)sizeof(R);  // elements per 32-byte store
+  R *q = row + start;
+  long long n = len - start;
+  if (n <= 0) return;
+  long long head = (long long)(((32u - (unsigned)((uintptr_t)q & 31u)) & 31u) / sizeof(R));  // up to the 32-byte boundary
+  if (head > n) head = n;
+  if (lane < head) st_cs(q + lane, Num<R>::inf());
+  q += head;
+  n -= head;
+  const long long nvec = n / VW;
+  for (long long i = lane; i < nvec; i += 32) st32B_fill_cs(q + i * VW, Num<R>::inf());  // 1 KB per warp instruction
+  const long long done = nvec * VW;
+  if (done + lane < n) st_cs(q + done + lane, Num<R>::inf());
 }
 
 // Claim the next trajectory for every lane of the warp that needs one: one atomic per warp.
@@ -253,7 +270,15 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   // SaveAt(dense=True) staging: one record of kDenseRec values per lane, padded to an odd stride (conflict-free reads)
   constexpr int kDenseK = DENSE_K ? S * D : 0;
   constexpr int kDenseRec = kDenseK + 2 * D;
-  constexpr int kDenseStride = kDenseRec | 1;
+  // 32-byte chunk path: every piece of the record (k, y0, y1) is a whole number of 32-byte vectors, so a lane moves one
+  // vector (2 x LDS.128 + 1 x STG.256) and a half / quarter warp moves a whole record
+  constexpr int kVW = 32 / (int)sizeof(R);
+  constexpr bool kDenseVec = (D % kVW == 0) && (kDenseK % kVW == 0) && (kDenseRec / kVW <= 16);
+  constexpr int kDenseChunks = kDenseRec / kVW;                                      // vectors per record
+  constexpr int kDenseGroup = kDenseChunks <= 4 ? 4 : (kDenseChunks <= 8 ? 8 : 16);  // lanes per record
+  // staging stride per lane: odd (conflict-free 64-bit accesses) for the scalar path; for the chunk path a multiple of 16
+  // bytes whose half is odd (records stay 16-byte aligned, per-lane element writes are 2-way conflicted at worst)
+  constexpr int kDenseStride = kDenseVec ? (((kDenseRec * (int)sizeof(R) + 15) / 16) | 1) * 16 / (int)sizeof(R) : (kDenseRec | 1);
   // dynamic shared memory: [VBT descent cache (SDE kernels)] [dense staging records (RICH, SaveAt(dense))]
   extern __shared__ __align__(16) unsigned char dense_smem_raw[];
   [[maybe_unused]] R *dense_smem = reinterpret_cast<R *>(dense_smem_raw + p.dense_smem_offset);
@@ -337,15 +362,15 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             const long long r = __shfl_sync(kFullMask, idx_i, src);
             if (pad_saves) {
               const long long sc = __shfl_sync(kFullMask, save_index, src);
-              pad_tail(p.ts_out + r * p.out_size, sc, (long long)p.out_size, lane);
-              pad_tail(p.ys_out + r * p.out_size * D, sc * D, (long long)p.out_size * D, lane);
+              pad_tail(p.ts_out + r * p.out_size, sc, (long long)p.out_size, lane, p.pad_vec != 0);
+              pad_tail(p.ys_out + r * p.out_size * D, sc * D, (long long)p.out_size * D, lane, p.pad_vec != 0);
             }
             if (p.save_dense) {
               const long long dc = __shfl_sync(kFullMask, dense_index, src), ms = p.max_steps;
-              pad_tail(p.dense_ts + r * (ms + 1), dc + 1, ms + 1, lane);
-              pad_tail(p.dense_y0 + r * ms * D, dc * D, ms * D, lane);
-              pad_tail(p.dense_y1 + r * ms * D, dc * D, ms * D, lane);
-              if (DENSE_K && p.dense_k != nullptr) pad_tail(p.dense_k + r * ms * (S * D), dc * (S * D), ms * (S * D), lane);
+              pad_tail(p.dense_ts + r * (ms + 1), dc + 1, ms + 1, lane, p.pad_vec != 0);
+              pad_tail(p.dense_y0 + r * ms * D, dc * D, ms * D, lane, p.pad_vec != 0);
+              pad_tail(p.dense_y1 + r * ms * D, dc * D, ms * D, lane, p.pad_vec != 0);
+              if (DENSE_K && p.dense_k != nullptr) pad_tail(p.dense_k + r * ms * (S * D), dc * (S * D), ms * (S * D), lane, p.pad_vec != 0);
             }
           }
         }
@@ -896,6 +921,30 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           __syncwarp();
           const int lane = threadIdx.x & 31;
           const R *wrec = dense_smem + (threadIdx.x >> 5) * 32 * kDenseStride;
+          if (kDenseVec && p.dense_vec_ok && p.flush_vec) {
+            // kDenseGroup lanes per record, 32 / kDenseGroup records per pass: lane (g, q) moves vector q of the g-th
+            // staged record of this pass
+            const int q = lane & (kDenseGroup - 1), g = lane / kDenseGroup;
+            unsigned m = staged;
+            while (m) {
+              int src = -1;
+#pragma unroll
+              for (int gg = 0; gg < 32 / kDenseGroup; ++gg) {  // hand the next 32 / kDenseGroup staged lanes to the groups
+                const int s_ = m ? __ffs(m) - 1 : -1;
+                if (m) m &= m - 1;
+                if (gg == g) src = s_;
+              }
+              const long long row = __shfl_sync(kFullMask, dense_row, src < 0 ? 0 : src);
+              if (src >= 0 && q < kDenseChunks) {
+                const R *v = wrec + src * kDenseStride + q * kVW;
+                R *dst;
+                if (q < kDenseK / kVW) dst = p.dense_k + row * kDenseK + q * kVW;
+                else if (q < (kDenseK + D) / kVW) dst = p.dense_y0 + row * D + (q * kVW - kDenseK);
+                else dst = p.dense_y1 + row * D + (q * kVW - kDenseK - D);
+                st32B(dst, v, p.dense_cs != 0);
+              }
+            }
+          } else
           for (unsigned m = staged; m; m &= m - 1) {
             const int src = __ffs(m) - 1;
             const long long row = __shfl_sync(kFullMask, dense_row, src);

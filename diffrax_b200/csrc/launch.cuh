@@ -113,6 +113,12 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
     // the partial sectors out one by one (C3: 27.1 ms vs 25.7 ms).  DFX_DENSE_CS=1 selects the streaming stores.
     static const int env_cs = [] { const char *e = getenv("DFX_DENSE_CS"); return e ? atoi(e) : 0; }();
     p.dense_cs = env_cs;
+    // measured on C3 (ms): scalar pad + scalar flush 26.2, scalar pad + 32-byte flush 24.6, 32-byte pad + scalar flush 28.0,
+    // both 32-byte 26.9 - the record flush gains from moving a record with half a warp, while 1 KB-per-instruction padding
+    // bursts from the finalising warp crowd out the other warps' record stores
+    static const int env_pv = [] { const char *e = getenv("DFX_PAD_VEC"); return e ? atoi(e) : 0; }();
+    static const int env_fv = [] { const char *e = getenv("DFX_FLUSH_VEC"); return e ? atoi(e) : 1; }();
+    p.pad_vec = env_pv; p.flush_vec = env_fv;
   }
   {
     // finalize/refill batching (ensemble_kernel.cuh): 2 is within a few percent of the optimum sqrt(2048 X / (n I)) for
@@ -138,7 +144,10 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
   }
   if (RICH && p.save_dense && (Solver::kInterp == kInterpLinear || p.dense_k != nullptr)) {
     const int kk = Solver::kInterp != kInterpLinear ? Solver::S * Field::kDim : 0;
-    const int stride = (kk + 2 * Field::kDim) | 1;
+    // must match kDenseStride in ensemble_kernel.cuh
+    const int rec_n = kk + 2 * Field::kDim, vw = 32 / (int)sizeof(R);
+    const bool vec = (Field::kDim % vw == 0) && (kk % vw == 0) && (rec_n / vw <= 16);
+    const int stride = vec ? (((rec_n * (int)sizeof(R) + 15) / 16) | 1) * 16 / (int)sizeof(R) : (rec_n | 1);
     const size_t rec = (size_t)kBlockThreads * stride * sizeof(R);
     if (smem + rec <= 100 * 1024) {
       p.dense_coop = 1;
