@@ -197,7 +197,19 @@ __device__ __forceinline__ void st32B(float *p, const float *v, bool cs) {    //
 // A lane writing a contiguous row with 256-bit stores covers whole 32-byte sectors by itself, so the L2 sees
 // full-sector writes even though neighbouring lanes write to different trajectories' rows.
 template <int N>
-__device__ __forceinline__ void store_row(double *dst, const double (&v)[N], bool vec_ok) {
+__device__ __forceinline__ void store_row(double *dst, const double (&v)[N], bool vec_ok, bool cs = true) {
+  if (!cs) {  // write-back stores (dense records: L2 merges neighbouring steps)
+    if (vec_ok && N % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < N; i += 4)
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "d"(v[i]), "d"(v[i + 1 < N ? i + 1 : i]),
+                     "d"(v[i + 2 < N ? i + 2 : i]), "d"(v[i + 3 < N ? i + 3 : i]) : "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) dst[i] = v[i];
+    }
+    return;
+  }
   if (vec_ok && N % 4 == 0) {
 #pragma unroll
     for (int i = 0; i < N; i += 4)
@@ -213,7 +225,12 @@ __device__ __forceinline__ void store_row(double *dst, const double (&v)[N], boo
   }
 }
 template <int N>
-__device__ __forceinline__ void store_row(float *dst, const float (&v)[N], bool vec_ok) {
+__device__ __forceinline__ void store_row(float *dst, const float (&v)[N], bool vec_ok, bool cs = true) {
+  if (!cs) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = v[i];
+    return;
+  }
   if (vec_ok && N % 8 == 0) {
 #pragma unroll
     for (int i = 0; i < N; i += 8)

@@ -875,8 +875,8 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               for (int c = 0; c < D; ++c) { rec[kDenseK + c] = y[c]; rec[kDenseK + D + c] = y1_dense[c]; }
               dense_row = row;
             } else {
-              store_row<D>(&p.dense_y0[row * D], y, p.dense_vec_ok != 0);
-              store_row<D>(&p.dense_y1[row * D], y1_dense, p.dense_vec_ok != 0);
+              store_row<D>(&p.dense_y0[row * D], y, p.dense_vec_ok != 0, p.dense_cs != 0);
+              store_row<D>(&p.dense_y1[row * D], y1_dense, p.dense_vec_ok != 0, p.dense_cs != 0);
               if constexpr (DENSE_K) {
                 if (p.dense_k != nullptr) {
                   R flat[S * D];
@@ -884,7 +884,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
                   for (int j = 0; j < S; ++j)
 #pragma unroll
                     for (int c = 0; c < D; ++c) flat[j * D + c] = k[j][c];
-                  store_row<S * D>(&p.dense_k[row * (S * D)], flat, p.dense_vec_ok != 0);
+                  store_row<S * D>(&p.dense_k[row * (S * D)], flat, p.dense_vec_ok != 0, p.dense_cs != 0);
                 }
               }
             }

@@ -149,7 +149,8 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
     const bool vec = (Field::kDim % vw == 0) && (kk % vw == 0) && (rec_n / vw <= 16);
     const int stride = vec ? (((rec_n * (int)sizeof(R) + 15) / 16) | 1) * 16 / (int)sizeof(R) : (rec_n | 1);
     const size_t rec = (size_t)kBlockThreads * stride * sizeof(R);
-    if (smem + rec <= 100 * 1024) {
+    static const int env_coop = [] { const char *e = getenv("DFX_DENSE_COOP"); return e ? atoi(e) : 1; }();
+    if (smem + rec <= 100 * 1024 && env_coop) {
       p.dense_coop = 1;
       smem += rec;
     }
