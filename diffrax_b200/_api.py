@@ -56,7 +56,13 @@ class RESULTS:
         2: "The minimum step size was reached in the differential equation solver.",
         3: "Terminating differential equation solve because an event occurred.",
         4: "The root finder locating the event time did not converge.",
+        5: "Maximum number of rejected steps was reached. Consider increasing "
+           "`diffrax.ClipStepSizeController(store_rejected_steps==...)`.",
+        6: "An internal error occurred in Diffrax. This is a bug! Please open a GitHub issue with a minimum working example. "
+           "(<50 lines of code is ideal)",
     }
+    max_steps_rejected = 5
+    internal_error = 6
 
 
 def is_successful(result):
@@ -238,14 +244,16 @@ class PIDController:
 class ClipStepSizeController:
     """clip.py:120-428: wraps an adaptive controller so that the solver steps exactly to `step_ts` and steps
     around `jump_ts` (to the float just before, resuming from the float just after; FSAL solvers re-evaluate
-    their carried derivative).  `store_rejected_steps` is not implemented."""
+    their carried derivative).  `store_rejected_steps=K` keeps a stack of K rejected step ends per trajectory that later
+    steps are clipped to (clip.py:398-424; for adaptive SDE solves with Levy area)."""
 
     def __init__(self, controller, step_ts=None, jump_ts=None, store_rejected_steps=None):
         if not isinstance(controller, PIDController):
             raise ValueError("Can only apply `ClipStepSizeController` to adaptive step size controllers, "
                              f"but got {controller}.")  # clip.py:203-207
-        if store_rejected_steps is not None:
-            raise NotImplementedError("store_rejected_steps is not implemented by the ensemble kernels")
+        if store_rejected_steps is not None and int(store_rejected_steps) < 1:
+            raise ValueError("store_rejected_steps must be None or a positive integer")
+        self.store_rejected_steps = None if store_rejected_steps is None else int(store_rejected_steps)
         self.controller = controller
         self.step_ts = None if step_ts is None else np.sort(np.asarray(step_ts, np.float64).reshape(-1))  # clip.py:209
         self.jump_ts = None if jump_ts is None else np.sort(np.asarray(jump_ts, np.float64).reshape(-1))
@@ -773,6 +781,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
                 keep_alive.append(a)
                 setattr(D, name, xp.ptr(a))
                 setattr(D, "n_" + name, int(a.shape[0]))
+        D.store_rejected_steps = ctrl.store_rejected_steps or 0
         ctrl = ctrl.controller
     if isinstance(ctrl, PIDController):
         D.controller = _lib.CTRL_PID

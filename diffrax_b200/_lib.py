@@ -41,6 +41,7 @@ class SolveDesc(C.Structure):
         ("error_order", C.c_double),
         ("hairer_initial_step", C.c_int32),
         ("step_ts", C.c_void_p), ("n_step_ts", C.c_int32), ("jump_ts", C.c_void_p), ("n_jump_ts", C.c_int32),
+        ("store_rejected_steps", C.c_int32),
         ("save_t0", C.c_int32), ("save_t1", C.c_int32), ("save_steps", C.c_int32), ("save_dense", C.c_int32),
         ("save_ts", C.c_void_p), ("n_save_ts", C.c_int32), ("max_steps", C.c_int32),
         ("ts_out", C.c_void_p), ("ys_out", C.c_void_p), ("stats", C.c_void_p), ("result", C.c_void_p),

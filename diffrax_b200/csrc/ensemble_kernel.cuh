@@ -77,6 +77,7 @@ struct SolveParams {
   int use_c1, use_c2, use_c3;
   const R *step_ts, *jump_ts;  // ClipStepSizeController (clip.py): sorted, user time; RICH instantiation only
   int n_step_ts, n_jump_ts;
+  R *reject_ts; int n_reject;  // store_rejected_steps: per-trajectory stack of rejected step ends, [N, n_reject] scratch (EXTRA only)
   int hairer;    // dt0 == None: use the Hairer starting step of pid.py:51-81 instead of the constant 0.01
   R inv_error_order;
   int fast_pid;  // pcoeff == dcoeff == 0, icoeff == 1 and error_order == solver order: pure I-controller fast path
@@ -241,6 +242,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   int save_index = 0, saveat_ts_index = 0, dense_index = 0;
   [[maybe_unused]] int step_index = 0, jump_index = 0;  // ClipStepSizeController state (RICH only)
   [[maybe_unused]] bool made_jump = false;
+  [[maybe_unused]] int reject_index = 0;  // ClipStepSizeController(store_rejected_steps=K): top of the stack, K = empty
   [[maybe_unused]] R event_value = R(0);  // Event: cond_fn at the previous state (RICH only)
   BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME> bm;
 #pragma unroll
@@ -406,6 +408,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           tnext = t0 + dt0;
           if constexpr (EXTRA) {  // ClipStepSizeController.init, clip.py:246-302
             made_jump = false;
+            reject_index = p.n_reject;  // clip.py:292-299
             if (p.step_ts != nullptr) {
               step_index = clip_find_idx(t0, p.step_ts, p.n_step_ts, 0, direction);  // searchsorted(side="right")
               tnext = jnp_min(clip_get_t(p.step_ts, p.n_step_ts, step_index, direction), tnext);
@@ -761,6 +764,17 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             next_t1 = jnp_max(next_after_up(next_t0), next_t1);
             jump_index = clip_find_idx(next_t0, p.jump_ts, p.n_jump_ts, jump_index, direction);
             next_t1 = jnp_min(prev_n<R>(clip_get_t(p.jump_ts, p.n_jump_ts, jump_index, direction), 1), next_t1);
+          }
+          if (p.reject_ts != nullptr) {  // clip.py:398-424 (t1 there is the attempted step's end st1)
+            R *rts = p.reject_ts + idx * (long long)p.n_reject;
+            const R rejected_t = (reject_index == p.n_reject) ? Num<R>::inf() : rts[reject_index];
+            if (st1 > rejected_t && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_INTERNAL_ERROR;
+            reject_index += (st1 == rejected_t) ? 1 : 0;
+            reject_index -= keep ? 0 : 1;
+            if (reject_index < 0 && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_MAX_STEPS_REJECTED;
+            if (reject_index >= 0 && reject_index < p.n_reject && !keep) rts[reject_index] = st1;
+            const R clip_to = (reject_index >= p.n_reject) ? Num<R>::inf() : rts[reject_index < 0 ? p.n_reject - 1 : reject_index];
+            next_t1 = jnp_min(clip_to, next_t1);
           }
           if (keep) made_jump = ctrl_made_jump;  // _integrate.py:425
         }

@@ -72,6 +72,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   p.dense_vec_ok = (((uintptr_t)d->dense_y0 | (uintptr_t)d->dense_y1 | (uintptr_t)d->dense_k) & 31u) == 0;
   p.y_final = (R *)d->y_final; p.t_final = (R *)d->t_final;
   p.keys = d->bm_keys;
+  p.reject_ts = nullptr; p.n_reject = d->store_rejected_steps > 0 ? d->store_rejected_steps : 0;
   p.state_in = (const R *)d->state_in; p.state_out = (R *)d->state_out; p.state_in_flags = d->state_in_flags;
   p.event_kind = d->event_kind; p.event_dir = d->event_direction; p.event_root = d->event_root_find;
   for (int c = 0; c < 4; ++c) p.ev_w[c] = R(0);
@@ -182,17 +183,19 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   if (p.n_traj == 0) return 0;
   // EXTRA: ClipStepSizeController / Hairer starting step / Event; RICH: any SaveAt mode beyond t1 (EXTRA implies RICH)
   const bool extra = (d->hairer_initial_step && std::isnan(d->dt0)) || d->step_ts || d->jump_ts || d->event_kind != DFX_EVENT_NONE ||
-                     d->state_in || d->state_out;
+                     d->state_in || d->state_out || d->store_rejected_steps > 0;
   const bool rich = extra || d->save_t0 || d->save_ts || d->save_steps || d->save_dense;
 
   // scratch: the work-queue counter.  (The +inf padding of unfilled output slots is written by the solve kernel itself
   // when it finalises a trajectory, so there is no second pass over the buffers.)
   unsigned long long *counter = nullptr;
   char *scratch = nullptr;
-  DFX_CUDA_OK(cudaMallocAsync((void **)&scratch, 16, stream));
+  const size_t reject_bytes = p.n_reject > 0 ? (size_t)p.n_traj * p.n_reject * sizeof(R) : 0;  // rejected-times stacks
+  DFX_CUDA_OK(cudaMallocAsync((void **)&scratch, 16 + reject_bytes, stream));
   DFX_CUDA_OK(cudaMemsetAsync(scratch, 0, 16, stream));
   counter = (unsigned long long *)scratch;
   p.work_counter = counter;
+  if (reject_bytes) p.reject_ts = (R *)(scratch + 16);
 
   int rc;
   if (extra) rc = launch_variant<R, Field, Solver, LEVY, true, true>(p, fp, stream);

@@ -54,7 +54,8 @@ enum dfx_levy { DFX_LEVY_NONE = 0, DFX_LEVY_BROWNIAN_INCREMENT = 1, DFX_LEVY_SPA
  * (test/test_saveat_solution.py:21). */
 enum dfx_result { DFX_RESULT_SUCCESSFUL = 0, DFX_RESULT_MAX_STEPS_REACHED = 1,
                   DFX_RESULT_DT_MIN_REACHED = 2, DFX_RESULT_EVENT_OCCURRED = 3 /* not a failure: _solution.py:52-62 is_okay */,
-                  DFX_RESULT_EVENT_ROOT_FIND_FAILED = 4 };
+                  DFX_RESULT_EVENT_ROOT_FIND_FAILED = 4, DFX_RESULT_MAX_STEPS_REJECTED = 5 /* _solution.py:24-27 */,
+                  DFX_RESULT_INTERNAL_ERROR = 6 };
 enum dfx_event { DFX_EVENT_NONE = 0, DFX_EVENT_AFFINE = 1, DFX_EVENT_STEADY_STATE = 2 };
 
 enum dfx_error { DFX_OK = 0, DFX_ERR_BAD_ARGUMENT = -1, DFX_ERR_UNSUPPORTED = -2,
@@ -97,12 +98,13 @@ typedef struct dfx_solve_desc {
 
   /* ClipStepSizeController(controller, step_ts, jump_ts) (_step_size_controller/clip.py:120-428; also
    * PIDController(step_ts=, jump_ts=), pid.py:88-97): times that must be stepped to exactly / stepped around.
-   * Sorted ascending, user time, time dtype; shared by all trajectories; NULL when unused.
-   * store_rejected_steps is not implemented. */
+   * Sorted ascending, user time, time dtype; shared by all trajectories; NULL when unused. */
   const void *step_ts;
   int32_t n_step_ts;
   const void *jump_ts;
   int32_t n_jump_ts;
+  int32_t store_rejected_steps;    /* 0 = None; else the length of the rejected-times stack: rejected step ends are
+                                    * revisited by later steps (clip.py:292-299, 398-424) */
 
   /* saveat (_saveat.py:22-26, 72-76) and max_steps (_integrate.py:904) */
   int32_t save_t0, save_t1, save_steps, save_dense;

@@ -49,7 +49,7 @@ class Desc(C.Structure):
         ("force_dtmin", C.c_int32),
         ("error_order", C.c_double),
         ("hairer_initial_step", C.c_int32),
-        ("step_ts", C.c_void_p), ("n_step_ts", C.c_int32), ("jump_ts", C.c_void_p), ("n_jump_ts", C.c_int32),
+        ("step_ts", C.c_void_p), ("n_step_ts", C.c_int32), ("jump_ts", C.c_void_p), ("n_jump_ts", C.c_int32), ("store_rejected_steps", C.c_int32),
         ("save_t0", C.c_int32), ("save_t1", C.c_int32), ("save_steps", C.c_int32), ("save_dense", C.c_int32),
         ("save_ts", C.c_void_p), ("n_save_ts", C.c_int32), ("max_steps", C.c_int32),
         ("out_size", C.c_int32),
@@ -169,7 +169,7 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
           bm_tol=1e-3, partitionable=True, callback=None, trace_traj=None, num_threads=0,
           t0_per_traj=None, t1_per_traj=None, step_ts=None, jump_ts=None,
           event=None, event_params=(), event_direction=None, event_root=None,
-          state_in=None, state_in_flags=7, save_state=False):
+          state_in=None, state_in_flags=7, save_state=False, store_rejected_steps=None):
     """Run the oracle on a batch.  Mirrors one vmapped diffeqsolve call of the reference."""
     L = lib()
     dt = np.dtype(dtype)
@@ -250,6 +250,7 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
         D.event_direction = 0 if event_direction is None else (1 if event_direction else 2)
         if event_root is not None:
             D.event_root_find, D.event_rtol, D.event_atol = 1, float(event_root[0]), float(event_root[1])
+    D.store_rejected_steps = 0 if store_rejected_steps is None else int(store_rejected_steps)
     state_out = None
     if state_in is not None:
         state_in = np.ascontiguousarray(state_in, dt)

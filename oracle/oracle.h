@@ -41,7 +41,8 @@ enum { ORC_FIELD_DECAY = 0, ORC_FIELD_LOTKA_VOLTERRA = 1, ORC_FIELD_LORENZ = 2,
 /* Brownian levy_area kind */
 enum { ORC_LEVY_NONE = 0, ORC_LEVY_BROWNIAN_INCREMENT = 1, ORC_LEVY_SPACE_TIME = 2 };
 /* RESULTS (_solution.py:13-31; only successful == 0 is pinned by the reference tests) */
-enum { ORC_OK = 0, ORC_MAX_STEPS_REACHED = 1, ORC_DT_MIN_REACHED = 2, ORC_EVENT_OCCURRED = 3, ORC_EVENT_ROOT_FIND_FAILED = 4 };
+enum { ORC_OK = 0, ORC_MAX_STEPS_REACHED = 1, ORC_DT_MIN_REACHED = 2, ORC_EVENT_OCCURRED = 3, ORC_EVENT_ROOT_FIND_FAILED = 4,
+       ORC_MAX_STEPS_REJECTED = 5, ORC_INTERNAL_ERROR = 6 };
 
 /* generic user vector field (ctypes callback): out[d] = f(t, y[d]) in double */
 typedef void (*orc_callback_vf)(double t, const double *y, double *out, int dim);
@@ -69,6 +70,7 @@ typedef struct orc_desc {
   /* ClipStepSizeController(controller, step_ts, jump_ts) (clip.py:120-428); sorted ascending, user time */
   const void *step_ts; int32_t n_step_ts;
   const void *jump_ts; int32_t n_jump_ts;
+  int32_t store_rejected_steps; /* 0 = None; else the length of the rejected-times stack (clip.py:292-299, 398-424) */
   /* SaveAt (_saveat.py:22-26,72-76) */
   int32_t save_t0, save_t1, save_steps, save_dense;
   const void *save_ts;       /* [T] REAL or NULL */

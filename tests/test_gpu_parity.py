@@ -578,6 +578,29 @@ def test_resume_with_solver_and_controller_state(dev):
     assert not torch.equal(fresh.stats["num_steps"], b.stats["num_steps"]) or not torch.equal(fresh.ys, b.ys)   # the history matters
 
 
+def test_clip_store_rejected_steps(dev):
+    """ClipStepSizeController(store_rejected_steps=K) (clip.py:292-299, 398-424) on a deterministic problem: the kernel's
+    rejected-times stack walks the same step sequence as the oracle's, and an overflowing stack reports max_steps_rejected."""
+    rng = np.random.default_rng(6)
+    n = 200
+    y0 = rng.uniform(-2, 2, (n, 2))
+    okw = dict(solver="bosh3", params=[1.0, 0.7, 2.0], rtol=1e-5, atol=1e-7, save_t1=True, save_steps=1, max_steps=4096)
+    term = dfx.ODETerm(dfx.fields.ForcedOscillator(1.0, 0.7, 2.0))
+    for K, dt0 in ((16, 1.5), (1, 5.0)):
+        o = oracle.solve("forced_osc", y0, 0.0, 6.0, dt0, store_rejected_steps=K, **okw)
+        ctrl = dfx.ClipStepSizeController(dfx.PIDController(rtol=1e-5, atol=1e-7), store_rejected_steps=K)
+        sol = dfx.diffeqsolve(term, dfx.Bosh3(), 0.0, 6.0, dt0, torch.tensor(y0, device=dev), saveat=dfx.SaveAt(t1=True, steps=True),
+                              stepsize_controller=ctrl, max_steps=4096, throw=False)
+        res = to_np(sol.result)
+        same = np.all(stats_np(sol) == o["stats"], axis=1) & (res == o["result"])
+        assert same.mean() > 0.97, same.mean()
+        assert relerr(to_np(sol.ts)[same], o["ts"][same]) < 1e-6 and relerr(to_np(sol.ys)[same], o["ys"][same]) < 1e-5
+        if K == 1:
+            assert (res == dfx.RESULTS.max_steps_rejected).any() and np.array_equal(res == 5, o["result"] == 5)
+        else:
+            assert (res == 0).all() and (stats_np(sol)[:, 2] > 0).any()
+
+
 def test_hairer_initial_step_flag(dev):
     """K2: the starting-step algorithm of pid.py:51-81 behind a flag; default is the constant 0.01 the reference uses."""
     rng = np.random.default_rng(9)

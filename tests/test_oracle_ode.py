@@ -321,3 +321,25 @@ def test_event_bouncing_ball_docstring():
                       event="steady_state", event_params=[0.0, 1e-3])
     assert r3["result"][0] == 3 and math.log(1000) <= r3["ts"][0, 0] < math.log(1000) + 1.0
     assert abs(r3["ys"][0, 0, 0]) < 1e-3
+
+
+def test_store_rejected_steps_revisits_rejected_times():
+    """ClipStepSizeController(store_rejected_steps=K), clip.py:292-299, 398-424: the end of every rejected step is pushed
+    on a stack and later steps are clipped to it, so each rejected time is eventually the end of an accepted step; a
+    stack that overflows ends the solve with RESULTS.max_steps_rejected."""
+    y0 = np.array([[1.0, 0.5], [-0.3, 1.2], [2.0, -1.0]])
+    kw = dict(solver="bosh3", params=[1.0, 0.7, 2.0], rtol=1e-5, atol=1e-7, save_t1=False, save_steps=1, max_steps=4096)
+    for traj in range(3):
+        r = oracle.solve("forced_osc", y0, 0.0, 6.0, 1.5, store_rejected_steps=16, trace_traj=traj, **kw)
+        assert r["result"][traj] == 0
+        tr = r["trace"]
+        rej = [row[1] for row in tr if row[2] == 0]
+        acc = [row[1] for row in tr if row[2] == 1]
+        assert len(rej) >= 1
+        assert all(any(x == t for x in acc) for t in rej)          # revisited exactly
+    plain = oracle.solve("forced_osc", y0, 0.0, 6.0, 1.5, **kw)
+    withstack = oracle.solve("forced_osc", y0, 0.0, 6.0, 1.5, store_rejected_steps=16, **kw)
+    assert np.all(withstack["stats"][:, 1] >= plain["stats"][:, 1])  # clipping to old rejected times costs steps
+    # a one-slot stack overflows as soon as two rejections are pending
+    small = oracle.solve("forced_osc", y0, 0.0, 6.0, 5.0, store_rejected_steps=1, **kw)
+    assert np.any(small["result"] == 5)                             # max_steps_rejected
