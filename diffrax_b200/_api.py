@@ -331,18 +331,36 @@ class Newton:
 
 
 class Event:
-    """_event.py:13-118: `Event(cond_fn, root_finder=None, direction=None)` with ONE registered condition function."""
+    """_event.py:13-118: `Event(cond_fn, root_finder=None, direction=None)`.  `cond_fn` is a registered condition functor
+    (AffineEvent, steady_state_event(...)) or a list / tuple / dict of up to 4 of them (the flattened PyTree; the first
+    one that triggers on a step decides, _integrate.py:619-626); `direction` is None / bool or a matching structure."""
 
-    def __init__(self, cond_fn, root_finder: Optional[Newton] = None, direction: Optional[bool] = None):
-        if not isinstance(cond_fn, (AffineEvent, SteadyStateEvent)):
-            raise TypeError("Event(cond_fn): cond_fn must be an AffineEvent or steady_state_event(...) "
-                            "(condition functions are registered device functors; PyTrees of them are not supported)")
-        if direction not in (None, False, True):
+    def __init__(self, cond_fn, root_finder: Optional[Newton] = None, direction=None):
+        def flat(x):
+            if isinstance(x, dict):
+                return [v for k in sorted(x) for v in flat(x[k])]     # jax flattens dicts by sorted key
+            if isinstance(x, (list, tuple)):
+                return [v for e in x for v in flat(e)]
+            return [x]
+        conds = flat(cond_fn)
+        if not conds or not all(isinstance(c, (AffineEvent, SteadyStateEvent)) for c in conds):
+            raise TypeError("Event(cond_fn): cond_fn must be an AffineEvent / steady_state_event(...) or a list / tuple / dict "
+                            "of them (condition functions are registered device functors)")
+        if len(conds) > _lib.MAX_EVENTS:
+            raise NotImplementedError(f"at most {_lib.MAX_EVENTS} condition functions per Event")
+        if direction in (None, False, True):
+            dirs = [direction] * len(conds)
+        else:
+            dirs = flat(direction)
+            if len(dirs) != len(conds):
+                raise ValueError("Missmatch in the structure of `cond_fn` and `direction`.")  # _event.py:40-41
+        if any(d not in (None, False, True) for d in dirs):
             raise ValueError("`direction` must be a `None`, `bool`, or a PyTree of `None | bool`s "
                              "with the same structure as `cond_fn`.")  # _event.py:43-47
         if root_finder is not None and not isinstance(root_finder, Newton):
             raise TypeError("Event(root_finder=...) must be None or diffrax_b200.Newton(rtol, atol)")
         self.cond_fn, self.root_finder, self.direction = cond_fn, root_finder, direction
+        self._conds, self._dirs = conds, dirs
 
 
 def save_y(t, y, args):
@@ -845,10 +863,12 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         raise ValueError("ShARK requires MultiTerm(ODETerm(drift), ControlTerm(diffusion, VirtualBrownianTree))")
 
     if event is not None:
-        ev_params = np.ascontiguousarray(event.cond_fn.params(d, ctrl), np.float64)
+        ev_params = np.ascontiguousarray(np.concatenate([np.asarray(c.params(d, ctrl), np.float64) for c in event._conds]))
         keep_alive.append(ev_params)
-        D.event_kind, D.event_params, D.n_event_params = event.cond_fn.kind, ev_params.ctypes.data, ev_params.size
-        D.event_direction = 0 if event.direction is None else (1 if event.direction else 2)
+        D.n_events, D.event_params, D.n_event_params = len(event._conds), ev_params.ctypes.data, ev_params.size
+        for i, (c, dr) in enumerate(zip(event._conds, event._dirs)):
+            D.event_kind[i] = c.kind
+            D.event_direction[i] = 0 if dr is None else (1 if dr else 2)
         if event.root_finder is not None:
             D.event_root_find, D.event_rtol, D.event_atol = 1, float(event.root_finder.rtol), float(event.root_finder.atol)
     # resuming (_integrate.py:1250-1271) / returning (1489-1500) the controller and solver states: one [N, 5 + d] record

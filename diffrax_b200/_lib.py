@@ -16,6 +16,7 @@ F64, F32 = 0, 1
 CTRL_CONSTANT, CTRL_PID = 0, 1
 LEVY_NONE, LEVY_BI, LEVY_STLA = 0, 1, 2
 EVENT_NONE, EVENT_AFFINE, EVENT_STEADY_STATE = 0, 1, 2
+MAX_EVENTS = 4
 SOLVER_IDS = {"tsit5": 0, "dopri5": 1, "dopri8": 2, "heun": 3, "bosh3": 4, "midpoint": 5,
               "ralston": 6, "euler": 7, "shark": 8}
 HALF_SOLVER = 0x100  # DFX_HALF_SOLVER: HalfSolver(inner) = HALF_SOLVER | inner id
@@ -52,7 +53,8 @@ class SolveDesc(C.Structure):
         ("levy_area", C.c_int32), ("bm_keys", C.c_void_p),
         ("bm_t0", C.c_double), ("bm_t1", C.c_double), ("bm_tol", C.c_double),
         ("threefry_partitionable", C.c_int32),
-        ("event_kind", C.c_int32), ("event_direction", C.c_int32), ("event_root_find", C.c_int32),
+        ("n_events", C.c_int32), ("event_kind", C.c_int32 * 4), ("event_direction", C.c_int32 * 4),
+        ("event_root_find", C.c_int32),
         ("event_params", C.c_void_p), ("n_event_params", C.c_int32),
         ("event_rtol", C.c_double), ("event_atol", C.c_double),
         ("state_in", C.c_void_p), ("state_in_flags", C.c_int32), ("state_out", C.c_void_p),

@@ -325,10 +325,18 @@ static int check_desc(const dfx_solve_desc *d) {
     set_error("Must have (t1 - t0) * dt0 >= 0");  // _integrate.py:1036-1045
     return DFX_ERR_BAD_ARGUMENT;
   }
-  if (d->event_kind != DFX_EVENT_NONE) {
-    const int need = d->event_kind == DFX_EVENT_AFFINE ? d->dim + 2 : (d->event_kind == DFX_EVENT_STEADY_STATE ? 2 : -1);
-    if (need < 0 || !d->event_params || d->n_event_params != need || d->dim > 4 || d->event_direction < 0 || d->event_direction > 2) {
-      set_error("bad event: kind %d needs %d event_params (got %d), dim <= 4, direction in {0,1,2}", d->event_kind, need, d->n_event_params);
+  if (d->n_events != 0) {
+    int need = 0;
+    bool ok = d->n_events > 0 && d->n_events <= DFX_MAX_EVENTS && d->dim <= 4 && d->event_params != nullptr;
+    for (int i = 0; ok && i < d->n_events; ++i) {
+      if (d->event_kind[i] == DFX_EVENT_AFFINE) need += d->dim + 2;
+      else if (d->event_kind[i] == DFX_EVENT_STEADY_STATE) need += 2;
+      else ok = false;
+      if (d->event_direction[i] < 0 || d->event_direction[i] > 2) ok = false;
+    }
+    if (!ok || d->n_event_params != need) {
+      set_error("bad event description: 1..%d events of kind affine (dim + 2 params) / steady state (2 params), dim <= 4, "
+                "direction in {0,1,2}; got %d events, %d params (need %d)", DFX_MAX_EVENTS, d->n_events, d->n_event_params, need);
       return DFX_ERR_BAD_ARGUMENT;
     }
   }

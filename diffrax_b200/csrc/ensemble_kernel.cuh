@@ -89,9 +89,10 @@ struct SolveParams {
   R *dense_ts, *dense_y0, *dense_y1, *dense_k;
   int *dense_count;
   // Event (RICH instantiation only): kind, direction (0 any / 1 up / 2 down), Newton root find on the local interpolant
-  int event_kind, event_dir, event_root;
-  R ev_w[4], ev_b, ev_wt, ev_rtol, ev_atol;  // affine: w, b, wt; steady state: ev_rtol / ev_atol; root finder: ev_rtol / ev_atol
-  R ev_ss_rtol, ev_ss_atol;
+  int n_events, event_kind[DFX_MAX_EVENTS], event_dir[DFX_MAX_EVENTS], event_root;
+  R ev_w[DFX_MAX_EVENTS][4], ev_b[DFX_MAX_EVENTS], ev_wt[DFX_MAX_EVENTS];  // affine: w . y + wt t + b
+  R ev_ss_rtol[DFX_MAX_EVENTS], ev_ss_atol[DFX_MAX_EVENTS];               // steady state
+  R ev_rtol, ev_atol;                                                     // Newton root finder
   const R *state_in; R *state_out; int state_in_flags;  // resumed / returned controller + solver state, [N, 5 + d] (EXTRA only)
   int refill_batch;  // finished lanes wait until this many can be finalised + refilled in one pass (>= 1)
   int dense_smem_offset;  // bytes of dynamic shared memory in front of the dense staging records (the VBT descent cache)
@@ -243,7 +244,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   [[maybe_unused]] int step_index = 0, jump_index = 0;  // ClipStepSizeController state (RICH only)
   [[maybe_unused]] bool made_jump = false;
   [[maybe_unused]] int reject_index = 0;  // ClipStepSizeController(store_rejected_steps=K): top of the stack, K = empty
-  [[maybe_unused]] R event_value = R(0);  // Event: cond_fn at the previous state (RICH only)
+  [[maybe_unused]] R event_value[DFX_MAX_EVENTS] = {};  // Event: the cond_fns at the previous state (EXTRA only)
   BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME> bm;
 #pragma unroll
   for (int c = 0; c < D; ++c) { y[c] = R(0); f_fsal[c] = R(0); }
@@ -251,12 +252,12 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   const R sqrt_d = (R)sqrt((double)D);
 
   // Event condition (see dfx_solve_desc): affine  w . y + wt t + b,  or steady state  rms(f) < atol + rtol rms(y)  (1 = True)
-  [[maybe_unused]] auto event_cond = [&](R t, const R (&yy)[D], R dir) -> R {
-    if (p.event_kind == DFX_EVENT_AFFINE) {
+  [[maybe_unused]] auto event_cond = [&](int i, R t, const R (&yy)[D], R dir) -> R {
+    if (p.event_kind[i] == DFX_EVENT_AFFINE) {
       R v = R(0);
 #pragma unroll
-      for (int c = 0; c < D; ++c) v += p.ev_w[c < 4 ? c : 3] * yy[c];
-      return v + p.ev_wt * t + p.ev_b;
+      for (int c = 0; c < D; ++c) v += p.ev_w[i][c < 4 ? c : 3] * yy[c];
+      return v + p.ev_wt[i] * t + p.ev_b[i];
     }
     R f[D], nf = R(0), ny = R(0);
     Field::template eval<R>(fp, t * dir, yy, f);
@@ -266,7 +267,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
       for (int c = 0; c < D; ++c) { nf += f[c] * f[c]; ny += yy[c] * yy[c]; }
       nf = r_sqrt(nf) / sqrt_d; ny = r_sqrt(ny) / sqrt_d;
     }
-    return (nf < p.ev_ss_atol + p.ev_ss_rtol * ny) ? R(1) : R(0);
+    return (nf < p.ev_ss_atol[i] + p.ev_ss_rtol[i] * ny) ? R(1) : R(0);
   };
 
   // SaveAt(dense=True) staging: one record of kDenseRec values per lane, padded to an odd stride (conflict-free reads)
@@ -315,7 +316,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           if (p.save_steps == 1) via_steps = true;
           else if (p.save_steps > 1) via_steps = (num_accepted % p.save_steps) == 0;
           // 862-872: with an event root finder the final value is (re)written whenever steps would have saved it
-          const bool ev_rule = EXTRA && p.event_kind != DFX_EVENT_NONE && p.event_root;
+          const bool ev_rule = EXTRA && p.n_events != 0 && p.event_root;
           const bool pred = ev_rule ? (p.save_t1 || via_steps) : (p.save_t1 && !via_steps);
           if (pred && save_index < p.out_size) {
             const long long o = idx * (long long)p.out_size + save_index;
@@ -487,7 +488,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             }
           }
           if constexpr (EXTRA) {
-            if (p.event_kind != DFX_EVENT_NONE) event_value = event_cond(tprev, y, direction);  // _integrate.py:1432-1476
+            for (int i = 0; i < p.n_events; ++i) event_value[i] = event_cond(i, tprev, y, direction);  // _integrate.py:1432-1476
           }
           active = true;
         }
@@ -795,25 +796,31 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         [[maybe_unused]] R t_event = tprev_new;
         [[maybe_unused]] R y_event[D];
         if constexpr (EXTRA) {
-          if (p.event_kind != DFX_EVENT_NONE) {
+          if (p.n_events != 0) {
             R ynew[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) ynew[c] = keep ? y1[c] : y[c];
-            const R nv = event_cond(tprev_new, ynew, direction);
-            const int so = (event_value > R(0)) - (event_value < R(0)), sn = (nv > R(0)) - (nv < R(0));
-            bool m;
-            if (p.event_kind == DFX_EVENT_STEADY_STATE) m = nv != R(0);
-            else if (p.event_dir == 0) m = so != sn;
-            else if (p.event_dir == 1) m = (so <= 0) && (sn > 0);
-            else m = (so > 0) && (sn <= 0);
-            event_value = nv;
+            // every condition is re-evaluated; the first one (in PyTree order) that triggers decides (619-626)
+            bool m = false;
+            int which = 0;
+            for (int i = 0; i < p.n_events; ++i) {
+              const R nv = event_cond(i, tprev_new, ynew, direction);
+              const int so = (event_value[i] > R(0)) - (event_value[i] < R(0)), sn = (nv > R(0)) - (nv < R(0));
+              bool mi;
+              if (p.event_kind[i] == DFX_EVENT_STEADY_STATE) mi = nv != R(0);
+              else if (p.event_dir[i] == 0) mi = so != sn;
+              else if (p.event_dir[i] == 1) mi = (so <= 0) && (sn > 0);
+              else mi = (so > 0) && (sn <= 0);
+              event_value[i] = nv;
+              if (mi && !m) { m = true; which = i; }
+            }
             if (m) {
               ev_hit = true;
               result = DFX_RESULT_EVENT_OCCURRED;
               if (p.event_root) {
                 R tf = st1;
                 bool ok = true;
-                if (p.event_kind == DFX_EVENT_AFFINE) {
+                if (p.event_kind[which] == DFX_EVENT_AFFINE) {
                   // [EXT] optimistix.Newton(rtol, atol), options lower / upper = the step, y0 = its end, max_steps 256:
                   // clipped Newton steps; Cauchy termination on the iterate and on the function value
                   auto along = [&](R t, R &g, R &dg) {
@@ -822,9 +829,9 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
                     interp_deriv<INTERP, R, S, D>(st0, st1, y, y1_dense, k, t, dq);
                     R v = R(0), dv = R(0);
 #pragma unroll
-                    for (int c = 0; c < D; ++c) { v += p.ev_w[c < 4 ? c : 3] * yq[c]; dv += p.ev_w[c < 4 ? c : 3] * dq[c]; }
-                    g = v + p.ev_wt * t + p.ev_b;
-                    dg = dv + p.ev_wt;
+                    for (int c = 0; c < D; ++c) { v += p.ev_w[which][c < 4 ? c : 3] * yq[c]; dv += p.ev_w[which][c < 4 ? c : 3] * dq[c]; }
+                    g = v + p.ev_wt[which] * t + p.ev_b[which];
+                    dg = dv + p.ev_wt[which];
                   };
                   R g, dg;
                   along(tf, g, dg);

@@ -14,7 +14,7 @@ using F = MlpField<4, 128>;
 template <class Solver>
 int launch_mlp(const dfx_solve_desc *d, void *stream_v) {
   const bool rich = d->save_t0 || d->save_ts || d->save_steps || d->save_dense || d->step_ts || d->jump_ts ||
-                    d->hairer_initial_step || d->event_kind != DFX_EVENT_NONE || d->state_in || d->state_out || d->store_rejected_steps > 0;
+                    d->hairer_initial_step || d->n_events != 0 || d->state_in || d->state_out || d->store_rejected_steps > 0;
   const char *no_tc = std::getenv("DFX_MLP_NO_TC");
   if (rich || !IsTableau<Solver>::value || (no_tc && no_tc[0] == '1')) return launch_solve<float, F, Solver, 0>(d, stream_v);
   if constexpr (IsTableau<Solver>::value) {

@@ -74,15 +74,25 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   p.keys = d->bm_keys;
   p.reject_ts = nullptr; p.n_reject = d->store_rejected_steps > 0 ? d->store_rejected_steps : 0;
   p.state_in = (const R *)d->state_in; p.state_out = (R *)d->state_out; p.state_in_flags = d->state_in_flags;
-  p.event_kind = d->event_kind; p.event_dir = d->event_direction; p.event_root = d->event_root_find;
-  for (int c = 0; c < 4; ++c) p.ev_w[c] = R(0);
-  p.ev_b = p.ev_wt = p.ev_ss_rtol = p.ev_ss_atol = R(0);
+  p.n_events = d->n_events; p.event_root = d->event_root_find;
   p.ev_rtol = (R)d->event_rtol; p.ev_atol = (R)d->event_atol;
-  if (d->event_kind == DFX_EVENT_AFFINE) {
-    for (int c = 0; c < d->dim && c < 4; ++c) p.ev_w[c] = (R)d->event_params[c];
-    p.ev_b = (R)d->event_params[d->dim]; p.ev_wt = (R)d->event_params[d->dim + 1];
-  } else if (d->event_kind == DFX_EVENT_STEADY_STATE) {
-    p.ev_ss_rtol = (R)d->event_params[0]; p.ev_ss_atol = (R)d->event_params[1];
+  {
+    int off = 0;
+    for (int i = 0; i < DFX_MAX_EVENTS; ++i) {
+      p.event_kind[i] = DFX_EVENT_NONE; p.event_dir[i] = 0;
+      for (int c = 0; c < 4; ++c) p.ev_w[i][c] = R(0);
+      p.ev_b[i] = p.ev_wt[i] = p.ev_ss_rtol[i] = p.ev_ss_atol[i] = R(0);
+      if (i >= d->n_events) continue;
+      p.event_kind[i] = d->event_kind[i]; p.event_dir[i] = d->event_direction[i];
+      if (d->event_kind[i] == DFX_EVENT_AFFINE) {
+        for (int c = 0; c < d->dim && c < 4; ++c) p.ev_w[i][c] = (R)d->event_params[off + c];
+        p.ev_b[i] = (R)d->event_params[off + d->dim]; p.ev_wt[i] = (R)d->event_params[off + d->dim + 1];
+        off += d->dim + 2;
+      } else if (d->event_kind[i] == DFX_EVENT_STEADY_STATE) {
+        p.ev_ss_rtol[i] = (R)d->event_params[off]; p.ev_ss_atol[i] = (R)d->event_params[off + 1];
+        off += 2;
+      }
+    }
   }
   if (sde) {
     p.vbt.t0 = d->bm_t0; p.vbt.t1 = d->bm_t1;
@@ -182,7 +192,7 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
   // EXTRA: ClipStepSizeController / Hairer starting step / Event; RICH: any SaveAt mode beyond t1 (EXTRA implies RICH)
-  const bool extra = (d->hairer_initial_step && std::isnan(d->dt0)) || d->step_ts || d->jump_ts || d->event_kind != DFX_EVENT_NONE ||
+  const bool extra = (d->hairer_initial_step && std::isnan(d->dt0)) || d->step_ts || d->jump_ts || d->n_events != 0 ||
                      d->state_in || d->state_out || d->store_rejected_steps > 0;
   const bool rich = extra || d->save_t0 || d->save_ts || d->save_steps || d->save_dense;
 

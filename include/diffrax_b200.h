@@ -57,6 +57,7 @@ enum dfx_result { DFX_RESULT_SUCCESSFUL = 0, DFX_RESULT_MAX_STEPS_REACHED = 1,
                   DFX_RESULT_EVENT_ROOT_FIND_FAILED = 4, DFX_RESULT_MAX_STEPS_REJECTED = 5 /* _solution.py:24-27 */,
                   DFX_RESULT_INTERNAL_ERROR = 6 };
 enum dfx_event { DFX_EVENT_NONE = 0, DFX_EVENT_AFFINE = 1, DFX_EVENT_STEADY_STATE = 2 };
+#define DFX_MAX_EVENTS 4
 
 enum dfx_error { DFX_OK = 0, DFX_ERR_BAD_ARGUMENT = -1, DFX_ERR_UNSUPPORTED = -2,
                  DFX_ERR_CUDA = -3, DFX_ERR_NO_DEVICE = -4 };
@@ -136,14 +137,18 @@ typedef struct dfx_solve_desc {
   int32_t threefry_partitionable; /* jax_threefry_partitionable (default True since JAX 0.5) */
 
   /* Event(cond_fn, root_finder, direction): _event.py:13-118, _integrate.py:542-633 (detection), 691-821 (root find, unsave).
-   * One registered condition function, evaluated in the solver's (direction-normalised) time like the reference's
+   * Up to DFX_MAX_EVENTS registered condition functions (the flattened PyTree `cond_fn`; the first one that triggers on a
+   * step wins, _integrate.py:619-626), evaluated in the solver's (direction-normalised) time like the reference's
    * cond_fn(tprev, y, ...):
-   *   DFX_EVENT_AFFINE        c(t, y) = w . y + wt * t + b        event_params = [w[0..d), b, wt]  real-valued: sign change
-   *   DFX_EVENT_STEADY_STATE  rms(f(t, y)) < atol + rtol * rms(y)  event_params = [rtol, atol]      boolean (_event.py:120-170)
-   * event_direction: 0 = None (any crossing), 1 = True (upcrossing), 2 = False (downcrossing).
+   *   DFX_EVENT_AFFINE        c(t, y) = w . y + wt * t + b        params [w[0..d), b, wt]  real-valued: sign change
+   *   DFX_EVENT_STEADY_STATE  rms(f(t, y)) < atol + rtol * rms(y)  params [rtol, atol]      boolean (_event.py:120-170)
+   * event_params holds the parameters of event 0, 1, ... back to back (host doubles).
+   * event_direction[i]: 0 = None (any crossing), 1 = True (upcrossing), 2 = False (downcrossing).
    * event_root_find: 0 = root_finder None (the solve ends at the end of the triggering step); 1 = Newton(event_rtol,
    *   event_atol) on the step's local interpolant, bracketed to the step, saved values after the event time removed. */
-  int32_t event_kind, event_direction, event_root_find;
+  int32_t n_events;                                 /* 0 = no event */
+  int32_t event_kind[4], event_direction[4];        /* DFX_MAX_EVENTS == 4 */
+  int32_t event_root_find;
   const double *event_params; int32_t n_event_params; /* host */
   double event_rtol, event_atol;
 

@@ -59,7 +59,8 @@ class Desc(C.Structure):
         ("levy_area", C.c_int32), ("bm_keys", C.c_void_p),
         ("bm_t0", C.c_double), ("bm_t1", C.c_double), ("bm_tol", C.c_double),
         ("threefry_partitionable", C.c_int32),
-        ("event_kind", C.c_int32), ("event_direction", C.c_int32), ("event_root_find", C.c_int32),
+        ("n_events", C.c_int32), ("event_kind", C.c_int32 * 4), ("event_direction", C.c_int32 * 4),
+        ("event_root_find", C.c_int32),
         ("event_params", C.c_void_p), ("n_event_params", C.c_int32),
         ("event_rtol", C.c_double), ("event_atol", C.c_double),
         ("state_in", C.c_void_p), ("state_in_flags", C.c_int32), ("state_out", C.c_void_p),
@@ -242,12 +243,18 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
     D.bm_t0, D.bm_t1, D.bm_tol = float(bm_t0), float(bm_t1), float(bm_tol)
     D.threefry_partitionable = int(partitionable)
     if event is not None:
-        # event: "affine" (params w[0..d), b, wt) or "steady_state" (params rtol, atol); event_direction None / True / False;
+        # event: "affine" (params w[0..d), b, wt) or "steady_state" (params rtol, atol) - or lists of them (then event_params
+        # is a list of parameter lists and event_direction a list); event_direction None / True / False;
         # event_root: None or (rtol, atol) of the Newton root finder
-        D.event_kind = {"affine": 1, "steady_state": 2}[event]
-        ev_params = np.ascontiguousarray(event_params, np.float64)
+        kinds = [event] if isinstance(event, str) else list(event)
+        plist = [event_params] if isinstance(event, str) else list(event_params)
+        dirs = [event_direction] * len(kinds) if not isinstance(event_direction, (list, tuple)) else list(event_direction)
+        D.n_events = len(kinds)
+        for i, (k_, d_) in enumerate(zip(kinds, dirs)):
+            D.event_kind[i] = {"affine": 1, "steady_state": 2}[k_]
+            D.event_direction[i] = 0 if d_ is None else (1 if d_ else 2)
+        ev_params = np.ascontiguousarray(np.concatenate([np.asarray(p_, np.float64).ravel() for p_ in plist]), np.float64)
         D.event_params, D.n_event_params = _ptr(ev_params), ev_params.size
-        D.event_direction = 0 if event_direction is None else (1 if event_direction else 2)
         if event_root is not None:
             D.event_root_find, D.event_rtol, D.event_atol = 1, float(event_root[0]), float(event_root[1])
     D.store_rejected_steps = 0 if store_rejected_steps is None else int(store_rejected_steps)

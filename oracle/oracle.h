@@ -101,8 +101,10 @@ typedef struct orc_desc {
    * event_root_find: 0 = root_finder None; 1 = Newton(event_rtol, event_atol) on the local interpolant, bracketed to the
    *   triggering step ([EXT] optimistix.Newton, restated from its published algorithm: clipped Newton steps from the step's
    *   end, Cauchy termination on both the iterate and the function value, at most 256 iterations). */
-  int32_t event_kind, event_direction, event_root_find;
-  const double *event_params; int32_t n_event_params;
+  int32_t n_events;                          /* 0 = no event; up to 4 conditions, the first that triggers wins (619-626) */
+  int32_t event_kind[4], event_direction[4];
+  int32_t event_root_find;
+  const double *event_params; int32_t n_event_params; /* the conditions' parameters back to back */
   double event_rtol, event_atol;
   /* Resuming: diffeqsolve(..., solver_state=, controller_state=, made_jump=) and SaveAt(solver_state=True, ...)
    * (_integrate.py:1250-1271, 1489-1500).  One record per trajectory, [N, 5 + d] REAL:

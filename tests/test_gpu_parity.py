@@ -601,6 +601,33 @@ def test_clip_store_rejected_steps(dev):
             assert (res == 0).all() and (stats_np(sol)[:, 2] > 0).any()
 
 
+def test_events_pytree_of_conditions(dev):
+    """Event with a PyTree of condition functions (_event.py:26-47, _integrate.py:599-626): every condition is tracked, the
+    first one (in flattened order) that triggers on a step decides, and the root find runs on that one."""
+    kw, n = _osc_case("tsit5", np.float64, save_t1=True)
+    y0t = torch.tensor(np.asarray(kw["y0"], np.float64), device=dev)
+    conds = {"b_high": dfx.AffineEvent([1.0, 0.0], b=-1.2), "a_low": dfx.AffineEvent([1.0, 0.0], b=+1.2),
+             "c_speed": [dfx.AffineEvent([0.0, 1.0], b=-2.5)]}
+    # flattened (sorted keys): a_low (x = -1.2), b_high (x = +1.2), c_speed (v = 2.5, upcrossing only)
+    event = dfx.Event(conds, dfx.Newton(1e-10, 1e-12), direction={"a_low": None, "b_high": None, "c_speed": [True]})
+    sol = dfx.diffeqsolve(dfx.ODETerm(FIELDS[kw["field"]](*kw["params"])), dfx.Tsit5(), kw["t0"], kw["t1"], kw["dt0"], y0t,
+                          event=event, stepsize_controller=dfx.PIDController(rtol=kw["rtol"], atol=kw["atol"]), max_steps=kw["max_steps"])
+    o = _oracle(dict(kw, event=["affine", "affine", "affine"],
+                     event_params=[[1.0, 0.0, 1.2, 0.0], [1.0, 0.0, -1.2, 0.0], [0.0, 1.0, -2.5, 0.0]],
+                     event_direction=[None, None, True], event_root=(1e-10, 1e-12)))
+    res = to_np(sol.result)
+    same = np.all(stats_np(sol) == o["stats"], axis=1) & (res == o["result"])
+    assert same.mean() > 0.98 and (res == 3).sum() > 20
+    assert relerr(to_np(sol.ts)[same], o["ts"][same]) < 1e-9 and relerr(to_np(sol.ys)[same], o["ys"][same]) < 1e-8
+    # each terminated trajectory sits on (at least) one of the three surfaces
+    yf = to_np(sol.ys)[:, -1]
+    hit = same & (res == 3)
+    dist = np.minimum.reduce([np.abs(yf[:, 0] + 1.2), np.abs(yf[:, 0] - 1.2), np.abs(yf[:, 1] - 2.5)])
+    assert dist[hit].max() < 1e-8
+    with pytest.raises(ValueError):
+        dfx.Event([dfx.AffineEvent([1.0, 0.0])], direction=[None, True])
+
+
 def test_hairer_initial_step_flag(dev):
     """K2: the starting-step algorithm of pid.py:51-81 behind a flag; default is the constant 0.01 the reference uses."""
     rng = np.random.default_rng(9)
