@@ -364,7 +364,7 @@ def run_ours(args):
                     "frac": achieved / peak if peak > 0 else None, "traffic": None,
                     "peak_source": "dfx_measure_int_peak: add/rotate/xor chains, measured in this run",
                     "threefry_blocks_per_step": blocks, "threefry_blocks_per_step_without_descent_cache": blocks_nocache}
-        roof["traffic"] = ncu_traffic(args.workload.split("_")[0])
+        roof["traffic"] = ncu_traffic(args.workload)   # (a capture of this very workload, or none)
         cpu_sample = min(args.cpu_sample, n_local)
         cpu_rate, cpu_dt, cores = cpu_port_rate(w, cpu_sample)
         line = {
