@@ -423,6 +423,8 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
     d.dense_k = dev_out(off(h->dense_k, ms * S * D * es), N * ms * S * D * es);
     d.dense_count = (int32_t *)dev_out(off(h->dense_count, 4), N * 4);
   }
+  d.state_in = dev_in(off(h->state_in, (5 + D) * es), N * (5 + D) * es);
+  d.state_out = dev_out(off(h->state_out, (5 + D) * es), N * (5 + D) * es);
   d.y_final = dev_out(off(h->y_final, D * es), N * D * es);
   d.t_final = dev_out(off(h->t_final, es), N * es);
   if (!rc) rc = dfx_ensemble_solve(&d, (void *)st);

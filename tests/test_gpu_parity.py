@@ -628,6 +628,24 @@ def test_events_pytree_of_conditions(dev):
         dfx.Event([dfx.AffineEvent([1.0, 0.0])], direction=[None, True])
 
 
+def test_host_path_carries_events_states_and_clip(dev):
+    """dfx_ensemble_solve_host stages every optional array (step_ts, state_in / state_out) and the host-side event
+    description: the same call with numpy buffers gives what the device path gives."""
+    rng = np.random.default_rng(8)
+    y0 = rng.uniform(-2, 2, (300, 2))
+    term = dfx.ODETerm(dfx.fields.ForcedOscillator(1.0, 0.7, 2.0))
+    ctrl = dfx.ClipStepSizeController(dfx.PIDController(rtol=1e-7, atol=1e-9, pcoeff=0.2, icoeff=0.5), step_ts=[0.5, 1.25],
+                                      store_rejected_steps=8)
+    kw = dict(saveat=dfx.SaveAt(t0=True, ts=np.linspace(0.25, 2.0, 8), t1=True, solver_state=True, controller_state=True),
+              stepsize_controller=ctrl, event=dfx.Event(dfx.AffineEvent([1.0, 0.0], b=-1.5), dfx.Newton(1e-10, 1e-12)), throw=False)
+    a = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 2.0, 0.3, torch.tensor(y0, device=dev), **kw)
+    b = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 2.0, 0.3, y0, **kw)                      # numpy in -> host path
+    for name in ("ts", "ys", "result", "solver_state", "controller_state"):
+        x, y = to_np(getattr(a, name)), to_np(getattr(b, name))
+        assert np.array_equal(x, y, equal_nan=True), name
+    assert (to_np(a.result) == 3).any() and (to_np(a.result) == 0).any()
+
+
 def test_hairer_initial_step_flag(dev):
     """K2: the starting-step algorithm of pid.py:51-81 behind a flag; default is the constant 0.01 the reference uses."""
     rng = np.random.default_rng(9)
