@@ -57,9 +57,29 @@ case("ou_heun_adaptive_f64", field="ou", params=[1.0, 0.0, 0.5], solver="heun", 
      rtol=0.0, atol=1e-2, dtmin=2.0 ** -7, levy_area="bi", keys=keys, bm_tol=2.0 ** -9, pcoeff=0.1, icoeff=0.3)
 
 
+# Oracle-only regression pins for the SURVEY §8f features (the GPU parity tests build their own inputs for these)
+CASES_EXTRA = {}
+rng2 = np.random.default_rng(77)
+m = 48
+yo = rng2.uniform(-2, 2, (m, 2))
+CASES_EXTRA["half_heun_ode"] = dict(field="forced_osc", params=[1.0, 0.7, 2.0], solver="half:heun", y0=yo, t0=0.0, t1=3.0, dt0=0.3,
+                                    rtol=1e-6, atol=1e-8, save_ts=np.linspace(0.0, 3.0, 7), save_t1=False, max_steps=20000)
+CASES_EXTRA["half_shark_sde_fixed"] = dict(field="ou", params=[1.0, 0.0, 0.5], solver="half:shark", y0=np.ones((m, 1)), t0=0.0, t1=1.0,
+                                           dt0=2.0 ** -5, controller="constant", levy_area="stla", keys=keys[:m], bm_tol=2.0 ** -9)
+CASES_EXTRA["event_newton_tsit5"] = dict(field="forced_osc", params=[1.0, 0.7, 2.0], solver="tsit5", y0=yo, t0=0.0, t1=3.0, dt0=0.3,
+                                         rtol=1e-9, atol=1e-11, save_t0=True, save_ts=np.linspace(0.25, 3.0, 12), save_t1=True,
+                                         event=["affine", "affine"], event_params=[[1.0, 0.0, -0.3, 0.0], [0.0, 1.0, 2.5, 0.0]],
+                                         event_direction=[None, False], event_root=(1e-10, 1e-12))
+CASES_EXTRA["clip_steps_jumps_rejected"] = dict(field="forced_osc", params=[1.0, 0.7, 2.0], solver="dopri5", y0=yo, t0=0.0, t1=3.0, dt0=1.0,
+                                                rtol=1e-7, atol=1e-9, step_ts=np.array([0.5, 1.75]), jump_ts=np.array([1.0, 2.5]),
+                                                store_rejected_steps=8, save_steps=1, save_t1=True, max_steps=512)
+CASES_EXTRA["steady_state_decay"] = dict(field="decay", params=[1.0], solver="bosh3", y0=rng2.uniform(0.5, 2.0, (m, 2)), t0=0.0, t1=50.0,
+                                         dt0=0.01, rtol=1e-6, atol=1e-4, event="steady_state", event_params=[1e-6, 1e-4])
+
+
 def main():
     out = {}
-    for name, kw in CASES.items():
+    for name, kw in list(CASES.items()) + list(CASES_EXTRA.items()):
         kw = dict(kw)
         field = kw.pop("field")
         y0, t0, t1, dt0 = kw.pop("y0"), kw.pop("t0"), kw.pop("t1"), kw.pop("dt0")
@@ -71,6 +91,7 @@ def main():
             tq = np.tile(np.linspace(t0, t1, 33), (y0.shape[0], 1))
             out[f"{name}/dense_tq"] = tq
             out[f"{name}/dense_eval"] = oracle.dense_evaluate(kw["solver"], r["dense"], tq)
+            out[f"{name}/dense_deriv"] = oracle.dense_evaluate(kw["solver"], r["dense"], tq, derivative=True)
         print(name, r["stats"][:3].tolist(), "failed:", int((r["result"] != 0).sum()))
     # PRNG / Brownian golden words
     out["prng/keys"] = keys

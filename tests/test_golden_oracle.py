@@ -13,9 +13,9 @@ import oracle  # noqa: E402
 GOLD = np.load(os.path.join(HERE, "golden", "ensemble_golden.npz"))
 
 
-@pytest.mark.parametrize("name", list(make_golden.CASES))
+@pytest.mark.parametrize("name", list(make_golden.CASES) + list(make_golden.CASES_EXTRA))
 def test_oracle_reproduces_golden(name):
-    kw = dict(make_golden.CASES[name])
+    kw = dict(make_golden.CASES[name] if name in make_golden.CASES else make_golden.CASES_EXTRA[name])
     field = kw.pop("field")
     y0, t0, t1, dt0 = kw.pop("y0"), kw.pop("t0"), kw.pop("t1"), kw.pop("dt0")
     r = oracle.solve(field, y0, t0, t1, dt0, **kw)
