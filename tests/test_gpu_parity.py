@@ -722,3 +722,58 @@ def test_full_size_properties_c5(dev):
         o = oracle.solve("ou", np.ones((2048, 1), np.float32), 0.0, 1.0, 2.0 ** -6, solver=oname, params=[1.0, 0.0, 0.5], dtype=np.float32,
                          controller="constant", levy_area=olv, keys=keys[:2048], bm_tol=2.0 ** -8)
         assert np.abs(to_np(sol.ys)[:2048] - o["ys"]).max() < 5e-6
+
+
+def test_full_size_properties_c4(dev):
+    """BASELINE config 4 at full size (65 536 trajectories, MLP field on the tensor cores): rows of a tile do not interact, so
+    the result of a trajectory is independent of which tile / row it lands in (permutation equivariance, bit for bit);
+    all trajectories succeed; a slice equals the fp32 oracle within the north-star tolerance."""
+    n = 1 << 16
+    mlp = make_golden._mlp
+    rng = np.random.default_rng(30)
+    y0 = rng.standard_normal((n, 4)).astype(np.float32)
+    term, ctrl = dfx.ODETerm(mlp), dfx.PIDController(rtol=1e-3, atol=1e-6)
+    y0d = torch.tensor(y0, device=dev)
+    a = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d, stepsize_controller=ctrl)
+    perm = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    b = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d[perm].contiguous(), stepsize_controller=ctrl)
+    assert torch.equal(a.ys[perm], b.ys) and torch.equal(a.stats["num_steps"][perm], b.stats["num_steps"])
+    assert bool(torch.isfinite(a.ys).all()) and int((a.result != 0).sum()) == 0
+    sl = slice(777, 777 + 512)
+    o = oracle.solve("mlp", y0[sl], 0.0, 10.0, None, solver="tsit5", params=mlp.oracle_params(), dtype=np.float32, rtol=1e-3, atol=1e-6)
+    assert relerr_state(to_np(a.ys)[sl], o["ys"]) < RTOL32
+    assert np.abs(to_np(a.stats["num_accepted_steps"])[sl] - o["stats"][:, 1]).max() <= 1
+
+
+def test_dense_output_properties_c3_shape(dev):
+    """BASELINE config 3 (CR3BP / Dopri8 / rtol 1e-12 / SaveAt(dense)) at 2^14 trajectories with the benchmark's max_steps:
+    the dense records are self-consistent - record i ends where record i + 1 starts, the knots are increasing, unfilled
+    slots are +inf in every array, the interpolant at the last knot is the final state - and a slice matches the oracle."""
+    n, ms = 1 << 14, 768
+    rng = np.random.default_rng(2)
+    y0 = np.array([0.994, 0.0, 0.0, -2.00158510637908252]) + 1e-4 * rng.standard_normal((n, 4))
+    t1 = 17.0652165601579625
+    sol = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.CR3BP(0.012277471)), dfx.Dopri8(), 0.0, t1, None, torch.tensor(y0, device=dev),
+                          saveat=dfx.SaveAt(dense=True, t1=True), stepsize_controller=dfx.PIDController(rtol=1e-12, atol=1e-12),
+                          max_steps=ms, throw=False)
+    ok = sol.result == 0
+    assert float(ok.double().mean()) > 0.99
+    di = sol.interpolation
+    cnt = di._count.long()
+    assert torch.equal(cnt, sol.stats["num_accepted_steps"].long())
+    idx = torch.arange(ms, device=dev)[None, :]
+    filled = idx < cnt[:, None]
+    assert bool(torch.isinf(di.infos["y0"][~filled]).all()) and bool(torch.isinf(di.infos["k"][~filled]).all())
+    assert bool(torch.isfinite(di.infos["y1"][filled]).all())
+    link = filled[:, 1:]                                                     # record i + 1 exists
+    assert torch.equal(di.infos["y1"][:, :-1][link], di.infos["y0"][:, 1:][link])
+    knots_ok = (di.ts[:, 1:] > di.ts[:, :-1]) | ~(torch.arange(1, ms + 1, device=dev)[None, :] <= cnt[:, None])
+    assert bool(knots_ok.all()) and bool((di.ts[:, 0] == 0).all())
+    last = torch.gather(di.ts, 1, cnt[:, None])[:, 0]
+    assert bool((last[ok] == t1).all())
+    ev = di.evaluate(torch.tensor(t1, device=dev, dtype=torch.float64))
+    assert torch.allclose(ev[ok], sol.ys[ok, -1], rtol=1e-12, atol=1e-13)
+    sl = slice(100, 100 + 64)
+    o = oracle.solve("cr3bp", y0[sl], 0.0, t1, None, solver="dopri8", params=[0.012277471], rtol=1e-12, atol=1e-12, max_steps=ms)
+    good = (o["result"] == 0) & to_np(ok)[sl]
+    assert relerr(to_np(sol.ys)[sl][good], o["ys"][good]) < 1e-6             # conditioning of the orbit ~1e6 (DESIGN.md §4)
