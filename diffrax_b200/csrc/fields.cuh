@@ -125,13 +125,15 @@ struct OuField {
   static constexpr int kDim = 1;
   static constexpr bool kSde = true;
   static constexpr int kNumParams = 3;
-  template <class R> struct P { R theta, mu, sigma; };
-  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0], (R)p[1], (R)p[2]}; }
+  // additive noise sigma + sigma_t * t: the optional 4th parameter gives time-dependent diffusion (the
+  // getting-started.md:63-84 example dy = -y dt + t/10 dw; exercises ShARK's g(t1) - g(t0) term, srk.py:612-618)
+  template <class R> struct P { R theta, mu, sigma, sigma_t; };
+  template <class R> static P<R> make(const double *p, int n, const void *) { return P<R>{(R)p[0], (R)p[1], (R)p[2], n >= 4 ? (R)p[3] : R(0)}; }
   template <class R>
   static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[1], R (&f)[1]) {
     f[0] = p.theta * (p.mu - y[0]);
   }
-  template <class R> static __device__ __forceinline__ R diffusion(const P<R> &p, R) { return p.sigma; }
+  template <class R> static __device__ __forceinline__ R diffusion(const P<R> &p, R t) { return p.sigma + p.sigma_t * t; }
 };
 
 // Neural-ODE vector field (BASELINE config 4): eqx.nn.MLP(d -> W -> W -> d) with softplus hidden activations and

@@ -108,11 +108,11 @@ class VanDerPol(Field):
 
 
 class OrnsteinUhlenbeck(Field):
-    """dy = theta (mu - y) dt + sigma dW (additive scalar noise)."""
+    """dy = theta (mu - y) dt + (sigma + sigma_t t) dW (additive scalar noise, optionally growing linearly in time)."""
     name, dim, is_sde = "ou", 1, True
 
-    def __init__(self, theta=1.0, mu=0.0, sigma=0.5):
-        self.p = [float(theta), float(mu), float(sigma)]
+    def __init__(self, theta=1.0, mu=0.0, sigma=0.5, sigma_t=0.0):
+        self.p = [float(theta), float(mu), float(sigma)] + ([float(sigma_t)] if sigma_t else [])
 
     def params(self):
         return self.p

@@ -646,6 +646,20 @@ def test_host_path_carries_events_states_and_clip(dev):
     assert (to_np(a.result) == 3).any() and (to_np(a.result) == 0).any()
 
 
+@pytest.mark.parametrize("solver,lv", [("euler", "bi"), ("heun", "bi"), ("shark", "stla")])
+def test_time_dependent_additive_noise(dev, solver, lv):
+    """dy = -y dt + (0.1 t) dw on [0, 3] (docs/usage/getting-started.md:63-84): time-dependent additive diffusion, which is
+    what ShARK's g(t1) - g(t0) correction (srk.py:612-618) exists for; fixed steps, so the GPU path equals the oracle."""
+    n = 256
+    keys = dfx.random.split(dfx.random.key(0), n)
+    kw = dict(field="ou", params=[1.0, 0.0, 0.0, 0.1], y0=np.ones((n, 1)), t0=0.0, t1=3.0, dt0=0.05, solver=solver,
+              controller="constant", levy_area=lv, keys=keys, bm_t0=0.0, bm_t1=3.0, bm_tol=1e-3, save_t1=True)
+    o, sol = _oracle(kw), run_case(kw, dev)
+    assert np.array_equal(stats_np(sol), o["stats"]) and relerr(to_np(sol.ys), o["ys"]) < 1e-12
+    ens = to_np(sol.ys)[:, 0, 0]
+    assert abs(ens.mean() - np.exp(-3.0)) < 0.06          # E y(3) = e^-3; Var y(3) = int_0^3 e^{-2(3-s)} (0.1 s)^2 ds ~ 0.18^2 -> mean of 256: sigma 0.011
+
+
 def test_hairer_initial_step_flag(dev):
     """K2: the starting-step algorithm of pid.py:51-81 behind a flag; default is the constant 0.01 the reference uses."""
     rng = np.random.default_rng(9)
