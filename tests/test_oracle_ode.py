@@ -343,3 +343,13 @@ def test_store_rejected_steps_revisits_rejected_times():
     # a one-slot stack overflows as soon as two rejections are pending
     small = oracle.solve("forced_osc", y0, 0.0, 6.0, 5.0, store_rejected_steps=1, **kw)
     assert np.any(small["result"] == 5)                             # max_steps_rejected
+
+
+def test_getting_started_ode_printout():
+    """docs/usage/getting-started.md:22-36: Dopri5, dy/dt = -y on [0, 3], dt0 = 0.1, PIDController(1e-5, 1e-5),
+    SaveAt(ts=[0, 1, 2, 3]) prints ts [0. 1. 2. 3.] and ys [1. 0.368 0.135 0.0498] (fp32 in the docs)."""
+    for dtype in (np.float32, np.float64):
+        r = oracle.solve("decay", np.ones((1, 1), dtype), 0.0, 3.0, 0.1, solver="dopri5", params=[1.0], dtype=dtype, rtol=1e-5,
+                         atol=1e-5, save_ts=np.array([0.0, 1.0, 2.0, 3.0]), save_t1=False)
+        assert np.array_equal(r["ts"][0], [0.0, 1.0, 2.0, 3.0])
+        assert [f"{v:.3g}" for v in r["ys"][0, :, 0]] == ["1", "0.368", "0.135", "0.0498"]
