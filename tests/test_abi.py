@@ -65,7 +65,7 @@ def test_out_size_rule(cuda_lib):
     assert T(save_steps=3, save_t1=1) == 4096 // 3 + 1 and T(save_steps=1, save_t1=1, save_t0=1) == 4097
 
 
-def test_sass_is_sm100a():
+def test_sass_is_sm100a(cuda_lib):
     """The shipped cubins target sm_100a and the hot kernel keeps its state in registers (no local memory)."""
     import subprocess, glob
     lib = os.path.join(ROOT, "diffrax_b200", "lib", "libdiffrax_b200.so")
