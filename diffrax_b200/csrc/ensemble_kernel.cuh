@@ -7,6 +7,9 @@
 //   pid.py:316-392, 394-567 PID controller; constant.py:30-104 ConstantStepSize
 //   _local_interpolation.py / tsit5.py / dopri5.py / dopri8.py interpolants for SaveAt(ts)
 //   _brownian/tree.py       VirtualBrownianTree increments (vbt.cuh)
+//   _solver/base.py:250-346 HalfSolver (HalfOf<Inner>); and, in the EXTRA instantiation only:
+//   clip.py:120-428 ClipStepSizeController, pid.py:33-81 Hairer starting step, _event.py + _integrate.py:542-633, 691-821
+//   Events with a Newton root find on the local interpolant, _integrate.py:1250-1271 resumed solver / controller state
 //
 // Mapping to the hardware
 //   * one trajectory per thread; y, the s stage values k[s][d], the FSAL derivative and the
@@ -14,10 +17,11 @@
 //     coefficients read from __constant__ memory as immediate c[bank][offset] operands);
 //   * HBM is touched only to read y0 once and to write saved outputs;
 //   * the adaptive loops diverge per trajectory, so the grid is persistent (a multiple of the SM
-//     count) and a lane that finishes its trajectory immediately claims the next one from a
-//     global work queue (warp-aggregated atomicAdd: one atomic per refilling warp).  The still
-//     active lanes therefore stay compacted in full warps until the queue drains; results do not
-//     depend on the lane <-> trajectory assignment because trajectories are independent.
+//     count) and a lane that finishes its trajectory claims the next one from a global work queue
+//     (warp-aggregated atomicAdd: one atomic per refilling warp; finished lanes wait until
+//     `refill_batch` of them share one finalize + refill pass).  The still active lanes therefore
+//     stay compacted in full warps until the queue drains; results do not depend on the
+//     lane <-> trajectory assignment because trajectories are independent.
 //   * accept / reject is a select, not a branch: every lane executes the same instruction stream.
 #pragma once
 #include "common.cuh"
@@ -75,7 +79,7 @@ struct SolveParams {
   int has_dtmin, has_dtmax, force_dtmin;
   R coeff1, coeff2, coeff3;  // PID exponents (pid.py:512-514), computed in double on the host
   int use_c1, use_c2, use_c3;
-  const R *step_ts, *jump_ts;  // ClipStepSizeController (clip.py): sorted, user time; RICH instantiation only
+  const R *step_ts, *jump_ts;  // ClipStepSizeController (clip.py): sorted, user time; EXTRA instantiation only
   int n_step_ts, n_jump_ts;
   R *reject_ts; int n_reject;  // store_rejected_steps: per-trajectory stack of rejected step ends, [N, n_reject] scratch (EXTRA only)
   int hairer;    // dt0 == None: use the Hairer starting step of pid.py:51-81 instead of the constant 0.01
@@ -88,7 +92,7 @@ struct SolveParams {
   int *stats, *result, *save_count;
   R *dense_ts, *dense_y0, *dense_y1, *dense_k;
   int *dense_count;
-  // Event (RICH instantiation only): kind, direction (0 any / 1 up / 2 down), Newton root find on the local interpolant
+  // Event (EXTRA instantiation only): kind, direction (0 any / 1 up / 2 down), Newton root find on the local interpolant
   int n_events, event_kind[DFX_MAX_EVENTS], event_dir[DFX_MAX_EVENTS], event_root;
   R ev_w[DFX_MAX_EVENTS][4], ev_b[DFX_MAX_EVENTS], ev_wt[DFX_MAX_EVENTS];  // affine: w . y + wt t + b
   R ev_ss_rtol[DFX_MAX_EVENTS], ev_ss_atol[DFX_MAX_EVENTS];               // steady state
@@ -241,7 +245,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   int cs_num_steps = 0;  // ConstantStepSize: steps_completed (constant.py:84) is num_steps + 1, every step being accepted
   int num_steps = 0, num_accepted = 0, result = DFX_RESULT_SUCCESSFUL;
   int save_index = 0, saveat_ts_index = 0, dense_index = 0;
-  [[maybe_unused]] int step_index = 0, jump_index = 0;  // ClipStepSizeController state (RICH only)
+  [[maybe_unused]] int step_index = 0, jump_index = 0;  // ClipStepSizeController state (EXTRA only)
   [[maybe_unused]] bool made_jump = false;
   [[maybe_unused]] int reject_index = 0;  // ClipStepSizeController(store_rejected_steps=K): top of the stack, K = empty
   [[maybe_unused]] R event_value[DFX_MAX_EVENTS] = {};  // Event: the cond_fns at the previous state (EXTRA only)
