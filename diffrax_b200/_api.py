@@ -447,15 +447,17 @@ class SpaceTimeLevyArea:
 class VirtualBrownianTree:
     """tree.py:245-301.  ``key`` is an ``[N, 2]`` uint32 array: one tree per trajectory, the
     pattern ``jax.vmap(lambda k: VirtualBrownianTree(t0, t1, tol, (), k))(jr.split(root, N))`` of
-    test/helpers.py:140-169.  Only ``shape == ()`` (scalar noise) is implemented."""
+    test/helpers.py:140-169.  ``shape`` is ``()`` (scalar noise) or ``(m,)`` (m independent components for a diagonal
+    diffusion; ``evaluate`` here covers ``()`` only)."""
 
     def __init__(self, t0, t1, tol, shape, key, levy_area=BrownianIncrement, *, partitionable: bool = True):
         if not (t0 < t1):
             raise ValueError("t0 must be strictly less than t1")  # tree.py:281
-        if tuple(shape) != ():
-            raise NotImplementedError("only shape=() Brownian motion is implemented")
+        shape = tuple(shape)
+        if len(shape) > 1:
+            raise NotImplementedError("Brownian motion of shape () or (m,) is implemented")
         self.t0, self.t1, self.tol = float(t0), float(t1), float(tol)
-        self.shape = ()
+        self.shape = shape   # (m,): m independent trees, leaf keys jr.split(key, m) (tree.py:301), driving a diagonal diffusion
         self.levy_area = levy_area
         self.key = key
         self.partitionable = bool(partitionable)
@@ -857,6 +859,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         D.levy_area, D.bm_keys = bm.levy_area.levy_id, xp.ptr(keys)
         D.bm_t0, D.bm_t1, D.bm_tol = bm.t0, bm.t1, bm.tol
         D.threefry_partitionable = int(bm.partitionable)
+        D.bm_dim = bm.shape[0] if bm.shape else 0
         if not field.is_sde:
             raise ValueError(f"{type(field).__name__} is not an SDE functor")
     elif isinstance(solver.solver if isinstance(solver, HalfSolver) else solver, ShARK):

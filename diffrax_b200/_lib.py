@@ -52,7 +52,7 @@ class SolveDesc(C.Structure):
         ("y_final", C.c_void_p), ("t_final", C.c_void_p),
         ("levy_area", C.c_int32), ("bm_keys", C.c_void_p),
         ("bm_t0", C.c_double), ("bm_t1", C.c_double), ("bm_tol", C.c_double),
-        ("threefry_partitionable", C.c_int32),
+        ("threefry_partitionable", C.c_int32), ("bm_dim", C.c_int32),
         ("n_events", C.c_int32), ("event_kind", C.c_int32 * 4), ("event_direction", C.c_int32 * 4),
         ("event_root_find", C.c_int32),
         ("event_params", C.c_void_p), ("n_event_params", C.c_int32),

@@ -265,7 +265,7 @@ int dfx_field_dim(int field_id) {
   switch (field_id) {
     case DFX_FIELD_DECAY: return 0;
     case DFX_FIELD_LOTKA_VOLTERRA: return 2; case DFX_FIELD_LORENZ: return 3; case DFX_FIELD_CR3BP: return 4;
-    case DFX_FIELD_OU: return 1; case DFX_FIELD_FORCED_OSC: return 2; case DFX_FIELD_VDP: return 2;
+    case DFX_FIELD_OU: return 0; case DFX_FIELD_FORCED_OSC: return 2; case DFX_FIELD_VDP: return 2;
     case DFX_FIELD_MLP: return 0;
   }
   return -1;
@@ -348,6 +348,14 @@ static int check_desc(const dfx_solve_desc *d) {
   }
   if (d->levy_area != DFX_LEVY_NONE) {
     if (!d->bm_keys) { set_error("SDE solve needs bm_keys"); return DFX_ERR_BAD_ARGUMENT; }
+    if (d->bm_dim != 0 && d->bm_dim != d->dim) {
+      set_error("VirtualBrownianTree(shape=(%d,)) drives a diagonal diffusion: it needs a state of the same dimension (got %d)", d->bm_dim, d->dim);
+      return DFX_ERR_BAD_ARGUMENT;
+    }
+    if (d->bm_dim == 0 && d->dim != 1 && d->field_id == DFX_FIELD_OU) {
+      set_error("the OU functor with a %d-dimensional state needs VirtualBrownianTree(shape=(%d,))", d->dim, d->dim);
+      return DFX_ERR_BAD_ARGUMENT;
+    }
     if (!(d->bm_t0 < d->bm_t1)) { set_error("t0 must be strictly less than t1"); return DFX_ERR_BAD_ARGUMENT; }  // tree.py:281
     if ((d->solver_id & ~DFX_HALF_SOLVER) == DFX_SHARK && d->levy_area != DFX_LEVY_SPACE_TIME) {
       set_error("The Brownian increment does not have the minimal Levy Area SpaceTimeLevyArea.");  // srk.py:391-395

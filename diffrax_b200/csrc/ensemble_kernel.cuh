@@ -24,6 +24,7 @@
 //     lane <-> trajectory assignment because trajectories are independent.
 //   * accept / reject is a select, not a branch: every lane executes the same instruction stream.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "fields.cuh"
 #include "interp.cuh"
@@ -57,6 +58,9 @@ struct HalfOf : Inner {
   static constexpr int kOrder = Inner::kOrder + 1;  // error order on an ODE (base.py:296-299)
   static constexpr bool kHalf = true;
 };
+// number of independent Brownian components a field is driven by (Field::kNoise when it declares one, else 1)
+template <class F, class = void> struct NoiseDim { static constexpr int value = 1; };
+template <class F> struct NoiseDim<F, std::void_t<decltype(F::kNoise)>> { static constexpr int value = F::kNoise; };
 template <class T, class = void> struct IsHalf { static constexpr bool value = false; };
 template <class I> struct IsHalf<HalfOf<I>> { static constexpr bool value = true; };
 template <class T> struct InnerId { static constexpr int value = T::kId; };
@@ -232,6 +236,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   [[maybe_unused]] constexpr bool kChainY0 = DFX_OPT_CHAIN_Y0 && TAB && !SDE && Solver::S <= 7;
   [[maybe_unused]] constexpr bool kLastStageF = DFX_OPT_LAST_STAGE_F && TAB && FSAL && Solver::kSsal;
   constexpr int INTERP = Solver::kInterp;
+  constexpr int NW = NoiseDim<Field>::value;  // independent Brownian components: 1 (shape=()) or D (shape=(D,), diagonal diffusion)
   constexpr bool DENSE_K = INTERP != kInterpLinear;
   constexpr bool FAST_PID = TAB && !SDE && sizeof(R) == 8;  // fp64 ODE solves: division-/pow-free I-controller path
 
@@ -249,7 +254,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   [[maybe_unused]] bool made_jump = false;
   [[maybe_unused]] int reject_index = 0;  // ClipStepSizeController(store_rejected_steps=K): top of the stack, K = empty
   [[maybe_unused]] R event_value[DFX_MAX_EVENTS] = {};  // Event: the cond_fns at the previous state (EXTRA only)
-  BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME> bm;
+  BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME> bm[NW];
 #pragma unroll
   for (int c = 0; c < D; ++c) { y[c] = R(0); f_fsal[c] = R(0); }
 
@@ -289,7 +294,10 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   // dynamic shared memory: [VBT descent cache (SDE kernels)] [dense staging records (RICH, SaveAt(dense))]
   extern __shared__ __align__(16) unsigned char dense_smem_raw[];
   [[maybe_unused]] R *dense_smem = reinterpret_cast<R *>(dense_smem_raw + p.dense_smem_offset);
-  if constexpr (SDE) bm.attach_cache(reinterpret_cast<R *>(dense_smem_raw), p.vbt);
+  if constexpr (SDE) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) bm[w].attach_cache(reinterpret_cast<R *>(dense_smem_raw) + w * p.vbt.cache_levels * VbtCache<R, LEVY == DFX_LEVY_SPACE_TIME>::kWords * p.vbt.cache_stride, p.vbt);
+  }
 
   for (;;) {
     // Finalising a trajectory and claiming + initialising the next one is ~300 instructions that the whole warp
@@ -428,7 +436,10 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           pid_inv = R(1); pid_prev_inv = R(1); at_dtmin = false;
           num_steps = 0; num_accepted = 0; result = DFX_RESULT_SUCCESSFUL;
           save_index = 0; saveat_ts_index = 0; dense_index = 0;
-          if constexpr (SDE) bm.init(p.keys + 2 * idx, p.vbt);
+          if constexpr (SDE) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) bm[w].template init_leaf<NW>(p.keys + 2 * idx, w, p.vbt);  // split_by_tree(key, shape)[w]
+          }
           if constexpr (FSAL) {
             // runge_kutta.py:684-695: the first step evaluates stage 0 at (t0, y0); a rejected first
             // step re-evaluates the same point, so computing it once here is value-identical.
@@ -514,8 +525,16 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         auto single_step = [&](const R st0, const R st1, const R (&y)[D], [[maybe_unused]] const R (&f_in)[D],
                                [[maybe_unused]] const bool reeval, R (&y1)[D], R (&yerr)[D], R (&k)[S][D], R (&f_last)[D]) {
           const R dt = st1 - st0;
-          R W = R(0), H = R(0);
-          if constexpr (SDE) bm.increment(st0, st1, p.vbt, W, H);  // one Brownian query per step (runge_kutta.py:644, srk.py:390)
+          // one Brownian query per step and component (runge_kutta.py:644, srk.py:390); Wc(c) / Hc(c): the increment driving component c
+          R Wv[NW], Hv[NW];
+#pragma unroll
+          for (int w = 0; w < NW; ++w) { Wv[w] = R(0); Hv[w] = R(0); }
+          if constexpr (SDE) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) bm[w].increment(st0, st1, p.vbt, Wv[w], Hv[w]);
+          }
+          auto Wc = [&](int c) { return Wv[NW == 1 ? 0 : c]; };
+          auto Hc = [&](int c) { return Hv[NW == 1 ? 0 : c]; };
 
           if constexpr (TAB) {
             // ---- explicit RK step, runge_kutta.py:643-1203 ----
@@ -537,7 +556,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   #pragma unroll
               for (int c = 0; c < D; ++c) {
                 R kk = control * fi[c];
-                if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * W;  // MultiTerm.vf_prod (_term.py:711-722)
+                if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * Wc(c);  // MultiTerm.vf_prod (_term.py:711-722)
                 k[0][c] = kk;
               }
             }
@@ -572,7 +591,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
                   if (i == S - 1) continue;  // the last stage value is only read by the error estimate, through f_last below
                 }
                 R kk = control * fi[c];
-                if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, ti) * W;
+                if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, ti) * Wc(c);
                 k[i][c] = kk;
               }
             }
@@ -615,7 +634,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   #pragma unroll
             for (int c = 0; c < D; ++c) {
               R kk = (direction * dt) * f0[c];
-              if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * W;
+              if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * Wc(c);
               k[0][c] = kk;
               y1[c] = y[c] + kk;
               yerr[c] = R(0);
@@ -627,22 +646,23 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               const R h = dt;
               const R g0 = Field::template diffusion<R>(fp, st0), g1 = Field::template diffusion<R>(fp, st1);
               const R g_delta = R(0.5) * (g1 - g0);
-              const R w_kg = g0 * W, h_kg = g0 * H;  // 441-447
+              auto w_kg = [&](int c) { return g0 * Wc(c); };  // 441-447
+              auto h_kg = [&](int c) { return g0 * Hc(c); };
               R z[D], fz[D];
   #pragma unroll
-              for (int c = 0; c < D; ++c) z[c] = y[c] + R(0) + (R(kSharkAW0) * w_kg + R(kSharkAH0) * h_kg);  // stage 0: 545
+              for (int c = 0; c < D; ++c) z[c] = y[c] + R(0) + (R(kSharkAW0) * w_kg(c) + R(kSharkAH0) * h_kg(c));  // stage 0: 545
               Field::template eval<R>(fp, st0, z, fz);  // 548: t0 + 0*h
   #pragma unroll
               for (int c = 0; c < D; ++c) k[0][c] = h * fz[c];
   #pragma unroll
-              for (int c = 0; c < D; ++c) z[c] = y[c] + R(kSharkA10) * k[0][c] + (R(kSharkAW1) * w_kg + R(kSharkAH1) * h_kg);
+              for (int c = 0; c < D; ++c) z[c] = y[c] + R(kSharkA10) * k[0][c] + (R(kSharkAW1) * w_kg(c) + R(kSharkAH1) * h_kg(c));
               Field::template eval<R>(fp, st0 + R(kSharkC1) * h, z, fz);
   #pragma unroll
               for (int c = 0; c < D; ++c) k[1][c] = h * fz[c];
   #pragma unroll
               for (int c = 0; c < D; ++c) {
-                R diffusion_result = R(kSharkBW) * w_kg + R(kSharkBH) * h_kg;   // 603-607
-                diffusion_result = diffusion_result + g_delta * (W - R(2.0) * H);  // 612-618
+                R diffusion_result = R(kSharkBW) * w_kg(c) + R(kSharkBH) * h_kg(c);   // 603-607
+                diffusion_result = diffusion_result + g_delta * (Wc(c) - R(2.0) * Hc(c));  // 612-618
                 yerr[c] = R(kSharkE0) * k[0][c] + R(kSharkE1) * k[1][c];        // 638-639, 663
                 const R drift_result = R(kSharkB0) * k[0][c] + R(kSharkB1) * k[1][c];  // 667
                 y1[c] = y[c] + drift_result + diffusion_result;                  // 669

@@ -136,6 +136,25 @@ struct OuField {
   template <class R> static __device__ __forceinline__ R diffusion(const P<R> &p, R t) { return p.sigma + p.sigma_t * t; }
 };
 
+// D independent OU components, each driven by its own Brownian motion: VirtualBrownianTree(shape=(D,)) with a diagonal
+// diffusion (vf_prod = g (.) dW).  Same field id as OuField; the launcher key is (field, dim).
+template <int D>
+struct OuDiagField {
+  static constexpr int kId = DFX_FIELD_OU;
+  static constexpr int kDim = D;
+  static constexpr int kNoise = D;
+  static constexpr bool kSde = true;
+  static constexpr int kNumParams = 3;
+  template <class R> using P = OuField::P<R>;
+  template <class R> static P<R> make(const double *p, int n, const void *w) { return OuField::make<R>(p, n, w); }
+  template <class R>
+  static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[D], R (&f)[D]) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) f[c] = p.theta * (p.mu - y[c]);
+  }
+  template <class R> static __device__ __forceinline__ R diffusion(const P<R> &p, R t) { return p.sigma + p.sigma_t * t; }
+};
+
 // Neural-ODE vector field (BASELINE config 4): eqx.nn.MLP(d -> W -> W -> d) with softplus hidden activations and
 // a tanh output (docs/examples/neural_ode.ipynb cell 5; benchmarks/small_neural_ode.py:25-28), evaluated per thread
 // on the FP32 CUDA cores.  This is the exact-fp32 reference implementation of the field inside the generic ensemble

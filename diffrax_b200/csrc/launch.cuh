@@ -143,13 +143,14 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
   p.vbt.cache_stride = kBlockThreads;
   if (LEVY != DFX_LEVY_NONE) {
     static const int env_cache = [] { const char *e = getenv("DFX_VBT_CACHE"); return e ? atoi(e) : 1; }();
-    const size_t per_level = (size_t)(LEVY == DFX_LEVY_SPACE_TIME ? 7 : 5) * kBlockThreads * sizeof(R);
-    int levels = env_cache ? (int)((24 * 1024) / per_level) : 0;
+    const size_t per_level = (size_t)(LEVY == DFX_LEVY_SPACE_TIME ? 7 : 5) * kBlockThreads * sizeof(R);  // per tree
+    constexpr int kTrees = NoiseDim<Field>::value;                                                          // one tree per Brownian component
+    int levels = env_cache ? (int)((24 * 1024) / (per_level * kTrees)) : 0;
     if (levels > p.vbt.depth) levels = p.vbt.depth;
     if (levels > 32) levels = 32;
     if (levels >= 2) {
       p.vbt.cache_levels = levels;
-      smem = ((levels * per_level + 15) / 16) * 16;
+      smem = ((levels * per_level * kTrees + 15) / 16) * 16;
       p.dense_smem_offset = (int)smem;
     }
   }

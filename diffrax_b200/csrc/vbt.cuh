@@ -206,6 +206,14 @@ struct BrownianTree {
     cache.stride = vp.cache_stride;
   }
 
+  // leaf `w` of split_by_tree(key, shape) = jr.split(key, NUM)[w] (tree.py:301, _misc.py:128-133): NUM = 1 for shape=()
+  template <int NUM>
+  __device__ __forceinline__ void init_leaf(const uint32_t *user_key, int w, const VbtParams &vp) {
+    init(user_key, vp);
+    Key k{user_key[0], user_key[1]};
+    leaf = split_child<NUM>(k, w, vp.partitionable != 0);
+  }
+
   __device__ __forceinline__ void init(const uint32_t *user_key, const VbtParams &vp) {
     cache.n_entry = 0;
     cache.path = 0;

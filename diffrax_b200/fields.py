@@ -108,8 +108,9 @@ class VanDerPol(Field):
 
 
 class OrnsteinUhlenbeck(Field):
-    """dy = theta (mu - y) dt + (sigma + sigma_t t) dW (additive scalar noise, optionally growing linearly in time)."""
-    name, dim, is_sde = "ou", 1, True
+    """dy = theta (mu - y) dt + (sigma + sigma_t t) dW (additive noise, optionally growing linearly in time).  With a state of
+    dimension m > 1 the components are independent and driven by VirtualBrownianTree(shape=(m,)) (diagonal diffusion)."""
+    name, dim, is_sde = "ou", 0, True
 
     def __init__(self, theta=1.0, mu=0.0, sigma=0.5, sigma_t=0.0):
         self.p = [float(theta), float(mu), float(sigma)] + ([float(sigma_t)] if sigma_t else [])

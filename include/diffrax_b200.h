@@ -135,6 +135,9 @@ typedef struct dfx_solve_desc {
   const uint32_t *bm_keys;    /* [N, 2] the keys the user passed to VirtualBrownianTree */
   double bm_t0, bm_t1, bm_tol;
   int32_t threefry_partitionable; /* jax_threefry_partitionable (default True since JAX 0.5) */
+  int32_t bm_dim;                 /* 0: VirtualBrownianTree(shape=()); m > 0: shape=(m,) with m == dim - one independent tree per
+                                   * state component (leaf keys split_by_tree(key, (m,)) = split(key, m); tree.py:301,
+                                   * _misc.py:128-133) driving a diagonal diffusion.  Kernels: the OU functor with dim 2, 3. */
 
   /* Event(cond_fn, root_finder, direction): _event.py:13-118, _integrate.py:542-633 (detection), 691-821 (root find, unsave).
    * Up to DFX_MAX_EVENTS registered condition functions (the flattened PyTree `cond_fn`; the first one that triggers on a

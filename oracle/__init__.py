@@ -58,7 +58,7 @@ class Desc(C.Structure):
         ("dense_count", C.c_void_p), ("y_final", C.c_void_p), ("t_final", C.c_void_p),
         ("levy_area", C.c_int32), ("bm_keys", C.c_void_p),
         ("bm_t0", C.c_double), ("bm_t1", C.c_double), ("bm_tol", C.c_double),
-        ("threefry_partitionable", C.c_int32),
+        ("threefry_partitionable", C.c_int32), ("bm_dim", C.c_int32),
         ("n_events", C.c_int32), ("event_kind", C.c_int32 * 4), ("event_direction", C.c_int32 * 4),
         ("event_root_find", C.c_int32),
         ("event_params", C.c_void_p), ("n_event_params", C.c_int32),
@@ -170,7 +170,7 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
           bm_tol=1e-3, partitionable=True, callback=None, trace_traj=None, num_threads=0,
           t0_per_traj=None, t1_per_traj=None, step_ts=None, jump_ts=None,
           event=None, event_params=(), event_direction=None, event_root=None,
-          state_in=None, state_in_flags=7, save_state=False, store_rejected_steps=None):
+          state_in=None, state_in_flags=7, save_state=False, store_rejected_steps=None, bm_dim=0):
     """Run the oracle on a batch.  Mirrors one vmapped diffeqsolve call of the reference."""
     L = lib()
     dt = np.dtype(dtype)
@@ -242,6 +242,7 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
     D.bm_keys = _ptr(ka)
     D.bm_t0, D.bm_t1, D.bm_tol = float(bm_t0), float(bm_t1), float(bm_tol)
     D.threefry_partitionable = int(partitionable)
+    D.bm_dim = int(bm_dim)
     if event is not None:
         # event: "affine" (params w[0..d), b, wt) or "steady_state" (params rtol, atol) - or lists of them (then event_params
         # is a list of parameter lists and event_direction a list); event_direction None / True / False;

@@ -93,6 +93,9 @@ typedef struct orc_desc {
   const uint32_t *bm_keys;   /* [N, 2] user keys (before split_by_tree) */
   double bm_t0, bm_t1, bm_tol;
   int32_t threefry_partitionable;
+  int32_t bm_dim;            /* 0: VirtualBrownianTree(shape=()); m > 0: shape=(m,) with m == dim - one independent tree per state
+                              * component (leaf keys split_by_tree(key, (m,)) = split(key, m), tree.py:301, _misc.py:128-133) driving
+                              * a diagonal diffusion */
   /* Event(cond_fn, root_finder, direction) (_event.py:13-118; _integrate.py:542-633, 691-821) with one registered condition:
    *   ORC_EVENT_AFFINE        c(t, y) = w . y + wt * t + b      event_params = [w[0..d), b, wt]   (real-valued: sign change)
    *   ORC_EVENT_STEADY_STATE  rms(f(t, y)) < atol + rtol * rms(y) event_params = [rtol, atol]      (boolean, _event.py:120-170)

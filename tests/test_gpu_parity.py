@@ -81,7 +81,8 @@ def run_case(kw, dev, host=False):
         keys = np.asarray(kw["keys"], np.uint32)
         keyt = keys if host else torch.tensor(keys.view(np.int32), device=dev)
         lv = dfx.BrownianIncrement if kw["levy_area"] == "bi" else dfx.SpaceTimeLevyArea
-        bm = dfx.VirtualBrownianTree(kw.get("bm_t0", 0.0), kw.get("bm_t1", 1.0), kw["bm_tol"], (), keyt, lv)
+        shape = (kw["bm_dim"],) if kw.get("bm_dim") else ()
+        bm = dfx.VirtualBrownianTree(kw.get("bm_t0", 0.0), kw.get("bm_t1", 1.0), kw["bm_tol"], shape, keyt, lv)
         terms = dfx.MultiTerm(dfx.ODETerm(field.drift), dfx.ControlTerm(field.diffusion, bm))
     else:
         terms = dfx.ODETerm(field)
@@ -677,6 +678,26 @@ def test_event_with_infinite_t1(dev):
     # of two implementations differ at the percent level; the event still fires on the same step
     assert relerr(to_np(sol.ts)[same], o["ts"][same]) < 0.1
     assert np.all(np.abs(to_np(sol.ys)) < 1.1e-6) and np.all(np.isfinite(to_np(sol.ts)))
+
+
+@pytest.mark.parametrize("solver,lv", [("heun", "bi"), ("shark", "stla")])
+@pytest.mark.parametrize("m", [2, 3])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_vector_brownian_motion_diagonal_noise(dev, solver, lv, m, dtype):
+    """VirtualBrownianTree(shape=(m,)) (tree.py:301: leaf keys split_by_tree(key, (m,)) = jr.split(key, m)) driving a diagonal
+    diffusion: m independent Ornstein-Uhlenbeck components, one tree each.  Fixed steps: the CUDA path equals the oracle, and
+    with partitionable threefry component 0's leaf key is the scalar tree's, so it reproduces the scalar solve bit for bit."""
+    n = 256
+    keys = dfx.random.split(dfx.random.key(11), n)
+    kw = dict(field="ou", params=[1.0, 0.0, 0.5, 0.2], y0=np.ones((n, m), dtype), dtype=dtype, t0=0.0, t1=1.0, dt0=2.0 ** -5, solver=solver,
+              controller="constant", levy_area=lv, keys=keys, bm_tol=2.0 ** -8, bm_dim=m, save_t1=True)
+    o, sol = _oracle(kw), run_case(kw, dev)
+    tol = 1e-12 if dtype == np.float64 else RTOL32
+    assert np.array_equal(stats_np(sol), o["stats"]) and relerr(to_np(sol.ys), o["ys"]) < tol
+    scalar = run_case(dict(kw, y0=np.ones((n, 1), dtype), bm_dim=0), dev)
+    assert torch.equal(sol.ys[:, -1, 0], scalar.ys[:, -1, 0])
+    comps = to_np(sol.ys)[:, -1, :]
+    assert np.abs(np.corrcoef(comps.T)[0, 1]) < 0.2                 # independent components
 
 
 def test_hairer_initial_step_flag(dev):
