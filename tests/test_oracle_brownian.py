@@ -110,3 +110,22 @@ def test_ou_moments():
         assert abs(y.mean() - np.exp(-1)) < 4 * np.sqrt(0.108 / n) + 2e-3
         assert abs(y.var() - 0.125 * (1 - np.exp(-2))) < 3e-3
         assert np.all(r["stats"][:, 0] == 64)
+
+
+def test_vector_brownian_motion_leaves():
+    """VirtualBrownianTree(shape=(m,)): leaf keys are split_by_tree(key, (m,)) = jr.split(key, m) (tree.py:301,
+    _misc.py:128-133).  With partitionable threefry split(key, m)[0] == split(key, 1)[0], so component 0 of a diagonal-noise
+    solve is the scalar solve; with the legacy layout the child keys depend on m and it is not.  Components are independent."""
+    import diffrax_b200 as dfx
+    n = 64
+    keys = dfx.random.split(dfx.random.key(21), n)
+    common = dict(params=[1.0, 0.0, 0.5], controller="constant", keys=keys, bm_tol=2.0 ** -8, solver="heun", levy_area="bi")
+    for part in (True, False):
+        vec = oracle.solve("ou", np.ones((n, 3)), 0.0, 1.0, 2.0 ** -5, bm_dim=3, partitionable=part, **common)
+        sca = oracle.solve("ou", np.ones((n, 1)), 0.0, 1.0, 2.0 ** -5, partitionable=part, **common)
+        same0 = np.array_equal(vec["ys"][:, -1, 0], sca["ys"][:, -1, 0])
+        assert same0 == part
+        c = np.corrcoef(vec["ys"][:, -1, :].T)
+        assert abs(c[0, 1]) < 0.4 and abs(c[0, 2]) < 0.4 and abs(c[1, 2]) < 0.4
+        # exact OU law per component: mean e^-1, variance sigma^2 (1 - e^-2) / 2
+        assert abs(vec["ys"][:, -1, :].mean() - np.exp(-1.0)) < 0.1
