@@ -325,12 +325,14 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         }
         {  // _integrate.py:847-877
           bool via_steps = false;
-          if (p.save_steps == 1) via_steps = true;
-          else if (p.save_steps > 1) via_steps = (num_accepted % p.save_steps) == 0;
+          if constexpr (RICH) {  // (the SaveAt(t1=True)-only instantiation has no steps and exactly one slot)
+            if (p.save_steps == 1) via_steps = true;
+            else if (p.save_steps > 1) via_steps = (num_accepted % p.save_steps) == 0;
+          }
           // 862-872: with an event root finder the final value is (re)written whenever steps would have saved it
           const bool ev_rule = EXTRA && p.n_events != 0 && p.event_root;
           const bool pred = ev_rule ? (p.save_t1 || via_steps) : (p.save_t1 && !via_steps);
-          if (pred && save_index < p.out_size) {
+          if (pred && (!RICH || save_index < p.out_size)) {
             const long long o = idx * (long long)p.out_size + save_index;
             p.ts_out[o] = tprev * direction;
   #pragma unroll
