@@ -88,7 +88,11 @@ def _ours_objects(w, dev=None):
     S = {"dopri5": dfx.Dopri5, "tsit5": dfx.Tsit5, "dopri8": dfx.Dopri8, "heun": dfx.Heun, "shark": dfx.ShARK}[w["solver"]]
     field = w["mlp"] if w["field"] == "mlp" else F(*w["params"])
     if w["levy_area"]:
-        keys = w["keys"] if dev is None else torch.tensor(w["keys"].view(np.int32), device=dev)
+        if dev is None:  # host path: the keys are an input of every step, so they sit in pinned memory like y0
+            keys = torch.from_numpy(w["keys"].view(np.int32).copy())
+            keys = keys.pin_memory() if torch.cuda.is_available() else keys
+        else:
+            keys = torch.tensor(w["keys"].view(np.int32), device=dev)
         lv = dfx.BrownianIncrement if w["levy_area"] == "bi" else dfx.SpaceTimeLevyArea
         bm = dfx.VirtualBrownianTree(0.0, 1.0, w["bm_tol"], (), keys, lv)
         term = dfx.MultiTerm(dfx.ODETerm(field.drift), dfx.ControlTerm(field.diffusion, bm))

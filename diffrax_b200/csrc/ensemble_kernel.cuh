@@ -110,6 +110,13 @@ struct SolveParams {
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
   R *y_final, *t_final;
   unsigned long long *work_counter;
+  // Host-pipelined mode (dfx_ensemble_solve_host; SaveAt(t1=True) instantiation only): ONE launch over the whole batch
+  // while the copy engines bring the inputs in and take the results out in chunks of pipe_chunk_len trajectories.
+  const unsigned *pipe_in_ready;  // device word: number of input chunks resident so far (bumped by a 4-byte H2D copy
+                                  // that is stream-ordered after the chunk's data)
+  unsigned *pipe_done;            // device: finalised trajectories per chunk
+  unsigned *pipe_host_flags;      // mapped pinned host memory: word c becomes 1 when every result of chunk c is written
+  int pipe_chunk_len;             // multiple of 32 trajectories, so no 128-byte line straddles two chunks
   const uint32_t *keys;
   VbtParams vbt;
 };
@@ -352,6 +359,25 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           for (int c = 0; c < D; ++c) p.y_final[idx * D + c] = y[c];
         }
         if (p.t_final) p.t_final[idx] = tprev * direction;
+        if constexpr (!RICH) {
+          if (p.pipe_done != nullptr) {  // release this trajectory's results; the last one of a chunk tells the host
+            __threadfence();
+            const int c = (int)(idx / p.pipe_chunk_len);
+            const long long rest = p.n_traj - (long long)c * p.pipe_chunk_len;
+            const unsigned cnt = (unsigned)(rest < p.pipe_chunk_len ? rest : (long long)p.pipe_chunk_len);
+            // one atomic per group of lanes that finalise into the same chunk (fixed-step ensembles finish in waves)
+            const unsigned peers = __match_any_sync(__activemask(), c);
+            unsigned total = 0;
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) total = atomicAdd(p.pipe_done + c, (unsigned)__popc(peers)) + (unsigned)__popc(peers);
+            if (total == cnt) {
+              __threadfence_system();
+              // (the value is a device timestamp in ~us, never 0: DFX_HOST_PIPE_TRACE prints it next to the host's clock)
+              unsigned long long gt;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+              *(volatile unsigned *)(p.pipe_host_flags + c) = (unsigned)(gt >> 10) | 1u;
+            }
+          }
+        }
         if constexpr (EXTRA) {
           if (p.state_out != nullptr) {
             R *so = p.state_out + idx * (5 + D);
@@ -402,6 +428,13 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         if (got >= 0 && got < p.n_traj) {
           idx_i = (int)got;
           const long long idx = got;
+          if constexpr (!RICH) {
+            if (p.pipe_in_ready != nullptr) {  // wait until the copy engine has delivered this trajectory's chunk
+              const unsigned need = (unsigned)(idx / p.pipe_chunk_len) + 1u;
+              while (*(volatile const unsigned *)p.pipe_in_ready < need) __nanosleep(200);
+              __threadfence();
+            }
+          }
           // _integrate.py:1076-1079, 1157-1165: time dtype and direction normalisation
           R a = p.t0_arr ? p.t0_arr[idx] : p.t0;
           R b = p.t1_arr ? p.t1_arr[idx] : p.t1;

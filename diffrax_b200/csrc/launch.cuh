@@ -14,6 +14,16 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int register_builtin(int field_id, int dim, int solver_id, int dtype, int levy, dfx_launcher_fn fn);
 
+// Host-pipelined mode: dfx_ensemble_solve_host parks the control words of its chunk pipeline here (thread-local,
+// api.cu) around its one dfx_ensemble_solve call; the launcher that picks them up says so through `consumed`.
+struct HostPipe {
+  const unsigned *in_ready;
+  unsigned *done, *host_flags;
+  int chunk_len;
+  bool consumed;
+};
+HostPipe *&host_pipe();
+
 #define DFX_CUDA_OK(expr)                                                                  \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \
@@ -196,6 +206,14 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   const bool extra = (d->hairer_initial_step && std::isnan(d->dt0)) || d->step_ts || d->jump_ts || d->n_events != 0 ||
                      d->state_in || d->state_out || d->store_rejected_steps > 0;
   const bool rich = extra || d->save_t0 || d->save_ts || d->save_steps || d->save_dense;
+  if (HostPipe *hp = host_pipe()) {
+    if (rich) { set_error("internal: the host pipeline only drives the SaveAt(t1=True) kernel"); return DFX_ERR_BAD_ARGUMENT; }
+    p.pipe_in_ready = hp->in_ready;
+    p.pipe_done = hp->done;
+    p.pipe_host_flags = hp->host_flags;
+    p.pipe_chunk_len = hp->chunk_len;
+    hp->consumed = true;
+  }
 
   // scratch: the work-queue counter.  (The +inf padding of unfilled output slots is written by the solve kernel itself
   // when it finalises a trajectory, so there is no second pass over the buffers.)

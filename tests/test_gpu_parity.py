@@ -759,6 +759,36 @@ def test_full_size_properties_c2(dev):
     assert relerr(to_np(a.ys)[sl], o["ys"]) < 1e-9
 
 
+def test_host_pipeline_matches_device_path(dev, monkeypatch):
+    """dfx_ensemble_solve_host above 256K trajectories runs ONE launch whose inputs arrive and whose results leave chunk by
+    chunk while it runs (in_ready word / per-chunk completion flags).  Ragged sizes, odd chunk counts and the SDE inputs
+    (per-trajectory keys) give the same bits as the device path, and as the multi-launch fallback (DFX_HOST_PIPE=0)."""
+    n = (1 << 18) + 777
+    rng = np.random.default_rng(5)
+    y0 = np.stack([rng.uniform(-15, 15, n), rng.uniform(-20, 20, n), rng.uniform(5, 45, n)], 1)
+    term, ctrl = dfx.ODETerm(dfx.fields.Lorenz()), dfx.PIDController(1e-6, 1e-6)
+    a = dfx.diffeqsolve(term, dfx.Dopri5(), 0.0, 0.5, None, torch.tensor(y0, device=dev), stepsize_controller=ctrl)
+    for chunks, pipe in (("5", "1"), ("16", "1"), ("64", "1"), ("1", "1"), ("3", "0")):
+        monkeypatch.setenv("DFX_HOST_CHUNKS", chunks)
+        monkeypatch.setenv("DFX_HOST_PIPE", pipe)
+        h = dfx.diffeqsolve(term, dfx.Dopri5(), 0.0, 0.5, None, y0, stepsize_controller=ctrl)
+        assert np.array_equal(h.ys, to_np(a.ys)) and np.array_equal(h.ts, to_np(a.ts)), (chunks, pipe)
+        assert np.array_equal(h.stats["num_steps"], to_np(a.stats["num_steps"])) and np.array_equal(h.result, to_np(a.result))
+        assert np.array_equal(h.stats["num_rejected_steps"], to_np(a.stats["num_rejected_steps"]))
+    monkeypatch.setenv("DFX_HOST_CHUNKS", "7")
+    monkeypatch.setenv("DFX_HOST_PIPE", "2")  # fixed-step solves take the multi-launch path by default; 2 forces the pipeline
+    keys = dfx.random.split(dfx.random.key(3), n)
+    ou = dfx.fields.OrnsteinUhlenbeck(1.0, 0.0, 0.5)
+    y1 = np.ones((n, 1), np.float32)
+    sols = []
+    for host in (False, True):
+        kk = keys if host else torch.tensor(keys.view(np.int32), device=dev)
+        bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -6, (), kk)
+        sols.append(dfx.diffeqsolve(dfx.MultiTerm(dfx.ODETerm(ou.drift), dfx.ControlTerm(ou.diffusion, bm)), dfx.Heun(), 0.0, 1.0,
+                                    2.0 ** -4, y1 if host else torch.tensor(y1, device=dev)))
+    assert np.array_equal(to_np(sols[0].ys), to_np(sols[1].ys)) and np.array_equal(to_np(sols[0].stats["num_steps"]), to_np(sols[1].stats["num_steps"]))
+
+
 def test_full_size_properties_c5(dev):
     """BASELINE config 5 at full size: 2^20 OU paths, Heun + BrownianIncrement and ShARK + SpaceTimeLevyArea, fp32.
     Properties: exact step count, ensemble moments of the exact OU law, slice parity with the oracle."""
