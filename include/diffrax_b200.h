@@ -184,7 +184,9 @@ int dfx_out_size(const dfx_solve_desc *desc);
 int dfx_ensemble_solve(const dfx_solve_desc *desc, void *cuda_stream);
 
 /* same call with HOST buffers: copies inputs H2D, solves, copies outputs D2H, synchronises.
- * `device` selects the CUDA device.  This is the end-to-end (`e2e`) path of bench.py. */
+ * `device` selects the CUDA device.  This is the end-to-end (`e2e`) path of bench.py.
+ * Pass pinned buffers for full PCIe speed.  Large adaptive SaveAt(t1=True) solves run as one launch
+ * with the transfers chunked alongside it; everything else as up to 8 pipelined launches. */
 int dfx_ensemble_solve_host(const dfx_solve_desc *desc, int device);
 
 /* replaces VirtualBrownianTree.evaluate(t0, t1, use_levy=True) vmapped over keys
