@@ -66,6 +66,15 @@ def test_fails_loudly_without_a_gpu():
         dfx.diffeqsolve(TERM, dfx.Dopri5(), 0.0, 1.0, None, Y0, stepsize_controller=PID)
 
 
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_pipelined_host_entry_fails_loudly_without_a_gpu():
+    """The size class that dfx_ensemble_solve_host runs as one launch with chunked transfers (>= 256K trajectories,
+    adaptive, SaveAt(t1)) is refused the same way - before any stream, allocation or polling loop is set up."""
+    y0 = np.ones((1 << 18, 3))
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        dfx.diffeqsolve(TERM, dfx.Dopri5(), 0.0, 1.0, None, y0, stepsize_controller=PID)
+
+
 def test_product_never_imports_the_oracle():
     import re
     pkg = os.path.join(ROOT, "diffrax_b200")
