@@ -617,6 +617,9 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
       progress = true;
     }
     if (progress || remaining == 0) continue;
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();  // polite busy-wait: the flags arrive over PCIe, microseconds apart at best
+#endif
     if (kernel_done) { set_error("internal: %d chunks were never completed", remaining); rc = DFX_ERR_CUDA; break; }
     if ((spin & 1023) == 0) {  // a finished or failed kernel ends the wait (one more pass picks up its last flags)
       const cudaError_t q = cudaEventQuery(ev_k);
