@@ -447,8 +447,8 @@ class SpaceTimeLevyArea:
 class VirtualBrownianTree:
     """tree.py:245-301.  ``key`` is an ``[N, 2]`` uint32 array: one tree per trajectory, the
     pattern ``jax.vmap(lambda k: VirtualBrownianTree(t0, t1, tol, (), k))(jr.split(root, N))`` of
-    test/helpers.py:140-169.  ``shape`` is ``()`` (scalar noise) or ``(m,)`` (m independent components for a diagonal
-    diffusion; ``evaluate`` here covers ``()`` only)."""
+    test/helpers.py:140-169.  ``shape`` is ``()`` or ``(m,)``; like the reference, a tuple of ints is ONE leaf
+    (tree.py:291-295) keyed ``jr.split(key, 1)[0]`` (tree.py:301) whose nodes draw ``jr.normal(key, shape)``."""
 
     def __init__(self, t0, t1, tol, shape, key, levy_area=BrownianIncrement, *, partitionable: bool = True):
         if not (t0 < t1):
@@ -457,26 +457,27 @@ class VirtualBrownianTree:
         if len(shape) > 1:
             raise NotImplementedError("Brownian motion of shape () or (m,) is implemented")
         self.t0, self.t1, self.tol = float(t0), float(t1), float(tol)
-        self.shape = shape   # (m,): m independent trees, leaf keys jr.split(key, m) (tree.py:301), driving a diagonal diffusion
+        self.shape = shape
         self.levy_area = levy_area
         self.key = key
         self.partitionable = bool(partitionable)
 
     def evaluate(self, t0, t1, left=True, use_levy=False):
-        """tree.py:326-354, vmapped over the keys.  Returns W (and H when use_levy)."""
+        """tree.py:326-354, vmapped over the keys.  Returns W (and H when use_levy), ``[N]`` or ``[N, m]``."""
         keys = _as_keys(self.key)
         xp = _Backend.of(keys)
         n = keys.shape[0]
         dtype = np.float64 if not hasattr(t0, "dtype") else None
         ta = xp.as_real(t0, n, dtype)
         tb = xp.as_real(t1, n, ta.dtype if dtype is None else dtype)
-        W = xp.empty((n,), ta.dtype)
-        H = xp.empty((n,), ta.dtype)
+        m = int(self.shape[0]) if self.shape else 0
+        W = xp.empty((n, m) if m else (n,), ta.dtype)
+        H = xp.empty((n, m) if m else (n,), ta.dtype)
         L = _lib.lib()
         if xp.device_ptrs:
             _lib.check(L.dfx_vbt_evaluate(xp.dtype_id(ta.dtype), self.levy_area.levy_id, int(self.partitionable), n,
                                           xp.ptr(keys), self.t0, self.t1, self.tol, xp.ptr(ta), xp.ptr(tb), 1,
-                                          xp.ptr(W), xp.ptr(H), xp.stream()))
+                                          xp.ptr(W), xp.ptr(H), m, xp.stream()))
         else:
             raise RuntimeError("VirtualBrownianTree.evaluate needs keys on a CUDA device")
         return (W, H) if use_levy else W
@@ -897,9 +898,12 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     ys_out = xp.empty((n, T, d), rdt)
     stats = xp.empty((n, 3), i32)
     result = xp.empty((n,), i32)
-    # final state: with SaveAt(t1=True) it is ys[:, -1] already; a separate buffer only when t1 is not saved
+    # final state: with plain SaveAt(t1=True) (exactly one slot) it is ys[:, 0] already.  Every other mode gets dedicated
+    # buffers: the kernel writes the final value at the trajectory's running save index, which is the LAST slot only
+    # when every earlier slot was filled - not under SaveAt(steps=...) (unused slots are +inf padding), nor when an
+    # event or max_steps ends a SaveAt(ts=..., t1=True) solve early.
     y_final = t_final = None
-    if not saveat.t1:
+    if not (saveat.t1 and T == 1):
         y_final = xp.empty((n, d), rdt)
         t_final = xp.empty((n,), rdt)
     D.ts_out, D.ys_out, D.stats, D.result = xp.ptr(ts_out), xp.ptr(ys_out), xp.ptr(stats), xp.ptr(result)

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdiffrax_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F64, F32 = 0, 1
 CTRL_CONSTANT, CTRL_PID = 0, 1
 LEVY_NONE, LEVY_BI, LEVY_STLA = 0, 1, 2
@@ -98,10 +98,10 @@ def lib():
     L.dfx_ensemble_solve.argtypes = [C.POINTER(SolveDesc), C.c_void_p]
     L.dfx_ensemble_solve_host.argtypes = [C.POINTER(SolveDesc), C.c_int]
     L.dfx_vbt_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_double,
-                                   C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+                                   C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.dfx_threefry2x32.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dfx_random_split.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    L.dfx_random_normal.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.dfx_random_normal.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     L.dfx_dense_evaluate.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]

@@ -99,26 +99,42 @@ __global__ void split_kernel(long long n, const uint32_t *keys, int num, int par
   }
 }
 
-template <class R>
+// jax.random.normal(key, shape, dtype) for n keys; shape () (m == 0) or (m,)
+template <class R, int M>
 __global__ void normal_kernel(long long n, const uint32_t *keys, int partitionable, R *out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = random_normal<R>(Key{keys[2 * i], keys[2 * i + 1]}, partitionable != 0);
+#pragma unroll
+  for (int w = 0; w < M; ++w) out[i * M + w] = random_normal<R, M>(Key{keys[2 * i], keys[2 * i + 1]}, partitionable != 0, w);
 }
 
-template <class R, bool STLA>
+template <class R, bool STLA, int M>
 __global__ void vbt_kernel(long long n, const uint32_t *keys, VbtParams vp, const R *ta, const R *tb, int per_traj,
                            R *W, R *H) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  BrownianTree<R, STLA> bm;
+  BrownianTree<R, STLA, M> bm;
   bm.init(keys + 2 * i, vp);
-  R w, h;
+  R w[M], h[M];
   bm.increment(ta[per_traj ? i : 0], tb[per_traj ? i : 0], vp, w, h);
-  W[i] = w;
-  if (H) H[i] = h;
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    W[i * M + c] = w[c];
+    if (H) H[i * M + c] = h[c];
+  }
 }
 
+template <class R, int M>
+static void launch_normal(int64_t n, const uint32_t *keys, int partitionable, void *out, cudaStream_t st) {
+  normal_kernel<R, M><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, keys, partitionable, (R *)out);
+}
+template <class R, int M>
+static void launch_vbt(bool stla, int64_t n, const uint32_t *keys, const VbtParams &vp, const void *ta, const void *tb, int per_traj,
+                       void *W, void *H, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (stla) vbt_kernel<R, true, M><<<blocks, 128, 0, st>>>(n, keys, vp, (const R *)ta, (const R *)tb, per_traj, (R *)W, (R *)H);
+  else vbt_kernel<R, false, M><<<blocks, 128, 0, st>>>(n, keys, vp, (const R *)ta, (const R *)tb, per_traj, (R *)W, (R *)H);
+}
 // DenseInterpolation.evaluate / .derivative (_global_interpolation.py:335-368), one thread per (trajectory, query).
 template <class R, class Solver, int D, bool DERIV>
 __global__ void dense_eval_kernel(long long n_traj, int max_steps, const R *dts, const R *dy0, const R *dy1,
@@ -461,6 +477,8 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
 static constexpr int kMaxPipeChunks = 64;
 static bool host_pipe_eligible(const dfx_solve_desc *h) {
   if (const char *e = std::getenv("DFX_HOST_PIPE")) { if (atoi(e) == 0) return false; }
+  // the kernel waits for chunks that are enqueued after its launch returns: with synchronous launches that never happens
+  if (const char *e = std::getenv("CUDA_LAUNCH_BLOCKING")) { if (atoi(e) != 0) return false; }
   const bool extra = (h->hairer_initial_step && std::isnan(h->dt0)) || h->step_ts || h->jump_ts || h->n_events != 0 ||
                      h->state_in || h->state_out || h->store_rejected_steps > 0;
   const bool rich = extra || h->save_t0 || h->save_ts || h->save_steps || h->save_dense;
@@ -486,14 +504,16 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
   const int nchunks = (int)((N + chunk_len - 1) / chunk_len);
 
   // per-thread pinned control block: [0, 64) completion flags written by the kernel, [64, 128) the values 1..64 that
-  // the copy engine moves into `in_ready`
+  // the copy engine moves into `in_ready`, [128] the abort word the kernel reads while it waits for inputs
   static thread_local unsigned *ctl_host = nullptr;
   if (!ctl_host) {
-    DFX_CUDA_OK(cudaHostAlloc((void **)&ctl_host, 2 * kMaxPipeChunks * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable));
+    DFX_CUDA_OK(cudaHostAlloc((void **)&ctl_host, (2 * kMaxPipeChunks + 1) * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable));
     for (int i = 0; i < kMaxPipeChunks; ++i) ctl_host[kMaxPipeChunks + i] = (unsigned)(i + 1);
   }
   volatile unsigned *flags = ctl_host;
   for (int i = 0; i < nchunks; ++i) flags[i] = 0;
+  volatile unsigned *abort_word = ctl_host + 2 * kMaxPipeChunks;
+  *abort_word = 0;
   unsigned *flags_dev = nullptr;
   DFX_CUDA_OK(cudaHostGetDevicePointer((void **)&flags_dev, ctl_host, 0));
 
@@ -589,7 +609,7 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
   bool launched = false;
   t_enq = now_ms();
   if (!rc) {
-    HostPipe hp{ctl_dev, ctl_dev + 1, flags_dev, (int)chunk_len, false};
+    HostPipe hp{ctl_dev, ctl_dev + 1, flags_dev, flags_dev + 2 * kMaxPipeChunks, (int)chunk_len, false};
     host_pipe() = &hp;
     rc = dfx_ensemble_solve(&d, (void *)s_k);
     host_pipe() = nullptr;
@@ -598,7 +618,12 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
     if (launched) PIPE_OK(cudaEventRecord(ev_k, s_k));
   }
   t_launch = now_ms();
+  if (const char *e = std::getenv("DFX_HOST_PIPE_FAULT")) {  // test hook: chunk delivery fails right after the launch
+    if (launched && atoi(e) != 0) fail("injected fault", cudaErrorUnknown);
+  }
   for (int c = 1; c < nchunks && launched && !rc; ++c) enqueue_inputs(c);
+  // If anything failed after the launch, some chunks will never be delivered: release the kernel's waiting lanes.
+  if (launched && rc) { *abort_word = 1; __sync_synchronize(); }
   const double t_enq_all = now_ms();
   std::vector<unsigned> v_flag;
   // chunks complete roughly, not exactly, in order: every pass sends whichever have become ready
@@ -625,8 +650,11 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
       const cudaError_t q = cudaEventQuery(ev_k);
       if (q == cudaSuccess) kernel_done = true;
       else if (q != cudaErrorNotReady) fail("ensemble kernel", q);
+      const cudaError_t qi = cudaStreamQuery(s_in);  // an input copy that failed asynchronously never bumps in_ready
+      if (qi != cudaSuccess && qi != cudaErrorNotReady) fail("input copies", qi);
     }
   }
+  if (launched && rc) { *abort_word = 1; __sync_synchronize(); }  // never leave the kernel waiting for inputs
   if (trace && s_k) { cudaStreamSynchronize(s_k); t_k = now_ms(); }
   for (cudaStream_t st : {s_in, s_k, s_out})
     if (st) { const cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) fail("stream sync", e); }
@@ -689,11 +717,16 @@ int dfx_random_split(int64_t n, const uint32_t *keys, int num, int partitionable
   DFX_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int dfx_random_normal(int dtype, int64_t n, const uint32_t *keys, int partitionable, void *out, void *stream) {
+int dfx_random_normal(int dtype, int64_t n, const uint32_t *keys, int partitionable, void *out, int m, void *stream) {
   if (n <= 0) return 0;
-  const unsigned blocks = (unsigned)((n + 255) / 256);
-  if (dtype == DFX_F64) normal_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, keys, partitionable, (double *)out);
-  else normal_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, keys, partitionable, (float *)out);
+  if (m < 0 || m > kMaxDim) { set_error("normal: shape (m,) with 0 <= m <= %d (0 = scalar), got %d", kMaxDim, m); return DFX_ERR_BAD_ARGUMENT; }
+  cudaStream_t st = (cudaStream_t)stream;
+#define DFX_NORMAL_CASE(M) case M: if (dtype == DFX_F64) launch_normal<double, M>(n, keys, partitionable, out, st); else launch_normal<float, M>(n, keys, partitionable, out, st); break;
+  switch (m == 0 ? 1 : m) {
+    DFX_NORMAL_CASE(1) DFX_NORMAL_CASE(2) DFX_NORMAL_CASE(3) DFX_NORMAL_CASE(4)
+    DFX_NORMAL_CASE(5) DFX_NORMAL_CASE(6) DFX_NORMAL_CASE(7) DFX_NORMAL_CASE(8)
+  }
+#undef DFX_NORMAL_CASE
   count_launch();
   DFX_CUDA_OK(cudaGetLastError());
   return 0;
@@ -701,25 +734,22 @@ int dfx_random_normal(int dtype, int64_t n, const uint32_t *keys, int partitiona
 
 int dfx_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, const uint32_t *keys, double bm_t0,
                      double bm_t1, double bm_tol, const void *ta, const void *tb, int per_traj_times, void *W, void *H,
-                     void *stream) {
+                     int bm_dim, void *stream) {
   if (n <= 0) return 0;
   if (!(bm_t0 < bm_t1)) { set_error("t0 must be strictly less than t1"); return DFX_ERR_BAD_ARGUMENT; }
+  if (bm_dim < 0 || bm_dim > 4) { set_error("VirtualBrownianTree shape () or (m,) with m <= 4, got m = %d", bm_dim); return DFX_ERR_BAD_ARGUMENT; }
   VbtParams vp;
   vp.t0 = bm_t0; vp.t1 = bm_t1; vp.levy = levy_area; vp.partitionable = partitionable;
+  vp.cache_levels = 0; vp.cache_stride = 0;
   const double tol_n = bm_tol / (bm_t1 - bm_t0);
   int depth = 0;
   while (std::ldexp(1.0, -depth) > tol_n && depth < 1000) ++depth;
   vp.depth = depth;
-  const unsigned blocks = (unsigned)((n + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   const bool stla = levy_area == DFX_LEVY_SPACE_TIME;
-  if (dtype == DFX_F64) {
-    if (stla) vbt_kernel<double, true><<<blocks, 128, 0, st>>>(n, keys, vp, (const double *)ta, (const double *)tb, per_traj_times, (double *)W, (double *)H);
-    else vbt_kernel<double, false><<<blocks, 128, 0, st>>>(n, keys, vp, (const double *)ta, (const double *)tb, per_traj_times, (double *)W, (double *)H);
-  } else {
-    if (stla) vbt_kernel<float, true><<<blocks, 128, 0, st>>>(n, keys, vp, (const float *)ta, (const float *)tb, per_traj_times, (float *)W, (float *)H);
-    else vbt_kernel<float, false><<<blocks, 128, 0, st>>>(n, keys, vp, (const float *)ta, (const float *)tb, per_traj_times, (float *)W, (float *)H);
-  }
+#define DFX_VBT_CASE(M) case M: if (dtype == DFX_F64) launch_vbt<double, M>(stla, n, keys, vp, ta, tb, per_traj_times, W, H, st); else launch_vbt<float, M>(stla, n, keys, vp, ta, tb, per_traj_times, W, H, st); break;
+  switch (bm_dim == 0 ? 1 : bm_dim) { DFX_VBT_CASE(1) DFX_VBT_CASE(2) DFX_VBT_CASE(3) DFX_VBT_CASE(4) }
+#undef DFX_VBT_CASE
   count_launch();
   DFX_CUDA_OK(cudaGetLastError());
   return 0;

@@ -116,6 +116,7 @@ struct SolveParams {
                                   // that is stream-ordered after the chunk's data)
   unsigned *pipe_done;            // device: finalised trajectories per chunk
   unsigned *pipe_host_flags;      // mapped pinned host memory: word c becomes 1 when every result of chunk c is written
+  const unsigned *pipe_abort;     // mapped pinned host memory: non-zero = the host cannot deliver the remaining inputs
   int pipe_chunk_len;             // multiple of 32 trajectories, so no 128-byte line straddles two chunks
   const uint32_t *keys;
   VbtParams vbt;
@@ -243,12 +244,13 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   [[maybe_unused]] constexpr bool kChainY0 = DFX_OPT_CHAIN_Y0 && TAB && !SDE && Solver::S <= 7;
   [[maybe_unused]] constexpr bool kLastStageF = DFX_OPT_LAST_STAGE_F && TAB && FSAL && Solver::kSsal;
   constexpr int INTERP = Solver::kInterp;
-  constexpr int NW = NoiseDim<Field>::value;  // independent Brownian components: 1 (shape=()) or D (shape=(D,), diagonal diffusion)
+  constexpr int NW = NoiseDim<Field>::value;  // Brownian components: 1 (shape=()) or D (shape=(D,), diagonal diffusion)
   constexpr bool DENSE_K = INTERP != kInterpLinear;
   constexpr bool FAST_PID = TAB && !SDE && sizeof(R) == 8;  // fp64 ODE solves: division-/pow-free I-controller path
 
   // ---- per-lane trajectory state (registers) ----
   bool active = false, exhausted = false;
+  [[maybe_unused]] bool pipe_aborted = false;  // host-pipelined mode: the host gave up delivering inputs
   int idx_i = -1;  // trajectory index (n_traj < 2^31 is checked on the host); widened at each use
   R y[D], f_fsal[D];
   R tprev = R(0), tnext = R(0), t0 = R(0), t1 = R(0), direction = R(1), t1_clip_floor = R(0);
@@ -261,7 +263,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   [[maybe_unused]] bool made_jump = false;
   [[maybe_unused]] int reject_index = 0;  // ClipStepSizeController(store_rejected_steps=K): top of the stack, K = empty
   [[maybe_unused]] R event_value[DFX_MAX_EVENTS] = {};  // Event: the cond_fns at the previous state (EXTRA only)
-  BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME> bm[NW];
+  BrownianTree<R, LEVY == DFX_LEVY_SPACE_TIME, NW> bm;  // one tree; shape (m,) = m components sharing the key path
 #pragma unroll
   for (int c = 0; c < D; ++c) { y[c] = R(0); f_fsal[c] = R(0); }
 
@@ -301,10 +303,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   // dynamic shared memory: [VBT descent cache (SDE kernels)] [dense staging records (RICH, SaveAt(dense))]
   extern __shared__ __align__(16) unsigned char dense_smem_raw[];
   [[maybe_unused]] R *dense_smem = reinterpret_cast<R *>(dense_smem_raw + p.dense_smem_offset);
-  if constexpr (SDE) {
-#pragma unroll
-    for (int w = 0; w < NW; ++w) bm[w].attach_cache(reinterpret_cast<R *>(dense_smem_raw) + w * p.vbt.cache_levels * VbtCache<R, LEVY == DFX_LEVY_SPACE_TIME>::kWords * p.vbt.cache_stride, p.vbt);
-  }
+  if constexpr (SDE) bm.attach_cache(reinterpret_cast<R *>(dense_smem_raw), p.vbt);
 
   for (;;) {
     // Finalising a trajectory and claiming + initialising the next one is ~300 instructions that the whole warp
@@ -431,10 +430,16 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           if constexpr (!RICH) {
             if (p.pipe_in_ready != nullptr) {  // wait until the copy engine has delivered this trajectory's chunk
               const unsigned need = (unsigned)(idx / p.pipe_chunk_len) + 1u;
-              while (*(volatile const unsigned *)p.pipe_in_ready < need) __nanosleep(200);
+              // the host raises the abort word (mapped host memory, read only while waiting) when it cannot deliver the
+              // remaining chunks, e.g. after a failed H2D enqueue: the kernel must never outwait a host that gave up
+              while (*(volatile const unsigned *)p.pipe_in_ready < need) {
+                if (*(volatile const unsigned *)p.pipe_abort != 0u) { pipe_aborted = true; break; }
+                __nanosleep(200);
+              }
               __threadfence();
             }
           }
+          if (!pipe_aborted) {
           // _integrate.py:1076-1079, 1157-1165: time dtype and direction normalisation
           R a = p.t0_arr ? p.t0_arr[idx] : p.t0;
           R b = p.t1_arr ? p.t1_arr[idx] : p.t1;
@@ -450,7 +455,8 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             if (p.has_dtmin) dt0 = jnp_max(dt0, p.dtmin);
           } else {
             const R dt0_up = Num<R>::from_bits(Num<R>::bits(dt0) + (dt0 > R(0) ? 1 : (dt0 < R(0) ? -1 : 1)));  // nextafter(dt0, +inf)
-            cs_num_steps = (int)ceil((double)((t1 - t0) / dt0_up));
+            // constant.py:52-54: an infinite t1 (steady-state set-ups) is marked num_steps = -1 and steps by dt0
+            cs_num_steps = r_isinf(t1) ? -1 : (int)ceil((double)((t1 - t0) / dt0_up));
           }
           tprev = t0;
           tnext = t0 + dt0;
@@ -471,10 +477,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           pid_inv = R(1); pid_prev_inv = R(1); at_dtmin = false;
           num_steps = 0; num_accepted = 0; result = DFX_RESULT_SUCCESSFUL;
           save_index = 0; saveat_ts_index = 0; dense_index = 0;
-          if constexpr (SDE) {
-#pragma unroll
-            for (int w = 0; w < NW; ++w) bm[w].template init_leaf<NW>(p.keys + 2 * idx, w, p.vbt);  // split_by_tree(key, shape)[w]
-          }
+          if constexpr (SDE) bm.init(p.keys + 2 * idx, p.vbt);  // leaf key = split_by_tree(key, shape)[0] (tree.py:301)
           if constexpr (FSAL) {
             // runge_kutta.py:684-695: the first step evaluates stage 0 at (t0, y0); a rejected first
             // step re-evaluates the same point, so computing it once here is value-identical.
@@ -541,7 +544,11 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             for (int i = 0; i < p.n_events; ++i) event_value[i] = event_cond(i, tprev, y, direction);  // _integrate.py:1432-1476
           }
           active = true;
+          }
         }
+      }
+      if constexpr (!RICH) {
+        if (p.pipe_in_ready != nullptr && __any_sync(kFullMask, pipe_aborted)) exhausted = true;  // stop claiming
       }
       }
     }
@@ -564,10 +571,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           R Wv[NW], Hv[NW];
 #pragma unroll
           for (int w = 0; w < NW; ++w) { Wv[w] = R(0); Hv[w] = R(0); }
-          if constexpr (SDE) {
-#pragma unroll
-            for (int w = 0; w < NW; ++w) bm[w].increment(st0, st1, p.vbt, Wv[w], Hv[w]);
-          }
+          if constexpr (SDE) bm.increment(st0, st1, p.vbt, Wv, Hv);
           auto Wc = [&](int c) { return Wv[NW == 1 ? 0 : c]; };
           auto Hc = [&](int c) { return Hv[NW == 1 ? 0 : c]; };
 
@@ -807,6 +811,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           const int cs_steps_completed = num_steps + 2;
           R t1n = t0 + (t1 - t0) * ((R)cs_steps_completed / (R)cs_num_steps);
           if (cs_steps_completed == cs_num_steps) t1n = t1;
+          if (cs_num_steps < 0) t1n = st1 + p.dt0 * direction;  // constant.py:93 (t1_sim_or_dt0 = dt0)
           next_t0 = st1;
           next_t1 = t1n;
         }

@@ -19,6 +19,7 @@ int register_builtin(int field_id, int dim, int solver_id, int dtype, int levy, 
 struct HostPipe {
   const unsigned *in_ready;
   unsigned *done, *host_flags;
+  const unsigned *abort;
   int chunk_len;
   bool consumed;
 };
@@ -153,8 +154,9 @@ int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, c
   p.vbt.cache_stride = kBlockThreads;
   if (LEVY != DFX_LEVY_NONE) {
     static const int env_cache = [] { const char *e = getenv("DFX_VBT_CACHE"); return e ? atoi(e) : 1; }();
-    const size_t per_level = (size_t)(LEVY == DFX_LEVY_SPACE_TIME ? 7 : 5) * kBlockThreads * sizeof(R);  // per tree
-    constexpr int kTrees = NoiseDim<Field>::value;                                                          // one tree per Brownian component
+    constexpr int kWordsPerLevel = VbtCache<R, LEVY == DFX_LEVY_SPACE_TIME, NoiseDim<Field>::value>::kWords;
+    const size_t per_level = (size_t)kWordsPerLevel * kBlockThreads * sizeof(R);
+    constexpr int kTrees = 1;  // one tree per trajectory, whatever the Brownian shape
     int levels = env_cache ? (int)((24 * 1024) / (per_level * kTrees)) : 0;
     if (levels > p.vbt.depth) levels = p.vbt.depth;
     if (levels > 32) levels = 32;
@@ -211,6 +213,7 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
     p.pipe_in_ready = hp->in_ready;
     p.pipe_done = hp->done;
     p.pipe_host_flags = hp->host_flags;
+    p.pipe_abort = hp->abort;
     p.pipe_chunk_len = hp->chunk_len;
     hp->consumed = true;
   }

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DFX_ABI_VERSION 1
+#define DFX_ABI_VERSION 2
 
 enum dfx_dtype { DFX_F64 = 0, DFX_F32 = 1 };
 
@@ -135,9 +135,11 @@ typedef struct dfx_solve_desc {
   const uint32_t *bm_keys;    /* [N, 2] the keys the user passed to VirtualBrownianTree */
   double bm_t0, bm_t1, bm_tol;
   int32_t threefry_partitionable; /* jax_threefry_partitionable (default True since JAX 0.5) */
-  int32_t bm_dim;                 /* 0: VirtualBrownianTree(shape=()); m > 0: shape=(m,) with m == dim - one independent tree per
-                                   * state component (leaf keys split_by_tree(key, (m,)) = split(key, m); tree.py:301,
-                                   * _misc.py:128-133) driving a diagonal diffusion.  Kernels: the OU functor with dim 2, 3. */
+  int32_t bm_dim;                 /* 0: VirtualBrownianTree(shape=()); m > 0: shape=(m,).  Either way the tree has ONE leaf
+                                   * (a tuple of ints is a single ShapeDtypeStruct, tree.py:291-295) keyed split(key, 1)[0]
+                                   * (tree.py:301, _misc.py:128-133); each node draws jr.normal(key, (m,)), so the m
+                                   * components share the key path.  Kernels: the OU functor with dim 2, 3 (diagonal
+                                   * diffusion, m == dim). */
 
   /* Event(cond_fn, root_finder, direction): _event.py:13-118, _integrate.py:542-633 (detection), 691-821 (root find, unsave).
    * Up to DFX_MAX_EVENTS registered condition functions (the flattened PyTree `cond_fn`; the first one that triggers on a
@@ -190,10 +192,11 @@ int dfx_ensemble_solve(const dfx_solve_desc *desc, void *cuda_stream);
 int dfx_ensemble_solve_host(const dfx_solve_desc *desc, int device);
 
 /* replaces VirtualBrownianTree.evaluate(t0, t1, use_levy=True) vmapped over keys
- * (tree.py:326-354).  ta/tb: [n] if per_traj_times else [1].  W, H: [n]; H may be NULL. */
+ * (tree.py:326-354).  ta/tb: [n] if per_traj_times else [1].  bm_dim: 0 = shape (), m = shape (m,) (m <= 4).
+ * W, H: [n] or [n, m]; H may be NULL. */
 int dfx_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, const uint32_t *keys,
                      double bm_t0, double bm_t1, double bm_tol, const void *ta, const void *tb,
-                     int per_traj_times, void *W, void *H, void *cuda_stream);
+                     int per_traj_times, void *W, void *H, int bm_dim, void *cuda_stream);
 
 /* jax.random primitives the tree relies on, exposed for known-answer tests
  * (jax/_src/prng.py threefry2x32 / split / random_bits+normal). */
@@ -201,8 +204,10 @@ int dfx_threefry2x32(int64_t n, const uint32_t *keys /*[n,2]*/, const uint32_t *
                      uint32_t *out /*[n,2]*/, void *cuda_stream);
 int dfx_random_split(int64_t n, const uint32_t *keys /*[n,2]*/, int num, int partitionable,
                      uint32_t *out /*[n,num,2]*/, void *cuda_stream);
+/* jax.random.normal(key, shape, dtype) per key: m = 0 -> shape (), out [n]; m > 0 -> shape (m,), out [n, m] (m <= 8).
+ * The float side (log1p, erf_inv) is one explicitly sequenced IEEE evaluation (csrc/prng.cuh). */
 int dfx_random_normal(int dtype, int64_t n, const uint32_t *keys /*[n,2]*/, int partitionable,
-                      void *out /*[n]*/, void *cuda_stream);
+                      void *out, int m, void *cuda_stream);
 
 /* replaces DenseInterpolation.evaluate vmapped (_global_interpolation.py:335-355):
  * trajectory i is evaluated at tq[i, 0..nq).  out: [N, nq, d]. */

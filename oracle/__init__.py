@@ -105,8 +105,16 @@ def lib():
         L.orc_erfinv_f64.restype = C.c_double
         L.orc_erfinv_f32.argtypes = [C.c_float]
         L.orc_erfinv_f32.restype = C.c_float
+        L.orc_normal_vec_f64.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
+        L.orc_normal_vec_f64.restype = C.c_double
+        L.orc_normal_vec_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
+        L.orc_normal_vec_f32.restype = C.c_float
+        L.orc_log1p_f64.argtypes = [C.c_double]
+        L.orc_log1p_f64.restype = C.c_double
+        L.orc_log1p_f32.argtypes = [C.c_float]
+        L.orc_log1p_f32.restype = C.c_float
         L.orc_vbt_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_double,
-                                       C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+                                       C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_vbt_evaluate.restype = C.c_int
         L.orc_dense_evaluate.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
@@ -139,10 +147,21 @@ def prng_key(seed: int):
     return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], np.uint32)
 
 
-def normal(key, dtype=np.float64, partitionable=True):
-    if np.dtype(dtype) == np.float64:
-        return lib().orc_normal_f64(int(key[0]), int(key[1]), int(partitionable))
-    return np.float32(lib().orc_normal_f32(int(key[0]), int(key[1]), int(partitionable)))
+def normal(key, dtype=np.float64, partitionable=True, shape=()):
+    """jax.random.normal(key, shape, dtype) for shape () or (m,)."""
+    f64 = np.dtype(dtype) == np.float64
+    fn = lib().orc_normal_vec_f64 if f64 else lib().orc_normal_vec_f32
+    m = shape[0] if shape else 1
+    out = np.array([fn(int(key[0]), int(key[1]), w, m, int(partitionable)) for w in range(m)], dtype)
+    return out if shape else out[0]
+
+
+def log1p(x, dtype=np.float64):
+    """The explicitly sequenced log1p of the normal draw (oracle.c), elementwise."""
+    f64 = np.dtype(dtype) == np.float64
+    fn = lib().orc_log1p_f64 if f64 else lib().orc_log1p_f32
+    xs = np.asarray(x, dtype)
+    return np.array([fn(float(v)) for v in xs.ravel()], dtype).reshape(xs.shape)
 
 
 def erfinv(x, dtype=np.float64):
@@ -285,17 +304,20 @@ def solve(field, y0, t0, t1, dt0=None, *, solver="dopri5", params=(), dtype=np.f
 
 
 def vbt_evaluate(keys, ta, tb, *, bm_t0=0.0, bm_t1=1.0, tol=1e-3, levy_area="bi", dtype=np.float64,
-                 partitionable=True):
+                 partitionable=True, shape=()):
     dt = np.dtype(dtype)
     keys = np.ascontiguousarray(keys, np.uint32).reshape(-1, 2)
     n = keys.shape[0]
     ta_a = np.ascontiguousarray(np.broadcast_to(np.asarray(ta, dt), (n,)))
     tb_a = np.ascontiguousarray(np.broadcast_to(np.asarray(tb, dt), (n,)))
-    W = np.empty(n, dt)
-    H = np.empty(n, dt)
-    lib().orc_vbt_evaluate(F64 if dt == np.float64 else F32, LEVY[levy_area], int(partitionable), n,
-                           keys.ctypes.data, bm_t0, bm_t1, tol, ta_a.ctypes.data, tb_a.ctypes.data, 1,
-                           W.ctypes.data, H.ctypes.data)
+    m = int(shape[0]) if shape else 0
+    W = np.empty((n, m) if m else n, dt)
+    H = np.empty((n, m) if m else n, dt)
+    rc = lib().orc_vbt_evaluate(F64 if dt == np.float64 else F32, LEVY[levy_area], int(partitionable), n,
+                                keys.ctypes.data, bm_t0, bm_t1, tol, ta_a.ctypes.data, tb_a.ctypes.data, 1,
+                                W.ctypes.data, H.ctypes.data, m)
+    if rc != 0:
+        raise ValueError(lib().orc_last_error().decode())
     return W, H
 
 

@@ -65,39 +65,111 @@ void orc_split(uint32_t k0, uint32_t k1, int num, int partitionable, uint32_t *o
   }
 }
 
-/* random_bits for a scalar (shape == ()) draw (prng.py `threefry_random_bits`):
- *  partitionable: block (0,0): 32-bit -> x0 ^ x1 ; 64-bit -> (x0 << 32) | x1
- *  original:      32-bit -> first word of block (0,0) ; 64-bit -> block (0,1): (x0 << 32) | x1 */
-static uint32_t bits32(uint32_t k0, uint32_t k1, int partitionable) {
-  uint32_t a, b;
-  orc_threefry2x32(k0, k1, 0u, 0u, &a, &b);
-  return partitionable ? (a ^ b) : a;
+/* ---------------------------------------------------------------------------------------
+ * The float side of jax.random.normal.  [EXT - jax / XLA, not under /root/reference.]
+ *
+ * XLA evaluates normal = sqrt(2) * erf_inv(u) with erf_inv = Giles' (2010) polynomials in
+ * w = -log1p(-u*u) (xla/client/lib/math.cc ErfInv32 / ErfInv64).  The last ulp of that chain
+ * is backend-specific in XLA itself (log1p comes from the backend's libm / libdevice and the
+ * LLVM back ends may contract a*b+c), so there is no single "JAX bit pattern" to restate.
+ * What this project pins instead is ONE explicitly sequenced evaluation, stated operation by
+ * operation below, that the CUDA side (csrc/prng.cuh) performs with the identical sequence of
+ * IEEE-754 correctly rounded operations (+, -, *, /, sqrt, fma): oracle and kernel agree bit
+ * for bit, and the sequence is within 1 ulp of the exact log1p (tests/test_oracle_prng.py).
+ *   - every "fma(a, b, c)" below is ONE rounding; every other operator rounds on its own
+ *     (this file is compiled with -ffp-contract=off);
+ *   - log1p follows the classical argument reduction 1+x = 2^k (1+f), f in [sqrt(1/2)-1, sqrt(2)-1),
+ *     log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)), s = f / (2 + f), with the rounding error of 1+x
+ *     carried in c (the published fdlibm scheme and coefficients).
+ * ------------------------------------------------------------------------------------- */
+double orc_log1p_f64(double x) {
+  static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                      Lp[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                               2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                               1.479819860511658591e-01};
+  if (!(x > -1.0)) return x == -1.0 ? -INFINITY : NAN;
+  if (x == INFINITY) return x;
+  double f, c = 0.0;
+  int k = 0;
+  if (x > -0.2928932188134524 && x < 0.41421356237309503) {
+    f = x; /* 1 + x already lies in [sqrt(1/2), sqrt(2)): no reduction, no rounding of 1 + x */
+  } else {
+    const double u = 1.0 + x;
+    uint64_t b;
+    memcpy(&b, &u, 8);
+    k = (int)((b >> 52) & 0x7ff) - 1023;
+    c = (k > 0) ? 1.0 - (u - x) : x - (u - 1.0); /* what the rounding of 1 + x lost */
+    c = c / u;
+    uint64_t m = b & 0x000fffffffffffffull;
+    if (m < 0x6a09e667f3bcdull) m |= 0x3ff0000000000000ull;          /* mantissa below sqrt(2): 1+f in [1, sqrt 2) */
+    else { k += 1; m |= 0x3fe0000000000000ull; }                     /* else halve it: 1+f in [sqrt(1/2), 1) */
+    double mu;
+    memcpy(&mu, &m, 8);
+    f = mu - 1.0;
+  }
+  const double hfsq = (0.5 * f) * f;
+  const double s = f / (2.0 + f);
+  const double z = s * s;
+  double r = Lp[6];
+  for (int i = 5; i >= 0; --i) r = fma(r, z, Lp[i]);
+  r = r * z;
+  if (k == 0) return f - (hfsq - s * (hfsq + r));
+  const double dk = (double)k;
+  return dk * ln2_hi - ((hfsq - (s * (hfsq + r) + (dk * ln2_lo + c))) - f);
 }
-static uint64_t bits64(uint32_t k0, uint32_t k1, int partitionable) {
-  uint32_t a, b;
-  orc_threefry2x32(k0, k1, 0u, partitionable ? 0u : 1u, &a, &b);
-  return ((uint64_t)a << 32) | (uint64_t)b;
+float orc_log1p_f32(float x) {
+  static const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f,
+                     Lp[7] = {6.6666668653e-01f, 4.0000000596e-01f, 2.8571429849e-01f, 2.2222198546e-01f,
+                              1.8183572590e-01f, 1.5313838422e-01f, 1.4798198640e-01f};
+  if (!(x > -1.0f)) return x == -1.0f ? -INFINITY : NAN;
+  if (x == INFINITY) return x;
+  float f, c = 0.0f;
+  int k = 0;
+  if (x > -0.29289323f && x < 0.41421357f) {
+    f = x;
+  } else {
+    const float u = 1.0f + x;
+    uint32_t b;
+    memcpy(&b, &u, 4);
+    k = (int)((b >> 23) & 0xff) - 127;
+    c = (k > 0) ? 1.0f - (u - x) : x - (u - 1.0f);
+    c = c / u;
+    uint32_t m = b & 0x007fffffu;
+    if (m < 0x3504f3u) m |= 0x3f800000u;
+    else { k += 1; m |= 0x3f000000u; }
+    float mu;
+    memcpy(&mu, &m, 4);
+    f = mu - 1.0f;
+  }
+  const float hfsq = (0.5f * f) * f;
+  const float s = f / (2.0f + f);
+  const float z = s * s;
+  float r = Lp[6];
+  for (int i = 5; i >= 0; --i) r = fmaf(r, z, Lp[i]);
+  r = r * z;
+  if (k == 0) return f - (hfsq - s * (hfsq + r));
+  const float dk = (float)k;
+  return dk * ln2_hi - ((hfsq - (s * (hfsq + r) + (dk * ln2_lo + c))) - f);
 }
 
-/* lax.erf_inv, f32: Giles (2010) single-precision polynomial as used by XLA (ErfInv32)
- * [EXT - restated from the published algorithm; not under /root/reference]. */
+/* lax.erf_inv, f32: Giles (2010) single-precision polynomial, coefficients and branch as XLA's ErfInv32
+ * [EXT].  Sequence: w = -log1p(-(x*x)); Horner with one fma per coefficient; result p * x. */
 float orc_erfinv_f32(float x) {
   static const float lt5[9] = {2.81022636e-08f, 3.43273939e-07f, -3.5233877e-06f, -4.39150654e-06f, 0.00021858087f,
                                -0.00125372503f, -0.00417768164f, 0.246640727f, 1.50140941f};
   static const float ge5[9] = {-0.000200214257f, 0.000100950558f, 0.00134934322f, -0.00367342844f, 0.00573950773f,
                                -0.0076224613f, 0.00943887047f, 1.00167406f, 2.83297682f};
   if (fabsf(x) == 1.0f) return x * INFINITY;
-  float w = -log1pf(-x * x);
+  float w = -orc_log1p_f32(-(x * x));
   const float *c;
   if (w < 5.0f) { w = w - 2.5f; c = lt5; } else { w = sqrtf(w) - 3.0f; c = ge5; }
   float p = c[0];
-  for (int i = 1; i < 9; ++i) p = c[i] + p * w;
+  for (int i = 1; i < 9; ++i) p = fmaf(p, w, c[i]);
   return p * x;
 }
 
-/* lax.erf_inv, f64: Giles' double-precision three-branch polynomial as used by XLA (ErfInv64)
- * [EXT - restated from the published algorithm; validated against scipy.special.erfinv in
- * tests/test_oracle_prng.py]. */
+/* lax.erf_inv, f64: Giles' double-precision three-branch polynomial, coefficients and branches as XLA's
+ * ErfInv64 [EXT]; validated against scipy.special.erfinv in tests/test_oracle_prng.py.  Same sequencing. */
 double orc_erfinv_f64(double x) {
   static const double a[23] = {-3.6444120640178196996e-21, -1.685059138182016589e-19, 1.2858480715256400167e-18,
                                1.115787767802518096e-17, -1.333171662854620906e-16, 2.0972767875968561637e-17,
@@ -121,42 +193,66 @@ double orc_erfinv_f64(double x) {
                                7.5995277030017761139e-05, -0.00021503011930044477347, -0.00013871931833623122026,
                                1.0103004648645343977, 4.8499064014085844221};
   if (fabs(x) == 1.0) return x * INFINITY;
-  double w = -log1p(-x * x);
+  double w = -orc_log1p_f64(-(x * x));
   const double *co;
   int n;
   if (w < 6.25) { w = w - 3.125; co = a; n = 23; }
   else if (w < 16.0) { w = sqrt(w) - 3.25; co = b; n = 19; }
   else { w = sqrt(w) - 5.0; co = c; n = 17; }
   double p = co[0];
-  for (int i = 1; i < n; ++i) p = co[i] + p * w;
+  for (int i = 1; i < n; ++i) p = fma(p, w, co[i]);
   return p * x;
 }
 
-/* jax.random.normal(key, (), dtype) (random.py `_normal_real` / `_uniform`):
- * mantissa fill -> [1,2) -> -1 -> u = max(lo, f*(hi-lo)+lo), lo = nextafter(-1, 0), hi = 1;
+/* random bits of element `w` of a draw of shape (m,) (prng.py threefry_random_bits; m = 1 is shape ()):
+ *  partitionable: counter (0, w): 32-bit -> x0 ^ x1 ; 64-bit -> (x0 << 32) | x1
+ *  original 32-bit: counters iota(m) padded with one 0 to even length 2h, halves (c[:h], c[h:]); the words are
+ *                   concat(x0s, x1s)[:m], so element w < h is x0 of block (w, h+w or 0 for the pad) and element
+ *                   w >= h is x1 of block (w-h, w)
+ *  original 64-bit: 2m 32-bit words from counters iota(2m), halves (c[:m], c[m:]); high words = x0s, low = x1s,
+ *                   so element w is (x0 << 32) | x1 of block (w, m+w) */
+static uint32_t bits32_vec(uint32_t k0, uint32_t k1, int w, int m, int partitionable) {
+  uint32_t a, b;
+  if (partitionable) { orc_threefry2x32(k0, k1, 0u, (uint32_t)w, &a, &b); return a ^ b; }
+  const int h = (m + 1) / 2;
+  if (w < h) { orc_threefry2x32(k0, k1, (uint32_t)w, (h + w < m) ? (uint32_t)(h + w) : 0u, &a, &b); return a; }
+  orc_threefry2x32(k0, k1, (uint32_t)(w - h), (uint32_t)w, &a, &b);
+  return b;
+}
+static uint64_t bits64_vec(uint32_t k0, uint32_t k1, int w, int m, int partitionable) {
+  uint32_t a, b;
+  if (partitionable) orc_threefry2x32(k0, k1, 0u, (uint32_t)w, &a, &b);
+  else orc_threefry2x32(k0, k1, (uint32_t)w, (uint32_t)(m + w), &a, &b);
+  return ((uint64_t)a << 32) | (uint64_t)b;
+}
+
+/* jax.random.normal(key, shape, dtype)[w] (random.py `_normal_real` / `_uniform`):
+ * mantissa fill -> [1,2) -> -1 -> u = max(lo, fma(f, hi - lo, lo)), lo = nextafter(-1, 0), hi = 1;
  * normal = sqrt(2) * erf_inv(u). */
-float orc_normal_f32(uint32_t k0, uint32_t k1, int partitionable) {
-  uint32_t bits = bits32(k0, k1, partitionable);
+float orc_normal_vec_f32(uint32_t k0, uint32_t k1, int w, int m, int partitionable) {
+  uint32_t bits = bits32_vec(k0, k1, w, m, partitionable);
   uint32_t fb = (bits >> 9) | 0x3F800000u;
   float f;
   memcpy(&f, &fb, 4);
   f = f - 1.0f;
   const float lo = nextafterf(-1.0f, 0.0f), hi = 1.0f;
-  float u = f * (hi - lo) + lo;
+  float u = fmaf(f, hi - lo, lo);
   if (!(u > lo)) u = lo; /* lax.max(lo, u) */
   return (float)sqrt(2.0) * orc_erfinv_f32(u);
 }
-double orc_normal_f64(uint32_t k0, uint32_t k1, int partitionable) {
-  uint64_t bits = bits64(k0, k1, partitionable);
+double orc_normal_vec_f64(uint32_t k0, uint32_t k1, int w, int m, int partitionable) {
+  uint64_t bits = bits64_vec(k0, k1, w, m, partitionable);
   uint64_t fb = (bits >> 12) | 0x3FF0000000000000ull;
   double f;
   memcpy(&f, &fb, 8);
   f = f - 1.0;
   const double lo = nextafter(-1.0, 0.0), hi = 1.0;
-  double u = f * (hi - lo) + lo;
+  double u = fma(f, hi - lo, lo);
   if (!(u > lo)) u = lo;
   return sqrt(2.0) * orc_erfinv_f64(u);
 }
+float orc_normal_f32(uint32_t k0, uint32_t k1, int partitionable) { return orc_normal_vec_f32(k0, k1, 0, 1, partitionable); }
+double orc_normal_f64(uint32_t k0, uint32_t k1, int partitionable) { return orc_normal_vec_f64(k0, k1, 0, 1, partitionable); }
 
 /* ---------------------------------------------------------------------------------------
  * type-generic core, instantiated for f64 and f32
@@ -244,20 +340,21 @@ int orc_solve(const orc_desc *d) {
 }
 
 int orc_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, const uint32_t *keys, double bm_t0,
-                     double bm_t1, double bm_tol, const void *ta, const void *tb, int per_traj_times, void *W, void *H) {
+                     double bm_t1, double bm_tol, const void *ta, const void *tb, int per_traj_times, void *W, void *H,
+                     int bm_dim) {
+  const int m = bm_dim > 0 ? bm_dim : 1;
+  if (m > ORC_MAX_DIM) { snprintf(g_err, sizeof g_err, "bm_dim %d out of range", bm_dim); return -1; }
   for (int64_t i = 0; i < n; ++i) {
     if (dtype == ORC_F64) {
       double a = ((const double *)ta)[per_traj_times ? i : 0], b = ((const double *)tb)[per_traj_times ? i : 0];
-      double w, h;
-      vbt_increment_f64(keys + 2 * i, bm_t0, bm_t1, bm_tol, levy_area, partitionable, a, b, &w, &h);
-      ((double *)W)[i] = w;
-      if (H) ((double *)H)[i] = h;
+      double w[ORC_MAX_DIM], h[ORC_MAX_DIM];
+      vbt_increment_vec_f64(keys + 2 * i, m, bm_t0, bm_t1, bm_tol, levy_area, partitionable, a, b, w, h);
+      for (int c = 0; c < m; ++c) { ((double *)W)[i * m + c] = w[c]; if (H) ((double *)H)[i * m + c] = h[c]; }
     } else {
       float a = ((const float *)ta)[per_traj_times ? i : 0], b = ((const float *)tb)[per_traj_times ? i : 0];
-      float w, h;
-      vbt_increment_f32(keys + 2 * i, bm_t0, bm_t1, bm_tol, levy_area, partitionable, a, b, &w, &h);
-      ((float *)W)[i] = w;
-      if (H) ((float *)H)[i] = h;
+      float w[ORC_MAX_DIM], h[ORC_MAX_DIM];
+      vbt_increment_vec_f32(keys + 2 * i, m, bm_t0, bm_t1, bm_tol, levy_area, partitionable, a, b, w, h);
+      for (int c = 0; c < m; ++c) { ((float *)W)[i * m + c] = w[c]; if (H) ((float *)H)[i * m + c] = h[c]; }
     }
   }
   return 0;

@@ -135,12 +135,18 @@ double orc_normal_f64(uint32_t k0, uint32_t k1, int partitionable);
 float orc_normal_f32(uint32_t k0, uint32_t k1, int partitionable);
 double orc_erfinv_f64(double x);
 float orc_erfinv_f32(float x);
+/* element w of jr.normal(key, (m,)); m == 1, w == 0 is the scalar draw */
+double orc_normal_vec_f64(uint32_t k0, uint32_t k1, int w, int m, int partitionable);
+float orc_normal_vec_f32(uint32_t k0, uint32_t k1, int w, int m, int partitionable);
+/* the explicitly sequenced log1p that erf_inv is built on (see oracle.c) */
+double orc_log1p_f64(double x);
+float orc_log1p_f32(float x);
 
-/* VirtualBrownianTree.evaluate(t0, t1, use_levy=True) for n independent scalar trees
- * (tree.py:326-354).  keys: [n,2] user keys; outputs W[n], H[n] (H may be NULL). */
+/* VirtualBrownianTree.evaluate(t0, t1, use_levy=True) for n independent trees of shape () (bm_dim == 0)
+ * or (bm_dim,) (tree.py:326-354).  keys: [n,2] user keys; outputs W[n(, m)], H[n(, m)] (H may be NULL). */
 int orc_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, const uint32_t *keys,
                      double bm_t0, double bm_t1, double bm_tol, const void *ta, const void *tb,
-                     int per_traj_times, void *W, void *H);
+                     int per_traj_times, void *W, void *H, int bm_dim);
 
 /* DenseInterpolation.evaluate (_global_interpolation.py:335-355) for one batch of queries:
  * each trajectory i evaluates at tq[i*nq + q]. out: [N, nq, d] */

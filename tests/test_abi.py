@@ -38,7 +38,7 @@ def test_struct_layout_matches_c(cuda_lib, tmp_path):
 
 def test_registry_and_metadata(cuda_lib):
     L = cuda_lib
-    assert L.dfx_abi_version() == 1
+    assert L.dfx_abi_version() == 2
     assert [L.dfx_num_stages(i) for i in range(9)] == [7, 7, 14, 2, 4, 2, 2, 1, 2]
     assert [L.dfx_solver_order(i) for i in range(3)] == [5, 5, 8]
     # BASELINE configs 1,2,3,5 have kernels registered (field, dim, solver, dtype, levy)

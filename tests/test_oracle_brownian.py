@@ -113,9 +113,11 @@ def test_ou_moments():
 
 
 def test_vector_brownian_motion_leaves():
-    """VirtualBrownianTree(shape=(m,)): leaf keys are split_by_tree(key, (m,)) = jr.split(key, m) (tree.py:301,
-    _misc.py:128-133).  With partitionable threefry split(key, m)[0] == split(key, 1)[0], so component 0 of a diagonal-noise
-    solve is the scalar solve; with the legacy layout the child keys depend on m and it is not.  Components are independent."""
+    """VirtualBrownianTree(shape=(m,)) is ONE leaf (a tuple of ints becomes a single ShapeDtypeStruct, tree.py:291-295) whose
+    key is split_by_tree(key, shape) = jr.split(key, 1)[0] (tree.py:301, _misc.py:128-133); every node draws
+    jr.normal(key, (m,)).  With partitionable threefry element 0 of an (m,) draw uses counter (0, 0) like the scalar draw, so
+    component 0 of a diagonal-noise solve is the scalar solve; with the legacy layout the counters depend on m and it is
+    not.  Components are independent."""
     import diffrax_b200 as dfx
     n = 64
     keys = dfx.random.split(dfx.random.key(21), n)
@@ -129,3 +131,22 @@ def test_vector_brownian_motion_leaves():
         assert abs(c[0, 1]) < 0.4 and abs(c[0, 2]) < 0.4 and abs(c[1, 2]) < 0.4
         # exact OU law per component: mean e^-1, variance sigma^2 (1 - e^-2) / 2
         assert abs(vec["ys"][:, -1, :].mean() - np.exp(-1.0)) < 0.1
+
+
+@pytest.mark.parametrize("levy", ["bi", "stla"])
+def test_vector_tree_shares_the_key_path(levy):
+    """shape (m,) vs shape (): same leaf key, same descent keys; only the element of each normal draw differs.  So the
+    (m,) increment's statistics per component match the scalar law, W of a 3-vector has independent N(0, t-s) components,
+    and (partitionable) component 0 equals the scalar tree bit for bit."""
+    import diffrax_b200 as dfx
+    keys = dfx.random.split(dfx.random.key(4), 4000)
+    W3, H3 = oracle.vbt_evaluate(keys, 0.2, 0.9, tol=2.0 ** -8, levy_area=levy, shape=(3,))
+    W1, H1 = oracle.vbt_evaluate(keys, 0.2, 0.9, tol=2.0 ** -8, levy_area=levy)
+    assert W3.shape == (4000, 3)
+    assert np.array_equal(W3[:, 0], W1) and np.array_equal(H3[:, 0], H1)
+    assert np.all(np.abs(W3.var(0) - 0.7) < 0.06) and np.all(np.abs(W3.mean(0)) < 0.05)
+    c = np.corrcoef(W3.T)
+    assert abs(c[0, 1]) < 0.06 and abs(c[0, 2]) < 0.06 and abs(c[1, 2]) < 0.06
+    if levy == "stla":  # H ~ N(0, (t-s)/12), independent of W
+        assert np.all(np.abs(H3.var(0) - 0.7 / 12) < 0.01)
+        assert abs(np.corrcoef(W3[:, 1], H3[:, 1])[0, 1]) < 0.06

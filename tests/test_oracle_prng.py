@@ -92,3 +92,75 @@ def test_normal_uniform_map_bits():
         want = np.float32(np.sqrt(2)) * np.float32(sp.erfinv(np.float64(u)))
         got = oracle.normal(k, np.float32, part)
         assert abs(float(got) - float(want)) <= 2e-5 * max(1.0, abs(float(want)))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_sequenced_log1p_within_one_ulp(dtype):
+    """The explicitly sequenced log1p (oracle.c / csrc/prng.cuh) against mpmath: <= 1 ulp over (-1, inf)."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([-rng.uniform(0, 1, 3000) ** 2, -10.0 ** rng.uniform(-18, 0, 1500), rng.uniform(0, 5, 300),
+                         10.0 ** rng.uniform(-10, 10, 300),
+                         [-0.2928932188134524, -0.2928932188134525, 0.41421356237309503, -0.5, -0.75, -1 + 2.0 ** -20, 0.0]])
+    xs = xs.astype(dtype)
+    xs = xs[xs > -1]
+    got = oracle.log1p(xs, dtype).astype(np.float64)
+    ref = np.array([float(mp.log1p(mp.mpf(float(v)))) for v in xs])
+    ulp = np.spacing(np.abs(ref.astype(dtype))).astype(np.float64)
+    assert np.max(np.abs(got - ref) / np.where(ulp > 0, ulp, 1.0)) <= 1.0
+    assert oracle.log1p(np.array([0.0], dtype), dtype)[0] == 0.0
+    assert oracle.log1p(np.array([-1.0], dtype), dtype)[0] == -np.inf
+    assert np.isnan(oracle.log1p(np.array([-1.5], dtype), dtype)[0])
+
+
+def _jax_random_bits(key, bit_width, m, part):
+    """jax/_src/prng.py threefry_random_bits for shape (m,), written whole-array the way JAX does it (iota, pad, halve,
+    concatenate) - an independent statement of the element <-> counter layout the oracle indexes per element."""
+    k0, k1 = int(key[0]), int(key[1])
+    tf = dfx.random.threefry2x32
+    if part:  # _threefry_random_bits_partitionable: counters (hi, lo) = (0, flat index)
+        b1, b2 = tf(k0, k1, np.zeros(m, np.uint32), np.arange(m, dtype=np.uint32))
+        return (b1.astype(np.uint64) << np.uint64(32)) | b2.astype(np.uint64) if bit_width == 64 else b1 ^ b2
+    max_count = int(np.ceil(bit_width * m / 32))            # _threefry_random_bits_original
+    count = np.arange(max_count, dtype=np.uint32)
+    odd = count.size % 2                                    # threefry_2x32: pad to even, split in halves, concatenate
+    if odd:
+        count = np.concatenate([count, np.zeros(1, np.uint32)])
+    x0, x1 = np.split(count, 2)
+    y0, y1 = tf(k0, k1, x0, x1)
+    bits = np.concatenate([y0, y1])
+    bits = bits[:-1] if odd else bits
+    if bit_width == 64:
+        hi, lo = np.split(bits, 2)
+        return (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
+    return bits
+
+
+@pytest.mark.parametrize("part", [True, False])
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 5, 8])
+def test_vector_normal_layout(part, m):
+    """jr.normal(key, (m,)): element w of the oracle's per-element indexing == the whole-array JAX layout; m == 1 is the
+    scalar draw.  Checked on the integer side through the (monotone, injective on the mantissa field) uniform map."""
+    for seed in (1, 99):
+        k = oracle.prng_key(seed)
+        for dtype, width in ((np.float32, 32), (np.float64, 64)):
+            bits = _jax_random_bits(k, width, m, part)
+            got = oracle.normal(k, dtype, part, (m,))
+            # rebuild the uniforms from the whole-array bits and push them through the oracle's own float side
+            for w in range(m):
+                # a scalar key whose block (0,0)/(0,1) we cannot choose, so compare via the uniform's mantissa: invert normal -> u
+                if width == 32:
+                    f = np.array([(int(bits[w]) >> 9) | 0x3F800000], np.uint32).view(np.float32)[0] - np.float32(1)
+                    lo = np.nextafter(np.float32(-1), np.float32(0))
+                    u = max(lo, np.float32(f * np.float32(2) + lo))
+                    want = np.float32(np.sqrt(2)) * oracle.erfinv(u, np.float32)
+                else:
+                    f = np.array([(int(bits[w]) >> 12) | 0x3FF0000000000000], np.uint64).view(np.float64)[0] - 1.0
+                    lo = np.nextafter(-1.0, 0.0)
+                    u = max(lo, f * 2.0 + lo)
+                    want = np.sqrt(2.0) * oracle.erfinv(u)
+                assert got[w] == want or abs(got[w] - want) <= 2 * np.spacing(abs(want))  # (fma vs mul+add in the uniform map)
+        if m == 1:
+            assert oracle.normal(k, np.float64, part, (1,))[0] == oracle.normal(k, np.float64, part)
+            assert oracle.normal(k, np.float32, part, (1,))[0] == oracle.normal(k, np.float32, part)
