@@ -1,27 +1,32 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the ensemble integrator (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c3|c5_heun|c5_shark]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c3|c4|c5_heun|c5_shark]
+                    [--scaling strong|weak] [--no-extras]
 
 metric   accepted RK steps / s across the ensemble (whole job, all ranks)
-step     ONE pass of the hot path over one batch of synthetic input: a complete
-         `diffeqsolve` of the whole ensemble resident in HBM
-workload C2 (BASELINE.json configs[1]): Lorenz sigma=10 rho=28 beta=8/3, Dopri5,
-         PIDController(rtol=atol=1e-8), dt0=None, t in [0,2], SaveAt(t1=True), fp64,
-         2^20 trajectories PER GPU (weak scaling: the path shards by trajectory, no data-path
-         collective; NCCL only gathers final states / reduces statistics after the kernel)
-e2e      same metric through the public `diffrax_b200.diffeqsolve` call with HOST (pinned)
-         buffers: H2D of y0 and D2H of ys/ts/stats/result inside the timed region
-roofline FP64 FMA pipe: achieved = attempted steps x 316 flop / device time of
-         the ensemble kernel (CUDA events on the launch stream); peak = DFMA-chain
-         microbenchmark measured live (MEASURED_PEAKS.json has no FP64 figure)
---impl reference  times the CPU restatement (oracle/, "port": the reference is pure Python on
-         JAX and jax is not installable here) on all host cores, bounded sample per step.
+step     ONE pass of the hot path over one batch of synthetic input: a complete sharded `diffeqsolve` of the whole
+         ensemble - each rank integrates its block of trajectories, then ONE NCCL all_gather distributes the final states
+         and the step statistics; the collective is INSIDE the timed region
+workload C2 (BASELINE.json configs[1]): Lorenz sigma=10 rho=28 beta=8/3, Dopri5, PIDController(rtol=atol=1e-8), dt0=None,
+         t in [0,2], SaveAt(t1=True), fp64, 2^20 trajectories IN TOTAL, sharded across the N GPUs ("scaling": "strong");
+         the weak-scaling figure (2^20 trajectories per GPU) rides along as the `weak` field when N > 1
+value    device time (CUDA events on the launch stream around solve + gather, max over ranks), inputs resident in HBM
+e2e      same metric through the public `diffrax_b200.prepare_sharded(...)()` call with HOST (pinned) buffers: H2D of
+         this rank's y0 block, D2H of its ys/ts/stats/result, the all_gather, and a host read of the global statistics
+roofline FP64 FMA pipe: achieved = attempted steps x 316 flop / device time of the ensemble kernel
+         of ONE rank; peak = DFMA-chain microbenchmark measured live (MEASURED_PEAKS.json has no FP64 figure)
+config_results  at N=1 the other BASELINE configs (C1, C3, C4, C5 Heun, C5 ShARK) are measured the same way after the
+         headline and appended to the one JSON line, each with value / roofline / e2e / clocks / cpu_baseline
+--impl reference  times the reference's CPU path: live Diffrax under jax.vmap on the JAX CPU backend when
+         `baseline.probe()` finds one (kind "reference"), else the CPU restatement in oracle/ (kind "port") on all host
+         cores; bounded sample per step.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -53,13 +58,15 @@ def workload(name: str, n: int, seed_offset: int = 0):
                     rtol=1e-6, atol=1e-6, save_ts=np.linspace(0, 10, 100),
                     label="C1 Lotka-Volterra/Tsit5/PID(1e-6,1e-6)/fp64/SaveAt(ts=100)")
     if name == "c3":
-        # Arenstorf initial condition perturbed by 1e-4 N(0,1) (1e-3 sends a third of the ensemble through lunar
-        # near-collisions needing > 8192 steps); one period; dense output with max_steps = 768 (103 GB of dense buffers).
+        # BASELINE config 3: the Arenstorf initial condition perturbed by 1e-3 N(0,1), one period, dense output.  2^18
+        # trajectories x max_steps x 520 B of dense buffers must fit 180 GB of HBM, so max_steps = 768 (105 GB); trajectories the
+        # perturbation sends through a lunar near-collision need more steps than that and end as max_steps_reached - they are
+        # counted in `failed_trajectories` and their accepted steps are real work.
         rng = np.random.default_rng(2 + seed_offset)
-        y0 = np.array([0.994, 0.0, 0.0, -2.00158510637908252]) + 1e-4 * rng.standard_normal((n, 4))
+        y0 = np.array([0.994, 0.0, 0.0, -2.00158510637908252]) + 1e-3 * rng.standard_normal((n, 4))
         return dict(base, field="cr3bp", params=[0.012277471], solver="dopri8", y0=y0, t0=0.0, t1=17.0652165601579625,
                     rtol=1e-12, atol=1e-12, save_dense=True, max_steps=768,
-                    label="C3 CR3BP(Arenstorf+1e-4 N(0,1))/Dopri8/PID(1e-12,1e-12)/fp64/one period/SaveAt(dense), max_steps=768")
+                    label="C3 CR3BP(Arenstorf+1e-3 N(0,1))/Dopri8/PID(1e-12,1e-12)/fp64/one period/SaveAt(dense), max_steps=768")
     if name == "c4":
         import diffrax_b200 as dfx
         mlp = dfx.fields.MLP.init(3, d=4, width=128)          # weights ~ U(+-1/sqrt(fan_in)), seed 3
@@ -149,10 +156,10 @@ class ClockSampler:
 
 def ncu_traffic(workload: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full`
-    summary (profiles/r01_<workload>_*_ncu_full.txt), in bytes per launch; None when no capture is committed."""
+    summary (profiles/r0N_<workload>_*_ncu_full.txt, newest round first), in bytes per launch; None when no capture."""
     import glob
     import re
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r01_{workload}_*ncu_full.txt"))):
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r0*_{workload}_*ncu_full.txt")), reverse=True):
         tot, units = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for m in re.finditer(r"dram__bytes_(read|write)\.sum \[(\w+)\] = ([0-9.]+)", open(f).read()):
             tot += float(m.group(3)) * units.get(m.group(2), 1.0)
@@ -175,228 +182,330 @@ def cpu_port_rate(w, sample: int, threads: int = 0):
     return float(o["stats"][:, 1].sum()) / dt, dt, oracle.hw_threads() if threads == 0 else threads
 
 
+_LIVE = {}
+
+
+def live_reference_rate(w, sample: int):
+    """accepted steps / s of LIVE Diffrax (jax.jit(jax.vmap(diffeqsolve)) on the JAX CPU backend, the pattern of
+    benchmarks/lotka_volterra.py:55-59) on `sample` trajectories, compiled once per (workload, sample)."""
+    import baseline
+    case = dict(w, y0=w["y0"][:sample], keys=None if w["keys"] is None else w["keys"][:sample],
+                save_t1=w["save_ts"] is None and not w["save_dense"])
+    case.pop("mlp", None); case.pop("label", None)
+    key = (w["label"], sample)
+    if key not in _LIVE:
+        fn, a = baseline.compiled(case)
+        import jax
+        jax.block_until_ready(fn(*a).stats["num_accepted_steps"])      # compile + warm-up
+        _LIVE[key] = (fn, a)
+    fn, a = _LIVE[key]
+    import jax
+    t = time.perf_counter()
+    sol = fn(*a)
+    acc = jax.block_until_ready(sol.stats["num_accepted_steps"])
+    dt = time.perf_counter() - t
+    return float(np.asarray(acc).sum()) / dt, dt, os.cpu_count() or 1
+
+
+def cpu_reference_rate(w, sample: int):
+    """(rate, seconds, cores, kind): the reference itself when importable, else the oracle port."""
+    import baseline
+    ok, why = baseline.probe()
+    if ok:
+        try:
+            return (*live_reference_rate(w, sample), "reference", why)
+        except Exception as e:  # noqa: BLE001  (a JAX twin missing for this case, an API drift ...): say so and fall back
+            why = f"live Diffrax failed on this workload ({type(e).__name__}: {e})"
+    return (*cpu_port_rate(w, sample), "port", why)
+
+
+# bounded CPU samples (trajectories) sized for a few seconds of host work per config
+CPU_SAMPLE = {"c1": 1024, "c2": 1 << 19, "c3": 1 << 13, "c4": 1 << 14, "c5_heun": 1 << 18, "c5_shark": 1 << 18}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  Diffrax itself needs
-    jax/equinox (absent, no network), so this is the oracle port on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores - live Diffrax when
+    `import jax, diffrax` works (baseline.probe()), else the oracle port - on the arm's own config / metric / unit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    args.ref_sample = min(args.ref_sample, DEFAULT_TRAJECTORIES[args.workload])
-    w = workload(args.workload, args.ref_sample)
-    for _ in range(args.warmup):
-        cpu_port_rate(w, min(args.ref_sample, 8192))
+    sample = min(args.ref_sample or CPU_SAMPLE[args.workload], DEFAULT_TRAJECTORIES[args.workload])
+    w = workload(args.workload, sample)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rate(w, min(sample, 8192))
     rates, times = [], []
-    cores = 1
+    cores, kind, why = 1, "port", ""
     for _ in range(args.steps):
-        r, dt, cores = cpu_port_rate(w, args.ref_sample)
+        r, dt, cores, kind, why = cpu_reference_rate(w, sample)
         rates.append(r); times.append(dt)
     total_t = sum(times)
     value = float(np.sum(np.array(rates) * np.array(times)) / total_t)
-    sample = f"{args.ref_sample} of the workload's trajectories per step (same seed/config), all host cores"
+    what = ("live Diffrax, jax.jit(jax.vmap(diffeqsolve)) on the JAX CPU backend" if kind == "reference"
+            else "oracle (C restatement of the reference; live Diffrax unavailable: " + why + ")")
+    smp = f"{sample} of the workload's trajectories per step (same seed/config), all host cores; {what}"
     line = {"impl": "reference", "metric": "accepted_rk_steps_per_s", "value": value, "unit": "steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if w["dtype"] == np.float64 else "f32", "data": "synthetic",
-            "config": {"workload": w["label"], "trajectories_per_step": args.ref_sample},
-            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": w["label"], "trajectories_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": kind, "sample": smp},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
+def _c5_blocks(name):
+    """threefry blocks per step the descent-cached algorithm executes on the C5 time grid (dt = 2^-6, 8 levels)."""
+    def walk(r, depth=8):
+        s_, bits = 0.0, []
+        for lv in range(depth):
+            t_ = s_ + 2.0 ** -(lv + 1)
+            right = r > t_
+            bits.append(right)
+            s_ = t_ if right else s_
+        return bits
+    nsteps_grid, lv_total, prev = 64, 0, walk(0.0)
+    for k_ in range(1, nsteps_grid + 1):
+        cur = walk(k_ / 64.0)
+        common = next((i for i in range(8) if cur[i] != prev[i]), 8)
+        lv_total += 8 - common
+        prev = cur
+    per_level, leaf = {"c5_heun": (3, 1), "c5_shark": (7, 4)}[name]
+    return per_level * lv_total / nsteps_grid + leaf, {"c5_heun": 3 * 8 + 4, "c5_shark": 7 * 8 + 9}[name]
+
+
+def _roofline(name, L, _lib, local, dev, att_per_gpu, acc_per_gpu, ms_per_step, out_bytes):
+    import torch
+    sec = ms_per_step * 1e-3
+    flop = FLOP_PER_ATTEMPTED_STEP.get(name)
+    if flop is not None:
+        peak = float(L.dfx_measure_fma_peak(_lib.F64, local))  # TFLOP/s, live DFMA-chain microbenchmark
+        achieved = att_per_gpu * flop / sec / 1e12  # per GPU: the kernel of ONE rank
+        roof = {"bound": "fma_fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "peak_source": "dfx_measure_fma_peak: 8 independent DFMA chains/thread, 8 CTAs x 256 thr/SM, "
+                               "measured in this run (MEASURED_PEAKS.json holds no FP64 FMA figure)",
+                "flop_per_attempted_step": flop}
+        if name == "c3":   # dense output: 8 (16 d + 1) = 520 B per accepted step (algorithmic) + the +inf padding of the layout
+            alg = acc_per_gpu * 520.0
+            roof["hbm_write"] = {"algorithmic_bytes_per_launch": alg, "layout_bytes_per_launch": float(out_bytes),
+                                 "achieved_GBps_algorithmic": alg / sec / 1e9, "achieved_GBps_layout": out_bytes / sec / 1e9,
+                                 "peak_GBps": 6546.6, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)"}
+    elif name == "c4":
+        # MLP field: 6 evaluations x 2 (128 d + 128^2 + 128 d) = 208 896 flop per attempted step (SURVEY.md section 8d);
+        # 196 608 of them are the 128x128 hidden layer that runs on tcgen05 (issued 3x for 3xTF32, and the kernel
+        # evaluates 7 stages per step: stage 0 is recomputed instead of carried, value-identical).
+        flop = 208896
+        a = torch.randn(8192, 8192, device=dev); b = torch.randn(8192, 8192, device=dev)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        best = 1e9
+        for _ in range(6):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        peak = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+        achieved = att_per_gpu * flop / sec / 1e12
+        issued = att_per_gpu * 7 * 3 * 2 * 128 * 128 / sec / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "peak_source": "cuBLAS TF32 GEMM 8192^3 (torch.matmul, allow_tf32) measured in this run; "
+                               "MEASURED_PEAKS.json has bf16 only",
+                "flop_per_attempted_step": flop, "issued_tensor_tflops": issued,
+                "note": "whole-solve average incl. the CUDA-core layers, softplus/tanh and the RK/PID algebra; "
+                        "tensor-pipe utilisation of the kernel: profiles/ ncu summary"}
+    else:
+        # C5: threefry blocks on the INT32 ALU.  A query W(r) walks L = 8 tree levels (BI 3 blocks/level, STLA 7) and
+        # draws the leaf bridge (BI 1 block, STLA 4); the step's other end point is the previous step's query, and the
+        # descent cache (csrc/vbt.cuh) resumes each walk at the first level where it leaves the previous one - so the
+        # ALGORITHM executes, per step, only the levels below the common prefix.  Counted exactly for this time grid.
+        blocks, blocks_nocache = _c5_blocks(name)
+        ops = blocks * 77.0          # 20 x (add, rotate, xor) + 17 injection adds per block
+        peak = float(L.dfx_measure_int_peak(local))
+        achieved = att_per_gpu * ops / sec / 1e12
+        roof = {"bound": "int32_alu", "achieved": achieved, "peak": peak, "unit": "Tera-op/s",
+                "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "peak_source": "dfx_measure_int_peak: add/rotate/xor chains, measured in this run",
+                "threefry_blocks_per_step": blocks, "threefry_blocks_per_step_without_descent_cache": blocks_nocache}
+    roof["traffic"] = ncu_traffic(name)   # (a capture of this very workload, or none)
+    return roof
+
+
+def measure(name, args, rank, local, world, dev, strong: bool, with_cpu: bool, steps=None):
+    """One workload through the sharded product entry: device-timed `value`, host-buffer `e2e`, roofline, clocks.
+    strong: the workload's trajectory count is the TOTAL over all ranks; else it is the count PER GPU (weak)."""
     import torch
     import torch.distributed as dist
-    from diffrax_b200 import _dist, _lib
-
-    rank, local, world = _dist.init_from_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    import diffrax_b200 as dfx
+    from diffrax_b200 import _lib
     L = _lib.lib()
-
-    n_local = args.trajectories or DEFAULT_TRAJECTORIES[args.workload]
-    w = workload(args.workload, n_local, seed_offset=1000 * rank)
-    dfx, term, solver, ctrl, saveat = _ours_objects(w, dev)
+    n_cfg = args.trajectories or DEFAULT_TRAJECTORIES[name]
+    n_total = n_cfg if strong else n_cfg * world
+    # the GLOBAL batch, identical on every rank (seeded); each rank integrates its contiguous block
+    w = workload(name, n_total)
+    _, term_d, solver, ctrl, saveat = _ours_objects(w, dev)
     y0_dev = torch.tensor(w["y0"], device=dev)
-    y0_host = torch.tensor(w["y0"]).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    # prepared call: descriptor + output buffers built once; each step is ONE C-ABI call
-    plan = dfx.prepare(term, solver, w["t0"], w["t1"], w["dt0"], y0_dev, saveat=saveat, stepsize_controller=ctrl,
-                       max_steps=w["max_steps"])
+    # prepared sharded call: descriptor + output buffers + gather record built once; each step = ONE C-ABI call + ONE collective
+    plan = dfx.prepare_sharded(term_d, solver, w["t0"], w["t1"], w["dt0"], y0_dev, saveat=saveat, stepsize_controller=ctrl,
+                               max_steps=w["max_steps"])
+    n_local = plan.hi - plan.lo
+
     def _tensors(x):
         if isinstance(x, torch.Tensor):
             yield x
         elif isinstance(x, dict):
             for v in x.values():
                 yield from _tensors(v)
-    out_bytes = sum(int(t.numel() * t.element_size()) for k in plan._keep for t in _tensors(k))
-    do_e2e = out_bytes < (2 << 30)      # C3's 69 GB of dense output is not staged through the host
-    _, term_h, _, _, _ = _ours_objects(w, None)
-
-    def step_device():
-        return plan(throw=False)
-
-    def step_host():
-        return dfx.diffeqsolve(term_h, solver, w["t0"], w["t1"], w["dt0"], y0_host, saveat=saveat,
-                               stepsize_controller=ctrl, throw=False, device=local, max_steps=w["max_steps"])
+    out_bytes = sum(int(t.numel() * t.element_size()) for k in plan.plan._keep for t in _tensors(k) if t.is_cuda) \
+        - int(y0_dev[plan.lo:plan.hi].numel() * y0_dev.element_size())
+    do_e2e = out_bytes < (2 << 30)      # C3's ~100 GB of dense output is not staged through the host
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also pays cudaMallocAsync pool growth, module load) ----
+    # ---- warm-up (also pays cudaMallocAsync pool growth, module load, NCCL channel set-up) ----
     for _ in range(max(args.warmup, 3)):
-        sol = step_device()
+        sol = plan(throw=False)
     torch.cuda.synchronize()
-    acc_local = int(sol.stats["num_accepted_steps"].sum())
-    att_local = int(sol.stats["num_steps"].sum())
-    failed_local = int((sol.result != 0).sum())
+    acc = int(sol.stats["num_accepted_steps"]); att = int(sol.stats["num_steps"]); failed = int(sol.stats["num_failed"])
+    loc = sol.local
+    att_local = int(loc.stats["num_steps"].sum()); acc_local = int(loc.stats["num_accepted_steps"].sum())
 
     # ---- timed: K steps, per-step CUDA events on the launch stream, L2 flushed between steps ----
+    K = steps or args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); plan(throw=False); e1.record(); torch.cuda.synchronize()
+    est_ms = max(e0.elapsed_time(e1), 1e-3)
+    if est_ms * K < 400.0:                      # short workloads: run long enough for the 20 ms clock sampler to see them
+        K = int(math.ceil(400.0 / est_ms))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        time.sleep(0.05)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     L.dfx_reset_launch_count()
     barrier()
     wall0 = time.perf_counter()
-    for e0, e1 in ev:
+    for (a0, a1), (k0, k1) in zip(ev, kev):
         flush.fill_(1)  # L2 flush, outside the event pair
-        e0.record()
-        sol = step_device()
-        e1.record()
+        a0.record()
+        k0.record()
+        loc_sol = plan.solve_local(throw=False)   # this rank's kernel ...
+        k1.record()
+        sol = plan.gather(loc_sol)                # ... and the one collective: finals + statistics of every rank
+        a1.record()
     barrier()
     wall = time.perf_counter() - wall0
     launches = int(L.dfx_launch_count())
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)  # device time of the K solves
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)     # solve + gather
+    ker_ms = sum(a.elapsed_time(b) for a, b in kev)    # the ensemble kernel of this rank alone
 
-    # ---- e2e: same K steps through the host-buffer call (H2D + D2H inside the timed region) ----
-    e2e_s, h2d, d2h = float("nan"), 0, 0
+    # ---- e2e: K steps through the host-buffer entry (H2D + D2H inside), gather + host read of the statistics ----
+    e2e_s, e2e_mean_s, h2d, d2h = float("nan"), float("nan"), 0, 0
     if do_e2e:
+        _, term_h, _, _, _ = _ours_objects(w, None)
+        y0_host = torch.tensor(w["y0"]).pin_memory()
+        hplan = dfx.prepare_sharded(term_h, solver, w["t0"], w["t1"], w["dt0"], y0_host, saveat=saveat, stepsize_controller=ctrl,
+                                    max_steps=w["max_steps"], device=dev)
         for _ in range(2):
-            sh = step_host()
+            sh = hplan(throw=False)
+            _ = int(sh.stats["num_accepted_steps"])
         barrier()
         per_step = []
+        Ke = min(K, max(args.steps, int(math.ceil(400.0 / max(est_ms, 0.2)))))
         t_all = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(Ke):
             t0 = time.perf_counter()
-            sh = step_host()
-            _ = int(sh.result[0])  # read the step's result on the host
+            sh = hplan(throw=False)
+            _ = int(sh.stats["num_accepted_steps"])  # the step's result (global statistics) read on the host
             per_step.append(time.perf_counter() - t0)
         barrier()
-        e2e_mean_s = (time.perf_counter() - t_all) / args.steps
-        # K host-timed steps; the per-step MEDIAN is reported (one scheduler hiccup of the host process - seen once as a
-        # single 180 ms step among 30 - would otherwise decide the figure); the plain mean is kept next to it
-        e2e_s = float(np.median(per_step)) * args.steps
-        h2d = y0_host.numel() * y0_host.element_size() + (0 if w["keys"] is None else w["keys"].nbytes)
-        d2h = sum(int(t.numel() * t.element_size()) for t in (sh.ts, sh.ys, sh.result)) \
-            + 3 * int(sh.stats["num_steps"].numel()) * 4
+        e2e_mean_s = (time.perf_counter() - t_all) / Ke
+        # per-step MEDIAN (one scheduler hiccup of the host process would otherwise decide the figure); mean kept next to it
+        e2e_s = float(np.median(per_step))
+        hl = sh.local
+        y_blk = y0_host[hplan.lo:hplan.hi]
+        h2d = y_blk.numel() * y_blk.element_size() + (0 if w["keys"] is None else n_local * 8)
+        d2h = sum(int(t.numel() * t.element_size()) for t in (hl.ts, hl.ys, hl.result)) + 3 * int(hl.stats["num_steps"].numel()) * 4 + 8
+        del hplan, y0_host
 
-    # ---- max over ranks, totals over ranks ----
-    t_max = torch.tensor([dev_ms, (e2e_s if do_e2e else 0.0) * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
-    tot = torch.tensor([acc_local, att_local, failed_local], dtype=torch.int64, device=dev)
+    # ---- max over ranks ----
+    t_max = torch.tensor([dev_ms, ker_ms, (e2e_s if do_e2e else 0.0) * 1e3, (e2e_mean_s if do_e2e else 0.0) * 1e3, wall * 1e3],
+                         dtype=torch.float64, device=dev)
+    cnt = torch.tensor([att_local, acc_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        # the only communication of the path: gather final states + reduce statistics (not timed)
-        _ = _dist.gather_final_states(sol.y_final, n_local * world)
-    dev_ms_max, e2e_ms_max, wall_ms_max = (float(x) for x in t_max)
-    acc, att, failed = (int(x) for x in tot)
-
+        dist.all_reduce(cnt, op=dist.ReduceOp.MAX)      # the busiest rank's kernel is the one the roofline describes
+    dev_ms_max, ker_ms_max, e2e_ms_max, e2e_mean_ms_max, wall_ms_max = (float(x) for x in t_max)
+    res = None
     if rank == 0:
-        ms_per_step = dev_ms_max / args.steps
-        value = acc / (ms_per_step * 1e-3)
-        flop = FLOP_PER_ATTEMPTED_STEP.get(args.workload)
-        if flop is not None and args.workload != "c4":
-            peak = float(L.dfx_measure_fma_peak(_lib.F64, local))  # TFLOP/s, live DFMA-chain microbenchmark
-            achieved = (att / world) * flop / (ms_per_step * 1e-3) / 1e12  # per-GPU: the kernel of ONE rank
-            roof = {"bound": "fma_fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                    "peak_source": "dfx_measure_fma_peak: 8 independent DFMA chains/thread, 8 CTAs x 256 thr/SM, "
-                                   "measured in this run (MEASURED_PEAKS.json holds no FP64 FMA figure)",
-                    "flop_per_attempted_step": flop}
-            if args.workload == "c3":   # dense output: 8 (16 d + 1) = 520 B per accepted step + inf padding of the tails
-                by = float(out_bytes)
-                roof["hbm_write"] = {"bytes_per_launch": by, "achieved_GBps": by / (ms_per_step * 1e-3) / 1e9 / world,
-                                     "peak_GBps": 6546.6, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)"}
-        elif args.workload == "c4":
-            # MLP field: 6 evaluations x 2 (128 d + 128^2 + 128 d) = 208 896 flop per attempted step (SURVEY.md §8d);
-            # 196 608 of them are the 128x128 hidden layer that runs on tcgen05 (issued 3x for 3xTF32, and the kernel
-            # evaluates 7 stages per step: stage 0 is recomputed instead of carried, value-identical).
-            flop = 208896
-            a = torch.randn(8192, 8192, device=dev); b = torch.randn(8192, 8192, device=dev)
-            torch.backends.cuda.matmul.allow_tf32 = True
-            best = 1e9
-            for _ in range(6):
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
-                best = min(best, e0.elapsed_time(e1))
-            peak = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
-            achieved = (att / world) * flop / (ms_per_step * 1e-3) / 1e12
-            issued = (att / world) * 7 * 3 * 2 * 128 * 128 / (ms_per_step * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                    "peak_source": "cuBLAS TF32 GEMM 8192^3 (torch.matmul, allow_tf32) measured in this run; "
-                                   "MEASURED_PEAKS.json has bf16 only",
-                    "flop_per_attempted_step": flop, "issued_tensor_tflops": issued,
-                    "note": "whole-solve average incl. the CUDA-core layers, softplus/tanh and the RK/PID algebra; "
-                            "tensor-pipe utilisation of the kernel: profiles/ ncu summary"}
-        else:
-            # C5: threefry blocks on the INT32 ALU.  A query W(r) walks L = 8 tree levels (BI 3 blocks/level, STLA 7) and
-            # draws the leaf bridge (BI 1 block, STLA 4); the step's other end point is the previous step's query, and the
-            # descent cache (csrc/vbt.cuh) resumes each walk at the first level where it leaves the previous one - so the
-            # ALGORITHM executes, per step, only the levels below the common prefix.  Counted exactly for this time grid:
-            def walk(r, depth=8):
-                s_, bits = 0.0, []
-                for lv in range(depth):
-                    t_ = s_ + 2.0 ** -(lv + 1)
-                    right = r > t_
-                    bits.append(right)
-                    s_ = t_ if right else s_
-                return bits
-            nsteps_grid, lv_total, prev = 64, 0, walk(0.0)
-            for k_ in range(1, nsteps_grid + 1):
-                cur = walk(k_ / 64.0)
-                common = next((i for i in range(8) if cur[i] != prev[i]), 8)
-                lv_total += 8 - common
-                prev = cur
-            per_level, leaf = {"c5_heun": (3, 1), "c5_shark": (7, 4)}[args.workload]
-            blocks = per_level * lv_total / nsteps_grid + leaf
-            blocks_nocache = {"c5_heun": 3 * 8 + 4, "c5_shark": 7 * 8 + 9}[args.workload]
-            ops = blocks * 77.0          # 20 x (add, rotate, xor) + 17 injection adds per block
-            peak = float(L.dfx_measure_int_peak(local))
-            achieved = (att / world) * ops / (ms_per_step * 1e-3) / 1e12
-            roof = {"bound": "int32_alu", "achieved": achieved, "peak": peak, "unit": "Tera-op/s",
-                    "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                    "peak_source": "dfx_measure_int_peak: add/rotate/xor chains, measured in this run",
-                    "threefry_blocks_per_step": blocks, "threefry_blocks_per_step_without_descent_cache": blocks_nocache}
-        roof["traffic"] = ncu_traffic(args.workload)   # (a capture of this very workload, or none)
-        cpu_sample = min(args.cpu_sample, n_local)
-        cpu_rate, cpu_dt, cores = cpu_port_rate(w, cpu_sample)
-        line = {
-            "metric": "accepted_rk_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if w["dtype"] == np.float64 else "f32", "data": "synthetic",
-            "config": {"workload": w["label"], "trajectories_per_gpu": n_local, "trajectories_total": n_local * world,
+        ms_per_step = dev_ms_max / K
+        roof = _roofline(name, L, _lib, local, dev, float(cnt[0]), float(cnt[1]), ker_ms_max / K, out_bytes)
+        res = {
+            "metric": "accepted_rk_steps_per_s", "value": acc / (ms_per_step * 1e-3), "unit": "steps/s", "n_gpus": world,
+            "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "kernel_ms_per_step": ker_ms_max / K,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f64" if w["dtype"] == np.float64 else "f32", "data": "synthetic",
+            "config": {"workload": w["label"], "trajectories_total": n_total, "trajectories_per_gpu": n_local,
                        "accepted_steps_per_solve": acc, "attempted_steps_per_solve": att, "failed_trajectories": failed,
                        "l2": "flushed between timed steps (256 MiB write outside the per-step CUDA-event pairs)",
-                       "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
-            "e2e": ({"value": acc / (e2e_ms_max * 1e-3 / args.steps), "unit": "steps/s", "h2d_bytes_per_step": h2d,
-                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / args.steps, "statistic": "median of the K per-step wall times",
-                     "mean_ms_per_step": e2e_mean_s * 1e3} if do_e2e else
+                       "parallelism": f"trajectory-sharded x{world}; ONE all_gather of [finals | t_final | statistics] per solve, "
+                                      "inside the timed region" if world > 1 else "single GPU (no collective)"},
+            "e2e": ({"value": acc / (e2e_ms_max * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max, "statistic": "median of the per-step wall times, max over ranks",
+                     "mean_ms_per_step": e2e_mean_ms_max, "call": "diffrax_b200.prepare_sharded(host buffers)(): H2D, kernel, D2H, all_gather, host read of the statistics"}
+                    if do_e2e else
                     {"value": None, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                      "note": "outputs exceed 2 GiB; not staged through the host"}),
             "gpu_launches": launches,
             "roofline": roof,
-            "cpu_baseline": {"value": cpu_rate, "unit": "steps/s", "cores": cores, "kind": "port",
-                             "sample": f"first {cpu_sample} trajectories of rank 0's batch, oracle (C port), "
-                                       f"{cpu_dt:.2f} s"},
-            "clocks": clocks, "wall_ms_per_step_incl_flush_and_host": wall_ms_max / args.steps,
+            "clocks": clocks, "wall_ms_per_step_incl_flush_and_host": wall_ms_max / K,
         }
+        if with_cpu:
+            cpu_sample = min(args.cpu_sample or CPU_SAMPLE[name], n_total)
+            rate, cpu_dt, cores, kind, why = cpu_reference_rate(w, cpu_sample)
+            res["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": cores, "kind": kind,
+                                   "sample": f"first {cpu_sample} trajectories of the batch, "
+                                             + ("live Diffrax (jax.vmap, JAX CPU)" if kind == "reference" else f"oracle C port (live Diffrax: {why})")
+                                             + f", {cpu_dt:.2f} s"}
+    del plan, y0_dev, flush, sol
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from diffrax_b200 import _dist
+
+    rank, local, world = _dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    strong = args.scaling == "strong"
+    line = measure(args.workload, args, rank, local, world, dev, strong, with_cpu=True)
+    if world > 1 and strong and not args.no_extras:
+        wk = measure(args.workload, args, rank, local, world, dev, False, with_cpu=False)
+        if rank == 0:
+            line["weak"] = {k: wk[k] for k in ("value", "unit", "ms_per_step", "kernel_ms_per_step", "steps")}
+            line["weak"].update(trajectories_per_gpu=wk["config"]["trajectories_per_gpu"], trajectories_total=wk["config"]["trajectories_total"],
+                                e2e_value=wk["e2e"]["value"], e2e_ms_per_step=wk["e2e"].get("ms_per_step"))
+    if world == 1 and not args.no_extras and args.workload == "c2" and not args.trajectories:
+        # the other BASELINE configs, same method, appended to the one JSON line
+        extras = {}
+        for name in ("c1", "c3", "c4", "c5_heun", "c5_shark"):
+            try:
+                extras[name] = measure(name, args, rank, local, world, dev, True, with_cpu=True, steps=min(args.steps, 10))
+            except Exception as e:  # noqa: BLE001  (never lose the headline to an extra)
+                extras[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["config_results"] = extras
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -469,9 +578,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--trajectories", type=int, default=0, help="trajectories per GPU (default: the workload's size)")
-    ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="trajectories of the cpu_baseline sample")
-    ap.add_argument("--ref-sample", type=int, default=1 << 19, help="trajectories per step of --impl reference")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the workload's trajectory count is the total over all GPUs (BASELINE: 1M sharded across 1/2/4/8); "
+                         "weak: it is the count per GPU")
+    ap.add_argument("--trajectories", type=int, default=0, help="trajectory count (total if strong, per GPU if weak; default: the workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories of the cpu_baseline sample (default: per workload)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="trajectories per step of --impl reference (default: per workload)")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: no config_results (N=1) / weak field (N>1)")
     args = ap.parse_args()
     if args.workload == "published_jump_step":
         run_published_jump_step(args)

@@ -10,7 +10,10 @@ from ._api import (RESULTS, AffineEvent, Event, Newton, SteadyStateEvent, is_eve
                    Dopri5, Dopri8, Euler, HalfSolver, Heun, Midpoint, MultiTerm, ODETerm, PIDController, Ralston, SaveAt,
                    ShARK, Solution, SpaceTimeLevyArea, SubSaveAt, Tsit5, VirtualBrownianTree, diffeqsolve, is_successful, prepare, EnsembleSolve)
 
+from ._dist import ShardedSolution, prepare_sharded, shard_range, sharded_diffeqsolve  # noqa: E402
+
 __all__ = [
+    "ShardedSolution", "prepare_sharded", "shard_range", "sharded_diffeqsolve",
     "RESULTS", "AffineEvent", "Event", "Newton", "SteadyStateEvent", "is_event", "is_okay", "steady_state_event", "Bosh3", "BrownianIncrement", "ClipStepSizeController", "ConstantStepSize", "ControlTerm", "DenseInterpolation", "Dopri5",
     "Dopri8", "Euler", "HalfSolver", "Heun", "Midpoint", "MultiTerm", "ODETerm", "PIDController", "Ralston", "SaveAt", "ShARK",
     "Solution", "SpaceTimeLevyArea", "SubSaveAt", "Tsit5", "VirtualBrownianTree", "diffeqsolve", "is_successful", "prepare",

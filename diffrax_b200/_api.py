@@ -706,26 +706,28 @@ class _MultiSolve:
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
                 stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096, throw: bool = True,
                 solver_state=None, controller_state=None, made_jump=None,
-                device: int = 0, hairer_initial_step: bool = False) -> Solution:
+                device: int = 0, hairer_initial_step: bool = False, final_out=None) -> Solution:
     """Batched forward solve == ``jax.vmap(lambda y0: diffrax.diffeqsolve(...))(y0)``
     (_integrate.py:888-1543).
 
     ``y0``: ``[N, d]`` (or ``[N]`` for scalar states).  torch CUDA tensors run in place on the
     current stream (device path); numpy arrays / CPU tensors go through
     ``dfx_ensemble_solve_host`` which stages them to GPU ``device`` and back.
-    ``t0`` / ``t1`` may be scalars or ``[N]`` arrays.  ``hairer_initial_step=True`` (extension) selects the
+    ``t0`` / ``t1`` may be scalars or ``[N]`` arrays.  ``final_out=(y_buf, t_buf)`` (extension): CUDA tensors ``[N, d]`` /
+    ``[N]`` that receive the final states / times on the device - also on the host-buffer path - so that a collective (the
+    multi-GPU gather, ``diffrax_b200.sharded_diffeqsolve``) can follow.  ``hairer_initial_step=True`` (extension) selects the
     starting-step algorithm coded at pid.py:51-81 for ``dt0=None``; the default reproduces what ``diffeqsolve`` does
     today, a first trial step of 0.01.
     """
     return prepare(terms, solver, t0, t1, dt0, y0, args, saveat=saveat, stepsize_controller=stepsize_controller, event=event,
                    max_steps=max_steps, solver_state=solver_state, controller_state=controller_state, made_jump=made_jump,
-                   device=device, hairer_initial_step=hairer_initial_step)(throw=throw)
+                   device=device, hairer_initial_step=hairer_initial_step, final_out=final_out)(throw=throw)
 
 
 def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
             stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096,
             solver_state=None, controller_state=None, made_jump=None, device: int = 0,
-            hairer_initial_step: bool = False) -> EnsembleSolve:
+            hairer_initial_step: bool = False, final_out=None) -> EnsembleSolve:
     """Validate the arguments of a `diffeqsolve` call and allocate its outputs once."""
     if args is not None:
         raise ValueError("args must be None: functor parameters are bound when the functor is created")
@@ -908,6 +910,26 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         t_final = xp.empty((n,), rdt)
     D.ts_out, D.ys_out, D.stats, D.result = xp.ptr(ts_out), xp.ptr(ys_out), xp.ptr(stats), xp.ptr(result)
     D.y_final, D.t_final = xp.ptr(y_final), xp.ptr(t_final)
+    if final_out is not None:   # caller-owned device buffers for the finals (the input of the multi-GPU gather)
+        yb, tb = final_out[:2]
+        if len(final_out) == 4:  # ... and, on the host path, device copies of the statistics / result codes
+            sb, rb = final_out[2:]
+            for buf, shape in ((sb, (n, 3)), (rb, (n,))):
+                if not (isinstance(buf, torch.Tensor) and buf.is_cuda and buf.is_contiguous() and tuple(buf.shape) == shape and buf.dtype == torch.int32):
+                    raise ValueError("final_out statistics / result buffers must be contiguous int32 CUDA tensors of shape [N, 3] / [N]")
+            keep_alive.extend([sb, rb])
+            if not xp.device_ptrs:
+                D.stats_device, D.result_device = sb.data_ptr(), rb.data_ptr()
+        for buf, shape in ((yb, (n, d)), (tb, (n,))):
+            if not (isinstance(buf, torch.Tensor) and buf.is_cuda and buf.is_contiguous() and tuple(buf.shape) == shape
+                    and buf.dtype == (rdt if is_torch else getattr(torch, str(np.dtype(rdt))))):
+                raise ValueError(f"final_out buffers must be contiguous CUDA tensors of shape {(n, d)} and {(n,)} in the state dtype")
+        keep_alive.extend([yb, tb])
+        if xp.device_ptrs:
+            D.y_final, D.t_final = yb.data_ptr(), tb.data_ptr()
+            y_final, t_final = yb, tb
+        else:
+            D.y_final_device, D.t_final_device = yb.data_ptr(), tb.data_ptr()
     dense = None
     if saveat.dense:
         s = L.dfx_num_stages(solver.solver_id)

@@ -65,3 +65,154 @@ def reduce_stats(stats: dict) -> dict:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     return {"num_steps": int(vec[0]), "num_accepted_steps": int(vec[1]), "num_rejected_steps": int(vec[2]),
             "num_failed": int(vec[3]), "max_steps_per_trajectory": int(mx[0])}
+
+
+# --------------------------------------------------------------------------------------
+# Product-level sharded entry: the BASELINE configuration "N trajectories sharded across 1/2/4/8 B200"
+# --------------------------------------------------------------------------------------
+import dataclasses
+from typing import Any, Optional
+
+
+@dataclasses.dataclass
+class ShardedSolution:
+    """Result of `sharded_diffeqsolve` on one rank.
+
+    local     this rank's `Solution` (rows [lo, hi) of the global batch; host or device arrays like the inputs)
+    y_final   [n_total, d] final states of the WHOLE batch, on this rank's device (NCCL all_gather), block order
+    t_final   [n_total]
+    stats     global totals: num_steps / num_accepted_steps / num_rejected_steps / num_failed / max_steps_per_trajectory
+    """
+    local: Any
+    lo: int
+    hi: int
+    n_total: int
+    y_final: Optional[torch.Tensor]
+    t_final: Optional[torch.Tensor]
+    stats: dict
+
+
+def _slice_rows(x, lo, hi):
+    return x if x is None or not hasattr(x, "shape") or len(x.shape) == 0 else x[lo:hi]
+
+
+def _slice_terms(terms, lo, hi):
+    """The same term structure over trajectories [lo, hi): per-trajectory Brownian keys are sliced."""
+    from . import _api
+    if isinstance(terms, _api.MultiTerm):
+        return _api.MultiTerm(*[_slice_terms(t, lo, hi) for t in terms.terms])
+    if isinstance(terms, _api.ControlTerm):
+        bm = terms.control
+        keys = _api._as_keys(bm.key)[lo:hi]
+        sub = _api.VirtualBrownianTree(bm.t0, bm.t1, bm.tol, bm.shape, keys, bm.levy_area, partitionable=bm.partitionable)
+        return _api.ControlTerm(terms.vector_field, sub)
+    return terms
+
+
+class ShardedSolve:
+    """A prepared sharded solve (see `prepare_sharded`): every call runs this rank's shard and then ONE collective - an
+    all_gather of a packed per-rank record [finals | t_final | 5 statistics] - so the gather of the final states and the
+    reduction of the statistics cost a single NCCL launch."""
+
+    def __init__(self, plan, lo, hi, n_total, d, dtype, device, group):
+        self.plan, self.lo, self.hi, self.n_total, self.d, self.group = plan, lo, hi, n_total, d, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.spans = [shard_range(n_total, r, self.world) for r in range(self.world)]
+        self.nmax = max(h - l for l, h in self.spans) if self.spans else 0
+        # packed record of one rank: nmax * d finals, nmax final times, 5 statistics (as reals: exact below 2^53 / 2^24)
+        self.rec = self.nmax * (d + 1) + 5
+        self.send = torch.zeros(self.rec, dtype=dtype, device=device)
+        self.recv = torch.empty(self.world * self.rec, dtype=dtype, device=device) if self.world > 1 else self.send
+        n = hi - lo
+        self.y_buf = self.send[: n * d].view(n, d)                       # the kernel writes the finals straight into the record
+        self.t_buf = self.send[self.nmax * d: self.nmax * d + n]
+        self.stat_buf = self.send[self.nmax * (d + 1):]
+        # host-buffer inputs: device copies of this rank's statistics / result codes, so the reduction needs no second H2D
+        self.stats_dev = torch.empty((n, 3), dtype=torch.int32, device=device) if device.type == "cuda" else None
+        self.result_dev = torch.empty((n,), dtype=torch.int32, device=device) if device.type == "cuda" else None
+
+    def __call__(self, throw: bool = True) -> ShardedSolution:
+        return self.gather(self.solve_local(throw=throw))
+
+    def solve_local(self, throw: bool = True):
+        """This rank's block: one C-ABI call; the finals land in the packed record."""
+        return self.plan(throw=throw)
+
+    def gather(self, sol) -> ShardedSolution:
+        """The one collective of the path: all_gather of every rank's [finals | t_final | statistics] record."""
+        st = sol.stats
+        dev = self.send.device
+        dt = torch.float64                                            # statistics are summed in fp64 whatever the state dtype
+        def _dev(x):
+            return x if isinstance(x, torch.Tensor) and x.is_cuda else torch.as_tensor(x).to(dev, non_blocking=True)
+        if isinstance(sol.result, torch.Tensor) and sol.result.is_cuda:          # device path
+            stats3 = torch.stack([st[k] for k in ("num_steps", "num_accepted_steps", "num_rejected_steps")], 1)
+            res = sol.result
+        elif self.stats_dev is not None and getattr(self, "host_outputs_on_device", False):   # host path: the call filled these
+            stats3, res = self.stats_dev, self.result_dev
+        else:
+            stats3 = torch.stack([_dev(st[k]) for k in ("num_steps", "num_accepted_steps", "num_rejected_steps")], 1)
+            res = _dev(sol.result)
+        s3 = stats3.to(dt)
+        failed = (res != 0).to(dt).sum().reshape(1)
+        mx = s3[:, 0].max().reshape(1) if s3.shape[0] else torch.zeros(1, dtype=dt, device=dev)
+        vec = torch.cat([s3.sum(0), failed, mx])
+        if self.send.dtype == torch.float64:
+            self.stat_buf.copy_(vec)
+        if self.world > 1:
+            if self.send.dtype != torch.float64:                      # fp32 states: the counters travel in their own fp64 record
+                allv = [torch.empty_like(vec) for _ in range(self.world)]
+                dist.all_gather(allv, vec, group=self.group)
+                allv = torch.stack(allv)
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+            rec = self.recv.view(self.world, self.rec)
+            if self.send.dtype == torch.float64:
+                allv = rec[:, self.nmax * (self.d + 1):]
+            y = torch.cat([rec[r, : (h - l) * self.d].view(h - l, self.d) for r, (l, h) in enumerate(self.spans)], 0)
+            t = torch.cat([rec[r, self.nmax * self.d: self.nmax * self.d + (h - l)] for r, (l, h) in enumerate(self.spans)], 0)
+        else:
+            allv = vec[None]
+            y, t = self.y_buf, self.t_buf
+        tot = allv[:, :4].sum(0)
+        stats = {"num_steps": tot[0], "num_accepted_steps": tot[1], "num_rejected_steps": tot[2], "num_failed": tot[3],
+                 "max_steps_per_trajectory": allv[:, 4].max()}                # 0-d device tensors: no host sync here
+        return ShardedSolution(sol, self.lo, self.hi, self.n_total, y, t, stats)
+
+
+def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, device=None, **kw) -> ShardedSolve:
+    """`prepare` for the sharded configuration.  `y0` (and per-trajectory `t0` / `t1`, Brownian keys) describe the GLOBAL
+    batch of N trajectories and are the same on every rank; rank r owns the contiguous block `shard_range(N, r, world)`.
+    Host inputs (NumPy / CPU tensors) go through the host-buffer entry of the C ABI, CUDA tensors through the device entry;
+    either way the finals land in a device record that one NCCL all_gather distributes."""
+    from . import _api
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_total = int(y0.shape[0])
+    lo, hi = shard_range(n_total, rank, world)
+    is_dev = isinstance(y0, torch.Tensor) and y0.is_cuda
+    if device is None:
+        device = y0.device if is_dev else torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    y_loc = y0[lo:hi]
+    if isinstance(y_loc, torch.Tensor):
+        y_loc = y_loc.contiguous()
+    d = 1 if y_loc.ndim == 1 else int(y_loc.shape[1])
+    import numpy as np
+    dtype = y_loc.dtype if isinstance(y_loc, torch.Tensor) else getattr(torch, str(np.asarray(y_loc).dtype))
+    if dtype not in (torch.float64, torch.float32):
+        dtype = torch.float64
+    sh = ShardedSolve.__new__(ShardedSolve)
+    # two-phase construction: the record buffers must exist before `prepare` binds them as final_out
+    ShardedSolve.__init__(sh, None, lo, hi, n_total, d, dtype, device, group)
+    sh.host_outputs_on_device = not is_dev
+    fo = (sh.y_buf, sh.t_buf) if is_dev else (sh.y_buf, sh.t_buf, sh.stats_dev, sh.result_dev)
+    sh.plan = _api.prepare(_slice_terms(terms, lo, hi), solver, _slice_rows(t0, lo, hi), _slice_rows(t1, lo, hi), dt0, y_loc, args,
+                           device=device.index if device.index is not None else 0, final_out=fo, **kw)
+    return sh
+
+
+def sharded_diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, throw: bool = True, group=None, device=None, **kw) -> ShardedSolution:
+    """`diffeqsolve` for a global batch sharded over the ranks of a `torch.distributed` group (one process per GPU):
+    trajectories are independent, so each rank integrates its block with no data-path collective, and ONE all_gather
+    then gives every rank the final states of the whole batch plus the global step statistics."""
+    return prepare_sharded(terms, solver, t0, t1, dt0, y0, args, group=group, device=device, **kw)(throw=throw)

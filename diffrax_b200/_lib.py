@@ -58,6 +58,8 @@ class SolveDesc(C.Structure):
         ("event_params", C.c_void_p), ("n_event_params", C.c_int32),
         ("event_rtol", C.c_double), ("event_atol", C.c_double),
         ("state_in", C.c_void_p), ("state_in_flags", C.c_int32), ("state_out", C.c_void_p),
+        ("y_final_device", C.c_void_p), ("t_final_device", C.c_void_p),
+        ("stats_device", C.c_void_p), ("result_device", C.c_void_p),
     ]
 
 

@@ -441,8 +441,11 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
   d.field_weights = dev_in(h->field_weights, (size_t)h->n_field_weights * es);
   d.ts_out = dev_out(off(h->ts_out, T * es), N * T * es);
   d.ys_out = dev_out(off(h->ys_out, T * D * es), N * T * D * es);
-  d.stats = (int32_t *)dev_out(off(h->stats, 12), N * 3 * 4);
-  d.result = (int32_t *)dev_out(off(h->result, 4), N * 4);
+  if (h->stats_device) { d.stats = h->stats_device + (size_t)lo * 3; d2h.emplace_back((char *)h->stats + (size_t)lo * 12, d.stats, N * 12); }
+  else d.stats = (int32_t *)dev_out(off(h->stats, 12), N * 3 * 4);
+  if (h->result_device) { d.result = h->result_device + (size_t)lo; d2h.emplace_back((char *)h->result + (size_t)lo * 4, d.result, N * 4); }
+  else d.result = (int32_t *)dev_out(off(h->result, 4), N * 4);
+  d.stats_device = d.result_device = nullptr;
   d.save_count = (int32_t *)dev_out(off(h->save_count, 4), N * 4);
   if (h->save_dense) {
     d.dense_ts = dev_out(off(h->dense_ts, (ms + 1) * es), N * (ms + 1) * es);
@@ -453,8 +456,20 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
   }
   d.state_in = dev_in(off(h->state_in, (5 + D) * es), N * (5 + D) * es);
   d.state_out = dev_out(off(h->state_out, (5 + D) * es), N * (5 + D) * es);
-  d.y_final = dev_out(off(h->y_final, D * es), N * D * es);
-  d.t_final = dev_out(off(h->t_final, es), N * es);
+  // finals: into the caller's device buffers when given (then copied to the host outputs from there), else scratch
+  if (h->y_final_device) {
+    d.y_final = (char *)h->y_final_device + (size_t)lo * D * es;
+    if (h->y_final) d2h.emplace_back((char *)h->y_final + (size_t)lo * D * es, d.y_final, N * D * es);
+  } else {
+    d.y_final = dev_out(off(h->y_final, D * es), N * D * es);
+  }
+  if (h->t_final_device) {
+    d.t_final = (char *)h->t_final_device + (size_t)lo * es;
+    if (h->t_final) d2h.emplace_back((char *)h->t_final + (size_t)lo * es, d.t_final, N * es);
+  } else {
+    d.t_final = dev_out(off(h->t_final, es), N * es);
+  }
+  d.y_final_device = d.t_final_device = nullptr;
   if (!rc) rc = dfx_ensemble_solve(&d, (void *)st);
   if (!rc)
     for (auto &c : d2h)
@@ -504,7 +519,7 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
   const int nchunks = (int)((N + chunk_len - 1) / chunk_len);
 
   // per-thread pinned control block: [0, 64) completion flags written by the kernel, [64, 128) the values 1..64 that
-  // the copy engine moves into `in_ready`, [128] the abort word the kernel reads while it waits for inputs
+  // the copy engine moves into `in_ready`, [128] a non-zero word (copied into the device abort word when delivery fails)
   static thread_local unsigned *ctl_host = nullptr;
   if (!ctl_host) {
     DFX_CUDA_OK(cudaHostAlloc((void **)&ctl_host, (2 * kMaxPipeChunks + 1) * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable));
@@ -512,8 +527,7 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
   }
   volatile unsigned *flags = ctl_host;
   for (int i = 0; i < nchunks; ++i) flags[i] = 0;
-  volatile unsigned *abort_word = ctl_host + 2 * kMaxPipeChunks;
-  *abort_word = 0;
+  ctl_host[2 * kMaxPipeChunks] = 0xFFFFFFFFu;
   unsigned *flags_dev = nullptr;
   DFX_CUDA_OK(cudaHostGetDevicePointer((void **)&flags_dev, ctl_host, 0));
 
@@ -574,8 +588,8 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
     cursor = 0;
     ins.clear();
     outs.clear();
-    ctl_dev = (unsigned *)dev_alloc((1 + (size_t)nchunks) * sizeof(unsigned));  // [in_ready, done[nchunks]]
-    if (!measuring) PIPE_OK(cudaMemsetAsync(ctl_dev, 0, (1 + (size_t)nchunks) * sizeof(unsigned), s_in));
+    ctl_dev = (unsigned *)dev_alloc((2 + (size_t)nchunks) * sizeof(unsigned));  // [in_ready, abort, done[nchunks]]
+    if (!measuring) PIPE_OK(cudaMemsetAsync(ctl_dev, 0, (2 + (size_t)nchunks) * sizeof(unsigned), s_in));
     d.field_weights = whole_in(h->field_weights, (size_t)h->n_field_weights * es);
     d.y0 = per_traj_in(h->y0, D * es);
     d.t0_per_traj = per_traj_in(h->t0_per_traj, es);
@@ -583,11 +597,18 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
     d.bm_keys = (const uint32_t *)per_traj_in(h->bm_keys, 8);
     d.ts_out = per_traj_out(h->ts_out, T * es);
     d.ys_out = per_traj_out(h->ys_out, T * D * es);
-    d.stats = (int32_t *)per_traj_out(h->stats, 12);
-    d.result = (int32_t *)per_traj_out(h->result, 4);
+    if (h->stats_device) { d.stats = h->stats_device; outs.push_back({(const char *)h->stats, (char *)h->stats_device, 12}); }
+    else d.stats = (int32_t *)per_traj_out(h->stats, 12);
+    if (h->result_device) { d.result = h->result_device; outs.push_back({(const char *)h->result, (char *)h->result_device, 4}); }
+    else d.result = (int32_t *)per_traj_out(h->result, 4);
+    d.stats_device = d.result_device = nullptr;
     d.save_count = (int32_t *)per_traj_out(h->save_count, 4);
-    d.y_final = per_traj_out(h->y_final, D * es);
-    d.t_final = per_traj_out(h->t_final, es);
+    // finals: the caller's device buffers when given (the host copies, if any, are taken from there chunk by chunk)
+    if (h->y_final_device) { d.y_final = h->y_final_device; if (h->y_final) outs.push_back({(const char *)h->y_final, (char *)h->y_final_device, D * es}); }
+    else d.y_final = per_traj_out(h->y_final, D * es);
+    if (h->t_final_device) { d.t_final = h->t_final_device; if (h->t_final) outs.push_back({(const char *)h->t_final, (char *)h->t_final_device, es}); }
+    else d.t_final = per_traj_out(h->t_final, es);
+    d.y_final_device = d.t_final_device = nullptr;
   };
   layout();
   {
@@ -609,7 +630,7 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
   bool launched = false;
   t_enq = now_ms();
   if (!rc) {
-    HostPipe hp{ctl_dev, ctl_dev + 1, flags_dev, flags_dev + 2 * kMaxPipeChunks, (int)chunk_len, false};
+    HostPipe hp{ctl_dev, ctl_dev + 2, flags_dev, (int)chunk_len, false};
     host_pipe() = &hp;
     rc = dfx_ensemble_solve(&d, (void *)s_k);
     host_pipe() = nullptr;
@@ -622,8 +643,15 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
     if (launched && atoi(e) != 0) fail("injected fault", cudaErrorUnknown);
   }
   for (int c = 1; c < nchunks && launched && !rc; ++c) enqueue_inputs(c);
-  // If anything failed after the launch, some chunks will never be delivered: release the kernel's waiting lanes.
-  if (launched && rc) { *abort_word = 1; __sync_synchronize(); }
+  // If anything failed after the launch, some chunks will never be delivered: release the kernel's waiting lanes by
+  // setting the device abort word next to `in_ready` (on the output stream: the input stream may be the one that failed).
+  bool abort_sent = false;
+  auto release_kernel = [&] {
+    if (!launched || abort_sent) return;
+    abort_sent = true;
+    cudaMemcpyAsync(ctl_dev + 1, ctl_host + 2 * kMaxPipeChunks, sizeof(unsigned), cudaMemcpyHostToDevice, s_out);
+  };
+  if (rc) release_kernel();
   const double t_enq_all = now_ms();
   std::vector<unsigned> v_flag;
   // chunks complete roughly, not exactly, in order: every pass sends whichever have become ready
@@ -654,7 +682,7 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
       if (qi != cudaSuccess && qi != cudaErrorNotReady) fail("input copies", qi);
     }
   }
-  if (launched && rc) { *abort_word = 1; __sync_synchronize(); }  // never leave the kernel waiting for inputs
+  if (rc) release_kernel();  // never leave the kernel waiting for inputs
   if (trace && s_k) { cudaStreamSynchronize(s_k); t_k = now_ms(); }
   for (cudaStream_t st : {s_in, s_k, s_out})
     if (st) { const cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) fail("stream sync", e); }

@@ -112,11 +112,10 @@ struct SolveParams {
   unsigned long long *work_counter;
   // Host-pipelined mode (dfx_ensemble_solve_host; SaveAt(t1=True) instantiation only): ONE launch over the whole batch
   // while the copy engines bring the inputs in and take the results out in chunks of pipe_chunk_len trajectories.
-  const unsigned *pipe_in_ready;  // device word: number of input chunks resident so far (bumped by a 4-byte H2D copy
+  const unsigned *pipe_in_ready;  // device words [in_ready, abort]: number of input chunks resident so far (bumped by a 4-byte H2D copy
                                   // that is stream-ordered after the chunk's data)
   unsigned *pipe_done;            // device: finalised trajectories per chunk
   unsigned *pipe_host_flags;      // mapped pinned host memory: word c becomes 1 when every result of chunk c is written
-  const unsigned *pipe_abort;     // mapped pinned host memory: non-zero = the host cannot deliver the remaining inputs
   int pipe_chunk_len;             // multiple of 32 trajectories, so no 128-byte line straddles two chunks
   const uint32_t *keys;
   VbtParams vbt;
@@ -430,10 +429,10 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           if constexpr (!RICH) {
             if (p.pipe_in_ready != nullptr) {  // wait until the copy engine has delivered this trajectory's chunk
               const unsigned need = (unsigned)(idx / p.pipe_chunk_len) + 1u;
-              // the host raises the abort word (mapped host memory, read only while waiting) when it cannot deliver the
-              // remaining chunks, e.g. after a failed H2D enqueue: the kernel must never outwait a host that gave up
+              // pipe_in_ready[1] is the abort word (device memory, next to in_ready): the host sets it when it cannot
+              // deliver the remaining chunks (e.g. a failed H2D enqueue) - the kernel must never outwait a host that gave up
               while (*(volatile const unsigned *)p.pipe_in_ready < need) {
-                if (*(volatile const unsigned *)p.pipe_abort != 0u) { pipe_aborted = true; break; }
+                if (((volatile const unsigned *)p.pipe_in_ready)[1] != 0u) { pipe_aborted = true; break; }
                 __nanosleep(200);
               }
               __threadfence();

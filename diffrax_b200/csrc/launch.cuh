@@ -19,7 +19,6 @@ int register_builtin(int field_id, int dim, int solver_id, int dtype, int levy, 
 struct HostPipe {
   const unsigned *in_ready;
   unsigned *done, *host_flags;
-  const unsigned *abort;
   int chunk_len;
   bool consumed;
 };
@@ -213,7 +212,6 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
     p.pipe_in_ready = hp->in_ready;
     p.pipe_done = hp->done;
     p.pipe_host_flags = hp->host_flags;
-    p.pipe_abort = hp->abort;
     p.pipe_chunk_len = hp->chunk_len;
     hp->consumed = true;
   }

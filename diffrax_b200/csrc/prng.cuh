@@ -99,26 +99,21 @@ __device__ __forceinline__ unsigned long long random_bits64(Key key, int w, bool
   return ((unsigned long long)a << 32) | (unsigned long long)b;
 }
 
-// log1p for x > -1 as ONE explicit operation sequence (see oracle/oracle.c orc_log1p_*, which performs the same one):
-// 1+x = 2^k (1+f), f in [sqrt(1/2)-1, sqrt(2)-1); log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)), s = f/(2+f); the rounding
-// error of 1+x is carried in c (the published fdlibm scheme and coefficients).  <= 1 ulp.
+// log1p on [-1, 0] (x = -u*u is all erf_inv needs) as ONE explicit, branch-free operation sequence - the same one as
+// oracle/oracle.c orc_log1p_*: 1+x = 2^k (1+f), f in [sqrt(1/2)-1, sqrt(2)-1), taken from the exact x by one fma
+// (f = 2^-k x + (2^-k - 1)); log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)), s = f/(2+f) (the published fdlibm scheme and
+// coefficients).  <= 1 ulp.
 __device__ __forceinline__ double x_log1p(double x) {
   constexpr double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
-  if (!(x > -1.0)) return x == -1.0 ? -Num<double>::inf() : Num<double>::nan();
-  if (x == Num<double>::inf()) return x;
-  double f = x, c = 0.0;
-  int k = 0;
-  if (!(x > -0.2928932188134524 && x < 0.41421356237309503)) {
-    const double u = x_add(1.0, x);
-    const long long b = __double_as_longlong(u);
-    k = (int)((b >> 52) & 0x7ff) - 1023;
-    c = (k > 0) ? x_sub(1.0, x_sub(u, x)) : x_sub(x, x_sub(u, 1.0));
-    c = x_div(c, u);
-    long long m = b & 0x000fffffffffffffLL;
-    if (m < 0x6a09e667f3bcdLL) m |= 0x3ff0000000000000LL;
-    else { k += 1; m |= 0x3fe0000000000000LL; }
-    f = x_sub(__longlong_as_double(m), 1.0);
-  }
+  if (!(x > -1.0 && x <= 0.0)) return x == -1.0 ? -Num<double>::inf() : Num<double>::nan();
+  const double u = x_add(1.0, x);
+  const int hi = __double2hiint(u);
+  const unsigned lo = (unsigned)__double2loint(u);
+  const int mh = hi & 0x000fffff;  // mantissa >= that of sqrt(2) (0x6a09e 667f3bcd)?
+  int k = ((hi >> 20) & 0x7ff) - 1023 + ((mh > 0x6a09e || (mh == 0x6a09e && lo >= 0x667f3bcdu)) ? 1 : 0);
+  k = (x > -0.2928932188134524) ? 0 : k;
+  const double scale = __hiloint2double((1023 - k) << 20, 0);
+  const double f = x_fma(scale, x, x_sub(scale, 1.0));
   const double hfsq = x_mul(x_mul(0.5, f), f);
   const double s = x_div(f, x_add(2.0, f));
   const double z = x_mul(s, s);
@@ -130,28 +125,18 @@ __device__ __forceinline__ double x_log1p(double x) {
   r = x_fma(r, z, 3.999999999940941908e-01);
   r = x_fma(r, z, 6.666666666666735130e-01);
   r = x_mul(r, z);
-  const double t = x_mul(s, x_add(hfsq, r));
-  if (k == 0) return x_sub(f, x_sub(hfsq, t));
   const double dk = (double)k;
-  return x_sub(x_mul(dk, ln2_hi), x_sub(x_sub(hfsq, x_add(t, x_add(x_mul(dk, ln2_lo), c))), f));
+  return x_sub(x_mul(dk, ln2_hi), x_sub(x_sub(hfsq, x_add(x_mul(s, x_add(hfsq, r)), x_mul(dk, ln2_lo))), f));
 }
 __device__ __forceinline__ float x_log1p(float x) {
   constexpr float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
-  if (!(x > -1.0f)) return x == -1.0f ? -Num<float>::inf() : Num<float>::nan();
-  if (x == Num<float>::inf()) return x;
-  float f = x, c = 0.0f;
-  int k = 0;
-  if (!(x > -0.29289323f && x < 0.41421357f)) {
-    const float u = x_add(1.0f, x);
-    const int b = __float_as_int(u);
-    k = ((b >> 23) & 0xff) - 127;
-    c = (k > 0) ? x_sub(1.0f, x_sub(u, x)) : x_sub(x, x_sub(u, 1.0f));
-    c = x_div(c, u);
-    int m = b & 0x007fffff;
-    if (m < 0x3504f3) m |= 0x3f800000;
-    else { k += 1; m |= 0x3f000000; }
-    f = x_sub(__int_as_float(m), 1.0f);
-  }
+  if (!(x > -1.0f && x <= 0.0f)) return x == -1.0f ? -Num<float>::inf() : Num<float>::nan();
+  const float u = x_add(1.0f, x);
+  const int b = __float_as_int(u);
+  int k = ((b >> 23) & 0xff) - 127 + (((b & 0x007fffff) >= 0x3504f3) ? 1 : 0);
+  k = (x > -0.29289323f) ? 0 : k;
+  const float scale = __int_as_float((127 - k) << 23);
+  const float f = x_fma(scale, x, x_sub(scale, 1.0f));
   const float hfsq = x_mul(x_mul(0.5f, f), f);
   const float s = x_div(f, x_add(2.0f, f));
   const float z = x_mul(s, s);
@@ -163,10 +148,8 @@ __device__ __forceinline__ float x_log1p(float x) {
   r = x_fma(r, z, 4.0000000596e-01f);
   r = x_fma(r, z, 6.6666668653e-01f);
   r = x_mul(r, z);
-  const float t = x_mul(s, x_add(hfsq, r));
-  if (k == 0) return x_sub(f, x_sub(hfsq, t));
   const float dk = (float)k;
-  return x_sub(x_mul(dk, ln2_hi), x_sub(x_sub(hfsq, x_add(t, x_add(x_mul(dk, ln2_lo), c))), f));
+  return x_sub(x_mul(dk, ln2_hi), x_sub(x_sub(hfsq, x_add(x_mul(s, x_add(hfsq, r)), x_mul(dk, ln2_lo))), f));
 }
 
 // lax.erf_inv - Giles' polynomials in w = -log1p(-x*x), coefficients and branches as XLA evaluates them

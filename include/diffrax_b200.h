@@ -164,6 +164,15 @@ typedef struct dfx_solve_desc {
    * state_in_flags: bit 0 controller_state passed, bit 1 solver_state passed, bit 2 made_jump passed. */
   const void *state_in; int32_t state_in_flags;
   void *state_out;
+
+  /* dfx_ensemble_solve_host only: optional DEVICE buffers (on the device the call runs on) that receive
+   * the final states / times ([N, d] / [N]) in addition to the host outputs, so that a collective can follow the call without a
+   * second H2D (the multi-GPU gather of SURVEY section 8e: NCCL all_gather of the finals).  Ignored by the device call,
+   * where y_final / t_final are device pointers already. */
+  void *y_final_device;
+  void *t_final_device;
+  int32_t *stats_device;      /* [N, 3]: likewise for the step statistics ... */
+  int32_t *result_device;     /* [N]:    ... and the result codes (reduced on the device before the gather) */
 } dfx_solve_desc;
 
 /* ---- library ---- */

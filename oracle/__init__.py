@@ -20,6 +20,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_LIB_FMA_PATH = os.path.join(_HERE, "liboracle_fma.so")
 
 F64, F32 = 0, 1
 SOLVERS = {"tsit5": 0, "dopri5": 1, "dopri8": 2, "heun": 3, "bosh3": 4, "midpoint": 5,
@@ -70,60 +71,81 @@ class Desc(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    """Compile liboracle.so with the committed Makefile (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_core.inc", "oracle.h", "oracle_tableaux.h")]
-    stale = force or not os.path.exists(_LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
-    if stale:
-        subprocess.run(["make", "-C", _HERE, "-s", "-B", "liboracle.so"], check=True)
+    """Compile liboracle.so (and the FMA-contracted variant liboracle_fma.so) with the committed Makefile (gcc only)."""
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_core.inc", "oracle.h", "oracle_tableaux.h", "Makefile")]
+    for target in (_LIB_PATH, _LIB_FMA_PATH):
+        stale = force or not os.path.exists(target) or any(os.path.getmtime(s) > os.path.getmtime(target) for s in srcs)
+        if stale:
+            subprocess.run(["make", "-C", _HERE, "-s", "-B", os.path.basename(target)], check=True)
     return _LIB_PATH
 
 
 _lib = None
+_libs = {}
+_variant = "strict"
+
+
+class rounding:
+    """``with oracle.rounding("fma"): ...`` runs the oracle built with FMA contraction allowed (liboracle_fma.so)."""
+
+    def __init__(self, variant):
+        assert variant in ("strict", "fma")
+        self.variant = variant
+
+    def __enter__(self):
+        global _variant
+        self.prev, _variant = _variant, self.variant
+
+    def __exit__(self, *exc):
+        global _variant
+        _variant = self.prev
+
+
+def _load(path):
+    L = C.CDLL(path)
+    L.orc_solve.argtypes = [C.POINTER(Desc)]
+    L.orc_solve.restype = C.c_int
+    L.orc_out_size.argtypes = [C.POINTER(Desc)]
+    L.orc_out_size.restype = C.c_int
+    L.orc_last_error.restype = C.c_char_p
+    L.orc_num_stages.argtypes = [C.c_int]
+    L.orc_num_stages.restype = C.c_int
+    L.orc_hw_threads.restype = C.c_int
+    L.orc_threefry2x32.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)] * 2
+    L.orc_split.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+    L.orc_normal_f64.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.orc_normal_f64.restype = C.c_double
+    L.orc_normal_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.orc_normal_f32.restype = C.c_float
+    L.orc_erfinv_f64.argtypes = [C.c_double]
+    L.orc_erfinv_f64.restype = C.c_double
+    L.orc_erfinv_f32.argtypes = [C.c_float]
+    L.orc_erfinv_f32.restype = C.c_float
+    L.orc_normal_vec_f64.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    L.orc_normal_vec_f64.restype = C.c_double
+    L.orc_normal_vec_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
+    L.orc_normal_vec_f32.restype = C.c_float
+    L.orc_log1p_f64.argtypes = [C.c_double]
+    L.orc_log1p_f64.restype = C.c_double
+    L.orc_log1p_f32.argtypes = [C.c_float]
+    L.orc_log1p_f32.restype = C.c_float
+    L.orc_vbt_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_double,
+                                   C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_vbt_evaluate.restype = C.c_int
+    L.orc_dense_evaluate.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
+                                     C.c_void_p]
+    L.orc_dense_evaluate.restype = C.c_int
+    L.orc_dense_derivative.argtypes = L.orc_dense_evaluate.argtypes
+    L.orc_dense_derivative.restype = C.c_int
+    return L
 
 
 def lib():
-    global _lib
-    if _lib is None:
+    if _variant not in _libs:
         build()
-        L = C.CDLL(_LIB_PATH)
-        L.orc_solve.argtypes = [C.POINTER(Desc)]
-        L.orc_solve.restype = C.c_int
-        L.orc_out_size.argtypes = [C.POINTER(Desc)]
-        L.orc_out_size.restype = C.c_int
-        L.orc_last_error.restype = C.c_char_p
-        L.orc_num_stages.argtypes = [C.c_int]
-        L.orc_num_stages.restype = C.c_int
-        L.orc_hw_threads.restype = C.c_int
-        L.orc_threefry2x32.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)] * 2
-        L.orc_split.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
-        L.orc_normal_f64.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
-        L.orc_normal_f64.restype = C.c_double
-        L.orc_normal_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
-        L.orc_normal_f32.restype = C.c_float
-        L.orc_erfinv_f64.argtypes = [C.c_double]
-        L.orc_erfinv_f64.restype = C.c_double
-        L.orc_erfinv_f32.argtypes = [C.c_float]
-        L.orc_erfinv_f32.restype = C.c_float
-        L.orc_normal_vec_f64.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
-        L.orc_normal_vec_f64.restype = C.c_double
-        L.orc_normal_vec_f32.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]
-        L.orc_normal_vec_f32.restype = C.c_float
-        L.orc_log1p_f64.argtypes = [C.c_double]
-        L.orc_log1p_f64.restype = C.c_double
-        L.orc_log1p_f32.argtypes = [C.c_float]
-        L.orc_log1p_f32.restype = C.c_float
-        L.orc_vbt_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_double,
-                                       C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-        L.orc_vbt_evaluate.restype = C.c_int
-        L.orc_dense_evaluate.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
-                                         C.c_void_p]
-        L.orc_dense_evaluate.restype = C.c_int
-        L.orc_dense_derivative.argtypes = L.orc_dense_evaluate.argtypes
-        L.orc_dense_derivative.restype = C.c_int
-        _lib = L
-    return _lib
+        _libs[_variant] = _load(_LIB_PATH if _variant == "strict" else _LIB_FMA_PATH)
+    return _libs[_variant]
 
 
 def hw_threads() -> int:

@@ -78,78 +78,58 @@ void orc_split(uint32_t k0, uint32_t k1, int num, int partitionable, uint32_t *o
  * for bit, and the sequence is within 1 ulp of the exact log1p (tests/test_oracle_prng.py).
  *   - every "fma(a, b, c)" below is ONE rounding; every other operator rounds on its own
  *     (this file is compiled with -ffp-contract=off);
- *   - log1p follows the classical argument reduction 1+x = 2^k (1+f), f in [sqrt(1/2)-1, sqrt(2)-1),
- *     log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)), s = f / (2 + f), with the rounding error of 1+x
- *     carried in c (the published fdlibm scheme and coefficients).
+ *   - log1p (needed on [-1, 0] only) follows the classical argument reduction 1+x = 2^k (1+f),
+ *     f in [sqrt(1/2)-1, sqrt(2)-1), log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)), s = f / (2 + f) (the published
+ *     fdlibm scheme and coefficients), branch-free: f comes from the exact x by one fma, so 1+x's rounding never enters.
  * ------------------------------------------------------------------------------------- */
-double orc_log1p_f64(double x) {
+double orc_log1p_f64(double x) { /* domain: -1 <= x <= 0 (the only one erf_inv needs: x = -u*u) */
   static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
                       Lp[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
                                2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
                                1.479819860511658591e-01};
-  if (!(x > -1.0)) return x == -1.0 ? -INFINITY : NAN;
-  if (x == INFINITY) return x;
-  double f, c = 0.0;
-  int k = 0;
-  if (x > -0.2928932188134524 && x < 0.41421356237309503) {
-    f = x; /* 1 + x already lies in [sqrt(1/2), sqrt(2)): no reduction, no rounding of 1 + x */
-  } else {
-    const double u = 1.0 + x;
-    uint64_t b;
-    memcpy(&b, &u, 8);
-    k = (int)((b >> 52) & 0x7ff) - 1023;
-    c = (k > 0) ? 1.0 - (u - x) : x - (u - 1.0); /* what the rounding of 1 + x lost */
-    c = c / u;
-    uint64_t m = b & 0x000fffffffffffffull;
-    if (m < 0x6a09e667f3bcdull) m |= 0x3ff0000000000000ull;          /* mantissa below sqrt(2): 1+f in [1, sqrt 2) */
-    else { k += 1; m |= 0x3fe0000000000000ull; }                     /* else halve it: 1+f in [sqrt(1/2), 1) */
-    double mu;
-    memcpy(&mu, &m, 8);
-    f = mu - 1.0;
-  }
+  if (!(x > -1.0 && x <= 0.0)) return x == -1.0 ? -INFINITY : NAN;
+  /* k from the (rounded) 1 + x; for x > sqrt(1/2) - 1 no reduction is needed */
+  const double u = 1.0 + x;
+  uint64_t b;
+  memcpy(&b, &u, 8);
+  int k = (int)((b >> 52) & 0x7ff) - 1023 + ((b & 0x000fffffffffffffull) >= 0x6a09e667f3bcdull ? 1 : 0);
+  if (x > -0.2928932188134524) k = 0;
+  /* 1 + f = 2^-k (1 + x)  =>  f = 2^-k x + (2^-k - 1): ONE fma from the exact x, so the rounding of 1 + x never enters */
+  const uint64_t sb = (uint64_t)(1023 - k) << 52;
+  double scale;
+  memcpy(&scale, &sb, 8);
+  const double f = fma(scale, x, scale - 1.0);
   const double hfsq = (0.5 * f) * f;
   const double s = f / (2.0 + f);
   const double z = s * s;
   double r = Lp[6];
   for (int i = 5; i >= 0; --i) r = fma(r, z, Lp[i]);
   r = r * z;
-  if (k == 0) return f - (hfsq - s * (hfsq + r));
   const double dk = (double)k;
-  return dk * ln2_hi - ((hfsq - (s * (hfsq + r) + (dk * ln2_lo + c))) - f);
+  return dk * ln2_hi - ((hfsq - (s * (hfsq + r) + dk * ln2_lo)) - f);
 }
 float orc_log1p_f32(float x) {
   static const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f,
                      Lp[7] = {6.6666668653e-01f, 4.0000000596e-01f, 2.8571429849e-01f, 2.2222198546e-01f,
                               1.8183572590e-01f, 1.5313838422e-01f, 1.4798198640e-01f};
-  if (!(x > -1.0f)) return x == -1.0f ? -INFINITY : NAN;
-  if (x == INFINITY) return x;
-  float f, c = 0.0f;
-  int k = 0;
-  if (x > -0.29289323f && x < 0.41421357f) {
-    f = x;
-  } else {
-    const float u = 1.0f + x;
-    uint32_t b;
-    memcpy(&b, &u, 4);
-    k = (int)((b >> 23) & 0xff) - 127;
-    c = (k > 0) ? 1.0f - (u - x) : x - (u - 1.0f);
-    c = c / u;
-    uint32_t m = b & 0x007fffffu;
-    if (m < 0x3504f3u) m |= 0x3f800000u;
-    else { k += 1; m |= 0x3f000000u; }
-    float mu;
-    memcpy(&mu, &m, 4);
-    f = mu - 1.0f;
-  }
+  if (!(x > -1.0f && x <= 0.0f)) return x == -1.0f ? -INFINITY : NAN;
+  const float u = 1.0f + x;
+  uint32_t b;
+  memcpy(&b, &u, 4);
+  int k = (int)((b >> 23) & 0xff) - 127 + ((b & 0x007fffffu) >= 0x3504f3u ? 1 : 0);
+  if (x > -0.29289323f) k = 0;
+  const uint32_t sb = (uint32_t)(127 - k) << 23;
+  float scale;
+  memcpy(&scale, &sb, 4);
+  const float f = fmaf(scale, x, scale - 1.0f);
   const float hfsq = (0.5f * f) * f;
   const float s = f / (2.0f + f);
   const float z = s * s;
   float r = Lp[6];
   for (int i = 5; i >= 0; --i) r = fmaf(r, z, Lp[i]);
   r = r * z;
-  if (k == 0) return f - (hfsq - s * (hfsq + r));
   const float dk = (float)k;
-  return dk * ln2_hi - ((hfsq - (s * (hfsq + r) + (dk * ln2_lo + c))) - f);
+  return dk * ln2_hi - ((hfsq - (s * (hfsq + r) + dk * ln2_lo)) - f);
 }
 
 /* lax.erf_inv, f32: Giles (2010) single-precision polynomial, coefficients and branch as XLA's ErfInv32

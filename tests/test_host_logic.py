@@ -133,3 +133,50 @@ def test_gather_and_reduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+_WORKER_SHARDED = r'''
+import os, sys, types, torch
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from diffrax_b200 import _dist
+rank, local, world = _dist.init_from_env("gloo")
+n_total, d = 11, 3
+lo, hi = _dist.shard_range(n_total, rank, world)
+full_y = torch.arange(n_total * d, dtype=torch.float64).reshape(n_total, d) * 0.5
+full_t = torch.arange(n_total, dtype=torch.float64) + 100.0
+steps = torch.arange(n_total, dtype=torch.int32) + 10
+sh = _dist.ShardedSolve(None, lo, hi, n_total, d, torch.float64, torch.device("cpu"), None)
+def plan(throw=True):              # stands in for the CUDA solve: writes this rank's finals into the packed record
+    sh.y_buf.copy_(full_y[lo:hi]); sh.t_buf.copy_(full_t[lo:hi])
+    return types.SimpleNamespace(stats={{"num_steps": steps[lo:hi], "num_accepted_steps": steps[lo:hi] - 3,
+                                         "num_rejected_steps": torch.full((hi - lo,), 3, dtype=torch.int32)}},
+                                 result=(torch.arange(lo, hi) % 4 == 0).to(torch.int32))
+sh.plan = plan
+for _ in range(2):                 # the record is reused across calls
+    out = sh()
+    assert torch.equal(out.y_final, full_y) and torch.equal(out.t_final, full_t), (rank, out.y_final)
+    assert int(out.stats["num_steps"]) == int(steps.sum()) and int(out.stats["num_accepted_steps"]) == int(steps.sum()) - 3 * n_total
+    assert int(out.stats["num_rejected_steps"]) == 3 * n_total and int(out.stats["num_failed"]) == 3
+    assert int(out.stats["max_steps_per_trajectory"]) == n_total - 1 + 10 and (out.lo, out.hi, out.n_total) == (lo, hi, n_total)
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_sharded_solve_record_world_size_2_gloo(tmp_path):
+    """The sharded product entry's one collective (packed [finals | t_final | statistics] record, uneven shards) under gloo
+    with two processes; the CUDA solve is replaced by a stub that writes the rank's rows."""
+    script = tmp_path / "worker_sharded.py"
+    script.write_text(_WORKER_SHARDED.format(root=ROOT))
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
