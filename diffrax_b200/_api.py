@@ -912,14 +912,15 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     D.y_final, D.t_final = xp.ptr(y_final), xp.ptr(t_final)
     if final_out is not None:   # caller-owned device buffers for the finals (the input of the multi-GPU gather)
         yb, tb = final_out[:2]
-        if len(final_out) == 4:  # ... and, on the host path, device copies of the statistics / result codes
-            sb, rb = final_out[2:]
-            for buf, shape in ((sb, (n, 3)), (rb, (n,))):
-                if not (isinstance(buf, torch.Tensor) and buf.is_cuda and buf.is_contiguous() and tuple(buf.shape) == shape and buf.dtype == torch.int32):
-                    raise ValueError("final_out statistics / result buffers must be contiguous int32 CUDA tensors of shape [N, 3] / [N]")
-            keep_alive.extend([sb, rb])
-            if not xp.device_ptrs:
-                D.stats_device, D.result_device = sb.data_ptr(), rb.data_ptr()
+        if len(final_out) == 3:  # ... and the ensemble totals [4] int64, reduced inside the kernel
+            tot = final_out[2]
+            if not (isinstance(tot, torch.Tensor) and tot.is_cuda and tot.is_contiguous() and tuple(tot.shape) == (4,) and tot.dtype == torch.int64):
+                raise ValueError("final_out totals buffer must be a contiguous int64 CUDA tensor of shape [4]")
+            keep_alive.append(tot)
+            if xp.device_ptrs:
+                D.totals = tot.data_ptr()
+            else:
+                D.totals_device = tot.data_ptr()
         for buf, shape in ((yb, (n, d)), (tb, (n,))):
             if not (isinstance(buf, torch.Tensor) and buf.is_cuda and buf.is_contiguous() and tuple(buf.shape) == shape
                     and buf.dtype == (rdt if is_torch else getattr(torch, str(np.dtype(rdt))))):

@@ -111,71 +111,48 @@ def _slice_terms(terms, lo, hi):
 
 class ShardedSolve:
     """A prepared sharded solve (see `prepare_sharded`): every call runs this rank's shard and then ONE collective - an
-    all_gather of a packed per-rank record [finals | t_final | 5 statistics] - so the gather of the final states and the
-    reduction of the statistics cost a single NCCL launch."""
+    all_gather of a packed per-rank record [finals | t_final | 4 int64 totals] - so the gather of the final states and the
+    reduction of the statistics cost a single NCCL launch.  The solve kernel writes the finals AND
+    the ensemble totals (reduced in-kernel) straight into the record; nothing is staged or reduced in between."""
 
     def __init__(self, plan, lo, hi, n_total, d, dtype, device, group):
         self.plan, self.lo, self.hi, self.n_total, self.d, self.group = plan, lo, hi, n_total, d, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.spans = [shard_range(n_total, r, self.world) for r in range(self.world)]
         self.nmax = max(h - l for l, h in self.spans) if self.spans else 0
-        # packed record of one rank: nmax * d finals, nmax final times, 5 statistics (as reals: exact below 2^53 / 2^24)
-        self.rec = self.nmax * (d + 1) + 5
-        self.send = torch.zeros(self.rec, dtype=dtype, device=device)
-        self.recv = torch.empty(self.world * self.rec, dtype=dtype, device=device) if self.world > 1 else self.send
+        es = torch.empty((), dtype=dtype).element_size()
         n = hi - lo
-        self.y_buf = self.send[: n * d].view(n, d)                       # the kernel writes the finals straight into the record
-        self.t_buf = self.send[self.nmax * d: self.nmax * d + n]
-        self.stat_buf = self.send[self.nmax * (d + 1):]
-        # host-buffer inputs: device copies of this rank's statistics / result codes, so the reduction needs no second H2D
-        self.stats_dev = torch.empty((n, 3), dtype=torch.int32, device=device) if device.type == "cuda" else None
-        self.result_dev = torch.empty((n,), dtype=torch.int32, device=device) if device.type == "cuda" else None
+        self._off_t = self.nmax * d * es
+        self._off_tot = (self.nmax * (d + 1) * es + 7) // 8 * 8
+        self.rec = self._off_tot + 4 * 8                         # bytes of one rank's record
+        self.dtype, self._es = dtype, es
+        self.send = torch.zeros(self.rec, dtype=torch.uint8, device=device)
+        self.recv = torch.empty(self.world * self.rec, dtype=torch.uint8, device=device) if self.world > 1 else self.send
+        self.y_buf = self.send[: n * d * es].view(dtype).view(n, d)        # the kernel writes the finals straight into the record
+        self.t_buf = self.send[self._off_t: self._off_t + n * es].view(dtype)
+        self.totals = self.send[self._off_tot:].view(torch.int64)          # [sum steps, sum accepted, failed, max steps]
 
     def __call__(self, throw: bool = True) -> ShardedSolution:
         return self.gather(self.solve_local(throw=throw))
 
     def solve_local(self, throw: bool = True):
-        """This rank's block: one C-ABI call; the finals land in the packed record."""
+        """This rank's block: one C-ABI call; the finals and the totals land in the packed record."""
         return self.plan(throw=throw)
 
     def gather(self, sol) -> ShardedSolution:
-        """The one collective of the path: all_gather of every rank's [finals | t_final | statistics] record."""
-        st = sol.stats
-        dev = self.send.device
-        dt = torch.float64                                            # statistics are summed in fp64 whatever the state dtype
-        def _dev(x):
-            return x if isinstance(x, torch.Tensor) and x.is_cuda else torch.as_tensor(x).to(dev, non_blocking=True)
-        if isinstance(sol.result, torch.Tensor) and sol.result.is_cuda:          # device path
-            stats3 = torch.stack([st[k] for k in ("num_steps", "num_accepted_steps", "num_rejected_steps")], 1)
-            res = sol.result
-        elif self.stats_dev is not None and getattr(self, "host_outputs_on_device", False):   # host path: the call filled these
-            stats3, res = self.stats_dev, self.result_dev
-        else:
-            stats3 = torch.stack([_dev(st[k]) for k in ("num_steps", "num_accepted_steps", "num_rejected_steps")], 1)
-            res = _dev(sol.result)
-        s3 = stats3.to(dt)
-        failed = (res != 0).to(dt).sum().reshape(1)
-        mx = s3[:, 0].max().reshape(1) if s3.shape[0] else torch.zeros(1, dtype=dt, device=dev)
-        vec = torch.cat([s3.sum(0), failed, mx])
-        if self.send.dtype == torch.float64:
-            self.stat_buf.copy_(vec)
+        """The one collective of the path: all_gather of every rank's [finals | t_final | totals] record."""
+        d, es = self.d, self._es
         if self.world > 1:
-            if self.send.dtype != torch.float64:                      # fp32 states: the counters travel in their own fp64 record
-                allv = [torch.empty_like(vec) for _ in range(self.world)]
-                dist.all_gather(allv, vec, group=self.group)
-                allv = torch.stack(allv)
             dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
             rec = self.recv.view(self.world, self.rec)
-            if self.send.dtype == torch.float64:
-                allv = rec[:, self.nmax * (self.d + 1):]
-            y = torch.cat([rec[r, : (h - l) * self.d].view(h - l, self.d) for r, (l, h) in enumerate(self.spans)], 0)
-            t = torch.cat([rec[r, self.nmax * self.d: self.nmax * self.d + (h - l)] for r, (l, h) in enumerate(self.spans)], 0)
+            y = torch.cat([rec[r, : (h - l) * d * es].view(self.dtype).view(h - l, d) for r, (l, h) in enumerate(self.spans)], 0)
+            t = torch.cat([rec[r, self._off_t: self._off_t + (h - l) * es].view(self.dtype) for r, (l, h) in enumerate(self.spans)], 0)
+            tot = rec[:, self._off_tot:].view(torch.int64)               # [world, 4]
         else:
-            allv = vec[None]
-            y, t = self.y_buf, self.t_buf
-        tot = allv[:, :4].sum(0)
-        stats = {"num_steps": tot[0], "num_accepted_steps": tot[1], "num_rejected_steps": tot[2], "num_failed": tot[3],
-                 "max_steps_per_trajectory": allv[:, 4].max()}                # 0-d device tensors: no host sync here
+            y, t, tot = self.y_buf, self.t_buf, self.totals[None]
+        sums = tot[:, :3].sum(0)
+        stats = {"num_steps": sums[0], "num_accepted_steps": sums[1], "num_rejected_steps": sums[0] - sums[1], "num_failed": sums[2],
+                 "max_steps_per_trajectory": tot[:, 3].max()}               # 0-d device tensors: no host sync here
         return ShardedSolution(sol, self.lo, self.hi, self.n_total, y, t, stats)
 
 
@@ -204,10 +181,8 @@ def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, de
     sh = ShardedSolve.__new__(ShardedSolve)
     # two-phase construction: the record buffers must exist before `prepare` binds them as final_out
     ShardedSolve.__init__(sh, None, lo, hi, n_total, d, dtype, device, group)
-    sh.host_outputs_on_device = not is_dev
-    fo = (sh.y_buf, sh.t_buf) if is_dev else (sh.y_buf, sh.t_buf, sh.stats_dev, sh.result_dev)
     sh.plan = _api.prepare(_slice_terms(terms, lo, hi), solver, _slice_rows(t0, lo, hi), _slice_rows(t1, lo, hi), dt0, y_loc, args,
-                           device=device.index if device.index is not None else 0, final_out=fo, **kw)
+                           device=device.index if device.index is not None else 0, final_out=(sh.y_buf, sh.t_buf, sh.totals), **kw)
     return sh
 
 

@@ -59,7 +59,7 @@ class SolveDesc(C.Structure):
         ("event_rtol", C.c_double), ("event_atol", C.c_double),
         ("state_in", C.c_void_p), ("state_in_flags", C.c_int32), ("state_out", C.c_void_p),
         ("y_final_device", C.c_void_p), ("t_final_device", C.c_void_p),
-        ("stats_device", C.c_void_p), ("result_device", C.c_void_p),
+        ("totals", C.c_void_p), ("totals_device", C.c_void_p),
     ]
 
 

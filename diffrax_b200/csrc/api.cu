@@ -402,7 +402,8 @@ int dfx_ensemble_solve(const dfx_solve_desc *d, void *cuda_stream) {
 // Host-buffer variant.  The batch is cut into chunks that are pipelined over two streams (H2D of chunk i+1 and D2H of
 // chunk i-1 overlap the kernel of chunk i); trajectories are independent, so chunking does not change any result.
 // Pass pinned host pointers for full PCIe speed.  Dense output is not chunked (its buffers are large; one chunk).
-static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cudaStream_t st, std::vector<void *> &allocs) {
+static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cudaStream_t st, std::vector<void *> &allocs,
+                            int64_t *chunk_totals /* host [4] or null */) {
   const size_t es = h->dtype == DFX_F64 ? 8 : 4;
   const size_t N = (size_t)cnt, D = (size_t)h->dim;
   const int T = dfx_out_size(h);
@@ -441,11 +442,10 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
   d.field_weights = dev_in(h->field_weights, (size_t)h->n_field_weights * es);
   d.ts_out = dev_out(off(h->ts_out, T * es), N * T * es);
   d.ys_out = dev_out(off(h->ys_out, T * D * es), N * T * D * es);
-  if (h->stats_device) { d.stats = h->stats_device + (size_t)lo * 3; d2h.emplace_back((char *)h->stats + (size_t)lo * 12, d.stats, N * 12); }
-  else d.stats = (int32_t *)dev_out(off(h->stats, 12), N * 3 * 4);
-  if (h->result_device) { d.result = h->result_device + (size_t)lo; d2h.emplace_back((char *)h->result + (size_t)lo * 4, d.result, N * 4); }
-  else d.result = (int32_t *)dev_out(off(h->result, 4), N * 4);
-  d.stats_device = d.result_device = nullptr;
+  d.stats = (int32_t *)dev_out(off(h->stats, 12), N * 3 * 4);
+  d.result = (int32_t *)dev_out(off(h->result, 4), N * 4);
+  d.totals = (int64_t *)dev_out(chunk_totals, chunk_totals ? 4 * sizeof(int64_t) : 0);  // per chunk; combined by the caller
+  d.totals_device = nullptr;
   d.save_count = (int32_t *)dev_out(off(h->save_count, 4), N * 4);
   if (h->save_dense) {
     d.dense_ts = dev_out(off(h->dense_ts, (ms + 1) * es), N * (ms + 1) * es);
@@ -597,11 +597,11 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
     d.bm_keys = (const uint32_t *)per_traj_in(h->bm_keys, 8);
     d.ts_out = per_traj_out(h->ts_out, T * es);
     d.ys_out = per_traj_out(h->ys_out, T * D * es);
-    if (h->stats_device) { d.stats = h->stats_device; outs.push_back({(const char *)h->stats, (char *)h->stats_device, 12}); }
-    else d.stats = (int32_t *)per_traj_out(h->stats, 12);
-    if (h->result_device) { d.result = h->result_device; outs.push_back({(const char *)h->result, (char *)h->result_device, 4}); }
-    else d.result = (int32_t *)per_traj_out(h->result, 4);
-    d.stats_device = d.result_device = nullptr;
+    d.stats = (int32_t *)per_traj_out(h->stats, 12);
+    d.result = (int32_t *)per_traj_out(h->result, 4);
+    // totals: ONE launch, so the kernel accumulates straight into the caller's device words (or scratch for a host copy)
+    d.totals = h->totals_device ? h->totals_device : (h->totals ? (int64_t *)dev_alloc(4 * sizeof(int64_t)) : nullptr);
+    d.totals_device = nullptr;
     d.save_count = (int32_t *)per_traj_out(h->save_count, 4);
     // finals: the caller's device buffers when given (the host copies, if any, are taken from there chunk by chunk)
     if (h->y_final_device) { d.y_final = h->y_final_device; if (h->y_final) outs.push_back({(const char *)h->y_final, (char *)h->y_final_device, D * es}); }
@@ -683,6 +683,8 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
     }
   }
   if (rc) release_kernel();  // never leave the kernel waiting for inputs
+  if (launched && !rc && h->totals && d.totals)  // stream-ordered after the kernel
+    PIPE_OK(cudaMemcpyAsync(h->totals, d.totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s_k));
   if (trace && s_k) { cudaStreamSynchronize(s_k); t_k = now_ms(); }
   for (cudaStream_t st : {s_in, s_k, s_out})
     if (st) { const cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) fail("stream sync", e); }
@@ -717,17 +719,31 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
   const int nstreams = nchunks > 1 ? 2 : 1;
   for (int i = 0; i < nstreams; ++i) DFX_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
   std::vector<void *> allocs[2];
+  const bool want_totals = h->totals || h->totals_device;
+  std::vector<int64_t> chunk_totals(want_totals ? 4 * (size_t)nchunks : 0, 0);
   int rc = 0;
   for (int64_t c = 0; c < nchunks && !rc; ++c) {
     const int64_t lo = h->n_traj * c / nchunks, hi = h->n_traj * (c + 1) / nchunks;
-    rc = solve_host_chunk(h, lo, hi - lo, st[c % nstreams], allocs[c % nstreams]);
+    rc = solve_host_chunk(h, lo, hi - lo, st[c % nstreams], allocs[c % nstreams], want_totals ? &chunk_totals[4 * (size_t)c] : nullptr);
   }
   for (int i = 0; i < nstreams; ++i) {
     for (void *p : allocs[i]) cudaFreeAsync(p, st[i]);
     cudaError_t e = cudaStreamSynchronize(st[i]);
     if (!rc && e != cudaSuccess) { set_error("stream sync failed: %s", cudaGetErrorString(e)); rc = DFX_ERR_CUDA; }
-    cudaStreamDestroy(st[i]);
   }
+  if (want_totals && !rc) {  // combine the chunks' totals: sums, and the max of the per-trajectory maxima
+    int64_t tot[4] = {0, 0, 0, 0};
+    for (int64_t c = 0; c < nchunks; ++c) {
+      for (int k = 0; k < 3; ++k) tot[k] += chunk_totals[4 * (size_t)c + k];
+      tot[3] = std::max(tot[3], chunk_totals[4 * (size_t)c + 3]);
+    }
+    if (h->totals) std::memcpy(h->totals, tot, sizeof(tot));
+    if (h->totals_device) {
+      const cudaError_t e = cudaMemcpy(h->totals_device, tot, sizeof(tot), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { set_error("totals H2D failed: %s", cudaGetErrorString(e)); rc = DFX_ERR_CUDA; }
+    }
+  }
+  for (int i = 0; i < nstreams; ++i) cudaStreamDestroy(st[i]);
   return rc;
 }
 

@@ -109,6 +109,7 @@ struct SolveParams {
   int dense_coop;    // SaveAt(dense): stage records through shared memory and store them warp-cooperatively (launcher provides the smem)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
   R *y_final, *t_final;
+  long long *totals;  // [4] or null: sums of attempted / accepted steps, failed trajectories, max steps of one trajectory (zeroed by the launcher)
   unsigned long long *work_counter;
   // Host-pipelined mode (dfx_ensemble_solve_host; SaveAt(t1=True) instantiation only): ONE launch over the whole batch
   // while the copy engines bring the inputs in and take the results out in chunks of pipe_chunk_len trajectories.
@@ -304,6 +305,10 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   [[maybe_unused]] R *dense_smem = reinterpret_cast<R *>(dense_smem_raw + p.dense_smem_offset);
   if constexpr (SDE) bm.attach_cache(reinterpret_cast<R *>(dense_smem_raw), p.vbt);
 
+  __shared__ long long warp_totals[kBlockThreads / 32][4];  // attempted, accepted, failed, max steps (see p.totals)
+  if ((threadIdx.x & 31) == 0) { long long *w_ = warp_totals[threadIdx.x >> 5]; w_[0] = w_[1] = w_[2] = w_[3] = 0; }
+  __syncwarp();
+
   for (;;) {
     // Finalising a trajectory and claiming + initialising the next one is ~300 instructions that the whole warp
     // issues for however few lanes need them; lanes finish at unrelated iterations, so doing it per lane costs about
@@ -389,6 +394,18 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           }
         }
         active = false;
+      }
+      if (p.totals != nullptr && waiting != 0u) {
+        // ensemble totals for the multi-GPU statistics reduction: one warp reduction per finalise
+        // pass into this warp's shared-memory slot; flushed with four global atomics when the warp leaves the kernel
+        const bool fin = (waiting >> (threadIdx.x & 31)) & 1u;
+        const int a_ = __reduce_add_sync(kFullMask, fin ? num_steps : 0), b_ = __reduce_add_sync(kFullMask, fin ? num_accepted : 0);
+        const int c_ = __reduce_add_sync(kFullMask, (fin && result != DFX_RESULT_SUCCESSFUL) ? 1 : 0);
+        const int m_ = __reduce_max_sync(kFullMask, fin ? num_steps : 0);
+        if ((threadIdx.x & 31) == 0) {
+          long long *w_ = warp_totals[threadIdx.x >> 5];
+          w_[0] += a_; w_[1] += b_; w_[2] += c_; w_[3] = w_[3] > m_ ? w_[3] : m_;
+        }
       }
       if constexpr (RICH) {
         // Unfilled output slots read +inf (_integrate.py:1296-1300, 1320-1322).  The tails are written here, by the whole
@@ -1050,6 +1067,13 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
       }
     }
 
+  }
+  if (p.totals != nullptr && (threadIdx.x & 31) == 0) {
+    const long long *w_ = warp_totals[threadIdx.x >> 5];
+    if (w_[0]) atomicAdd((unsigned long long *)p.totals + 0, (unsigned long long)w_[0]);
+    if (w_[1]) atomicAdd((unsigned long long *)p.totals + 1, (unsigned long long)w_[1]);
+    if (w_[2]) atomicAdd((unsigned long long *)p.totals + 2, (unsigned long long)w_[2]);
+    if (w_[3]) atomicMax(p.totals + 3, w_[3]);
   }
 }
 

@@ -81,6 +81,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   p.dense_count = d->dense_count;
   p.dense_vec_ok = (((uintptr_t)d->dense_y0 | (uintptr_t)d->dense_y1 | (uintptr_t)d->dense_k) & 31u) == 0;
   p.y_final = (R *)d->y_final; p.t_final = (R *)d->t_final;
+  p.totals = (long long *)d->totals;
   p.keys = d->bm_keys;
   p.reject_ts = nullptr; p.n_reject = d->store_rejected_steps > 0 ? d->store_rejected_steps : 0;
   p.state_in = (const R *)d->state_in; p.state_out = (R *)d->state_out; p.state_in_flags = d->state_in_flags;
@@ -227,6 +228,7 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   p.work_counter = counter;
   if (reject_bytes) p.reject_ts = (R *)(scratch + 16);
 
+  if (p.totals) DFX_CUDA_OK(cudaMemsetAsync(p.totals, 0, 4 * sizeof(long long), stream));
   int rc;
   if (extra) rc = launch_variant<R, Field, Solver, LEVY, true, true>(p, fp, stream);
   else if (rich) rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);

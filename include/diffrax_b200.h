@@ -171,8 +171,13 @@ typedef struct dfx_solve_desc {
    * where y_final / t_final are device pointers already. */
   void *y_final_device;
   void *t_final_device;
-  int32_t *stats_device;      /* [N, 3]: likewise for the step statistics ... */
-  int32_t *result_device;     /* [N]:    ... and the result codes (reduced on the device before the gather) */
+
+  /* Ensemble totals, reduced inside the solve kernel (the statistics half of the multi-GPU gather): [4] int64 =
+   * sum of num_steps, sum of num_accepted_steps, number of trajectories with result != successful, max num_steps of one
+   * trajectory.  `totals` lives where the other outputs live (device for dfx_ensemble_solve, host for *_host);
+   * `totals_device` is the optional device copy for the host call, like y_final_device.  NULL = not wanted. */
+  int64_t *totals;
+  int64_t *totals_device;
 } dfx_solve_desc;
 
 /* ---- library ---- */

@@ -149,9 +149,9 @@ steps = torch.arange(n_total, dtype=torch.int32) + 10
 sh = _dist.ShardedSolve(None, lo, hi, n_total, d, torch.float64, torch.device("cpu"), None)
 def plan(throw=True):              # stands in for the CUDA solve: writes this rank's finals into the packed record
     sh.y_buf.copy_(full_y[lo:hi]); sh.t_buf.copy_(full_t[lo:hi])
-    return types.SimpleNamespace(stats={{"num_steps": steps[lo:hi], "num_accepted_steps": steps[lo:hi] - 3,
-                                         "num_rejected_steps": torch.full((hi - lo,), 3, dtype=torch.int32)}},
-                                 result=(torch.arange(lo, hi) % 4 == 0).to(torch.int32))
+    res = (torch.arange(lo, hi) % 4 == 0)
+    sh.totals.copy_(torch.tensor([int(steps[lo:hi].sum()), int(steps[lo:hi].sum()) - 3 * (hi - lo), int(res.sum()), int(steps[lo:hi].max())]))
+    return types.SimpleNamespace(stats={{"num_steps": steps[lo:hi]}}, result=res.to(torch.int32))
 sh.plan = plan
 for _ in range(2):                 # the record is reused across calls
     out = sh()
