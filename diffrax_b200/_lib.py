@@ -67,7 +67,7 @@ class SolveDesc(C.Structure):
 EXPORTS = [
     "dfx_abi_version", "dfx_last_error", "dfx_device_count", "dfx_num_stages", "dfx_solver_order",
     "dfx_field_dim", "dfx_has_kernel", "dfx_out_size", "dfx_ensemble_solve", "dfx_ensemble_solve_host",
-    "dfx_vbt_evaluate", "dfx_threefry2x32", "dfx_random_split", "dfx_random_normal", "dfx_dense_evaluate", "dfx_dense_derivative",
+    "dfx_vbt_evaluate", "dfx_broadcast_device_scalar", "dfx_threefry2x32", "dfx_random_split", "dfx_random_normal", "dfx_dense_evaluate", "dfx_dense_derivative",
     "dfx_measure_fma_peak", "dfx_measure_int_peak", "dfx_launch_count", "dfx_reset_launch_count",
     "dfx_register_launcher",
 ]
@@ -101,6 +101,7 @@ def lib():
     L.dfx_ensemble_solve_host.argtypes = [C.POINTER(SolveDesc), C.c_int]
     L.dfx_vbt_evaluate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_double,
                                    C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.dfx_broadcast_device_scalar.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dfx_threefry2x32.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dfx_random_split.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.dfx_random_normal.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]

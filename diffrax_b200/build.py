@@ -74,11 +74,46 @@ def build(force=False, jobs=None, verbose=True):
     return LIB
 
 
+FFI_SRC = os.path.join(CSRC, "ffi", "xla_ffi_shim.cc")
+FFI_LIB = os.path.join(LIBDIR, "libdfx_xla_ffi.so")
+FFI_STUB = os.path.join(HERE, "..", "tests", "ffi_stub")
+
+
+def ffi_include_dir():
+    """(dir, kind): jaxlib's XLA FFI headers when jax is importable, else the compile-check stub under tests/ffi_stub."""
+    try:
+        import jax.ffi  # noqa: F401
+        return jax.ffi.include_dir(), "jaxlib"
+    except Exception:  # noqa: BLE001
+        return FFI_STUB, "stub"
+
+
+def build_ffi(out=None, verbose=True):
+    """Compile + link csrc/ffi/xla_ffi_shim.cc (the jax.ffi handlers) against libdiffrax_b200.so.
+    With jaxlib's headers the result is the loadable handler library; with the stub it is a compile / link check only."""
+    build(verbose=False)
+    inc, kind = ffi_include_dir()
+    out = out or FFI_LIB
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", inc, "-I", os.path.join(HERE, "..", "include"),
+           "-I", "/usr/local/cuda/include", FFI_SRC, "-L", LIBDIR, "-ldiffrax_b200", "-Wl,-rpath,$ORIGIN", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stderr[-6000:])
+        raise RuntimeError("building the jax.ffi shim failed")
+    if verbose:
+        print(f"[build] {out} (XLA FFI headers: {kind})", flush=True)
+    return out, kind
+
+
 if __name__ == "__main__":
     import argparse
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("-j", type=int, default=None)
+    ap.add_argument("--ffi", action="store_true", help="also build the jax.ffi handler library (lib/libdfx_xla_ffi.so)")
     a = ap.parse_args()
     build(a.force, a.j)
+    if a.ffi:
+        build_ffi()

@@ -99,6 +99,12 @@ __global__ void split_kernel(long long n, const uint32_t *keys, int num, int par
   }
 }
 
+// dst[0..n) = *src (a device-resident scalar; the jax.ffi shim's unbatched traced t0 / t1)
+template <class R> __global__ void broadcast_kernel(long long n, const R *src, R *dst) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = *src;
+}
+
 // jax.random.normal(key, shape, dtype) for n keys; shape () (m == 0) or (m,)
 template <class R, int M>
 __global__ void normal_kernel(long long n, const uint32_t *keys, int partitionable, R *out) {
@@ -745,6 +751,17 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
   }
   for (int i = 0; i < nstreams; ++i) cudaStreamDestroy(st[i]);
   return rc;
+}
+
+int dfx_broadcast_device_scalar(int dtype, int64_t n, const void *src_device, void *dst_device, void *stream) {
+  if (n <= 0) return 0;
+  if (!src_device || !dst_device) { set_error("broadcast: null pointer"); return DFX_ERR_BAD_ARGUMENT; }
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == DFX_F64) broadcast_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const double *)src_device, (double *)dst_device);
+  else broadcast_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, (const float *)src_device, (float *)dst_device);
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int dfx_threefry2x32(int64_t n, const uint32_t *keys, const uint32_t *ctrs, uint32_t *out, void *stream) {

@@ -236,6 +236,10 @@ int dfx_dense_derivative(int dtype, int solver_id, int64_t n_traj, int dim, int 
                          const void *dense_k, const int32_t *dense_count, double direction,
                          const void *tq, int nq, void *out, void *cuda_stream);
 
+/* dst_device[0..n) = *src_device on `cuda_stream`: a device-resident scalar (an unbatched traced t0 / t1 reaching the
+ * jax.ffi handler) turned into the per-trajectory array the descriptor takes. */
+int dfx_broadcast_device_scalar(int dtype, int64_t n, const void *src_device, void *dst_device, void *cuda_stream);
+
 /* measured FMA-pipe peaks for the roofline denominators (dependent-free FMA chains);
  * returns TFLOP/s (2 flop per FMA) or a negative dfx_error. */
 double dfx_measure_fma_peak(int dtype, int device);

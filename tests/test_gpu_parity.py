@@ -882,7 +882,15 @@ def test_y_final_is_the_final_state_in_every_saveat_mode(dev):
     assert bool(torch.isfinite(s3.y_final).all()) and bool((s3.t_final < 5.0).all()) and bool((s3.result == 1).all())
     o = oracle.solve("lotka_volterra", y0, 0.0, 5.0, 0.1, solver="tsit5", params=[1.5, -1.0, -3.0, 1.0], rtol=1e-6, atol=1e-6,
                      save_ts=np.linspace(0.0, 5.0, 9), save_t1=True, max_steps=12)
-    assert relerr(to_np(s3.y_final), o["y_final"]) < RTOL64
+    # A solve cut short ends at a step boundary, not at a pinned time.  The embedded error estimate is a cancellation
+    # (|y_error| ~ 1e-7 |y| here), so last-ulp differences in the stage arithmetic move the step-size factor - and with it every
+    # later step time - by ~1e-10 relative between ANY two roundings of the reference's arithmetic (FMA contraction is enough).
+    # Both runs are on the same solution curve to 1e-10: compare after the first-order shift y'(t) (t_gpu - t_oracle).
+    yo, to_, yg, tg = o["y_final"], o["t_final"], to_np(s3.y_final), to_np(s3.t_final)
+    f = np.stack([1.5 * yo[:, 0] - yo[:, 0] * yo[:, 1], -3.0 * yo[:, 1] + yo[:, 0] * yo[:, 1]], 1)
+    assert np.abs(tg - to_).max() < 1e-8 * 5.0
+    assert relerr(yg - f * (tg - to_)[:, None], yo) < RTOL64
+    assert relerr(yg, yo) < 1e-8
     # the host path returns the same
     h = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 5.0, None, y0, saveat=dfx.SaveAt(steps=True, t1=True), stepsize_controller=ctrl, max_steps=256)
     assert np.array_equal(h.y_final, to_np(ref.ys[:, 0]))
