@@ -379,6 +379,10 @@ def measure(name, args, rank, local, world, dev, strong: bool, with_cpu: bool, s
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); plan(throw=False); e1.record(); torch.cuda.synchronize()
     est_ms = max(e0.elapsed_time(e1), 1e-3)
+    if world > 1:                               # every rank must run the SAME number of steps (each one is a collective)
+        em = torch.tensor([est_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(em, op=dist.ReduceOp.MAX)
+        est_ms = float(em[0])
     if est_ms * K < 400.0:                      # short workloads: run long enough for the 20 ms clock sampler to see them
         K = int(math.ceil(400.0 / est_ms))
     sampler = ClockSampler(local)

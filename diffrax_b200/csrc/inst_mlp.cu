@@ -31,6 +31,20 @@ int launch_mlp(const dfx_solve_desc *d, void *stream_v) {
     DFX_CUDA_OK(cudaMallocAsync((void **)&counter, 16, stream));
     DFX_CUDA_OK(cudaMemsetAsync(counter, 0, 16, stream));
     p.work_counter = counter;
+    // W2 -> TF32 hi / lo in the UMMA shared-memory image (global scratch), and the tensor map the CTAs stage it through (TMA)
+    float *w2_image = nullptr;
+    DFX_CUDA_OK(cudaMallocAsync((void **)&w2_image, 2 * sizeof(float) * kMlpW * kMlpW, stream));
+    const float *gW2 = (const float *)d->field_weights + kMlpW * kMlpD + kMlpW;
+    mlp_split_w2_kernel<<<(kMlpW * kMlpW + 255) / 256, 256, 0, stream>>>(gW2, w2_image);
+    count_launch();
+    CUtensorMap w2_map;
+    char tm_err[160];
+    if (make_w2_tensor_map(&w2_map, w2_image, tm_err, sizeof tm_err)) {
+      set_error("%s", tm_err);
+      cudaFreeAsync(w2_image, stream);
+      cudaFreeAsync(counter, stream);
+      return DFX_ERR_CUDA;
+    }
     const char *slow_act = std::getenv("DFX_MLP_EXACT_ACT");
     const bool fast = !(slow_act && slow_act[0] == '1');
     int sms = 0;
@@ -42,18 +56,19 @@ int launch_mlp(const dfx_solve_desc *d, void *stream_v) {
       DFX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       long long blocks = (p.n_traj + 127) / 128;
       if (blocks > sms) blocks = sms;  // persistent: one CTA (one 128-trajectory M tile) per SM
-      kern<<<(unsigned)blocks, kMlpThreads, smem, stream>>>(p, (const float *)d->field_weights);
+      kern<<<(unsigned)blocks, kMlpThreads, smem, stream>>>(p, (const float *)d->field_weights, w2_map);
     } else {
       auto kern = fast ? mlp_tc2_kernel<Solver, true> : mlp_tc2_kernel<Solver, false>;
       const int smem = (int)sizeof(MlpSmem2);
       DFX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       long long blocks = (p.n_traj + 255) / 256;
       if (blocks > sms) blocks = sms;  // persistent: one CTA (two 128-trajectory M tiles) per SM
-      kern<<<(unsigned)blocks, kMlp2Threads, smem, stream>>>(p, (const float *)d->field_weights);
+      kern<<<(unsigned)blocks, kMlp2Threads, smem, stream>>>(p, (const float *)d->field_weights, w2_map);
     }
     count_launch();
     DFX_CUDA_OK(cudaGetLastError());
     cudaFreeAsync(counter, stream);
+    cudaFreeAsync(w2_image, stream);
   }
   return 0;
 }

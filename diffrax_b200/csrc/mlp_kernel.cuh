@@ -25,6 +25,8 @@
 //   * every stage, including stage 0, is evaluated each step (the FSAL value f(t1, y1) equals f at the next step's
 //     (t0, y0) bit for bit, so re-evaluating it is value-identical to diffrax's reuse; runge_kutta.py:684-695).
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
+
 #include "ensemble_kernel.cuh"
 
 namespace dfx {
@@ -47,6 +49,7 @@ struct MlpSmem {
   float k[14 * kMlpD][kMlpW];   // stage values k[i][c] per row (the 4 threads of a row write identical values), S <= 14
   long long idx[kMlpW];
   unsigned long long mbar;
+  unsigned long long mbar_w;    // completion of the TMA loads of the W2 image
   uint32_t tmem_base;
 };
 
@@ -67,6 +70,63 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr, uint32_t lbo_byt
   d |= (uint64_t)1 << 46;  // version_
   return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
+// Host: tensor map over the W2 image ([1024 rows][32 floats], row-major, 128-byte rows), box = 256 rows x 32 floats.
+// cuTensorMapEncodeTiled is a driver entry point; it is fetched through the runtime so the library links against cudart only.
+inline int make_w2_tensor_map(CUtensorMap *out, const float *image_dev, char *err, size_t err_len) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      snprintf(err, err_len, "cuTensorMapEncodeTiled is not available from this driver (the MLP kernel stages W2 with TMA)");
+      return -1;
+    }
+    encode = (encode_fn)fn;
+  }
+  const cuuint64_t dims[2] = {32, 2 * kMlpW * kMlpW * 4 / 128};  // innermost first: 32 floats per row, 1024 rows
+  const cuuint64_t strides[1] = {128};                            // bytes between rows
+  const cuuint32_t box[2] = {32, 256}, estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)image_dev, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(err, err_len, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -1; }
+  return 0;
+}
+
+// ---- TMA staging of W2 ----
+// The 128x128 hidden-layer weights are split into TF32 hi / lo ONCE per launch by a small kernel that writes them to global
+// memory already in the shared-memory image the tensor core wants (canonical K-major no-swizzle UMMA layout: 8x4-element
+// core matrices of 128 B, LBO 128 B along K, SBO 4096 B along N) - 2 x 64 KB = 1024 rows of 128 B.  Every CTA of the solve
+// kernel then stages that image with four cp.async.bulk.tensor (TMA) tile loads of 256 rows each, completion on an
+// mbarrier, instead of 32 K per-thread __ldg + st.shared: the copy engine moves the bytes while the threads stage the small
+// layers and allocate TMEM.
+constexpr int kW2ImageRows = 2 * kMlpW * kMlpW * 4 / 128;  // hi + lo: 1024 rows of 128 bytes
+constexpr int kW2BoxRows = 256;                            // one TMA box: 256 rows x 32 floats = 32 KB
+__global__ void mlp_split_w2_kernel(const float *__restrict__ gW2, float *__restrict__ image) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kMlpW * kMlpW) return;
+  const int n = i >> 7, k = i & 127;  // W2[n][k], (out, in) row-major == K-major B operand
+  const float v = __ldg(gW2 + i), hi = to_tf32(v), lo = to_tf32(v - hi);
+  const int off = (n >> 3) * 1024 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
+  image[off] = hi;
+  image[kMlpW * kMlpW + off] = lo;
+}
+// one 2-D tile load: box (32 floats, kW2BoxRows rows) at row `row0` of the image -> shared memory, completes on `mbar`
+__device__ __forceinline__ void tma_load_rows(uint32_t smem_dst, const CUtensorMap *tmap, int row0, uint32_t mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(smem_dst), "l"((unsigned long long)tmap), "r"(0), "r"(row0), "r"(mbar) : "memory");
+}
+// called by ONE thread after the mbarrier is initialised: arm it with the byte count and issue the four tile loads
+__device__ __forceinline__ void tma_stage_w2(float *smem_image, const CUtensorMap *tmap, uint32_t mbar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(kW2ImageRows * 128) : "memory");
+#pragma unroll
+  for (int r = 0; r < kW2ImageRows; r += kW2BoxRows) tma_load_rows(smem_u32(smem_image) + r * 128, tmap, r, mbar);
+}
+
 // UMMA instruction descriptor (InstrDescriptor): D fp32, A/B TF32, both K-major, N=128, M=128.
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -149,7 +209,7 @@ template <bool FAST> __device__ __forceinline__ void tf32_split(float x, uint32_
 
 template <class Solver, bool FAST_ACT>
 __global__ void __launch_bounds__(kMlpThreads, 1)
-mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
+mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w, const __grid_constant__ CUtensorMap w2_map) {
   using R = float;
   constexpr int D = kMlpD, W = kMlpW, S = Solver::S;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -162,13 +222,13 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
 
   // ---------------- one-time set-up: weights -> smem (W2 split into TF32 hi / lo), TMEM, mbarrier ----------------
   const float *gW1 = w, *gb1 = gW1 + W * D, *gW2 = gb1 + W, *gb2 = gW2 + W * W, *gW3 = gb2 + W, *gb3 = gW3 + D * W;
-  for (int i = tid; i < W * W; i += kMlpThreads) {
-    const int n = i >> 7, k = i & 127;  // W2[n][k], (out, in) row-major == K-major B operand
-    const float v = __ldg(gW2 + i), hi = to_tf32(v), lo = to_tf32(v - hi);
-    const int off = (n >> 3) * 1024 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
-    sm.Bhi[off] = hi;
-    sm.Blo[off] = lo;
+  // W2 (TF32 hi / lo, already in the UMMA shared-memory layout): TMA tile loads, issued first so they overlap the rest
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.mbar_w)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_stage_w2(sm.Bhi, &w2_map, smem_u32(&sm.mbar_w));
   }
+  (void)gW2;
   constexpr float kIn = FAST_ACT ? 1.4426950408889634f : 1.0f;   // log2(e) into the pre-activations
   constexpr float kOut = FAST_ACT ? 0.6931471805599453f : 1.0f;  // ln2 back out of the last hidden layer
   for (int i = tid; i < W * D; i += kMlpThreads) {
@@ -190,6 +250,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  mbar_wait(smem_u32(&sm.mbar_w), 0);  // the W2 image has landed (TMA complete_tx)
   const uint32_t tmem = sm.tmem_base;
   const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's lane quadrant
   const uint32_t mbar = smem_u32(&sm.mbar);

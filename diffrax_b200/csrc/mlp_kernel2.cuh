@@ -36,6 +36,7 @@ struct MlpSmem2 {
   long long idx[kMlp2Groups][kMlpW];
   unsigned long long mbar_done[kMlp2Groups];
   unsigned long long mbar_empty[kMlp2Groups][kMlp2Slots];
+  unsigned long long mbar_w;    // completion of the TMA loads of the W2 image
   uint32_t tmem_base;
 };
 
@@ -55,7 +56,7 @@ __device__ __forceinline__ bool group_and(int id, int count, bool v) {
 
 template <class Solver, bool FAST_ACT>
 __global__ void __launch_bounds__(kMlp2Threads, 1)
-mlp_tc2_kernel(const SolveParams<float> p, const float *__restrict__ w) {
+mlp_tc2_kernel(const SolveParams<float> p, const float *__restrict__ w, const __grid_constant__ CUtensorMap w2_map) {
   using R = float;
   constexpr int D = kMlpD, W = kMlpW, S = Solver::S;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -72,13 +73,14 @@ mlp_tc2_kernel(const SolveParams<float> p, const float *__restrict__ w) {
 
   // ---------------- one-time set-up: weights -> smem (W2 split into TF32 hi / lo), TMEM, mbarriers ----------------
   const float *gW1 = w, *gb1 = gW1 + W * D, *gW2 = gb1 + W, *gb2 = gW2 + W * W, *gW3 = gb2 + W, *gb3 = gW3 + D * W;
-  for (int i = tid; i < W * W; i += kMlp2Threads) {
-    const int n = i >> 7, k = i & 127;  // W2[n][k], (out, in) row-major == K-major B operand
-    const float v = __ldg(gW2 + i), hi = to_tf32(v), lo = to_tf32(v - hi);
-    const int off = (n >> 3) * 1024 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
-    sm.Bhi[off] = hi;
-    sm.Blo[off] = lo;
+  // W2 (TF32 hi / lo, already in the UMMA shared-memory layout, mlp_split_w2_kernel): TMA tile loads with mbarrier
+  // completion, issued first so the copy engine works while the threads stage the small layers and allocate TMEM
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.mbar_w)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_stage_w2(sm.Bhi, &w2_map, smem_u32(&sm.mbar_w));
   }
+  (void)gW2;
   constexpr float kIn = FAST_ACT ? 1.4426950408889634f : 1.0f;   // log2(e) into the pre-activations
   constexpr float kOut = FAST_ACT ? 0.6931471805599453f : 1.0f;  // ln2 back out of the last hidden layer
   for (int i = tid; i < W * D; i += kMlp2Threads) {
@@ -104,6 +106,7 @@ mlp_tc2_kernel(const SolveParams<float> p, const float *__restrict__ w) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  mbar_wait(smem_u32(&sm.mbar_w), 0);  // the W2 image has landed (TMA complete_tx)
   const uint32_t tmem_all = sm.tmem_base;
   const uint32_t tmem = tmem_all + (uint32_t)(g * 256);          // this tile: D [0,128), A ring [128,256)
   const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's lane quadrant

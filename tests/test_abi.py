@@ -76,3 +76,29 @@ def test_sass_is_sm100a(cuda_lib):
     # the per-step path keeps everything in registers; ptxas may park one refill-only flag (2 bytes, touched once per
     # finalize/refill pass, i.e. once per ~200 steps) in local memory
     assert m and int(m.group(1)) <= 8 and int(m.group(2)) <= 8, m.groups()
+
+
+def test_sass_opcodes_of_the_shipped_kernels(cuda_lib):
+    """Opcode-level evidence in the SHIPPED library (cuobjdump -sass of libdiffrax_b200.so, not a build log):
+    the ODE hot kernel is FP64-FMA code without local-memory traffic in its step loop, the MLP kernel is
+    tcgen05 (UTC*MMA) with TMEM loads/stores and TMA staging (UTMALDG), the SDE kernels are integer threefry code."""
+    import subprocess
+    lib = os.path.join(ROOT, "diffrax_b200", "lib", "libdiffrax_b200.so")
+
+    def sass(fun_regex):
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", fun_regex, lib], capture_output=True, text=True).stdout
+        return [m.group(1) for m in re.finditer(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", out, re.M)]
+
+    names = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
+    def first(pattern):
+        m = re.search(pattern, names)
+        assert m, pattern
+        return m.group(0)
+    c2 = sass(first(r"_ZN3dfx15ensemble_kernelIdNS_11LorenzFieldENS_6Dopri5ELi0ELb0ELb0EEEv\w+"))
+    assert c2.count("DFMA") > 150 and c2.count("DMUL") > 40
+    assert c2.count("LDL") + c2.count("STL") <= 4          # registers, not local memory (a refill-only flag at most)
+    mlp = sass(first(r"_ZN3dfx14mlp_tc2_kernelINS_5Tsit5ELb1EEEv\w+"))
+    assert "UTCHMMA" in mlp and "LDTM" in mlp and "STTM" in mlp and any(o.startswith("UTMALDG") for o in mlp)
+    assert not any(o.startswith("HMMA") for o in mlp)      # no legacy mma.sync path
+    ou = sass(first(r"_ZN3dfx15ensemble_kernelIfNS_7OuFieldENS_4HeunELi1ELb0ELb0EEEv\w+"))
+    assert ou.count("SHF") + ou.count("LOP3") > 200         # threefry rotates / xors dominate

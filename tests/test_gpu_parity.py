@@ -371,12 +371,14 @@ def test_mlp_tensor_core_kernel_matches_cuda_core_functor_and_oracle(dev, monkey
 
 
 def test_tensor_core_sass_present():
-    """The MLP kernel really is tcgen05: UTC*MMA + TMEM load/store opcodes in the shipped cubin."""
+    """The MLP kernel really is tcgen05 with TMA staging: UTC*MMA + TMEM load/store + UTMALDG (cp.async.bulk.tensor) opcodes
+    in the shipped cubin."""
     import subprocess
     root = os.path.dirname(HERE)
     out = subprocess.run(["cuobjdump", "-sass", os.path.join(root, "diffrax_b200", "csrc", "_obj", "inst_mlp.o")],
                          capture_output=True, text=True).stdout
     assert "UTCHMMA" in out and "LDTM" in out and "STTM" in out
+    assert "UTMALDG" in out, "W2 must be staged with cp.async.bulk.tensor (TMA)"
 
 
 @pytest.mark.parametrize("solver", ["tsit5", "dopri5", "heun", "bosh3"])
