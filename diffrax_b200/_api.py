@@ -575,15 +575,44 @@ class _TorchBackend(_Backend):
 class DenseInterpolation:
     """_global_interpolation.py:315-397, batched over trajectories."""
 
-    def __init__(self, solver, ts, ts_size, infos, direction, t0_if_trivial, y0_if_trivial, backend):
+    def __init__(self, solver, ts, ts_size, infos, direction, t0_if_trivial, y0_if_trivial, backend, lazy_padding=False):
         self.solver = solver
-        self.ts = ts                    # [N, max_steps+1] normalised time
+        self._ts = ts                   # [N, max_steps+1] normalised time
         self._count = ts_size           # [N] int32 accepted steps (ts_size - 1), filled by the solve
-        self.infos = infos              # dict(y0, y1, k)
+        self._infos = infos             # dict(y0, y1, k)
         self.direction = direction      # [N] or scalar +-1
         self.t0_if_trivial = t0_if_trivial
         self.y0_if_trivial = y0_if_trivial
         self._xp = backend
+        # dense_lazy_padding: the solve left the unfilled tails unwritten (63 % of the bytes at BASELINE config 3);
+        # evaluate / derivative never read them, and the raw `ts` / `infos` arrays are completed with +inf on first access
+        self._lazy = bool(lazy_padding)
+        self._needs_padding = self._lazy
+
+    def _mark_solved(self):
+        """Called after every launch of the prepared solve that owns these buffers."""
+        self._needs_padding = self._lazy
+
+    def _materialize(self):
+        if self._needs_padding:
+            xp = self._xp
+            n, msp1 = self._ts.shape
+            _lib.check(_lib.lib().dfx_dense_pad(xp.dtype_id(self._ts.dtype), self.solver.solver_id, n, self._infos["y0"].shape[-1],
+                                                msp1 - 1, xp.ptr(self._ts), xp.ptr(self._infos["y0"]), xp.ptr(self._infos["y1"]),
+                                                xp.ptr(self._infos.get("k")), xp.ptr(self._count), xp.stream()))
+            self._needs_padding = False
+
+    @property
+    def ts(self):
+        """[N, max_steps + 1] knots, +inf beyond each trajectory's last one (the reference's padded buffer)."""
+        self._materialize()
+        return self._ts
+
+    @property
+    def infos(self):
+        """dict(y0, y1, k) of [N, max_steps, ...] dense_infos, +inf in unfilled slots."""
+        self._materialize()
+        return self._infos
 
     @property
     def ts_size(self):
@@ -611,9 +640,10 @@ class DenseInterpolation:
         xp = self._xp
         if not xp.device_ptrs:
             raise RuntimeError("DenseInterpolation needs the dense buffers on a CUDA device")
-        n, msp1 = self.ts.shape
-        d = self.infos["y0"].shape[-1]
-        tq = torch.as_tensor(t, dtype=self.ts.dtype, device=self.ts.device)
+        ts_, infos_ = self._ts, self._infos       # raw buffers: the kernels only read the filled prefix
+        n, msp1 = ts_.shape
+        d = infos_["y0"].shape[-1]
+        tq = torch.as_tensor(t, dtype=ts_.dtype, device=ts_.device)
         squeeze = tq.ndim == 0
         if tq.ndim == 0:
             tq = tq.expand(n, 1)
@@ -621,10 +651,10 @@ class DenseInterpolation:
             tq = tq.unsqueeze(0).expand(n, tq.shape[0])
         tq = tq.contiguous()
         nq = tq.shape[1]
-        out = xp.empty((n, nq, d), self.ts.dtype)
+        out = xp.empty((n, nq, d), ts_.dtype)
         _lib.check(getattr(_lib.lib(), entry)(
-            xp.dtype_id(self.ts.dtype), self.solver.solver_id, n, d, msp1 - 1, xp.ptr(self.ts),
-            xp.ptr(self.infos["y0"]), xp.ptr(self.infos["y1"]), xp.ptr(self.infos.get("k")), xp.ptr(self._count),
+            xp.dtype_id(ts_.dtype), self.solver.solver_id, n, d, msp1 - 1, xp.ptr(ts_),
+            xp.ptr(infos_["y0"]), xp.ptr(infos_["y1"]), xp.ptr(infos_.get("k")), xp.ptr(self._count),
             float(self.direction), xp.ptr(tq), nq, xp.ptr(out), xp.stream()))
         return out, tq, squeeze
 
@@ -667,6 +697,8 @@ class EnsembleSolve:
         else:
             _lib.check(L.dfx_ensemble_solve_host(C.byref(self.desc), int(self._host_device)))
         sol = self._solution
+        if isinstance(sol.interpolation, DenseInterpolation):
+            sol.interpolation._mark_solved()
         if throw:
             bad = ~is_okay(sol.result)  # an event is not an error (_integrate.py:1541-1542 with is_okay)
             if bool(bad.any()):
@@ -706,7 +738,7 @@ class _MultiSolve:
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
                 stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096, throw: bool = True,
                 solver_state=None, controller_state=None, made_jump=None,
-                device: int = 0, hairer_initial_step: bool = False, final_out=None) -> Solution:
+                device: int = 0, hairer_initial_step: bool = False, final_out=None, dense_padding: str = "lazy") -> Solution:
     """Batched forward solve == ``jax.vmap(lambda y0: diffrax.diffeqsolve(...))(y0)``
     (_integrate.py:888-1543).
 
@@ -721,13 +753,13 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = N
     """
     return prepare(terms, solver, t0, t1, dt0, y0, args, saveat=saveat, stepsize_controller=stepsize_controller, event=event,
                    max_steps=max_steps, solver_state=solver_state, controller_state=controller_state, made_jump=made_jump,
-                   device=device, hairer_initial_step=hairer_initial_step, final_out=final_out)(throw=throw)
+                   device=device, hairer_initial_step=hairer_initial_step, final_out=final_out, dense_padding=dense_padding)(throw=throw)
 
 
 def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
             stepsize_controller=None, event: Optional[Event] = None, max_steps: Optional[int] = 4096,
             solver_state=None, controller_state=None, made_jump=None, device: int = 0,
-            hairer_initial_step: bool = False, final_out=None) -> EnsembleSolve:
+            hairer_initial_step: bool = False, final_out=None, dense_padding: str = "lazy") -> EnsembleSolve:
     """Validate the arguments of a `diffeqsolve` call and allocate its outputs once."""
     if args is not None:
         raise ValueError("args must be None: functor parameters are bound when the functor is created")
@@ -940,6 +972,11 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
             dense["k"] = xp.empty((n, max_steps, s, d), rdt)
         D.dense_ts, D.dense_y0, D.dense_y1 = xp.ptr(dense["ts"]), xp.ptr(dense["y0"]), xp.ptr(dense["y1"])
         D.dense_k, D.dense_count = xp.ptr(dense.get("k")), xp.ptr(dense["count"])
+        if dense_padding not in ("lazy", "eager"):
+            raise ValueError("dense_padding must be 'lazy' or 'eager'")
+        # device path: leave the +inf tails to DenseInterpolation (written on first access of the raw arrays);
+        # host buffers are copied back whole, so they are always padded by the solve
+        D.dense_lazy_padding = int(dense_padding == "lazy" and is_torch and xp.device_ptrs)
 
     stats_d = {"num_steps": stats[:, 0], "num_accepted_steps": stats[:, 1], "num_rejected_steps": stats[:, 2],
                "max_steps": max_steps}
@@ -952,7 +989,7 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         t0_norm = (t0arr if t0arr is not None else xp.as_real(t0s, n, rdt)) * dirn
         interpolation = DenseInterpolation(solver, dense["ts"], dense["count"],
                                            {k: v for k, v in dense.items() if k in ("y0", "y1", "k")},
-                                           dirn, t0_norm, y0a, xp)
+                                           dirn, t0_norm, y0a, xp, lazy_padding=bool(D.dense_lazy_padding))
     elif dense is not None:
         interpolation = dense  # raw buffers on the host path
     if y_final is None and T > 0:

@@ -60,6 +60,7 @@ class SolveDesc(C.Structure):
         ("state_in", C.c_void_p), ("state_in_flags", C.c_int32), ("state_out", C.c_void_p),
         ("y_final_device", C.c_void_p), ("t_final_device", C.c_void_p),
         ("totals", C.c_void_p), ("totals_device", C.c_void_p),
+        ("dense_lazy_padding", C.c_int32),
     ]
 
 
@@ -67,7 +68,7 @@ class SolveDesc(C.Structure):
 EXPORTS = [
     "dfx_abi_version", "dfx_last_error", "dfx_device_count", "dfx_num_stages", "dfx_solver_order",
     "dfx_field_dim", "dfx_has_kernel", "dfx_out_size", "dfx_ensemble_solve", "dfx_ensemble_solve_host",
-    "dfx_vbt_evaluate", "dfx_broadcast_device_scalar", "dfx_threefry2x32", "dfx_random_split", "dfx_random_normal", "dfx_dense_evaluate", "dfx_dense_derivative",
+    "dfx_vbt_evaluate", "dfx_broadcast_device_scalar", "dfx_threefry2x32", "dfx_random_split", "dfx_random_normal", "dfx_dense_evaluate", "dfx_dense_derivative", "dfx_dense_pad",
     "dfx_measure_fma_peak", "dfx_measure_int_peak", "dfx_launch_count", "dfx_reset_launch_count",
     "dfx_register_launcher",
 ]
@@ -109,6 +110,8 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]
     L.dfx_dense_derivative.argtypes = L.dfx_dense_evaluate.argtypes
+    L.dfx_dense_pad.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p]
     L.dfx_measure_fma_peak.argtypes = [C.c_int, C.c_int]
     L.dfx_measure_fma_peak.restype = C.c_double
     L.dfx_measure_int_peak.argtypes = [C.c_int]

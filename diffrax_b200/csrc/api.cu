@@ -154,8 +154,10 @@ __global__ void dense_eval_kernel(long long n_traj, int max_steps, const R *dts,
   R t = tq[gid] * direction;
   // _nan_if_out_of_bounds (370-381)
   if (ts_size <= 1 || t < ts[0] || t > ts[ts_size - 1]) t = Num<R>::nan();
-  // _interpret_t (36-45): searchsorted(ts, t, side="left") over the inf-padded array, then clip(index-1, 0, ts_size-2)
-  int lo = 0, hi = max_steps + 1;
+  // _interpret_t (36-45): searchsorted(ts, t, side="left") over the inf-padded array, then clip(index-1, 0, ts_size-2).
+  // Searching the filled prefix [0, ts_size) gives the same index (every padding slot is +inf > t) and does not read the
+  // tails, which are unwritten under dense_lazy_padding.
+  int lo = 0, hi = ts_size;
   if (t != t) lo = max_steps + 1;
   else while (lo < hi) { const int mid = (lo + hi) >> 1; if (ts[mid] < t) lo = mid + 1; else hi = mid; }
   int index = lo - 1;
@@ -178,6 +180,20 @@ __global__ void dense_eval_kernel(long long n_traj, int max_steps, const R *dts,
 #pragma unroll
     for (int c = 0; c < D; ++c) out[gid * D + c] = o[c];
   }
+}
+
+// +inf into the unfilled tails of the SaveAt(dense=True) buffers (_integrate.py:1296-1300, 1320-1322): one warp per
+// trajectory, coalesced streaming stores.  Used when a solve ran with dense_lazy_padding and somebody wants the raw arrays.
+template <class R>
+__global__ void dense_pad_kernel(long long n_traj, int max_steps, int d, int sd, R *dts, R *dy0, R *dy1, R *dk, const int *dcount) {
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_traj) return;
+  const long long dc = dcount[w], ms = max_steps;
+  pad_tail(dts + w * (ms + 1), dc + 1, ms + 1, lane, true);
+  pad_tail(dy0 + w * ms * d, dc * d, ms * d, lane, true);
+  pad_tail(dy1 + w * ms * d, dc * d, ms * d, lane, true);
+  if (dk) pad_tail(dk + w * ms * sd, dc * sd, ms * sd, lane, true);
 }
 
 // Pipe-peak microbenchmarks: 8 independent FMA chains per thread, enough warps to fill every SM.
@@ -837,6 +853,20 @@ int dfx_dense_derivative(int dtype, int solver_id, int64_t n_traj, int dim, int 
                          double direction, const void *tq, int nq, void *out, void *stream) {
   return dense_eval_entry(true, dtype, solver_id, n_traj, dim, max_steps, dense_ts, dense_y0, dense_y1, dense_k, dense_count,
                           direction, tq, nq, out, stream);
+}
+
+int dfx_dense_pad(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, void *dense_ts, void *dense_y0, void *dense_y1,
+                  void *dense_k, const int32_t *dense_count, void *stream) {
+  if (n_traj <= 0 || max_steps <= 0) return 0;
+  if (!dense_ts || !dense_y0 || !dense_y1 || !dense_count) { set_error("dense_pad: null buffer"); return DFX_ERR_BAD_ARGUMENT; }
+  const int s = dfx_num_stages(solver_id);
+  if (s < 0) { set_error("unknown solver %d", solver_id); return DFX_ERR_BAD_ARGUMENT; }
+  const unsigned blocks = (unsigned)((n_traj * 32 + 255) / 256);
+  if (dtype == DFX_F64) dense_pad_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(n_traj, max_steps, dim, s * dim, (double *)dense_ts, (double *)dense_y0, (double *)dense_y1, (double *)dense_k, dense_count);
+  else dense_pad_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(n_traj, max_steps, dim, s * dim, (float *)dense_ts, (float *)dense_y0, (float *)dense_y1, (float *)dense_k, dense_count);
+  count_launch();
+  DFX_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 double dfx_measure_fma_peak(int dtype, int device) {

@@ -107,6 +107,7 @@ struct SolveParams {
   int pad_vec, flush_vec;  // 32-byte stores for the +inf padding / the dense record flush
   int dense_cs;      // dense records with st.global.cs (evict-first) instead of write-back stores
   int dense_coop;    // SaveAt(dense): stage records through shared memory and store them warp-cooperatively (launcher provides the smem)
+  int dense_lazy;    // SaveAt(dense): leave the unfilled tails unwritten (dfx_dense_pad fills them on demand)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
   R *y_final, *t_final;
   long long *totals;  // [4] or null: sums of attempted / accepted steps, failed trajectories, max steps of one trajectory (zeroed by the launcher)
@@ -413,7 +414,8 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         // solve itself leaves most of the HBM write bandwidth idle, so the padding rides along for free (C3: the separate
         // pass cost 10.8 ms on top of a 22.8 ms solve) and every output byte is still written exactly once.
         const bool pad_saves = (p.save_ts != nullptr) || (p.save_steps > 0);
-        if (pad_saves || p.save_dense) {
+        const bool pad_dense = p.save_dense && !p.dense_lazy;
+        if (pad_saves || pad_dense) {
           const int lane = threadIdx.x & 31;
           for (unsigned m = waiting; m; m &= m - 1) {
             const int src = __ffs(m) - 1;
@@ -423,7 +425,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               pad_tail(p.ts_out + r * p.out_size, sc, (long long)p.out_size, lane, p.pad_vec != 0);
               pad_tail(p.ys_out + r * p.out_size * D, sc * D, (long long)p.out_size * D, lane, p.pad_vec != 0);
             }
-            if (p.save_dense) {
+            if (pad_dense) {
               const long long dc = __shfl_sync(kFullMask, dense_index, src), ms = p.max_steps;
               pad_tail(p.dense_ts + r * (ms + 1), dc + 1, ms + 1, lane, p.pad_vec != 0);
               pad_tail(p.dense_y0 + r * ms * D, dc * D, ms * D, lane, p.pad_vec != 0);

@@ -67,6 +67,11 @@ int launch_mlp(const dfx_solve_desc *d, void *stream_v) {
     }
     count_launch();
     DFX_CUDA_OK(cudaGetLastError());
+    if (p.totals) {
+      DFX_CUDA_OK(cudaMemsetAsync(p.totals, 0, 4 * sizeof(long long), stream));
+      totals_from_stats_kernel<<<64, 256, 0, stream>>>(p.n_traj, p.stats, p.result, p.totals);
+      count_launch();
+    }
     cudaFreeAsync(counter, stream);
     cudaFreeAsync(w2_image, stream);
   }

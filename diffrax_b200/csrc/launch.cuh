@@ -79,6 +79,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   p.stats = d->stats; p.result = d->result; p.save_count = d->save_count;
   p.dense_ts = (R *)d->dense_ts; p.dense_y0 = (R *)d->dense_y0; p.dense_y1 = (R *)d->dense_y1; p.dense_k = (R *)d->dense_k;
   p.dense_count = d->dense_count;
+  p.dense_lazy = d->dense_lazy_padding;
   p.dense_vec_ok = (((uintptr_t)d->dense_y0 | (uintptr_t)d->dense_y1 | (uintptr_t)d->dense_k) & 31u) == 0;
   p.y_final = (R *)d->y_final; p.t_final = (R *)d->t_final;
   p.totals = (long long *)d->totals;

@@ -97,6 +97,26 @@ inline int make_w2_tensor_map(CUtensorMap *out, const float *image_dev, char *er
   return 0;
 }
 
+// Ensemble totals (dfx_solve_desc.totals) from the per-trajectory statistics: the tensor-core kernels do not reduce them
+// in-kernel, so a small pass over stats / result does (N is 65 536 for BASELINE config 4: microseconds).
+__global__ void totals_from_stats_kernel(long long n, const int *__restrict__ stats, const int *__restrict__ result, long long *totals) {
+  long long a = 0, b = 0, c = 0, m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int s = stats[3 * i];
+    a += s; b += stats[3 * i + 1]; c += result[i] != 0; m = m > s ? m : s;
+  }
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(kFullMask, a, o); b += __shfl_xor_sync(kFullMask, b, o); c += __shfl_xor_sync(kFullMask, c, o);
+    const long long mo = __shfl_xor_sync(kFullMask, m, o); m = m > mo ? m : mo;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd((unsigned long long *)totals + 0, (unsigned long long)a);
+    atomicAdd((unsigned long long *)totals + 1, (unsigned long long)b);
+    atomicAdd((unsigned long long *)totals + 2, (unsigned long long)c);
+    atomicMax(totals + 3, m);
+  }
+}
+
 // ---- TMA staging of W2 ----
 // The 128x128 hidden-layer weights are split into TF32 hi / lo ONCE per launch by a small kernel that writes them to global
 // memory already in the shared-memory image the tensor core wants (canonical K-major no-swizzle UMMA layout: 8x4-element

@@ -178,6 +178,12 @@ typedef struct dfx_solve_desc {
    * `totals_device` is the optional device copy for the host call, like y_final_device.  NULL = not wanted. */
   int64_t *totals;
   int64_t *totals_device;
+
+  /* SaveAt(dense=True): 0 = every unfilled slot of dense_ts / dense_y0 / dense_y1 / dense_k is written +inf by the solve
+   * (the reference's buffers, _integrate.py:1296-1300, 1320-1322); 1 = the tails are left unwritten (dense_count says how
+   * many records are valid; dfx_dense_evaluate / _derivative never read beyond them) and dfx_dense_pad() fills them on
+   * demand.  At BASELINE config 3 the padding is 63 % of the bytes the eager layout writes. */
+  int32_t dense_lazy_padding;
 } dfx_solve_desc;
 
 /* ---- library ---- */
@@ -239,6 +245,10 @@ int dfx_dense_derivative(int dtype, int solver_id, int64_t n_traj, int dim, int 
 /* dst_device[0..n) = *src_device on `cuda_stream`: a device-resident scalar (an unbatched traced t0 / t1 reaching the
  * jax.ffi handler) turned into the per-trajectory array the descriptor takes. */
 int dfx_broadcast_device_scalar(int dtype, int64_t n, const void *src_device, void *dst_device, void *cuda_stream);
+
+/* fills the unfilled tails of dense buffers produced with dense_lazy_padding = 1 with +inf (device pointers) */
+int dfx_dense_pad(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, void *dense_ts, void *dense_y0,
+                  void *dense_y1, void *dense_k, const int32_t *dense_count, void *cuda_stream);
 
 /* measured FMA-pipe peaks for the roofline denominators (dependent-free FMA chains);
  * returns TFLOP/s (2 flop per FMA) or a negative dfx_error. */

@@ -943,6 +943,10 @@ def test_full_size_properties_c4(dev):
     b = dfx.diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d[perm].contiguous(), stepsize_controller=ctrl)
     assert torch.equal(a.ys[perm], b.ys) and torch.equal(a.stats["num_steps"][perm], b.stats["num_steps"])
     assert bool(torch.isfinite(a.ys).all()) and int((a.result != 0).sum()) == 0
+    # the sharded entry on the tensor-core path: totals reduced from the per-trajectory statistics
+    sh = dfx.sharded_diffeqsolve(term, dfx.Tsit5(), 0.0, 10.0, None, y0d, stepsize_controller=ctrl)
+    assert int(sh.stats["num_steps"]) == int(a.stats["num_steps"].sum()) and int(sh.stats["num_failed"]) == 0
+    assert int(sh.stats["num_accepted_steps"]) == int(a.stats["num_accepted_steps"].sum()) and torch.equal(sh.y_final, a.ys[:, 0])
     sl = slice(777, 777 + 512)
     o = oracle.solve("mlp", y0[sl], 0.0, 10.0, None, solver="tsit5", params=mlp.oracle_params(), dtype=np.float32, rtol=1e-3, atol=1e-6)
     assert relerr_state(to_np(a.ys)[sl], o["ys"]) < RTOL32
