@@ -10,6 +10,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdiffrax_b200.so")
+if os.environ.get("DFX_LIB"):  # kernel experiments (tools/build_variant.py): an explicitly named build of the same library
+    LIB_PATH = os.path.abspath(os.environ["DFX_LIB"])
 
 ABI_VERSION = 2
 F64, F32 = 0, 1
@@ -22,6 +24,7 @@ SOLVER_IDS = {"tsit5": 0, "dopri5": 1, "dopri8": 2, "heun": 3, "bosh3": 4, "midp
 HALF_SOLVER = 0x100  # DFX_HALF_SOLVER: HalfSolver(inner) = HALF_SOLVER | inner id
 FIELD_IDS = {"decay": 0, "lotka_volterra": 1, "lorenz": 2, "cr3bp": 3, "mlp": 4, "ou": 5,
              "forced_osc": 6, "vdp": 7}
+FIELD_OU_MATRIX = 16   # + m: OU drift with a constant [d, m] diffusion matrix
 
 
 class SolveDesc(C.Structure):

@@ -390,7 +390,13 @@ static int check_desc(const dfx_solve_desc *d) {
   }
   if (d->levy_area != DFX_LEVY_NONE) {
     if (!d->bm_keys) { set_error("SDE solve needs bm_keys"); return DFX_ERR_BAD_ARGUMENT; }
-    if (d->bm_dim != 0 && d->bm_dim != d->dim) {
+    const bool matrix = d->field_id > DFX_FIELD_OU_MATRIX && d->field_id <= DFX_FIELD_OU_MATRIX + 4;
+    if (matrix && d->bm_dim != d->field_id - DFX_FIELD_OU_MATRIX) {
+      set_error("a [d, %d] diffusion matrix needs VirtualBrownianTree(shape=(%d,)), got shape (%d,)", d->field_id - DFX_FIELD_OU_MATRIX,
+                d->field_id - DFX_FIELD_OU_MATRIX, d->bm_dim);
+      return DFX_ERR_BAD_ARGUMENT;
+    }
+    if (!matrix && d->bm_dim != 0 && d->bm_dim != d->dim) {
       set_error("VirtualBrownianTree(shape=(%d,)) drives a diagonal diffusion: it needs a state of the same dimension (got %d)", d->bm_dim, d->dim);
       return DFX_ERR_BAD_ARGUMENT;
     }

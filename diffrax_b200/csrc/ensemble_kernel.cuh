@@ -61,6 +61,9 @@ struct HalfOf : Inner {
 // number of independent Brownian components a field is driven by (Field::kNoise when it declares one, else 1)
 template <class F, class = void> struct NoiseDim { static constexpr int value = 1; };
 template <class F> struct NoiseDim<F, std::void_t<decltype(F::kNoise)>> { static constexpr int value = F::kNoise; };
+// matrix-valued diffusion: Field::noise_prod(fp, t, W[NW], c) = row c of g(t) . W instead of the scalar g(t) * W[c]
+template <class F, class = void> struct MatrixNoise { static constexpr bool value = false; };
+template <class F> struct MatrixNoise<F, std::void_t<decltype(F::kMatrixNoise)>> { static constexpr bool value = F::kMatrixNoise; };
 template <class T, class = void> struct IsHalf { static constexpr bool value = false; };
 template <class I> struct IsHalf<HalfOf<I>> { static constexpr bool value = true; };
 template <class T> struct InnerId { static constexpr int value = T::kId; };
@@ -226,7 +229,10 @@ template <class R> __device__ __forceinline__ int clip_find_idx(R t, const R *ts
 //   EXTRA  (RICH only) the rarely used machinery: ClipStepSizeController, the Hairer starting step, Events.  Kept out of
 //          the plain SaveAt kernels because it costs them registers and instruction-cache footprint (Dopri8 dense: 216 ->
 //          255 registers with spills when it was compiled in)
-template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false>
+//   SPEC   (fp64 ODE SaveAt(t1) solves only) the controller configuration is known at compile time: PIDController with the
+//          default pure I-controller at the solver's order (the fast path) and no dtmin / dtmax.  Removes the uniform
+//          branches and parameter loads of the general controller from the step loop (C2: -2 % time).
+template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false, bool SPEC = false>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<R, Field, Solver, LEVY, RICH>())
 ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) {
   constexpr int D = Field::kDim;
@@ -236,6 +242,13 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   constexpr bool FSAL = Solver::kFsal && !SDE;
 #ifndef DFX_OPT_CHAIN_Y0
 #define DFX_OPT_CHAIN_Y0 1
+#endif
+#ifndef DFX_OPT_ABSMAX_FP64
+#define DFX_OPT_ABSMAX_FP64 1   // max(|y0|, |y1|) of the error scale on the FP64 pipe (DSETP + select) instead of 7 integer-ALU ops:
+                                // the issue port, not the FP64 pipe, is the tighter limit of the step loop (C2: -1.8 % time)
+#endif
+#ifndef DFX_OPT_EARLY_STAGE
+#define DFX_OPT_EARLY_STAGE 0   // SaveAt(dense): write each stage value to the staging record as soon as it exists
 #endif
 #ifndef DFX_OPT_LAST_STAGE_F
 #define DFX_OPT_LAST_STAGE_F 1
@@ -590,8 +603,15 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
 #pragma unroll
           for (int w = 0; w < NW; ++w) { Wv[w] = R(0); Hv[w] = R(0); }
           if constexpr (SDE) bm.increment(st0, st1, p.vbt, Wv, Hv);
-          auto Wc = [&](int c) { return Wv[NW == 1 ? 0 : c]; };
-          auto Hc = [&](int c) { return Hv[NW == 1 ? 0 : c]; };
+          auto Wc = [&](int c) { return Wv[NW == 1 ? 0 : (c < NW ? c : 0)]; };
+          auto Hc = [&](int c) { return Hv[NW == 1 ? 0 : (c < NW ? c : 0)]; };
+          // ControlTerm.prod (_term.py:417-427): g(t) . X for component c, X = W or H.  Scalar / diagonal diffusion: g(t) X_c;
+          // matrix diffusion: tensordot over the Brownian axis
+          [[maybe_unused]] auto gprod = [&](R t, const R (&X)[NW], int c) -> R {
+            if constexpr (!SDE) return R(0);
+            else if constexpr (MatrixNoise<Field>::value) return Field::template noise_prod<R>(fp, t, X, c);
+            else return Field::template diffusion<R>(fp, t) * X[NW == 1 ? 0 : (c < NW ? c : 0)];
+          };
 
           if constexpr (TAB) {
             // ---- explicit RK step, runge_kutta.py:643-1203 ----
@@ -613,7 +633,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   #pragma unroll
               for (int c = 0; c < D; ++c) {
                 R kk = control * fi[c];
-                if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * Wc(c);  // MultiTerm.vf_prod (_term.py:711-722)
+                if constexpr (SDE) kk = kk + gprod(st0, Wv, c);  // MultiTerm.vf_prod (_term.py:711-722)
                 k[0][c] = kk;
               }
             }
@@ -648,7 +668,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
                   if (i == S - 1) continue;  // the last stage value is only read by the error estimate, through f_last below
                 }
                 R kk = control * fi[c];
-                if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, ti) * Wc(c);
+                if constexpr (SDE) kk = kk + gprod(ti, Wv, c);
                 k[i][c] = kk;
               }
             }
@@ -691,7 +711,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   #pragma unroll
             for (int c = 0; c < D; ++c) {
               R kk = (direction * dt) * f0[c];
-              if constexpr (SDE) kk = kk + Field::template diffusion<R>(fp, st0) * Wc(c);
+              if constexpr (SDE) kk = kk + gprod(st0, Wv, c);
               k[0][c] = kk;
               y1[c] = y[c] + kk;
               yerr[c] = R(0);
@@ -701,10 +721,17 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             // ---- ShARK: srk.py:335-671 additive-noise branch with shark.py:10-30 ----
             if constexpr (SDE) {
               const R h = dt;
-              const R g0 = Field::template diffusion<R>(fp, st0), g1 = Field::template diffusion<R>(fp, st1);
-              const R g_delta = R(0.5) * (g1 - g0);
-              auto w_kg = [&](int c) { return g0 * Wc(c); };  // 441-447
-              auto h_kg = [&](int c) { return g0 * Hc(c); };
+              // w_kg = g(t0) . W, h_kg = g(t0) . H (441-447); g_delta = (g(t1) - g(t0)) / 2 applied to W - 2 H (612-618)
+              auto w_kg = [&](int c) { return gprod(st0, Wv, c); };
+              auto h_kg = [&](int c) { return gprod(st0, Hv, c); };
+              auto time_var = [&](int c) -> R {
+                if constexpr (MatrixNoise<Field>::value) {  // constant matrix: g_delta = 0.5 (G - G) = 0 exactly, so prod(g_delta, .) = 0
+                  return R(0);
+                } else {
+                  const R g0 = Field::template diffusion<R>(fp, st0), g1 = Field::template diffusion<R>(fp, st1);
+                  return (R(0.5) * (g1 - g0)) * (Wc(c) - R(2.0) * Hc(c));
+                }
+              };
               R z[D], fz[D];
   #pragma unroll
               for (int c = 0; c < D; ++c) z[c] = y[c] + R(0) + (R(kSharkAW0) * w_kg(c) + R(kSharkAH0) * h_kg(c));  // stage 0: 545
@@ -719,7 +746,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   #pragma unroll
               for (int c = 0; c < D; ++c) {
                 R diffusion_result = R(kSharkBW) * w_kg(c) + R(kSharkBH) * h_kg(c);   // 603-607
-                diffusion_result = diffusion_result + g_delta * (Wc(c) - R(2.0) * Hc(c));  // 612-618
+                diffusion_result = diffusion_result + time_var(c);  // 612-618
                 yerr[c] = R(kSharkE0) * k[0][c] + R(kSharkE1) * k[1][c];        // 638-639, 663
                 const R drift_result = R(kSharkB0) * k[0][c] + R(kSharkB1) * k[1][c];  // 667
                 y1[c] = y[c] + drift_result + diffusion_result;                  // 669
@@ -749,7 +776,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         // ---- step-size controller ----
         bool keep;
         R next_t0, next_t1;
-        if (p.controller == DFX_CTRL_PID) {
+        if (SPEC || p.controller == DFX_CTRL_PID) {
           // pid.py:394-567.  y_error NaN -> inf first (_integrate.py:386).
           R dtn, inv = R(1), factor;
           bool slow = true;
@@ -761,11 +788,16 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             // on (float)q.  NaN or inf anywhere (y1, y_error) makes q non-finite and fails the range test, and q
             // within 1e-6 of the accept boundary (where the reference's own rounding of sqrt and '/' decides) is
             // excluded too: all of those take the faithful path below, so accept/reject decisions are the reference's.
-            if (p.fast_pid) {
+            if (SPEC || p.fast_pid) {
               R ss = R(0);
 #pragma unroll
               for (int c = 0; c < D; ++c) {  // _scale, 483-490 (a NaN y1 propagates through abs_max_bits)
+#if DFX_OPT_ABSMAX_FP64
+                const R ya_ = r_abs(y[c]), yb_ = r_abs(y1[c]);
+                const R yy = (ya_ > yb_) ? ya_ : yb_;  // (a NaN y1 fails the compare and is selected: it propagates)
+#else
                 const R yy = abs_max_bits(y[c], y1[c]);
+#endif
                 const R sc = yerr[c] * fast_rcp(p.atol + yy * p.rtol);
                 ss += sc * sc;
               }
@@ -774,7 +806,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               if (qf > 1e-30f && qf < 1e30f && fabsf(qf - 1.0f) > 1e-6f) {
                 slow = false;
                 keep = qf < 1.0f;                                  // 493 (same decision as q < 1 outside the 1e-6 band)
-                if (p.has_dtmin) keep = keep || at_dtmin;          // 495-496
+                if (!SPEC && p.has_dtmin) keep = keep || at_dtmin;          // 495-496
                 factor = p.safety * (R)inv_root<2 * Solver::kOrder>((double)q, qf);  // 515, 522
                 const R fmin = keep ? R(1) : p.factormin;          // 518
                 const R fmax = keep ? p.factormax : p.safety;      // 520
@@ -811,7 +843,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             dtn = dt * factor;                              // 531
             if (inv == R(0) || r_isinf(inv)) inv = R(1);    // 537-538
           }
-          if (p.has_dtmax | p.has_dtmin) {  // one uniform branch around both limits: neither is set by default
+          if (!SPEC && (p.has_dtmax | p.has_dtmin)) {  // one uniform branch around both limits: neither is set by default
             if (p.has_dtmax) dtn = jnp_min(dtn, p.dtmax);   // 545-546
             if (p.has_dtmin) {                              // 547-555
               if (!p.force_dtmin && dtn < p.dtmin && result == DFX_RESULT_SUCCESSFUL) result = DFX_RESULT_DT_MIN_REACHED;

@@ -155,6 +155,39 @@ struct OuDiagField {
   template <class R> static __device__ __forceinline__ R diffusion(const P<R> &p, R t) { return p.sigma + p.sigma_t * t; }
 };
 
+// D Ornstein-Uhlenbeck components driven through a constant D x M diffusion MATRIX by VirtualBrownianTree(shape=(M,)):
+// ControlTerm(lambda t, y, args: G, bm) with G of shape (D, M), whose prod is tensordot(G, dW) (_term.py:267-268, 417-427).
+// Field id DFX_FIELD_OU_MATRIX + M; params [theta, mu, G row-major (D*M)].
+template <int D, int M>
+struct OuMatrixField {
+  static constexpr int kId = DFX_FIELD_OU_MATRIX + M;
+  static constexpr int kDim = D;
+  static constexpr int kNoise = M;
+  static constexpr bool kMatrixNoise = true;
+  static constexpr bool kSde = true;
+  static constexpr int kNumParams = 2 + D * M;
+  template <class R> struct P { R theta, mu; R g[D][M]; };
+  template <class R> static P<R> make(const double *p, int, const void *) {
+    P<R> o;
+    o.theta = (R)p[0]; o.mu = (R)p[1];
+    for (int c = 0; c < D; ++c)
+      for (int j = 0; j < M; ++j) o.g[c][j] = (R)p[2 + c * M + j];
+    return o;
+  }
+  template <class R>
+  static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[D], R (&f)[D]) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) f[c] = p.theta * (p.mu - y[c]);
+  }
+  // row c of G . w  (tensordot over the Brownian axis, ascending j)
+  template <class R> static __device__ __forceinline__ R noise_prod(const P<R> &p, R, const R (&w)[M], int c) {
+    R acc = R(0);
+#pragma unroll
+    for (int j = 0; j < M; ++j) acc += p.g[c][j] * w[j];
+    return acc;
+  }
+};
+
 // Neural-ODE vector field (BASELINE config 4): eqx.nn.MLP(d -> W -> W -> d) with softplus hidden activations and
 // a tanh output (docs/examples/neural_ode.ipynb cell 5; benchmarks/small_neural_ode.py:25-28), evaluated per thread
 // on the FP32 CUDA cores.  This is the exact-fp32 reference implementation of the field inside the generic ensemble

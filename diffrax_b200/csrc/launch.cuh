@@ -121,9 +121,9 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
 struct DeviceInfo { int sms; };
 int device_sm_count(int *sms);  // cached per device (api.cu)
 
-template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false>
+template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false, bool SPEC = false>
 int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, cudaStream_t stream) {
-  auto kern = ensemble_kernel<R, Field, Solver, LEVY, RICH, EXTRA>;
+  auto kern = ensemble_kernel<R, Field, Solver, LEVY, RICH, EXTRA, SPEC>;
   int sms = 0;
   if (int rc = device_sm_count(&sms)) return rc;
   // SaveAt(dense=True): per-lane staging records for the warp-cooperative stores
@@ -233,7 +233,18 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   int rc;
   if (extra) rc = launch_variant<R, Field, Solver, LEVY, true, true>(p, fp, stream);
   else if (rich) rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);
-  else rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
+  else {
+    // fp64 ODE solves with the default controller configuration: the specialised instantiation (see SPEC)
+    constexpr bool kHasSpec = IsTableau<Solver>::value && !SDE && sizeof(R) == 8;
+    bool spec = false;
+    if constexpr (kHasSpec) spec = p.controller == DFX_CTRL_PID && p.fast_pid && !p.has_dtmin && !p.has_dtmax;
+    if constexpr (kHasSpec) {
+      if (spec) rc = launch_variant<R, Field, Solver, LEVY, false, false, true>(p, fp, stream);
+      else rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
+    } else {
+      rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
+    }
+  }
   cudaFreeAsync(scratch, stream);
   return rc;
 }

@@ -119,6 +119,28 @@ class OrnsteinUhlenbeck(Field):
         return self.p
 
 
+class OrnsteinUhlenbeckMatrix(Field):
+    """dy = theta (mu - y) dt + G dW with a constant ``[d, m]`` diffusion MATRIX ``G`` and an m-dimensional Brownian motion:
+    ``ControlTerm(lambda t, y, args: G, VirtualBrownianTree(..., shape=(m,), ...))``, whose product is
+    ``tensordot(G, dW)`` (_term.py:267-268, 417-427).  Kernels: (d, m) in {(2, 2), (3, 2), (2, 3)}."""
+    name, is_sde = "ou_matrix", True
+
+    def __init__(self, theta, mu, G):
+        import numpy as np
+        self.G = np.asarray(G, np.float64)
+        if self.G.ndim != 2:
+            raise ValueError("G must be a [d, m] matrix")
+        self.dim, self.m = int(self.G.shape[0]), int(self.G.shape[1])
+        self.p = [float(theta), float(mu)] + [float(v) for v in self.G.ravel()]
+
+    @property
+    def field_id(self):
+        return _lib.FIELD_OU_MATRIX + self.m
+
+    def params(self):
+        return self.p
+
+
 class MLP(Field):
     """Neural-ODE vector field: ``eqx.nn.MLP(in=d, out=d, width, depth=2, activation=softplus, final_activation=tanh)``
     (docs/examples/neural_ode.ipynb cell 5).  ``layers`` is ``[(W1, b1), (W2, b2), (W3, b3)]`` with eqx ``Linear``

@@ -45,7 +45,9 @@ enum dfx_controller { DFX_CTRL_CONSTANT = 0, DFX_CTRL_PID = 1 };
  * User functors register further ids >= DFX_FIELD_USER with dfx_register_launcher. */
 enum dfx_field { DFX_FIELD_DECAY = 0, DFX_FIELD_LOTKA_VOLTERRA = 1, DFX_FIELD_LORENZ = 2,
                  DFX_FIELD_CR3BP = 3, DFX_FIELD_MLP = 4, DFX_FIELD_OU = 5,
-                 DFX_FIELD_FORCED_OSC = 6, DFX_FIELD_VDP = 7, DFX_FIELD_USER = 1000 };
+                 DFX_FIELD_FORCED_OSC = 6, DFX_FIELD_VDP = 7,
+                 DFX_FIELD_OU_MATRIX = 16, /* + m (1..4): OU drift with a constant [d, m] diffusion matrix, params [theta, mu, G] */
+                 DFX_FIELD_USER = 1000 };
 
 /* VirtualBrownianTree(levy_area=...) (_brownian/tree.py:238-254) */
 enum dfx_levy { DFX_LEVY_NONE = 0, DFX_LEVY_BROWNIAN_INCREMENT = 1, DFX_LEVY_SPACE_TIME = 2 };

@@ -1015,3 +1015,27 @@ def test_sharded_entry_single_rank(dev, host):
     r2 = dfx.diffeqsolve(mk(torch.tensor(keys.view(np.int32), device=dev)), dfx.Heun(), 0.0, 1.0, 2.0 ** -5, y1.to(dev))
     o2 = dfx.sharded_diffeqsolve(mk(kk), dfx.Heun(), 0.0, 1.0, 2.0 ** -5, y1.pin_memory() if host else y1.to(dev))
     assert torch.equal(o2.y_final, r2.ys[:, 0]) and int(o2.stats["num_steps"]) == 32 * n
+
+
+@pytest.mark.parametrize("solver,lv", [("heun", "bi"), ("shark", "stla"), ("euler", "bi")])
+@pytest.mark.parametrize("shape", [(2, 2), (3, 2), (2, 3)])
+def test_matrix_valued_diffusion(dev, solver, lv, shape):
+    """General ControlTerm (_term.py:267-268, 417-427): constant [d, m] diffusion matrix, VirtualBrownianTree(shape=(m,)),
+    prod = tensordot(G, dW).  Fixed steps: CUDA == oracle to 1e-12; the ensemble covariance is G G^T (1 - e^-2) / 2."""
+    d, m = shape
+    if (solver == "euler" and shape != (2, 2)):
+        pytest.skip("Euler kernel registered for (2, 2) only")
+    rng = np.random.default_rng(3)
+    G = rng.uniform(-0.5, 0.5, (d, m))
+    n = 4096
+    keys = dfx.random.split(dfx.random.key(31), n)
+    field = dfx.fields.OrnsteinUhlenbeckMatrix(1.0, 0.0, G)
+    cls = dfx.BrownianIncrement if lv == "bi" else dfx.SpaceTimeLevyArea
+    bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -8, (m,), torch.tensor(keys.view(np.int32), device=dev), cls)
+    terms = dfx.MultiTerm(dfx.ODETerm(field.drift), dfx.ControlTerm(field.diffusion, bm))
+    sol = dfx.diffeqsolve(terms, SOLVERS[solver](), 0.0, 1.0, 2.0 ** -5, torch.ones(n, d, dtype=torch.float64, device=dev))
+    o = oracle.solve(16 + m, np.ones((n, d)), 0.0, 1.0, 2.0 ** -5, solver=solver, params=[1.0, 0.0] + list(G.ravel()),
+                     controller="constant", levy_area=lv, keys=keys, bm_tol=2.0 ** -8, bm_dim=m)
+    assert np.array_equal(stats_np(sol), o["stats"]) and np.abs(to_np(sol.ys) - o["ys"]).max() < 1e-12
+    cov = np.cov(to_np(sol.ys)[:, -1, :].T)
+    assert np.abs(cov - G @ G.T * (1 - np.exp(-2.0)) / 2).max() < 0.02

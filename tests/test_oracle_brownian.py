@@ -150,3 +150,21 @@ def test_vector_tree_shares_the_key_path(levy):
     if levy == "stla":  # H ~ N(0, (t-s)/12), independent of W
         assert np.all(np.abs(H3.var(0) - 0.7 / 12) < 0.01)
         assert abs(np.corrcoef(W3[:, 1], H3[:, 1])[0, 1]) < 0.06
+
+
+@pytest.mark.parametrize("solver,levy", [("euler", "bi"), ("heun", "bi"), ("shark", "stla")])
+def test_matrix_valued_diffusion_covariance_law(solver, levy):
+    """General ControlTerm: a constant [d, m] diffusion matrix G with an m-dimensional Brownian motion, prod = tensordot(G, dW)
+    (_term.py:267-268, 417-427).  dy = theta (mu - y) dt + G dW has the exact law  mean mu + (y0 - mu) e^{-theta t},
+    covariance G G^T (1 - e^{-2 theta t}) / (2 theta): the oracle's ensemble reproduces it (correlated components)."""
+    import diffrax_b200 as dfx
+    n = 6000
+    keys = dfx.random.split(dfx.random.key(5), n)
+    G = np.array([[0.5, 0.2], [0.0, 0.3], [0.1, -0.4]])
+    r = oracle.solve(oracle.FIELDS["ou_matrix2"], np.ones((n, 3)), 0.0, 1.0, 2.0 ** -6, solver=solver, params=[1.0, 0.0] + list(G.ravel()),
+                     controller="constant", levy_area=levy, keys=keys, bm_tol=2.0 ** -8, bm_dim=2)
+    y = r["ys"][:, -1, :]
+    want = G @ G.T * (1 - np.exp(-2.0)) / 2
+    tol = 0.012 if solver != "euler" else 0.02
+    assert np.abs(np.cov(y.T) - want).max() < tol
+    assert np.abs(y.mean(0) - np.exp(-1.0)).max() < 0.02
