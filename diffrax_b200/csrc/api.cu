@@ -748,7 +748,13 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
   for (int i = 0; i < nstreams; ++i) DFX_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
   std::vector<void *> allocs[2];
   const bool want_totals = h->totals || h->totals_device;
-  std::vector<int64_t> chunk_totals(want_totals ? 4 * (size_t)nchunks : 0, 0);
+  // per-chunk totals land in PINNED memory: a D2H copy into pageable memory would block the host and serialise the chunks
+  static thread_local int64_t *chunk_totals = nullptr;
+  if (want_totals) {
+    if (!chunk_totals) DFX_CUDA_OK(cudaHostAlloc((void **)&chunk_totals, 4 * 64 * sizeof(int64_t), cudaHostAllocPortable));
+    if (nchunks > 64) nchunks = 64;
+    std::memset(chunk_totals, 0, 4 * (size_t)nchunks * sizeof(int64_t));
+  }
   int rc = 0;
   for (int64_t c = 0; c < nchunks && !rc; ++c) {
     const int64_t lo = h->n_traj * c / nchunks, hi = h->n_traj * (c + 1) / nchunks;

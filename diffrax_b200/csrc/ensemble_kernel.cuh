@@ -811,7 +811,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
                 const R fmin = keep ? R(1) : p.factormin;          // 518
                 const R fmax = keep ? p.factormax : p.safety;      // 520
                 factor = pos_min_bits(pos_max_bits(factor, fmin), fmax);  // 521-525 (all operands positive)
-                dtn = dt * factor;                                 // 531
+                dtn = x_mul(dt, factor);                           // 531 (own rounding: never fused into next_t0 + dtn)
               }
             }
           }
@@ -840,7 +840,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             const R fmin = keep ? R(1) : p.factormin;       // 518
             const R fmax = keep ? p.factormax : p.safety;   // 520
             factor = jnp_min(jnp_max(factor, fmin), fmax);  // 521-525
-            dtn = dt * factor;                              // 531
+            dtn = x_mul(dt, factor);                        // 531
             if (inv == R(0) || r_isinf(inv)) inv = R(1);    // 537-538
           }
           if (!SPEC && (p.has_dtmax | p.has_dtmin)) {  // one uniform branch around both limits: neither is set by default
@@ -853,7 +853,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             }
           }
           next_t0 = keep ? st1 : st0;                     // 557-558
-          next_t1 = next_t0 + dtn;
+          next_t1 = x_add(next_t0, dtn);  // the reference's two roundings, identical in every instantiation of the kernel
           if (keep) { pid_prev_inv = pid_inv; pid_inv = inv; }  // 560-564
         } else {
           // constant.py:57-104
