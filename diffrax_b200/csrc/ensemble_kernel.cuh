@@ -329,7 +329,8 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
     // 32 * 300 / (steps per trajectory * instructions per step) of the run (10 % on C2).  Finished lanes therefore
     // wait (idle) until `refill_batch` of them can share one pass, or nothing else is running.
     // a lane is `done` when its loop condition (_integrate.py:355-363, 685-687) has turned false
-    const bool done = active && !((tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL));
+    // (SPEC: no dtmin, no events - `result` can only change when the trajectory is finalised)
+    const bool done = active && !((tprev < t1) && (num_steps < p.max_steps) && (SPEC || result == DFX_RESULT_SUCCESSFUL));
     const unsigned running = __ballot_sync(kFullMask, active && !done);
     const unsigned waiting = __ballot_sync(kFullMask, done);
     if (running == 0u || __popc(waiting) >= p.refill_batch) {
@@ -588,7 +589,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
     // ---------------- one attempted step (all active lanes, same instruction stream) ----------------
     [[maybe_unused]] long long dense_row = -1;  // >= 0: this lane staged a dense record in shared memory this iteration
     if (active) {
-      const bool run = (tprev < t1) && (num_steps < p.max_steps) && (result == DFX_RESULT_SUCCESSFUL);  // 355-363, 685-687
+      const bool run = (tprev < t1) && (num_steps < p.max_steps) && (SPEC || result == DFX_RESULT_SUCCESSFUL);  // 355-363, 685-687
       if (run) {
         [[maybe_unused]] const long long idx = idx_i;
         const R st0 = tprev, st1 = tnext;
@@ -831,12 +832,12 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             }
             const R scaled_error = (D == 1) ? r_abs(sc0) : r_sqrt(ss) / sqrt_d;  // optx.rms_norm
             keep = scaled_error < R(1);                     // 493
-            if (p.has_dtmin) keep = keep || at_dtmin;       // 495-496
+            if (!SPEC && p.has_dtmin) keep = keep || at_dtmin;       // 495-496
             inv = R(1) / scaled_error;                      // 498
             factor = p.safety;
             if (p.use_c1) factor = factor * r_pow(inv, p.coeff1);          // 515
-            if (p.use_c2) factor = factor * r_pow(pid_inv, p.coeff2);      // 516
-            if (p.use_c3) factor = factor * r_pow(pid_prev_inv, p.coeff3); // 517
+            if (!SPEC && p.use_c2) factor = factor * r_pow(pid_inv, p.coeff2);      // 516 (SPEC: pure I-controller, no history)
+            if (!SPEC && p.use_c3) factor = factor * r_pow(pid_prev_inv, p.coeff3); // 517
             const R fmin = keep ? R(1) : p.factormin;       // 518
             const R fmax = keep ? p.factormax : p.safety;   // 520
             factor = jnp_min(jnp_max(factor, fmin), fmax);  // 521-525
@@ -854,7 +855,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           }
           next_t0 = keep ? st1 : st0;                     // 557-558
           next_t1 = x_add(next_t0, dtn);  // the reference's two roundings, identical in every instantiation of the kernel
-          if (keep) { pid_prev_inv = pid_inv; pid_inv = inv; }  // 560-564
+          if constexpr (!SPEC) { if (keep) { pid_prev_inv = pid_inv; pid_inv = inv; } }  // 560-564 (unused by the pure I-controller)
         } else {
           // constant.py:57-104
           keep = true;

@@ -20,31 +20,4 @@ DFX_REGISTER(double, F, ::dfx::HalfOf<::dfx::Heun>, 1)
 DFX_REGISTER(double, F, ::dfx::HalfOf<::dfx::SharkSolver>, 2)
 DFX_REGISTER(float, F, ::dfx::HalfOf<::dfx::Heun>, 1)
 DFX_REGISTER(float, F, ::dfx::HalfOf<::dfx::SharkSolver>, 2)
-// vector Brownian motion, shape=(D,), diagonal diffusion: D = 2, 3
-using F2 = ::dfx::OuDiagField<2>;
-using F3 = ::dfx::OuDiagField<3>;
-DFX_REGISTER(double, F2, ::dfx::EulerSolver, 1)
-DFX_REGISTER(double, F2, ::dfx::Heun, 1)
-DFX_REGISTER(double, F2, ::dfx::SharkSolver, 2)
-DFX_REGISTER(float, F2, ::dfx::Heun, 1)
-DFX_REGISTER(float, F2, ::dfx::SharkSolver, 2)
-DFX_REGISTER(double, F3, ::dfx::Heun, 1)
-DFX_REGISTER(double, F3, ::dfx::SharkSolver, 2)
-DFX_REGISTER(float, F3, ::dfx::Heun, 1)
-DFX_REGISTER(float, F3, ::dfx::SharkSolver, 2)
-// matrix-valued additive diffusion: ControlTerm(lambda t, y, args: G[d, m], VirtualBrownianTree(shape=(m,)))
-using M22 = ::dfx::OuMatrixField<2, 2>;
-using M32 = ::dfx::OuMatrixField<3, 2>;
-using M23 = ::dfx::OuMatrixField<2, 3>;
-DFX_REGISTER(double, M22, ::dfx::EulerSolver, 1)
-DFX_REGISTER(double, M22, ::dfx::Heun, 1)
-DFX_REGISTER(double, M22, ::dfx::SharkSolver, 2)
-DFX_REGISTER(float, M22, ::dfx::Heun, 1)
-DFX_REGISTER(float, M22, ::dfx::SharkSolver, 2)
-DFX_REGISTER(double, M32, ::dfx::Heun, 1)
-DFX_REGISTER(double, M32, ::dfx::SharkSolver, 2)
-DFX_REGISTER(float, M32, ::dfx::Heun, 1)
-DFX_REGISTER(double, M23, ::dfx::Heun, 1)
-DFX_REGISTER(double, M23, ::dfx::SharkSolver, 2)
-DFX_REGISTER(float, M23, ::dfx::SharkSolver, 2)
 }  // namespace

@@ -231,13 +231,19 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
 
   if (p.totals) DFX_CUDA_OK(cudaMemsetAsync(p.totals, 0, 4 * sizeof(long long), stream));
   int rc;
+  // fp64 ODE solves with the default controller configuration run the specialised instantiations (see SPEC)
+  constexpr bool kHasSpec = IsTableau<Solver>::value && !IsHalf<Solver>::value && !SDE && sizeof(R) == 8;
+  bool spec = false;
+  if constexpr (kHasSpec) spec = p.controller == DFX_CTRL_PID && p.fast_pid && !p.has_dtmin && !p.has_dtmax;
   if (extra) rc = launch_variant<R, Field, Solver, LEVY, true, true>(p, fp, stream);
-  else if (rich) rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);
-  else {
-    // fp64 ODE solves with the default controller configuration: the specialised instantiation (see SPEC)
-    constexpr bool kHasSpec = IsTableau<Solver>::value && !SDE && sizeof(R) == 8;
-    bool spec = false;
-    if constexpr (kHasSpec) spec = p.controller == DFX_CTRL_PID && p.fast_pid && !p.has_dtmin && !p.has_dtmax;
+  else if (rich) {
+    if constexpr (kHasSpec) {
+      if (spec) rc = launch_variant<R, Field, Solver, LEVY, true, false, true>(p, fp, stream);
+      else rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);
+    } else {
+      rc = launch_variant<R, Field, Solver, LEVY, true>(p, fp, stream);
+    }
+  } else {
     if constexpr (kHasSpec) {
       if (spec) rc = launch_variant<R, Field, Solver, LEVY, false, false, true>(p, fp, stream);
       else rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
