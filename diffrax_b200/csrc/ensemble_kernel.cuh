@@ -178,10 +178,9 @@ template <class R> __device__ __forceinline__ void pad_tail(R *row, long long st
 }
 
 // Claim the next trajectory for every lane of the warp that needs one: one atomic per warp.
-__device__ __forceinline__ long long claim_work(bool need, unsigned long long *counter) {
+__device__ __forceinline__ long long claim_work(bool need, unsigned long long *counter, int lane) {
   const unsigned m = __ballot_sync(kFullMask, need);
   if (m == 0) return -1;
-  const int lane = threadIdx.x & 31;
   const int leader = __ffs(m) - 1;
   unsigned long long base = 0;
   if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
@@ -320,7 +319,14 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   if constexpr (SDE) bm.attach_cache(reinterpret_cast<R *>(dense_smem_raw), p.vbt);
 
   __shared__ long long warp_totals[kBlockThreads / 32][4];  // attempted, accepted, failed, max steps (see p.totals)
-  if ((threadIdx.x & 31) == 0) { long long *w_ = warp_totals[threadIdx.x >> 5]; w_[0] = w_[1] = w_[2] = w_[3] = 0; }
+  // lane id and this warp's totals slot as a 32-bit shared address, computed ONCE: left to the compiler, the special-register
+  // reads (tid, shared window) behind them are re-issued at the top of every iteration of the step loop
+  const int lane_id = threadIdx.x & 31;
+  const uint32_t tot_addr = (uint32_t)__cvta_generic_to_shared(&warp_totals[threadIdx.x >> 5][0]);
+  if (lane_id == 0) {
+    asm volatile("st.shared.v2.u64 [%0], {%1, %1};" :: "r"(tot_addr), "l"(0ull) : "memory");
+    asm volatile("st.shared.v2.u64 [%0], {%1, %1};" :: "r"(tot_addr + 16u), "l"(0ull) : "memory");
+  }
   __syncwarp();
 
   for (;;) {
@@ -330,7 +336,9 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
     // wait (idle) until `refill_batch` of them can share one pass, or nothing else is running.
     // a lane is `done` when its loop condition (_integrate.py:355-363, 685-687) has turned false
     // (SPEC: no dtmin, no events - `result` can only change when the trajectory is finalised)
-    const bool done = active && !((tprev < t1) && (num_steps < p.max_steps) && (SPEC || result == DFX_RESULT_SUCCESSFUL));
+    // `runnable` is evaluated once per iteration (here, and again only for lanes that are refilled below)
+    bool runnable = (tprev < t1) && (num_steps < p.max_steps) && (SPEC || result == DFX_RESULT_SUCCESSFUL);
+    const bool done = active && !runnable;
     const unsigned running = __ballot_sync(kFullMask, active && !done);
     const unsigned waiting = __ballot_sync(kFullMask, done);
     if (running == 0u || __popc(waiting) >= p.refill_batch) {
@@ -386,7 +394,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             // one atomic per group of lanes that finalise into the same chunk (fixed-step ensembles finish in waves)
             const unsigned peers = __match_any_sync(__activemask(), c);
             unsigned total = 0;
-            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) total = atomicAdd(p.pipe_done + c, (unsigned)__popc(peers)) + (unsigned)__popc(peers);
+            if (lane_id == __ffs(peers) - 1) total = atomicAdd(p.pipe_done + c, (unsigned)__popc(peers)) + (unsigned)__popc(peers);
             if (total == cnt) {
               __threadfence_system();
               // (the value is a device timestamp in ~us, never 0: DFX_HOST_PIPE_TRACE prints it next to the host's clock)
@@ -413,13 +421,17 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
       if (p.totals != nullptr && waiting != 0u) {
         // ensemble totals for the multi-GPU statistics reduction: one warp reduction per finalise
         // pass into this warp's shared-memory slot; flushed with four global atomics when the warp leaves the kernel
-        const bool fin = (waiting >> (threadIdx.x & 31)) & 1u;
+        const bool fin = (waiting >> lane_id) & 1u;
         const int a_ = __reduce_add_sync(kFullMask, fin ? num_steps : 0), b_ = __reduce_add_sync(kFullMask, fin ? num_accepted : 0);
         const int c_ = __reduce_add_sync(kFullMask, (fin && result != DFX_RESULT_SUCCESSFUL) ? 1 : 0);
         const int m_ = __reduce_max_sync(kFullMask, fin ? num_steps : 0);
-        if ((threadIdx.x & 31) == 0) {
-          long long *w_ = warp_totals[threadIdx.x >> 5];
-          w_[0] += a_; w_[1] += b_; w_[2] += c_; w_[3] = w_[3] > m_ ? w_[3] : m_;
+        if (lane_id == 0) {
+          long long w0, w1, w2, w3;
+          asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(tot_addr) : "memory");
+          asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "r"(tot_addr + 16u) : "memory");
+          w0 += a_; w1 += b_; w2 += c_; w3 = w3 > m_ ? w3 : m_;
+          asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"(tot_addr), "l"(w0), "l"(w1) : "memory");
+          asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"(tot_addr + 16u), "l"(w2), "l"(w3) : "memory");
         }
       }
       if constexpr (RICH) {
@@ -430,7 +442,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         const bool pad_saves = (p.save_ts != nullptr) || (p.save_steps > 0);
         const bool pad_dense = p.save_dense && !p.dense_lazy;
         if (pad_saves || pad_dense) {
-          const int lane = threadIdx.x & 31;
+          const int lane = lane_id;
           for (unsigned m = waiting; m; m &= m - 1) {
             const int src = __ffs(m) - 1;
             const long long r = __shfl_sync(kFullMask, idx_i, src);
@@ -452,7 +464,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
       // ---------------- refill: finished lanes claim the next trajectory ----------------
       // `exhausted` is warp-uniform (it is set from a warp vote), so the collective below is convergent.
       if (!exhausted) {
-      const long long got = claim_work(!active, p.work_counter);
+      const long long got = claim_work(!active, p.work_counter, lane_id);
       // the queue only grows: once any lane is handed an index past the end, it is drained for good
       exhausted = __any_sync(kFullMask, !active && got >= p.n_traj);
       if (!active) {
@@ -576,6 +588,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             for (int i = 0; i < p.n_events; ++i) event_value[i] = event_cond(i, tprev, y, direction);  // _integrate.py:1432-1476
           }
           active = true;
+          runnable = (tprev < t1) && (0 < p.max_steps) && (SPEC || result == DFX_RESULT_SUCCESSFUL);
           }
         }
       }
@@ -589,7 +602,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
     // ---------------- one attempted step (all active lanes, same instruction stream) ----------------
     [[maybe_unused]] long long dense_row = -1;  // >= 0: this lane staged a dense record in shared memory this iteration
     if (active) {
-      const bool run = (tprev < t1) && (num_steps < p.max_steps) && (SPEC || result == DFX_RESULT_SUCCESSFUL);  // 355-363, 685-687
+      const bool run = runnable;  // 355-363, 685-687: tprev < t1, num_steps < max_steps, result == successful
       if (run) {
         [[maybe_unused]] const long long idx = idx_i;
         const R st0 = tprev, st1 = tnext;
@@ -1103,12 +1116,14 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
     }
 
   }
-  if (p.totals != nullptr && (threadIdx.x & 31) == 0) {
-    const long long *w_ = warp_totals[threadIdx.x >> 5];
-    if (w_[0]) atomicAdd((unsigned long long *)p.totals + 0, (unsigned long long)w_[0]);
-    if (w_[1]) atomicAdd((unsigned long long *)p.totals + 1, (unsigned long long)w_[1]);
-    if (w_[2]) atomicAdd((unsigned long long *)p.totals + 2, (unsigned long long)w_[2]);
-    if (w_[3]) atomicMax(p.totals + 3, w_[3]);
+  if (p.totals != nullptr && lane_id == 0) {
+    long long w0, w1, w2, w3;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(tot_addr) : "memory");
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "r"(tot_addr + 16u) : "memory");
+    if (w0) atomicAdd((unsigned long long *)p.totals + 0, (unsigned long long)w0);
+    if (w1) atomicAdd((unsigned long long *)p.totals + 1, (unsigned long long)w1);
+    if (w2) atomicAdd((unsigned long long *)p.totals + 2, (unsigned long long)w2);
+    if (w3) atomicMax(p.totals + 3, w3);
   }
 }
 

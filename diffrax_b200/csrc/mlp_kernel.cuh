@@ -402,7 +402,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w, const __g
     // ---- refill (claims are made by the quarter-0 thread of each row and shared through smem) ----
     if (!exhausted) {
       if (!mma_warp && part == 0) {
-        const long long got = claim_work(!active, p.work_counter);
+        const long long got = claim_work(!active, p.work_counter, (int)(threadIdx.x & 31));
         sm.idx[row] = got;
       }
       __syncthreads();

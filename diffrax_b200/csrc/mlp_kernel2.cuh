@@ -242,7 +242,7 @@ mlp_tc2_kernel(const SolveParams<float> p, const float *__restrict__ w, const __
     // ---- refill (claims are made by the half-0 thread of each row and shared through smem); group-scoped barriers ----
     if (!exhausted) {
       if (!mma_warp && half == 0) {
-        const long long got = claim_work(!active, p.work_counter);
+        const long long got = claim_work(!active, p.work_counter, (int)(threadIdx.x & 31));
         sm.idx[g][row] = got;
       }
       named_bar_sync(bar_grp, kMlp2GroupThreads);
