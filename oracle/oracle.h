@@ -6,6 +6,8 @@
  * PARITY STATUS: "parity unpinned" at the north-star tolerances against a live
  * Diffrax: jax / equinox / optimistix are not importable in the authoring container
  *  and the reference ships no golden vectors for this path (§8c).
+ * baseline/ holds the live-reference arm (probe + case builder + gen_golden.py): wherever jax + diffrax
+ * are importable, tests/test_live_reference.py pins this oracle against Diffrax itself.
  * The oracle is pinned instead against every offline anchor the reference's tests
  * use: the Random123 threefry2x32 known-answer vectors, analytic solutions
  * (test_integrate.py:48-141, test_saveat_solution.py:29-195), scipy DOP853 on the

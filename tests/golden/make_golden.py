@@ -5,8 +5,9 @@ The reference (Diffrax) cannot be imported in the authoring container (no jax), 
 come from the CPU oracle, which tests/test_oracle_*.py pin to the reference's own offline anchors.
 They serve two purposes: (1) the oracle is regression-pinned to them (test_golden_oracle), and
 (2) the GPU parity tests compare the CUDA path against them without re-running anything.
-If a live Diffrax becomes available, regenerate with it (same keys) and the comparison tightens
-to reference-level parity.   Usage:  python tests/golden/make_golden.py
+Wherever a live Diffrax is importable, `python baseline/gen_golden.py` runs the SAME cases through the reference itself
+and writes tests/golden/diffrax_golden.npz, which tests/test_live_reference.py then pins the oracle to.
+Usage:  python tests/golden/make_golden.py
 """
 import os
 import sys
