@@ -231,8 +231,12 @@ template <class R> __device__ __forceinline__ int clip_find_idx(R t, const R *ts
 //   SPEC   (fp64 ODE SaveAt(t1) solves only) the controller configuration is known at compile time: PIDController with the
 //          default pure I-controller at the solver's order (the fast path) and no dtmin / dtmax.  Removes the uniform
 //          branches and parameter loads of the general controller from the step loop (C2: -2 % time).
-template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false, bool SPEC = false>
-__global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<R, Field, Solver, LEVY, RICH>())
+//   MOREB  extra CTAs per SM asked of ptxas on top of the default occupancy target (SPEC SaveAt(t1) kernels only): a batch
+//          that is a little larger than the default grid's lanes runs as ONE resident generation at the higher occupancy
+//          instead of one generation plus a mostly empty second one (the sharded 2^20 / 8 GPUs case: 131 072 trajectories
+//          vs 113 664 lanes at 6 CTAs/SM, 132 608 at 7)
+template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false, bool SPEC = false, int MOREB = 0>
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<R, Field, Solver, LEVY, RICH>() + MOREB)
 ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) {
   constexpr int D = Field::kDim;
   constexpr int S = Solver::S;

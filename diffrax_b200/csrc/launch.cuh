@@ -121,9 +121,18 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
 struct DeviceInfo { int sms; };
 int device_sm_count(int *sms);  // cached per device (api.cu)
 
-template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false, bool SPEC = false>
+// resident lanes of the persistent grid of one instantiation (no dynamic shared memory: the SaveAt(t1) ODE kernels)
+template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA, bool SPEC, int MOREB>
+long long resident_lanes(int sms) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ensemble_kernel<R, Field, Solver, LEVY, RICH, EXTRA, SPEC, MOREB>,
+                                                    kBlockThreads, 0) != cudaSuccess) return 0;
+  return (long long)sms * per_sm * kBlockThreads;
+}
+
+template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false, bool SPEC = false, int MOREB = 0>
 int launch_variant(SolveParams<R> &p, const typename Field::template P<R> &fp, cudaStream_t stream) {
-  auto kern = ensemble_kernel<R, Field, Solver, LEVY, RICH, EXTRA, SPEC>;
+  auto kern = ensemble_kernel<R, Field, Solver, LEVY, RICH, EXTRA, SPEC, MOREB>;
   int sms = 0;
   if (int rc = device_sm_count(&sms)) return rc;
   // SaveAt(dense=True): per-lane staging records for the warp-cooperative stores
@@ -245,7 +254,16 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
     }
   } else {
     if constexpr (kHasSpec) {
-      if (spec) rc = launch_variant<R, Field, Solver, LEVY, false, false, true>(p, fp, stream);
+      if (spec) {
+        // one resident generation if one more CTA per SM makes the whole batch fit (see MOREB)
+        int sms = 0;
+        if (int e = device_sm_count(&sms)) return e;
+        static const int env_moreb = [] { const char *e = getenv("DFX_MORE_BLOCKS"); return e ? atoi(e) : 1; }();
+        const long long base = resident_lanes<R, Field, Solver, LEVY, false, false, true, 0>(sms);
+        const long long more = env_moreb ? resident_lanes<R, Field, Solver, LEVY, false, false, true, 1>(sms) : 0;
+        if (p.n_traj > base && p.n_traj <= more) rc = launch_variant<R, Field, Solver, LEVY, false, false, true, 1>(p, fp, stream);
+        else rc = launch_variant<R, Field, Solver, LEVY, false, false, true>(p, fp, stream);
+      }
       else rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
     } else {
       rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);
