@@ -119,6 +119,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
 }
 
 struct DeviceInfo { int sms; };
+constexpr long long kMoreBlocksMaxGenerations = 1;  // see launch_solve: when the one-more-CTA instantiation is preferred
 int device_sm_count(int *sms);  // cached per device (api.cu)
 
 // resident lanes of the persistent grid of one instantiation (no dynamic shared memory: the SaveAt(t1) ODE kernels)
@@ -261,7 +262,11 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
         static const int env_moreb = [] { const char *e = getenv("DFX_MORE_BLOCKS"); return e ? atoi(e) : 1; }();
         const long long base = resident_lanes<R, Field, Solver, LEVY, false, false, true, 0>(sms);
         const long long more = env_moreb ? resident_lanes<R, Field, Solver, LEVY, false, false, true, 1>(sms) : 0;
-        if (p.n_traj > base && p.n_traj <= more) rc = launch_variant<R, Field, Solver, LEVY, false, false, true, 1>(p, fp, stream);
+        // fewer (and fuller) generations at the higher occupancy; with many generations the queue evens the tail out by
+        // itself and the default occupancy has the better per-warp throughput (C2 at 2^20: 2.97 vs 3.05 ms)
+        const bool fewer = base > 0 && more > base && p.n_traj > base &&
+                           (p.n_traj + more - 1) / more < (p.n_traj + base - 1) / base && (p.n_traj + more - 1) / more <= kMoreBlocksMaxGenerations;
+        if (env_moreb == 2 || (env_moreb == 1 && fewer)) rc = launch_variant<R, Field, Solver, LEVY, false, false, true, 1>(p, fp, stream);
         else rc = launch_variant<R, Field, Solver, LEVY, false, false, true>(p, fp, stream);
       }
       else rc = launch_variant<R, Field, Solver, LEVY, false>(p, fp, stream);

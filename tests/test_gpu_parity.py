@@ -1057,3 +1057,18 @@ def test_one_generation_occupancy_variant_gives_the_same_bits(dev):
     o = oracle.solve("lorenz", y0[:512], 0.0, 2.0, None, solver="dopri5", params=[10.0, 28.0, 8.0 / 3.0], rtol=1e-8, atol=1e-8)
     assert np.abs(to_np(a.stats["num_accepted_steps"])[:512] - o["stats"][:, 1]).max() <= 1
     assert relerr(to_np(a.ys)[:512], o["ys"]) < 1e-9
+
+
+def test_degenerate_batches(dev):
+    """Empty batch, max_steps = 0 and t0 == t1: no hang, the reference's results (nothing integrated; max_steps_reached only when
+    there was something left to integrate)."""
+    term, ctrl = dfx.ODETerm(dfx.fields.Lorenz()), dfx.PIDController(1e-6, 1e-6)
+    e = dfx.diffeqsolve(term, dfx.Dopri5(), 0.0, 1.0, None, torch.empty(0, 3, dtype=torch.float64, device=dev), stepsize_controller=ctrl)
+    assert e.ys.shape == (0, 1, 3) and e.result.shape == (0,)
+    y0 = torch.tensor(np.random.default_rng(0).uniform(1, 2, (70, 3)), device=dev)
+    z = dfx.diffeqsolve(term, dfx.Dopri5(), 0.0, 1.0, None, y0, stepsize_controller=ctrl, max_steps=0, throw=False)
+    assert bool((z.result == 1).all()) and bool((z.stats["num_steps"] == 0).all()) and torch.equal(z.ys[:, 0], y0)
+    s = dfx.diffeqsolve(term, dfx.Dopri5(), 0.5, 0.5, None, y0, stepsize_controller=ctrl)
+    assert bool((s.result == 0).all()) and bool((s.stats["num_steps"] == 0).all()) and torch.equal(s.ys[:, 0], y0)
+    sh = dfx.sharded_diffeqsolve(term, dfx.Dopri5(), 0.0, 1.0, None, y0, stepsize_controller=ctrl, max_steps=0, throw=False)
+    assert int(sh.stats["num_failed"]) == 70 and int(sh.stats["num_steps"]) == 0
