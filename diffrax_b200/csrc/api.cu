@@ -340,7 +340,7 @@ static int check_desc(const dfx_solve_desc *d) {
   if (d->n_traj < 0 || d->n_traj > 0x7fffffffLL || d->dim < 1 || d->dim > kMaxDim) { set_error("bad n_traj (0 .. 2^31-1 per call) / dim"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->dtype != DFX_F64 && d->dtype != DFX_F32) { set_error("bad dtype %d", d->dtype); return DFX_ERR_BAD_ARGUMENT; }
   if (d->n_traj > 0 && !d->y0) { set_error("y0 is null"); return DFX_ERR_BAD_ARGUMENT; }
-  if (!d->stats || !d->result) { set_error("stats / result buffers are required"); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->n_traj > 0 && (!d->stats || !d->result)) { set_error("stats / result buffers are required"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->max_steps < 0) { set_error("max_steps must be >= 0 (max_steps=None is not supported)"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->save_steps < 0) { set_error("save_steps must be >= 0"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->controller == DFX_CTRL_CONSTANT && is_nan(d->dt0)) {
@@ -383,8 +383,8 @@ static int check_desc(const dfx_solve_desc *d) {
     }
   }
   const int T = dfx_out_size(d);
-  if (T > 0 && (!d->ts_out || !d->ys_out)) { set_error("ts_out / ys_out are required (T_out = %d)", T); return DFX_ERR_BAD_ARGUMENT; }
-  if (d->save_dense && (!d->dense_ts || !d->dense_y0 || !d->dense_y1 || !d->dense_count)) {
+  if (d->n_traj > 0 && T > 0 && (!d->ts_out || !d->ys_out)) { set_error("ts_out / ys_out are required (T_out = %d)", T); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->n_traj > 0 && d->save_dense && (!d->dense_ts || !d->dense_y0 || !d->dense_y1 || !d->dense_count)) {
     set_error("dense buffers are required for SaveAt(dense=True)");
     return DFX_ERR_BAD_ARGUMENT;
   }
@@ -418,6 +418,10 @@ static int check_desc(const dfx_solve_desc *d) {
 
 int dfx_ensemble_solve(const dfx_solve_desc *d, void *cuda_stream) {
   if (int rc = check_desc(d)) return rc;
+  if (d->n_traj == 0) {  // an empty batch: nothing to integrate (the totals, if wanted, are zero)
+    if (d->totals) DFX_CUDA_OK(cudaMemsetAsync(d->totals, 0, 4 * sizeof(int64_t), (cudaStream_t)cuda_stream));
+    return 0;
+  }
   dfx_launcher_fn fn = find_launcher(d->field_id, d->dim, d->solver_id, d->dtype, d->levy_area);
   if (!fn) {
     set_error("no kernel registered for field %d dim %d solver %d dtype %d levy %d", d->field_id, d->dim,
@@ -732,6 +736,7 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
 
 int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
   if (int rc = check_desc(h)) return rc;
+  if (h->n_traj == 0) { if (h->totals) std::memset(h->totals, 0, 4 * sizeof(int64_t)); return 0; }
   if (dfx_device_count() <= device) { set_error("CUDA device %d not available", device); return DFX_ERR_NO_DEVICE; }
   DFX_CUDA_OK(cudaSetDevice(device));
   if (host_pipe_eligible(h)) return solve_host_pipelined(h, device);

@@ -37,6 +37,7 @@ constexpr int kMlpThreads = kMlpComputeThreads + 32;  // + the MMA-issuing warp
 constexpr int kMlpChunks = 4, kMlpChunk = 8;          // a thread's 32 hidden units in 4 chunks of 8 (one K = 8 step each)
 constexpr uint32_t kTmemCols = 512;
 
+constexpr int kMlpMaxStages = 7;  // tableaux registered for the MLP field: Tsit5, Dopri5 (7), Bosh3 (4), Heun (2)
 struct MlpSmem {
   float Bhi[kMlpW * kMlpW];     // W2 hi, canonical K-major no-swizzle: (n,k) -> (n/8)*1024 + (k/4)*32 + (n%8)*4 + (k%4)
   float Blo[kMlpW * kMlpW];
@@ -46,7 +47,8 @@ struct MlpSmem {
   float W3[kMlpW * kMlpD];     // transposed: W3t[o][c]
   float b3[kMlpD];
   float part[4][kMlpW][kMlpD];  // layer-3 partial sums of the four hidden-unit quarters
-  float k[14 * kMlpD][kMlpW];   // stage values k[i][c] per row (the 4 threads of a row write identical values), S <= 14
+  float k[4][kMlpMaxStages * kMlpD][kMlpW];  // stage values k[i][c]: one private copy per thread of a row (4 hidden-unit quarters),
+                                             // so every word has exactly one writer and one reader
   long long idx[kMlpW];
   unsigned long long mbar;
   unsigned long long mbar_w;    // completion of the TMA loads of the W2 image
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w, const __grid_constant__ CUtensorMap w2_map) {
   using R = float;
   constexpr int D = kMlpD, W = kMlpW, S = Solver::S;
+  static_assert(S <= kMlpMaxStages, "stage-value storage is sized for at most kMlpMaxStages stages");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   MlpSmem &sm = *reinterpret_cast<MlpSmem *>(smem_raw);
 
@@ -464,14 +467,14 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w, const __g
         for (int j = 0; j < i; ++j) {
           const R a = Solver::template a<R>(i, j);  // structural zeros contribute exact zeros
 #pragma unroll
-          for (int c = 0; c < D; ++c) yi[c] += a * sm.k[j * D + c][row];
+          for (int c = 0; c < D; ++c) yi[c] += a * sm.k[part][j * D + c][row];
         }
 #pragma unroll
         for (int c = 0; c < D; ++c) yi[c] = y[c] + yi[c];
       }
       eval(yi, fi);  // the field is autonomous: stage times do not enter
 #pragma unroll
-      for (int c = 0; c < D; ++c) sm.k[i * D + c][row] = control * fi[c];
+      for (int c = 0; c < D; ++c) sm.k[part][i * D + c][row] = control * fi[c];
     }
     if constexpr (Solver::kSsal) {
 #pragma unroll
@@ -482,7 +485,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w, const __g
       for (int j = 0; j < S; ++j) {
         const R b = Solver::template b_sol<R>(j);
 #pragma unroll
-        for (int c = 0; c < D; ++c) y1[c] += b * sm.k[j * D + c][row];
+        for (int c = 0; c < D; ++c) y1[c] += b * sm.k[part][j * D + c][row];
       }
 #pragma unroll
       for (int c = 0; c < D; ++c) y1[c] = y[c] + y1[c];
@@ -492,7 +495,7 @@ mlp_tc_kernel(const SolveParams<float> p, const float *__restrict__ w, const __g
     for (int j = 0; j < S; ++j) {
       const R b = Solver::template b_err<R>(j);
 #pragma unroll
-      for (int c = 0; c < D; ++c) yerr[c] += b * sm.k[j * D + c][row];
+      for (int c = 0; c < D; ++c) yerr[c] += b * sm.k[part][j * D + c][row];
     }
 
     if (run) {

@@ -32,7 +32,7 @@ struct MlpSmem2 {
   float W3[kMlpW * kMlpD];      // transposed: W3t[o][c]
   float b3[kMlpD];
   float part[kMlp2Groups][2][kMlpW][kMlpD];    // layer-3 partial sums of the two hidden-unit halves
-  float k[kMlp2Groups][14 * kMlpD][kMlpW];     // stage values per row (both threads of a row write identical values)
+  float k[kMlp2Groups][2][kMlpMaxStages * kMlpD][kMlpW];  // stage values: one private copy per thread of a row (2 halves)
   long long idx[kMlp2Groups][kMlpW];
   unsigned long long mbar_done[kMlp2Groups];
   unsigned long long mbar_empty[kMlp2Groups][kMlp2Slots];
@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kMlp2Threads, 1)
 mlp_tc2_kernel(const SolveParams<float> p, const float *__restrict__ w, const __grid_constant__ CUtensorMap w2_map) {
   using R = float;
   constexpr int D = kMlpD, W = kMlpW, S = Solver::S;
+  static_assert(S <= kMlpMaxStages, "stage-value storage is sized for at most kMlpMaxStages stages");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   MlpSmem2 &sm = *reinterpret_cast<MlpSmem2 *>(smem_raw);
 
@@ -113,7 +114,7 @@ mlp_tc2_kernel(const SolveParams<float> p, const float *__restrict__ w, const __
   const uint32_t mbar_done = smem_u32(&sm.mbar_done[g]);
   const uint64_t bdesc_hi = make_b_desc(smem_u32(sm.Bhi), 128, 4096), bdesc_lo = make_b_desc(smem_u32(sm.Blo), 128, 4096);
   uint32_t phase = 0;  // parity of both the done and the empty barriers: each completes exactly once per evaluation
-  float (*gk)[kMlpW] = sm.k[g];
+  float (*gk)[kMlpW] = sm.k[g][half];  // private to this thread: one writer, one reader per word
 
   // ---------------- the MMA warp's side of one MLP evaluation ----------------
   // chunk c: K-steps kk = 8 h + c (h = 0, 1) of B; A columns of ring slot c % 4: hi at 128 + 32 s + 8 h, lo 16 further
@@ -291,8 +292,8 @@ mlp_tc2_kernel(const SolveParams<float> p, const float *__restrict__ w, const __
     const R dt = st1 - st0;
     const R control = direction * dt;
     // The stage loop is rolled (one copy of the MLP evaluation in the instruction stream); the stage values therefore
-    // live in shared memory, one copy per row: the two threads of a row store bit-identical values to the same word and
-    // each reads back what it wrote itself, so no barrier is needed.
+    // live in shared memory, one private copy per thread (the two threads of a row compute identical values), so no
+    // barrier is needed and every word has exactly one writer.
     R y1[D], yerr[D], yi[D], fi[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) yi[c] = y[c];
