@@ -485,6 +485,7 @@ def measure(name, args, rank, local, world, dev, strong: bool, with_cpu: bool, s
 
 
 def run_ours(args):
+    import gc
     import torch
     import torch.distributed as dist
     from diffrax_b200 import _dist
@@ -497,6 +498,7 @@ def run_ours(args):
     strong = args.scaling == "strong"
     line = measure(args.workload, args, rank, local, world, dev, strong, with_cpu=True)
     if world > 1 and strong and not args.no_extras:
+        gc.collect(); torch.cuda.empty_cache()
         wk = measure(args.workload, args, rank, local, world, dev, False, with_cpu=False)
         if rank == 0:
             line["weak"] = {k: wk[k] for k in ("value", "unit", "ms_per_step", "kernel_ms_per_step", "steps")}
@@ -506,10 +508,11 @@ def run_ours(args):
         # the other BASELINE configs, same method, appended to the one JSON line
         extras = {}
         for name in ("c1", "c3", "c3_1e-4", "c4", "c5_heun", "c5_shark"):
+            gc.collect(); torch.cuda.empty_cache()        # the previous config's buffers (C3: 105 GB) go back to the driver first
             try:
                 extras[name] = measure(name, args, rank, local, world, dev, True, with_cpu=True, steps=min(args.steps, 10))
             except Exception as e:  # noqa: BLE001  (never lose the headline to an extra)
-                extras[name] = {"error": f"{type(e).__name__}: {e}"}
+                extras[name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
         line["config_results"] = extras
     if rank == 0:
         print(json.dumps(line), flush=True)
