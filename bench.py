@@ -438,6 +438,7 @@ def measure(name, args, rank, local, world, dev, strong: bool, with_cpu: bool, s
         y_blk = y0_host[hplan.lo:hplan.hi]
         h2d = y_blk.numel() * y_blk.element_size() + (0 if w["keys"] is None else n_local * 8)
         d2h = sum(int(t.numel() * t.element_size()) for t in (hl.ts, hl.ys, hl.result)) + 3 * int(hl.stats["num_steps"].numel()) * 4 + 8
+        hplan.close()
         del hplan, y0_host
 
     # ---- max over ranks ----
@@ -460,8 +461,10 @@ def measure(name, args, rank, local, world, dev, strong: bool, with_cpu: bool, s
             "config": {"workload": w["label"], "trajectories_total": n_total, "trajectories_per_gpu": n_local,
                        "accepted_steps_per_solve": acc, "attempted_steps_per_solve": att, "failed_trajectories": failed,
                        "l2": "flushed between timed steps (256 MiB write outside the per-step CUDA-event pairs)",
-                       "parallelism": f"trajectory-sharded x{world}; ONE all_gather of [finals | t_final | statistics] per solve, "
-                                      "inside the timed region" if world > 1 else "single GPU (no collective)"},
+                       "parallelism": (f"trajectory-sharded x{world}; gather of the finals "
+                                       + ("FUSED into the solve kernel (P2P stores into every rank's buffer over NVLink peer memory) + a 32-byte all_gather "
+                                          "of the in-kernel totals" if plan.peer is not None else "by ONE all_gather of [finals | t_final | statistics]")
+                                       + ", inside the timed region") if world > 1 else "single GPU (no collective)"},
             "e2e": ({"value": acc / (e2e_ms_max * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max, "statistic": "median of the per-step wall times, max over ranks",
                      "mean_ms_per_step": e2e_mean_ms_max, "call": "diffrax_b200.prepare_sharded(host buffers)(): H2D, kernel, D2H, all_gather, host read of the statistics"}
@@ -479,6 +482,7 @@ def measure(name, args, rank, local, world, dev, strong: bool, with_cpu: bool, s
                                    "sample": f"first {cpu_sample} trajectories of the batch, "
                                              + ("live Diffrax (jax.vmap, JAX CPU)" if kind == "reference" else f"oracle C port (live Diffrax: {why})")
                                              + f", {cpu_dt:.2f} s"}
+    plan.close()
     del plan, y0_dev, flush, sol
     torch.cuda.empty_cache()
     return res

@@ -70,6 +70,7 @@ def reduce_stats(stats: dict) -> dict:
 # --------------------------------------------------------------------------------------
 # Product-level sharded entry: the BASELINE configuration "N trajectories sharded across 1/2/4/8 B200"
 # --------------------------------------------------------------------------------------
+import ctypes as C
 import dataclasses
 from typing import Any, Optional
 
@@ -109,13 +110,90 @@ def _slice_terms(terms, lo, hi):
     return terms
 
 
-class ShardedSolve:
-    """A prepared sharded solve (see `prepare_sharded`): every call runs this rank's shard and then ONE collective - an
-    all_gather of a packed per-rank record [finals | t_final | 4 int64 totals] - so the gather of the final states and the
-    reduction of the statistics cost a single NCCL launch.  The solve kernel writes the finals AND
-    the ensemble totals (reduced in-kernel) straight into the record; nothing is staged or reduced in between."""
+class _DevBuf:
+    """A raw device allocation (dfx_peer_alloc / dfx_peer_open) exposed to torch through __cuda_array_interface__."""
 
-    def __init__(self, plan, lo, hi, n_total, d, dtype, device, group):
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = int(ptr), int(nbytes)
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def tensor(self, device):
+        return torch.as_tensor(self, device=device)
+
+
+class _PeerGather:
+    """The fused gather: every rank owns TWO global buffers [finals (N x d) | t_final (N)] in peer-mappable device memory
+    (CUDA IPC), maps its peers' buffers, and hands all of them to the solve kernel, which stores each trajectory's final
+    state into every rank's buffer (P2P stores over NVLink / NVSwitch) the moment the trajectory is finalised.  The transfer
+    overlaps the solve; afterwards a 32-byte all_gather of the in-kernel totals is both the barrier and the statistics
+    reduction.  The two buffers alternate between calls, so a rank that races ahead into the next solve writes the buffer its
+    peers are NOT reading."""
+
+    def __init__(self, n_total, d, dtype, device, group):
+        from . import _lib
+        self.L = _lib.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_total, self.d, self.dtype, self.device = n_total, d, dtype, device
+        es = torch.empty((), dtype=dtype).element_size()
+        self.nbytes = (n_total * (d + 1) * es + 255) // 256 * 256
+        self.own, handles = [], []
+        with torch.cuda.device(device):
+            for _ in range(2):
+                ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                _lib.check(self.L.dfx_peer_alloc(self.nbytes, C.byref(ptr), h))
+                self.own.append(ptr.value)
+                handles.append(h.raw)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, handles, group=group)
+            self.mapped = []          # [buffer][rank] -> device pointer valid here
+            self._opened = []
+            for b in range(2):
+                row = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        row.append(self.own[b])
+                    else:
+                        q = C.c_void_p()
+                        _lib.check(self.L.dfx_peer_open(gathered[r][b], C.byref(q)))
+                        row.append(q.value)
+                        self._opened.append(q.value)
+                self.mapped.append(row)
+        self.views = []
+        for b in range(2):
+            raw = _DevBuf(self.own[b], self.nbytes).tensor(device)
+            y = raw[: n_total * d * es].view(dtype).view(n_total, d)
+            t = raw[n_total * d * es: n_total * (d + 1) * es].view(dtype)
+            self.views.append((y, t, raw))
+        self.t_off = n_total * d * es
+        self.turn = 0
+
+    def bind(self, desc, lo, which):
+        desc.n_peers = self.world
+        desc.peer_row_offset = lo
+        for r in range(self.world):
+            desc.peer_y_final[r] = self.mapped[which][r]
+            desc.peer_t_final[r] = self.mapped[which][r] + self.t_off
+
+    def close(self):
+        for q in self._opened:
+            self.L.dfx_peer_close(q)
+        self._opened = []
+        for p_ in self.own:
+            self.L.dfx_peer_free(p_)
+        self.own = []
+
+
+class ShardedSolve:
+    """A prepared sharded solve (see `prepare_sharded`): every call runs this rank's shard and makes every rank see the final
+    states of the WHOLE batch plus the global step statistics.
+
+    gather="peer" (default on one node with world > 1): the all_gather of the finals is FUSED into the solve kernel - P2P
+    stores into every rank's buffer over NVLink as trajectories finish (`_PeerGather`) - and the only collective left is a
+    32-byte all_gather of the in-kernel totals, which doubles as the barrier.
+    gather="nccl": ONE all_gather of a packed per-rank record [finals | t_final | 4 int64 totals] after the kernel; the kernel
+    writes the finals and the totals straight into the record."""
+
+    def __init__(self, plan, lo, hi, n_total, d, dtype, device, group, gather="nccl"):
         self.plan, self.lo, self.hi, self.n_total, self.d, self.group = plan, lo, hi, n_total, d, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.spans = [shard_range(n_total, r, self.world) for r in range(self.world)]
@@ -131,18 +209,31 @@ class ShardedSolve:
         self.y_buf = self.send[: n * d * es].view(dtype).view(n, d)        # the kernel writes the finals straight into the record
         self.t_buf = self.send[self._off_t: self._off_t + n * es].view(dtype)
         self.totals = self.send[self._off_tot:].view(torch.int64)          # [sum steps, sum accepted, failed, max steps]
+        self.peer = None
+        if gather == "peer" and self.world > 1 and device.type == "cuda":
+            self.peer = _PeerGather(n_total, d, dtype, device, group)
+            self.tot_all = torch.empty(self.world * 4, dtype=torch.int64, device=device)
 
     def __call__(self, throw: bool = True) -> ShardedSolution:
         return self.gather(self.solve_local(throw=throw))
 
     def solve_local(self, throw: bool = True):
-        """This rank's block: one C-ABI call; the finals and the totals land in the packed record."""
+        """This rank's block: one C-ABI call; the finals and the totals land in the packed record (and, in peer mode, in
+        every rank's global buffer)."""
+        if self.peer is not None:
+            self.peer.turn ^= 1
+            self.peer.bind(self.plan.desc, self.lo, self.peer.turn)
         return self.plan(throw=throw)
 
     def gather(self, sol) -> ShardedSolution:
-        """The one collective of the path: all_gather of every rank's [finals | t_final | totals] record."""
+        """Make the global finals + statistics visible: a 32-byte all_gather (peer mode: barrier + totals) or the one
+        all_gather of every rank's [finals | t_final | totals] record."""
         d, es = self.d, self._es
-        if self.world > 1:
+        if self.peer is not None:
+            dist.all_gather_into_tensor(self.tot_all, self.totals, group=self.group)   # also orders every rank's P2P stores before the reads
+            y, t, _ = self.peer.views[self.peer.turn]
+            tot = self.tot_all.view(self.world, 4)
+        elif self.world > 1:
             dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
             rec = self.recv.view(self.world, self.rec)
             y = torch.cat([rec[r, : (h - l) * d * es].view(self.dtype).view(h - l, d) for r, (l, h) in enumerate(self.spans)], 0)
@@ -155,8 +246,13 @@ class ShardedSolve:
                  "max_steps_per_trajectory": tot[:, 3].max()}               # 0-d device tensors: no host sync here
         return ShardedSolution(sol, self.lo, self.hi, self.n_total, y, t, stats)
 
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
-def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, device=None, **kw) -> ShardedSolve:
+
+def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, device=None, gather=None, **kw) -> ShardedSolve:
     """`prepare` for the sharded configuration.  `y0` (and per-trajectory `t0` / `t1`, Brownian keys) describe the GLOBAL
     batch of N trajectories and are the same on every rank; rank r owns the contiguous block `shard_range(N, r, world)`.
     Host inputs (NumPy / CPU tensors) go through the host-buffer entry of the C ABI, CUDA tensors through the device entry;
@@ -178,9 +274,13 @@ def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, de
     dtype = y_loc.dtype if isinstance(y_loc, torch.Tensor) else getattr(torch, str(np.asarray(y_loc).dtype))
     if dtype not in (torch.float64, torch.float32):
         dtype = torch.float64
+    if gather is None:   # the fused peer gather on one node; DFX_GATHER=nccl selects the plain collective
+        gather = os.environ.get("DFX_GATHER", "peer" if (world > 1 and dist.get_backend(group) == "nccl") else "nccl")
+    if gather not in ("peer", "nccl"):
+        raise ValueError("gather must be 'peer' or 'nccl'")
     sh = ShardedSolve.__new__(ShardedSolve)
     # two-phase construction: the record buffers must exist before `prepare` binds them as final_out
-    ShardedSolve.__init__(sh, None, lo, hi, n_total, d, dtype, device, group)
+    ShardedSolve.__init__(sh, None, lo, hi, n_total, d, dtype, device, group, gather)
     sh.plan = _api.prepare(_slice_terms(terms, lo, hi), solver, _slice_rows(t0, lo, hi), _slice_rows(t1, lo, hi), dt0, y_loc, args,
                            device=device.index if device.index is not None else 0, final_out=(sh.y_buf, sh.t_buf, sh.totals), **kw)
     return sh

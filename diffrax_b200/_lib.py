@@ -64,6 +64,8 @@ class SolveDesc(C.Structure):
         ("y_final_device", C.c_void_p), ("t_final_device", C.c_void_p),
         ("totals", C.c_void_p), ("totals_device", C.c_void_p),
         ("dense_lazy_padding", C.c_int32),
+        ("n_peers", C.c_int32), ("peer_row_offset", C.c_int64),
+        ("peer_y_final", C.c_void_p * 8), ("peer_t_final", C.c_void_p * 8),
     ]
 
 
@@ -71,7 +73,7 @@ class SolveDesc(C.Structure):
 EXPORTS = [
     "dfx_abi_version", "dfx_last_error", "dfx_device_count", "dfx_num_stages", "dfx_solver_order",
     "dfx_field_dim", "dfx_has_kernel", "dfx_out_size", "dfx_ensemble_solve", "dfx_ensemble_solve_host",
-    "dfx_vbt_evaluate", "dfx_broadcast_device_scalar", "dfx_threefry2x32", "dfx_random_split", "dfx_random_normal", "dfx_dense_evaluate", "dfx_dense_derivative", "dfx_dense_pad",
+    "dfx_vbt_evaluate", "dfx_broadcast_device_scalar", "dfx_threefry2x32", "dfx_random_split", "dfx_random_normal", "dfx_dense_evaluate", "dfx_dense_derivative", "dfx_dense_pad", "dfx_peer_alloc", "dfx_peer_open", "dfx_peer_close", "dfx_peer_free",
     "dfx_measure_fma_peak", "dfx_measure_int_peak", "dfx_launch_count", "dfx_reset_launch_count",
     "dfx_register_launcher",
 ]
@@ -115,6 +117,10 @@ def lib():
     L.dfx_dense_derivative.argtypes = L.dfx_dense_evaluate.argtypes
     L.dfx_dense_pad.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]
+    L.dfx_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]
+    L.dfx_peer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.dfx_peer_close.argtypes = [C.c_void_p]
+    L.dfx_peer_free.argtypes = [C.c_void_p]
     L.dfx_measure_fma_peak.argtypes = [C.c_int, C.c_int]
     L.dfx_measure_fma_peak.restype = C.c_double
     L.dfx_measure_int_peak.argtypes = [C.c_int]

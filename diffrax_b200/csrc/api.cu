@@ -382,6 +382,9 @@ static int check_desc(const dfx_solve_desc *d) {
       return DFX_ERR_BAD_ARGUMENT;
     }
   }
+  if (d->n_peers < 0 || d->n_peers > DFX_MAX_PEERS) { set_error("n_peers must be 0 .. %d", DFX_MAX_PEERS); return DFX_ERR_BAD_ARGUMENT; }
+  for (int q = 0; q < d->n_peers; ++q)
+    if (!d->peer_y_final[q] || !d->peer_t_final[q]) { set_error("peer buffer %d is null", q); return DFX_ERR_BAD_ARGUMENT; }
   const int T = dfx_out_size(d);
   if (d->n_traj > 0 && T > 0 && (!d->ts_out || !d->ys_out)) { set_error("ts_out / ys_out are required (T_out = %d)", T); return DFX_ERR_BAD_ARGUMENT; }
   if (d->n_traj > 0 && d->save_dense && (!d->dense_ts || !d->dense_y0 || !d->dense_y1 || !d->dense_count)) {
@@ -502,6 +505,7 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
     d.t_final = dev_out(off(h->t_final, es), N * es);
   }
   d.y_final_device = d.t_final_device = nullptr;
+  d.peer_row_offset = h->peer_row_offset + lo;  // (the peer buffers are device pointers already: passed through)
   if (!rc) rc = dfx_ensemble_solve(&d, (void *)st);
   if (!rc)
     for (auto &c : d2h)
@@ -785,6 +789,26 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
   for (int i = 0; i < nstreams; ++i) cudaStreamDestroy(st[i]);
   return rc;
 }
+
+int dfx_peer_alloc(int64_t bytes, void **device_ptr, void *ipc_handle) {
+  if (bytes <= 0 || !device_ptr || !ipc_handle) { set_error("peer_alloc: bad argument"); return DFX_ERR_BAD_ARGUMENT; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  DFX_CUDA_OK(cudaMalloc(device_ptr, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, *device_ptr);
+  if (e != cudaSuccess) { cudaFree(*device_ptr); *device_ptr = nullptr; set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); return DFX_ERR_CUDA; }
+  std::memcpy(ipc_handle, &h, 64);
+  return 0;
+}
+int dfx_peer_open(const void *ipc_handle, void **device_ptr) {
+  if (!ipc_handle || !device_ptr) { set_error("peer_open: bad argument"); return DFX_ERR_BAD_ARGUMENT; }
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, ipc_handle, 64);
+  DFX_CUDA_OK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int dfx_peer_close(void *device_ptr) { if (device_ptr) DFX_CUDA_OK(cudaIpcCloseMemHandle(device_ptr)); return 0; }
+int dfx_peer_free(void *device_ptr) { if (device_ptr) DFX_CUDA_OK(cudaFree(device_ptr)); return 0; }
 
 int dfx_broadcast_device_scalar(int dtype, int64_t n, const void *src_device, void *dst_device, void *stream) {
   if (n <= 0) return 0;

@@ -113,6 +113,8 @@ struct SolveParams {
   int dense_lazy;    // SaveAt(dense): leave the unfilled tails unwritten (dfx_dense_pad fills them on demand)
   int dense_vec_ok;  // dense_y0 / dense_y1 / dense_k base pointers are 32-byte aligned (rows then are, when their size allows)
   R *y_final, *t_final;
+  // fused gather over peer memory (dfx_solve_desc.peer_*): final states / times also go to row peer_row0 + i of every peer buffer
+  int n_peers; long long peer_row0; R *peer_y[DFX_MAX_PEERS]; R *peer_t[DFX_MAX_PEERS];
   long long *totals;  // [4] or null: sums of attempted / accepted steps, failed trajectories, max steps of one trajectory (zeroed by the launcher)
   unsigned long long *work_counter;
   // Host-pipelined mode (dfx_ensemble_solve_host; SaveAt(t1=True) instantiation only): ONE launch over the whole batch
@@ -389,6 +391,18 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           for (int c = 0; c < D; ++c) p.y_final[idx * D + c] = y[c];
         }
         if (p.t_final) p.t_final[idx] = tprev * direction;
+        if (p.n_peers != 0) {
+          // the all_gather of the finals, fused: P2P stores over NVLink into every rank's global buffer (this rank's own
+          // included), issued as trajectories finish, so the transfer rides along with the solve
+          const long long g = p.peer_row0 + idx;
+#pragma unroll 1
+          for (int q = 0; q < p.n_peers; ++q) {
+            R *yq = p.peer_y[q] + g * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) yq[c] = y[c];
+            p.peer_t[q][g] = tprev * direction;
+          }
+        }
         if constexpr (!RICH) {
           if (p.pipe_done != nullptr) {  // release this trajectory's results; the last one of a chunk tells the host
             __threadfence();

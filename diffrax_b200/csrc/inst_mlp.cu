@@ -67,6 +67,11 @@ int launch_mlp(const dfx_solve_desc *d, void *stream_v) {
     }
     count_launch();
     DFX_CUDA_OK(cudaGetLastError());
+    if (p.n_peers != 0) {
+      if (!p.y_final || !p.t_final) { set_error("the MLP kernel's peer gather needs y_final / t_final buffers"); return DFX_ERR_BAD_ARGUMENT; }
+      peer_scatter_kernel<float><<<148, 256, 0, stream>>>(p.n_traj, kMlpD, p.y_final, p.t_final, p.n_peers, p.peer_row0, p);
+      count_launch();
+    }
     if (p.totals) {
       DFX_CUDA_OK(cudaMemsetAsync(p.totals, 0, 4 * sizeof(long long), stream));
       totals_from_stats_kernel<<<64, 256, 0, stream>>>(p.n_traj, p.stats, p.result, p.totals);

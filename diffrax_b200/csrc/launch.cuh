@@ -83,6 +83,8 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   p.dense_vec_ok = (((uintptr_t)d->dense_y0 | (uintptr_t)d->dense_y1 | (uintptr_t)d->dense_k) & 31u) == 0;
   p.y_final = (R *)d->y_final; p.t_final = (R *)d->t_final;
   p.totals = (long long *)d->totals;
+  p.n_peers = d->n_peers; p.peer_row0 = d->peer_row_offset;
+  for (int q = 0; q < DFX_MAX_PEERS; ++q) { p.peer_y[q] = (R *)d->peer_y_final[q]; p.peer_t[q] = (R *)d->peer_t_final[q]; }
   p.keys = d->bm_keys;
   p.reject_ts = nullptr; p.n_reject = d->store_rejected_steps > 0 ? d->store_rejected_steps : 0;
   p.state_in = (const R *)d->state_in; p.state_out = (R *)d->state_out; p.state_in_flags = d->state_in_flags;

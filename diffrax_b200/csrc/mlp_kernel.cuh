@@ -119,6 +119,19 @@ __global__ void totals_from_stats_kernel(long long n, const int *__restrict__ st
   }
 }
 
+// The fused peer gather for kernels that do not store to the peers themselves (the tensor-core kernels): one pass that copies
+// this rank's finals into row peer_row0 + i of every peer buffer (P2P stores over NVLink).
+template <class R>
+__global__ void peer_scatter_kernel(long long n, int d, const R *__restrict__ y_final, const R *__restrict__ t_final, int n_peers,
+                                    long long row0, SolveParams<R> p) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (int q = 0; q < n_peers; ++q) {
+      for (int c = 0; c < d; ++c) p.peer_y[q][(row0 + i) * d + c] = y_final[i * d + c];
+      p.peer_t[q][row0 + i] = t_final[i];
+    }
+  }
+}
+
 // ---- TMA staging of W2 ----
 // The 128x128 hidden-layer weights are split into TF32 hi / lo ONCE per launch by a small kernel that writes them to global
 // memory already in the shared-memory image the tensor core wants (canonical K-major no-swizzle UMMA layout: 8x4-element

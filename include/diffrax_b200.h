@@ -60,6 +60,7 @@ enum dfx_result { DFX_RESULT_SUCCESSFUL = 0, DFX_RESULT_MAX_STEPS_REACHED = 1,
                   DFX_RESULT_INTERNAL_ERROR = 6 };
 enum dfx_event { DFX_EVENT_NONE = 0, DFX_EVENT_AFFINE = 1, DFX_EVENT_STEADY_STATE = 2 };
 #define DFX_MAX_EVENTS 4
+#define DFX_MAX_PEERS 8
 
 enum dfx_error { DFX_OK = 0, DFX_ERR_BAD_ARGUMENT = -1, DFX_ERR_UNSUPPORTED = -2,
                  DFX_ERR_CUDA = -3, DFX_ERR_NO_DEVICE = -4 };
@@ -186,6 +187,17 @@ typedef struct dfx_solve_desc {
    * many records are valid; dfx_dense_evaluate / _derivative never read beyond them) and dfx_dense_pad() fills them on
    * demand.  At BASELINE config 3 the padding is 63 % of the bytes the eager layout writes. */
   int32_t dense_lazy_padding;
+
+  /* Fused gather of the final states over NVLink peer memory (multi-GPU, one process per GPU).  When
+   * n_peers > 0 the solve kernel stores every trajectory's final state / time, the moment it is finalised, into row
+   * (peer_row_offset + i) of EACH of the n_peers buffers below - device pointers valid on this device: this rank's own
+   * global buffer and its peers' buffers opened with dfx_peer_open (CUDA IPC; P2P stores travel over NVLink / NVSwitch).
+   * The all_gather of the finals thereby overlaps the solve; what remains after the kernel is a barrier.  [N_total, d] /
+   * [N_total] in the state dtype. */
+  int32_t n_peers;                       /* 0 = off; at most DFX_MAX_PEERS */
+  int64_t peer_row_offset;               /* first global row of this rank's block */
+  void *peer_y_final[8];                 /* DFX_MAX_PEERS == 8 */
+  void *peer_t_final[8];
 } dfx_solve_desc;
 
 /* ---- library ---- */
@@ -251,6 +263,15 @@ int dfx_broadcast_device_scalar(int dtype, int64_t n, const void *src_device, vo
 /* fills the unfilled tails of dense buffers produced with dense_lazy_padding = 1 with +inf (device pointers) */
 int dfx_dense_pad(int dtype, int solver_id, int64_t n_traj, int dim, int max_steps, void *dense_ts, void *dense_y0,
                   void *dense_y1, void *dense_k, const int32_t *dense_count, void *cuda_stream);
+
+/* Peer memory for the fused gather (dfx_solve_desc.peer_*): a device allocation that other processes of the same node can
+ * map.  dfx_peer_alloc: cudaMalloc on the current device + its 64-byte CUDA IPC handle (send it to the peers by any
+ * means, e.g. torch.distributed.all_gather_object); dfx_peer_open: map a peer's allocation into this process (peer access
+ * enabled lazily); dfx_peer_close / dfx_peer_free undo them. */
+int dfx_peer_alloc(int64_t bytes, void **device_ptr, void *ipc_handle_64_bytes);
+int dfx_peer_open(const void *ipc_handle_64_bytes, void **device_ptr);
+int dfx_peer_close(void *device_ptr);
+int dfx_peer_free(void *device_ptr);
 
 /* measured FMA-pipe peaks for the roofline denominators (dependent-free FMA chains);
  * returns TFLOP/s (2 flop per FMA) or a negative dfx_error. */

@@ -1072,3 +1072,17 @@ def test_degenerate_batches(dev):
     assert bool((s.result == 0).all()) and bool((s.stats["num_steps"] == 0).all()) and torch.equal(s.ys[:, 0], y0)
     sh = dfx.sharded_diffeqsolve(term, dfx.Dopri5(), 0.0, 1.0, None, y0, stepsize_controller=ctrl, max_steps=0, throw=False)
     assert int(sh.stats["num_failed"]) == 70 and int(sh.stats["num_steps"]) == 0
+
+
+def test_fused_peer_gather_two_gpus():
+    """The fused gather (finals stored into every rank's buffer by the solve kernel over NVLink peer memory, then a 32-byte
+    all_gather) against the NCCL record gather and a single-GPU solve: tools/peer_gather_check.py under torchrun, 2 ranks."""
+    import socket
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on one node")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "tools", "peer_gather_check.py")], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "peer gather ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
