@@ -211,8 +211,19 @@ class ShardedSolve:
         self.totals = self.send[self._off_tot:].view(torch.int64)          # [sum steps, sum accepted, failed, max steps]
         self.peer = None
         if gather == "peer" and self.world > 1 and device.type == "cuda":
-            self.peer = _PeerGather(n_total, d, dtype, device, group)
-            self.tot_all = torch.empty(self.world * 4, dtype=torch.int64, device=device)
+            # every rank must end up in the same mode: agree on whether peer memory could be set up everywhere
+            # (it cannot across nodes, or where CUDA IPC / P2P access is unavailable) and fall back to the NCCL record together
+            try:
+                peer, ok = _PeerGather(n_total, d, dtype, device, group), 1
+            except Exception as e:  # noqa: BLE001
+                peer, ok, self.peer_error = None, 0, f"{type(e).__name__}: {e}"
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag[0]) == 1:
+                self.peer = peer
+                self.tot_all = torch.empty(self.world * 4, dtype=torch.int64, device=device)
+            elif peer is not None:
+                peer.close()
 
     def __call__(self, throw: bool = True) -> ShardedSolution:
         return self.gather(self.solve_local(throw=throw))
@@ -247,9 +258,16 @@ class ShardedSolve:
         return ShardedSolution(sol, self.lo, self.hi, self.n_total, y, t, stats)
 
     def close(self):
-        if self.peer is not None:
+        """Unmap the peers' buffers and free this rank's (peer mode); safe to call more than once."""
+        if getattr(self, "peer", None) is not None:
             self.peer.close()
             self.peer = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
 
 def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, device=None, gather=None, **kw) -> ShardedSolve:
