@@ -107,17 +107,15 @@ def test_golden_cases_device_path(name, dev):
     sol = run_case(kw, dev)
     f32 = np.dtype(kw.get("dtype", np.float64)) == np.float32
     tol = RTOL32 if f32 else RTOL64
-    if name.startswith("c3_"):
-        # Arenstorf orbit: the flow map's condition number over this arc is ~1e6 (lunar fly-by at distance 6e-3),
-        # so 1-ulp differences (FMA contraction on the GPU vs none in the oracle) surface at ~1e-10; see DESIGN.md.
-        tol = 1e-9
+    # (c3: the Arenstorf arc has a flow-map condition number of ~1e6, so 1-ulp differences surface at ~7e-11 - measured,
+    # tools/parity_report.py / profiles/r02_parity_report.txt - which still is inside the north star's 1e-10)
     if name == "ou_heun_adaptive_f64":
         # adaptive stepping driven by a Brownian path is chaotic in the step times: a 1-ulp change of `safety`
         # (or of pow()) moves the result by up to ~5e-7 in the ORACLE itself (tests/test_oracle_ode.py shows it)
         tol = 5e-6
     st = stats_np(sol)
     gst = GOLD[f"{name}/stats"]
-    assert np.abs(st[:, 1] - gst[:, 1]).max() <= (2 if f32 else 1), "accepted-step counts differ by more than +-1"
+    assert np.abs(st[:, 1] - gst[:, 1]).max() <= (1 if f32 else 0), "accepted-step counts: equal in fp64, within +-1 in fp32"
     same = np.all(st == gst, axis=1)
     assert same.mean() >= (0.5 if f32 else 0.98), same.mean()
     assert np.array_equal(to_np(sol.result)[same], GOLD[f"{name}/result"][same])
@@ -984,7 +982,18 @@ def test_dense_output_properties_c3_shape(dev):
     sl = slice(100, 100 + 64)
     o = oracle.solve("cr3bp", y0[sl], 0.0, t1, None, solver="dopri8", params=[0.012277471], rtol=1e-12, atol=1e-12, max_steps=ms)
     good = (o["result"] == 0) & to_np(ok)[sl]
-    assert relerr(to_np(sol.ys)[sl][good], o["ys"][good]) < 1e-6             # conditioning of the orbit ~1e6
+    # One full Arenstorf period passes the Moon at distance ~6e-3 twice: the flow map amplifies a 1-ulp perturbation by ~1e6 and
+    # more.  Measured per trajectory, not argued: the oracle rebuilt with FMA contraction allowed (oracle.rounding("fma")) moves
+    # these same trajectories; the CUDA path may exceed the north star's 1e-10 only in proportion to that measured sensitivity.
+    with oracle.rounding("fma"):
+        o2 = oracle.solve("cr3bp", y0[sl], 0.0, t1, None, solver="dopri8", params=[0.012277471], rtol=1e-12, atol=1e-12, max_steps=ms)
+    good &= (o2["result"] == 0)
+    scale = np.abs(o["ys"]) + 1e-3 * np.abs(o["ys"][good]).max()
+    err = (np.abs(to_np(sol.ys)[sl] - o["ys"]) / scale).max(axis=(1, 2))[good]
+    sens = (np.abs(o2["ys"] - o["ys"]) / scale).max(axis=(1, 2))[good]
+    assert np.all(err < np.maximum(RTOL64, 16 * sens)), (err.max(), sens.max())
+    assert err.max() < 1e-9 and (err < RTOL64).mean() > 0.9
+    print(f"C3 full period: max rel err {err.max():.2e}, oracle FMA sensitivity max {sens.max():.2e}, {100 * (err < RTOL64).mean():.1f}% within 1e-10")
 
 
 @pytest.mark.parametrize("host", [False, True])
