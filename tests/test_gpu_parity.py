@@ -1095,3 +1095,31 @@ def test_fused_peer_gather_two_gpus():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(root, "tools", "peer_gather_check.py")], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "peer gather ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("solver", ["tsit5", "dopri5", "dopri8", "bosh3"])
+def test_every_solver_dt0_none(dev, solver):
+    """dt0=None: the reference's first trial step is the constant 0.01.  For a high-order pair that step's error
+    estimate is at rounding-noise level, so its step-size factor - not the counts - differs between roundings; measured against
+    the oracle's own FMA-contracted build: accepted counts within +-1, states within 1e-10 or 64x the measured sensitivity."""
+    rng = np.random.default_rng(11)
+    n = 256
+    y0 = rng.uniform(-2, 2, (n, 2))
+    kw = dict(field="forced_osc", params=[1.0, 0.7, 2.0], solver=solver, y0=y0, t0=0.0, t1=3.0, dt0=None, rtol=1e-7, atol=1e-9,
+              save_t1=True, max_steps=4096)
+    o, sol = _oracle(kw), run_case(kw, dev)
+    with oracle.rounding("fma"):
+        o2 = _oracle(kw)
+    st = stats_np(sol)
+    assert np.abs(st[:, 1] - o["stats"][:, 1]).max() <= 1
+    same = np.all(st == o["stats"], axis=1) & np.all(o2["stats"] == o["stats"], axis=1)
+    assert same.mean() > 0.9, same.mean()
+    scale = np.abs(o["ys"]) + 1e-3 * np.abs(o["ys"]).max()
+    err = (np.abs(to_np(sol.ys) - o["ys"]) / scale).max(axis=(1, 2))[same]
+    sens = (np.abs(o2["ys"] - o["ys"]) / scale).max(axis=(1, 2))[same]
+    print(f"{solver}: dt0=None max rel err {err.max():.2e}, oracle FMA sensitivity max {sens.max():.2e}, same stats {same.mean():.3f}")
+    # (one alternative rounding is ONE sample of a trajectory's sensitivity, so the bound uses the ensemble's largest:
+    #  measured - tsit5 / dopri5 / bosh3 ~1e-13 against ~1e-13; dopri8 6.6e-10 against 3.9e-11, the 8th-order pair's first
+    #  0.01 step having an error estimate below rounding noise)
+    assert err.max() < max(RTOL64, 64 * sens.max()), (err.max(), sens.max())
+    assert relerr(to_np(sol.ys), o["ys"]) < 0.1 * kw["rtol"]
