@@ -752,9 +752,17 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
     const int64_t v = atoll(e);
     if (v >= 1 && !h->save_dense) nchunks = v > h->n_traj ? (h->n_traj > 0 ? h->n_traj : 1) : v;
   }
-  cudaStream_t st[2];
+  // two non-blocking streams per host thread and device, created once (creating / destroying them costs more than the
+  // copies of a small ensemble)
+  struct ChunkStreams { int device = -1; cudaStream_t s[2] = {nullptr, nullptr}; };
+  static thread_local ChunkStreams cs;
+  if (cs.device != device) {
+    for (cudaStream_t &x : cs.s) { if (x) cudaStreamDestroy(x); x = nullptr; }
+    for (cudaStream_t &x : cs.s) DFX_CUDA_OK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+    cs.device = device;
+  }
+  cudaStream_t st[2] = {cs.s[0], cs.s[1]};
   const int nstreams = nchunks > 1 ? 2 : 1;
-  for (int i = 0; i < nstreams; ++i) DFX_CUDA_OK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
   std::vector<void *> allocs[2];
   const bool want_totals = h->totals || h->totals_device;
   // per-chunk totals land in PINNED memory: a D2H copy into pageable memory would block the host and serialise the chunks
@@ -786,7 +794,6 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
       if (e != cudaSuccess) { set_error("totals H2D failed: %s", cudaGetErrorString(e)); rc = DFX_ERR_CUDA; }
     }
   }
-  for (int i = 0; i < nstreams; ++i) cudaStreamDestroy(st[i]);
   return rc;
 }
 
