@@ -66,3 +66,24 @@ def test_jax_binding_module_is_syntactically_valid():
         import pytest
         with pytest.raises(ImportError):
             import diffrax_b200.jax_ffi  # noqa: F401
+
+
+def test_python_binding_matches_the_handler_signature():
+    """diffrax_b200/jax_ffi.py passes exactly the attributes the C++ binding declares (same names), nine operands and twelve
+    results for the solve, six operands and one result for the dense evaluation."""
+    import re
+    src = open(os.path.join(ROOT, "diffrax_b200", "csrc", "ffi", "xla_ffi_shim.cc")).read()
+    py = open(os.path.join(ROOT, "diffrax_b200", "jax_ffi.py")).read()
+    solve_bind = src[src.index("#define DFX_BIND_SOLVE"):src.index("#define DFX_BIND_DENSE")]
+    dense_bind = src[src.index("#define DFX_BIND_DENSE"):src.index("XLA_FFI_DEFINE_HANDLER_SYMBOL(DfxEnsembleSolveF64")]
+    attrs = re.findall(r'\.Attr<[^>]+>+\("(\w+)"\)', solve_bind)
+    call = py[py.index("outs = call("):py.index("ts_o, ys_o, stats")]
+    kwargs = re.findall(r"\b(\w+)=", call)
+    assert attrs and sorted(set(kwargs)) == sorted(attrs), (set(attrs) ^ set(kwargs))
+    assert solve_bind.count(".Arg<") == 9 and solve_bind.count(".Ret<") == 12
+    out_types = py[py.index("out_types = ("):py.index('name = "DfxEnsembleSolveF64"')]
+    assert out_types.count("S(") == 12
+    dattrs = re.findall(r'\.Attr<[^>]+>+\("(\w+)"\)', dense_bind)
+    dcall = py[py.index("return call(dense["):py.index("def lorenz_dopri5_example")]
+    assert sorted(re.findall(r"\b(\w+)=", dcall)) == sorted(dattrs)
+    assert dense_bind.count(".Arg<") == 6 and dense_bind.count(".Ret<") == 1
