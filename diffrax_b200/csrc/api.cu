@@ -479,7 +479,13 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
   d.ys_out = dev_out(off(h->ys_out, T * D * es), N * T * D * es);
   d.stats = (int32_t *)dev_out(off(h->stats, 12), N * 3 * 4);
   d.result = (int32_t *)dev_out(off(h->result, 4), N * 4);
-  d.totals = (int64_t *)dev_out(chunk_totals, chunk_totals ? 4 * sizeof(int64_t) : 0);  // per chunk; combined by the caller
+  if (lo == 0 && cnt == h->n_traj && h->totals_device) {
+    // a single chunk: the kernel accumulates straight into the caller's device words (no host round trip)
+    d.totals = h->totals_device;
+    if (h->totals) d2h.emplace_back((void *)h->totals, (void *)h->totals_device, 4 * sizeof(int64_t));
+  } else {
+    d.totals = (int64_t *)dev_out(chunk_totals, chunk_totals ? 4 * sizeof(int64_t) : 0);  // per chunk; combined by the caller
+  }
   d.totals_device = nullptr;
   d.save_count = (int32_t *)dev_out(off(h->save_count, 4), N * 4);
   if (h->save_dense) {
@@ -782,7 +788,7 @@ int dfx_ensemble_solve_host(const dfx_solve_desc *h, int device) {
     cudaError_t e = cudaStreamSynchronize(st[i]);
     if (!rc && e != cudaSuccess) { set_error("stream sync failed: %s", cudaGetErrorString(e)); rc = DFX_ERR_CUDA; }
   }
-  if (want_totals && !rc) {  // combine the chunks' totals: sums, and the max of the per-trajectory maxima
+  if (want_totals && !rc && !(nchunks == 1 && h->totals_device)) {  // combine the chunks' totals: sums, and the max of the per-trajectory maxima
     int64_t tot[4] = {0, 0, 0, 0};
     for (int64_t c = 0; c < nchunks; ++c) {
       for (int k = 0; k < 3; ++k) tot[k] += chunk_totals[4 * (size_t)c + k];
