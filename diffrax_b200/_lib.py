@@ -23,7 +23,7 @@ SOLVER_IDS = {"tsit5": 0, "dopri5": 1, "dopri8": 2, "heun": 3, "bosh3": 4, "midp
               "ralston": 6, "euler": 7, "shark": 8}
 HALF_SOLVER = 0x100  # DFX_HALF_SOLVER: HalfSolver(inner) = HALF_SOLVER | inner id
 FIELD_IDS = {"decay": 0, "lotka_volterra": 1, "lorenz": 2, "cr3bp": 3, "mlp": 4, "ou": 5,
-             "forced_osc": 6, "vdp": 7}
+             "forced_osc": 6, "vdp": 7, "gbm": 8}
 FIELD_OU_MATRIX = 16   # + m: OU drift with a constant [d, m] diffusion matrix
 
 

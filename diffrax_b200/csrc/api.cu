@@ -407,6 +407,10 @@ static int check_desc(const dfx_solve_desc *d) {
       set_error("the OU functor with a %d-dimensional state needs VirtualBrownianTree(shape=(%d,))", d->dim, d->dim);
       return DFX_ERR_BAD_ARGUMENT;
     }
+    if (d->field_id == DFX_FIELD_GBM && (d->solver_id & ~DFX_HALF_SOLVER) == DFX_SHARK) {
+      set_error("ShARK is an additive-noise SRK (shark.py:10-30): the diffusion of this field depends on y");
+      return DFX_ERR_BAD_ARGUMENT;
+    }
     if (!(d->bm_t0 < d->bm_t1)) { set_error("t0 must be strictly less than t1"); return DFX_ERR_BAD_ARGUMENT; }  // tree.py:281
     if ((d->solver_id & ~DFX_HALF_SOLVER) == DFX_SHARK && d->levy_area != DFX_LEVY_SPACE_TIME) {
       set_error("The Brownian increment does not have the minimal Levy Area SpaceTimeLevyArea.");  // srk.py:391-395

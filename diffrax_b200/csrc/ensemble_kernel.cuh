@@ -64,6 +64,9 @@ template <class F> struct NoiseDim<F, std::void_t<decltype(F::kNoise)>> { static
 // matrix-valued diffusion: Field::noise_prod(fp, t, W[NW], c) = row c of g(t) . W instead of the scalar g(t) * W[c]
 template <class F, class = void> struct MatrixNoise { static constexpr bool value = false; };
 template <class F> struct MatrixNoise<F, std::void_t<decltype(F::kMatrixNoise)>> { static constexpr bool value = F::kMatrixNoise; };
+// state-dependent (multiplicative) diffusion: Field::noise_prod(fp, t, y, W[NW], c) = component c of g(t, y) . W
+template <class F, class = void> struct StateNoise { static constexpr bool value = false; };
+template <class F> struct StateNoise<F, std::void_t<decltype(F::kStateNoise)>> { static constexpr bool value = F::kStateNoise; };
 template <class T, class = void> struct IsHalf { static constexpr bool value = false; };
 template <class I> struct IsHalf<HalfOf<I>> { static constexpr bool value = true; };
 template <class T> struct InnerId { static constexpr int value = T::kId; };
@@ -639,8 +642,9 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           auto Hc = [&](int c) { return Hv[NW == 1 ? 0 : (c < NW ? c : 0)]; };
           // ControlTerm.prod (_term.py:417-427): g(t) . X for component c, X = W or H.  Scalar / diagonal diffusion: g(t) X_c;
           // matrix diffusion: tensordot over the Brownian axis
-          [[maybe_unused]] auto gprod = [&](R t, const R (&X)[NW], int c) -> R {
+          [[maybe_unused]] auto gprod = [&](R t, const R (&yy)[D], const R (&X)[NW], int c) -> R {
             if constexpr (!SDE) return R(0);
+            else if constexpr (StateNoise<Field>::value) return Field::template noise_prod<R>(fp, t, yy, X, c);  // g(t, y) . X
             else if constexpr (MatrixNoise<Field>::value) return Field::template noise_prod<R>(fp, t, X, c);
             else return Field::template diffusion<R>(fp, t) * X[NW == 1 ? 0 : (c < NW ? c : 0)];
           };
@@ -665,7 +669,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   #pragma unroll
               for (int c = 0; c < D; ++c) {
                 R kk = control * fi[c];
-                if constexpr (SDE) kk = kk + gprod(st0, Wv, c);  // MultiTerm.vf_prod (_term.py:711-722)
+                if constexpr (SDE) kk = kk + gprod(st0, y, Wv, c);  // MultiTerm.vf_prod (_term.py:711-722)
                 k[0][c] = kk;
               }
             }
@@ -700,7 +704,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
                   if (i == S - 1) continue;  // the last stage value is only read by the error estimate, through f_last below
                 }
                 R kk = control * fi[c];
-                if constexpr (SDE) kk = kk + gprod(ti, Wv, c);
+                if constexpr (SDE) kk = kk + gprod(ti, yi, Wv, c);
                 k[i][c] = kk;
               }
             }
@@ -743,7 +747,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   #pragma unroll
             for (int c = 0; c < D; ++c) {
               R kk = (direction * dt) * f0[c];
-              if constexpr (SDE) kk = kk + gprod(st0, Wv, c);
+              if constexpr (SDE) kk = kk + gprod(st0, y, Wv, c);
               k[0][c] = kk;
               y1[c] = y[c] + kk;
               yerr[c] = R(0);
@@ -754,8 +758,8 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
             if constexpr (SDE) {
               const R h = dt;
               // w_kg = g(t0) . W, h_kg = g(t0) . H (441-447); g_delta = (g(t1) - g(t0)) / 2 applied to W - 2 H (612-618)
-              auto w_kg = [&](int c) { return gprod(st0, Wv, c); };
-              auto h_kg = [&](int c) { return gprod(st0, Hv, c); };
+              auto w_kg = [&](int c) { return gprod(st0, y, Wv, c); };
+              auto h_kg = [&](int c) { return gprod(st0, y, Hv, c); };
               auto time_var = [&](int c) -> R {
                 if constexpr (MatrixNoise<Field>::value) {  // constant matrix: g_delta = 0.5 (G - G) = 0 exactly, so prod(g_delta, .) = 0
                   return R(0);

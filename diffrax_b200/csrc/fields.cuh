@@ -188,6 +188,28 @@ struct OuMatrixField {
   }
 };
 
+// Geometric Brownian motion, dy = mu y dt + sigma y dW: STATE-DEPENDENT (multiplicative) diagonal diffusion,
+// ControlTerm(lambda t, y, args: sigma * y, bm) with a scalar Brownian motion driving every component (tensordot with a 0-d
+// control).  Heun converges to the Stratonovich solution (heun.py:24-33); ShARK / SRK need additive noise and are refused.
+template <int D>
+struct GbmField {
+  static constexpr int kId = DFX_FIELD_GBM;
+  static constexpr int kDim = D;
+  static constexpr bool kStateNoise = true;
+  static constexpr bool kSde = true;
+  static constexpr int kNumParams = 2;
+  template <class R> struct P { R mu, sigma; };
+  template <class R> static P<R> make(const double *p, int, const void *) { return P<R>{(R)p[0], (R)p[1]}; }
+  template <class R>
+  static __device__ __forceinline__ void eval(const P<R> &p, R, const R (&y)[D], R (&f)[D]) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) f[c] = p.mu * y[c];
+  }
+  template <class R> static __device__ __forceinline__ R noise_prod(const P<R> &p, R, const R (&y)[D], const R (&w)[1], int c) {
+    return (p.sigma * y[c]) * w[0];
+  }
+};
+
 // Neural-ODE vector field (BASELINE config 4): eqx.nn.MLP(d -> W -> W -> d) with softplus hidden activations and
 // a tanh output (docs/examples/neural_ode.ipynb cell 5; benchmarks/small_neural_ode.py:25-28), evaluated per thread
 // on the FP32 CUDA cores.  This is the exact-fp32 reference implementation of the field inside the generic ensemble

@@ -119,6 +119,19 @@ class OrnsteinUhlenbeck(Field):
         return self.p
 
 
+class GeometricBrownianMotion(Field):
+    """dy = mu y dt + sigma y dW: state-dependent (multiplicative) diagonal diffusion with a scalar Brownian motion -
+    ``ControlTerm(lambda t, y, args: sigma * y, VirtualBrownianTree(..., shape=(), ...))``.  Euler / Heun (Heun converges to the
+    Stratonovich solution); kernels for state dimension 1 and 2."""
+    name, dim, is_sde = "gbm", 0, True
+
+    def __init__(self, mu=0.1, sigma=0.2):
+        self.p = [float(mu), float(sigma)]
+
+    def params(self):
+        return self.p
+
+
 class OrnsteinUhlenbeckMatrix(Field):
     """dy = theta (mu - y) dt + G dW with a constant ``[d, m]`` diffusion MATRIX ``G`` and an m-dimensional Brownian motion:
     ``ControlTerm(lambda t, y, args: G, VirtualBrownianTree(..., shape=(m,), ...))``, whose product is

@@ -46,6 +46,7 @@ enum dfx_controller { DFX_CTRL_CONSTANT = 0, DFX_CTRL_PID = 1 };
 enum dfx_field { DFX_FIELD_DECAY = 0, DFX_FIELD_LOTKA_VOLTERRA = 1, DFX_FIELD_LORENZ = 2,
                  DFX_FIELD_CR3BP = 3, DFX_FIELD_MLP = 4, DFX_FIELD_OU = 5,
                  DFX_FIELD_FORCED_OSC = 6, DFX_FIELD_VDP = 7,
+                 DFX_FIELD_GBM = 8,        /* geometric Brownian motion: dy = mu y dt + sigma y dW (state-dependent diffusion) */
                  DFX_FIELD_OU_MATRIX = 16, /* + m (1..4): OU drift with a constant [d, m] diffusion matrix, params [theta, mu, G] */
                  DFX_FIELD_USER = 1000 };
 

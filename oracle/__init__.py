@@ -26,7 +26,7 @@ F64, F32 = 0, 1
 SOLVERS = {"tsit5": 0, "dopri5": 1, "dopri8": 2, "heun": 3, "bosh3": 4, "midpoint": 5,
            "ralston": 6, "euler": 7, "shark": 8}
 FIELDS = {"decay": 0, "lotka_volterra": 1, "lorenz": 2, "cr3bp": 3, "mlp": 4, "ou": 5,
-          "forced_osc": 6, "vdp": 7, "ou_matrix2": 18, "ou_matrix3": 19, "callback": 100}
+          "forced_osc": 6, "vdp": 7, "gbm": 8, "ou_matrix2": 18, "ou_matrix3": 19, "callback": 100}
 LEVY = {None: 0, "none": 0, "bi": 1, "brownian_increment": 1, "stla": 2, "space_time": 2}
 CTRL_CONSTANT, CTRL_PID = 0, 1
 

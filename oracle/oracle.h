@@ -40,6 +40,7 @@ enum { ORC_CTRL_CONSTANT = 0, ORC_CTRL_PID = 1 };
 enum { ORC_FIELD_DECAY = 0, ORC_FIELD_LOTKA_VOLTERRA = 1, ORC_FIELD_LORENZ = 2,
        ORC_FIELD_CR3BP = 3, ORC_FIELD_MLP = 4, ORC_FIELD_OU = 5, ORC_FIELD_FORCED_OSC = 6,
        ORC_FIELD_VDP = 7,
+       ORC_FIELD_GBM = 8,        /* dy = mu y dt + sigma y dW: state-dependent diagonal diffusion, params [mu, sigma] */
        ORC_FIELD_OU_MATRIX = 16, /* + m: OU drift with a constant [d, m] diffusion matrix; params [theta, mu, G row-major] */
        ORC_FIELD_CALLBACK = 100 };
 /* Brownian levy_area kind */

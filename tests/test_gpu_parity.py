@@ -1123,3 +1123,36 @@ def test_every_solver_dt0_none(dev, solver):
     #  0.01 step having an error estimate below rounding noise)
     assert err.max() < max(RTOL64, 64 * sens.max()), (err.max(), sens.max())
     assert relerr(to_np(sol.ys), o["ys"]) < 0.1 * kw["rtol"]
+
+
+@pytest.mark.parametrize("solver", ["euler", "heun"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_state_dependent_diffusion_gbm(dev, solver, dtype):
+    """ControlTerm with a state-dependent diffusion g(t, y) = sigma y (geometric Brownian motion): the CUDA path equals the
+    oracle on fixed steps, follows the exact Stratonovich / Ito solution driven by the same Brownian path, and ShARK (an
+    additive-noise SRK) is refused."""
+    n = 2048
+    keys = dfx.random.split(dfx.random.key(8), n)
+    kd = torch.tensor(keys.view(np.int32), device=dev)
+    mu, sigma = 0.3, 0.4
+    field = dfx.fields.GeometricBrownianMotion(mu, sigma)
+    bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -12, (), kd)
+    terms = dfx.MultiTerm(dfx.ODETerm(field.drift), dfx.ControlTerm(field.diffusion, bm))
+    sol = dfx.diffeqsolve(terms, SOLVERS[solver](), 0.0, 1.0, 2.0 ** -8, torch.ones(n, 1, dtype=getattr(torch, np.dtype(dtype).name), device=dev))
+    o = oracle.solve("gbm", np.ones((n, 1), dtype), 0.0, 1.0, 2.0 ** -8, solver=solver, params=[mu, sigma], dtype=dtype, controller="constant",
+                     levy_area="bi", keys=keys, bm_tol=2.0 ** -12)
+    assert np.array_equal(stats_np(sol), o["stats"])
+    assert relerr(to_np(sol.ys), o["ys"]) < (1e-12 if dtype == np.float64 else RTOL32)
+    W = to_np(bm.evaluate(0.0, 1.0)).astype(np.float64)
+    exact = np.exp(mu + sigma * W) if solver == "heun" else np.exp(mu - 0.5 * sigma ** 2 + sigma * W)
+    rms = np.sqrt(np.mean((to_np(sol.ys)[:, -1, 0] - exact) ** 2))
+    assert rms < (2e-3 if solver == "heun" else 4e-2)
+    if solver == "heun" and dtype == np.float64:
+        bm2 = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -12, (), kd, dfx.SpaceTimeLevyArea)
+        with pytest.raises(ValueError):
+            dfx.diffeqsolve(dfx.MultiTerm(dfx.ODETerm(field.drift), dfx.ControlTerm(field.diffusion, bm2)), dfx.ShARK(), 0.0, 1.0, 2.0 ** -8,
+                            torch.ones(n, 1, dtype=torch.float64, device=dev))
+        # adaptive stepping by step doubling (HalfSolver(Heun)) on the multiplicative-noise SDE
+        ad = dfx.diffeqsolve(terms, dfx.HalfSolver(dfx.Heun()), 0.0, 1.0, 2.0 ** -6, torch.ones(n, 1, dtype=torch.float64, device=dev),
+                             stepsize_controller=dfx.PIDController(rtol=0.0, atol=1e-3, dtmin=2.0 ** -11, pcoeff=0.1, icoeff=0.3), max_steps=1 << 14)
+        assert np.sqrt(np.mean((to_np(ad.ys)[:, -1, 0] - np.exp(mu + sigma * W)) ** 2)) < 5e-3

@@ -168,3 +168,25 @@ def test_matrix_valued_diffusion_covariance_law(solver, levy):
     tol = 0.012 if solver != "euler" else 0.02
     assert np.abs(np.cov(y.T) - want).max() < tol
     assert np.abs(y.mean(0) - np.exp(-1.0)).max() < 0.02
+
+
+def test_state_dependent_diffusion_gbm_converges_to_the_exact_solutions():
+    """ControlTerm with a state-dependent diffusion g(t, y) = sigma y (geometric Brownian motion), scalar Brownian motion from
+    the VirtualBrownianTree.  Path-wise against the closed forms driven by THE SAME W(1) (oracle.vbt_evaluate):
+    Heun -> Stratonovich  y0 exp(mu t + sigma W)   (heun.py:24-33),   Euler -> Ito  y0 exp((mu - sigma^2 / 2) t + sigma W)."""
+    import diffrax_b200 as dfx
+    n = 400
+    keys = dfx.random.split(dfx.random.key(8), n)
+    mu, sigma = 0.3, 0.4
+    W, _ = oracle.vbt_evaluate(keys, 0.0, 1.0, tol=2.0 ** -12)
+    errs = {}
+    for solver, exact in (("heun", np.exp(mu + sigma * W)), ("euler", np.exp(mu - 0.5 * sigma ** 2 + sigma * W))):
+        errs[solver] = []
+        for k in (6, 8, 10):
+            r = oracle.solve("gbm", np.ones((n, 1)), 0.0, 1.0, 2.0 ** -k, solver=solver, params=[mu, sigma], controller="constant",
+                             levy_area="bi", keys=keys, bm_tol=2.0 ** -12, max_steps=1 << 12)
+            errs[solver].append(np.sqrt(np.mean((r["ys"][:, -1, 0] - exact) ** 2)))
+    assert errs["heun"][-1] < 2e-4 and errs["euler"][-1] < 1.5e-2
+    # strong order: commutative noise - Heun 1.0, Euler-Maruyama 0.5; error ratio over a factor 16 in dt
+    assert errs["heun"][0] / errs["heun"][-1] > 8.0
+    assert 2.5 < errs["euler"][0] / errs["euler"][-1] < 7.0
