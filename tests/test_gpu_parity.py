@@ -1143,7 +1143,8 @@ def test_state_dependent_diffusion_gbm(dev, solver, dtype):
                      levy_area="bi", keys=keys, bm_tol=2.0 ** -12)
     assert np.array_equal(stats_np(sol), o["stats"])
     assert relerr(to_np(sol.ys), o["ys"]) < (1e-12 if dtype == np.float64 else RTOL32)
-    W = to_np(bm.evaluate(0.0, 1.0)).astype(np.float64)
+    tdt = getattr(torch, np.dtype(dtype).name)   # (the tree draws in the dtype of the query times: fp32 and fp64 paths differ)
+    W = to_np(bm.evaluate(torch.zeros(n, dtype=tdt, device=dev), torch.ones(n, dtype=tdt, device=dev))).astype(np.float64)
     exact = np.exp(mu + sigma * W) if solver == "heun" else np.exp(mu - 0.5 * sigma ** 2 + sigma * W)
     rms = np.sqrt(np.mean((to_np(sol.ys)[:, -1, 0] - exact) ** 2))
     assert rms < (2e-3 if solver == "heun" else 4e-2)
