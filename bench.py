@@ -488,6 +488,44 @@ def measure(name, args, rank, local, world, dev, strong: bool, with_cpu: bool, s
     return res
 
 
+def parity_report(dev):
+    """the run also emits a small parity report - this arm against live Diffrax when the probe finds
+    it, else against the oracle: Brownian increments bit-exact, accepted-step counts, saved states (C2 slice, fp64)."""
+    import torch
+    import diffrax_b200 as dfx
+    import oracle
+    import baseline
+    n = 2048
+    w = workload("c2", n)
+    sol = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.Lorenz(*w["params"])), dfx.Dopri5(), 0.0, 2.0, None, torch.tensor(w["y0"], device=dev),
+                          stepsize_controller=dfx.PIDController(rtol=1e-8, atol=1e-8))
+    ok, why = baseline.probe()
+    ref = None
+    if ok:
+        try:
+            ref, against = baseline.solve(dict(w, save_t1=True)), "live Diffrax (" + why + ")"
+        except Exception as e:  # noqa: BLE001
+            why = f"live Diffrax failed: {type(e).__name__}: {e}"
+    if ref is None:
+        ref = oracle.solve("lorenz", w["y0"], 0.0, 2.0, None, solver="dopri5", params=w["params"], rtol=1e-8, atol=1e-8)
+        against = "oracle (C restatement; live Diffrax unavailable: " + why + ")"
+    ys = sol.ys.cpu().numpy()
+    rys = np.asarray(ref["ys"]).reshape(ys.shape)
+    err = np.abs(ys - rys) / (np.abs(rys) + 1e-3 * np.abs(rys).max())
+    dacc = np.abs(sol.stats["num_accepted_steps"].cpu().numpy() - np.asarray(ref["stats"])[:, 1])
+    keys = dfx.random.split(dfx.random.key(0), 4096)
+    kd = torch.tensor(keys.view(np.int32), device=dev)
+    bit = True
+    for lv, cls in (("bi", dfx.BrownianIncrement), ("stla", dfx.SpaceTimeLevyArea)):
+        bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -8, (), kd, cls)
+        W, H = bm.evaluate(torch.full((4096,), 0.25, device=dev), torch.full((4096,), 0.625, device=dev), use_levy=True)
+        Wo, Ho = oracle.vbt_evaluate(keys, 0.25, 0.625, tol=2.0 ** -8, levy_area=lv, dtype=np.float32)
+        bit = bit and np.array_equal(W.cpu().numpy(), Wo) and (lv == "bi" or np.array_equal(H.cpu().numpy(), Ho))
+    return {"against": against, "c2_slice_trajectories": n, "max_rel_state_err": float(err.max()),
+            "frac_within_1e-10": float((err.max(axis=(1, 2)) < 1e-10).mean()), "max_abs_accepted_step_diff": int(dacc.max()),
+            "brownian_increments_bit_exact_vs_oracle": bool(bit), "brownian_sample": "4096 keys, W (and H) of [0.25, 0.625], tol 2^-8, fp32"}
+
+
 def run_ours(args):
     import gc
     import torch
@@ -508,6 +546,11 @@ def run_ours(args):
             line["weak"] = {k: wk[k] for k in ("value", "unit", "ms_per_step", "kernel_ms_per_step", "steps")}
             line["weak"].update(trajectories_per_gpu=wk["config"]["trajectories_per_gpu"], trajectories_total=wk["config"]["trajectories_total"],
                                 e2e_value=wk["e2e"]["value"], e2e_ms_per_step=wk["e2e"].get("ms_per_step"))
+    if rank == 0 and args.workload == "c2" and not args.trajectories:
+        try:
+            line["parity"] = parity_report(dev)
+        except Exception as e:  # noqa: BLE001
+            line["parity"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if world == 1 and not args.no_extras and args.workload == "c2" and not args.trajectories:
         # the other BASELINE configs, same method, appended to the one JSON line
         extras = {}
