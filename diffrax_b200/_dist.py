@@ -82,7 +82,8 @@ class ShardedSolution:
     local     this rank's `Solution` (rows [lo, hi) of the global batch; host or device arrays like the inputs)
     y_final   [n_total, d] final states of the WHOLE batch, on this rank's device (NCCL all_gather), block order
     t_final   [n_total]
-    stats     global totals: num_steps / num_accepted_steps / num_rejected_steps / num_failed / max_steps_per_trajectory
+    stats     global totals: num_steps / num_accepted_steps / num_rejected_steps / num_failed (result neither successful nor
+              event_occurred) / max_steps_per_trajectory
     """
     local: Any
     lo: int
@@ -226,7 +227,13 @@ class ShardedSolve:
                 peer.close()
 
     def __call__(self, throw: bool = True) -> ShardedSolution:
-        return self.gather(self.solve_local(throw=throw))
+        # the block is always solved with throw=False: one rank raising before the collective would leave the others waiting;
+        # `throw` is applied to the GLOBAL failure count afterwards, so every rank raises (or none does) - _integrate.py:1541-1542
+        out = self.gather(self.solve_local(throw=False))
+        if throw and int(out.stats["num_failed"]) > 0:
+            raise RuntimeError(f"{int(out.stats['num_failed'])} of {self.n_total} trajectories failed (result codes in `.local.result`; "
+                               "pass throw=False to inspect them)")
+        return out
 
     def solve_local(self, throw: bool = True):
         """This rank's block: one C-ABI call; the finals and the totals land in the packed record (and, in peer mode, in
@@ -255,7 +262,9 @@ class ShardedSolve:
         sums = tot[:, :3].sum(0)
         stats = {"num_steps": sums[0], "num_accepted_steps": sums[1], "num_rejected_steps": sums[0] - sums[1], "num_failed": sums[2],
                  "max_steps_per_trajectory": tot[:, 3].max()}               # 0-d device tensors: no host sync here
-        return ShardedSolution(sol, self.lo, self.hi, self.n_total, y, t, stats)
+        out = ShardedSolution(sol, self.lo, self.hi, self.n_total, y, t, stats)
+        out._owner = self   # y_final / t_final may be views of this object's peer buffers: keep them alive with the result
+        return out
 
     def close(self):
         """Unmap the peers' buffers and free this rank's (peer mode); safe to call more than once."""
@@ -273,8 +282,10 @@ class ShardedSolve:
 def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, device=None, gather=None, **kw) -> ShardedSolve:
     """`prepare` for the sharded configuration.  `y0` (and per-trajectory `t0` / `t1`, Brownian keys) describe the GLOBAL
     batch of N trajectories and are the same on every rank; rank r owns the contiguous block `shard_range(N, r, world)`.
-    Host inputs (NumPy / CPU tensors) go through the host-buffer entry of the C ABI, CUDA tensors through the device entry;
-    either way the finals land in a device record that one NCCL all_gather distributes."""
+    Host inputs (NumPy / CPU tensors) go through the host-buffer entry of the C ABI, CUDA tensors through the device entry.
+    `gather`: "peer" (default with NCCL on one node) fuses the gather of the finals into the solve kernel over NVLink peer
+    memory; "nccl" distributes a packed per-rank record with one all_gather (see `ShardedSolve`).  Call `.close()` on the
+    returned object when done with it (peer mode holds CUDA-IPC mappings)."""
     from . import _api
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -306,6 +317,7 @@ def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, de
 
 def sharded_diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, throw: bool = True, group=None, device=None, **kw) -> ShardedSolution:
     """`diffeqsolve` for a global batch sharded over the ranks of a `torch.distributed` group (one process per GPU):
-    trajectories are independent, so each rank integrates its block with no data-path collective, and ONE all_gather
-    then gives every rank the final states of the whole batch plus the global step statistics."""
+    trajectories are independent, so each rank integrates its block with no data-path collective; the final states of the
+    whole batch reach every rank through the fused peer gather (or one all_gather), the global step statistics through a
+    32-byte all_gather.  `throw` is collective: every rank raises if ANY trajectory of the global batch failed."""
     return prepare_sharded(terms, solver, t0, t1, dt0, y0, args, group=group, device=device, **kw)(throw=throw)

@@ -444,7 +444,8 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
         // pass into this warp's shared-memory slot; flushed with four global atomics when the warp leaves the kernel
         const bool fin = (waiting >> lane_id) & 1u;
         const int a_ = __reduce_add_sync(kFullMask, fin ? num_steps : 0), b_ = __reduce_add_sync(kFullMask, fin ? num_accepted : 0);
-        const int c_ = __reduce_add_sync(kFullMask, (fin && result != DFX_RESULT_SUCCESSFUL) ? 1 : 0);
+        // failed = not is_okay(result): an event is not a failure (_solution.py:52-62)
+        const int c_ = __reduce_add_sync(kFullMask, (fin && result != DFX_RESULT_SUCCESSFUL && result != DFX_RESULT_EVENT_OCCURRED) ? 1 : 0);
         const int m_ = __reduce_max_sync(kFullMask, fin ? num_steps : 0);
         if (lane_id == 0) {
           long long w0, w1, w2, w3;

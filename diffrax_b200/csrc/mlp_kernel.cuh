@@ -105,7 +105,7 @@ __global__ void totals_from_stats_kernel(long long n, const int *__restrict__ st
   long long a = 0, b = 0, c = 0, m = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int s = stats[3 * i];
-    a += s; b += stats[3 * i + 1]; c += result[i] != 0; m = m > s ? m : s;
+    a += s; b += stats[3 * i + 1]; c += (result[i] != DFX_RESULT_SUCCESSFUL && result[i] != DFX_RESULT_EVENT_OCCURRED); m = m > s ? m : s;
   }
   for (int o = 16; o; o >>= 1) {
     a += __shfl_xor_sync(kFullMask, a, o); b += __shfl_xor_sync(kFullMask, b, o); c += __shfl_xor_sync(kFullMask, c, o);

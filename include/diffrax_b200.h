@@ -177,7 +177,8 @@ typedef struct dfx_solve_desc {
   void *t_final_device;
 
   /* Ensemble totals, reduced inside the solve kernel (the statistics half of the multi-GPU gather): [4] int64 =
-   * sum of num_steps, sum of num_accepted_steps, number of trajectories with result != successful, max num_steps of one
+   * sum of num_steps, sum of num_accepted_steps, number of trajectories whose result is neither successful nor event_occurred
+   * (i.e. not is_okay, _solution.py:52-62), max num_steps of one
    * trajectory.  `totals` lives where the other outputs live (device for dfx_ensemble_solve, host for *_host);
    * `totals_device` is the optional device copy for the host call, like y_final_device.  NULL = not wanted. */
   int64_t *totals;

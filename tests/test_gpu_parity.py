@@ -563,6 +563,11 @@ def test_events_steady_state_and_results(dev):
     assert same.mean() > 0.95
     assert relerr(to_np(sol.ts)[same], o["ts"][same]) < 1e-9 and relerr(to_np(sol.ys)[same], o["ys"][same]) < 1e-8
     assert float(sol.ts.max()) < 20.0                                    # stopped long before t1 = 100
+    # the in-kernel ensemble totals count not-is_okay results: events are not failures, the sharded entry does not raise
+    sh = dfx.sharded_diffeqsolve(dfx.ODETerm(dfx.fields.LinearDecay(1.0)), dfx.Tsit5(), 0.0, 100.0, 0.01, torch.tensor(y0, device=dev),
+                                 stepsize_controller=ctrl, event=dfx.Event(dfx.steady_state_event()))
+    assert int(sh.stats["num_failed"]) == 0 and int(sh.stats["num_steps"]) == int(sol.stats["num_steps"].sum())
+    assert torch.equal(sh.y_final, sol.ys[:, -1])
     with pytest.raises(ValueError, match="steady_state_event"):
         dfx.diffeqsolve(dfx.ODETerm(dfx.fields.LinearDecay(1.0)), dfx.Tsit5(), 0.0, 1.0, 0.01, torch.tensor(y0, device=dev),
                         event=dfx.Event(dfx.steady_state_event()))
@@ -1081,6 +1086,8 @@ def test_degenerate_batches(dev):
     assert bool((s.result == 0).all()) and bool((s.stats["num_steps"] == 0).all()) and torch.equal(s.ys[:, 0], y0)
     sh = dfx.sharded_diffeqsolve(term, dfx.Dopri5(), 0.0, 1.0, None, y0, stepsize_controller=ctrl, max_steps=0, throw=False)
     assert int(sh.stats["num_failed"]) == 70 and int(sh.stats["num_steps"]) == 0
+    with pytest.raises(RuntimeError, match="70 of 70 trajectories failed"):
+        dfx.sharded_diffeqsolve(term, dfx.Dopri5(), 0.0, 1.0, None, y0, stepsize_controller=ctrl, max_steps=0)
 
 
 def test_fused_peer_gather_two_gpus():

@@ -154,11 +154,16 @@ def plan(throw=True):              # stands in for the CUDA solve: writes this r
     return types.SimpleNamespace(stats={{"num_steps": steps[lo:hi]}}, result=res.to(torch.int32))
 sh.plan = plan
 for _ in range(2):                 # the record is reused across calls
-    out = sh()
+    out = sh(throw=False)
     assert torch.equal(out.y_final, full_y) and torch.equal(out.t_final, full_t), (rank, out.y_final)
     assert int(out.stats["num_steps"]) == int(steps.sum()) and int(out.stats["num_accepted_steps"]) == int(steps.sum()) - 3 * n_total
     assert int(out.stats["num_rejected_steps"]) == 3 * n_total and int(out.stats["num_failed"]) == 3
     assert int(out.stats["max_steps_per_trajectory"]) == n_total - 1 + 10 and (out.lo, out.hi, out.n_total) == (lo, hi, n_total)
+try:                               # throw is collective: the failures sit in rank 0's and rank 1's blocks, BOTH ranks raise after the gather
+    sh(throw=True); raised = False
+except RuntimeError as e:
+    raised = "3 of 11 trajectories failed" in str(e)
+assert raised, rank
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 '''
