@@ -103,14 +103,16 @@ class Solution:
 # terms
 # --------------------------------------------------------------------------------------
 class ODETerm:
-    """_term.py:174-226: ``ODETerm(vector_field)``; vector_field is a registered functor."""
+    """_term.py:174-226: ``ODETerm(vector_field)``; vector_field is a device functor: one of the built-in ones in
+    `diffrax_b200.fields`, or the user's own right-hand side compiled on first use (`fields.CudaField`)."""
 
     def __init__(self, vector_field: Union[Field, FieldPart]):
         if isinstance(vector_field, Field):
             vector_field = vector_field.drift
         if not isinstance(vector_field, FieldPart) or vector_field.part != "drift":
-            raise TypeError("ODETerm(vector_field): vector_field must be a registered device functor "
-                            "from diffrax_b200.fields (or its `.drift`)")
+            raise TypeError("ODETerm(vector_field): vector_field must be a device functor from diffrax_b200.fields (or its "
+                            "`.drift`): a built-in one, or your own right-hand side as `fields.CudaField(dim, \"f[0] = ...;\", "
+                            "params=[...])` - a Python callable cannot run inside the solve kernel")
         self.vector_field = vector_field
 
 
@@ -899,6 +901,10 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
             raise ValueError(f"{type(field).__name__} is not an SDE functor")
     elif isinstance(solver.solver if isinstance(solver, HalfSolver) else solver, ShARK):
         raise ValueError("ShARK requires MultiTerm(ODETerm(drift), ControlTerm(diffusion, VirtualBrownianTree))")
+    # a user-written functor (fields.CudaField) compiles + registers its kernel for this combination on first use
+    ensure = getattr(field, "ensure_kernel", None)
+    if ensure is not None:
+        ensure(d, int(D.solver_id), int(D.dtype), int(D.levy_area))
 
     if event is not None:
         ev_params = np.ascontiguousarray(np.concatenate([np.asarray(c.params(d, ctrl), np.float64) for c in event._conds]))

@@ -25,6 +25,7 @@ HALF_SOLVER = 0x100  # DFX_HALF_SOLVER: HalfSolver(inner) = HALF_SOLVER | inner 
 FIELD_IDS = {"decay": 0, "lotka_volterra": 1, "lorenz": 2, "cr3bp": 3, "mlp": 4, "ou": 5,
              "forced_osc": 6, "vdp": 7, "gbm": 8}
 FIELD_OU_MATRIX = 16   # + m: OU drift with a constant [d, m] diffusion matrix
+FIELD_USER = 1000      # user functors (fields.CudaField) register ids >= this with dfx_register_launcher
 
 
 class SolveDesc(C.Structure):
@@ -83,6 +84,19 @@ _lib = None
 
 class LibraryMissing(RuntimeError):
     pass
+
+
+_plugins = {}
+
+
+def load_plugin(path):
+    """dlopen a shared object of user functors built against libdiffrax_b200.so: its static
+    registrars call dfx_register_launcher on load."""
+    lib()
+    path = os.path.abspath(path)
+    if path not in _plugins:
+        _plugins[path] = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    return _plugins[path]
 
 
 def lib():

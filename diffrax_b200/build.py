@@ -74,6 +74,40 @@ def build(force=False, jobs=None, verbose=True):
     return LIB
 
 
+USER_DIR = os.path.join(LIBDIR, "user")
+
+
+def build_user_field(tag, source, verbose=False):
+    """Compile one generated translation unit (fields.CudaField: a user functor + ONE DFX_REGISTER) against csrc/launch.cuh
+    into lib/user/dfx_user_<tag>.so, linked to libdiffrax_b200.so.  Cached: the tag carries the content hash of the functor,
+    and the object is rebuilt when the kernel headers are newer."""
+    os.makedirs(USER_DIR, exist_ok=True)
+    out = os.path.join(USER_DIR, f"dfx_user_{tag}.so")
+    src = os.path.join(USER_DIR, f"dfx_user_{tag}.cu")
+    if not os.path.exists(LIB):
+        raise RuntimeError(f"{LIB} not found: build it with `python -m diffrax_b200.build` first")
+    if os.path.exists(src) and open(src).read() == source and not _stale(out, [src, LIB] + _headers()):
+        return out
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"compiling a CudaField needs nvcc ({NVCC} not found; set NVCC)")
+    with open(src, "w") as f:
+        f.write(source)
+    tmp = out + f".tmp{os.getpid()}"
+    flags = [x for x in FLAGS if x not in ("-Xptxas", "-v")]
+    cmd = [NVCC, *ARCH, *flags, "-I", CSRC, "-shared", "-o", tmp, src, "-L", LIBDIR, "-ldiffrax_b200",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/.."]
+    t0 = time.time()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise RuntimeError("nvcc failed on the generated CudaField source " + src + ":\n" + (r.stderr or r.stdout)[-4000:])
+    os.replace(tmp, out)   # atomic: concurrent ranks may build the same tag
+    if verbose:
+        print(f"[build] {out} {time.time() - t0:.1f}s", flush=True)
+    return out
+
+
 FFI_SRC = os.path.join(CSRC, "ffi", "xla_ffi_shim.cc")
 FFI_LIB = os.path.join(LIBDIR, "libdfx_xla_ffi.so")
 FFI_STUB = os.path.join(HERE, "..", "tests", "ffi_stub")

@@ -399,7 +399,8 @@ static int check_desc(const dfx_solve_desc *d) {
                 d->field_id - DFX_FIELD_OU_MATRIX, d->bm_dim);
       return DFX_ERR_BAD_ARGUMENT;
     }
-    if (!matrix && d->bm_dim != 0 && d->bm_dim != d->dim) {
+    // (user functors, field ids >= DFX_FIELD_USER, define their own noise shape: the launcher checks bm_dim against it)
+    if (!matrix && d->field_id < DFX_FIELD_USER && d->bm_dim != 0 && d->bm_dim != d->dim) {
       set_error("VirtualBrownianTree(shape=(%d,)) drives a diagonal diffusion: it needs a state of the same dimension (got %d)", d->bm_dim, d->dim);
       return DFX_ERR_BAD_ARGUMENT;
     }

@@ -217,6 +217,18 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
+  if constexpr (SDE) {
+    // the Brownian motion's shape is compiled into the functor: shape () / (1,) -> 1 component, (m,) -> m
+    if ((d->bm_dim == 0 ? 1 : d->bm_dim) != NoiseDim<Field>::value) {
+      if (d->bm_dim == 0) set_error("this functor is driven by a Brownian motion with %d components, got VirtualBrownianTree shape ()", NoiseDim<Field>::value);
+      else set_error("this functor is driven by a Brownian motion with %d component(s), got VirtualBrownianTree shape (%d,)", NoiseDim<Field>::value, d->bm_dim);
+      return DFX_ERR_BAD_ARGUMENT;
+    }
+    if (StateNoise<Field>::value && InnerId<Solver>::value == DFX_SHARK) {
+      set_error("ShARK is an additive-noise SRK (shark.py:10-30): the diffusion of this field depends on y");
+      return DFX_ERR_BAD_ARGUMENT;
+    }
+  }
   // EXTRA: ClipStepSizeController / Hairer starting step / Event; RICH: any SaveAt mode beyond t1 (EXTRA implies RICH)
   const bool extra = (d->hairer_initial_step && std::isnan(d->dt0)) || d->step_ts || d->jump_ts || d->n_events != 0 ||
                      d->state_in || d->state_out || d->store_rejected_steps > 0;

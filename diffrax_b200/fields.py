@@ -199,3 +199,148 @@ class MLP(Field):
             np_dt = np.float32 if "32" in str(dtype) else np.float64
             self._cache[key] = xp.asarray(self.flat(np_dt), dtype)
         return self._cache[key]
+
+
+# --------------------------------------------------------------------------------------
+# User-supplied vector fields, compiled on first use
+# --------------------------------------------------------------------------------------
+_SOLVER_CPP = {0: "::dfx::Tsit5", 1: "::dfx::Dopri5", 2: "::dfx::Dopri8", 3: "::dfx::Heun", 4: "::dfx::Bosh3",
+               5: "::dfx::Midpoint", 6: "::dfx::Ralston", 7: "::dfx::EulerSolver", 8: "::dfx::SharkSolver"}
+_HALF = 0x100
+
+_USER_TU = r"""// generated by diffrax_b200.fields.CudaField - do not edit
+@DEFINES@
+#include "launch.cuh"
+namespace {
+@PREAMBLE@
+struct UserField {
+  static constexpr int kId = @ID@;
+  static constexpr int kDim = @DIM@;
+  static constexpr bool kSde = @SDE@;
+  static constexpr int kNumParams = @NP@;
+@NOISE_TRAITS@
+  template <class R> struct P { R p[@NP1@]; };
+  template <class R> static P<R> make(const double *q, int n, const void *) {
+    P<R> o;
+    for (int i = 0; i < @NP1@; ++i) o.p[i] = (i < n && i < @NP@) ? (R)q[i] : R(0);
+    return o;
+  }
+  // vector_field(t, y, args) of ODETerm (_term.py:174-211): y[kDim] -> f[kDim]; p[] are the bound `args`
+  template <class R>
+  static __device__ __forceinline__ void eval(const P<R> &P_, R t, const R (&y)[@DIM@], R (&f)[@DIM@]) {
+    [[maybe_unused]] const R *p = P_.p;
+    (void)t;
+@DRIFT@
+  }
+@NOISE_FNS@
+};
+[[maybe_unused]] constexpr bool kUseSde = UserField::kSde;
+DFX_REGISTER(@REAL@, UserField, @SOLVER@, @LEVY@)
+}  // namespace
+"""
+
+
+class CudaField(Field):
+    """A vector field written by the user as CUDA C++ statements - what a Python ``vector_field(t, y, args)`` is to the
+    reference's ``ODETerm`` (_term.py:174-211).  The solver kernels are templates over the field functor, so the statements
+    are compiled into a kernel of their own (nvcc, sm_100a) the first time a (solver, dtype) combination is asked for
+    (~10 s; cached under ``diffrax_b200/lib/user/`` by content hash) and registered through ``dfx_register_launcher``.
+
+    ``drift``: statements that assign ``f[0..dim)`` from ``t``, ``y[0..dim)`` and the parameters ``p[0..n_params)``; ``R`` is the
+    working type (``double`` / ``float``).  Example - the damped pendulum::
+
+        pend = CudaField(2, "f[0] = y[1]; f[1] = -p[0] * sin(y[0]) - p[1] * y[1];", params=[9.81, 0.1])
+        sol = diffeqsolve(ODETerm(pend), Dopri5(), 0.0, 10.0, None, y0, stepsize_controller=PIDController(1e-8, 1e-8))
+
+    SDEs (``MultiTerm(ODETerm(f.drift), ControlTerm(f.diffusion, VirtualBrownianTree(...)))``), either
+    * ``diffusion="<expr>"``: additive noise ``g(t)`` (an expression in ``t`` and ``p``) times a Brownian motion of shape ``()``
+      (dim 1) or ``(dim,)`` (diagonal) - Euler / Heun / ShARK and ``HalfSolver`` of the latter two; or
+    * ``noise="<statements>"``, ``noise_dim=m``: the general ``ControlTerm.prod`` (_term.py:417-427): assign ``gx[0..dim)``, the
+      product ``g(t, y) . x`` with the Brownian increment ``x[0..m)`` (``m = 1`` for shape ``()``) - Euler / Heun (Stratonovich).
+
+    ``preamble``: device helper functions / constants placed before the functor.  ``min_blocks_per_sm``: occupancy target handed
+    to ptxas (``__launch_bounds__``) instead of the register-budget heuristic of csrc/ensemble_kernel.cuh - e.g. 6 for a
+    3-dimensional fp64 field with a 7-stage solver (what the built-in Lorenz/Dopri5 kernel uses)."""
+    is_user = True
+
+    def __init__(self, dim, drift, *, params=(), diffusion=None, noise=None, noise_dim=None, preamble="", name=None,
+                 min_blocks_per_sm=None):
+        import hashlib
+        self.dim = int(dim)
+        if not 1 <= self.dim <= 8:
+            raise ValueError("CudaField: 1 <= dim <= 8")
+        if diffusion is not None and noise is not None:
+            raise ValueError("CudaField: give `diffusion` (additive g(t)) or `noise` (general g(t, y) . x), not both")
+        self.p = [float(v) for v in params]
+        self.drift_src, self.diffusion_src, self.noise_src, self.preamble = str(drift), diffusion, noise, str(preamble)
+        self.is_sde = diffusion is not None or noise is not None
+        self.noise_dim = 1 if not self.is_sde else (int(noise_dim) if noise_dim else (self.dim if diffusion is not None else 1))
+        if diffusion is not None and self.noise_dim not in (1, self.dim):
+            raise ValueError("CudaField: additive `diffusion` is scalar (dim 1) or diagonal (noise_dim == dim)")
+        if self.is_sde and not 1 <= self.noise_dim <= 4:
+            raise ValueError("CudaField: 1 <= noise_dim <= 4")
+        self.min_blocks = None if min_blocks_per_sm is None else int(min_blocks_per_sm)
+        if self.min_blocks is not None and not 1 <= self.min_blocks <= 16:
+            raise ValueError("CudaField: 1 <= min_blocks_per_sm <= 16")
+        key = "\0".join([str(self.dim), self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble, str(len(self.p)),
+                         str(self.min_blocks)])
+        self._hash = hashlib.sha256(key.encode()).hexdigest()[:16]
+        self._id = _lib.FIELD_USER + int(self._hash[:7], 16)
+        self.name = name or f"user_{self._hash}"
+        self._ready = set()
+
+    @property
+    def field_id(self):
+        return self._id
+
+    def params(self):
+        return self.p
+
+    def source(self, solver_id, dtype_id, levy):
+        inner = solver_id & ~_HALF
+        solver = _SOLVER_CPP[inner]
+        if solver_id & _HALF:
+            solver = f"::dfx::HalfOf<{solver}>"
+        np_ = len(self.p)
+        traits, fns = "", ""
+        if self.is_sde:
+            traits = f"  static constexpr int kNoise = {self.noise_dim};\n"
+            if self.noise_src is not None:
+                traits += "  static constexpr bool kStateNoise = true;\n"
+                fns = (f"  template <class R> static __device__ __forceinline__ R noise_prod(const P<R> &P_, R t, const R (&y)[{self.dim}], "
+                       f"const R (&x)[{self.noise_dim}], int c) {{\n    [[maybe_unused]] const R *p = P_.p;\n    (void)t;\n    R gx[{self.dim}];\n"
+                       f"{self.noise_src}\n    return gx[c];\n  }}\n")
+            else:
+                fns = ("  template <class R> static __device__ __forceinline__ R diffusion(const P<R> &P_, R t) {\n"
+                       f"    [[maybe_unused]] const R *p = P_.p;\n    (void)t;\n    return (R)({self.diffusion_src});\n  }}\n")
+        rep = {"@DEFINES@": "" if self.min_blocks is None else f"#define DFX_MIN_BLOCKS {self.min_blocks}",
+               "@PREAMBLE@": self.preamble, "@ID@": str(self._id), "@DIM@": str(self.dim), "@SDE@": "true" if self.is_sde else "false",
+               "@NP@": str(np_), "@NP1@": str(max(np_, 1)), "@NOISE_TRAITS@": traits, "@DRIFT@": self.drift_src, "@NOISE_FNS@": fns,
+               "@REAL@": "double" if dtype_id == _lib.F64 else "float", "@SOLVER@": solver, "@LEVY@": str(int(levy))}
+        src = _USER_TU
+        for k, v in rep.items():
+            src = src.replace(k, v)
+        return src
+
+    def ensure_kernel(self, dim, solver_id, dtype_id, levy):
+        """Compile (once) and load the kernel for this (solver, dtype, Levy area); called by `prepare`."""
+        if dim != self.dim:
+            raise ValueError(f"CudaField has state dimension {self.dim}, got y0 with d={dim}")
+        key = (int(solver_id), int(dtype_id), int(levy))
+        if key in self._ready:
+            return
+        inner = solver_id & ~_HALF
+        if inner not in _SOLVER_CPP:
+            raise ValueError(f"unknown solver id {solver_id}")
+        if bool(levy) != self.is_sde:
+            raise ValueError("CudaField: SDE solves need `diffusion=` or `noise=`; ODE solves must not have them")
+        if self.noise_src is not None and inner == 8:
+            raise ValueError("ShARK is an additive-noise SRK (shark.py:10-30): the diffusion of this field depends on y")
+        L = _lib.lib()
+        if not L.dfx_has_kernel(self._id, self.dim, int(solver_id), int(dtype_id), int(levy)):
+            from . import build
+            path = build.build_user_field(f"{self._hash}_{solver_id:x}_{dtype_id}_{levy}", self.source(solver_id, dtype_id, levy))
+            _lib.load_plugin(path)
+            if not L.dfx_has_kernel(self._id, self.dim, int(solver_id), int(dtype_id), int(levy)):
+                raise RuntimeError(f"{path} was loaded but registered no launcher for this combination")
+        self._ready.add(key)

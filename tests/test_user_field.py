@@ -1,0 +1,174 @@
+"""User-written vector fields (fields.CudaField): what a Python `vector_field(t, y, args)` is to the reference's ODETerm /
+ControlTerm (_term.py:174-211, 417-427).  CPU: source generation, nvcc build for sm_100a, launcher registration through
+dfx_register_launcher.  GPU: the compiled kernels against the oracle's callback field and against the built-in functors
+with the same right-hand sides."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+import torch  # noqa: E402
+import diffrax_b200 as dfx  # noqa: E402
+from diffrax_b200 import _lib  # noqa: E402
+import oracle  # noqa: E402
+
+PENDULUM = "f[0] = y[1]; f[1] = -p[0] * sin(y[0]) - p[1] * y[1];"
+
+
+def test_user_field_compiles_and_registers():
+    pend = dfx.fields.CudaField(2, PENDULUM, params=[9.81, 0.1])
+    L = _lib.lib()
+    assert pend.field_id >= _lib.FIELD_USER and not pend.is_sde
+    pend.ensure_kernel(2, 1, _lib.F64, 0)                      # Dopri5, fp64: nvcc -> lib/user/*.so -> dlopen -> registrar
+    assert L.dfx_has_kernel(pend.field_id, 2, 1, _lib.F64, 0) == 1
+    assert L.dfx_has_kernel(pend.field_id, 2, 0, _lib.F64, 0) == 0   # only what was asked for
+    pend.ensure_kernel(2, 1, _lib.F64, 0)                      # cached
+    again = dfx.fields.CudaField(2, PENDULUM, params=[1.0, 0.0])     # same source, other parameters: same kernel
+    assert again.field_id == pend.field_id
+    other = dfx.fields.CudaField(2, "f[0] = y[1]; f[1] = -y[0];")
+    assert other.field_id != pend.field_id
+    src = pend.source(0x100 | 3, _lib.F32, 0)
+    assert "HalfOf<::dfx::Heun>" in src and "DFX_REGISTER(float" in src and PENDULUM in src
+
+
+def test_user_field_argument_errors():
+    with pytest.raises(ValueError, match="not both"):
+        dfx.fields.CudaField(1, "f[0] = -y[0];", diffusion="1.0", noise="gx[0] = x[0];")
+    with pytest.raises(ValueError, match="dim"):
+        dfx.fields.CudaField(9, "f[0] = 0;")
+    gbm = dfx.fields.CudaField(1, "f[0] = p[0] * y[0];", params=[0.1, 0.2], noise="gx[0] = p[1] * y[0] * x[0];")
+    with pytest.raises(ValueError, match="additive-noise"):
+        gbm.ensure_kernel(1, 8, _lib.F64, 2)                   # ShARK needs additive noise (shark.py:10-30)
+    with pytest.raises(ValueError, match="SDE solves need"):
+        dfx.fields.CudaField(1, "f[0] = -y[0];").ensure_kernel(1, 3, _lib.F64, 1)
+    with pytest.raises(RuntimeError, match="nvcc failed"):
+        dfx.fields.CudaField(1, "f[0] = no_such_function(y[0]);").ensure_kernel(1, 1, _lib.F64, 0)
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["dopri5", "tsit5", "dopri8"])
+def test_user_pendulum_against_oracle_callback(dev, solver):
+    rng = np.random.default_rng(5)
+    y0 = rng.uniform(-1.5, 1.5, (48, 2))
+    g, c = 9.81, 0.1
+    pend = dfx.fields.CudaField(2, PENDULUM, params=[g, c])
+    S = {"dopri5": dfx.Dopri5, "tsit5": dfx.Tsit5, "dopri8": dfx.Dopri8}[solver]
+    ts = np.linspace(0.0, 3.0, 7)
+    sol = dfx.diffeqsolve(dfx.ODETerm(pend), S(), 0.0, 3.0, None, torch.tensor(y0, device=dev), saveat=dfx.SaveAt(ts=ts),
+                          stepsize_controller=dfx.PIDController(rtol=1e-8, atol=1e-8))
+    o = oracle.solve("callback", y0, 0.0, 3.0, None, solver=solver, rtol=1e-8, atol=1e-8, save_ts=ts, save_t1=False,
+                     callback=lambda t, y: np.array([y[1], -g * math.sin(y[0]) - c * y[1]]))
+    st = np.stack([_np(sol.stats[k]) for k in ("num_steps", "num_accepted_steps", "num_rejected_steps")], 1)
+    same = np.all(st == o["stats"], axis=1)
+    assert same.mean() > 0.95 and np.abs(st[:, 1] - o["stats"][:, 1]).max() <= 1
+    err = np.abs(_np(sol.ys)[same] - o["ys"][same]).max() / np.abs(o["ys"]).max()
+    assert err < 1e-10, err          # (device sin vs libm sin: last-place differences only)
+    assert bool((sol.result == 0).all())
+
+
+@pytest.mark.gpu
+def test_user_lorenz_equals_builtin_bitwise(dev):
+    """The same right-hand side as csrc/fields.cuh LorenzField: identical bits, on the device and the host path."""
+    rng = np.random.default_rng(1)
+    y0 = np.stack([rng.uniform(-15, 15, 3000), rng.uniform(-20, 20, 3000), rng.uniform(5, 45, 3000)], 1)
+    user = dfx.fields.CudaField(3, "f[0] = p[0] * (y[1] - y[0]); f[1] = y[0] * (p[1] - y[2]) - y[1]; f[2] = y[0] * y[1] - p[2] * y[2];",
+                                params=[10.0, 28.0, 8.0 / 3.0])
+    ctrl = dfx.PIDController(rtol=1e-8, atol=1e-8)
+    for host in (False, True):
+        y = y0 if host else torch.tensor(y0, device=dev)
+        a = dfx.diffeqsolve(dfx.ODETerm(user), dfx.Dopri5(), 0.0, 1.0, None, y, stepsize_controller=ctrl)
+        b = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.Lorenz()), dfx.Dopri5(), 0.0, 1.0, None, y, stepsize_controller=ctrl)
+        assert np.array_equal(_np(a.ys), _np(b.ys)) and np.array_equal(_np(a.stats["num_steps"]), _np(b.stats["num_steps"]))
+    # fp32, Tsit5, steps saved, backwards in time
+    y32 = torch.tensor(y0[:300].astype(np.float32), device=dev)
+    kw = dict(saveat=dfx.SaveAt(steps=True, t0=True), stepsize_controller=dfx.PIDController(rtol=1e-4, atol=1e-5), max_steps=128, throw=False)
+    a = dfx.diffeqsolve(dfx.ODETerm(user), dfx.Tsit5(), 0.5, 0.0, None, y32, **kw)
+    b = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.Lorenz()), dfx.Tsit5(), 0.5, 0.0, None, y32, **kw)
+    assert np.array_equal(_np(a.ys), _np(b.ys)) and np.array_equal(_np(a.ts), _np(b.ts))
+
+
+@pytest.mark.gpu
+def test_user_sde_fields_equal_builtins(dev):
+    n = 500
+    keys = dfx.random.split(dfx.random.key(7), n)
+    y1 = torch.ones(n, 1, device=dev, dtype=torch.float32)
+    # additive noise, scalar Brownian motion: OU with ShARK (space-time Levy area), fp32, and HalfSolver(Heun) adaptive, fp64
+    uou = dfx.fields.CudaField(1, "f[0] = p[0] * (p[1] - y[0]);", params=[1.0, 0.0, 0.5], diffusion="p[2]")
+    bou = dfx.fields.OrnsteinUhlenbeck(1.0, 0.0, 0.5)
+    for field_pair in [(uou, bou)]:
+        outs = []
+        for f in field_pair:
+            bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -8, (), keys, dfx.SpaceTimeLevyArea)
+            terms = dfx.MultiTerm(dfx.ODETerm(f.drift), dfx.ControlTerm(f.diffusion, bm))
+            outs.append(dfx.diffeqsolve(terms, dfx.ShARK(), 0.0, 1.0, 2.0 ** -6, y1))
+        assert np.array_equal(_np(outs[0].ys), _np(outs[1].ys))
+        outs = []
+        for f in field_pair:
+            bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -10, (), keys)
+            terms = dfx.MultiTerm(dfx.ODETerm(f.drift), dfx.ControlTerm(f.diffusion, bm))
+            outs.append(dfx.diffeqsolve(terms, dfx.HalfSolver(dfx.Heun()), 0.0, 1.0, 0.05, y1.double(),
+                                        stepsize_controller=dfx.PIDController(rtol=1e-3, atol=1e-4, pcoeff=0.1, icoeff=0.3), throw=False))
+        # adaptive stepping on a Brownian path is chaotic in the step times: the two functors compile to differently contracted
+        # FMAs (g = p[2] here, sigma + sigma_t t there), and a last-place difference that flips one accept / reject decision
+        # changes the path sampled afterwards - so: (nearly) identical on the majority, and close to the tolerance everywhere
+        diff = np.abs(_np(outs[0].ys) - _np(outs[1].ys)).ravel()
+        assert (diff < 1e-6).mean() > 0.5, (diff < 1e-6).mean()
+        assert diff.max() < 0.05                                            # both are the same strong solution to the tolerance
+    # state-dependent noise, scalar Brownian motion, d = 2: geometric Brownian motion with Heun (Stratonovich)
+    ugbm = dfx.fields.CudaField(2, "f[0] = p[0] * y[0]; f[1] = p[0] * y[1];", params=[0.1, 0.2],
+                                noise="gx[0] = (p[1] * y[0]) * x[0]; gx[1] = (p[1] * y[1]) * x[0];", noise_dim=1)
+    bgbm = dfx.fields.GeometricBrownianMotion(0.1, 0.2)
+    y2 = torch.tensor(np.random.default_rng(0).uniform(0.5, 2.0, (n, 2)), device=dev)
+    outs = []
+    for f in (ugbm, bgbm):
+        bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -9, (), keys)
+        terms = dfx.MultiTerm(dfx.ODETerm(f.drift), dfx.ControlTerm(f.diffusion, bm))
+        outs.append(dfx.diffeqsolve(terms, dfx.Heun(), 0.0, 1.0, 2.0 ** -7, y2))
+    assert np.array_equal(_np(outs[0].ys), _np(outs[1].ys))
+    # a [2, 2] diffusion matrix through the general product (noise_dim = 2) against OrnsteinUhlenbeckMatrix
+    G = np.array([[0.3, -0.1], [0.2, 0.4]])
+    umat = dfx.fields.CudaField(2, "f[0] = p[0] * (p[1] - y[0]); f[1] = p[0] * (p[1] - y[1]);", params=[1.0, 0.2, *G.ravel()],
+                                noise="gx[0] = p[2] * x[0] + p[3] * x[1]; gx[1] = p[4] * x[0] + p[5] * x[1];", noise_dim=2)
+    bmat = dfx.fields.OrnsteinUhlenbeckMatrix(1.0, 0.2, G)
+    outs = []
+    for f in (umat, bmat):
+        bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -9, (2,), keys)
+        terms = dfx.MultiTerm(dfx.ODETerm(f.drift), dfx.ControlTerm(f.diffusion, bm))
+        outs.append(dfx.diffeqsolve(terms, dfx.Heun(), 0.0, 1.0, 2.0 ** -7, y2))
+    assert np.abs(_np(outs[0].ys) - _np(outs[1].ys)).max() < 1e-13
+    # the Brownian shape is part of the functor
+    with pytest.raises(ValueError, match="Brownian motion with 2 component"):
+        bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -9, (), keys)
+        dfx.diffeqsolve(dfx.MultiTerm(dfx.ODETerm(umat.drift), dfx.ControlTerm(umat.diffusion, bm)), dfx.Heun(), 0.0, 1.0, 2.0 ** -7, y2)
+
+
+@pytest.mark.gpu
+def test_user_field_with_events_dense_and_sharded_entry(dev):
+    """The generated kernels are the full ensemble kernels: dense output, an event with root finding, the sharded entry."""
+    rng = np.random.default_rng(9)
+    y0 = torch.tensor(rng.uniform(0.5, 1.5, (200, 2)), device=dev)
+    osc = dfx.fields.CudaField(2, "f[0] = y[1]; f[1] = -p[0] * y[0];", params=[4.0])
+    ctrl = dfx.PIDController(rtol=1e-9, atol=1e-9)
+    sol = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, saveat=dfx.SaveAt(dense=True, t1=True), stepsize_controller=ctrl)
+    tq = torch.tensor([0.3, 1.1, 1.9], device=dev, dtype=torch.float64)
+    ev = _np(sol.interpolation.evaluate(tq))
+    a, b = _np(y0)[:, 0:1], _np(y0)[:, 1:2]
+    exact = a * np.cos(2 * _np(tq))[None] + b / 2 * np.sin(2 * _np(tq))[None]
+    assert np.abs(ev[..., 0] - exact).max() < 1e-7
+    # event: x crosses zero downwards, located by Newton on the step's interpolant: x(t_event) = 0 and the exact crossing time
+    evs = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl,
+                          event=dfx.Event(dfx.AffineEvent([1.0, 0.0]), dfx.Newton(1e-12, 1e-12), direction=False))
+    assert bool(dfx.is_event(evs.result).all())
+    assert np.abs(_np(evs.ys)[:, -1, 0]).max() < 1e-8
+    t_exact = np.arctan2(_np(y0)[:, 0], -_np(y0)[:, 1] / 2) / 2      # first zero of a cos 2t + (b/2) sin 2t with a, b > 0
+    assert np.abs(_np(evs.ts)[:, -1] - t_exact).max() < 1e-7
+    sh = dfx.sharded_diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl)
+    assert torch.equal(sh.y_final, sol.ys[:, -1]) and int(sh.stats["num_failed"]) == 0
