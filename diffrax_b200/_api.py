@@ -905,6 +905,9 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     ensure = getattr(field, "ensure_kernel", None)
     if ensure is not None:
         ensure(d, int(D.solver_id), int(D.dtype), int(D.levy_area))
+    else:  # a built-in functor with a solver it was not prebuilt for: instantiated on first use
+        from .fields import ensure_builtin_kernel
+        ensure_builtin_kernel(field, d, int(D.solver_id), int(D.dtype), int(D.levy_area), int(D.bm_dim))
 
     if event is not None:
         ev_params = np.ascontiguousarray(np.concatenate([np.asarray(c.params(d, ctrl), np.float64) for c in event._conds]))

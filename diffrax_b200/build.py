@@ -90,9 +90,12 @@ def build_user_field(tag, source, verbose=False):
         return out
     if not os.path.exists(NVCC):
         raise RuntimeError(f"compiling a CudaField needs nvcc ({NVCC} not found; set NVCC)")
-    with open(src, "w") as f:
+    import threading
+    uniq = f".tmp{os.getpid()}_{threading.get_ident()}"   # concurrent threads / ranks may build the same tag
+    with open(src + uniq, "w") as f:
         f.write(source)
-    tmp = out + f".tmp{os.getpid()}"
+    os.replace(src + uniq, src)
+    tmp = out + uniq
     flags = [x for x in FLAGS if x not in ("-Xptxas", "-v")]
     cmd = [NVCC, *ARCH, *flags, "-I", CSRC, "-shared", "-o", tmp, src, "-L", LIBDIR, "-ldiffrax_b200",
            "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/.."]
@@ -102,7 +105,7 @@ def build_user_field(tag, source, verbose=False):
         if os.path.exists(tmp):
             os.remove(tmp)
         raise RuntimeError("nvcc failed on the generated CudaField source " + src + ":\n" + (r.stderr or r.stdout)[-4000:])
-    os.replace(tmp, out)   # atomic: concurrent ranks may build the same tag
+    os.replace(tmp, out)   # atomic
     if verbose:
         print(f"[build] {out} {time.time() - t0:.1f}s", flush=True)
     return out

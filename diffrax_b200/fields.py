@@ -41,9 +41,16 @@ class Field:
     def weights(self, xp, dtype):
         return None
 
+    def cpp_functor(self, dim, bm_dim):
+        """The csrc/fields.cuh functor type for a state of dimension `dim` driven by a Brownian motion of shape `(bm_dim,)`
+        (0: shape () or none); None when there is none.  Used to instantiate (field, solver, dtype) combinations that are not
+        among the prebuilt kernels on first use - `ensure_builtin_kernel`."""
+        return None
+
 
 class LinearDecay(Field):
-    """dy/dt = -lam * y  (test/test_integrate.py:60, test_saveat_solution.py:29-41); d in {1,2,3}."""
+    """dy/dt = -lam * y  (test/test_integrate.py:60, test_saveat_solution.py:29-41); kernels prebuilt for d in {1,2,3},
+    other dimensions (up to 8) are instantiated on first use."""
     name = "decay"
 
     def __init__(self, lam=1.0):
@@ -51,6 +58,9 @@ class LinearDecay(Field):
 
     def params(self):
         return [self.lam]
+
+    def cpp_functor(self, dim, bm_dim):
+        return f"::dfx::DecayField<{dim}>"
 
 
 class LotkaVolterra(Field):
@@ -63,6 +73,9 @@ class LotkaVolterra(Field):
     def params(self):
         return self.p
 
+    def cpp_functor(self, dim, bm_dim):
+        return "::dfx::LotkaVolterraField"
+
 
 class Lorenz(Field):
     """Lorenz-63: [sigma (y-x), x (rho - z) - y, x y - beta z]."""
@@ -73,6 +86,9 @@ class Lorenz(Field):
 
     def params(self):
         return self.p
+
+    def cpp_functor(self, dim, bm_dim):
+        return "::dfx::LorenzField"
 
 
 class CR3BP(Field):
@@ -85,6 +101,9 @@ class CR3BP(Field):
     def params(self):
         return [self.mu]
 
+    def cpp_functor(self, dim, bm_dim):
+        return "::dfx::Cr3bpField"
+
 
 class ForcedOscillator(Field):
     """y0' = y1, y1' = -w0^2 y0 + A sin(w t)."""
@@ -96,6 +115,9 @@ class ForcedOscillator(Field):
     def params(self):
         return self.p
 
+    def cpp_functor(self, dim, bm_dim):
+        return "::dfx::ForcedOscField"
+
 
 class VanDerPol(Field):
     name, dim = "vdp", 2
@@ -105,6 +127,9 @@ class VanDerPol(Field):
 
     def params(self):
         return [self.mu]
+
+    def cpp_functor(self, dim, bm_dim):
+        return "::dfx::VdpField"
 
 
 class OrnsteinUhlenbeck(Field):
@@ -118,6 +143,9 @@ class OrnsteinUhlenbeck(Field):
     def params(self):
         return self.p
 
+    def cpp_functor(self, dim, bm_dim):
+        return "::dfx::OuField" if dim == 1 else f"::dfx::OuDiagField<{dim}>"
+
 
 class GeometricBrownianMotion(Field):
     """dy = mu y dt + sigma y dW: state-dependent (multiplicative) diagonal diffusion with a scalar Brownian motion -
@@ -130,6 +158,9 @@ class GeometricBrownianMotion(Field):
 
     def params(self):
         return self.p
+
+    def cpp_functor(self, dim, bm_dim):
+        return f"::dfx::GbmField<{dim}>"
 
 
 class OrnsteinUhlenbeckMatrix(Field):
@@ -152,6 +183,9 @@ class OrnsteinUhlenbeckMatrix(Field):
 
     def params(self):
         return self.p
+
+    def cpp_functor(self, dim, bm_dim):
+        return f"::dfx::OuMatrixField<{self.dim}, {self.m}>"
 
 
 class MLP(Field):
@@ -344,3 +378,41 @@ class CudaField(Field):
             if not L.dfx_has_kernel(self._id, self.dim, int(solver_id), int(dtype_id), int(levy)):
                 raise RuntimeError(f"{path} was loaded but registered no launcher for this combination")
         self._ready.add(key)
+
+
+_BUILTIN_TU = r"""// generated by diffrax_b200.fields.ensure_builtin_kernel - do not edit
+#include "launch.cuh"
+namespace {
+using F = @FUNCTOR@;
+DFX_REGISTER(@REAL@, F, @SOLVER@, @LEVY@)
+}  // namespace
+"""
+
+
+def ensure_builtin_kernel(field, dim, solver_id, dtype_id, levy, bm_dim):
+    """The shipped library prebuilds the (field, solver, dtype, Levy area) combinations of csrc/inst_*.cu; any other
+    combination of a built-in functor with a solver - HalfSolver(Midpoint()), Euler on a vector OU process, LinearDecay with
+    d = 5, ... - is instantiated here the first time it is asked for: one generated translation unit with ONE DFX_REGISTER,
+    nvcc for sm_100a (~6 s), cached under lib/user/, dlopen.  `DFX_JIT=0` disables it (the solve then fails with "no kernel
+    registered").  Returns True when a kernel is available afterwards."""
+    import os
+    L = _lib.lib()
+    if L.dfx_has_kernel(field.field_id, dim, int(solver_id), int(dtype_id), int(levy)):
+        return True
+    functor = field.cpp_functor(dim, bm_dim)
+    inner = solver_id & ~_HALF
+    if functor is None or inner not in _SOLVER_CPP or os.environ.get("DFX_JIT", "1") == "0":
+        return False
+    if bool(levy) and not field.is_sde:
+        return False
+    if inner == 8 and (levy != _lib.LEVY_STLA or field.name == "gbm"):
+        return False   # refused by the argument checks of the C ABI with the reference's messages (srk.py:391-395, shark.py:10-30)
+    solver = _SOLVER_CPP[inner]
+    if solver_id & _HALF:
+        solver = f"::dfx::HalfOf<{solver}>"
+    src = _BUILTIN_TU.replace("@FUNCTOR@", functor).replace("@REAL@", "double" if dtype_id == _lib.F64 else "float")
+    src = src.replace("@SOLVER@", solver).replace("@LEVY@", str(int(levy)))
+    from . import build
+    tag = f"builtin_{field.field_id}_{dim}_{int(solver_id):x}_{int(dtype_id)}_{int(levy)}"
+    _lib.load_plugin(build.build_user_field(tag, src))
+    return bool(L.dfx_has_kernel(field.field_id, dim, int(solver_id), int(dtype_id), int(levy)))

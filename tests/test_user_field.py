@@ -172,3 +172,47 @@ def test_user_field_with_events_dense_and_sharded_entry(dev):
     assert np.abs(_np(evs.ts)[:, -1] - t_exact).max() < 1e-7
     sh = dfx.sharded_diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl)
     assert torch.equal(sh.y_final, sol.ys[:, -1]) and int(sh.stats["num_failed"]) == 0
+
+
+def test_builtin_combination_is_instantiated_on_first_use():
+    """(field, solver, dtype) pairs that csrc/inst_*.cu does not prebuild are compiled when first asked for - through `prepare`,
+    which needs no GPU."""
+    from diffrax_b200 import fields
+    L = _lib.lib()
+    half_mid = dfx.HalfSolver(dfx.Midpoint())
+    dfx.prepare(dfx.ODETerm(dfx.fields.VanDerPol(1.0)), half_mid, 0.0, 1.0, 0.1, np.ones((4, 2), np.float32),
+                stepsize_controller=dfx.PIDController(1e-3, 1e-5))
+    assert L.dfx_has_kernel(_lib.FIELD_IDS["vdp"], 2, half_mid.solver_id, _lib.F32, 0) == 1
+    assert fields.ensure_builtin_kernel(dfx.fields.LinearDecay(), 5, 1, _lib.F64, 0, 0)          # LinearDecay with d = 5
+    # combinations the C ABI refuses with the reference's message are not compiled
+    assert not fields.ensure_builtin_kernel(dfx.fields.GeometricBrownianMotion(), 1, 8, _lib.F64, _lib.LEVY_STLA, 0)
+    assert not fields.ensure_builtin_kernel(dfx.fields.Lorenz(), 3, 1, _lib.F64, _lib.LEVY_BI, 0)  # not an SDE functor
+
+
+@pytest.mark.gpu
+def test_on_demand_builtin_kernels_against_the_oracle(dev):
+    rng = np.random.default_rng(3)
+    # HalfSolver(Midpoint) on van der Pol, fp64, adaptive
+    y0 = rng.uniform(0.5, 2.0, (64, 2))
+    sol = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.VanDerPol(1.3)), dfx.HalfSolver(dfx.Midpoint()), 0.0, 2.0, 0.05, torch.tensor(y0, device=dev),
+                          stepsize_controller=dfx.PIDController(rtol=1e-5, atol=1e-7), saveat=dfx.SaveAt(ts=[0.5, 1.0, 2.0]))
+    o = oracle.solve("vdp", y0, 0.0, 2.0, 0.05, solver="half:midpoint", params=[1.3], rtol=1e-5, atol=1e-7, save_ts=[0.5, 1.0, 2.0], save_t1=False)
+    st = np.stack([_np(sol.stats[k]) for k in ("num_steps", "num_accepted_steps", "num_rejected_steps")], 1)
+    same = np.all(st == o["stats"], axis=1)
+    assert same.mean() > 0.9 and np.abs(_np(sol.ys)[same] - o["ys"][same]).max() < 1e-9
+    # LinearDecay with d = 5 (prebuilt: 1..3), Dopri5 at fixed steps
+    y5 = rng.uniform(0.5, 2.0, (40, 5))
+    sol = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.LinearDecay(0.7)), dfx.Dopri5(), 0.0, 1.0, 0.125, torch.tensor(y5, device=dev))
+    o = oracle.solve("decay", y5, 0.0, 1.0, 0.125, solver="dopri5", params=[0.7], controller="constant")
+    assert np.abs(_np(sol.ys) - o["ys"]).max() < 1e-14 and np.abs(_np(sol.ys)[:, 0] - y5 * np.exp(-0.7)).max() < 1e-7
+    # Euler-Maruyama on a 3-dimensional OU process with shape (3,) noise: the Brownian increments are bit-exact, so is the path
+    n = 50
+    keys = np.random.default_rng(4).integers(0, 2 ** 32, (n, 2), dtype=np.uint64).astype(np.uint32)
+    ou = dfx.fields.OrnsteinUhlenbeck(1.2, 0.3, 0.4)
+    bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -8, (3,), torch.tensor(keys.view(np.int32), device=dev))
+    y3 = rng.uniform(0.5, 2.0, (n, 3))
+    sol = dfx.diffeqsolve(dfx.MultiTerm(dfx.ODETerm(ou.drift), dfx.ControlTerm(ou.diffusion, bm)), dfx.Euler(), 0.0, 1.0, 2.0 ** -6,
+                          torch.tensor(y3, device=dev))
+    o = oracle.solve("ou", y3, 0.0, 1.0, 2.0 ** -6, solver="euler", params=[1.2, 0.3, 0.4], controller="constant", levy_area="bi", keys=keys,
+                     bm_t0=0.0, bm_t1=1.0, bm_tol=2.0 ** -8, bm_dim=3)
+    assert np.abs(_np(sol.ys) - o["ys"]).max() < 1e-13

@@ -29,7 +29,8 @@ ODE_FIELDS = {
 }
 SOLVERS = {"tsit5": dfx.Tsit5, "dopri5": dfx.Dopri5, "dopri8": dfx.Dopri8, "heun": dfx.Heun, "bosh3": dfx.Bosh3,
            "midpoint": dfx.Midpoint, "ralston": dfx.Ralston, "euler": dfx.Euler, "shark": dfx.ShARK}
-ADAPTIVE = ["tsit5", "dopri5", "dopri8", "heun", "bosh3", "half:heun", "half:euler", "half:midpoint", "half:ralston"]
+ADAPTIVE = ["tsit5", "dopri5", "dopri8", "heun", "bosh3", "half:heun", "half:euler", "half:midpoint", "half:ralston", "half:bosh3",
+            "half:tsit5"]
 FIXED = ["tsit5", "dopri5", "heun", "bosh3", "midpoint", "ralston", "euler", "half:euler"]
 
 
@@ -94,6 +95,11 @@ def random_case(r):
         c["rtol"] = float(10.0 ** r.uniform(-5 if f32 else -9, -3))
         c["atol"] = float(10.0 ** r.uniform(-6 if f32 else -10, -4))
         c["dt0"] = None if r.random() < 0.5 else sign * span * float(r.choice([0.01, 0.1, 1.0]))
+        if c["solver"] in ("half:tsit5", "half:bosh3"):
+            # step doubling around a 3rd / 5th order method: with the default first step of 0.01 the two results y1 and y1_alt
+            # agree to the last place or differ by one ulp - |y1 - y1_alt| in {0, ulp} is pure rounding noise, and the reference's
+            # factor is factormax for 0 (1 / 0 = inf, pid.py:498) but ~4 for one ulp.  Start these with a step that has an error
+            c["dt0"] = sign * span * 0.25
         if r.random() < 0.4:
             c["pcoeff"], c["icoeff"], c["dcoeff"] = float(r.choice([0.0, 0.1, 0.4])), float(r.choice([1.0, 0.3])), float(r.choice([0.0, 0.05]))
         if r.random() < 0.15:
@@ -170,6 +176,26 @@ def run_oracle(c, **over):
     return oracle.solve(c["field"], c["y0"], c["t0"], c["t1"], c["dt0"], **kw)
 
 
+def sensitivity2(c, o):
+    """Second tier, adaptive solves only.  The embedded error estimate is a difference of nearly equal numbers (for HalfSolver
+    literally |y1 - y1_alt|), so its RELATIVE rounding noise is eps |y| / |err| - 1e-6 and more in fp64 when a step is far more
+    accurate than asked for - and it differs between the GPU's contracted FMAs and the oracle.  A 1-ulp probe of y0 moves
+    y1 and y1_alt together and does not see it; scaling the tolerances by (1 +- 1e-6) (fp64) / (1 +- 1e-3) (fp32) does: it is the
+    same perturbation of err / tolerance."""
+    if c["controller"] != "pid":
+        return 1.0, 0.0, 0.0
+    h = 1e-3 if c["dtype"] == np.float32 else 1e-6
+    frac, sy, st = 1.0, 0.0, 0.0
+    for sgn in (1.0, -1.0):
+        f = run_oracle(c, rtol=c["rtol"] * (1 + sgn * h), atol=c["atol"] * (1 + sgn * h))
+        same = np.all(f["stats"] == o["stats"], axis=1) & (f["result"] == o["result"])
+        if not same.any():
+            return 0.0, np.inf, np.inf
+        frac = min(frac, float(same.mean()))
+        sy, st = max(sy, relerr(f["ys"][same], o["ys"][same])), max(st, relerr(f["ts"][same], o["ts"][same]))
+    return frac, sy, st
+
+
 def sensitivity(c, o):
     """The oracle's own rounding sensitivity on this case: strict IEEE sequencing against the FMA-contracted build (the two
     differ the way the CUDA compiler's contraction differs from the oracle).  Returns (fraction of trajectories whose step
@@ -192,6 +218,9 @@ def sensitivity(c, o):
     return frac, sy, st
 
 
+TIER2 = []
+
+
 def check(c, sol, o):
     msgs = check_raw(c, sol, o)
     if not msgs:
@@ -204,6 +233,10 @@ def check(c, sol, o):
     e_t = relerr(ts[same], o["ts"][same]) if same.any() else 0.0
     # explained by rounding sensitivity: the two oracle builds disagree about as much as the GPU and the oracle do
     if e_y <= 64 * sy + 1e-300 and e_t <= 64 * st_ + (1e-6 if c["dtype"] == np.float32 else 1e-13) and same.mean() >= min(0.9, frac) - 0.25:
+        return []
+    frac2, sy2, st2 = sensitivity2(c, o)
+    if e_y <= 8 * sy2 + 1e-300 and e_t <= 8 * st2 + (1e-6 if c["dtype"] == np.float32 else 1e-13) and same.mean() >= min(0.9, frac2) - 0.25:
+        TIER2.append(1)
         return []
     return msgs + [f"(oracle vs its own fma / safety+-1ulp / y0+-1ulp probes: stats agree {frac:.3f}, ys {sy:.2e}, ts {st_:.2e}; gpu vs oracle: stats agree {same.mean():.3f}, ys {e_y:.2e}, ts {e_t:.2e})"]
 
@@ -239,7 +272,24 @@ def main():
     ap.add_argument("--cases", type=int, default=300)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--prebuild", action="store_true", help="no GPU needed: compile (in parallel) the kernels that the cases will "
+                    "instantiate on first use, so that a following GPU run finds them under diffrax_b200/lib/user/")
     a = ap.parse_args()
+    if a.prebuild:
+        import concurrent.futures as cf
+        r = np.random.default_rng(a.seed)
+        cases = [random_case(r) for _ in range(a.cases)]
+
+        def one(c):
+            try:
+                run_gpu({**c, "host": True}, None)
+            except Exception as e:  # noqa: BLE001  (without a GPU every case ends in "CUDA device not available" - after the build)
+                return str(e)[:80]
+            return "ok"
+        with cf.ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+            out = list(ex.map(one, cases))
+        print("prebuild:", {k: out.count(k) for k in sorted(set(out))})
+        return
     dev = torch.device("cuda:0")
     r = np.random.default_rng(a.seed)
     bad = skipped = 0
@@ -270,7 +320,8 @@ def main():
             print(f"[{i}] ok {tag}")
     for k, v in sorted(refusals.items()):
         print(f"refused x{v}: {k}")
-    print(f"fuzz_parity: {a.cases} cases, {skipped} refused by the facade, {bad} failures (seed {a.seed})")
+    print(f"fuzz_parity: {a.cases} cases, {skipped} refused by the facade, {bad} failures (seed {a.seed}); "
+          f"{len(TIER2)} cases needed the tolerance-scaling probe (error-estimate cancellation noise)")
     sys.exit(1 if bad else 0)
 
 
