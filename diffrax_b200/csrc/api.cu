@@ -873,7 +873,7 @@ int dfx_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, con
                      int bm_dim, void *stream) {
   if (n <= 0) return 0;
   if (!(bm_t0 < bm_t1)) { set_error("t0 must be strictly less than t1"); return DFX_ERR_BAD_ARGUMENT; }
-  if (bm_dim < 0 || bm_dim > 4) { set_error("VirtualBrownianTree shape () or (m,) with m <= 4, got m = %d", bm_dim); return DFX_ERR_BAD_ARGUMENT; }
+  if (bm_dim < 0 || bm_dim > kMaxDim) { set_error("VirtualBrownianTree shape () or (m,) with m <= %d, got m = %d", kMaxDim, bm_dim); return DFX_ERR_BAD_ARGUMENT; }
   VbtParams vp;
   vp.t0 = bm_t0; vp.t1 = bm_t1; vp.levy = levy_area; vp.partitionable = partitionable;
   vp.cache_levels = 0; vp.cache_stride = 0;
@@ -884,7 +884,10 @@ int dfx_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, con
   cudaStream_t st = (cudaStream_t)stream;
   const bool stla = levy_area == DFX_LEVY_SPACE_TIME;
 #define DFX_VBT_CASE(M) case M: if (dtype == DFX_F64) launch_vbt<double, M>(stla, n, keys, vp, ta, tb, per_traj_times, W, H, st); else launch_vbt<float, M>(stla, n, keys, vp, ta, tb, per_traj_times, W, H, st); break;
-  switch (bm_dim == 0 ? 1 : bm_dim) { DFX_VBT_CASE(1) DFX_VBT_CASE(2) DFX_VBT_CASE(3) DFX_VBT_CASE(4) }
+  switch (bm_dim == 0 ? 1 : bm_dim) {
+    DFX_VBT_CASE(1) DFX_VBT_CASE(2) DFX_VBT_CASE(3) DFX_VBT_CASE(4)
+    DFX_VBT_CASE(5) DFX_VBT_CASE(6) DFX_VBT_CASE(7) DFX_VBT_CASE(8)
+  }
 #undef DFX_VBT_CASE
   count_launch();
   DFX_CUDA_OK(cudaGetLastError());

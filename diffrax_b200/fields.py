@@ -311,8 +311,8 @@ class CudaField(Field):
         self.noise_dim = 1 if not self.is_sde else (int(noise_dim) if noise_dim else (self.dim if diffusion is not None else 1))
         if diffusion is not None and self.noise_dim not in (1, self.dim):
             raise ValueError("CudaField: additive `diffusion` is scalar (dim 1) or diagonal (noise_dim == dim)")
-        if self.is_sde and not 1 <= self.noise_dim <= 4:
-            raise ValueError("CudaField: 1 <= noise_dim <= 4")
+        if self.is_sde and not 1 <= self.noise_dim <= 8:
+            raise ValueError("CudaField: 1 <= noise_dim <= 8")
         self.min_blocks = None if min_blocks_per_sm is None else int(min_blocks_per_sm)
         if self.min_blocks is not None and not 1 <= self.min_blocks <= 16:
             raise ValueError("CudaField: 1 <= min_blocks_per_sm <= 16")

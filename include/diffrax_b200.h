@@ -228,7 +228,7 @@ int dfx_ensemble_solve(const dfx_solve_desc *desc, void *cuda_stream);
 int dfx_ensemble_solve_host(const dfx_solve_desc *desc, int device);
 
 /* replaces VirtualBrownianTree.evaluate(t0, t1, use_levy=True) vmapped over keys
- * (tree.py:326-354).  ta/tb: [n] if per_traj_times else [1].  bm_dim: 0 = shape (), m = shape (m,) (m <= 4).
+ * (tree.py:326-354).  ta/tb: [n] if per_traj_times else [1].  bm_dim: 0 = shape (), m = shape (m,) (m <= 8).
  * W, H: [n] or [n, m]; H may be NULL. */
 int dfx_vbt_evaluate(int dtype, int levy_area, int partitionable, int64_t n, const uint32_t *keys,
                      double bm_t0, double bm_t1, double bm_tol, const void *ta, const void *tb,

@@ -189,7 +189,7 @@ def test_normals_bit_exact(dev, cuda_lib, part, m, tag, tdt, did):
 
 @pytest.mark.parametrize("lv,cls", [("bi", dfx.BrownianIncrement), ("stla", dfx.SpaceTimeLevyArea)])
 @pytest.mark.parametrize("tag,tdt", [("f64", torch.float64), ("f32", torch.float32)])
-@pytest.mark.parametrize("m", [0, 3])
+@pytest.mark.parametrize("m", [0, 3, 8])
 @pytest.mark.parametrize("part", [True, False])
 def test_vbt_increments_bit_exact(dev, lv, cls, tag, tdt, m, part):
     """north star: 'Brownian/PRNG increments bit-exact'.  W (and H) of VirtualBrownianTree.evaluate, shape () and (m,), both

@@ -216,3 +216,11 @@ def test_on_demand_builtin_kernels_against_the_oracle(dev):
     o = oracle.solve("ou", y3, 0.0, 1.0, 2.0 ** -6, solver="euler", params=[1.2, 0.3, 0.4], controller="constant", levy_area="bi", keys=keys,
                      bm_t0=0.0, bm_t1=1.0, bm_tol=2.0 ** -8, bm_dim=3)
     assert np.abs(_np(sol.ys) - o["ys"]).max() < 1e-13
+    # ... and with 6 components (shape (6,)), Heun + space-time Levy area, fp32
+    y6 = rng.uniform(0.5, 2.0, (n, 6)).astype(np.float32)
+    bm = dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -7, (6,), torch.tensor(keys.view(np.int32), device=dev), dfx.SpaceTimeLevyArea)
+    sol = dfx.diffeqsolve(dfx.MultiTerm(dfx.ODETerm(ou.drift), dfx.ControlTerm(ou.diffusion, bm)), dfx.Heun(), 0.0, 1.0, 2.0 ** -5,
+                          torch.tensor(y6, device=dev))
+    o = oracle.solve("ou", y6, 0.0, 1.0, 2.0 ** -5, solver="heun", params=[1.2, 0.3, 0.4], controller="constant", levy_area="stla", keys=keys,
+                     bm_t0=0.0, bm_t1=1.0, bm_tol=2.0 ** -7, bm_dim=6, dtype=np.float32)
+    assert np.abs(_np(sol.ys) - o["ys"]).max() < 2e-6
