@@ -345,9 +345,10 @@ class Event:
                 return [v for e in x for v in flat(e)]
             return [x]
         conds = flat(cond_fn)
-        if not conds or not all(isinstance(c, (AffineEvent, SteadyStateEvent)) for c in conds):
-            raise TypeError("Event(cond_fn): cond_fn must be an AffineEvent / steady_state_event(...) or a list / tuple / dict "
-                            "of them (condition functions are registered device functors)")
+        from .fields import UserEvent
+        if not conds or not all(isinstance(c, (AffineEvent, SteadyStateEvent, UserEvent)) for c in conds):
+            raise TypeError("Event(cond_fn): cond_fn must be an AffineEvent / steady_state_event(...) / `CudaField(events=[...]).event(i)` "
+                            "or a list / tuple / dict of them (condition functions are device functors)")
         if len(conds) > _lib.MAX_EVENTS:
             raise NotImplementedError(f"at most {_lib.MAX_EVENTS} condition functions per Event")
         if direction in (None, False, True):
@@ -910,6 +911,9 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         ensure_builtin_kernel(field, d, int(D.solver_id), int(D.dtype), int(D.levy_area), int(D.bm_dim))
 
     if event is not None:
+        for c in event._conds:
+            if getattr(c, "field", field) is not field:
+                raise ValueError("Event: a `CudaField.event(i)` condition belongs to the functor it was defined on; the terms use another one")
         ev_params = np.ascontiguousarray(np.concatenate([np.asarray(c.params(d, ctrl), np.float64) for c in event._conds]))
         keep_alive.append(ev_params)
         D.n_events, D.event_params, D.n_event_params = len(event._conds), ev_params.ctypes.data, ev_params.size

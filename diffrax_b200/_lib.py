@@ -17,7 +17,7 @@ ABI_VERSION = 2
 F64, F32 = 0, 1
 CTRL_CONSTANT, CTRL_PID = 0, 1
 LEVY_NONE, LEVY_BI, LEVY_STLA = 0, 1, 2
-EVENT_NONE, EVENT_AFFINE, EVENT_STEADY_STATE = 0, 1, 2
+EVENT_NONE, EVENT_AFFINE, EVENT_STEADY_STATE, EVENT_USER = 0, 1, 2, 3
 MAX_EVENTS = 4
 SOLVER_IDS = {"tsit5": 0, "dopri5": 1, "dopri8": 2, "heun": 3, "bosh3": 4, "midpoint": 5,
               "ralston": 6, "euler": 7, "shark": 8}

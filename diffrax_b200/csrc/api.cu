@@ -369,16 +369,17 @@ static int check_desc(const dfx_solve_desc *d) {
   }
   if (d->n_events != 0) {
     int need = 0;
-    bool ok = d->n_events > 0 && d->n_events <= DFX_MAX_EVENTS && d->dim <= 4 && d->event_params != nullptr;
+    bool ok = d->n_events > 0 && d->n_events <= DFX_MAX_EVENTS && d->event_params != nullptr;
     for (int i = 0; ok && i < d->n_events; ++i) {
-      if (d->event_kind[i] == DFX_EVENT_AFFINE) need += d->dim + 2;
+      if (d->event_kind[i] == DFX_EVENT_AFFINE) { need += d->dim + 2; ok = d->dim <= 4; }
       else if (d->event_kind[i] == DFX_EVENT_STEADY_STATE) need += 2;
+      else if (d->event_kind[i] == DFX_EVENT_USER) { need += 1; ok = d->field_id >= DFX_FIELD_USER; }
       else ok = false;
       if (d->event_direction[i] < 0 || d->event_direction[i] > 2) ok = false;
     }
     if (!ok || d->n_event_params != need) {
-      set_error("bad event description: 1..%d events of kind affine (dim + 2 params) / steady state (2 params), dim <= 4, "
-                "direction in {0,1,2}; got %d events, %d params (need %d)", DFX_MAX_EVENTS, d->n_events, d->n_event_params, need);
+      set_error("bad event description: 1..%d events of kind affine (dim + 2 params, dim <= 4) / steady state (2 params) / user "
+                "(1 param, user functors only), direction in {0,1,2}; got %d events, %d params (need %d)", DFX_MAX_EVENTS, d->n_events, d->n_event_params, need);
       return DFX_ERR_BAD_ARGUMENT;
     }
   }

@@ -67,6 +67,9 @@ template <class F> struct MatrixNoise<F, std::void_t<decltype(F::kMatrixNoise)>>
 // state-dependent (multiplicative) diffusion: Field::noise_prod(fp, t, y, W[NW], c) = component c of g(t, y) . W
 template <class F, class = void> struct StateNoise { static constexpr bool value = false; };
 template <class F> struct StateNoise<F, std::void_t<decltype(F::kStateNoise)>> { static constexpr bool value = F::kStateNoise; };
+// condition functions of the functor's own (Event(cond_fn) with an arbitrary cond_fn): Field::event<R>(fp, j, t, y), j < kUserEvents
+template <class F, class = void> struct UserEvents { static constexpr int value = 0; };
+template <class F> struct UserEvents<F, std::void_t<decltype(F::kUserEvents)>> { static constexpr int value = F::kUserEvents; };
 template <class T, class = void> struct IsHalf { static constexpr bool value = false; };
 template <class I> struct IsHalf<HalfOf<I>> { static constexpr bool value = true; };
 template <class T> struct InnerId { static constexpr int value = T::kId; };
@@ -106,6 +109,7 @@ struct SolveParams {
   int n_events, event_kind[DFX_MAX_EVENTS], event_dir[DFX_MAX_EVENTS], event_root;
   R ev_w[DFX_MAX_EVENTS][4], ev_b[DFX_MAX_EVENTS], ev_wt[DFX_MAX_EVENTS];  // affine: w . y + wt t + b
   R ev_ss_rtol[DFX_MAX_EVENTS], ev_ss_atol[DFX_MAX_EVENTS];               // steady state
+  int ev_user[DFX_MAX_EVENTS];                                            // user: index of the functor's condition
   R ev_rtol, ev_atol;                                                     // Newton root finder
   const R *state_in; R *state_out; int state_in_flags;  // resumed / returned controller + solver state, [N, 5 + d] (EXTRA only)
   int refill_batch;  // finished lanes wait until this many can be finalised + refilled in one pass (>= 1)
@@ -298,6 +302,10 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
 #pragma unroll
       for (int c = 0; c < D; ++c) v += p.ev_w[i][c < 4 ? c : 3] * yy[c];
       return v + p.ev_wt[i] * t + p.ev_b[i];
+    }
+    if (p.event_kind[i] == DFX_EVENT_USER) {
+      if constexpr (UserEvents<Field>::value > 0) return Field::template event<R>(fp, p.ev_user[i], t, yy);
+      else return R(0);
     }
     R f[D], nf = R(0), ny = R(0);
     Field::template eval<R>(fp, t * dir, yy, f);
@@ -971,12 +979,23 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
               if (p.event_root) {
                 R tf = st1;
                 bool ok = true;
-                if (p.event_kind[which] == DFX_EVENT_AFFINE) {
+                if (p.event_kind[which] == DFX_EVENT_AFFINE || p.event_kind[which] == DFX_EVENT_USER) {
                   // [EXT] optimistix.Newton(rtol, atol), options lower / upper = the step, y0 = its end, max_steps 256:
                   // clipped Newton steps; Cauchy termination on the iterate and on the function value
+                  const R fd_h = (st1 - st0) * (sizeof(R) == 8 ? R(1e-6) : R(1e-3));
                   auto along = [&](R t, R &g, R &dg) {
                     R yq[D], dq[D];
                     interp_eval<INTERP, R, S, D>(st0, st1, y, y1_dense, k, t, yq);
+                    if (p.event_kind[which] == DFX_EVENT_USER) {
+                      // the user's condition has no derivative to offer (the reference differentiates cond_fn by JVP): central
+                      // difference of t -> cond(t, interpolant(t)) over 1e-6 of the step (the root itself only depends on cond)
+                      g = event_cond(which, t, yq, direction);
+                      R ya[D], yb[D];
+                      interp_eval<INTERP, R, S, D>(st0, st1, y, y1_dense, k, t + fd_h, ya);
+                      interp_eval<INTERP, R, S, D>(st0, st1, y, y1_dense, k, t - fd_h, yb);
+                      dg = (event_cond(which, t + fd_h, ya, direction) - event_cond(which, t - fd_h, yb, direction)) / (R(2) * fd_h);
+                      return;
+                    }
                     interp_deriv<INTERP, R, S, D>(st0, st1, y, y1_dense, k, t, dq);
                     R v = R(0), dv = R(0);
 #pragma unroll

@@ -96,6 +96,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
       p.event_kind[i] = DFX_EVENT_NONE; p.event_dir[i] = 0;
       for (int c = 0; c < 4; ++c) p.ev_w[i][c] = R(0);
       p.ev_b[i] = p.ev_wt[i] = p.ev_ss_rtol[i] = p.ev_ss_atol[i] = R(0);
+      p.ev_user[i] = 0;
       if (i >= d->n_events) continue;
       p.event_kind[i] = d->event_kind[i]; p.event_dir[i] = d->event_direction[i];
       if (d->event_kind[i] == DFX_EVENT_AFFINE) {
@@ -105,6 +106,9 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
       } else if (d->event_kind[i] == DFX_EVENT_STEADY_STATE) {
         p.ev_ss_rtol[i] = (R)d->event_params[off]; p.ev_ss_atol[i] = (R)d->event_params[off + 1];
         off += 2;
+      } else if (d->event_kind[i] == DFX_EVENT_USER) {
+        p.ev_user[i] = (int)d->event_params[off];
+        off += 1;
       }
     }
   }
@@ -217,6 +221,11 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
+  for (int i = 0; i < d->n_events && i < DFX_MAX_EVENTS; ++i)
+    if (d->event_kind[i] == DFX_EVENT_USER && (p.ev_user[i] < 0 || p.ev_user[i] >= UserEvents<Field>::value)) {
+      set_error("event %d asks for condition %d of a functor that defines %d", i, p.ev_user[i], UserEvents<Field>::value);
+      return DFX_ERR_BAD_ARGUMENT;
+    }
   if constexpr (SDE) {
     // the Brownian motion's shape is compiled into the functor: shape () / (1,) -> 1 component, (m,) -> m
     if ((d->bm_dim == 0 ? 1 : d->bm_dim) != NoiseDim<Field>::value) {

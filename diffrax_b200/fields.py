@@ -242,6 +242,18 @@ _SOLVER_CPP = {0: "::dfx::Tsit5", 1: "::dfx::Dopri5", 2: "::dfx::Dopri8", 3: "::
                5: "::dfx::Midpoint", 6: "::dfx::Ralston", 7: "::dfx::EulerSolver", 8: "::dfx::SharkSolver"}
 _HALF = 0x100
 
+class UserEvent:
+    """Condition function number `index` of a `CudaField(events=[...])`, for `Event(cond_fn=...)` (_event.py:13-118): a
+    real-valued expression in `t`, `y[i]`, `p[i]`; the solve stops on the step where it changes sign."""
+    kind = _lib.EVENT_USER
+
+    def __init__(self, field, index):
+        self.field, self.index = field, int(index)
+
+    def params(self, d, ctrl):
+        return [float(self.index)]
+
+
 _USER_TU = r"""// generated by diffrax_b200.fields.CudaField - do not edit
 @DEFINES@
 #include "launch.cuh"
@@ -292,13 +304,15 @@ class CudaField(Field):
     * ``noise="<statements>"``, ``noise_dim=m``: the general ``ControlTerm.prod`` (_term.py:417-427): assign ``gx[0..dim)``, the
       product ``g(t, y) . x`` with the Brownian increment ``x[0..m)`` (``m = 1`` for shape ``()``) - Euler / Heun (Stratonovich).
 
-    ``preamble``: device helper functions / constants placed before the functor.  ``min_blocks_per_sm``: occupancy target handed
+    ``events=["<expr>", ...]``: real-valued condition functions in ``t``, ``y``, ``p`` for ``Event(field.event(i), ...)`` - the
+    reference's arbitrary ``cond_fn(t, y, args)`` (_event.py:13-118); with a root finder the crossing is located on the step's
+    interpolant.  ``preamble``: device helper functions / constants placed before the functor.  ``min_blocks_per_sm``: occupancy target handed
     to ptxas (``__launch_bounds__``) instead of the register-budget heuristic of csrc/ensemble_kernel.cuh - e.g. 6 for a
     3-dimensional fp64 field with a 7-stage solver (what the built-in Lorenz/Dopri5 kernel uses)."""
     is_user = True
 
     def __init__(self, dim, drift, *, params=(), diffusion=None, noise=None, noise_dim=None, preamble="", name=None,
-                 min_blocks_per_sm=None):
+                 min_blocks_per_sm=None, events=()):
         import hashlib
         self.dim = int(dim)
         if not 1 <= self.dim <= 8:
@@ -316,7 +330,10 @@ class CudaField(Field):
         self.min_blocks = None if min_blocks_per_sm is None else int(min_blocks_per_sm)
         if self.min_blocks is not None and not 1 <= self.min_blocks <= 16:
             raise ValueError("CudaField: 1 <= min_blocks_per_sm <= 16")
-        key = "\0".join([str(self.dim), self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble, str(len(self.p)),
+        self.event_srcs = [str(e) for e in events]
+        if len(self.event_srcs) > _lib.MAX_EVENTS:
+            raise ValueError(f"CudaField: at most {_lib.MAX_EVENTS} condition functions")
+        key = "\0".join(self.event_srcs + [str(self.dim), self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble, str(len(self.p)),
                          str(self.min_blocks)])
         self._hash = hashlib.sha256(key.encode()).hexdigest()[:16]
         self._id = _lib.FIELD_USER + int(self._hash[:7], 16)
@@ -329,6 +346,12 @@ class CudaField(Field):
 
     def params(self):
         return self.p
+
+    def event(self, index=0):
+        """The `index`-th expression of `events=[...]` as a condition function: `Event(field.event(0), Newton(1e-10, 1e-10))`."""
+        if not 0 <= index < len(self.event_srcs):
+            raise IndexError(f"this CudaField defines {len(self.event_srcs)} condition function(s)")
+        return UserEvent(self, index)
 
     def source(self, solver_id, dtype_id, levy):
         inner = solver_id & ~_HALF
@@ -347,6 +370,11 @@ class CudaField(Field):
             else:
                 fns = ("  template <class R> static __device__ __forceinline__ R diffusion(const P<R> &P_, R t) {\n"
                        f"    [[maybe_unused]] const R *p = P_.p;\n    (void)t;\n    return (R)({self.diffusion_src});\n  }}\n")
+        if self.event_srcs:
+            traits += f"  static constexpr int kUserEvents = {len(self.event_srcs)};\n"
+            cases = "".join(f"      case {i}: return (R)({e});\n" for i, e in enumerate(self.event_srcs))
+            fns += (f"  template <class R> static __device__ __forceinline__ R event(const P<R> &P_, int i, R t, const R (&y)[{self.dim}]) {{\n"
+                    f"    [[maybe_unused]] const R *p = P_.p;\n    (void)t;\n    switch (i) {{\n{cases}    }}\n    return R(0);\n  }}\n")
         rep = {"@DEFINES@": "" if self.min_blocks is None else f"#define DFX_MIN_BLOCKS {self.min_blocks}",
                "@PREAMBLE@": self.preamble, "@ID@": str(self._id), "@DIM@": str(self.dim), "@SDE@": "true" if self.is_sde else "false",
                "@NP@": str(np_), "@NP1@": str(max(np_, 1)), "@NOISE_TRAITS@": traits, "@DRIFT@": self.drift_src, "@NOISE_FNS@": fns,

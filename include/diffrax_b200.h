@@ -59,7 +59,7 @@ enum dfx_result { DFX_RESULT_SUCCESSFUL = 0, DFX_RESULT_MAX_STEPS_REACHED = 1,
                   DFX_RESULT_DT_MIN_REACHED = 2, DFX_RESULT_EVENT_OCCURRED = 3 /* not a failure: _solution.py:52-62 is_okay */,
                   DFX_RESULT_EVENT_ROOT_FIND_FAILED = 4, DFX_RESULT_MAX_STEPS_REJECTED = 5 /* _solution.py:24-27 */,
                   DFX_RESULT_INTERNAL_ERROR = 6 };
-enum dfx_event { DFX_EVENT_NONE = 0, DFX_EVENT_AFFINE = 1, DFX_EVENT_STEADY_STATE = 2 };
+enum dfx_event { DFX_EVENT_NONE = 0, DFX_EVENT_AFFINE = 1, DFX_EVENT_STEADY_STATE = 2, DFX_EVENT_USER = 3 };
 #define DFX_MAX_EVENTS 4
 #define DFX_MAX_PEERS 8
 
@@ -151,6 +151,9 @@ typedef struct dfx_solve_desc {
    * cond_fn(tprev, y, ...):
    *   DFX_EVENT_AFFINE        c(t, y) = w . y + wt * t + b        params [w[0..d), b, wt]  real-valued: sign change
    *   DFX_EVENT_STEADY_STATE  rms(f(t, y)) < atol + rtol * rms(y)  params [rtol, atol]      boolean (_event.py:120-170)
+   *   DFX_EVENT_USER          the functor's own event<R>(params, j, t, y) params [j]               real-valued: sign change
+   *                           (user functors with kUserEvents > 0, e.g. fields.CudaField(events=[...]); the root find
+   *                           differentiates it along the interpolant by central differences)
    * event_params holds the parameters of event 0, 1, ... back to back (host doubles).
    * event_direction[i]: 0 = None (any crossing), 1 = True (upcrossing), 2 = False (downcrossing).
    * event_root_find: 0 = root_finder None (the solve ends at the end of the triggering step); 1 = Newton(event_rtol,

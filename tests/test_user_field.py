@@ -224,3 +224,45 @@ def test_on_demand_builtin_kernels_against_the_oracle(dev):
     o = oracle.solve("ou", y6, 0.0, 1.0, 2.0 ** -5, solver="heun", params=[1.2, 0.3, 0.4], controller="constant", levy_area="stla", keys=keys,
                      bm_t0=0.0, bm_t1=1.0, bm_tol=2.0 ** -7, bm_dim=6, dtype=np.float32)
     assert np.abs(_np(sol.ys) - o["ys"]).max() < 2e-6
+
+
+def test_user_event_source_and_checks():
+    osc = dfx.fields.CudaField(2, "f[0] = y[1]; f[1] = -p[0] * y[0];", params=[4.0], events=["y[0] * y[1]", "y[0] - p[0] * t"])
+    plain = dfx.fields.CudaField(2, "f[0] = y[1]; f[1] = -p[0] * y[0];", params=[4.0])
+    assert osc.field_id != plain.field_id                                   # the conditions are part of the functor
+    src = osc.source(0, _lib.F64, 0)
+    assert "kUserEvents = 2" in src and "case 1: return (R)(y[0] - p[0] * t);" in src
+    ev = dfx.Event([osc.event(0), osc.event(1)], dfx.Newton(1e-10, 1e-10), direction=[False, None])
+    p = dfx.prepare(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 1.0, 0.1, np.ones((3, 2)), stepsize_controller=dfx.PIDController(1e-6, 1e-6), event=ev)
+    assert p.desc.n_events == 2 and list(p.desc.event_kind)[:2] == [_lib.EVENT_USER, _lib.EVENT_USER]
+    with pytest.raises(IndexError):
+        osc.event(2)
+    with pytest.raises(ValueError, match="belongs to the functor"):
+        dfx.prepare(dfx.ODETerm(plain), dfx.Tsit5(), 0.0, 1.0, 0.1, np.ones((3, 2)), event=dfx.Event(osc.event(0)))
+
+
+@pytest.mark.gpu
+def test_user_event_conditions(dev):
+    """Event(cond_fn) with the user's own condition: x v changes sign first where v does (the turning point, t = phi / 2 for
+    x = a cos 2t + (b/2) sin 2t, phi = atan2(b/2, a)); and `y[0]` as a user condition finds the crossing AffineEvent([1, 0]) finds."""
+    rng = np.random.default_rng(9)
+    y0n = rng.uniform(0.5, 1.5, (200, 2))
+    y0 = torch.tensor(y0n, device=dev)
+    osc = dfx.fields.CudaField(2, "f[0] = y[1]; f[1] = -p[0] * y[0];", params=[4.0], events=["y[0] * y[1]", "y[0]"])
+    ctrl = dfx.PIDController(rtol=1e-10, atol=1e-10)
+    a = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl,
+                        event=dfx.Event(osc.event(0), dfx.Newton(1e-12, 1e-12)))
+    assert bool(dfx.is_event(a.result).all())
+    phi = np.arctan2(y0n[:, 1] / 2, y0n[:, 0])
+    assert np.abs(_np(a.ts)[:, -1] - phi / 2).max() < 1e-8
+    assert np.abs(_np(a.ys)[:, -1, 1]).max() < 1e-7                                   # v = 0 there
+    b = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl,
+                        event=dfx.Event(osc.event(1), dfx.Newton(1e-12, 1e-12), direction=False))
+    c = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl,
+                        event=dfx.Event(dfx.AffineEvent([1.0, 0.0]), dfx.Newton(1e-12, 1e-12), direction=False))
+    assert torch.equal(b.stats["num_steps"], c.stats["num_steps"]) and torch.equal(b.result, c.result)
+    assert np.abs(_np(b.ts) - _np(c.ts)).max() < 1e-10 and np.abs(_np(b.ys) - _np(c.ys)).max() < 1e-9
+    # without a root finder: the solve ends at the end of the triggering step, exactly as with the affine condition
+    b = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl, event=dfx.Event(osc.event(1)))
+    c = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl, event=dfx.Event(dfx.AffineEvent([1.0, 0.0])))
+    assert torch.equal(b.ts, c.ts) and torch.equal(b.ys, c.ys)
