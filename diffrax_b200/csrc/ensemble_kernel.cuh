@@ -262,6 +262,9 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
 #ifndef DFX_OPT_EARLY_STAGE
 #define DFX_OPT_EARLY_STAGE 0   // SaveAt(dense): write each stage value to the staging record as soon as it exists
 #endif
+#ifndef DFX_OPT_FAST_PID
+#define DFX_OPT_FAST_PID 1      // the division- / pow-free I-controller path of fp64 ODE solves (and with it the SPEC instantiations)
+#endif
 #ifndef DFX_OPT_LAST_STAGE_F
 #define DFX_OPT_LAST_STAGE_F 1
 #endif
@@ -272,7 +275,7 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
   constexpr int INTERP = Solver::kInterp;
   constexpr int NW = NoiseDim<Field>::value;  // Brownian components: 1 (shape=()) or D (shape=(D,), diagonal diffusion)
   constexpr bool DENSE_K = INTERP != kInterpLinear;
-  constexpr bool FAST_PID = TAB && !SDE && sizeof(R) == 8;  // fp64 ODE solves: division-/pow-free I-controller path
+  constexpr bool FAST_PID = DFX_OPT_FAST_PID && TAB && !SDE && sizeof(R) == 8;  // fp64 ODE solves: division-/pow-free I-controller path
 
   // ---- per-lane trajectory state (registers) ----
   bool active = false, exhausted = false;

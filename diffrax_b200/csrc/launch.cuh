@@ -265,7 +265,7 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   if (p.totals) DFX_CUDA_OK(cudaMemsetAsync(p.totals, 0, 4 * sizeof(long long), stream));
   int rc;
   // fp64 ODE solves with the default controller configuration run the specialised instantiations (see SPEC)
-  constexpr bool kHasSpec = IsTableau<Solver>::value && !IsHalf<Solver>::value && !SDE && sizeof(R) == 8;
+  constexpr bool kHasSpec = DFX_OPT_FAST_PID && IsTableau<Solver>::value && !IsHalf<Solver>::value && !SDE && sizeof(R) == 8;
   bool spec = false;
   if constexpr (kHasSpec) spec = p.controller == DFX_CTRL_PID && p.fast_pid && !p.has_dtmin && !p.has_dtmax;
   if (extra) rc = launch_variant<R, Field, Solver, LEVY, true, true>(p, fp, stream);

@@ -312,7 +312,7 @@ class CudaField(Field):
     is_user = True
 
     def __init__(self, dim, drift, *, params=(), diffusion=None, noise=None, noise_dim=None, preamble="", name=None,
-                 min_blocks_per_sm=None, events=()):
+                 min_blocks_per_sm=None, events=(), defines=None):
         import hashlib
         self.dim = int(dim)
         if not 1 <= self.dim <= 8:
@@ -330,10 +330,13 @@ class CudaField(Field):
         self.min_blocks = None if min_blocks_per_sm is None else int(min_blocks_per_sm)
         if self.min_blocks is not None and not 1 <= self.min_blocks <= 16:
             raise ValueError("CudaField: 1 <= min_blocks_per_sm <= 16")
+        # `defines`: preprocessor switches of csrc/ensemble_kernel.cuh for THIS functor's kernels, e.g. the reference's plain
+        # operation order {"DFX_OPT_CHAIN_Y0": 0, "DFX_OPT_LAST_STAGE_F": 0, "DFX_OPT_FAST_PID": 0, "DFX_OPT_ABSMAX_FP64": 0}
+        self.defines = dict(defines or {})
         self.event_srcs = [str(e) for e in events]
         if len(self.event_srcs) > _lib.MAX_EVENTS:
             raise ValueError(f"CudaField: at most {_lib.MAX_EVENTS} condition functions")
-        key = "\0".join(self.event_srcs + [str(self.dim), self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble, str(len(self.p)),
+        key = "\0".join(self.event_srcs + [repr(sorted(self.defines.items())), str(self.dim), self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble, str(len(self.p)),
                          str(self.min_blocks)])
         self._hash = hashlib.sha256(key.encode()).hexdigest()[:16]
         self._id = _lib.FIELD_USER + int(self._hash[:7], 16)
@@ -375,7 +378,8 @@ class CudaField(Field):
             cases = "".join(f"      case {i}: return (R)({e});\n" for i, e in enumerate(self.event_srcs))
             fns += (f"  template <class R> static __device__ __forceinline__ R event(const P<R> &P_, int i, R t, const R (&y)[{self.dim}]) {{\n"
                     f"    [[maybe_unused]] const R *p = P_.p;\n    (void)t;\n    switch (i) {{\n{cases}    }}\n    return R(0);\n  }}\n")
-        rep = {"@DEFINES@": "" if self.min_blocks is None else f"#define DFX_MIN_BLOCKS {self.min_blocks}",
+        defs = "".join(f"#define {k} {v}\n" for k, v in sorted(self.defines.items()))
+        rep = {"@DEFINES@": defs + ("" if self.min_blocks is None else f"#define DFX_MIN_BLOCKS {self.min_blocks}"),
                "@PREAMBLE@": self.preamble, "@ID@": str(self._id), "@DIM@": str(self.dim), "@SDE@": "true" if self.is_sde else "false",
                "@NP@": str(np_), "@NP1@": str(max(np_, 1)), "@NOISE_TRAITS@": traits, "@DRIFT@": self.drift_src, "@NOISE_FNS@": fns,
                "@REAL@": "double" if dtype_id == _lib.F64 else "float", "@SOLVER@": solver, "@LEVY@": str(int(levy))}

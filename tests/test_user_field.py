@@ -266,3 +266,38 @@ def test_user_event_conditions(dev):
     b = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl, event=dfx.Event(osc.event(1)))
     c = dfx.diffeqsolve(dfx.ODETerm(osc), dfx.Tsit5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl, event=dfx.Event(dfx.AffineEvent([1.0, 0.0])))
     assert torch.equal(b.ts, c.ts) and torch.equal(b.ys, c.ys)
+
+
+PLAIN = {"DFX_OPT_CHAIN_Y0": 0, "DFX_OPT_LAST_STAGE_F": 0, "DFX_OPT_FAST_PID": 0, "DFX_OPT_ABSMAX_FP64": 0}
+LORENZ_SRC = "f[0] = p[0] * (y[1] - y[0]); f[1] = y[0] * (p[1] - y[2]) - y[1]; f[2] = y[0] * y[1] - p[2] * y[2];"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["dopri5", "tsit5", "dopri8", "bosh3"])
+def test_reference_operation_order_build_stays_under_test(dev, solver):
+    """The shipped kernels leave the reference's operation order in four places (stage sums chained onto y0, the last stage's
+    k taken from f(y1), the division- / pow-free I-controller, max|y| on the FP64 pipe).  A build of the same kernel with all
+    four switched OFF - the reference's own order: vector_tree_dot then y0 + incr (runge_kutta.py:871), pow() and IEEE
+    division in the controller (pid.py:476-567) - is compiled here and must (1) match the oracle even more closely and (2)
+    agree with the shipped kernel in every accept / reject decision and to the north-star 1e-10 in the states."""
+    rng = np.random.default_rng(1)
+    n = 4096
+    y0n = np.stack([rng.uniform(-15, 15, n), rng.uniform(-20, 20, n), rng.uniform(5, 45, n)], 1)
+    y0 = torch.tensor(y0n, device=dev)
+    S = {"dopri5": dfx.Dopri5, "tsit5": dfx.Tsit5, "dopri8": dfx.Dopri8, "bosh3": dfx.Bosh3}[solver]
+    tol = 1e-6 if solver == "bosh3" else 1e-8
+    ctrl = dfx.PIDController(rtol=tol, atol=tol)
+    plain = dfx.fields.CudaField(3, LORENZ_SRC, params=[10.0, 28.0, 8.0 / 3.0], defines=PLAIN)
+    a = dfx.diffeqsolve(dfx.ODETerm(plain), S(), 0.0, 1.0, 0.01, y0, stepsize_controller=ctrl, max_steps=100000)
+    b = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.Lorenz()), S(), 0.0, 1.0, 0.01, y0, stepsize_controller=ctrl, max_steps=100000)
+    o = oracle.solve("lorenz", y0n, 0.0, 1.0, 0.01, solver=solver, params=[10.0, 28.0, 8.0 / 3.0], rtol=tol, atol=tol, max_steps=100000)
+    sa, sb = _np(a.stats["num_accepted_steps"]), _np(b.stats["num_accepted_steps"])
+    ra, rb = _np(a.stats["num_steps"]), _np(b.stats["num_steps"])
+    same_ab = (sa == sb) & (ra == rb)
+    same_ao = (sa == o["stats"][:, 1]) & (ra == o["stats"][:, 0])
+    assert same_ab.mean() > 0.995 and same_ao.mean() > 0.995, (same_ab.mean(), same_ao.mean())
+    scale = np.abs(o["ys"]).max()
+    e_ao = np.abs(_np(a.ys)[same_ao] - o["ys"][same_ao]).max() / scale
+    e_ab = np.abs(_np(a.ys)[same_ab] - _np(b.ys)[same_ab]).max() / scale
+    e_bo = np.abs(_np(b.ys)[same_ao & same_ab] - o["ys"][same_ao & same_ab]).max() / scale
+    assert e_ao < 1e-10 and e_ab < 1e-10 and e_bo < 1e-10, (e_ao, e_ab, e_bo)
