@@ -337,7 +337,9 @@ static int check_desc(const dfx_solve_desc *d) {
               sizeof(dfx_solve_desc), d->abi_version, DFX_ABI_VERSION);
     return DFX_ERR_BAD_ARGUMENT;
   }
-  if (d->n_traj < 0 || d->n_traj > 0x7fffffffLL || d->dim < 1 || d->dim > kMaxDim) { set_error("bad n_traj (0 .. 2^31-1 per call) / dim"); return DFX_ERR_BAD_ARGUMENT; }
+  // (one thread per trajectory: dim <= 8; user functors may be "wide" - one warp per trajectory, csrc/wide_kernel.cuh - up to 1024)
+  const int max_dim = d->field_id >= DFX_FIELD_USER ? 1024 : kMaxDim;
+  if (d->n_traj < 0 || d->n_traj > 0x7fffffffLL || d->dim < 1 || d->dim > max_dim) { set_error("bad n_traj (0 .. 2^31-1 per call) / dim (1 .. %d)", max_dim); return DFX_ERR_BAD_ARGUMENT; }
   if (d->dtype != DFX_F64 && d->dtype != DFX_F32) { set_error("bad dtype %d", d->dtype); return DFX_ERR_BAD_ARGUMENT; }
   if (d->n_traj > 0 && !d->y0) { set_error("y0 is null"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->n_traj > 0 && (!d->stats || !d->result)) { set_error("stats / result buffers are required"); return DFX_ERR_BAD_ARGUMENT; }

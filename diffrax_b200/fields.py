@@ -304,6 +304,9 @@ class CudaField(Field):
     * ``noise="<statements>"``, ``noise_dim=m``: the general ``ControlTerm.prod`` (_term.py:417-427): assign ``gx[0..dim)``, the
       product ``g(t, y) . x`` with the Brownian increment ``x[0..m)`` (``m = 1`` for shape ``()``) - Euler / Heun (Stratonovich).
 
+    ``wide=True``: a WIDE state (``dim`` up to 1024), one trajectory per warp (csrc/wide_kernel.cuh): the state is spread over
+    the 32 lanes, and ``drift`` is written per component - statements that assign ``fi``, component ``i`` of f, from ``i``, the
+    whole state ``y[0..D)``, ``p`` and ``t``; e.g. Lorenz-96: ``"fi = (y[(i + 1) % D] - y[(i + D - 2) % D]) * y[(i + D - 1) % D] - y[i] + p[0];"``.
     ``events=["<expr>", ...]``: real-valued condition functions in ``t``, ``y``, ``p`` for ``Event(field.event(i), ...)`` - the
     reference's arbitrary ``cond_fn(t, y, args)`` (_event.py:13-118); with a root finder the crossing is located on the step's
     interpolant.  ``preamble``: device helper functions / constants placed before the functor.  ``min_blocks_per_sm``: occupancy target handed
@@ -312,11 +315,18 @@ class CudaField(Field):
     is_user = True
 
     def __init__(self, dim, drift, *, params=(), diffusion=None, noise=None, noise_dim=None, preamble="", name=None,
-                 min_blocks_per_sm=None, events=(), defines=None):
+                 min_blocks_per_sm=None, events=(), defines=None, wide=False):
         import hashlib
         self.dim = int(dim)
-        if not 1 <= self.dim <= 8:
-            raise ValueError("CudaField: 1 <= dim <= 8")
+        self.wide = bool(wide)
+        if self.wide:
+            if not 1 <= self.dim <= 1024:
+                raise ValueError("CudaField(wide=True): 1 <= dim <= 1024")
+            if diffusion is not None or noise is not None or events:
+                raise ValueError("CudaField(wide=True) is an ODE functor: no diffusion / noise / events")
+        elif not 1 <= self.dim <= 8:
+            raise ValueError("CudaField: 1 <= dim <= 8 with one trajectory per thread; pass wide=True (one trajectory per warp, "
+                             "dim <= 1024) and write the drift per component: `fi = ...` from `i`, `y[...]`, `p[...]`")
         if diffusion is not None and noise is not None:
             raise ValueError("CudaField: give `diffusion` (additive g(t)) or `noise` (general g(t, y) . x), not both")
         self.p = [float(v) for v in params]
@@ -336,7 +346,7 @@ class CudaField(Field):
         self.event_srcs = [str(e) for e in events]
         if len(self.event_srcs) > _lib.MAX_EVENTS:
             raise ValueError(f"CudaField: at most {_lib.MAX_EVENTS} condition functions")
-        key = "\0".join(self.event_srcs + [repr(sorted(self.defines.items())), str(self.dim), self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble, str(len(self.p)),
+        key = "\0".join(self.event_srcs + ["wide" if self.wide else "thread", repr(sorted(self.defines.items())), str(self.dim), self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble, str(len(self.p)),
                          str(self.min_blocks)])
         self._hash = hashlib.sha256(key.encode()).hexdigest()[:16]
         self._id = _lib.FIELD_USER + int(self._hash[:7], 16)
@@ -362,6 +372,14 @@ class CudaField(Field):
         if solver_id & _HALF:
             solver = f"::dfx::HalfOf<{solver}>"
         np_ = len(self.p)
+        if self.wide:
+            rep = {"@DEFINES@": "".join(f"#define {k} {v}\n" for k, v in sorted(self.defines.items())), "@PREAMBLE@": self.preamble,
+                   "@ID@": str(self._id), "@DIM@": str(self.dim), "@NP@": str(np_), "@NP1@": str(max(np_, 1)), "@DRIFT@": self.drift_src,
+                   "@REAL@": "double" if dtype_id == _lib.F64 else "float", "@SOLVER@": solver}
+            src = _WIDE_TU
+            for k, v in rep.items():
+                src = src.replace(k, v)
+            return src
         traits, fns = "", ""
         if self.is_sde:
             traits = f"  static constexpr int kNoise = {self.noise_dim};\n"
@@ -400,6 +418,9 @@ class CudaField(Field):
             raise ValueError(f"unknown solver id {solver_id}")
         if bool(levy) != self.is_sde:
             raise ValueError("CudaField: SDE solves need `diffusion=` or `noise=`; ODE solves must not have them")
+        if self.wide and ((solver_id & _HALF) or inner in (7, 8)):
+            raise ValueError("CudaField(wide=True): the warp-per-trajectory kernel runs the explicit RK tableaux "
+                             "(Tsit5, Dopri5, Dopri8, Bosh3, Heun, Midpoint, Ralston)")
         if self.noise_src is not None and inner == 8:
             raise ValueError("ShARK is an additive-noise SRK (shark.py:10-30): the diffusion of this field depends on y")
         L = _lib.lib()
@@ -410,6 +431,39 @@ class CudaField(Field):
             if not L.dfx_has_kernel(self._id, self.dim, int(solver_id), int(dtype_id), int(levy)):
                 raise RuntimeError(f"{path} was loaded but registered no launcher for this combination")
         self._ready.add(key)
+
+
+_WIDE_TU = r"""// generated by diffrax_b200.fields.CudaField(wide=True) - do not edit
+@DEFINES@
+#include "wide_kernel.cuh"
+namespace {
+@PREAMBLE@
+struct UserField {
+  static constexpr int kId = @ID@;
+  static constexpr int kDim = @DIM@;
+  static constexpr bool kSde = false;
+  static constexpr int kNumParams = @NP@;
+  template <class R> struct P { R p[@NP1@]; };
+  template <class R> static P<R> make(const double *q, int n, const void *) {
+    P<R> o;
+    for (int i = 0; i < @NP1@; ++i) o.p[i] = (i < n && i < @NP@) ? (R)q[i] : R(0);
+    return o;
+  }
+  // component i of vector_field(t, y, args); y is the whole state (shared memory, read-only)
+  template <class R>
+  static __device__ __forceinline__ R component(const P<R> &P_, R t, int i, const R *y) {
+    [[maybe_unused]] const R *p = P_.p;
+    [[maybe_unused]] constexpr int D = @DIM@;
+    (void)t;
+    R fi = R(0);
+@DRIFT@
+    return fi;
+  }
+};
+[[maybe_unused]] constexpr bool kUseSde = UserField::kSde;
+DFX_REGISTER_WIDE(@REAL@, UserField, @SOLVER@)
+}  // namespace
+"""
 
 
 _BUILTIN_TU = r"""// generated by diffrax_b200.fields.ensure_builtin_kernel - do not edit

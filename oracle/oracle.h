@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ORC_MAX_DIM 8
+#define ORC_MAX_DIM 128   /* (8 in the per-thread kernels; the warp-per-trajectory kernel of wide functors is checked up to 128) */
 #define ORC_MAX_STAGES 14
 
 /* dtype */

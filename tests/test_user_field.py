@@ -301,3 +301,89 @@ def test_reference_operation_order_build_stays_under_test(dev, solver):
     e_ab = np.abs(_np(a.ys)[same_ab] - _np(b.ys)[same_ab]).max() / scale
     e_bo = np.abs(_np(b.ys)[same_ao & same_ab] - o["ys"][same_ao & same_ab]).max() / scale
     assert e_ao < 1e-10 and e_ab < 1e-10 and e_bo < 1e-10, (e_ao, e_ab, e_bo)
+
+
+L96 = "fi = (y[(i + 1) % D] - y[(i + D - 2) % D]) * y[(i + D - 1) % D] - y[i] + p[0];"
+
+
+def _l96(F, D):
+    return lambda t, y: (np.roll(y, -1) - np.roll(y, 2)) * np.roll(y, 1) - y + F
+
+
+def test_wide_field_source_and_checks():
+    f = dfx.fields.CudaField(40, L96, params=[8.0], wide=True)
+    src = f.source(1, _lib.F64, 0)
+    assert "wide_kernel.cuh" in src and "DFX_REGISTER_WIDE(double, UserField, ::dfx::Dopri5)" in src and "kDim = 40" in src
+    f.ensure_kernel(40, 1, _lib.F64, 0)
+    assert _lib.lib().dfx_has_kernel(f.field_id, 40, 1, _lib.F64, 0) == 1
+    with pytest.raises(ValueError, match="wide=True"):
+        dfx.fields.CudaField(40, L96, params=[8.0])                      # more than 8 components needs the warp mapping
+    with pytest.raises(ValueError, match="ODE functor"):
+        dfx.fields.CudaField(40, L96, params=[8.0], wide=True, events=["y[0]"])
+    with pytest.raises(ValueError, match="explicit RK tableaux"):
+        f.ensure_kernel(40, 0x100 | 3, _lib.F64, 0)
+    p = dfx.prepare(dfx.ODETerm(f), dfx.Dopri5(), 0.0, 1.0, None, np.ones((3, 40)), stepsize_controller=dfx.PIDController(1e-6, 1e-6))
+    assert p.desc.dim == 40
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,solver", [(40, "dopri5"), (100, "tsit5"), (33, "dopri8"), (64, "bosh3")])
+def test_wide_state_warp_per_trajectory_against_oracle(dev, D, solver):
+    """Lorenz-96 with D components, one trajectory per warp (csrc/wide_kernel.cuh), against the oracle's callback field:
+    identical accept / reject sequences, saved states (interpolated SaveAt(ts) + t1) to 1e-10."""
+    rng = np.random.default_rng(D)
+    n = 24
+    y0 = 8.0 + rng.normal(0, 0.5, (n, D))
+    f = dfx.fields.CudaField(D, L96, params=[8.0], wide=True)
+    S = {"dopri5": dfx.Dopri5, "tsit5": dfx.Tsit5, "dopri8": dfx.Dopri8, "bosh3": dfx.Bosh3}[solver]
+    tol = 1e-6 if solver == "bosh3" else 1e-9
+    ts = [0.1, 0.25, 0.5]
+    sol = dfx.diffeqsolve(dfx.ODETerm(f), S(), 0.0, 0.5, 0.01, torch.tensor(y0, device=dev), saveat=dfx.SaveAt(ts=ts, t0=True),
+                          stepsize_controller=dfx.PIDController(rtol=tol, atol=tol))
+    o = oracle.solve("callback", y0, 0.0, 0.5, 0.01, solver=solver, rtol=tol, atol=tol, save_ts=ts, save_t0=True, save_t1=False, callback=_l96(8.0, D))
+    st = np.stack([_np(sol.stats[k]) for k in ("num_steps", "num_accepted_steps", "num_rejected_steps")], 1)
+    same = np.all(st == o["stats"], axis=1)
+    assert same.mean() >= 0.9, (st[:4], o["stats"][:4])
+    assert np.array_equal(_np(sol.ts), o["ts"])
+    err = np.abs(_np(sol.ys)[same] - o["ys"][same]).max() / np.abs(o["ys"]).max()
+    assert err < 1e-10, err
+    assert bool((sol.result == 0).all())
+
+
+@pytest.mark.gpu
+def test_wide_state_modes(dev):
+    """Fixed steps + SaveAt(steps) with +inf padding, fp32, backwards in time, per-trajectory t1, the host entry, the sharded
+    entry's totals, and a refusal of what the wide kernel does not cover."""
+    D, n = 72, 70
+    rng = np.random.default_rng(2)
+    y0 = rng.uniform(0.5, 2.0, (n, D))
+    lam = np.linspace(0.5, 2.0, D)
+    dec = dfx.fields.CudaField(D, "fi = -(p[0] + p[1] * (R)i) * y[i];", params=[0.5, 1.5 / (D - 1)], wide=True)
+    # constant steps, steps saved: exact t grid, states against the oracle, unfilled slots +inf
+    sol = dfx.diffeqsolve(dfx.ODETerm(dec), dfx.Tsit5(), 0.0, 1.0, 0.125, torch.tensor(y0, device=dev), saveat=dfx.SaveAt(steps=True), max_steps=12)
+    o = oracle.solve("callback", y0, 0.0, 1.0, 0.125, solver="tsit5", controller="constant", save_steps=1, save_t1=False, max_steps=12,
+                     callback=lambda t, y: -lam * y)
+    assert np.array_equal(_np(sol.ts), o["ts"]) and np.isinf(_np(sol.ts)[:, 8:]).all() and np.isinf(_np(sol.ys)[:, 8:]).all()
+    assert np.abs(_np(sol.ys)[:, :8] - o["ys"][:, :8]).max() < 1e-14
+    assert np.abs(_np(sol.ys)[:, 7] - y0 * np.exp(-lam)).max() < 1e-6
+    # adaptive, backwards in time, per-trajectory t1, host buffers
+    t1 = rng.uniform(-1.0, -0.2, n)
+    ctrl = dfx.PIDController(rtol=1e-8, atol=1e-10)
+    a = dfx.diffeqsolve(dfx.ODETerm(dec), dfx.Dopri5(), 0.0, t1, None, y0, stepsize_controller=ctrl)                      # numpy in: host entry
+    b = dfx.diffeqsolve(dfx.ODETerm(dec), dfx.Dopri5(), 0.0, torch.tensor(t1, device=dev), None, torch.tensor(y0, device=dev), stepsize_controller=ctrl)
+    assert np.array_equal(_np(a.ys), _np(b.ys)) and np.array_equal(_np(a.stats["num_steps"]), _np(b.stats["num_steps"]))
+    assert np.abs(_np(b.ys)[:, 0] / (y0 * np.exp(-lam[None] * t1[:, None])) - 1).max() < 1e-6
+    # fp32
+    c = dfx.diffeqsolve(dfx.ODETerm(dec), dfx.Bosh3(), 0.0, 1.0, None, torch.tensor(y0.astype(np.float32), device=dev),
+                        stepsize_controller=dfx.PIDController(rtol=1e-4, atol=1e-6))
+    assert c.ys.dtype == torch.float32 and np.abs(_np(c.ys)[:, 0] / (y0 * np.exp(-lam)) - 1).max() < 1e-3
+    # sharded entry: finals + in-kernel totals
+    sh = dfx.sharded_diffeqsolve(dfx.ODETerm(dec), dfx.Dopri5(), 0.0, torch.tensor(t1, device=dev), None, torch.tensor(y0, device=dev), stepsize_controller=ctrl)
+    assert torch.equal(sh.y_final, b.ys[:, -1]) and int(sh.stats["num_steps"]) == int(b.stats["num_steps"].sum())
+    assert int(sh.stats["max_steps_per_trajectory"]) == int(b.stats["num_steps"].max()) and int(sh.stats["num_failed"]) == 0
+    # max_steps reached is reported per trajectory
+    z = dfx.diffeqsolve(dfx.ODETerm(dec), dfx.Dopri5(), 0.0, 1.0, None, torch.tensor(y0, device=dev), stepsize_controller=ctrl, max_steps=3, throw=False)
+    assert bool((z.result == 1).all())
+    with pytest.raises(RuntimeError, match="warp-per-trajectory"):
+        dfx.diffeqsolve(dfx.ODETerm(dec), dfx.Dopri5(), 0.0, 1.0, None, torch.tensor(y0, device=dev), stepsize_controller=ctrl,
+                        saveat=dfx.SaveAt(dense=True), max_steps=64)
