@@ -108,7 +108,9 @@ def lib():
         raise LibraryMissing(
             f"{LIB_PATH} not found: build it with `python -m diffrax_b200.build` "
             "(there is no CPU or PyTorch fallback for the ensemble kernels)")
-    L = C.CDLL(LIB_PATH)
+    # RTLD_GLOBAL: plugins of user functors (load_plugin) bind dfx::register_builtin & co. to THIS loaded instance by name - not
+    # through a DT_NEEDED entry, which would map a second copy of the library if the file was rebuilt after it was loaded
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     L.dfx_abi_version.restype = C.c_int
     L.dfx_last_error.restype = C.c_char_p
     L.dfx_device_count.restype = C.c_int

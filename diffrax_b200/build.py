@@ -27,8 +27,13 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxe
          "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")] + os.environ.get("DFX_NVCC_EXTRA", "").split()
 
 
-def _headers():
-    return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "diffrax_b200.h")]
+# headers that only generated plugin sources include (fields.CudaField(wide=True)): not dependencies of the library's own objects
+PLUGIN_ONLY_HEADERS = ("wide_kernel.cuh",)
+
+
+def _headers(plugin=False):
+    hs = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "diffrax_b200.h")]
+    return hs if plugin else [h for h in hs if os.path.basename(h) not in PLUGIN_ONLY_HEADERS]
 
 
 def _stale(target, deps):
@@ -79,14 +84,14 @@ USER_DIR = os.path.join(LIBDIR, "user")
 
 def build_user_field(tag, source, verbose=False):
     """Compile one generated translation unit (fields.CudaField: a user functor + ONE DFX_REGISTER) against csrc/launch.cuh
-    into lib/user/dfx_user_<tag>.so, linked to libdiffrax_b200.so.  Cached: the tag carries the content hash of the functor,
+    into lib/user/dfx_user_<tag>.so (a plugin of the loaded libdiffrax_b200.so).  Cached: the tag carries the content hash of the functor,
     and the object is rebuilt when the kernel headers are newer."""
     os.makedirs(USER_DIR, exist_ok=True)
     out = os.path.join(USER_DIR, f"dfx_user_{tag}.so")
     src = os.path.join(USER_DIR, f"dfx_user_{tag}.cu")
     if not os.path.exists(LIB):
         raise RuntimeError(f"{LIB} not found: build it with `python -m diffrax_b200.build` first")
-    if os.path.exists(src) and open(src).read() == source and not _stale(out, [src, LIB] + _headers()):
+    if os.path.exists(src) and open(src).read() == source and not _stale(out, [src, LIB] + _headers(plugin=True)):
         return out
     if not os.path.exists(NVCC):
         raise RuntimeError(f"compiling a CudaField needs nvcc ({NVCC} not found; set NVCC)")
@@ -97,8 +102,9 @@ def build_user_field(tag, source, verbose=False):
     os.replace(src + uniq, src)
     tmp = out + uniq
     flags = [x for x in FLAGS if x not in ("-Xptxas", "-v")]
-    cmd = [NVCC, *ARCH, *flags, "-I", CSRC, "-shared", "-o", tmp, src, "-L", LIBDIR, "-ldiffrax_b200",
-           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/.."]
+    # (no -ldiffrax_b200: the registrar's symbols stay undefined in the plugin and are resolved at dlopen time against the
+    # library instance the process has already loaded RTLD_GLOBAL - see _lib.lib)
+    cmd = [NVCC, *ARCH, *flags, "-I", CSRC, "-shared", "-o", tmp, src]
     t0 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

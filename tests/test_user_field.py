@@ -387,3 +387,21 @@ def test_wide_state_modes(dev):
     with pytest.raises(RuntimeError, match="warp-per-trajectory"):
         dfx.diffeqsolve(dfx.ODETerm(dec), dfx.Dopri5(), 0.0, 1.0, None, torch.tensor(y0, device=dev), stepsize_controller=ctrl,
                         saveat=dfx.SaveAt(dense=True), max_steps=64)
+
+
+def test_plugin_binds_to_the_loaded_library_instance():
+    """A plugin must register into the library instance this process has loaded even when the FILE was rebuilt since (a new
+    inode at the same path: the test suite's own `cuda_lib` fixture does that when a header is newer than the objects) - it
+    carries no DT_NEEDED entry for libdiffrax_b200.so and resolves the registrar by name (RTLD_GLOBAL)."""
+    import shutil
+    import subprocess
+    L = _lib.lib()
+    shutil.copy2(_lib.LIB_PATH, _lib.LIB_PATH + ".swap")
+    os.replace(_lib.LIB_PATH + ".swap", _lib.LIB_PATH)                 # same bytes, new inode
+    f = dfx.fields.CudaField(2, "f[0] = y[1]; f[1] = -p[0] * y[0] - 0.125 * y[1];", params=[2.0])
+    f.ensure_kernel(2, 4, _lib.F32, 0)                                    # Bosh3, fp32
+    assert L.dfx_has_kernel(f.field_id, 2, 4, _lib.F32, 0) == 1
+    from diffrax_b200 import build
+    so = [p for p in _lib._plugins if f._hash in p][0]
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "libdiffrax_b200" not in needed
