@@ -191,7 +191,8 @@ class OrnsteinUhlenbeckMatrix(Field):
 class MLP(Field):
     """Neural-ODE vector field: ``eqx.nn.MLP(in=d, out=d, width, depth=2, activation=softplus, final_activation=tanh)``
     (docs/examples/neural_ode.ipynb cell 5).  ``layers`` is ``[(W1, b1), (W2, b2), (W3, b3)]`` with eqx ``Linear``
-    weight shapes ``(out, in)``.  Built-in kernels exist for d=4, width=128, fp32."""
+    weight shapes ``(out, in)``.  d=4, width=128, fp32 runs on the tcgen05 tensor-core kernel; other sizes (d <= 8, width <= 256) and
+    fp64 run the per-thread functor, instantiated on first use."""
     name, dim = "mlp", 4
 
     def __init__(self, layers):
@@ -216,6 +217,22 @@ class MLP(Field):
 
     def params(self):
         return [float(self.width), 2.0]
+
+    @property
+    def field_id(self):
+        # the prebuilt kernels (tensor-core path included) are for d = 4, width 128; any other size is the generic per-thread
+        # functor MlpField<d, width> under an id of its own, instantiated on first use (ensure_builtin_kernel)
+        if (self.dim, self.width) == (4, 128):
+            return _lib.FIELD_IDS["mlp"]
+        return _lib.FIELD_USER + (1 << 28) + self.dim * 4096 + self.width
+
+    def cpp_functor(self, dim, bm_dim):
+        if (self.dim, self.width) == (4, 128):
+            return "::dfx::MlpField<4, 128>"
+        if not (1 <= self.dim <= 8 and 1 <= self.width <= 256):
+            return None
+        return (f"UserMlp; struct UserMlp : ::dfx::MlpField<{self.dim}, {self.width}> "
+                f"{{ static constexpr int kId = {self.field_id}; }}")
 
     def flat(self, dtype):
         import numpy as np
@@ -469,7 +486,8 @@ DFX_REGISTER_WIDE(@REAL@, UserField, @SOLVER@)
 _BUILTIN_TU = r"""// generated by diffrax_b200.fields.ensure_builtin_kernel - do not edit
 #include "launch.cuh"
 namespace {
-using F = @FUNCTOR@;
+struct @FUNCTOR_DECL@;
+using F = @FUNCTOR_NAME@;
 DFX_REGISTER(@REAL@, F, @SOLVER@, @LEVY@)
 }  // namespace
 """
@@ -496,7 +514,10 @@ def ensure_builtin_kernel(field, dim, solver_id, dtype_id, levy, bm_dim):
     solver = _SOLVER_CPP[inner]
     if solver_id & _HALF:
         solver = f"::dfx::HalfOf<{solver}>"
-    src = _BUILTIN_TU.replace("@FUNCTOR@", functor).replace("@REAL@", "double" if dtype_id == _lib.F64 else "float")
+    # cpp_functor: a type name, or "Name; struct Name : Base { ... }" for a derived functor (MLP sizes with ids of their own)
+    name, _, decl = functor.partition("; struct ")
+    src = _BUILTIN_TU.replace("@FUNCTOR_DECL@", decl if decl else "DfxUnused {}").replace("@FUNCTOR_NAME@", name)
+    src = src.replace("@REAL@", "double" if dtype_id == _lib.F64 else "float")
     src = src.replace("@SOLVER@", solver).replace("@LEVY@", str(int(levy)))
     from . import build
     tag = f"builtin_{field.field_id}_{dim}_{int(solver_id):x}_{int(dtype_id)}_{int(levy)}"

@@ -405,3 +405,25 @@ def test_plugin_binds_to_the_loaded_library_instance():
     so = [p for p in _lib._plugins if f._hash in p][0]
     needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
     assert "libdiffrax_b200" not in needed
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,width,dtype", [(2, 32, np.float64), (3, 64, np.float32)])
+def test_mlp_field_other_sizes_on_demand(dev, d, width, dtype):
+    """eqx.nn.MLP-shaped fields of other sizes than the prebuilt d=4 / width 128 (and fp64): the per-thread functor
+    MlpField<d, width>, instantiated on first use, against the oracle's MLP field."""
+    mlp = dfx.fields.MLP.init(11, d=d, width=width, dtype=np.dtype(dtype).name)
+    assert mlp.field_id >= _lib.FIELD_USER
+    rng = np.random.default_rng(d)
+    y0 = rng.normal(0, 1, (64, d)).astype(dtype)
+    f32 = dtype == np.float32
+    rtol, atol = (1e-3, 1e-6) if f32 else (1e-7, 1e-9)
+    sol = dfx.diffeqsolve(dfx.ODETerm(mlp), dfx.Tsit5(), 0.0, 2.0, 0.1, torch.tensor(y0, device=dev),
+                          stepsize_controller=dfx.PIDController(rtol=rtol, atol=atol), saveat=dfx.SaveAt(ts=[0.5, 1.0, 2.0]))
+    o = oracle.solve("mlp", y0, 0.0, 2.0, 0.1, solver="tsit5", params=mlp.oracle_params(), dtype=dtype, rtol=rtol, atol=atol,
+                     save_ts=[0.5, 1.0, 2.0], save_t1=False)
+    st = np.stack([_np(sol.stats[k]) for k in ("num_steps", "num_accepted_steps", "num_rejected_steps")], 1)
+    same = np.all(st == o["stats"], axis=1)
+    assert same.mean() > (0.7 if f32 else 0.95)
+    err = np.abs(_np(sol.ys)[same] - o["ys"][same]).max() / np.abs(o["ys"]).max()
+    assert err < (2e-4 if f32 else 1e-10), err
