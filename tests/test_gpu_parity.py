@@ -1164,3 +1164,14 @@ def test_state_dependent_diffusion_gbm(dev, solver, dtype):
         ad = dfx.diffeqsolve(terms, dfx.HalfSolver(dfx.Heun()), 0.0, 1.0, 2.0 ** -6, torch.ones(n, 1, dtype=torch.float64, device=dev),
                              stepsize_controller=dfx.PIDController(rtol=0.0, atol=1e-3, dtmin=2.0 ** -11, pcoeff=0.1, icoeff=0.3), max_steps=1 << 14)
         assert np.sqrt(np.mean((to_np(ad.ys)[:, -1, 0] - np.exp(mu + sigma * W)) ** 2)) < 5e-3
+
+
+def test_randomised_differential_check_subset(dev):
+    """tools/fuzz_parity.py on 200 random field x solver x controller x SaveAt x dtype x direction x per-trajectory-t1 x
+    host/device combinations (prebuilt kernels only: DFX_JIT=0 makes the facade refuse the others): no unexplained difference
+    between the CUDA path and the oracle.  The full 2 x 600-case run is profiles/r02_fuzz_parity.txt."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--cases", "200", "--seed", "3"],
+                       env=dict(os.environ, DFX_JIT="0"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and " 0 failures" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
