@@ -11,7 +11,8 @@
 //     warp-uniform: no divergence, and the trajectories of different warps are as independent as in the other kernel.
 // Scope: explicit RK tableaux (Tsit5, Dopri5, Dopri8, Bosh3, Heun, Midpoint, Ralston), PIDController (the faithful
 // pid.py:394-567 path; dtmin / dtmax) and ConstantStepSize, SaveAt(t0, t1, ts, steps), per-trajectory t0 / t1, finals + totals.
-// The operation order is the reference's (vector_tree_dot, then y0 + incr), as in the oracle.
+// The controller is the reference's faithful path; the stage sums are chained onto y0 for <= 7 stages like in the per-thread
+// kernel (DFX_OPT_CHAIN_Y0=0 restores vector_tree_dot, then y0 + incr).
 #pragma once
 #include "launch.cuh"
 
@@ -115,11 +116,20 @@ __global__ void __launch_bounds__(kWideBlock, wide_min_blocks<Field::kDim>()) wi
       for (int i = 1; i < S; ++i) {
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          R incr = R(0);
+          if constexpr (DFX_OPT_CHAIN_Y0 && S <= 7) {
+            // as in the per-thread kernel: ONE chain of FMAs seeded with y0 (a DMUL and a DADD less per stage and component)
+            R acc = y[c];
 #pragma unroll
-          for (int j = 0; j < i; ++j)
-            if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];  // vector_tree_dot (base.py:37-41)
-          yi[c] = y[c] + incr;                                     // 871
+            for (int j = 0; j < i; ++j)
+              if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) acc += Solver::template a<R>(i, j) * k[j][c];
+            yi[c] = acc;
+          } else {
+            R incr = R(0);
+#pragma unroll
+            for (int j = 0; j < i; ++j)
+              if (Solver::hA(i * (i - 1) / 2 + j) != 0.0) incr += Solver::template a<R>(i, j) * k[j][c];  // vector_tree_dot (base.py:37-41)
+            yi[c] = y[c] + incr;                                   // 871
+          }
         }
         const R ti = (Solver::hC(i) == 1.0) ? st1 : st0 + Solver::template c<R>(i) * dt;  // 1023
         feval(ti * direction, yi, fi);
