@@ -292,25 +292,29 @@ int launch_wide(const dfx_solve_desc *d, void *stream_v) {
   if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
-  unsigned long long *counter = nullptr;
-  DFX_CUDA_OK(cudaMallocAsync((void **)&counter, 16, stream));
-  DFX_CUDA_OK(cudaMemsetAsync(counter, 0, 16, stream));
-  p.work_counter = counter;
-  if (p.totals) DFX_CUDA_OK(cudaMemsetAsync(p.totals, 0, 4 * sizeof(long long), stream));
   int sms = 0;
   if (int e = device_sm_count(&sms)) return e;
   const size_t smem = (size_t)(kWideBlock / 32) * Field::kDim * sizeof(R);
   int per_sm = 0;
   DFX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_kernel<R, Field, Solver>, kWideBlock, smem));
   if (per_sm < 1) { set_error("the wide kernel does not fit an SM (state dimension %d)", Field::kDim); return DFX_ERR_UNSUPPORTED; }
-  const long long warps_needed = (p.n_traj + 0);  // one warp per trajectory at a time
-  long long blocks = (warps_needed + kWideBlock / 32 - 1) / (kWideBlock / 32);
+  long long blocks = (p.n_traj + kWideBlock / 32 - 1) / (kWideBlock / 32);   // one warp per trajectory at a time
   const long long resident = (long long)sms * per_sm;
   if (blocks > resident) blocks = resident;              // persistent: the work queue feeds the resident warps
+  unsigned long long *counter = nullptr;
+  DFX_CUDA_OK(cudaMallocAsync((void **)&counter, 16, stream));
+  if (cudaMemsetAsync(counter, 0, 16, stream) != cudaSuccess ||
+      (p.totals && cudaMemsetAsync(p.totals, 0, 4 * sizeof(long long), stream) != cudaSuccess)) {
+    cudaFreeAsync(counter, stream);
+    set_error("cudaMemsetAsync failed");
+    return DFX_ERR_CUDA;
+  }
+  p.work_counter = counter;
   wide_kernel<R, Field, Solver><<<(unsigned)blocks, kWideBlock, smem, stream>>>(p, fp);
   count_launch();
-  DFX_CUDA_OK(cudaGetLastError());
+  const cudaError_t le = cudaGetLastError();
   cudaFreeAsync(counter, stream);
+  if (le != cudaSuccess) { set_error("wide_kernel launch failed: %s", cudaGetErrorString(le)); return DFX_ERR_CUDA; }
   return 0;
 }
 
