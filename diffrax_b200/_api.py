@@ -391,8 +391,9 @@ class SubSaveAt:
 
 class SaveAt:
     """_saveat.py:65-105.  `subs` may be a SubSaveAt or a (nested) list / tuple / dict of them; `Solution.ts` / `.ys`
-    then have the same structure.  Each SubSaveAt is served by its own launch of the same solve (the step sequence does
-    not depend on what is saved, so the values are those of a single solve)."""
+    then have the same structure.  All leaves without `steps` share ONE solve over the union of their `ts` (`_MultiSolve`);
+    a leaf with `steps` gets a launch of its own (the step sequence does not depend on what is saved, so the values are
+    those of a single solve either way)."""
 
     def __init__(self, *, t0: bool = False, t1: bool = False, ts=None, steps: Union[bool, int] = False, fn=save_y,
                  subs=None, dense: bool = False, solver_state: bool = False, controller_state: bool = False,
@@ -712,30 +713,79 @@ class EnsembleSolve:
             sol = dataclasses.replace(sol, made_jump=(mj != 0))
         fn = getattr(self, "_fn", save_y)
         if fn is not save_y:  # SubSaveAt.fn, applied to every saved slot at once (see SubSaveAt)
-            ts, ys = sol.ts, sol.ys
-            out = fn(ts, ys, None)
-            valid = (ts == ts) & (abs(ts) != math.inf)
-            while valid.ndim < out.ndim:
-                valid = valid[..., None]
-            inf = math.inf
-            out = torch.where(valid, out, torch.full_like(out, inf)) if isinstance(out, torch.Tensor) else np.where(valid, out, inf)
-            sol = dataclasses.replace(sol, ys=out)
+            sol = dataclasses.replace(sol, ys=_apply_save_fn(fn, sol.ts, sol.ys))
         return sol
 
 
-class _MultiSolve:
-    """SaveAt(subs=<tree of SubSaveAt>): one prepared solve per leaf; `ts` / `ys` come back in the structure of `subs`."""
+def _apply_save_fn(fn, ts, ys):
+    """SubSaveAt.fn on every saved slot at once; unfilled slots are reset to inf (the reference's padding, _integrate.py:1296-1300)."""
+    out = fn(ts, ys, None)
+    valid = (ts == ts) & (abs(ts) != math.inf)
+    while valid.ndim < out.ndim:
+        valid = valid[..., None]
+    return torch.where(valid, out, torch.full_like(out, math.inf)) if isinstance(out, torch.Tensor) else np.where(valid, out, math.inf)
 
-    def __init__(self, subs, solves):
-        self.subs, self.solves = subs, solves
+
+class _MultiSolve:
+    """SaveAt(subs=<tree of SubSaveAt>); `ts` / `ys` come back in the structure of `subs`.
+
+    Every leaf without `steps` (t0 / t1 / ts only) is served by ONE shared solve: saving does not feed back into the stepping,
+    and the value the step interpolant gives at a time does not depend on which other times are asked for, so a solve that
+    saves the UNION of the leaves' `ts` holds every leaf's rows bit for bit.  `providers[i]` is `("own", prepared solve)` or
+    `("union", (has_t0, has_t1, column indices of the leaf's ts in the union, fn))`; leaves with `steps` keep a solve each."""
+
+    def __init__(self, subs, providers, union):
+        self.subs, self.providers, self.union = subs, providers, union
+
+    @staticmethod
+    def _from_union(u, spec):
+        has_t0, has_t1, cols, fn = spec
+        ts_u, ys_u = u.ts, u.ys
+        is_t = isinstance(ts_u, torch.Tensor)
+        n = ts_u.shape[0]
+        width = int(has_t0) + len(cols) + int(has_t1)
+        if is_t:
+            ts = torch.full((n, width), math.inf, dtype=ts_u.dtype, device=ts_u.device)
+            ys = torch.full((n, width) + tuple(ys_u.shape[2:]), math.inf, dtype=ys_u.dtype, device=ys_u.device)
+            idx = torch.as_tensor(cols, dtype=torch.long, device=ts_u.device)
+            rows = torch.arange(n, device=ts_u.device)
+        else:
+            ts = np.full((n, width), np.inf, ts_u.dtype)
+            ys = np.full((n, width) + tuple(ys_u.shape[2:]), np.inf, ys_u.dtype)
+            idx = np.asarray(cols, np.int64)
+            rows = np.arange(n)
+        off = int(has_t0)
+        if has_t0:
+            ts[:, 0], ys[:, 0] = ts_u[:, 0], ys_u[:, 0]
+        if len(cols):
+            ts[:, off:off + len(cols)] = ts_u[:, idx]
+            ys[:, off:off + len(cols)] = ys_u[:, idx]
+        if has_t1:
+            # the final value goes to the trajectory's running save index (_integrate.py:847-877): right after the ts it reached
+            g = ts[:, off:off + len(cols)]
+            reached = ((g == g) & (abs(g) != math.inf)).sum(1)
+            pos = reached + off
+            ts[rows, pos] = u.t_final
+            ys[rows, pos] = u.y_final
+        if fn is not save_y:
+            ys = _apply_save_fn(fn, ts, ys)
+        return ts, ys
 
     def __call__(self, throw: bool = True) -> Solution:
-        sols = [sv(throw=throw) for sv in self.solves]
-        it = iter(sols)
-        ts = _tree_map_subs(lambda _: next(it).ts, self.subs)
-        it = iter(sols)
-        ys = _tree_map_subs(lambda _: next(it).ys, self.subs)
-        return dataclasses.replace(sols[0], ts=ts, ys=ys)
+        u = self.union(throw=throw) if self.union is not None else None
+        outs, first = [], u
+        for kind, what in self.providers:
+            if kind == "own":
+                sol = what(throw=throw)
+                first = first if first is not None else sol
+                outs.append((sol.ts, sol.ys))
+            else:
+                outs.append(self._from_union(u, what))
+        it = iter(outs)
+        ts = _tree_map_subs(lambda _: next(it)[0], self.subs)
+        it = iter(outs)
+        ys = _tree_map_subs(lambda _: next(it)[1], self.subs)
+        return dataclasses.replace(first, ts=ts, ys=ys)
 
 
 def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
@@ -771,11 +821,44 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         leaves = _tree_leaves_subs(saveat.subs)
         if not leaves:
             raise ValueError("Empty saveat -- nothing will be saved.")
-        solves = [prepare(terms, solver, t0, t1, dt0, y0, args, saveat=SaveAt(subs=leaf, dense=saveat.dense and i == 0),
-                          stepsize_controller=stepsize_controller, event=event, max_steps=max_steps, device=device,
-                          solver_state=solver_state, controller_state=controller_state, made_jump=made_jump,
-                          hairer_initial_step=hairer_initial_step) for i, leaf in enumerate(leaves)]
-        return _MultiSolve(saveat.subs, solves)
+        def _prep(sub, dense):
+            return prepare(terms, solver, t0, t1, dt0, y0, args, saveat=SaveAt(subs=sub, dense=dense),
+                           stepsize_controller=stepsize_controller, event=event, max_steps=max_steps, device=device,
+                           solver_state=solver_state, controller_state=controller_state, made_jump=made_jump,
+                           hairer_initial_step=hairer_initial_step)
+        scalar_times = not (hasattr(t0, "shape") and len(getattr(t0, "shape")) >= 1) and not (hasattr(t1, "shape") and len(getattr(t1, "shape")) >= 1)
+        shared = [i for i, leaf in enumerate(leaves) if leaf.steps == 0]
+        if len(shared) < 2 or not scalar_times:   # (per-trajectory t0 / t1 may run in both directions: no common ordering of ts)
+            solves = [_prep(leaf, saveat.dense and i == 0) for i, leaf in enumerate(leaves)]
+            return _MultiSolve(saveat.subs, [("own", sv) for sv in solves], None)
+        # one solve for every leaf without `steps`: it saves the union of their ts (in the direction of integration) and t0;
+        # its finals (dedicated buffers: no t1 slot among the union's columns) serve the leaves' t1 rows
+        rdt_np = np.float32 if str(getattr(y0, "dtype", "float64")).endswith("float32") else np.float64
+        backwards = float(t1) < float(t0)
+        per_leaf = []
+        for i in shared:
+            tsi = leaves[i].ts
+            tsi = np.zeros(0, rdt_np) if tsi is None else np.asarray(tsi.detach().cpu() if isinstance(tsi, torch.Tensor) else tsi, rdt_np).reshape(-1)
+            dd = np.diff(-tsi if backwards else tsi)
+            if tsi.size and (not np.all(dd > 0) and not np.all(dd >= 0)):
+                raise RuntimeError("saveat.ts must be increasing or decreasing.")  # _integrate.py:1223-1227
+            per_leaf.append(tsi)
+        allts = np.unique(np.concatenate(per_leaf)) if any(a.size for a in per_leaf) else np.zeros(0, rdt_np)
+        any_t0 = any(leaves[i].t0 for i in shared)
+        if allts.size == 0 and not any_t0:
+            union = _prep(SubSaveAt(t1=True), saveat.dense)            # only t1 leaves: ys[:, 0] is the final value
+        else:
+            union = _prep(SubSaveAt(t0=any_t0, ts=(allts[::-1].copy() if backwards else allts) if allts.size else None), saveat.dense)
+        providers = []
+        for i, leaf in enumerate(leaves):
+            if i not in shared:
+                providers.append(("own", _prep(leaf, False)))
+                continue
+            tsi = per_leaf[shared.index(i)]
+            pos = np.searchsorted(allts, tsi)
+            cols = [int(any_t0) + int((allts.size - 1 - q) if backwards else q) for q in pos]
+            providers.append(("union", (leaf.t0, leaf.t1, cols, leaf.fn)))
+        return _MultiSolve(saveat.subs, providers, union)
     ctrl = ConstantStepSize() if stepsize_controller is None else stepsize_controller
     field, bm = _parse_terms(terms)
     if max_steps is None:

@@ -1175,3 +1175,34 @@ def test_randomised_differential_check_subset(dev):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--cases", "200", "--seed", "3"],
                        env=dict(os.environ, DFX_JIT="0"), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and " 0 failures" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("mode", ["plain", "max_steps", "event", "backwards", "host"])
+def test_subsaveat_leaves_share_one_solve(dev, mode):
+    """SaveAt(subs=...) leaves without `steps` are served by ONE solve over the union of their ts: each leaf must report,
+    bit for bit, what a solve with that SubSaveAt alone reports - also when max_steps or an event ends trajectories early (the
+    final value then sits right after the ts each trajectory reached) and backwards in time."""
+    rng = np.random.default_rng(8)
+    y0n = rng.uniform(-2, 2, (257, 2))
+    y0 = y0n if mode == "host" else torch.tensor(y0n, device=dev)
+    term, ctrl = dfx.ODETerm(dfx.fields.ForcedOscillator(1.0, 0.7, 2.0)), dfx.PIDController(rtol=1e-7, atol=1e-9)
+    t0, t1 = (3.0, 0.0) if mode == "backwards" else (0.0, 3.0)
+    grid = np.linspace(0.0, 3.0, 13)[1:-1]
+    some = np.array([0.4, 1.0, 2.75])
+    if mode == "backwards":
+        grid, some = grid[::-1].copy(), some[::-1].copy()
+    kw = dict(stepsize_controller=ctrl, max_steps=(12 if mode == "max_steps" else 2048), throw=False)
+    if mode == "event":
+        kw["event"] = dfx.Event(dfx.AffineEvent([1.0, 0.0], b=-0.3), dfx.Newton(1e-10, 1e-12))
+    leaves = {"end": dfx.SubSaveAt(t1=True), "start": dfx.SubSaveAt(t0=True),
+              "grid": dfx.SubSaveAt(t0=True, ts=grid, t1=True, fn=lambda t, y, args: y[..., 0] * 2.0),
+              "some": dfx.SubSaveAt(ts=some, t1=True), "ts_only": dfx.SubSaveAt(ts=some)}
+    sol = dfx.diffeqsolve(term, dfx.Dopri5(), t0, t1, None, y0, saveat=dfx.SaveAt(subs=leaves), **kw)
+    if mode != "plain":
+        fin = np.isfinite(to_np(sol.ts["grid"]))
+        assert mode in ("backwards", "host") or (not fin.all() and fin.any())      # early termination is exercised
+    for name, leaf in leaves.items():
+        ref = dfx.diffeqsolve(term, dfx.Dopri5(), t0, t1, None, y0, saveat=dfx.SaveAt(subs=leaf), **kw)
+        assert np.array_equal(to_np(sol.ts[name]), to_np(ref.ts)), name
+        assert np.array_equal(to_np(sol.ys[name]), to_np(ref.ys)), name
+    assert np.array_equal(to_np(sol.stats["num_steps"]), to_np(ref.stats["num_steps"])) and np.array_equal(to_np(sol.result), to_np(ref.result))
