@@ -85,13 +85,14 @@ USER_DIR = os.path.join(LIBDIR, "user")
 def build_user_field(tag, source, verbose=False):
     """Compile one generated translation unit (fields.CudaField: a user functor + ONE DFX_REGISTER) against csrc/launch.cuh
     into lib/user/dfx_user_<tag>.so (a plugin of the loaded libdiffrax_b200.so).  Cached: the tag carries the content hash of the functor,
-    and the object is rebuilt when the kernel headers are newer."""
+    and the object is rebuilt when the kernel headers are newer
+    (the plugin binds to the library by name at load time, so relinking the library does not invalidate it)."""
     os.makedirs(USER_DIR, exist_ok=True)
     out = os.path.join(USER_DIR, f"dfx_user_{tag}.so")
     src = os.path.join(USER_DIR, f"dfx_user_{tag}.cu")
     if not os.path.exists(LIB):
         raise RuntimeError(f"{LIB} not found: build it with `python -m diffrax_b200.build` first")
-    if os.path.exists(src) and open(src).read() == source and not _stale(out, [src, LIB] + _headers(plugin=True)):
+    if os.path.exists(src) and open(src).read() == source and not _stale(out, [src] + _headers(plugin=True)):
         return out
     if not os.path.exists(NVCC):
         raise RuntimeError(f"compiling a CudaField needs nvcc ({NVCC} not found; set NVCC)")
