@@ -555,14 +555,18 @@ static bool host_pipe_eligible(const dfx_solve_desc *h) {
   const bool adaptive = h->controller == DFX_CTRL_PID;
   const char *e = std::getenv("DFX_HOST_PIPE");
   if (!(adaptive || (e && atoi(e) == 2))) return false;
-  return !rich && h->field_id != DFX_FIELD_MLP && h->field_id < DFX_FIELD_USER && h->n_traj >= 256 * 1024;
+  long long min_traj = 256 * 1024;
+  if (const char *m = std::getenv("DFX_HOST_PIPE_MIN")) { const long long v = atoll(m); if (v >= 1024) min_traj = v; }  // experiments
+  return !rich && h->field_id != DFX_FIELD_MLP && h->field_id < DFX_FIELD_USER && h->n_traj >= min_traj;
 }
 
 static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
   const size_t es = h->dtype == DFX_F64 ? 8 : 4;
   const size_t N = (size_t)h->n_traj, D = (size_t)h->dim;
   const size_t T = (size_t)dfx_out_size(h);
-  int64_t want = 16;
+  // chunk count: measured on C2 (B200, PCIe gen 5): 2^20 trajectories 16 chunks; 2^19: 12 (2.06 ms; 16: 2.10, 8: 2.08); 2^18: 8
+  // (1.24 ms; 16: 1.30, 4: 1.26) - every chunk costs a completion round trip through mapped host memory
+  int64_t want = h->n_traj >= (1 << 20) ? 16 : (h->n_traj >= (1 << 19) ? 12 : 8);
   if (const char *e = std::getenv("DFX_HOST_CHUNKS")) { const int64_t v = atoll(e); if (v >= 1) want = v; }
   if (want > kMaxPipeChunks) want = kMaxPipeChunks;
   const size_t chunk_len = ((N + (size_t)want - 1) / (size_t)want + 31) & ~(size_t)31;
