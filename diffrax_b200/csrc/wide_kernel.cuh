@@ -10,7 +10,8 @@
 //     leaves the same value in every lane, so that all control flow (accept / reject, the step loop, the work queue) is
 //     warp-uniform: no divergence, and the trajectories of different warps are as independent as in the other kernel.
 // Scope: explicit RK tableaux (Tsit5, Dopri5, Dopri8, Bosh3, Heun, Midpoint, Ralston), PIDController (the faithful
-// pid.py:394-567 path; dtmin / dtmax) and ConstantStepSize, SaveAt(t0, t1, ts, steps), per-trajectory t0 / t1, finals + totals.
+// pid.py:394-567 path; dtmin / dtmax) and ConstantStepSize, SaveAt(t0, t1, ts, steps), per-trajectory t0 / t1, finals + totals + the
+// fused peer gather of the sharded entry.
 // The controller is the reference's faithful path; the stage sums are chained onto y0 for <= 7 stages like in the per-thread
 // kernel (DFX_OPT_CHAIN_Y0=0 restores vector_tree_dot, then y0 + incr).
 #pragma once
@@ -258,6 +259,17 @@ __global__ void __launch_bounds__(kWideBlock, wide_min_blocks<Field::kDim>()) wi
       for (int j = 0; j < CH; ++j)
         if (lane + 32 * j < D) p.y_final[idx * D + lane + 32 * j] = y[j];
     }
+    if (p.n_peers != 0) {
+      // the all_gather of the finals, fused (see ensemble_kernel.cuh): P2P stores into every rank's global buffer
+      const long long g = p.peer_row0 + idx;
+#pragma unroll 1
+      for (int q = 0; q < p.n_peers; ++q) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (lane + 32 * j < D) p.peer_y[q][g * D + lane + 32 * j] = y[j];
+        if (lane == 0) p.peer_t[q][g] = tprev * direction;
+      }
+    }
     // unfilled output slots read +inf (_integrate.py:1296-1300, 1320-1322)
     if (p.save_ts != nullptr || p.save_steps > 0) {
       pad_tail(p.ts_out + idx * p.out_size, (long long)save_index, (long long)p.out_size, lane, false);
@@ -281,9 +293,9 @@ int launch_wide(const dfx_solve_desc *d, void *stream_v) {
   cudaStream_t stream = (cudaStream_t)stream_v;
   static_assert(IsTableau<Solver>::value && !IsHalf<Solver>::value, "the wide kernel runs explicit RK tableaux");
   if (d->levy_area != DFX_LEVY_NONE || d->n_events != 0 || d->step_ts || d->jump_ts || d->state_in || d->state_out || d->save_dense ||
-      d->store_rejected_steps > 0 || (d->hairer_initial_step && std::isnan(d->dt0)) || d->n_peers != 0) {
+      d->store_rejected_steps > 0 || (d->hairer_initial_step && std::isnan(d->dt0))) {
     set_error("the warp-per-trajectory kernel of a wide functor covers ODE solves with SaveAt(t0, t1, ts, steps): no Brownian "
-              "motion, events, ClipStepSizeController, dense output, resumed states, Hairer starting step or peer gather");
+              "motion, events, ClipStepSizeController, dense output, resumed states or Hairer starting step");
     return DFX_ERR_UNSUPPORTED;
   }
   if (host_pipe() != nullptr) { set_error("internal: the host pipeline does not drive the wide kernel"); return DFX_ERR_UNSUPPORTED; }

@@ -50,7 +50,19 @@ o2 = p2()
 torch.cuda.synchronize()
 assert torch.equal(o2.y_final, r2.ys[:, 0]) and int(o2.stats["num_steps"]) == 32 * n
 p2.close()
+# a wide state (one trajectory per warp, csrc/wide_kernel.cuh): the same fused gather, every rank compiles / loads the plugin
+D, nw = 40, 3001
+l96 = dfx.fields.CudaField(D, "fi = (y[(i + 1) % D] - y[(i + D - 2) % D]) * y[(i + D - 1) % D] - y[i] + p[0];", params=[8.0], wide=True)
+yw = torch.tensor(8.0 + np.random.default_rng(5).normal(0, 0.5, (nw, D)), device=dev)
+cw = dfx.PIDController(1e-7, 1e-7)
+r3 = dfx.diffeqsolve(dfx.ODETerm(l96), dfx.Tsit5(), 0.0, 0.5, None, yw, stepsize_controller=cw)
+for mode in ("peer", "nccl"):
+    p3 = dfx.prepare_sharded(dfx.ODETerm(l96), dfx.Tsit5(), 0.0, 0.5, None, yw, stepsize_controller=cw, gather=mode)
+    o3 = p3()
+    torch.cuda.synchronize()
+    assert torch.equal(o3.y_final, r3.ys[:, 0]) and int(o3.stats["num_steps"]) == int(r3.stats["num_steps"].sum()), (rank, mode)
+    p3.close()
 dist.barrier()
 if rank == 0:
-    print(f"peer gather ok: world {world}, {n} trajectories, device + host inputs, peer == nccl == single-GPU")
+    print(f"peer gather ok: world {world}, {n} trajectories, device + host inputs, peer == nccl == single-GPU; wide state (d = {D}) too")
 dist.destroy_process_group()
