@@ -95,6 +95,9 @@ def random_case(r):
         c["rtol"] = float(10.0 ** r.uniform(-5 if f32 else -9, -3))
         c["atol"] = float(10.0 ** r.uniform(-6 if f32 else -10, -4))
         c["dt0"] = None if r.random() < 0.5 else sign * span * float(r.choice([0.01, 0.1, 1.0]))
+        if c["dtype"] == np.float32 and c["solver"] == "dopri8" and c["dt0"] is None:
+            # the same in fp32 for the 8th-order pair: the error estimate of a 0.01 first step is below eps
+            c["dt0"] = sign * span * 0.1
         if c["solver"] in ("half:tsit5", "half:bosh3"):
             # step doubling around a 3rd / 5th order method: with the default first step of 0.01 the two results y1 and y1_alt
             # agree to the last place or differ by one ulp - |y1 - y1_alt| in {0, ulp} is pure rounding noise, and the reference's
