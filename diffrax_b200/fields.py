@@ -363,8 +363,10 @@ class CudaField(Field):
         self.event_srcs = [str(e) for e in events]
         if len(self.event_srcs) > _lib.MAX_EVENTS:
             raise ValueError(f"CudaField: at most {_lib.MAX_EVENTS} condition functions")
-        key = "\0".join(self.event_srcs + ["wide" if self.wide else "thread", repr(sorted(self.defines.items())), str(self.dim), self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble, str(len(self.p)),
-                         str(self.min_blocks)])
+        # everything that shapes the generated source identifies the functor (parameter VALUES do not: they are run-time data)
+        key = "\0".join(self.event_srcs + ["wide" if self.wide else "thread", repr(sorted(self.defines.items())), str(self.dim),
+                                           self.drift_src, str(diffusion), str(noise), str(self.noise_dim), self.preamble,
+                                           str(len(self.p)), str(self.min_blocks)])
         self._hash = hashlib.sha256(key.encode()).hexdigest()[:16]
         self._id = _lib.FIELD_USER + int(self._hash[:7], 16)
         self.name = name or f"user_{self._hash}"
