@@ -814,8 +814,6 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
             solver_state=None, controller_state=None, made_jump=None, device: int = 0,
             hairer_initial_step: bool = False, final_out=None, dense_padding: str = "lazy") -> EnsembleSolve:
     """Validate the arguments of a `diffeqsolve` call and allocate its outputs once."""
-    if args is not None:
-        raise ValueError("args must be None: functor parameters are bound when the functor is created")
     saveat = SaveAt(t1=True) if saveat is None else saveat
     if saveat.subs is not None and not isinstance(saveat.subs, SubSaveAt):
         leaves = _tree_leaves_subs(saveat.subs)
@@ -987,7 +985,22 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
         raise ValueError("ShARK requires MultiTerm(ODETerm(drift), ControlTerm(diffusion, VirtualBrownianTree))")
     # a user-written functor (fields.CudaField) compiles + registers its kernel for this combination on first use
     ensure = getattr(field, "ensure_kernel", None)
-    if ensure is not None:
+    if args is not None:
+        # vmapped `args` (_integrate.py:896): per-trajectory functor parameters [N, n_params] - a parameter sweep over the ensemble
+        if ensure is None:
+            raise ValueError("args: the parameters of a built-in functor are bound when it is created (one set for the ensemble); a "
+                             "`fields.CudaField` takes per-trajectory parameters as `args` of shape [N, len(params)]")
+        aa = xp.asarray(args if is_torch else np.asarray(args), rdt)
+        if aa.ndim != 2 or int(aa.shape[0]) != n or int(aa.shape[1]) != len(field.params()):
+            raise ValueError(f"args must have shape [N, n_params] = [{n}, {len(field.params())}], got {tuple(aa.shape)}")
+        if is_torch and aa.device != y0a.device:
+            aa = aa.to(y0a.device)
+        aa = aa.contiguous() if is_torch else np.ascontiguousarray(aa)
+        keep_alive.append(aa)
+        D.field_id = field.field_id_args
+        D.traj_args, D.n_traj_args = xp.ptr(aa), int(aa.shape[1])
+        ensure(d, int(D.solver_id), int(D.dtype), int(D.levy_area), per_traj=True)
+    elif ensure is not None:
         ensure(d, int(D.solver_id), int(D.dtype), int(D.levy_area))
     else:  # a built-in functor with a solver it was not prebuilt for: instantiated on first use
         from .fields import ensure_builtin_kernel

@@ -310,7 +310,8 @@ def prepare_sharded(terms, solver, t0, t1, dt0, y0, args=None, *, group=None, de
     sh = ShardedSolve.__new__(ShardedSolve)
     # two-phase construction: the record buffers must exist before `prepare` binds them as final_out
     ShardedSolve.__init__(sh, None, lo, hi, n_total, d, dtype, device, group, gather)
-    sh.plan = _api.prepare(_slice_terms(terms, lo, hi), solver, _slice_rows(t0, lo, hi), _slice_rows(t1, lo, hi), dt0, y_loc, args,
+    sh.plan = _api.prepare(_slice_terms(terms, lo, hi), solver, _slice_rows(t0, lo, hi), _slice_rows(t1, lo, hi), dt0, y_loc,
+                           None if args is None else args[lo:hi],   # per-trajectory parameters follow their trajectories
                            device=device.index if device.index is not None else 0, final_out=(sh.y_buf, sh.t_buf, sh.totals), **kw)
     return sh
 

@@ -67,6 +67,7 @@ class SolveDesc(C.Structure):
         ("dense_lazy_padding", C.c_int32),
         ("n_peers", C.c_int32), ("peer_row_offset", C.c_int64),
         ("peer_y_final", C.c_void_p * 8), ("peer_t_final", C.c_void_p * 8),
+        ("traj_args", C.c_void_p), ("n_traj_args", C.c_int32),
     ]
 
 

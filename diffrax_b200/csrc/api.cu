@@ -344,6 +344,7 @@ static int check_desc(const dfx_solve_desc *d) {
   if (d->n_traj > 0 && !d->y0) { set_error("y0 is null"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->n_traj > 0 && (!d->stats || !d->result)) { set_error("stats / result buffers are required"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->max_steps < 0) { set_error("max_steps must be >= 0 (max_steps=None is not supported)"); return DFX_ERR_BAD_ARGUMENT; }
+  if (d->traj_args != nullptr && (d->n_traj_args < 1 || d->n_traj_args > 64)) { set_error("traj_args needs 1 <= n_traj_args <= 64"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->save_steps < 0) { set_error("save_steps must be >= 0"); return DFX_ERR_BAD_ARGUMENT; }
   if (d->controller == DFX_CTRL_CONSTANT && is_nan(d->dt0)) {
     // constant.py:41-45
@@ -483,6 +484,7 @@ static int solve_host_chunk(const dfx_solve_desc *h, int64_t lo, int64_t cnt, cu
   d.jump_ts = dev_in(h->jump_ts, (size_t)h->n_jump_ts * es);
   d.bm_keys = (const uint32_t *)dev_in(off(h->bm_keys, 8), N * 8);
   d.field_weights = dev_in(h->field_weights, (size_t)h->n_field_weights * es);
+  d.traj_args = dev_in(off(h->traj_args, (size_t)h->n_traj_args * es), N * (size_t)h->n_traj_args * es);
   d.ts_out = dev_out(off(h->ts_out, T * es), N * T * es);
   d.ys_out = dev_out(off(h->ys_out, T * D * es), N * T * D * es);
   d.stats = (int32_t *)dev_out(off(h->stats, 12), N * 3 * 4);
@@ -649,6 +651,7 @@ static int solve_host_pipelined(const dfx_solve_desc *h, int device) {
     d.t0_per_traj = per_traj_in(h->t0_per_traj, es);
     d.t1_per_traj = per_traj_in(h->t1_per_traj, es);
     d.bm_keys = (const uint32_t *)per_traj_in(h->bm_keys, 8);
+    d.traj_args = per_traj_in(h->traj_args, (size_t)h->n_traj_args * es);
     d.ts_out = per_traj_out(h->ts_out, T * es);
     d.ys_out = per_traj_out(h->ys_out, T * D * es);
     d.stats = (int32_t *)per_traj_out(h->stats, 12);

@@ -70,6 +70,9 @@ template <class F> struct StateNoise<F, std::void_t<decltype(F::kStateNoise)>> {
 // condition functions of the functor's own (Event(cond_fn) with an arbitrary cond_fn): Field::event<R>(fp, j, t, y), j < kUserEvents
 template <class F, class = void> struct UserEvents { static constexpr int value = 0; };
 template <class F> struct UserEvents<F, std::void_t<decltype(F::kUserEvents)>> { static constexpr int value = F::kUserEvents; };
+// per-trajectory functor parameters (the vmapped `args`): Field::P<R> is { R p[kNumParams]; } and trajectory i uses traj_args[i, :]
+template <class F, class = void> struct PerTrajArgs { static constexpr bool value = false; };
+template <class F> struct PerTrajArgs<F, std::void_t<decltype(F::kPerTrajArgs)>> { static constexpr bool value = F::kPerTrajArgs; };
 template <class T, class = void> struct IsHalf { static constexpr bool value = false; };
 template <class I> struct IsHalf<HalfOf<I>> { static constexpr bool value = true; };
 template <class T> struct InnerId { static constexpr int value = T::kId; };
@@ -133,6 +136,8 @@ struct SolveParams {
   int pipe_chunk_len;             // multiple of 32 trajectories, so no 128-byte line straddles two chunks
   const uint32_t *keys;
   VbtParams vbt;
+  const R *traj_args;  // [n_traj, n_traj_args] per-trajectory functor parameters, or null
+  int n_traj_args;
 };
 
 #ifndef DFX_BLOCK_THREADS
@@ -246,7 +251,11 @@ template <class R> __device__ __forceinline__ int clip_find_idx(R t, const R *ts
 //          vs 113 664 lanes at 6 CTAs/SM, 132 608 at 7)
 template <class R, class Field, class Solver, int LEVY, bool RICH, bool EXTRA = false, bool SPEC = false, int MOREB = 0>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<R, Field, Solver, LEVY, RICH>() + MOREB)
-ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) {
+ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp_in) {
+  // the functor's parameters: the launch-wide kernel argument, or (functors compiled with kPerTrajArgs) a per-lane copy that is
+  // reloaded from traj_args[idx, :] whenever the lane claims a trajectory; the copy is dead code for every other functor
+  [[maybe_unused]] typename Field::template P<R> fp_lane = fp_in;
+  const typename Field::template P<R> &fp = PerTrajArgs<Field>::value ? fp_lane : fp_in;
   constexpr int D = Field::kDim;
   constexpr int S = Solver::S;
   constexpr bool SDE = LEVY != DFX_LEVY_NONE;
@@ -525,6 +534,12 @@ ensemble_kernel(const SolveParams<R> p, const typename Field::template P<R> fp) 
           t1 = b * direction;
 #pragma unroll
           for (int c = 0; c < D; ++c) y[c] = p.y0[idx * D + c];
+          if constexpr (PerTrajArgs<Field>::value) {
+            if (p.traj_args != nullptr) {
+#pragma unroll
+              for (int i = 0; i < Field::kNumParams; ++i) fp_lane.p[i] = p.traj_args[idx * Field::kNumParams + i];
+            }
+          }
           // controller init: pid.py:316-392 (dt0=None -> 0.01) / constant.py:30-55
           R dt0 = p.has_dt0 ? p.dt0 * direction : R(0.01);
           if (p.controller == DFX_CTRL_PID) {

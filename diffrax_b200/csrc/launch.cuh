@@ -86,6 +86,7 @@ int fill_params(const dfx_solve_desc *d, SolveParams<R> &p, bool sde) {
   p.n_peers = d->n_peers; p.peer_row0 = d->peer_row_offset;
   for (int q = 0; q < DFX_MAX_PEERS; ++q) { p.peer_y[q] = (R *)d->peer_y_final[q]; p.peer_t[q] = (R *)d->peer_t_final[q]; }
   p.keys = d->bm_keys;
+  p.traj_args = (const R *)d->traj_args; p.n_traj_args = d->n_traj_args;
   p.reject_ts = nullptr; p.n_reject = d->store_rejected_steps > 0 ? d->store_rejected_steps : 0;
   p.state_in = (const R *)d->state_in; p.state_out = (R *)d->state_out; p.state_in_flags = d->state_in_flags;
   p.n_events = d->n_events; p.event_root = d->event_root_find;
@@ -221,6 +222,10 @@ int launch_solve(const dfx_solve_desc *d, void *stream_v) {
   if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
+  if (d->traj_args != nullptr && (!PerTrajArgs<Field>::value || d->n_traj_args != Field::kNumParams)) {
+    set_error("per-trajectory args: this functor takes %d (got %d)", PerTrajArgs<Field>::value ? Field::kNumParams : 0, d->n_traj_args);
+    return DFX_ERR_BAD_ARGUMENT;
+  }
   for (int i = 0; i < d->n_events && i < DFX_MAX_EVENTS; ++i)
     if (d->event_kind[i] == DFX_EVENT_USER && (p.ev_user[i] < 0 || p.ev_user[i] >= UserEvents<Field>::value)) {
       set_error("event %d asks for condition %d of a functor that defines %d", i, p.ev_user[i], UserEvents<Field>::value);

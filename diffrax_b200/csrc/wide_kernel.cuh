@@ -35,7 +35,9 @@ constexpr int kWideBlock = 128;
 template <int D> constexpr int wide_min_blocks() { return DFX_WIDE_MIN_BLOCKS > 0 ? DFX_WIDE_MIN_BLOCKS : (D <= 128 ? 4 : 1); }
 
 template <class R, class Field, class Solver>
-__global__ void __launch_bounds__(kWideBlock, wide_min_blocks<Field::kDim>()) wide_kernel(SolveParams<R> p, typename Field::template P<R> fp) {
+__global__ void __launch_bounds__(kWideBlock, wide_min_blocks<Field::kDim>()) wide_kernel(SolveParams<R> p, typename Field::template P<R> fp_in) {
+  [[maybe_unused]] typename Field::template P<R> fp_warp = fp_in;   // per-trajectory args (see ensemble_kernel.cuh)
+  const typename Field::template P<R> &fp = PerTrajArgs<Field>::value ? fp_warp : fp_in;
   constexpr int D = Field::kDim, S = Solver::S, CH = (D + 31) / 32;
   constexpr bool FSAL = Solver::kFsal;
   constexpr int INTERP = Solver::kInterp;
@@ -80,6 +82,12 @@ __global__ void __launch_bounds__(kWideBlock, wide_min_blocks<Field::kDim>()) wi
     R y[CH], f_fsal[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) { y[j] = (lane + 32 * j < D) ? p.y0[idx * D + lane + 32 * j] : R(0); f_fsal[j] = R(0); }
+    if constexpr (PerTrajArgs<Field>::value) {
+      if (p.traj_args != nullptr) {
+#pragma unroll
+        for (int i = 0; i < Field::kNumParams; ++i) fp_warp.p[i] = p.traj_args[idx * Field::kNumParams + i];
+      }
+    }
     R dt0 = p.has_dt0 ? p.dt0 * direction : R(0.01);
     int cs_num_steps = 0;
     if (p.controller == DFX_CTRL_PID) {
@@ -304,6 +312,10 @@ int launch_wide(const dfx_solve_desc *d, void *stream_v) {
   if (d->n_field_params < Field::kNumParams) { set_error("field needs %d parameters, got %d", Field::kNumParams, d->n_field_params); return DFX_ERR_BAD_ARGUMENT; }
   const auto fp = Field::template make<R>(d->field_params, d->n_field_params, d->field_weights);
   if (p.n_traj == 0) return 0;
+  if (d->traj_args != nullptr && (!PerTrajArgs<Field>::value || d->n_traj_args != Field::kNumParams)) {
+    set_error("per-trajectory args: this functor takes %d (got %d)", PerTrajArgs<Field>::value ? Field::kNumParams : 0, d->n_traj_args);
+    return DFX_ERR_BAD_ARGUMENT;
+  }
   int sms = 0;
   if (int e = device_sm_count(&sms)) return e;
   const size_t smem = (size_t)(kWideBlock / 32) * Field::kDim * sizeof(R);

@@ -281,6 +281,7 @@ struct UserField {
   static constexpr int kDim = @DIM@;
   static constexpr bool kSde = @SDE@;
   static constexpr int kNumParams = @NP@;
+@ARGS_TRAIT@
 @NOISE_TRAITS@
   template <class R> struct P { R p[@NP1@]; };
   template <class R> static P<R> make(const double *q, int n, const void *) {
@@ -324,6 +325,8 @@ class CudaField(Field):
     ``wide=True``: a WIDE state (``dim`` up to 1024), one trajectory per warp (csrc/wide_kernel.cuh): the state is spread over
     the 32 lanes, and ``drift`` is written per component - statements that assign ``fi``, component ``i`` of f, from ``i``, the
     whole state ``y[0..D)``, ``p`` and ``t``; e.g. Lorenz-96: ``"fi = (y[(i + 1) % D] - y[(i + D - 2) % D]) * y[(i + D - 1) % D] - y[i] + p[0];"``.
+    Parameter sweeps: ``diffeqsolve(..., args=A)`` with ``A`` of shape ``[N, len(params)]`` gives trajectory ``i`` the parameters
+    ``p[] = A[i]`` (what a vmapped ``args`` is to the reference, _integrate.py:896); ``params`` then only fixes their number.
     ``events=["<expr>", ...]``: real-valued condition functions in ``t``, ``y``, ``p`` for ``Event(field.event(i), ...)`` - the
     reference's arbitrary ``cond_fn(t, y, args)`` (_event.py:13-118); with a root finder the crossing is located on the step's
     interpolant.  ``preamble``: device helper functions / constants placed before the functor.  ``min_blocks_per_sm``: occupancy target handed
@@ -385,7 +388,12 @@ class CudaField(Field):
             raise IndexError(f"this CudaField defines {len(self.event_srcs)} condition function(s)")
         return UserEvent(self, index)
 
-    def source(self, solver_id, dtype_id, levy):
+    @property
+    def field_id_args(self):
+        """The id of the kernel variant that reads per-trajectory parameters (`diffeqsolve(..., args=[N, n_params])`)."""
+        return self._id + (1 << 29)
+
+    def source(self, solver_id, dtype_id, levy, per_traj=False):
         inner = solver_id & ~_HALF
         solver = _SOLVER_CPP[inner]
         if solver_id & _HALF:
@@ -393,7 +401,8 @@ class CudaField(Field):
         np_ = len(self.p)
         if self.wide:
             rep = {"@DEFINES@": "".join(f"#define {k} {v}\n" for k, v in sorted(self.defines.items())), "@PREAMBLE@": self.preamble,
-                   "@ID@": str(self._id), "@DIM@": str(self.dim), "@NP@": str(np_), "@NP1@": str(max(np_, 1)), "@DRIFT@": self.drift_src,
+                   "@ARGS_TRAIT@": "  static constexpr bool kPerTrajArgs = true;" if per_traj else "",
+                   "@ID@": str(self.field_id_args if per_traj else self._id), "@DIM@": str(self.dim), "@NP@": str(np_), "@NP1@": str(max(np_, 1)), "@DRIFT@": self.drift_src,
                    "@REAL@": "double" if dtype_id == _lib.F64 else "float", "@SOLVER@": solver}
             src = _WIDE_TU
             for k, v in rep.items():
@@ -417,7 +426,9 @@ class CudaField(Field):
                     f"    [[maybe_unused]] const R *p = P_.p;\n    (void)t;\n    switch (i) {{\n{cases}    }}\n    return R(0);\n  }}\n")
         defs = "".join(f"#define {k} {v}\n" for k, v in sorted(self.defines.items()))
         rep = {"@DEFINES@": defs + ("" if self.min_blocks is None else f"#define DFX_MIN_BLOCKS {self.min_blocks}"),
-               "@PREAMBLE@": self.preamble, "@ID@": str(self._id), "@DIM@": str(self.dim), "@SDE@": "true" if self.is_sde else "false",
+               "@ARGS_TRAIT@": "  static constexpr bool kPerTrajArgs = true;" if per_traj else "",
+               "@PREAMBLE@": self.preamble, "@ID@": str(self.field_id_args if per_traj else self._id), "@DIM@": str(self.dim),
+               "@SDE@": "true" if self.is_sde else "false",
                "@NP@": str(np_), "@NP1@": str(max(np_, 1)), "@NOISE_TRAITS@": traits, "@DRIFT@": self.drift_src, "@NOISE_FNS@": fns,
                "@REAL@": "double" if dtype_id == _lib.F64 else "float", "@SOLVER@": solver, "@LEVY@": str(int(levy))}
         src = _USER_TU
@@ -425,11 +436,14 @@ class CudaField(Field):
             src = src.replace(k, v)
         return src
 
-    def ensure_kernel(self, dim, solver_id, dtype_id, levy):
-        """Compile (once) and load the kernel for this (solver, dtype, Levy area); called by `prepare`."""
+    def ensure_kernel(self, dim, solver_id, dtype_id, levy, per_traj=False):
+        """Compile (once) and load the kernel for this (solver, dtype, Levy area); called by `prepare`.  `per_traj`: the variant
+        whose parameters `p[]` are read per trajectory from `args[N, n_params]` (registered under `field_id_args`)."""
         if dim != self.dim:
             raise ValueError(f"CudaField has state dimension {self.dim}, got y0 with d={dim}")
-        key = (int(solver_id), int(dtype_id), int(levy))
+        if per_traj and not self.p:
+            raise ValueError("CudaField: per-trajectory args need a functor with parameters (`params=[...]` gives their number)")
+        key = (int(solver_id), int(dtype_id), int(levy), bool(per_traj))
         if key in self._ready:
             return
         inner = solver_id & ~_HALF
@@ -443,11 +457,13 @@ class CudaField(Field):
         if self.noise_src is not None and inner == 8:
             raise ValueError("ShARK is an additive-noise SRK (shark.py:10-30): the diffusion of this field depends on y")
         L = _lib.lib()
-        if not L.dfx_has_kernel(self._id, self.dim, int(solver_id), int(dtype_id), int(levy)):
+        fid = self.field_id_args if per_traj else self._id
+        if not L.dfx_has_kernel(fid, self.dim, int(solver_id), int(dtype_id), int(levy)):
             from . import build
-            path = build.build_user_field(f"{self._hash}_{solver_id:x}_{dtype_id}_{levy}", self.source(solver_id, dtype_id, levy))
+            path = build.build_user_field(f"{self._hash}_{solver_id:x}_{dtype_id}_{levy}" + ("_a" if per_traj else ""),
+                                          self.source(solver_id, dtype_id, levy, per_traj))
             _lib.load_plugin(path)
-            if not L.dfx_has_kernel(self._id, self.dim, int(solver_id), int(dtype_id), int(levy)):
+            if not L.dfx_has_kernel(fid, self.dim, int(solver_id), int(dtype_id), int(levy)):
                 raise RuntimeError(f"{path} was loaded but registered no launcher for this combination")
         self._ready.add(key)
 
@@ -462,6 +478,7 @@ struct UserField {
   static constexpr int kDim = @DIM@;
   static constexpr bool kSde = false;
   static constexpr int kNumParams = @NP@;
+@ARGS_TRAIT@
   template <class R> struct P { R p[@NP1@]; };
   template <class R> static P<R> make(const double *q, int n, const void *) {
     P<R> o;

@@ -203,6 +203,13 @@ typedef struct dfx_solve_desc {
   int64_t peer_row_offset;               /* first global row of this rank's block */
   void *peer_y_final[8];                 /* DFX_MAX_PEERS == 8 */
   void *peer_t_final[8];
+
+  /* Per-trajectory `args` (the vmapped `args` of diffeqsolve(..., args=...), _integrate.py:896: a parameter sweep across the
+   * ensemble): [n_traj, n_traj_args] dtype-typed values, DEVICE (or host for *_host) pointer; trajectory i evaluates the
+   * functor with parameters traj_args[i, :] instead of field_params.  Only for functors compiled with kPerTrajArgs
+   * (fields.CudaField registers such a variant under its own field id); NULL = off. */
+  const void *traj_args;
+  int32_t n_traj_args;
 } dfx_solve_desc;
 
 /* ---- library ---- */

@@ -427,3 +427,54 @@ def test_mlp_field_other_sizes_on_demand(dev, d, width, dtype):
     assert same.mean() > (0.7 if f32 else 0.95)
     err = np.abs(_np(sol.ys)[same] - o["ys"][same]).max() / np.abs(o["ys"]).max()
     assert err < (2e-4 if f32 else 1e-10), err
+
+
+def test_per_trajectory_args_source_and_checks():
+    lor = dfx.fields.CudaField(3, LORENZ_SRC, params=[10.0, 28.0, 8.0 / 3.0])
+    src = lor.source(1, _lib.F64, 0, per_traj=True)
+    assert "kPerTrajArgs = true" in src and f"kId = {lor.field_id_args}" in src and "kPerTrajArgs" not in lor.source(1, _lib.F64, 0)
+    args = np.tile([10.0, 28.0, 8.0 / 3.0], (5, 1))
+    p = dfx.prepare(dfx.ODETerm(lor), dfx.Dopri5(), 0.0, 1.0, None, np.ones((5, 3)), args, stepsize_controller=dfx.PIDController(1e-6, 1e-6))
+    assert p.desc.field_id == lor.field_id_args and p.desc.n_traj_args == 3 and p.desc.traj_args
+    assert _lib.lib().dfx_has_kernel(lor.field_id_args, 3, 1, _lib.F64, 0) == 1
+    with pytest.raises(ValueError, match=r"\[N, n_params\]"):
+        dfx.prepare(dfx.ODETerm(lor), dfx.Dopri5(), 0.0, 1.0, None, np.ones((5, 3)), args[:, :2], stepsize_controller=dfx.PIDController(1e-6, 1e-6))
+    with pytest.raises(ValueError, match="built-in functor"):
+        dfx.prepare(dfx.ODETerm(dfx.fields.Lorenz()), dfx.Dopri5(), 0.0, 1.0, None, np.ones((5, 3)), args, stepsize_controller=dfx.PIDController(1e-6, 1e-6))
+
+
+@pytest.mark.gpu
+def test_per_trajectory_args_parameter_sweep(dev):
+    """diffeqsolve(..., args=[N, n_params]) - the vmapped `args` of the reference, a parameter sweep across the ensemble: every
+    trajectory must come out exactly as in a solve of its parameter group with ensemble-wide parameters (device path, the
+    chunked host path with its row offsets, the sharded entry); and the same for a wide state."""
+    rng = np.random.default_rng(12)
+    n = 300_000                                   # host path: more than one chunk
+    y0 = np.stack([rng.uniform(-15, 15, n), rng.uniform(-20, 20, n), rng.uniform(5, 45, n)], 1)
+    rhos = np.array([14.0, 28.0, 35.0, 99.96])
+    grp = rng.integers(0, 4, n)
+    args = np.stack([np.full(n, 10.0), rhos[grp], np.full(n, 8.0 / 3.0)], 1)
+    lor = dfx.fields.CudaField(3, LORENZ_SRC, params=[10.0, 28.0, 8.0 / 3.0])
+    ctrl = dfx.PIDController(rtol=1e-6, atol=1e-6)
+    y0d, argsd = torch.tensor(y0, device=dev), torch.tensor(args, device=dev)
+    sweep = dfx.diffeqsolve(dfx.ODETerm(lor), dfx.Dopri5(), 0.0, 1.0, None, y0d, argsd, stepsize_controller=ctrl)
+    for g, rho in enumerate(rhos):
+        m = torch.tensor(grp == g, device=dev)
+        one = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.CudaField(3, LORENZ_SRC, params=[10.0, float(rho), 8.0 / 3.0])), dfx.Dopri5(), 0.0, 1.0, None,
+                              y0d[m], stepsize_controller=ctrl)
+        assert torch.equal(sweep.ys[m], one.ys) and torch.equal(sweep.stats["num_steps"][m], one.stats["num_steps"])
+    assert len(set(_np(sweep.stats["num_steps"])[grp == 0].tolist()) ^ set(_np(sweep.stats["num_steps"])[grp == 3].tolist())) > 0  # the sweep matters
+    host = dfx.diffeqsolve(dfx.ODETerm(lor), dfx.Dopri5(), 0.0, 1.0, None, y0, args, stepsize_controller=ctrl)            # numpy in: host entry
+    assert np.array_equal(_np(host.ys), _np(sweep.ys)) and np.array_equal(_np(host.stats["num_steps"]), _np(sweep.stats["num_steps"]))
+    sh = dfx.sharded_diffeqsolve(dfx.ODETerm(lor), dfx.Dopri5(), 0.0, 1.0, None, y0d, argsd, stepsize_controller=ctrl)
+    assert torch.equal(sh.y_final, sweep.ys[:, 0]) and int(sh.stats["num_steps"]) == int(sweep.stats["num_steps"].sum())
+    # wide state: Lorenz-96 with a per-trajectory forcing F
+    D, nw = 40, 600
+    l96 = dfx.fields.CudaField(D, L96, params=[8.0], wide=True)
+    yw = torch.tensor(8.0 + rng.normal(0, 0.5, (nw, D)), device=dev)
+    F = np.where(np.arange(nw) % 2 == 0, 8.0, 4.0)
+    a = dfx.diffeqsolve(dfx.ODETerm(l96), dfx.Tsit5(), 0.0, 0.5, None, yw, torch.tensor(F[:, None], device=dev), stepsize_controller=ctrl)
+    for val in (8.0, 4.0):
+        m = torch.tensor(F == val, device=dev)
+        b = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.CudaField(D, L96, params=[val], wide=True)), dfx.Tsit5(), 0.0, 0.5, None, yw[m], stepsize_controller=ctrl)
+        assert torch.equal(a.ys[m], b.ys)
