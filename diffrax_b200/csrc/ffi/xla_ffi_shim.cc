@@ -15,6 +15,8 @@
 //   save_ts   [T] or [1, T] (shared by all trajectories; T may be 0), step_ts / jump_ts likewise
 //   keys      [2] or [N, 2] uint32 key data (zero elements for ODEs)
 //   state_in  [0] or [N, 5 + d];  field_weights [0] or the MLP weights
+//   traj_args [0], or [K] / [N, K]: the vmapped `args` of diffeqsolve (per-trajectory functor parameters; an unbatched [K]
+//             under a batch of N > 1 is the same as passing it through the `params` attribute and is rejected here)
 // Results are caller(XLA)-owned; unused ones (dense_* without SaveAt(dense), state_out without SaveAt(solver_state=...))
 // are declared with zero elements by the Python side.
 //
@@ -38,7 +40,7 @@ ffi::Error EnsembleSolve(cudaStream_t stream,
                          // ---- operands ----
                          ffi::Buffer<DT> y0, ffi::Buffer<DT> t0s, ffi::Buffer<DT> t1s, ffi::Buffer<DT> save_ts,
                          ffi::Buffer<DT> step_ts, ffi::Buffer<DT> jump_ts, ffi::Buffer<ffi::U32> keys,
-                         ffi::Buffer<DT> state_in, ffi::Buffer<DT> field_weights,
+                         ffi::Buffer<DT> state_in, ffi::Buffer<DT> field_weights, ffi::Buffer<DT> traj_args,
                          // ---- results ----
                          ffi::ResultBuffer<DT> ts_out, ffi::ResultBuffer<DT> ys_out, ffi::ResultBuffer<ffi::S32> stats,
                          ffi::ResultBuffer<ffi::S32> result, ffi::ResultBuffer<DT> y_final, ffi::ResultBuffer<DT> t_final,
@@ -71,6 +73,11 @@ ffi::Error EnsembleSolve(cudaStream_t stream,
   if (field_weights.element_count()) { d.field_weights = field_weights.untyped_data(); d.n_field_weights = (int64_t)field_weights.element_count(); }
   d.y0 = y0.untyped_data();
   d.t0 = t0; d.t1 = t1; d.dt0 = dt0;
+  if (traj_args.element_count()) {
+    if (traj_args.element_count() % (size_t)n != 0) return ffi::Error::InvalidArgument("traj_args must be [K] or [N, K] with N = the batch of y0");
+    d.traj_args = traj_args.untyped_data();
+    d.n_traj_args = static_cast<int32_t>(traj_args.element_count() / (size_t)n);
+  }
 
   // per-trajectory integration regions ("vmappable everything, including the region of integration", README.md:10)
   void *scratch = nullptr;
@@ -176,7 +183,7 @@ ffi::Error DenseEvaluate(cudaStream_t stream, ffi::Buffer<DT> dense_ts, ffi::Buf
       .Ctx<ffi::PlatformStream<cudaStream_t>>()                                                                     \
       .Arg<ffi::Buffer<DT>>().Arg<ffi::Buffer<DT>>().Arg<ffi::Buffer<DT>>().Arg<ffi::Buffer<DT>>()                   \
       .Arg<ffi::Buffer<DT>>().Arg<ffi::Buffer<DT>>().Arg<ffi::Buffer<ffi::U32>>().Arg<ffi::Buffer<DT>>()             \
-      .Arg<ffi::Buffer<DT>>()                                                                                       \
+      .Arg<ffi::Buffer<DT>>().Arg<ffi::Buffer<DT>>()                                                                \
       .Ret<ffi::Buffer<DT>>().Ret<ffi::Buffer<DT>>().Ret<ffi::Buffer<ffi::S32>>().Ret<ffi::Buffer<ffi::S32>>()       \
       .Ret<ffi::Buffer<DT>>().Ret<ffi::Buffer<DT>>()                                                                \
       .Ret<ffi::Buffer<DT>>().Ret<ffi::Buffer<DT>>().Ret<ffi::Buffer<DT>>().Ret<ffi::Buffer<DT>>()                   \

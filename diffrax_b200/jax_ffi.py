@@ -52,8 +52,11 @@ def solve_one(y0, *, field_id, params, solver_id, num_stages, t0, t1, dt0, contr
               store_rejected_steps=0, save_t0=False, save_t1=True, save_ts=None, save_steps=0, save_dense=False,
               max_steps=4096, key=None, levy_area=0, bm_shape=(), bm_t0=0.0, bm_t1=1.0, bm_tol=1e-3, state_in=None,
               state_in_flags=0, save_state=False, event_kind=(), event_direction=(), event_params=(), event_root=None,
-              field_weights=None):
+              field_weights=None, args=None):
     """One trajectory: y0 [d].  `t0` / `t1` may be Python floats (static attributes) or traced scalars (operands).
+    `args` [K]: this trajectory's functor parameters (the `args` of the reference's diffeqsolve; under `jax.vmap` the handler
+    receives [N, K]) - for functors compiled with per-trajectory parameters (`fields.CudaField`: pass `field_id=f.field_id_args`
+    after `f.ensure_kernel(..., per_traj=True)`).
     Returns (ts [T], ys [T, d], stats [3], result [], y_final [d], t_final [], dense, state_out)."""
     register()
     y0 = jnp.asarray(y0)
@@ -80,6 +83,7 @@ def solve_one(y0, *, field_id, params, solver_id, num_stages, t0, t1, dt0, contr
         jnp.zeros((0,), jnp.uint32) if key is None else jax.random.key_data(key).astype(jnp.uint32),
         empty if state_in is None else jnp.asarray(state_in, dt),
         empty if field_weights is None else jnp.asarray(field_weights, dt),
+        empty if args is None else jnp.asarray(args, dt),
         field_id=np.int32(field_id), solver_id=np.int32(solver_id), controller=np.int32(controller),
         levy_area=np.int32(levy_area), bm_dim=np.int32(bm_shape[0] if bm_shape else 0),
         t0=float(t0) if static_t else 0.0, t1=float(t1) if static_t else 0.0, dt0=nan if dt0 is None else float(dt0),

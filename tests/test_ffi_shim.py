@@ -69,7 +69,7 @@ def test_jax_binding_module_is_syntactically_valid():
 
 
 def test_python_binding_matches_the_handler_signature():
-    """diffrax_b200/jax_ffi.py passes exactly the attributes the C++ binding declares (same names), nine operands and twelve
+    """diffrax_b200/jax_ffi.py passes exactly the attributes the C++ binding declares (same names), ten operands and twelve
     results for the solve, six operands and one result for the dense evaluation."""
     import re
     src = open(os.path.join(ROOT, "diffrax_b200", "csrc", "ffi", "xla_ffi_shim.cc")).read()
@@ -80,7 +80,7 @@ def test_python_binding_matches_the_handler_signature():
     call = py[py.index("outs = call("):py.index("ts_o, ys_o, stats")]
     kwargs = re.findall(r"\b(\w+)=", call)
     assert attrs and sorted(set(kwargs)) == sorted(attrs), (set(attrs) ^ set(kwargs))
-    assert solve_bind.count(".Arg<") == 9 and solve_bind.count(".Ret<") == 12
+    assert solve_bind.count(".Arg<") == 10 and solve_bind.count(".Ret<") == 12
     out_types = py[py.index("out_types = ("):py.index('name = "DfxEnsembleSolveF64"')]
     assert out_types.count("S(") == 12
     dattrs = re.findall(r'\.Attr<[^>]+>+\("(\w+)"\)', dense_bind)
