@@ -27,7 +27,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
-from typing import Any, Optional, Sequence, Union
+from typing import Any, Optional, Union
 
 import numpy as np
 

@@ -4,7 +4,6 @@ dfx_register_launcher.  GPU: the compiled kernels against the oracle's callback 
 with the same right-hand sides."""
 import math
 import os
-import sys
 
 import numpy as np
 import pytest
@@ -401,7 +400,6 @@ def test_plugin_binds_to_the_loaded_library_instance():
     f = dfx.fields.CudaField(2, "f[0] = y[1]; f[1] = -p[0] * y[0] - 0.125 * y[1];", params=[2.0])
     f.ensure_kernel(2, 4, _lib.F32, 0)                                    # Bosh3, fp32
     assert L.dfx_has_kernel(f.field_id, 2, 4, _lib.F32, 0) == 1
-    from diffrax_b200 import build
     so = [p for p in _lib._plugins if f._hash in p][0]
     needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
     assert "libdiffrax_b200" not in needed
