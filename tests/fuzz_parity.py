@@ -2,7 +2,7 @@
 combinations of field x solver x controller x SaveAt x dtype x direction x per-trajectory t1 x max_steps that no
 hand-written test spells out.  Test infrastructure (imports oracle/): run on a GPU box,
 
-    python tools/fuzz_parity.py --cases 400 --seed 0
+    python tests/fuzz_parity.py --cases 400 --seed 0
 
 Per case: result codes and step statistics must agree on (almost) every trajectory; on the trajectories whose step
 sequences are identical the saved times / states must agree to 1e-9 (fp64) / 2e-4 (fp32).  Exit code 1 on any failure."""

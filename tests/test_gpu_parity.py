@@ -1167,12 +1167,12 @@ def test_state_dependent_diffusion_gbm(dev, solver, dtype):
 
 
 def test_randomised_differential_check_subset(dev):
-    """tools/fuzz_parity.py on 200 random field x solver x controller x SaveAt x dtype x direction x per-trajectory-t1 x
+    """tests/fuzz_parity.py on 200 random field x solver x controller x SaveAt x dtype x direction x per-trajectory-t1 x
     host/device combinations (prebuilt kernels only: DFX_JIT=0 makes the facade refuse the others): no unexplained difference
-    between the CUDA path and the oracle.  The full 2 x 600-case run is profiles/r02_fuzz_parity.txt."""
+    between the CUDA path and the oracle.  The full 4 x 600-case run is profiles/r02_fuzz_parity.txt."""
     import subprocess
     root = os.path.dirname(HERE)
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "--cases", "200", "--seed", "3"],
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_parity.py"), "--cases", "200", "--seed", "3"],
                        env=dict(os.environ, DFX_JIT="0"), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and " 0 failures" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
 
