@@ -353,3 +353,18 @@ def test_getting_started_ode_printout():
                          atol=1e-5, save_ts=np.array([0.0, 1.0, 2.0, 3.0]), save_t1=False)
         assert np.array_equal(r["ts"][0], [0.0, 1.0, 2.0, 3.0])
         assert [f"{v:.3g}" for v in r["ys"][0, :, 0]] == ["1", "0.368", "0.135", "0.0498"]
+
+
+def test_wide_state_callback_against_scipy_dop853():
+    """The oracle at a wide state (Lorenz-96, 40 components - what the warp-per-trajectory kernel is checked against,
+    tests/test_user_field.py) agrees with scipy's independent DOP853 at tight tolerance (the test_detest.py:451-459 recipe)."""
+    from scipy.integrate import solve_ivp
+    D, F = 40, 8.0
+    f = lambda t, y: (np.roll(y, -1) - np.roll(y, 2)) * np.roll(y, 1) - y + F      # noqa: E731
+    rng = np.random.default_rng(40)
+    y0 = F + rng.normal(0, 0.5, (3, D))
+    r = oracle.solve("callback", y0, 0.0, 0.5, 0.01, solver="dopri8", rtol=1e-11, atol=1e-11, max_steps=100000, callback=f)
+    assert np.all(r["result"] == 0)
+    for i in range(3):
+        s = solve_ivp(f, (0.0, 0.5), y0[i], method="DOP853", rtol=1e-12, atol=1e-12)
+        assert np.abs(r["ys"][i, 0] - s.y[:, -1]).max() < 1e-8 * np.abs(s.y[:, -1]).max()
