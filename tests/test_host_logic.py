@@ -185,3 +185,31 @@ def test_sharded_solve_record_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_subsaveat_union_assembly():
+    """SaveAt(subs=...): the rows of a leaf are cut out of the ONE solve over the union of the leaves' ts (`_MultiSolve`): t0 first,
+    then the leaf's ts (inf where the trajectory stopped before them), and the final value right after the ts it reached."""
+    import types
+    from diffrax_b200._api import _MultiSolve, save_y
+    inf = np.inf
+    # union solve: t0 column + ts {1, 2, 3, 4}; trajectory 0 ran to the end (t = 5), trajectory 1 stopped at t = 2.5
+    ts_u = np.array([[0.0, 1.0, 2.0, 3.0, 4.0], [0.0, 1.0, 2.0, inf, inf]])
+    ys_u = np.where(np.isfinite(ts_u), ts_u * 10.0, inf)[..., None] * np.ones(2)
+    u = types.SimpleNamespace(ts=ts_u, ys=ys_u, t_final=np.array([5.0, 2.5]), y_final=np.array([[50.0, 50.0], [25.0, 25.0]]))
+    ts, ys = _MultiSolve._from_union(u, (True, True, [2, 4], save_y))           # leaf: t0, ts = {2, 4}, t1
+    assert np.array_equal(ts, [[0.0, 2.0, 4.0, 5.0], [0.0, 2.0, 2.5, inf]])
+    assert np.array_equal(ys[..., 0], [[0.0, 20.0, 40.0, 50.0], [0.0, 20.0, 25.0, inf]])
+    ts, ys = _MultiSolve._from_union(u, (False, True, [], save_y))              # leaf: t1 only
+    assert np.array_equal(ts, [[5.0], [2.5]]) and np.array_equal(ys[:, 0, 0], [50.0, 25.0])
+    ts, ys = _MultiSolve._from_union(u, (False, False, [3], lambda t, y, args: y.sum(-1)))   # leaf: ts = {3}, fn
+    assert np.array_equal(ts, [[3.0], [inf]]) and np.array_equal(ys, [[60.0], [inf]])
+    # the planner: leaves without steps share a solve, a leaf with steps keeps its own; union columns follow the direction
+    subs = [dfx.SubSaveAt(t1=True), dfx.SubSaveAt(t0=True, ts=[2.0, 1.0]), dfx.SubSaveAt(steps=True), dfx.SubSaveAt(ts=[2.5, 1.0])]
+    p = dfx.prepare(TERM, dfx.Dopri5(), 3.0, 0.0, None, Y0, saveat=dfx.SaveAt(subs=subs), stepsize_controller=PID, max_steps=64)
+    assert [k for k, _ in p.providers] == ["union", "union", "own", "union"]
+    assert p.union.desc.n_save_ts == 3 and p.union.desc.save_t0 == 1 and p.union.desc.save_t1 == 0     # {2.5, 2, 1} backwards
+    assert p.providers[1][1][2] == [2, 3] and p.providers[3][1][2] == [1, 3]
+    with pytest.raises(RuntimeError, match="increasing or decreasing"):
+        dfx.prepare(TERM, dfx.Dopri5(), 0.0, 3.0, None, Y0, saveat=dfx.SaveAt(subs=[dfx.SubSaveAt(ts=[1.0, 0.5, 2.0]), dfx.SubSaveAt(t1=True)]),
+                    stepsize_controller=PID)
