@@ -16,9 +16,11 @@ y0 = torch.tensor(np.stack([rng.uniform(-15, 15, n), rng.uniform(-20, 20, n), rn
 ctrl = dfx.PIDController(rtol=1e-8, atol=1e-8)
 fields = {"built-in Lorenz": dfx.fields.Lorenz(), "CudaField (heuristic occupancy)": dfx.fields.CudaField(3, SRC, params=[10.0, 28.0, 8.0 / 3.0]),
           "CudaField(min_blocks_per_sm=6)": dfx.fields.CudaField(3, SRC, params=[10.0, 28.0, 8.0 / 3.0], min_blocks_per_sm=6)}
+fields["CudaField(min_blocks_per_sm=6) + per-trajectory args [N, 3]"] = fields["CudaField(min_blocks_per_sm=6)"]
+args = torch.tensor(np.tile([10.0, 28.0, 8.0 / 3.0], (n, 1)), device="cuda")
 ref = None
 for name, f in fields.items():
-    plan = dfx.prepare(dfx.ODETerm(f), dfx.Dopri5(), 0.0, 2.0, None, y0, stepsize_controller=ctrl)
+    plan = dfx.prepare(dfx.ODETerm(f), dfx.Dopri5(), 0.0, 2.0, None, y0, args if "args" in name else None, stepsize_controller=ctrl)
     for _ in range(3):
         sol = plan(throw=False)
     torch.cuda.synchronize()
@@ -29,4 +31,4 @@ for name, f in fields.items():
     e1.record(); torch.cuda.synchronize()
     ys = sol.ys.clone()
     ref = ys if ref is None else ref
-    print(f"{name:34s} {e0.elapsed_time(e1) / 20:.3f} ms per solve of 2^20 trajectories; bit-identical to the built-in: {bool(torch.equal(ys, ref))}")
+    print(f"{name:62s} {e0.elapsed_time(e1) / 20:.3f} ms per solve of 2^20 trajectories; bit-identical to the built-in: {bool(torch.equal(ys, ref))}")
