@@ -77,7 +77,7 @@ def test_pipelined_host_entry_fails_loudly_without_a_gpu():
 
 def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing in the package, the headers, the baseline arm's helpers or tools/ touches it
-    (the check scripts that do - fuzz_parity.py, gpu_quickcheck.py - live under tests/)."""
+    (the check script that does - fuzz_parity.py - lives under tests/)."""
     import re
     paths = []
     for top in ("diffrax_b200", "include", "tools"):
