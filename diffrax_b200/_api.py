@@ -877,6 +877,14 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     rdt = y0a.dtype
     if field.dim not in (0, d):
         raise ValueError(f"{type(field).__name__} has state dimension {field.dim}, got y0 with d={d}")
+    if args is not None and getattr(field, "ensure_kernel", None) is None:
+        # per-trajectory parameters on a built-in functor: run its generated twin (same statements, same bits), whose parameters
+        # are a plain array that the per-trajectory kernel variant reloads for every trajectory
+        twin = field.cuda_twin(d)
+        if twin is None:
+            raise ValueError(f"args: {type(field).__name__} has no per-trajectory-parameter kernel (its parameters are bound when it is "
+                             "created); a `fields.CudaField` takes `args` of shape [N, len(params)]")
+        field = twin
 
     L = _lib.lib()
     D = _lib.new_desc()
@@ -987,9 +995,6 @@ def prepare(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = None,
     ensure = getattr(field, "ensure_kernel", None)
     if args is not None:
         # vmapped `args` (_integrate.py:896): per-trajectory functor parameters [N, n_params] - a parameter sweep over the ensemble
-        if ensure is None:
-            raise ValueError("args: the parameters of a built-in functor are bound when it is created (one set for the ensemble); a "
-                             "`fields.CudaField` takes per-trajectory parameters as `args` of shape [N, len(params)]")
         aa = xp.asarray(args if is_torch else np.asarray(args), rdt)
         if aa.ndim != 2 or int(aa.shape[0]) != n or int(aa.shape[1]) != len(field.params()):
             raise ValueError(f"args must have shape [N, n_params] = [{n}, {len(field.params())}], got {tuple(aa.shape)}")

@@ -41,6 +41,12 @@ class Field:
     def weights(self, xp, dtype):
         return None
 
+    def cuda_twin(self, dim):
+        """This functor written as a `CudaField` (the same statements as csrc/fields.cuh, so the same bits), or None.  It is what
+        `diffeqsolve(..., args=[N, n_params])` runs on a built-in functor: the per-trajectory-parameter kernel variant exists for
+        generated functors (their parameters are a plain array `p[]`)."""
+        return None
+
     def cpp_functor(self, dim, bm_dim):
         """The csrc/fields.cuh functor type for a state of dimension `dim` driven by a Brownian motion of shape `(bm_dim,)`
         (0: shape () or none); None when there is none.  Used to instantiate (field, solver, dtype) combinations that are not
@@ -59,6 +65,9 @@ class LinearDecay(Field):
     def params(self):
         return [self.lam]
 
+    def cuda_twin(self, dim):
+        return CudaField(dim, " ".join(f"f[{i}] = -p[0] * y[{i}];" for i in range(dim)), params=self.params())
+
     def cpp_functor(self, dim, bm_dim):
         return f"::dfx::DecayField<{dim}>"
 
@@ -72,6 +81,10 @@ class LotkaVolterra(Field):
 
     def params(self):
         return self.p
+
+    def cuda_twin(self, dim):
+        return CudaField(2, "const R x = y[0], yy = y[1]; f[0] = p[0] * x + (p[1] * x) * yy; f[1] = p[2] * yy + (p[3] * x) * yy;",
+                         params=self.params())
 
     def cpp_functor(self, dim, bm_dim):
         return "::dfx::LotkaVolterraField"
@@ -87,6 +100,10 @@ class Lorenz(Field):
     def params(self):
         return self.p
 
+    def cuda_twin(self, dim):
+        return CudaField(3, "f[0] = p[0] * (y[1] - y[0]); f[1] = y[0] * (p[1] - y[2]) - y[1]; f[2] = y[0] * y[1] - p[2] * y[2];",
+                         params=self.params(), min_blocks_per_sm=6)
+
     def cpp_functor(self, dim, bm_dim):
         return "::dfx::LorenzField"
 
@@ -100,6 +117,13 @@ class CR3BP(Field):
 
     def params(self):
         return [self.mu]
+
+    def cuda_twin(self, dim):
+        return CudaField(4, "const R mu = p[0], mup = (R)1 - p[0]; const R x = y[0], yy = y[1], vx = y[2], vy = y[3]; "
+                            "const R dx1 = x + mu, dx2 = x - mup; const R r1s = dx1 * dx1 + yy * yy, r2s = dx2 * dx2 + yy * yy; "
+                            "const R w1 = mup / (r1s * ::dfx::r_sqrt(r1s)), w2 = mu / (r2s * ::dfx::r_sqrt(r2s)); "
+                            "f[0] = vx; f[1] = vy; f[2] = x + R(2) * vy - w1 * dx1 - w2 * dx2; f[3] = yy - R(2) * vx - (w1 + w2) * yy;",
+                         params=self.params())
 
     def cpp_functor(self, dim, bm_dim):
         return "::dfx::Cr3bpField"
@@ -115,6 +139,9 @@ class ForcedOscillator(Field):
     def params(self):
         return self.p
 
+    def cuda_twin(self, dim):
+        return CudaField(2, "f[0] = y[1]; f[1] = -p[0] * y[0] + p[1] * ::dfx::r_sin(p[2] * t);", params=self.params())
+
     def cpp_functor(self, dim, bm_dim):
         return "::dfx::ForcedOscField"
 
@@ -127,6 +154,9 @@ class VanDerPol(Field):
 
     def params(self):
         return [self.mu]
+
+    def cuda_twin(self, dim):
+        return CudaField(2, "f[0] = y[1]; f[1] = p[0] * (R(1) - y[0] * y[0]) * y[1] - y[0];", params=self.params())
 
     def cpp_functor(self, dim, bm_dim):
         return "::dfx::VdpField"
@@ -142,6 +172,10 @@ class OrnsteinUhlenbeck(Field):
 
     def params(self):
         return self.p
+
+    def cuda_twin(self, dim):
+        p4 = (self.p + [0.0])[:4]      # [theta, mu, sigma, sigma_t]
+        return CudaField(dim, " ".join(f"f[{i}] = p[0] * (p[1] - y[{i}]);" for i in range(dim)), params=p4, diffusion="p[2] + p[3] * t")
 
     def cpp_functor(self, dim, bm_dim):
         return "::dfx::OuField" if dim == 1 else f"::dfx::OuDiagField<{dim}>"

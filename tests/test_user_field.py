@@ -437,8 +437,12 @@ def test_per_trajectory_args_source_and_checks():
     assert _lib.lib().dfx_has_kernel(lor.field_id_args, 3, 1, _lib.F64, 0) == 1
     with pytest.raises(ValueError, match=r"\[N, n_params\]"):
         dfx.prepare(dfx.ODETerm(lor), dfx.Dopri5(), 0.0, 1.0, None, np.ones((5, 3)), args[:, :2], stepsize_controller=dfx.PIDController(1e-6, 1e-6))
-    with pytest.raises(ValueError, match="built-in functor"):
-        dfx.prepare(dfx.ODETerm(dfx.fields.Lorenz()), dfx.Dopri5(), 0.0, 1.0, None, np.ones((5, 3)), args, stepsize_controller=dfx.PIDController(1e-6, 1e-6))
+    # a built-in functor runs its generated twin under `args`
+    q = dfx.prepare(dfx.ODETerm(dfx.fields.Lorenz()), dfx.Dopri5(), 0.0, 1.0, None, np.ones((5, 3)), args, stepsize_controller=dfx.PIDController(1e-6, 1e-6))
+    assert q.desc.field_id >= _lib.FIELD_USER and q.desc.n_traj_args == 3
+    with pytest.raises(ValueError, match="no per-trajectory-parameter kernel"):
+        dfx.prepare(dfx.ODETerm(dfx.fields.MLP.init(1)), dfx.Tsit5(), 0.0, 1.0, None, np.ones((5, 4), np.float32), np.ones((5, 2), np.float32),
+                    stepsize_controller=dfx.PIDController(1e-3, 1e-6))
 
 
 @pytest.mark.gpu
@@ -476,3 +480,42 @@ def test_per_trajectory_args_parameter_sweep(dev):
         m = torch.tensor(F == val, device=dev)
         b = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.CudaField(D, L96, params=[val], wide=True)), dfx.Tsit5(), 0.0, 0.5, None, yw[m], stepsize_controller=ctrl)
         assert torch.equal(a.ys[m], b.ys)
+
+
+@pytest.mark.gpu
+def test_builtin_functors_take_per_trajectory_args(dev):
+    """`args` on a built-in functor runs its generated twin: with every row equal to the functor's own parameters the result is,
+    bit for bit, the built-in kernel's (so the twins ARE the functors of csrc/fields.cuh); with a real sweep, each row's own."""
+    rng = np.random.default_rng(21)
+    n = 500
+    ctrl = dfx.PIDController(rtol=1e-7, atol=1e-9)
+    cases = [(dfx.fields.LinearDecay(0.7), 3, 0.0), (dfx.fields.LotkaVolterra(), 2, 0.0), (dfx.fields.Lorenz(), 3, 0.0),
+             (dfx.fields.CR3BP(), 4, 0.0), (dfx.fields.ForcedOscillator(1.0, 0.7, 2.0), 2, 0.0), (dfx.fields.VanDerPol(1.5), 2, 0.0)]
+    for f, d, _ in cases:
+        y0 = torch.tensor(rng.uniform(0.5, 1.5, (n, d)), device=dev)
+        if isinstance(f, dfx.fields.CR3BP):
+            y0 = torch.tensor(np.array([0.994, 0.0, 0.0, -2.00158510637908252]) + 1e-3 * rng.standard_normal((n, 4)), device=dev)
+        same = torch.tensor(np.tile(f.params(), (n, 1)), device=dev)
+        a = dfx.diffeqsolve(dfx.ODETerm(f), dfx.Tsit5(), 0.0, 1.0, None, y0, same, stepsize_controller=ctrl, throw=False)
+        b = dfx.diffeqsolve(dfx.ODETerm(f), dfx.Tsit5(), 0.0, 1.0, None, y0, stepsize_controller=ctrl, throw=False)
+        assert torch.equal(a.ys, b.ys) and torch.equal(a.stats["num_steps"], b.stats["num_steps"]), type(f).__name__
+        assert torch.equal(a.result, b.result) and int((b.result == 0).sum()) > n // 2
+    # a sweep over the van der Pol stiffness: row i is the solve with mu_i
+    mus = np.where(np.arange(n) % 2 == 0, 0.5, 3.0)
+    y0 = torch.tensor(rng.uniform(0.5, 1.5, (n, 2)), device=dev)
+    sw = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.VanDerPol()), dfx.Tsit5(), 0.0, 2.0, None, y0, torch.tensor(mus[:, None], device=dev), stepsize_controller=ctrl,
+                         throw=False)
+    for mu in (0.5, 3.0):
+        m = torch.tensor(mus == mu, device=dev)
+        one = dfx.diffeqsolve(dfx.ODETerm(dfx.fields.VanDerPol(mu)), dfx.Tsit5(), 0.0, 2.0, None, y0[m], stepsize_controller=ctrl, throw=False)
+        assert torch.equal(sw.ys[m], one.ys)
+    # SDE: OU with a per-path mean, fixed steps
+    keys = dfx.random.split(dfx.random.key(5), n)
+    ou = dfx.fields.OrnsteinUhlenbeck(1.0, 0.0, 0.5)
+    mk = lambda f: dfx.MultiTerm(dfx.ODETerm(f.drift), dfx.ControlTerm(f.diffusion, dfx.VirtualBrownianTree(0.0, 1.0, 2.0 ** -8, (), keys)))  # noqa: E731
+    y1 = torch.ones(n, 1, device=dev, dtype=torch.float64)
+    pa = np.tile([1.0, 0.0, 0.5, 0.0], (n, 1)); pa[:, 1] = np.where(np.arange(n) % 2 == 0, 0.0, 2.0)
+    sw = dfx.diffeqsolve(mk(ou), dfx.Heun(), 0.0, 1.0, 2.0 ** -6, y1, torch.tensor(pa, device=dev))
+    base = dfx.diffeqsolve(mk(ou), dfx.Heun(), 0.0, 1.0, 2.0 ** -6, y1)
+    even = torch.arange(n, device=dev) % 2 == 0
+    assert torch.equal(sw.ys[even], base.ys[even]) and not torch.equal(sw.ys[~even], base.ys[~even])
